@@ -1,0 +1,147 @@
+"""ctypes binding of the C-ABI in ``include/hulc2_b200.h``.
+
+The library is loaded lazily on the first op call.  There is NO fallback: a missing
+``libhulc2_b200.so`` or a missing CUDA device raises ``RuntimeError`` (the product path must
+fail loudly when the CUDA extension is absent).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhulc2_b200.so")
+
+c_float_p = C.c_void_p  # device pointers travel as integers
+LL = C.c_longlong
+I = C.c_int
+F = C.c_float
+P = C.c_void_p
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("M", I), ("N", I), ("K", I),
+        ("A", P), ("a_rs", LL), ("a_ks", LL), ("a_inner", I), ("a_rs_outer", LL), ("a_rs_inner", LL),
+        ("B", P), ("b_rs", LL), ("b_ks", LL),
+        ("C", P), ("ldc", LL), ("c_inner", I), ("c_rs_outer", LL), ("c_rs_inner", LL),
+        ("bias", P),
+        ("add", P), ("ld_add", LL),
+        ("mask", P), ("ld_mask", LL),
+        ("keep", P), ("ld_keep", LL), ("keep_scale", F),
+        ("relu", I), ("accumulate", I),
+        ("alpha", F),
+        ("precision", I),
+        ("workspace", P), ("workspace_bytes", LL),
+    ]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("F", I), ("C", I), ("H", I), ("W", I), ("Cout", I), ("KH", I), ("KW", I), ("stride", I), ("in_nhwc", I),
+        ("x", P), ("w", P), ("bias", P), ("y", P), ("relu", I),
+        ("dy", P), ("dw", P), ("dx", P), ("xmask", P), ("accumulate", I),
+        ("precision", I),
+        ("workspace", P), ("workspace_bytes", LL),
+    ]
+
+
+# name -> argtypes (without the trailing stream); every function returns int and takes a stream last
+_SIGS = {
+    "hulc2_gemm": [C.POINTER(GemmArgs)],
+    "hulc2_conv2d_fwd": [C.POINTER(ConvArgs)],
+    "hulc2_conv2d_wgrad": [C.POINTER(ConvArgs)],
+    "hulc2_conv2d_dgrad": [C.POINTER(ConvArgs)],
+    "hulc2_permute_conv_weight": [P, P, I, I, I, I, I, I],
+    "hulc2_copy2d": [P, LL, P, LL, LL, I, I],
+    "hulc2_transpose01": [P, LL, P, LL, I, I, I, I],
+    "hulc2_fill": [P, LL, F],
+    "hulc2_axpy": [P, P, LL, F],
+    "hulc2_colsum": [P, LL, LL, I, P, I, P, LL],
+    "hulc2_relu_mask": [P, P, P, LL],
+    "hulc2_nhwc_to_nchw": [P, P, I, I, I],
+    "hulc2_nchw_to_nhwc": [P, P, I, I, I, P],
+    "hulc2_spatial_softmax_fwd": [P, P, P, P, P, I, I, I],
+    "hulc2_spatial_softmax_bwd": [P, P, P, P, P, P, P, P, I, I, I, I],
+    "hulc2_layernorm_fwd": [P, LL, P, LL, P, F, P, P, P, LL, P, P, P, LL, I, F],
+    "hulc2_layernorm_bwd": [P, LL, P, LL, P, P, P, P, LL, P, P, F, P, P, LL, I],
+    "hulc2_add_pos_fwd": [P, P, P, F, P, I, I, I],
+    "hulc2_add_pos_bwd": [P, P, F, P, P, I, I, I],
+    "hulc2_attention_fwd": [P, P, F, P, P, I, I, I, I],
+    "hulc2_attention_bwd": [P, P, P, F, P, P, I, I, I, I],
+    "hulc2_mean_seq_fwd": [P, P, I, I, I],
+    "hulc2_mean_seq_bwd": [P, P, I, I, I],
+    "hulc2_kl_fwd": [P, P, P, I, I, I, F, F],
+    "hulc2_kl_bwd": [P, P, P, P, P, I, I, I, F, F],
+    "hulc2_onehot_fwd": [P, P, I, I, I],
+    "hulc2_st_onehot_bwd": [P, P, P, I, I, I],
+    "hulc2_categorical_sample": [P, P, P, I, I, I],
+    "hulc2_logistic_loss_fwd": [P, LL, P, P, P, P, I, I, I, I, I, F, F, I, P, LL],
+    "hulc2_logistic_loss_bwd": [P, LL, P, P, P, P, P, I, I, I, I, I, F, F, I],
+    "hulc2_logistic_sample": [P, LL, P, P, P, P, I, I, I, I, F, I],
+    "hulc2_heads_unpack": [P, LL, P, P, P, P, I, I, I, I, F, I],
+    "hulc2_world_to_tcp": [P, P, I, P, LL],
+    "hulc2_tcp_to_world": [P, P, I, P, LL],
+    "hulc2_infonce_fwd": [P, P, P, P, P, I, I, P, LL],
+    "hulc2_infonce_bwd": [P, P, P, P, P, P, P, P, I, I, P, LL],
+    "hulc2_rnn_relu_fwd": [P, P, P, P, I, I, I, I],
+    "hulc2_rnn_relu_bwd": [P, P, P, P, I, I, I, I],
+    "hulc2_adam_step": [P, P, P, P, LL, F, F, F, F, F, I, F],
+    "hulc2_philox_uniform": [P, LL, C.c_ulonglong, C.c_ulonglong],
+    "hulc2_dropout_mask": [P, LL, F, C.c_ulonglong, C.c_ulonglong],
+}
+_NO_STREAM = {"hulc2_last_error": (C.c_char_p, []), "hulc2_version": (I, []), "hulc2_device_supports_tcgen05": (I, [])}
+
+EXPORTED_SYMBOLS = sorted(list(_SIGS) + list(_NO_STREAM))
+
+_lib: Optional[C.CDLL] = None
+launch_count = 0  # number of C-ABI compute calls issued (bench.py reports it as gpu_launches evidence)
+
+
+def load_library(require_cuda: bool = True) -> C.CDLL:
+    """Loads libhulc2_b200.so and declares prototypes.  ``require_cuda=False`` is for the CPU-side
+    symbol-export test only; compute entry points still need a device."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"hulc2_b200: CUDA library not found at {LIB_PATH}. Build it with `python -m hulc2_b200.build` "
+                "(there is no CPU or PyTorch fallback)."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, args in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = I
+            fn.argtypes = list(args) + [P]
+        for name, (res, args) in _NO_STREAM.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    if require_cuda and not torch.cuda.is_available():
+        raise RuntimeError("hulc2_b200: no CUDA device available; this package has no CPU fallback")
+    return _lib
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args) -> None:
+    """Invoke a C-ABI entry point on torch's current stream; raise RuntimeError on failure."""
+    global launch_count
+    lib = load_library()
+    rc = getattr(lib, name)(*args, stream())
+    launch_count += 1
+    if rc != 0:
+        msg = lib.hulc2_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{name} failed with code {rc}: {msg}")

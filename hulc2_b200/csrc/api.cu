@@ -1,0 +1,114 @@
+// extern "C" entry points that dispatch between the fp32 CUDA-core path and the bf16 tcgen05 path,
+// plus the host-side step loops of the decoder recurrence.
+#include <string.h>
+
+#include "common.cuh"
+#include "../../include/hulc2_b200.h"
+
+int hulc2_gemm_f32_impl(const hulc2_gemm_args* a, cudaStream_t st);
+int hulc2_conv2d_fwd_f32_impl(const hulc2_conv_args* a, cudaStream_t st);
+int hulc2_conv2d_wgrad_f32_impl(const hulc2_conv_args* a, cudaStream_t st);
+int hulc2_conv2d_dgrad_f32_impl(const hulc2_conv_args* a, cudaStream_t st);
+int hulc2_gemm_bf16_impl(const hulc2_gemm_args* a, cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+void hulc2_set_error(const char* msg) {
+  strncpy(g_err, msg ? msg : "", sizeof(g_err) - 1);
+  g_err[sizeof(g_err) - 1] = 0;
+}
+
+extern "C" {
+
+const char* hulc2_last_error(void) { return g_err; }
+int hulc2_version(void) { return 100; }
+
+int hulc2_device_supports_tcgen05(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+  return p.major == 10 ? 1 : 0;
+}
+
+int hulc2_gemm(const hulc2_gemm_args* a, cudaStream_t st) {
+  if (!a) { hulc2_set_error("gemm: null args"); return HULC2_EINVAL; }
+  if (a->precision == 0) return hulc2_gemm_f32_impl(a, st);
+  if (a->precision == 1) return hulc2_gemm_bf16_impl(a, st);
+  hulc2_set_error("gemm: unknown precision");
+  return HULC2_EINVAL;
+}
+
+static int check_conv(const hulc2_conv_args* a) {
+  if (!a || a->F < 0 || a->C <= 0 || a->Cout <= 0 || a->KH <= 0 || a->KW <= 0 || a->stride <= 0 || a->H < a->KH || a->W < a->KW) {
+    hulc2_set_error("conv2d: bad geometry");
+    return HULC2_EINVAL;
+  }
+  return HULC2_OK;
+}
+int hulc2_conv2d_fwd(const hulc2_conv_args* a, cudaStream_t st) {
+  if (int e = check_conv(a)) return e;
+  if (a->precision == 0) return hulc2_conv2d_fwd_f32_impl(a, st);
+  hulc2_set_error("conv2d_fwd: precision not implemented");
+  return HULC2_ENOTIMPL;
+}
+int hulc2_conv2d_wgrad(const hulc2_conv_args* a, cudaStream_t st) {
+  if (int e = check_conv(a)) return e;
+  if (a->precision == 0) return hulc2_conv2d_wgrad_f32_impl(a, st);
+  hulc2_set_error("conv2d_wgrad: precision not implemented");
+  return HULC2_ENOTIMPL;
+}
+int hulc2_conv2d_dgrad(const hulc2_conv_args* a, cudaStream_t st) {
+  if (int e = check_conv(a)) return e;
+  if (a->precision == 0) return hulc2_conv2d_dgrad_f32_impl(a, st);
+  hulc2_set_error("conv2d_dgrad: precision not implemented");
+  return HULC2_ENOTIMPL;
+}
+
+// h[t] = relu(pre[t] + h[t-1] W_hh^T)      (nn.RNN, nonlinearity=relu; decoders/utils/rnn.py:5-14)
+int hulc2_rnn_relu_fwd(const float* pre, const float* w_hh, const float* h0, float* h, int S, int B, int H, int precision,
+                       cudaStream_t st) {
+  if (S <= 0 || B <= 0) return HULC2_OK;
+  const long long step = (long long)B * H;
+  for (int t = 0; t < S; ++t) {
+    hulc2_gemm_args g;
+    memset(&g, 0, sizeof(g));
+    const float* prev = (t == 0) ? h0 : h + (t - 1) * step;
+    g.M = B; g.N = H; g.K = prev ? H : 0;
+    g.A = prev ? prev : w_hh; g.a_rs = H; g.a_ks = 1;
+    g.B = w_hh; g.b_rs = H; g.b_ks = 1;
+    g.C = h + t * step; g.ldc = H;
+    g.add = pre + t * step; g.ld_add = H;
+    g.relu = 1; g.alpha = 1.f; g.keep_scale = 1.f;
+    g.precision = precision;
+    if (int e = hulc2_gemm(&g, st)) return e;
+  }
+  return HULC2_OK;
+}
+
+// in place: dh[t] <- dz[t] = (dh[t] + dz[t+1] W_hh) * (h[t] > 0); optional dh0 = dz[0] W_hh
+int hulc2_rnn_relu_bwd(float* dh, const float* w_hh, const float* h, float* dh0, int S, int B, int H, int precision,
+                       cudaStream_t st) {
+  if (S <= 0 || B <= 0) return HULC2_OK;
+  const long long step = (long long)B * H;
+  if (int e = hulc2_relu_mask(dh + (S - 1) * step, h + (S - 1) * step, dh + (S - 1) * step, step, st)) return e;
+  for (int t = S - 2; t >= -1; --t) {
+    if (t < 0 && !dh0) break;
+    hulc2_gemm_args g;
+    memset(&g, 0, sizeof(g));
+    g.M = B; g.N = H; g.K = H;
+    g.A = dh + (t + 1) * step; g.a_rs = H; g.a_ks = 1;
+    g.B = w_hh; g.b_rs = 1; g.b_ks = H;                 // B(n=i, k=j) = W_hh[j, i]
+    g.alpha = 1.f; g.keep_scale = 1.f; g.precision = precision;
+    if (t >= 0) {
+      g.C = dh + t * step; g.ldc = H;
+      g.add = dh + t * step; g.ld_add = H;
+      g.mask = h + t * step; g.ld_mask = H;
+    } else {
+      g.C = dh0; g.ldc = H;
+    }
+    if (int e = hulc2_gemm(&g, st)) return e;
+  }
+  return HULC2_OK;
+}
+
+}  // extern "C"

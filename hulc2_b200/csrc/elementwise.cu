@@ -1,0 +1,286 @@
+// Memory-bound utility kernels: strided copies, column sums (bias gradients), layout shuffles,
+// Philox noise, fused Adam.  All are grid-stride, coalesced, sized in multiples of the SM count.
+#include "common.cuh"
+#include "../../include/hulc2_b200.h"
+
+namespace {
+
+constexpr int kSMs = 148;
+
+inline int grid_for(long long n, int block, int per_sm = 8) {
+  long long want = (n + block - 1) / block;
+  long long cap = (long long)kSMs * per_sm;
+  return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+__global__ void copy2d_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
+                              long long rows, int cols, int accumulate) {
+  long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / cols;
+    int c = (int)(i - r * cols);
+    float v = src[r * lds + c];
+    float* d = dst + r * ldd + c;
+    *d = accumulate ? (*d + v) : v;
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ dst, long long n, float value) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = value;
+}
+
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float a) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += a * x[i];
+}
+
+__global__ void relu_mask_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dz[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
+// stage 1: block (32 cols x 8 row-lanes) sums its row slab; partial[slab][cols]
+__global__ void colsum_partial_kernel(const float* __restrict__ x, long long ld, long long rows, int cols,
+                                      float* __restrict__ partial, long long rows_per_slab) {
+  __shared__ float red[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  long long r0 = (long long)blockIdx.y * rows_per_slab;
+  long long r1 = r0 + rows_per_slab < rows ? r0 + rows_per_slab : rows;
+  float s = 0.f;
+  if (c < cols)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) s += x[r * ld + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+    partial[(long long)blockIdx.y * cols + c] = t;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int slabs, int cols, float* __restrict__ out, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int j = 0; j < slabs; ++j) s += partial[(long long)j * cols + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+// per-frame [HW, C] <-> [C, HW] transposes through a padded shared tile
+__global__ void transpose_frames_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols,
+                                        const float* __restrict__ mask) {
+  // src frame is [rows, cols] row-major, dst frame is [cols, rows]; mask (optional) has dst layout
+  __shared__ float tile[32][33];
+  long long fbase = (long long)blockIdx.z * rows * cols;
+  int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? src[fbase + (long long)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) {
+      long long o = fbase + (long long)c * rows + r;
+      float v = tile[threadIdx.x][j];
+      if (mask) v = mask[o] > 0.f ? v : 0.f;
+      dst[o] = v;
+    }
+  }
+}
+
+// dst[d1, d0, :D2] (+)= src[(d0*D1 + d1)*src_ld + :D2]   (batch-major <-> time-major row shuffles)
+__global__ void transpose01_kernel(const float* __restrict__ src, long long src_ld, float* __restrict__ dst, long long dst_ld,
+                                   int D0, int D1, int D2, int accumulate) {
+  long long total = (long long)D0 * D1 * D2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % D2);
+    long long r = i / D2;          // r = d1*D0 + d0 (destination row)
+    int d0 = (int)(r % D0), d1 = (int)(r / D0);
+    float v = src[((long long)d0 * D1 + d1) * src_ld + c];
+    float* d = dst + r * dst_ld + c;
+    *d = accumulate ? (*d + v) : v;
+  }
+}
+
+__global__ void permute_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int KH, int KW,
+                                      int dir, int accumulate) {
+  int total = O * I * KH * KW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    // i indexes OIHW
+    int kw = i % KW, t = i / KW;
+    int kh = t % KH; t /= KH;
+    int ci = t % I, o = t / I;
+    int ohwi = ((o * KH + kh) * KW + kw) * I + ci;
+    int hwoi = ((kh * KW + kw) * O + o) * I + ci;
+    if (dir == 0) dst[ohwi] = src[i];
+    else if (dir == 1) dst[i] = accumulate ? dst[i] + src[ohwi] : src[ohwi];
+    else dst[hwoi] = src[i];
+  }
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ void philox4(uint64_t seed, uint64_t ctr, uint32_t (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+__global__ void philox_uniform_kernel(float* __restrict__ out, long long n, uint64_t seed, uint64_t offset) {
+  long long nq = (n + 3) / 4;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+    uint32_t r[4];
+    philox4(seed, offset + (uint64_t)q, r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      long long i = q * 4 + j;
+      if (i < n) out[i] = u01(r[j]);
+    }
+  }
+}
+__global__ void dropout_mask_kernel(unsigned char* __restrict__ out, long long n, float p, uint64_t seed, uint64_t offset) {
+  long long nq = (n + 3) / 4;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+    uint32_t r[4];
+    philox4(seed, offset + (uint64_t)q, r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      long long i = q * 4 + j;
+      if (i < n) out[i] = u01(r[j]) >= p ? 1 : 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- Adam (torch.optim.Adam, amsgrad=False, maximize=False)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                            float grad_scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    float mi = m[i] + (1.f - b1) * (gi - m[i]);          // exp_avg.lerp_(grad, 1-beta1)
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+    m[i] = mi; v[i] = vi;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int hulc2_copy2d(const float* src, long long lds, float* dst, long long ldd, long long rows, int cols, int accumulate,
+                 cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return HULC2_OK;
+  copy2d_kernel<<<grid_for(rows * cols, 256), 256, 0, st>>>(src, lds, dst, ldd, rows, cols, accumulate);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_fill(float* dst, long long n, float value, cudaStream_t st) {
+  if (n <= 0) return HULC2_OK;
+  fill_kernel<<<grid_for(n, 256), 256, 0, st>>>(dst, n, value);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_axpy(const float* x, float* y, long long n, float a, cudaStream_t st) {
+  if (n <= 0) return HULC2_OK;
+  axpy_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, y, n, a);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_relu_mask(const float* dy, const float* y, float* dz, long long n, cudaStream_t st) {
+  if (n <= 0) return HULC2_OK;
+  relu_mask_kernel<<<grid_for(n, 256), 256, 0, st>>>(dy, y, dz, n);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_colsum(const float* x, long long ld, long long rows, int cols, float* out, int accumulate, void* workspace,
+                 long long workspace_bytes, cudaStream_t st) {
+  if (cols <= 0) return HULC2_OK;
+  int colblocks = hulc2_cdiv(cols, 32);
+  long long max_slabs = workspace ? workspace_bytes / ((long long)cols * sizeof(float)) : 0;
+  if (max_slabs < 1) { hulc2_set_error("colsum: workspace too small"); return HULC2_EWORKSPACE; }
+  long long slabs = (2LL * kSMs + colblocks - 1) / colblocks;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs > (rows + 63) / 64) slabs = (rows + 63) / 64;
+  if (slabs < 1) slabs = 1;
+  if (slabs > 65535) slabs = 65535;
+  long long per = (rows + slabs - 1) / slabs;
+  if (per < 1) per = 1;
+  slabs = rows > 0 ? (rows + per - 1) / per : 1;
+  colsum_partial_kernel<<<dim3(colblocks, (unsigned)slabs), dim3(32, 8), 0, st>>>(x, ld, rows, cols, (float*)workspace, per);
+  HULC2_CHECK_LAUNCH();
+  colsum_final_kernel<<<hulc2_cdiv(cols, 128), 128, 0, st>>>((const float*)workspace, (int)slabs, cols, out, accumulate);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_nhwc_to_nchw(const float* src, float* dst, int F, int HW, int C, cudaStream_t st) {
+  if (F <= 0) return HULC2_OK;
+  dim3 grid(hulc2_cdiv(C, 32), hulc2_cdiv(HW, 32), F);
+  transpose_frames_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, HW, C, nullptr);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_nchw_to_nhwc(const float* src, float* dst, int F, int HW, int C, const float* mask, cudaStream_t st) {
+  if (F <= 0) return HULC2_OK;
+  dim3 grid(hulc2_cdiv(HW, 32), hulc2_cdiv(C, 32), F);
+  transpose_frames_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, C, HW, mask);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_transpose01(const float* src, long long src_ld, float* dst, long long dst_ld, int D0, int D1, int D2, int accumulate,
+                      cudaStream_t st) {
+  long long total = (long long)D0 * D1 * D2;
+  if (total <= 0) return HULC2_OK;
+  transpose01_kernel<<<grid_for(total, 256), 256, 0, st>>>(src, src_ld, dst, dst_ld, D0, D1, D2, accumulate);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_permute_conv_weight(const float* src, float* dst, int O, int I, int KH, int KW, int dir, int accumulate,
+                              cudaStream_t st) {
+  int total = O * I * KH * KW;
+  if (total <= 0) return HULC2_OK;
+  permute_weight_kernel<<<grid_for(total, 256), 256, 0, st>>>(src, dst, O, I, KH, KW, dir, accumulate);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_philox_uniform(float* out, long long n, unsigned long long seed, unsigned long long offset, cudaStream_t st) {
+  if (n <= 0) return HULC2_OK;
+  philox_uniform_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(out, n, seed, offset);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_dropout_mask(unsigned char* out, long long n, float p, unsigned long long seed, unsigned long long offset,
+                       cudaStream_t st) {
+  if (n <= 0) return HULC2_OK;
+  dropout_mask_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(out, n, p, seed, offset);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float grad_scale, cudaStream_t st) {
+  if (n <= 0) return HULC2_OK;
+  if (step < 1) { hulc2_set_error("adam: step must be >= 1"); return HULC2_EINVAL; }
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+                                                    (float)sqrt(bc2), grad_scale);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+}  // extern "C"

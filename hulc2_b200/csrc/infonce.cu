@@ -1,0 +1,143 @@
+// Visuo-lingual InfoNCE (hulc2/models/hulc2.py:472-508): row L2-normalisation (no eps), B x B similarity
+// scaled by exp(logit_scale), symmetric cross-entropy with diagonal labels over the rows selected by
+// use_for_aux_lang_loss.  The boolean row selection of the reference (data-dependent shapes + two host
+// syncs) becomes a static-shape masked computation.  B x B x 32 is tiny (262 kFLOP at B=64): one CTA,
+// deterministic, phases separated by __syncthreads, intermediates in a caller workspace.
+#include "common.cuh"
+#include "../../include/hulc2_b200.h"
+
+namespace {
+
+struct Ws {
+  float *imn, *txn, *sim, *rlse, *clse, *inorm, *tnorm;
+};
+__device__ __forceinline__ Ws carve(float* w, int B, int D) {
+  Ws s;
+  s.imn = w; s.txn = s.imn + (long long)B * D; s.sim = s.txn + (long long)B * D;
+  s.rlse = s.sim + (long long)B * B; s.clse = s.rlse + B; s.inorm = s.clse + B; s.tnorm = s.inorm + B;
+  return s;
+}
+
+__device__ void infonce_forward_phases(const float* img, const float* txt, const unsigned char* use, float scale, int B, int D,
+                                       const Ws& w) {
+  for (int r = threadIdx.x; r < B; r += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int d = 0; d < D; ++d) { float x = img[(long long)r * D + d], y = txt[(long long)r * D + d]; a += x * x; b += y * y; }
+    a = sqrtf(a); b = sqrtf(b);
+    w.inorm[r] = a; w.tnorm[r] = b;
+    for (int d = 0; d < D; ++d) { w.imn[(long long)r * D + d] = img[(long long)r * D + d] / a; w.txn[(long long)r * D + d] = txt[(long long)r * D + d] / b; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B * B; i += blockDim.x) {
+    int r = i / B, c = i - r * B;
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) s = fmaf(scale * w.imn[(long long)r * D + d], w.txn[(long long)c * D + d], s);
+    w.sim[i] = s;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < B; r += blockDim.x) {
+    float m1 = -INFINITY, m2 = -INFINITY;
+    for (int c = 0; c < B; ++c)
+      if (!use || use[c]) { m1 = fmaxf(m1, w.sim[(long long)r * B + c]); m2 = fmaxf(m2, w.sim[(long long)c * B + r]); }
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = 0; c < B; ++c)
+      if (!use || use[c]) { s1 += expf(w.sim[(long long)r * B + c] - m1); s2 += expf(w.sim[(long long)c * B + r] - m2); }
+    w.rlse[r] = m1 + logf(s1);
+    w.clse[r] = m2 + logf(s2);
+  }
+  __syncthreads();
+}
+
+__global__ void infonce_fwd_kernel(const float* __restrict__ img, const float* __restrict__ txt,
+                                   const unsigned char* __restrict__ use, const float* __restrict__ logit_scale,
+                                   float* __restrict__ loss, int B, int D, float* __restrict__ wsp) {
+  __shared__ float red[32];
+  Ws w = carve(wsp, B, D);
+  infonce_forward_phases(img, txt, use, expf(logit_scale[0]), B, D, w);
+  float acc = 0.f, cnt = 0.f;
+  for (int r = threadIdx.x; r < B; r += blockDim.x)
+    if (!use || use[r]) { acc += (w.rlse[r] - w.sim[(long long)r * B + r]) + (w.clse[r] - w.sim[(long long)r * B + r]); cnt += 1.f; }
+  acc = block_sum(acc, red);
+  cnt = block_sum(cnt, red);
+  if (threadIdx.x == 0) loss[0] = cnt > 0.f ? acc / (2.f * cnt) : 0.f;
+}
+
+__global__ void infonce_bwd_kernel(const float* __restrict__ img, const float* __restrict__ txt,
+                                   const unsigned char* __restrict__ use, const float* __restrict__ logit_scale,
+                                   const float* __restrict__ gout, float* __restrict__ dimg, float* __restrict__ dtxt,
+                                   float* __restrict__ dlogit_scale, int B, int D, float* __restrict__ wsp) {
+  __shared__ float red[32];
+  Ws w = carve(wsp, B, D);
+  const float scale = expf(logit_scale[0]);
+  infonce_forward_phases(img, txt, use, scale, B, D, w);
+  float cnt = 0.f;
+  for (int r = threadIdx.x; r < B; r += blockDim.x) if (!use || use[r]) cnt += 1.f;
+  cnt = block_sum(cnt, red);
+  const float g = cnt > 0.f ? (gout ? gout[0] : 1.f) / (2.f * cnt) : 0.f;
+  // dsim(i,j) = g * [softmax_row_i(j) + softmax_col_j(i) - 2*delta_ij] on selected rows/cols
+  auto dsim = [&](int i, int j) -> float {
+    if (use && (!use[i] || !use[j])) return 0.f;
+    float s = w.sim[(long long)i * B + j];
+    float v = expf(s - w.rlse[i]) + expf(s - w.clse[j]);
+    if (i == j) v -= 2.f;
+    return g * v;
+  };
+  float dsc = 0.f;
+  for (int i = threadIdx.x; i < B * B; i += blockDim.x) {
+    float dv = dsim(i / B, i % B);
+    if (dv != 0.f) dsc += dv * w.sim[i];
+  }
+  dsc = block_sum(dsc, red);
+  if (threadIdx.x == 0 && dlogit_scale) dlogit_scale[0] += dsc;  // d/d(log scale) = sum dsim*sim
+  // gradients wrt the normalised features, then through x/||x||
+  for (int i = threadIdx.x; i < B * D; i += blockDim.x) {
+    int r = i / D, d = i - r * D;
+    float a = 0.f, b = 0.f;
+    for (int c = 0; c < B; ++c) {
+      if (use && (!use[c] || !use[r])) continue;
+      a = fmaf(dsim(r, c), w.txn[(long long)c * D + d], a);
+      b = fmaf(dsim(c, r), w.imn[(long long)c * D + d], b);
+    }
+    dimg[i] = scale * a;   // temporarily d(imn)
+    dtxt[i] = scale * b;   // temporarily d(txn)
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < B; r += blockDim.x) {
+    if (use && !use[r]) {
+      for (int d = 0; d < D; ++d) dimg[(long long)r * D + d] = dtxt[(long long)r * D + d] = 0.f;
+      continue;
+    }
+    float da = 0.f, db = 0.f;
+    for (int d = 0; d < D; ++d) { da += w.imn[(long long)r * D + d] * dimg[(long long)r * D + d]; db += w.txn[(long long)r * D + d] * dtxt[(long long)r * D + d]; }
+    for (int d = 0; d < D; ++d) {
+      dimg[(long long)r * D + d] = (dimg[(long long)r * D + d] - w.imn[(long long)r * D + d] * da) / w.inorm[r];
+      dtxt[(long long)r * D + d] = (dtxt[(long long)r * D + d] - w.txn[(long long)r * D + d] * db) / w.tnorm[r];
+    }
+  }
+}
+
+long long ws_floats(int B, int D) { return 2LL * B * D + (long long)B * B + 4LL * B; }
+
+}  // namespace
+
+extern "C" {
+
+int hulc2_infonce_fwd(const float* img, const float* txt, const unsigned char* use, const float* logit_scale, float* loss,
+                      int B, int D, void* workspace, long long workspace_bytes, cudaStream_t st) {
+  if (B <= 0) return HULC2_OK;
+  if (!workspace || workspace_bytes < ws_floats(B, D) * (long long)sizeof(float)) { hulc2_set_error("infonce: workspace too small"); return HULC2_EWORKSPACE; }
+  infonce_fwd_kernel<<<1, 1024, 0, st>>>(img, txt, use, logit_scale, loss, B, D, (float*)workspace);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_infonce_bwd(const float* img, const float* txt, const unsigned char* use, const float* logit_scale, const float* gout,
+                      float* dimg, float* dtxt, float* dlogit_scale, int B, int D, void* workspace, long long workspace_bytes,
+                      cudaStream_t st) {
+  if (B <= 0) return HULC2_OK;
+  if (!workspace || workspace_bytes < ws_floats(B, D) * (long long)sizeof(float)) { hulc2_set_error("infonce: workspace too small"); return HULC2_EWORKSPACE; }
+  infonce_bwd_kernel<<<1, 1024, 0, st>>>(img, txt, use, logit_scale, gout, dimg, dtxt, dlogit_scale, B, D, (float*)workspace);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+// LayerNorm (+residual +dropout) and SpatialSoftmax, forward and backward.  Memory-bound: one pass
+// over HBM per tensor, warp-shuffle reductions, coalesced along the feature/channel axis.
+#include "common.cuh"
+#include "../../include/hulc2_b200.h"
+
+namespace {
+
+constexpr int LN_VALS = 8;  // per-lane register slots: D <= 256
+
+// --------------------------------------------------------------------------- LayerNorm
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ res, long long ldr,
+                                     const unsigned char* __restrict__ keep, float keep_scale,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
+                                     long long ldy, float* __restrict__ tsum, float* __restrict__ mean_out,
+                                     float* __restrict__ rstd_out, long long rows, int D, float eps) {
+  int lane = threadIdx.x & 31;
+  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    float v[LN_VALS];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_VALS; ++j) {
+      int c = lane + 32 * j;
+      float t = 0.f;
+      if (c < D) {
+        t = x[r * ldx + c];
+        if (res) {
+          float rv = res[r * ldr + c];
+          if (keep) rv = keep[r * D + c] ? rv * keep_scale : 0.f;
+          t += rv;
+        }
+        if (tsum) tsum[r * D + c] = t;
+      }
+      v[j] = t;
+      s += t;
+    }
+    float mu = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_VALS; ++j) {
+      int c = lane + 32 * j;
+      float d = (c < D) ? v[j] - mu : 0.f;
+      q += d * d;
+    }
+    float rs = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+    for (int j = 0; j < LN_VALS; ++j) {
+      int c = lane + 32 * j;
+      if (c < D) y[r * ldy + c] = (v[j] - mu) * rs * gamma[c] + beta[c];
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[r] = mu;
+      if (rstd_out) rstd_out[r] = rs;
+    }
+  }
+}
+
+__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, long long ldy, const float* __restrict__ t, long long ldt,
+                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd, float* __restrict__ dx, long long lddx,
+                                     float* __restrict__ dres, const unsigned char* __restrict__ keep, float keep_scale,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int D) {
+  __shared__ float sg[8][LN_VALS * 32];
+  __shared__ float sb[8][LN_VALS * 32];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float ag[LN_VALS], ab[LN_VALS];
+#pragma unroll
+  for (int j = 0; j < LN_VALS; ++j) ag[j] = ab[j] = 0.f;
+  for (long long r = warp; r < rows; r += nwarps) {
+    float mu = mean[r], rs = rstd[r];
+    float xh[LN_VALS], g[LN_VALS];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_VALS; ++j) {
+      int c = lane + 32 * j;
+      xh[j] = g[j] = 0.f;
+      if (c < D) {
+        float d = dy[r * ldy + c];
+        xh[j] = (t[r * ldt + c] - mu) * rs;
+        g[j] = d * gamma[c];
+        ag[j] += d * xh[j];
+        ab[j] += d;
+        c1 += g[j];
+        c2 += g[j] * xh[j];
+      }
+    }
+    c1 = warp_sum(c1) / (float)D;
+    c2 = warp_sum(c2) / (float)D;
+#pragma unroll
+    for (int j = 0; j < LN_VALS; ++j) {
+      int c = lane + 32 * j;
+      if (c < D) {
+        float v = rs * (g[j] - c1 - xh[j] * c2);
+        dx[r * lddx + c] = v;
+        if (dres) dres[r * D + c] = keep ? (keep[r * D + c] ? v * keep_scale : 0.f) : v;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < LN_VALS; ++j) { sg[w][lane + 32 * j] = ag[j]; sb[w][lane + 32 * j] = ab[j]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a += sg[k][c]; b += sb[k][c]; }
+    if (dgamma) atomicAdd(dgamma + c, a);
+    if (dbeta) atomicAdd(dbeta + c, b);
+  }
+}
+
+// --------------------------------------------------------------------------- SpatialSoftmax (NHWC)
+// block = one frame; thread (c, g): channel c, position group g of G = blockDim.x / C.
+template <bool BWD>
+__global__ void spatial_softmax_kernel(const float* __restrict__ x, const float* __restrict__ x_map,
+                                       const float* __restrict__ y_map, const float* __restrict__ temperature,
+                                       float* __restrict__ out, const float* __restrict__ dout, float* __restrict__ dx,
+                                       float* __restrict__ dtemp, int HW, int C, int relu_mask) {
+  extern __shared__ float sm[];  // [G][C] x 3
+  const int G = blockDim.x / C;
+  const int c = threadIdx.x % C, g = threadIdx.x / C;
+  const bool active = g < G;
+  const float invT = 1.f / temperature[0];
+  const float* xf = x + (long long)blockIdx.x * HW * C;
+  float* s0 = sm; float* s1 = sm + G * C; float* s2 = sm + 2 * G * C;
+
+  float mx = -INFINITY;
+  if (active) for (int i = g; i < HW; i += G) mx = fmaxf(mx, xf[(long long)i * C + c] * invT);
+  if (active) s0[g * C + c] = mx;
+  __syncthreads();
+  if (active) { mx = s0[c]; for (int k = 1; k < G; ++k) mx = fmaxf(mx, s0[k * C + c]); }
+  __syncthreads();
+
+  float se = 0.f, sx = 0.f, sy = 0.f;
+  if (active)
+    for (int i = g; i < HW; i += G) {
+      float e = expf(xf[(long long)i * C + c] * invT - mx);
+      se += e; sx += e * x_map[i]; sy += e * y_map[i];
+    }
+  if (active) { s0[g * C + c] = se; s1[g * C + c] = sx; s2[g * C + c] = sy; }
+  __syncthreads();
+  if (active) {
+    se = sx = sy = 0.f;
+    for (int k = 0; k < G; ++k) { se += s0[k * C + c]; sx += s1[k * C + c]; sy += s2[k * C + c]; }
+  }
+  const float inv = active ? 1.f / se : 0.f;
+  const float ex = sx * inv, ey = sy * inv;
+  if (!BWD) {
+    if (active && g == 0) {
+      out[(long long)blockIdx.x * 2 * C + 2 * c] = ex;
+      out[(long long)blockIdx.x * 2 * C + 2 * c + 1] = ey;
+    }
+    return;
+  }
+  if (!active) return;
+  const float gx = dout[(long long)blockIdx.x * 2 * C + 2 * c], gy = dout[(long long)blockIdx.x * 2 * C + 2 * c + 1];
+  float* dxf = dx + (long long)blockIdx.x * HW * C;
+  float dt = 0.f;
+  for (int i = g; i < HW; i += G) {
+    float xv = xf[(long long)i * C + c];
+    float p = expf(xv * invT - mx) * inv;
+    float dl = p * (gx * (x_map[i] - ex) + gy * (y_map[i] - ey));  // d/d(logit_i), logit = x/T
+    dt += dl * xv;
+    float v = dl * invT;
+    if (relu_mask && !(xv > 0.f)) v = 0.f;
+    dxf[(long long)i * C + c] = v;
+  }
+  if (dtemp) atomicAdd(dtemp, -dt * invT * invT);
+}
+
+}  // namespace
+
+extern "C" {
+
+int hulc2_layernorm_fwd(const float* x, long long ldx, const float* res, long long ldr, const unsigned char* keep,
+                        float keep_scale, const float* gamma, const float* beta, float* y, long long ldy, float* tsum,
+                        float* mean, float* rstd, long long rows, int D, float eps, cudaStream_t st) {
+  if (rows <= 0) return HULC2_OK;
+  if (D > 32 * LN_VALS || D <= 0) { hulc2_set_error("layernorm: D must be in (0,256]"); return HULC2_EINVAL; }
+  long long blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  layernorm_fwd_kernel<<<(int)blocks, 256, 0, st>>>(x, ldx, res, ldr, keep, keep_scale, gamma, beta, y, ldy, tsum, mean, rstd, rows, D, eps);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+int hulc2_layernorm_bwd(const float* dy, long long ldy, const float* t, long long ldt, const float* gamma, const float* mean,
+                        const float* rstd, float* dx, long long lddx, float* dres, const unsigned char* keep, float keep_scale,
+                        float* dgamma, float* dbeta, long long rows, int D, cudaStream_t st) {
+  if (rows <= 0) return HULC2_OK;
+  if (D > 32 * LN_VALS || D <= 0) { hulc2_set_error("layernorm: D must be in (0,256]"); return HULC2_EINVAL; }
+  long long blocks = (rows + 7) / 8;
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  layernorm_bwd_kernel<<<(int)blocks, 256, 0, st>>>(dy, ldy, t, ldt, gamma, mean, rstd, dx, lddx, dres, keep, keep_scale, dgamma, dbeta, rows, D);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+static int ssm_threads(int C) {
+  if (C > 256) return 0;
+  int G = 256 / C;
+  return G * C > 0 ? 256 : 0;
+}
+
+int hulc2_spatial_softmax_fwd(const float* x, const float* x_map, const float* y_map, const float* temperature, float* out,
+                              int F, int HW, int C, cudaStream_t st) {
+  if (F <= 0) return HULC2_OK;
+  if (!ssm_threads(C)) { hulc2_set_error("spatial_softmax: C must be <= 256"); return HULC2_EINVAL; }
+  int G = 256 / C;
+  spatial_softmax_kernel<false><<<F, 256, 3 * G * C * sizeof(float), st>>>(x, x_map, y_map, temperature, out, nullptr, nullptr, nullptr, HW, C, 0);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+int hulc2_spatial_softmax_bwd(const float* x, const float* x_map, const float* y_map, const float* temperature,
+                              const float* out, const float* dout, float* dx, float* dtemperature, int F, int HW, int C,
+                              int relu_mask, cudaStream_t st) {
+  (void)out;
+  if (F <= 0) return HULC2_OK;
+  if (!ssm_threads(C)) { hulc2_set_error("spatial_softmax: C must be <= 256"); return HULC2_EINVAL; }
+  int G = 256 / C;
+  spatial_softmax_kernel<true><<<F, 256, 3 * G * C * sizeof(float), st>>>(x, x_map, y_map, temperature, nullptr, dout, dx, dtemperature, HW, C, relu_mask);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+"""RNN factories (mirror of hulc2/models/decoders/utils/rnn.py:5-46).  The returned torch modules are
+parameter containers (``weight_ih_l0`` ...); the recurrence itself runs in the CUDA library.  Only the
+default ``rnn_decoder`` (ReLU Elman RNN) has kernels this round; GRU/LSTM/MLP are SURVEY 8f row 4."""
+import torch
+import torch.nn as nn
+
+
+def rnn_decoder(in_features: int, hidden_size: int, num_layers: int, policy_rnn_dropout_p: float) -> torch.nn.Module:
+    return nn.RNN(
+        input_size=in_features,
+        hidden_size=hidden_size,
+        num_layers=num_layers,
+        nonlinearity="relu",
+        bidirectional=False,
+        batch_first=True,
+        dropout=policy_rnn_dropout_p,
+    )
+
+
+def lstm_decoder(in_features: int, hidden_size: int, num_layers: int, policy_rnn_dropout_p: float) -> torch.nn.Module:
+    raise NotImplementedError("lstm_decoder: recurrence cell not built yet (SURVEY.md 8f row 4)")
+
+
+def gru_decoder(in_features: int, hidden_size: int, num_layers: int, policy_rnn_dropout_p: float) -> torch.nn.Module:
+    raise NotImplementedError("gru_decoder: recurrence cell not built yet (SURVEY.md 8f row 4)")
+
+
+def mlp_decoder(in_features: int, hidden_size: int, num_layers: int, policy_rnn_dropout_p: float) -> torch.nn.Module:
+    raise NotImplementedError("mlp_decoder is never selected by a shipped config")
+
+
+RNN_MODELS = {"rnn_decoder": rnn_decoder, "lstm_decoder": lstm_decoder, "gru_decoder": gru_decoder, "mlp_decoder": mlp_decoder}

@@ -1,0 +1,80 @@
+"""Randomness of the policy step as explicit inputs.
+
+The reference draws noise with ``torch.multinomial`` / ``torch.rand`` / ``nn.Dropout``
+(distributions.py:38, logistic_decoder_rnn.py:236,248, plan_recognition_net.py:142 + the encoder
+layers).  Here every draw goes through this module: by default from the library's Philox4x32-10
+kernels (counter-based, seeded per process), or -- for parity tests and reproducible rollouts --
+from caller-supplied tensors queued with :func:`supplied`.
+"""
+from __future__ import annotations
+
+import contextlib
+from collections import deque
+from typing import Deque, Dict, Optional
+
+import torch
+
+from . import ops
+
+_state = {"seed": 0x5EED, "counter": 0}
+_queues: Dict[str, Deque[torch.Tensor]] = {"categories": deque(), "uniforms": deque(), "masks": deque()}
+
+
+def manual_seed(seed: int) -> None:
+    _state["seed"] = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _state["counter"] = 0
+
+
+def _next_offset(n: int) -> int:
+    off = _state["counter"]
+    _state["counter"] += (n + 3) // 4 + 1
+    return off
+
+
+@contextlib.contextmanager
+def supplied(categories=(), uniforms=(), masks=()):
+    """Queue tensors to be consumed (in call order) instead of fresh draws."""
+    _queues["categories"].extend(categories)
+    _queues["uniforms"].extend(uniforms)
+    _queues["masks"].extend(masks)
+    try:
+        yield
+    finally:
+        left = {k: len(v) for k, v in _queues.items() if len(v)}
+        for q in _queues.values():
+            q.clear()
+        if left:
+            raise AssertionError(f"unused supplied noise: {left}")
+
+
+def uniform(shape, device) -> torch.Tensor:
+    if _queues["uniforms"]:
+        t = _queues["uniforms"].popleft()
+        assert tuple(t.shape) == tuple(shape), (tuple(t.shape), tuple(shape))
+        return t.to(device=device, dtype=torch.float32)
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return ops.uniform(tuple(shape), device, _state["seed"], _next_offset(n))
+
+
+def categories(logits: torch.Tensor, cats: int, classes: int) -> torch.Tensor:
+    """Category indices [B,cats] ~ Categorical(softmax(logits)) (or the next supplied tensor)."""
+    if _queues["categories"]:
+        t = _queues["categories"].popleft()
+        assert tuple(t.shape) == (logits.shape[0], cats), (tuple(t.shape), (logits.shape[0], cats))
+        return t.to(device=logits.device, dtype=torch.int64)
+    u = uniform((logits.shape[0], cats), logits.device)
+    return ops.categorical_sample(logits.detach(), u, cats, classes)
+
+
+def keep_mask(shape, p: float, device) -> Optional[torch.Tensor]:
+    """uint8 dropout keep mask with P(keep) = 1-p (or the next supplied mask)."""
+    if _queues["masks"]:
+        t = _queues["masks"].popleft()
+        assert tuple(t.shape) == tuple(shape), (tuple(t.shape), tuple(shape))
+        return t.to(device=device, dtype=torch.uint8).contiguous()
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return ops.dropout_mask(tuple(shape), p, device, _state["seed"], _next_offset(n))

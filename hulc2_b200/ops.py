@@ -1,0 +1,826 @@
+"""Autograd operators of the HULC++ policy step, each backed by the C-ABI CUDA kernels.
+
+Every ``torch.autograd.Function`` here launches only kernels of ``libhulc2_b200.so`` (through
+``_lib.call``); torch provides device memory (``torch.empty``), views and the autograd tape.
+There is no eager/PyTorch fallback: calling any op without the library or without a CUDA device
+raises ``RuntimeError``.
+
+Layout notes
+  * activations inside the conv encoders are NHWC (the implicit-GEMM output layout);
+  * the decoder runs time-major ``[S,B,*]`` so every recurrence step is one contiguous matrix;
+  * 2-D operands may be row-strided views (``stride(1) == 1``), e.g. ``emb[:, 0]``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, GemmArgs, call
+
+_PRECISION = {"fp32": 0, "bf16": 1}
+_precision = 0
+_WS_BYTES = 96 << 20
+_ws = {}
+
+
+def set_precision(p: str) -> None:
+    """'fp32' = CUDA-core path (1e-5 parity); 'bf16' = tcgen05 tensor-core contractions."""
+    global _precision
+    _precision = _PRECISION[p]
+
+
+def get_precision() -> str:
+    return "bf16" if _precision else "fp32"
+
+
+def workspace(device) -> torch.Tensor:
+    key = (device.type, device.index)
+    if key not in _ws:
+        _ws[key] = torch.empty(_WS_BYTES, dtype=torch.uint8, device=device)
+    return _ws[key]
+
+
+def _p(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"hulc2_b200 ops take float32 tensors, got {t.dtype}")
+    if not t.is_cuda:
+        raise RuntimeError("hulc2_b200 ops need CUDA tensors (no CPU fallback)")
+    return t
+
+
+def _rows2d(t: torch.Tensor) -> torch.Tensor:
+    """Returns a 2-D tensor with unit inner stride (copying only if the view is not expressible)."""
+    if t.dim() != 2:
+        t = t.reshape(-1, t.shape[-1])
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+# ----------------------------------------------------------------------------- raw kernel wrappers
+def gemm(M, N, K, A, a_rs, a_ks, B, b_rs, b_ks, Cout, ldc, *, a_off=0, b_off=0, c_off=0, bias=None, add=None, ld_add=0,
+         mask=None, ld_mask=0, keep=None, ld_keep=0, keep_scale=1.0, relu=False, accumulate=False, alpha=1.0,
+         a_inner=0, a_rs_outer=0, a_rs_inner=0, c_inner=0, c_rs_outer=0, c_rs_inner=0, precision=None):
+    """C[m,n] = epi(alpha * sum_k A(m,k) B(n,k)); offsets are in elements."""
+    ws = workspace(Cout.device)
+    g = GemmArgs()
+    g.M, g.N, g.K = int(M), int(N), int(K)
+    g.A = A.data_ptr() + 4 * a_off
+    g.a_rs, g.a_ks, g.a_inner, g.a_rs_outer, g.a_rs_inner = a_rs, a_ks, a_inner, a_rs_outer, a_rs_inner
+    g.B = B.data_ptr() + 4 * b_off
+    g.b_rs, g.b_ks = b_rs, b_ks
+    g.C = Cout.data_ptr() + 4 * c_off
+    g.ldc, g.c_inner, g.c_rs_outer, g.c_rs_inner = ldc, c_inner, c_rs_outer, c_rs_inner
+    g.bias = _p(bias)
+    g.add, g.ld_add = _p(add), ld_add
+    g.mask, g.ld_mask = _p(mask), ld_mask
+    g.keep, g.ld_keep, g.keep_scale = _p(keep), ld_keep, keep_scale
+    g.relu, g.accumulate, g.alpha = int(relu), int(accumulate), alpha
+    g.precision = _precision if precision is None else precision
+    g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
+    call("hulc2_gemm", C.byref(g))
+
+
+def _conv_args(F, Cin, H, W, Cout, k, stride, in_nhwc) -> ConvArgs:
+    a = ConvArgs()
+    a.F, a.C, a.H, a.W, a.Cout, a.KH, a.KW, a.stride, a.in_nhwc = F, Cin, H, W, Cout, k, k, stride, int(in_nhwc)
+    a.precision = _precision
+    return a
+
+
+def colsum(x: torch.Tensor, ld: int, rows: int, cols: int, out: torch.Tensor, accumulate=False, x_off=0):
+    ws = workspace(x.device)
+    call("hulc2_colsum", x.data_ptr() + 4 * x_off, ld, rows, cols, out.data_ptr(), int(accumulate), ws.data_ptr(), ws.numel())
+
+
+# ----------------------------------------------------------------------------- MLP (stack of nn.Linear [+ReLU] [+dropout])
+class MLPFunction(torch.autograd.Function):
+    """y = L_n(...act(L_1(x))) with L_i = nn.Linear.  Covers goal_encoders.py:19-27/52-60, plan_proposal_net.py:25-40,
+    proj_vis_lang.py:10-21, vision_network.py:49-52, the transformer FFN and every single nn.Linear on the path.
+    args: x, n_layers, relu flags tuple, keeps tuple (u8 mask or None per layer), keep_scale, then W1, b1, W2, b2, ..."""
+
+    @staticmethod
+    def forward(ctx, x, relus, keeps, keep_scale, *wb):
+        x2 = _rows2d(_f32(x))
+        M = x2.shape[0]
+        n = len(wb) // 2
+        acts = []
+        cur, ld = x2, _ld(x2)
+        for i in range(n):
+            W, b = wb[2 * i], wb[2 * i + 1]
+            N, K = W.shape
+            y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+            if M > 0:
+                gemm(M, N, K, cur, ld, 1, W, K, 1, y, N, bias=b, relu=relus[i], keep=keeps[i], ld_keep=N, keep_scale=keep_scale)
+            acts.append(y)
+            cur, ld = y, N
+        ctx.relus, ctx.keeps, ctx.keep_scale, ctx.n = relus, keeps, keep_scale, n
+        ctx.x_shape = x.shape
+        ctx.save_for_backward(x2, *acts, *wb)
+        return acts[-1].view(*x.shape[:-1], acts[-1].shape[1])
+
+    @staticmethod
+    def backward(ctx, dout):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        x2, acts, wb = saved[0], saved[1 : 1 + n], saved[1 + n :]
+        M = x2.shape[0]
+        g = _rows2d(dout.contiguous())
+        if g.data_ptr() == dout.data_ptr() and (ctx.relus[n - 1] or ctx.keeps[n - 1] is not None):
+            g = g.clone()
+        if ctx.relus[n - 1]:
+            assert ctx.keeps[n - 1] is None, "dropout after the last layer of an MLP stack is not supported"
+            call("hulc2_relu_mask", g.data_ptr(), acts[n - 1].data_ptr(), g.data_ptr(), g.numel())
+        grads: List[Optional[torch.Tensor]] = [None] * (2 * n)
+        dx = None
+        for i in range(n - 1, -1, -1):
+            W = wb[2 * i]
+            N, K = W.shape
+            inp = x2 if i == 0 else acts[i - 1]
+            ld_in = _ld(x2) if i == 0 else K
+            if ctx.needs_input_grad[4 + 2 * i]:
+                dW = torch.empty_like(W)
+                gemm(N, K, M, g, 1, N, inp, 1, ld_in, dW, K)           # dW = g^T inp
+                grads[2 * i] = dW
+            if ctx.needs_input_grad[5 + 2 * i]:
+                db = torch.empty(N, device=W.device, dtype=torch.float32)
+                colsum(g, N, M, N, db)
+                grads[2 * i + 1] = db
+            if i > 0 or ctx.needs_input_grad[0]:
+                gi = torch.empty(M, K, device=W.device, dtype=torch.float32)
+                if M > 0:
+                    if i > 0:
+                        gemm(M, K, N, g, N, 1, W, 1, K, gi, K, mask=acts[i - 1] if ctx.relus[i - 1] else None, ld_mask=K,
+                             keep=ctx.keeps[i - 1], ld_keep=K, keep_scale=ctx.keep_scale)
+                    else:
+                        gemm(M, K, N, g, N, 1, W, 1, K, gi, K)
+                g = gi
+                if i == 0:
+                    dx = gi.view(ctx.x_shape)
+        return (dx, None, None, None, *grads)
+
+
+def mlp(x, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], relus: Sequence[bool], keeps=None, keep_scale=1.0):
+    keeps = tuple(keeps) if keeps is not None else (None,) * len(layers)
+    flat = [t for wb in layers for t in wb]
+    return MLPFunction.apply(x, tuple(bool(r) for r in relus), keeps, float(keep_scale), *flat)
+
+
+def linear(x, W, b, relu=False):
+    return mlp(x, [(W, b)], [relu])
+
+
+# ----------------------------------------------------------------------------- conv trunks
+def _conv_trunk_fwd(x, w1, b1, w2, b2, w3, b3):
+    """conv(k8,s4)+ReLU -> conv(k4,s2)+ReLU -> conv(k3,s1)+ReLU; x NCHW, outputs NHWC."""
+    F_, Cin, H, W = x.shape
+    dev = x.device
+    ws = workspace(dev)
+
+    def osz(h, k, s):
+        return (h - k) // s + 1
+
+    H1, W1 = osz(H, 8, 4), osz(W, 8, 4)
+    H2, W2 = osz(H1, 4, 2), osz(W1, 4, 2)
+    H3, W3 = osz(H2, 3, 1), osz(W2, 3, 1)
+    y1 = torch.empty(F_, H1, W1, 32, device=dev, dtype=torch.float32)
+    y2 = torch.empty(F_, H2, W2, 64, device=dev, dtype=torch.float32)
+    y3 = torch.empty(F_, H3, W3, 64, device=dev, dtype=torch.float32)
+    w2p = torch.empty(64, 4, 4, 32, device=dev, dtype=torch.float32)
+    w3p = torch.empty(64, 3, 3, 64, device=dev, dtype=torch.float32)
+    call("hulc2_permute_conv_weight", w2.data_ptr(), w2p.data_ptr(), 64, 32, 4, 4, 0, 0)
+    call("hulc2_permute_conv_weight", w3.data_ptr(), w3p.data_ptr(), 64, 64, 3, 3, 0, 0)
+    for (xin, w, b, y, cin, h, wd, cout, k, s, nhwc) in (
+        (x, w1, b1, y1, Cin, H, W, 32, 8, 4, 0),
+        (y1, w2p, b2, y2, 32, H1, W1, 64, 4, 2, 1),
+        (y2, w3p, b3, y3, 64, H2, W2, 64, 3, 1, 1),
+    ):
+        a = _conv_args(F_, cin, h, wd, cout, k, s, nhwc)
+        a.x, a.w, a.bias, a.y, a.relu = xin.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), 1
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        call("hulc2_conv2d_fwd", C.byref(a))
+    return y1, y2, y3
+
+
+def _conv_trunk_bwd(x, y1, y2, dz3, w2, w3, need):
+    """dz3 = gradient wrt the PRE-activation of conv3 (already ReLU-masked), NHWC. Returns param grads."""
+    F_, Cin, H, W = x.shape
+    dev = x.device
+    ws = workspace(dev)
+    H1, W1, H2, W2 = y1.shape[1], y1.shape[2], y2.shape[1], y2.shape[2]
+    H3, W3 = dz3.shape[1], dz3.shape[2]
+
+    def wgrad(xin, dz, cin, h, wd, cout, k, s, nhwc, shape_oihw):
+        a = _conv_args(F_, cin, h, wd, cout, k, s, nhwc)
+        dw = torch.empty(cout, cin * k * k, device=dev, dtype=torch.float32)
+        a.x, a.dy, a.dw, a.accumulate = xin.data_ptr(), dz.data_ptr(), dw.data_ptr(), 0
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        call("hulc2_conv2d_wgrad", C.byref(a))
+        if nhwc:
+            out = torch.empty(shape_oihw, device=dev, dtype=torch.float32)
+            call("hulc2_permute_conv_weight", dw.data_ptr(), out.data_ptr(), cout, cin, k, k, 1, 0)
+            return out
+        return dw.view(shape_oihw)
+
+    def bgrad(dz, cout):
+        db = torch.empty(cout, device=dev, dtype=torch.float32)
+        colsum(dz, cout, dz.numel() // cout, cout, db)
+        return db
+
+    def dgrad(dz, w_oihw, xmask, cin, h, wd, cout, k, s):
+        whwoi = torch.empty(k, k, cout, cin, device=dev, dtype=torch.float32)
+        call("hulc2_permute_conv_weight", w_oihw.data_ptr(), whwoi.data_ptr(), cout, cin, k, k, 2, 0)
+        dx = torch.empty(F_, h, wd, cin, device=dev, dtype=torch.float32)
+        a = _conv_args(F_, cin, h, wd, cout, k, s, 1)
+        a.dy, a.w, a.dx, a.xmask = dz.data_ptr(), whwoi.data_ptr(), dx.data_ptr(), xmask.data_ptr()
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        call("hulc2_conv2d_dgrad", C.byref(a))
+        return dx
+
+    g = {}
+    if need[2]:
+        g["w3"] = wgrad(y2, dz3, 64, H2, W2, 64, 3, 1, 1, (64, 64, 3, 3))
+        g["b3"] = bgrad(dz3, 64)
+    dz2 = dgrad(dz3, w3, y2, 64, H2, W2, 64, 3, 1)
+    if need[1]:
+        g["w2"] = wgrad(y1, dz2, 32, H1, W1, 64, 4, 2, 1, (64, 32, 4, 4))
+        g["b2"] = bgrad(dz2, 64)
+    dz1 = dgrad(dz2, w2, y1, 32, H1, W1, 64, 4, 2)
+    if need[0]:
+        g["w1"] = wgrad(x, dz1, Cin, H, W, 32, 8, 4, 0, (32, Cin, 8, 8))
+        g["b1"] = bgrad(dz1, 32)
+    return g
+
+
+class StaticConvSSM(torch.autograd.Function):
+    """Static-camera trunk: 3 convs + SpatialSoftmax (vision_network.py:55-58, 100-108) -> [F, 2*64]."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3, x_map, y_map, temperature):
+        x = _f32(x).contiguous()
+        y1, y2, y3 = _conv_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
+        F_ = x.shape[0]
+        HW = y3.shape[1] * y3.shape[2]
+        out = torch.empty(F_, 128, device=x.device, dtype=torch.float32)
+        call("hulc2_spatial_softmax_fwd", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
+             out.data_ptr(), F_, HW, 64)
+        ctx.save_for_backward(x, y1, y2, y3, w2, w3, x_map, y_map, temperature, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y1, y2, y3, w2, w3, x_map, y_map, temperature, out = ctx.saved_tensors
+        dout = dout.contiguous()
+        F_ = x.shape[0]
+        HW = y3.shape[1] * y3.shape[2]
+        dz3 = torch.empty_like(y3)
+        dtemp = None
+        if ctx.needs_input_grad[9]:
+            dtemp = torch.zeros(1, device=x.device, dtype=torch.float32)
+        call("hulc2_spatial_softmax_bwd", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
+             out.data_ptr(), dout.data_ptr(), dz3.data_ptr(), _p(dtemp), F_, HW, 64, 1)
+        g = _conv_trunk_bwd(x, y1, y2, dz3, w2, w3, (True, True, True))
+        return (None, g["w1"], g["b1"], g["w2"], g["b2"], g["w3"], g["b3"], None, None, dtemp)
+
+
+class GripperConvFlatten(torch.autograd.Function):
+    """Gripper trunk: 3 convs + nn.Flatten in (C,H,W) order (vision_network_gripper.py:11-22) -> [F, 64*7*7]."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3):
+        x = _f32(x).contiguous()
+        y1, y2, y3 = _conv_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
+        F_ = x.shape[0]
+        HW = y3.shape[1] * y3.shape[2]
+        flat = torch.empty(F_, 64 * HW, device=x.device, dtype=torch.float32)
+        call("hulc2_nhwc_to_nchw", y3.data_ptr(), flat.data_ptr(), F_, HW, 64)
+        ctx.save_for_backward(x, y1, y2, y3, w2, w3)
+        return flat
+
+    @staticmethod
+    def backward(ctx, dflat):
+        x, y1, y2, y3, w2, w3 = ctx.saved_tensors
+        dflat = dflat.contiguous()
+        F_ = x.shape[0]
+        HW = y3.shape[1] * y3.shape[2]
+        dz3 = torch.empty_like(y3)
+        call("hulc2_nchw_to_nhwc", dflat.data_ptr(), dz3.data_ptr(), F_, HW, 64, y3.data_ptr())
+        g = _conv_trunk_bwd(x, y1, y2, dz3, w2, w3, (True, True, True))
+        return (None, g["w1"], g["b1"], g["w2"], g["b2"], g["w3"], g["b3"])
+
+
+# ----------------------------------------------------------------------------- LayerNorm
+class LayerNormFunction(torch.autograd.Function):
+    """y = LN(x + dropout(res)) * gamma + beta (eps 1e-5); res/keep optional.  Used for the encoder / goal
+    LayerNorms and the post-LN residual blocks of nn.TransformerEncoderLayer."""
+
+    @staticmethod
+    def forward(ctx, x, res, keep, keep_scale, gamma, beta, eps):
+        x2 = _rows2d(_f32(x))
+        rows, D = x2.shape
+        y = torch.empty(rows, D, device=x.device, dtype=torch.float32)
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+        r2 = _rows2d(res) if res is not None else None
+        t = torch.empty(rows, D, device=x.device, dtype=torch.float32) if res is not None else None
+        call("hulc2_layernorm_fwd", x2.data_ptr(), _ld(x2), _p(r2), _ld(r2) if r2 is not None else 0, _p(keep), keep_scale,
+             gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), D, _p(t), mean.data_ptr(), rstd.data_ptr(), rows, D, eps)
+        ctx.save_for_backward(t if t is not None else x2, gamma, mean, rstd)
+        ctx.keep, ctx.keep_scale, ctx.has_res, ctx.shape = keep, keep_scale, res is not None, x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        t, gamma, mean, rstd = ctx.saved_tensors
+        rows, D = t.shape[0], gamma.shape[0]
+        dy2 = _rows2d(dy.contiguous())
+        dx = torch.empty(rows, D, device=dy.device, dtype=torch.float32)
+        dres = torch.empty(rows, D, device=dy.device, dtype=torch.float32) if ctx.has_res else None
+        dgamma = torch.zeros(D, device=dy.device, dtype=torch.float32)
+        dbeta = torch.zeros(D, device=dy.device, dtype=torch.float32)
+        call("hulc2_layernorm_bwd", dy2.data_ptr(), D, t.data_ptr(), _ld(t), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+             dx.data_ptr(), D, _p(dres), _p(ctx.keep), ctx.keep_scale, dgamma.data_ptr(), dbeta.data_ptr(), rows, D)
+        return (dx.view(ctx.shape), dres.view(ctx.shape) if dres is not None else None, None, None, dgamma, dbeta, None)
+
+
+def layer_norm(x, gamma, beta, res=None, keep=None, keep_scale=1.0, eps=1e-5):
+    return LayerNormFunction.apply(x, res, keep, float(keep_scale), gamma, beta, float(eps))
+
+
+# ----------------------------------------------------------------------------- transformer pieces
+class AddPosFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, pos, keep, keep_scale):
+        emb = _f32(emb).contiguous()
+        B, S, E = emb.shape
+        out = torch.empty_like(emb)
+        call("hulc2_add_pos_fwd", emb.data_ptr(), pos.data_ptr(), _p(keep), keep_scale, out.data_ptr(), B, S, E)
+        ctx.keep, ctx.keep_scale, ctx.pos_shape = keep, keep_scale, pos.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        B, S, E = dout.shape
+        demb = torch.empty_like(dout)
+        dpos = torch.zeros(ctx.pos_shape, device=dout.device, dtype=torch.float32)
+        call("hulc2_add_pos_bwd", dout.data_ptr(), _p(ctx.keep), ctx.keep_scale, demb.data_ptr(), dpos.data_ptr(), B, S, E)
+        return demb, dpos, None, None
+
+
+class AttentionFunction(torch.autograd.Function):
+    """softmax(q k^T / sqrt(dh)) v per (window, head) with dropout on the probabilities; qkv [B*S, 3E]."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, S, H, keep, keep_scale):
+        qkv = _f32(qkv).contiguous()
+        E = qkv.shape[-1] // 3
+        out = torch.empty(B * S, E, device=qkv.device, dtype=torch.float32)
+        probs = torch.empty(B, H, S, S, device=qkv.device, dtype=torch.float32)
+        call("hulc2_attention_fwd", qkv.data_ptr(), _p(keep), keep_scale, out.data_ptr(), probs.data_ptr(), B, S, H, E // H)
+        ctx.save_for_backward(qkv, probs)
+        ctx.dims, ctx.keep, ctx.keep_scale = (B, S, H, E // H), keep, keep_scale
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, probs = ctx.saved_tensors
+        B, S, H, Dh = ctx.dims
+        dout = dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        call("hulc2_attention_bwd", qkv.data_ptr(), probs.data_ptr(), _p(ctx.keep), ctx.keep_scale, dout.data_ptr(),
+             dqkv.data_ptr(), B, S, H, Dh)
+        return dqkv, None, None, None, None, None
+
+
+class MeanSeqFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32(x).contiguous()
+        B, S, E = x.shape
+        out = torch.empty(B, E, device=x.device, dtype=torch.float32)
+        call("hulc2_mean_seq_fwd", x.data_ptr(), out.data_ptr(), B, S, E)
+        ctx.dims = (B, S, E)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, S, E = ctx.dims
+        dout = dout.contiguous()
+        dx = torch.empty(B, S, E, device=dout.device, dtype=torch.float32)
+        call("hulc2_mean_seq_bwd", dout.data_ptr(), dx.data_ptr(), B, S, E)
+        return dx
+
+
+# ----------------------------------------------------------------------------- latent plan
+class KLFunction(torch.autograd.Function):
+    """hulc2.py:444-466 for the discrete plan: balanced categorical KL, scaled by kl_beta."""
+
+    @staticmethod
+    def forward(ctx, pp, pr, cats, classes, alpha, beta):
+        pp, pr = _f32(pp).contiguous(), _f32(pr).contiguous()
+        B = pp.shape[0]
+        loss = torch.empty(1, device=pp.device, dtype=torch.float32)
+        call("hulc2_kl_fwd", pp.data_ptr(), pr.data_ptr(), loss.data_ptr(), B, cats, classes, alpha, beta)
+        ctx.save_for_backward(pp, pr)
+        ctx.cfg = (B, cats, classes, alpha, beta)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        pp, pr = ctx.saved_tensors
+        B, cats, classes, alpha, beta = ctx.cfg
+        g = g.contiguous()
+        dpp, dpr = torch.empty_like(pp), torch.empty_like(pr)
+        call("hulc2_kl_bwd", pp.data_ptr(), pr.data_ptr(), g.data_ptr(), dpp.data_ptr(), dpr.data_ptr(), B, cats, classes, alpha, beta)
+        return dpp, dpr, None, None, None, None
+
+
+class PlanRSampleFunction(torch.autograd.Function):
+    """OneHotCategoricalStraightThrough.rsample given the drawn indices (hulc2.py:235, distributions.py:23-26)."""
+
+    @staticmethod
+    def forward(ctx, logits, idx, cats, classes):
+        logits = _f32(logits).contiguous()
+        B = logits.shape[0]
+        plan = torch.empty(B, cats * classes, device=logits.device, dtype=torch.float32)
+        call("hulc2_onehot_fwd", idx.contiguous().data_ptr(), plan.data_ptr(), B, cats, classes)
+        ctx.save_for_backward(logits)
+        ctx.cfg = (B, cats, classes)
+        return plan
+
+    @staticmethod
+    def backward(ctx, dplan):
+        (logits,) = ctx.saved_tensors
+        B, cats, classes = ctx.cfg
+        dplan = dplan.contiguous()
+        dl = torch.empty_like(logits)
+        call("hulc2_st_onehot_bwd", logits.data_ptr(), dplan.data_ptr(), dl.data_ptr(), B, cats, classes)
+        return dl, None, None, None
+
+
+def onehot(idx: torch.Tensor, cats: int, classes: int) -> torch.Tensor:
+    B = idx.shape[0]
+    plan = torch.empty(B, cats * classes, device=idx.device, dtype=torch.float32)
+    call("hulc2_onehot_fwd", idx.contiguous().data_ptr(), plan.data_ptr(), B, cats, classes)
+    return plan
+
+
+def categorical_sample(logits: torch.Tensor, u: torch.Tensor, cats: int, classes: int) -> torch.Tensor:
+    B = logits.shape[0]
+    idx = torch.empty(B, cats, device=logits.device, dtype=torch.int64)
+    call("hulc2_categorical_sample", logits.contiguous().data_ptr(), u.contiguous().data_ptr(), idx.data_ptr(), B, cats, classes)
+    return idx
+
+
+def uniform(shape, device, seed: int, offset: int = 0) -> torch.Tensor:
+    out = torch.empty(shape, device=device, dtype=torch.float32)
+    call("hulc2_philox_uniform", out.data_ptr(), out.numel(), seed, offset)
+    return out
+
+
+def dropout_mask(shape, p: float, device, seed: int, offset: int = 0) -> torch.Tensor:
+    out = torch.empty(shape, device=device, dtype=torch.uint8)
+    call("hulc2_dropout_mask", out.data_ptr(), out.numel(), p, seed, offset)
+    return out
+
+
+# ----------------------------------------------------------------------------- decoder recurrence
+class RNNDecoderFunction(torch.autograd.Function):
+    """2-layer Elman ReLU RNN over x_t = [plan | emb_t | goal] (logistic_decoder_rnn.py:262-268, rnn.py:5-14).
+    plan and goal are constant over time, so W_ih x_t splits into a per-window base term and a per-step
+    embedding term (same algebra, 32x fewer FLOPs than materialising [B,S,1120]).  Returns time-major
+    hidden states of the last layer [S,B,H] and h_n [2,B,H]."""
+
+    @staticmethod
+    def forward(ctx, plan, emb, goal, h0, wi0, wh0, bi0, bh0, wi1, wh1, bi1, bh1):
+        plan, goal = _f32(plan).contiguous(), _f32(goal).contiguous()
+        B, S, Es = emb.shape
+        P, G = plan.shape[1], goal.shape[1]
+        H = wh0.shape[0]
+        In = wi0.shape[1]
+        assert In == P + Es + G
+        dev = plan.device
+        embT = torch.empty(S, B, Es, device=dev, dtype=torch.float32)
+        assert emb.stride(2) == 1 and emb.stride(0) == S * emb.stride(1)
+        call("hulc2_transpose01", emb.data_ptr(), emb.stride(1), embT.data_ptr(), Es, B, S, Es, 0)
+        bsum0 = torch.empty(H, device=dev, dtype=torch.float32)
+        bsum1 = torch.empty(H, device=dev, dtype=torch.float32)
+        for bs, bi, bh in ((bsum0, bi0, bh0), (bsum1, bi1, bh1)):
+            call("hulc2_copy2d", bi.data_ptr(), H, bs.data_ptr(), H, 1, H, 0)
+            call("hulc2_axpy", bh.data_ptr(), bs.data_ptr(), H, 1.0)
+        base = torch.empty(B, H, device=dev, dtype=torch.float32)
+        gemm(B, H, P, plan, P, 1, wi0, In, 1, base, H, bias=bsum0)
+        gemm(B, H, G, goal, G, 1, wi0, In, 1, base, H, b_off=P + Es, accumulate=True)
+        pre = torch.empty(S, B, H, device=dev, dtype=torch.float32)
+        call("hulc2_copy2d", base.data_ptr(), 0, pre.data_ptr(), B * H, S, B * H, 0)
+        gemm(S * B, H, Es, embT, Es, 1, wi0, In, 1, pre, H, b_off=P, accumulate=True)
+        H0 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
+        h00 = h0[0].contiguous() if h0 is not None else None
+        h01 = h0[1].contiguous() if h0 is not None else None
+        call("hulc2_rnn_relu_fwd", pre.data_ptr(), wh0.data_ptr(), _p(h00), H0.data_ptr(), S, B, H, _lib_precision())
+        gemm(S * B, H, H, H0, H, 1, wi1, H, 1, pre, H, bias=bsum1)
+        H1 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
+        call("hulc2_rnn_relu_fwd", pre.data_ptr(), wh1.data_ptr(), _p(h01), H1.data_ptr(), S, B, H, _lib_precision())
+        hn = torch.empty(2, B, H, device=dev, dtype=torch.float32)
+        call("hulc2_copy2d", H0.data_ptr() + 4 * (S - 1) * B * H, B * H, hn.data_ptr(), B * H, 1, B * H, 0)
+        call("hulc2_copy2d", H1.data_ptr() + 4 * (S - 1) * B * H, B * H, hn.data_ptr() + 4 * B * H, B * H, 1, B * H, 0)
+        ctx.save_for_backward(plan, embT, goal, H0, H1, wi0, wh0, wi1, wh1, h00 if h00 is not None else plan.new_empty(0),
+                              h01 if h01 is not None else plan.new_empty(0))
+        ctx.dims = (B, S, Es, P, G, H, In)
+        ctx.has_h0 = h0 is not None
+        ctx.mark_non_differentiable(hn)
+        return H1, hn
+
+    @staticmethod
+    def backward(ctx, dH1, _dhn):
+        plan, embT, goal, H0, H1, wi0, wh0, wi1, wh1, h00, h01 = ctx.saved_tensors
+        B, S, Es, P, G, H, In = ctx.dims
+        dev = plan.device
+        prec = _lib_precision()
+        step = B * H
+        dH1 = dH1.contiguous()
+        dz1 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
+        call("hulc2_copy2d", dH1.data_ptr(), step, dz1.data_ptr(), step, S, step, 0)
+        call("hulc2_rnn_relu_bwd", dz1.data_ptr(), wh1.data_ptr(), H1.data_ptr(), None, S, B, H, prec)
+        dwh1 = torch.empty_like(wh1)
+        if S > 1:
+            gemm(H, H, (S - 1) * B, dz1, 1, H, H1, 1, H, dwh1, H, a_off=step)
+        else:
+            call("hulc2_fill", dwh1.data_ptr(), dwh1.numel(), 0.0)
+        if ctx.has_h0:
+            gemm(H, H, B, dz1, 1, H, h01, 1, H, dwh1, H, accumulate=True)
+        dwi1 = torch.empty_like(wi1)
+        gemm(H, H, S * B, dz1, 1, H, H0, 1, H, dwi1, H)
+        db1 = torch.empty(H, device=dev, dtype=torch.float32)
+        colsum(dz1, H, S * B, H, db1)
+        dz0 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
+        gemm(S * B, H, H, dz1, H, 1, wi1, 1, H, dz0, H)                      # dH0 = dz1 W_ih1
+        call("hulc2_rnn_relu_bwd", dz0.data_ptr(), wh0.data_ptr(), H0.data_ptr(), None, S, B, H, prec)
+        dwh0 = torch.empty_like(wh0)
+        if S > 1:
+            gemm(H, H, (S - 1) * B, dz0, 1, H, H0, 1, H, dwh0, H, a_off=step)
+        else:
+            call("hulc2_fill", dwh0.data_ptr(), dwh0.numel(), 0.0)
+        if ctx.has_h0:
+            gemm(H, H, B, dz0, 1, H, h00, 1, H, dwh0, H, accumulate=True)
+        db0 = torch.empty(H, device=dev, dtype=torch.float32)
+        colsum(dz0, H, S * B, H, db0)
+        dzsum = torch.empty(B, H, device=dev, dtype=torch.float32)
+        colsum(dz0, B * H, S, B * H, dzsum)                                  # sum over time
+        dwi0 = torch.empty_like(wi0)
+        gemm(H, P, B, dzsum, 1, H, plan, 1, P, dwi0, In)
+        gemm(H, Es, S * B, dz0, 1, H, embT, 1, Es, dwi0, In, c_off=P)
+        gemm(H, G, B, dzsum, 1, H, goal, 1, G, dwi0, In, c_off=P + Es)
+        dplan = dgoal = demb = None
+        if ctx.needs_input_grad[0]:
+            dplan = torch.empty(B, P, device=dev, dtype=torch.float32)
+            gemm(B, P, H, dzsum, H, 1, wi0, 1, In, dplan, P)
+        if ctx.needs_input_grad[2]:
+            dgoal = torch.empty(B, G, device=dev, dtype=torch.float32)
+            gemm(B, G, H, dzsum, H, 1, wi0, 1, In, dgoal, G, b_off=P + Es)
+        if ctx.needs_input_grad[1]:
+            dembT = torch.empty(S, B, Es, device=dev, dtype=torch.float32)
+            gemm(S * B, Es, H, dz0, H, 1, wi0, 1, In, dembT, Es, b_off=P)
+            demb = torch.empty(B, S, Es, device=dev, dtype=torch.float32)
+            call("hulc2_transpose01", dembT.data_ptr(), Es, demb.data_ptr(), Es, S, B, Es, 0)
+        return (dplan, demb, dgoal, None, dwi0, dwh0, db0, db0.clone(), dwi1, dwh1, db1, db1.clone())
+
+
+def _lib_precision() -> int:
+    return _precision
+
+
+# ----------------------------------------------------------------------------- heads + logistic-mixture loss
+HEAD_LD = 184  # 3*A*M + 2 = 182 columns, row-padded to 16 bytes
+
+
+def heads_forward(Hs, wp, bp, wm, bm, wsc, bsc, wg, bg) -> torch.Tensor:
+    """Four nn.Linear heads (logistic_decoder_rnn.py:269-274) into one [rows, 184] buffer
+    [logit_probs | means | log_scales | gripper]."""
+    rows, H = Hs.shape[0] * Hs.shape[1], Hs.shape[2]
+    AM = wp.shape[0]
+    heads = torch.empty(rows, HEAD_LD, device=Hs.device, dtype=torch.float32)
+    for W, b, off in ((wp, bp, 0), (wm, bm, AM), (wsc, bsc, 2 * AM)):
+        gemm(rows, AM, H, Hs, H, 1, W, H, 1, heads, HEAD_LD, c_off=off, bias=b)
+    if wg is not None:
+        gemm(rows, 2, H, Hs, H, 1, wg, H, 1, heads, HEAD_LD, c_off=3 * AM, bias=bg)
+    return heads
+
+
+class DecoderLossFunction(torch.autograd.Function):
+    """heads + discretised logistic-mixture NLL + gripper cross-entropy (logistic_decoder_rnn.py:133-152,181-228).
+    Hs is time-major [S,B,H]; actions [B,S,A+1] (already in the tcp frame)."""
+
+    @staticmethod
+    def forward(ctx, Hs, actions, amin, amax, cfg, wp, bp, wm, bm, wsc, bsc, wg, bg):
+        Hs = _f32(Hs).contiguous()
+        S, B, H = Hs.shape
+        A, M, num_classes, ls_min, alpha = cfg
+        heads = heads_forward(Hs, wp, bp, wm, bm, wsc, bsc, wg, bg)
+        out = torch.empty(3, device=Hs.device, dtype=torch.float32)
+        ws = workspace(Hs.device)
+        actions = _f32(actions).contiguous()
+        call("hulc2_logistic_loss_fwd", heads.data_ptr(), HEAD_LD, actions.data_ptr(), amin.data_ptr(), amax.data_ptr(),
+             out.data_ptr(), B, S, A, M, num_classes, ls_min, alpha, 1, ws.data_ptr(), ws.numel())
+        ctx.save_for_backward(Hs, heads, actions, amin, amax, wp, wm, wsc, wg)
+        ctx.cfg = cfg
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        Hs, heads, actions, amin, amax, wp, wm, wsc, wg = ctx.saved_tensors
+        S, B, H = Hs.shape
+        A, M, num_classes, ls_min, alpha = ctx.cfg
+        AM = A * M
+        rows = S * B
+        dev = Hs.device
+        g = g.contiguous()
+        dheads = torch.empty_like(heads)
+        call("hulc2_logistic_loss_bwd", heads.data_ptr(), HEAD_LD, actions.data_ptr(), amin.data_ptr(), amax.data_ptr(),
+             g.data_ptr(), dheads.data_ptr(), B, S, A, M, num_classes, ls_min, alpha, 1)
+        dbias = torch.empty(3 * AM + 2, device=dev, dtype=torch.float32)
+        colsum(dheads, HEAD_LD, rows, 3 * AM + 2, dbias)
+        dH = torch.empty(S, B, H, device=dev, dtype=torch.float32)
+        wgrads = []
+        for i, (W, n) in enumerate(((wp, AM), (wm, AM), (wsc, AM), (wg, 2))):
+            off = i * AM
+            dW = torch.empty_like(W)
+            gemm(n, H, rows, dheads, 1, HEAD_LD, Hs, 1, H, dW, H, a_off=off)
+            wgrads.append(dW)
+            gemm(rows, H, n, dheads, HEAD_LD, 1, W, 1, H, dH, H, a_off=off, accumulate=(i > 0))
+        return (dH, None, None, None, None, wgrads[0], dbias[0:AM], wgrads[1], dbias[AM : 2 * AM], wgrads[2],
+                dbias[2 * AM : 3 * AM], wgrads[3], dbias[3 * AM :])
+
+
+def heads_unpack(heads, B, S, A, M, ls_min, time_major=True):
+    dev = heads.device
+    lp = torch.empty(B, S, A, M, device=dev, dtype=torch.float32)
+    ls = torch.empty(B, S, A, M, device=dev, dtype=torch.float32)
+    mu = torch.empty(B, S, A, M, device=dev, dtype=torch.float32)
+    gr = torch.empty(B, S, 2, device=dev, dtype=torch.float32)
+    call("hulc2_heads_unpack", heads.data_ptr(), HEAD_LD, lp.data_ptr(), ls.data_ptr(), mu.data_ptr(), gr.data_ptr(), B, S, A, M,
+         ls_min, int(time_major))
+    return lp, ls, mu, gr
+
+
+def heads_pack(lp, ls, mu, gr) -> torch.Tensor:
+    """[B,S,A,M] tensors -> batch-major fused heads buffer (for the public _loss/_sample API)."""
+    B, S, A, M = lp.shape
+    AM = A * M
+    heads = torch.empty(B * S, HEAD_LD, device=lp.device, dtype=torch.float32)
+    for t, off in ((lp, 0), (mu, AM), (ls, 2 * AM)):
+        t = _f32(t).contiguous()
+        call("hulc2_copy2d", t.data_ptr(), AM, heads.data_ptr() + 4 * off, HEAD_LD, B * S, AM, 0)
+    if gr is not None:
+        gr = _f32(gr).contiguous()
+        call("hulc2_copy2d", gr.data_ptr(), 2, heads.data_ptr() + 4 * 3 * AM, HEAD_LD, B * S, 2, 0)
+    return heads
+
+
+class LogisticLossFunction(torch.autograd.Function):
+    """Public ``_loss`` on separate [B,S,A,M] tensors (logistic_decoder_rnn.py:133-152)."""
+
+    @staticmethod
+    def forward(ctx, lp, ls, mu, gr, actions, amin, amax, cfg):
+        B, S, A, M = lp.shape
+        _, _, num_classes, ls_min, alpha = cfg
+        heads = heads_pack(lp, ls, mu, gr)
+        out = torch.empty(3, device=lp.device, dtype=torch.float32)
+        ws = workspace(lp.device)
+        actions = _f32(actions).contiguous()
+        call("hulc2_logistic_loss_fwd", heads.data_ptr(), HEAD_LD, actions.data_ptr(), amin.data_ptr(), amax.data_ptr(),
+             out.data_ptr(), B, S, A, M, num_classes, ls_min, alpha, 0, ws.data_ptr(), ws.numel())
+        ctx.save_for_backward(heads, actions, amin, amax)
+        ctx.cfg, ctx.dims = cfg, (B, S, A, M)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        heads, actions, amin, amax = ctx.saved_tensors
+        B, S, A, M = ctx.dims
+        _, _, num_classes, ls_min, alpha = ctx.cfg
+        dheads = torch.empty_like(heads)
+        call("hulc2_logistic_loss_bwd", heads.data_ptr(), HEAD_LD, actions.data_ptr(), amin.data_ptr(), amax.data_ptr(),
+             g.contiguous().data_ptr(), dheads.data_ptr(), B, S, A, M, num_classes, ls_min, alpha, 0)
+        AM = A * M
+        outs = []
+        for off, n, shape in ((0, AM, (B, S, A, M)), (2 * AM, AM, (B, S, A, M)), (AM, AM, (B, S, A, M)), (3 * AM, 2, (B, S, 2))):
+            t = torch.empty(B * S, n, device=heads.device, dtype=torch.float32)
+            call("hulc2_copy2d", dheads.data_ptr() + 4 * off, HEAD_LD, t.data_ptr(), n, B * S, n, 0)
+            outs.append(t.view(shape))
+        return (outs[0], outs[1], outs[2], outs[3], None, None, None, None)
+
+
+def logistic_sample(heads, u1, u2, gripper_bounds, B, S, A, M, ls_min, time_major) -> torch.Tensor:
+    act = torch.empty(B, S, A + 1, device=heads.device, dtype=torch.float32)
+    call("hulc2_logistic_sample", heads.data_ptr(), HEAD_LD, _f32(u1).contiguous().data_ptr(), _f32(u2).contiguous().data_ptr(),
+         gripper_bounds.data_ptr(), act.data_ptr(), B, S, A, M, ls_min, int(time_major))
+    return act
+
+
+def world_to_tcp(actions: torch.Tensor, robot_obs: torch.Tensor) -> torch.Tensor:
+    a, r = _f32(actions).contiguous(), _f32(robot_obs).contiguous()
+    out = torch.empty_like(a)
+    call("hulc2_world_to_tcp", a.data_ptr(), r.data_ptr(), r.shape[-1], out.data_ptr(), a.numel() // 7)
+    return out
+
+
+def tcp_to_world(actions: torch.Tensor, robot_obs: torch.Tensor) -> torch.Tensor:
+    a, r = _f32(actions).contiguous(), _f32(robot_obs).contiguous()
+    out = torch.empty_like(a)
+    call("hulc2_tcp_to_world", a.data_ptr(), r.data_ptr(), r.shape[-1], out.data_ptr(), a.numel() // 7)
+    return out
+
+
+# ----------------------------------------------------------------------------- InfoNCE
+class InfoNCEFunction(torch.autograd.Function):
+    """hulc2.py:494-508 on projected features; ``use`` = uint8 row mask (static shapes, no host sync)."""
+
+    @staticmethod
+    def forward(ctx, img, txt, logit_scale, use):
+        img, txt = _f32(img).contiguous(), _f32(txt).contiguous()
+        B, D = img.shape
+        loss = torch.empty(1, device=img.device, dtype=torch.float32)
+        ws = workspace(img.device)
+        call("hulc2_infonce_fwd", img.data_ptr(), txt.data_ptr(), _p(use), logit_scale.data_ptr(), loss.data_ptr(), B, D,
+             ws.data_ptr(), ws.numel())
+        ctx.save_for_backward(img, txt, logit_scale)
+        ctx.use = use
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        img, txt, logit_scale = ctx.saved_tensors
+        B, D = img.shape
+        dimg, dtxt = torch.empty_like(img), torch.empty_like(txt)
+        dls = torch.zeros((), device=img.device, dtype=torch.float32)
+        ws = workspace(img.device)
+        call("hulc2_infonce_bwd", img.data_ptr(), txt.data_ptr(), _p(ctx.use), logit_scale.data_ptr(), g.contiguous().data_ptr(),
+             dimg.data_ptr(), dtxt.data_ptr(), dls.data_ptr(), B, D, ws.data_ptr(), ws.numel())
+        return dimg, dtxt, dls, None
+
+
+# ----------------------------------------------------------------------------- scalar combine
+class WeightedSumFunction(torch.autograd.Function):
+    """total = sum_i w_i * x_i for 0-d tensors (hulc2.py:243,426-430) without leaving the library."""
+
+    @staticmethod
+    def forward(ctx, weights, *xs):
+        out = torch.zeros((), device=xs[0].device, dtype=torch.float32)
+        for w, x in zip(weights, xs):
+            call("hulc2_axpy", x.contiguous().data_ptr(), out.data_ptr(), 1, float(w))
+        ctx.weights = weights
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        outs = []
+        for w in ctx.weights:
+            t = torch.zeros((), device=g.device, dtype=torch.float32)
+            call("hulc2_axpy", g.contiguous().data_ptr(), t.data_ptr(), 1, float(w))
+            outs.append(t)
+        return (None, *outs)
+
+
+def weighted_sum(weights, xs):
+    return WeightedSumFunction.apply(tuple(float(w) for w in weights), *xs)
+
+
+class ConcatColsFunction(torch.autograd.Function):
+    """[a | b] along the feature axis for 2-D row-strided operands (plan_proposal_net.py:43)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a2, b2 = _rows2d(_f32(a)), _rows2d(_f32(b))
+        M, Ka, Kb = a2.shape[0], a2.shape[1], b2.shape[1]
+        out = torch.empty(M, Ka + Kb, device=a.device, dtype=torch.float32)
+        call("hulc2_copy2d", a2.data_ptr(), _ld(a2), out.data_ptr(), Ka + Kb, M, Ka, 0)
+        call("hulc2_copy2d", b2.data_ptr(), _ld(b2), out.data_ptr() + 4 * Ka, Ka + Kb, M, Kb, 0)
+        ctx.dims = (M, Ka, Kb)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        M, Ka, Kb = ctx.dims
+        dout = dout.contiguous()
+        da = torch.empty(M, Ka, device=dout.device, dtype=torch.float32)
+        db = torch.empty(M, Kb, device=dout.device, dtype=torch.float32)
+        call("hulc2_copy2d", dout.data_ptr(), Ka + Kb, da.data_ptr(), Ka, M, Ka, 0)
+        call("hulc2_copy2d", dout.data_ptr() + 4 * Ka, Ka + Kb, db.data_ptr(), Kb, M, Kb, 0)
+        return da, db
+
+
+def concat_cols(a, b):
+    return ConcatColsFunction.apply(a, b)

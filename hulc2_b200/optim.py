@@ -1,0 +1,134 @@
+"""Fused Adam over a flat parameter arena (hulc2.py:185-198, conf/model/optimizer/adam.yaml).
+
+``torch.optim.Adam`` semantics (amsgrad=False, maximize=False), but parameters, gradients and both
+moments live in four contiguous fp32 arenas so one kernel launch updates all 47 M parameters and a
+data-parallel reducer can all-reduce contiguous gradient buckets.  ``param.data`` / ``param.grad``
+become views into the arenas; state_dict names/shapes of the module are unchanged.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List
+
+import torch
+
+from ._lib import call
+
+_ALIGN = 4  # elements (16 bytes)
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params: Iterable, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self._arenas: List[Dict] = []
+        self.grad_scale = 1.0  # multiplied into gradients inside the kernel (e.g. 1/world_size)
+        for group in self.param_groups:
+            self._arenas.append(self._build_arena(group))
+
+    # ------------------------------------------------------------------ arena
+    @staticmethod
+    def _build_arena(group) -> Dict:
+        ps = [p for p in group["params"] if p.requires_grad]
+        if not ps:
+            return {"params": [], "n": 0}
+        dev = ps[0].device
+        offs, n = [], 0
+        for p in ps:
+            if p.dtype != torch.float32:
+                raise TypeError("FusedAdam keeps fp32 master parameters")
+            offs.append(n)
+            n += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        arena = {"params": ps, "offs": offs, "n": n}
+        for name in ("p", "g", "m", "v"):
+            arena[name] = torch.zeros(n, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for p, o in zip(ps, offs):
+                view = arena["p"][o : o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+        arena["step"] = 0
+        return arena
+
+    def _attach_grads(self, arena) -> None:
+        """Make every ``param.grad`` the matching view of the gradient arena (copying stray grads in)."""
+        for p, o in zip(arena["params"], arena["offs"]):
+            view = arena["g"][o : o + p.numel()].view(p.shape)
+            if p.grad is None:
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                g = p.grad.contiguous()
+                call("hulc2_copy2d", g.data_ptr(), g.numel(), view.data_ptr(), g.numel(), 1, g.numel(), 0)
+                p.grad = view
+
+    def attach(self) -> None:
+        for a in self._arenas:
+            if a["n"]:
+                self._attach_grads(a)
+
+    def grad_arenas(self) -> List[torch.Tensor]:
+        return [a["g"] for a in self._arenas if a["n"]]
+
+    # ------------------------------------------------------------------ optimizer API
+    def zero_grad(self, set_to_none: bool = False) -> None:  # noqa: D401
+        """Zero-fills the gradient arena and keeps ``param.grad`` attached (``set_to_none`` is ignored so
+        the next backward accumulates in place into contiguous buckets)."""
+        for a in self._arenas:
+            if a["n"]:
+                call("hulc2_fill", a["g"].data_ptr(), a["n"], 0.0)
+                for p, o in zip(a["params"], a["offs"]):
+                    view = a["g"][o : o + p.numel()].view(p.shape)
+                    if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                        p.grad = view
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group, a in zip(self.param_groups, self._arenas):
+            if not a["n"]:
+                continue
+            self._attach_grads(a)
+            a["step"] += 1
+            b1, b2 = group["betas"]
+            call("hulc2_adam_step", a["p"].data_ptr(), a["g"].data_ptr(), a["m"].data_ptr(), a["v"].data_ptr(), a["n"],
+                 float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(a["step"]),
+                 float(self.grad_scale))
+        return loss
+
+    # ------------------------------------------------------------------ checkpointing (torch.optim.Adam-compatible layout)
+    def state_dict(self):
+        state, idx = {}, 0
+        groups = []
+        for group, a in zip(self.param_groups, self._arenas):
+            ids = []
+            for p in group["params"]:
+                ids.append(idx)
+                if a["n"] and any(p is q for q in a["params"]):
+                    o = a["offs"][[i for i, q in enumerate(a["params"]) if q is p][0]]
+                    state[idx] = {
+                        "step": torch.tensor(float(a["step"])),
+                        "exp_avg": a["m"][o : o + p.numel()].view(p.shape).clone(),
+                        "exp_avg_sq": a["v"][o : o + p.numel()].view(p.shape).clone(),
+                    }
+                idx += 1
+            g = {k: v for k, v in group.items() if k != "params"}
+            g["params"] = ids
+            groups.append(g)
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        idx = 0
+        for group, a, g_sd in zip(self.param_groups, self._arenas, sd["param_groups"]):
+            for k, v in g_sd.items():
+                if k != "params":
+                    group[k] = v
+            for p in group["params"]:
+                st = sd["state"].get(idx, sd["state"].get(str(idx)))
+                if st is not None and a["n"]:
+                    o = a["offs"][[i for i, q in enumerate(a["params"]) if q is p][0]]
+                    a["m"][o : o + p.numel()].view(p.shape).copy_(st["exp_avg"])
+                    a["v"][o : o + p.numel()].view(p.shape).copy_(st["exp_avg_sq"])
+                    a["step"] = int(float(st["step"]))
+                idx += 1

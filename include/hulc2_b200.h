@@ -1,0 +1,197 @@
+/* hulc2_b200 -- C-ABI of the B200-native HULC++ low-level policy step.
+ *
+ * The reference (mees/hulc2) has no native interface for this path: its hot path is ~1.3 kLoC of
+ * PyTorch nn.Modules.  Each entry point below therefore replaces the body of a
+ * reference Python function (cited as file:line relative to the reference root); the binding a
+ * maintainer adds is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions (SURVEY.md section 8b "C-ABI layer"):
+ *  - all pointers are DEVICE pointers borrowed for the duration of the call; fp32 unless noted;
+ *  - every call is asynchronous on `stream`, never synchronises, never allocates; scratch memory is
+ *    a caller-provided workspace;
+ *  - returns 0 on success, a negative HULC2_E* code otherwise (hulc2_last_error() gives the text);
+ *  - `precision`: 0 = fp32 CUDA-core path (1e-5 parity), 1 = bf16 tcgen05 tensor-core path.
+ */
+#ifndef HULC2_B200_H
+#define HULC2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* hulc2_stream_t; /* == cudaStream_t */
+
+const char* hulc2_last_error(void);
+int hulc2_version(void);
+/* 1 when the running device is sm_100 (B200) and the tcgen05 path is usable. */
+int hulc2_device_supports_tcgen05(void);
+
+/* ------------------------------------------------------------------ dense contractions
+ * C[m,n] = epilogue( alpha * sum_k A(m,k) * B(n,k) ),  A(m,k) = A[R(m) + k*a_ks], B(n,k) = B[n*b_rs + k*b_ks]
+ * R(m) = m*a_rs, or (m / a_inner)*a_rs_outer + (m % a_inner)*a_rs_inner when a_inner > 0 (same for C rows).
+ * epilogue: +bias[n]; +add[m,n]; +C (accumulate); relu; zero where mask[m,n] <= 0; dropout keep (u8) * keep_scale.
+ * Serves nn.Linear forward / input-grad / weight-grad everywhere on the path, e.g.
+ * plan_proposal_net.py:42-47, goal_encoders.py:29-34, logistic_decoder_rnn.py:269-274. */
+typedef struct {
+  int M, N, K;
+  const float* A; long long a_rs, a_ks; int a_inner; long long a_rs_outer, a_rs_inner;
+  const float* B; long long b_rs, b_ks;
+  float* C; long long ldc; int c_inner; long long c_rs_outer, c_rs_inner;
+  const float* bias;
+  const float* add; long long ld_add;
+  const float* mask; long long ld_mask;
+  const unsigned char* keep; long long ld_keep; float keep_scale;
+  int relu, accumulate;
+  float alpha;
+  int precision;
+  void* workspace; long long workspace_bytes;
+} hulc2_gemm_args;
+int hulc2_gemm(const hulc2_gemm_args* a, hulc2_stream_t stream);
+
+/* ------------------------------------------------------------------ convolutions (implicit GEMM)
+ * vision_network.py:38-48 and vision_network_gripper.py:11-26 (valid padding, square stride).
+ * Activations produced by this library are NHWC; the first conv reads the caller's NCHW frames.
+ *  fwd  : y[F,OH,OW,Cout] = relu?(conv(x,w)+bias);  x NCHW with w OIHW (in_nhwc=0) or x NHWC with w OHWI (in_nhwc=1)
+ *  wgrad: dw (same layout as w) (+)= sum_pixels dy^T im2col(x);   needs workspace for split-K
+ *  dgrad: dx[F,H,W,C] (NHWC) = gather(dy, w_hwoi[KH,KW,Cout,C]), zeroed where xmask <= 0 (xmask may be null) */
+typedef struct {
+  int F, C, H, W, Cout, KH, KW, stride, in_nhwc;
+  const float* x; const float* w; const float* bias; float* y; int relu;
+  const float* dy; float* dw; float* dx; const float* xmask; int accumulate;
+  int precision;
+  void* workspace; long long workspace_bytes;
+} hulc2_conv_args;
+int hulc2_conv2d_fwd(const hulc2_conv_args* a, hulc2_stream_t stream);
+int hulc2_conv2d_wgrad(const hulc2_conv_args* a, hulc2_stream_t stream);
+int hulc2_conv2d_dgrad(const hulc2_conv_args* a, hulc2_stream_t stream);
+/* weight layout shuffles between the state_dict layout (OIHW) and the kernel layouts.
+ * dir 0: OIHW -> OHWI, 1: OHWI -> OIHW (accumulate optional), 2: OIHW -> HWOI */
+int hulc2_permute_conv_weight(const float* src, float* dst, int O, int I, int KH, int KW, int dir, int accumulate,
+                              hulc2_stream_t stream);
+
+/* ------------------------------------------------------------------ small data movement
+ * copy2d: dst[r*ldd + c] (+)= src[r*lds + c];  colsum: out[c] (+)= sum_r x[r*ld + c] (bias gradients);
+ * nhwc<->nchw per-frame transposes (nn.Flatten order of nature_cnn, vision_network_gripper.py:22-23). */
+int hulc2_copy2d(const float* src, long long lds, float* dst, long long ldd, long long rows, int cols, int accumulate,
+                 hulc2_stream_t stream);
+/* dst[d1, d0, :D2] (+)= src[(d0*D1 + d1)*src_ld + :D2]: batch-major [B,S,*] <-> time-major [S,B,*] row shuffle */
+int hulc2_transpose01(const float* src, long long src_ld, float* dst, long long dst_ld, int D0, int D1, int D2,
+                      int accumulate, hulc2_stream_t stream);
+int hulc2_fill(float* dst, long long n, float value, hulc2_stream_t stream);
+int hulc2_axpy(const float* x, float* y, long long n, float a, hulc2_stream_t stream); /* y += a*x */
+int hulc2_colsum(const float* x, long long ld, long long rows, int cols, float* out, int accumulate, void* workspace,
+                 long long workspace_bytes, hulc2_stream_t stream);
+int hulc2_relu_mask(const float* dy, const float* y, float* dz, long long n, hulc2_stream_t stream);
+int hulc2_nhwc_to_nchw(const float* src, float* dst, int F, int HW, int C, hulc2_stream_t stream);
+int hulc2_nchw_to_nhwc(const float* src, float* dst, int F, int HW, int C, const float* mask, hulc2_stream_t stream);
+
+/* ------------------------------------------------------------------ SpatialSoftmax  (vision_network.py:100-108)
+ * x NHWC [F,HW,C]; out[f, 2c] = sum_i x_map[i] p_i, out[f, 2c+1] = sum_i y_map[i] p_i, p = softmax(x/temperature)
+ * bwd: dx[f,i,c] = p_i/T * (gx (x_map_i - Ex) + gy (y_map_i - Ey)), zeroed where x <= 0 when relu_mask != 0. */
+int hulc2_spatial_softmax_fwd(const float* x, const float* x_map, const float* y_map, const float* temperature,
+                              float* out, int F, int HW, int C, hulc2_stream_t stream);
+int hulc2_spatial_softmax_bwd(const float* x, const float* x_map, const float* y_map, const float* temperature,
+                              const float* out, const float* dout, float* dx, float* dtemperature, int F, int HW, int C,
+                              int relu_mask, hulc2_stream_t stream);
+
+/* ------------------------------------------------------------------ LayerNorm (+ residual + dropout)
+ * t = x + keep*scale*res (res/keep optional); y = (t-mean)/sqrt(var+eps)*gamma + beta   (eps 1e-5 everywhere)
+ * bwd: dx (= grad of t), dres = dx*keep*scale (optional), dgamma/dbeta accumulated atomically. */
+int hulc2_layernorm_fwd(const float* x, long long ldx, const float* res, long long ldr, const unsigned char* keep,
+                        float keep_scale, const float* gamma, const float* beta, float* y, long long ldy, float* tsum,
+                        float* mean, float* rstd, long long rows, int D, float eps, hulc2_stream_t stream);
+int hulc2_layernorm_bwd(const float* dy, long long ldy, const float* t, long long ldt, const float* gamma,
+                        const float* mean, const float* rstd, float* dx, long long lddx, float* dres,
+                        const unsigned char* keep, float keep_scale, float* dgamma, float* dbeta, long long rows, int D,
+                        hulc2_stream_t stream);
+
+/* ------------------------------------------------------------------ plan-recognition transformer pieces
+ * plan_recognition_net.py:125-148 + torch nn.TransformerEncoderLayer (post-LN, ReLU, 8 heads x 16, S <= 32).
+ * add_pos: x[b,s,:] = (emb[b,s,:] + pos[s,:]) * keep*scale.   attention: qkv [B*S, 3E] packed [q|k|v],
+ * probabilities p [B,H,S,S] are saved (pre-dropout) for the backward.   mean_seq: out[b,:] = mean_s x[b,s,:]. */
+int hulc2_add_pos_fwd(const float* emb, const float* pos, const unsigned char* keep, float keep_scale, float* out, int B,
+                      int S, int E, hulc2_stream_t stream);
+int hulc2_add_pos_bwd(const float* dout, const unsigned char* keep, float keep_scale, float* demb, float* dpos, int B,
+                      int S, int E, hulc2_stream_t stream);
+int hulc2_attention_fwd(const float* qkv, const unsigned char* keep, float keep_scale, float* out, float* probs, int B,
+                        int S, int H, int Dh, hulc2_stream_t stream);
+int hulc2_attention_bwd(const float* qkv, const float* probs, const unsigned char* keep, float keep_scale,
+                        const float* dout, float* dqkv, int B, int S, int H, int Dh, hulc2_stream_t stream);
+int hulc2_mean_seq_fwd(const float* x, float* out, int B, int S, int E, hulc2_stream_t stream);
+int hulc2_mean_seq_bwd(const float* dout, float* dx, int B, int S, int E, hulc2_stream_t stream);
+
+/* ------------------------------------------------------------------ latent plan  (distributions.py:15-60, hulc2.py:444-466)
+ * kl: loss = beta*(alpha*KL(sg(pr)||pp) + (1-alpha)*KL(pr||sg(pp))), categorical over `classes`, summed over
+ * categories, mean over B.  Gradients are written scaled by *gout (device scalar, may be null = 1).
+ * onehot: plan[b, cat*classes + idx[b,cat]] = 1.  st_bwd: straight-through gradient of rsample() w.r.t. logits.
+ * sample: idx[b,cat] = inverse-CDF draw from softmax(logits) with supplied uniform u[b,cat]. */
+int hulc2_kl_fwd(const float* pp_logits, const float* pr_logits, float* loss, int B, int cats, int classes, float alpha,
+                 float beta, hulc2_stream_t stream);
+int hulc2_kl_bwd(const float* pp_logits, const float* pr_logits, const float* gout, float* dpp, float* dpr, int B,
+                 int cats, int classes, float alpha, float beta, hulc2_stream_t stream);
+int hulc2_onehot_fwd(const long long* idx, float* plan, int B, int cats, int classes, hulc2_stream_t stream);
+int hulc2_st_onehot_bwd(const float* logits, const float* dplan, float* dlogits, int B, int cats, int classes,
+                        hulc2_stream_t stream);
+int hulc2_categorical_sample(const float* logits, const float* u, long long* idx, int B, int cats, int classes,
+                             hulc2_stream_t stream);
+
+/* ------------------------------------------------------------------ logistic-mixture decoder head
+ * heads [rows, ld] = [logit_probs(A*M) | means(A*M) | log_scales(A*M, unclamped) | gripper logits(2)] per row,
+ * rows are TIME-MAJOR (row = s*B + b); actions [B,S,A+1] batch-major.
+ * loss (logistic_decoder_rnn.py:133-152,181-228): out[0] = total, out[1] = logistic NLL, out[2] = gripper CE.
+ * bwd writes d(heads) scaled by *gout/(B*S).   sample (:231-255): uniforms u1 [B,S,A,M], u2 [B,S,A] -> act [B,S,A+1]. */
+int hulc2_logistic_loss_fwd(const float* heads, long long ld, const float* actions, const float* act_min,
+                            const float* act_max, float* out, int B, int S, int A, int M, int num_classes,
+                            float log_scale_min, float gripper_alpha, int time_major, void* workspace,
+                            long long workspace_bytes, hulc2_stream_t stream);
+int hulc2_logistic_loss_bwd(const float* heads, long long ld, const float* actions, const float* act_min,
+                            const float* act_max, const float* gout, float* dheads, int B, int S, int A, int M,
+                            int num_classes, float log_scale_min, float gripper_alpha, int time_major,
+                            hulc2_stream_t stream);
+int hulc2_logistic_sample(const float* heads, long long ld, const float* u1, const float* u2,
+                          const float* gripper_bounds, float* act, int B, int S, int A, int M, float log_scale_min,
+                          int time_major, hulc2_stream_t stream);
+/* splits the fused heads buffer into the reference's forward() outputs (logistic_decoder_rnn.py:275-284) */
+int hulc2_heads_unpack(const float* heads, long long ld, float* logit_probs, float* log_scales, float* means,
+                       float* gripper, int B, int S, int A, int M, float log_scale_min, int time_major,
+                       hulc2_stream_t stream);
+
+/* ------------------------------------------------------------------ tcp <-> world frames (gripper_control.py:16-63) */
+int hulc2_world_to_tcp(const float* action, const float* robot_obs, int robot_dim, float* out, long long rows,
+                       hulc2_stream_t stream);
+int hulc2_tcp_to_world(const float* action, const float* robot_obs, int robot_dim, float* out, long long rows,
+                       hulc2_stream_t stream);
+
+/* ------------------------------------------------------------------ InfoNCE (hulc2.py:472-508)
+ * img,txt [B,D] projected features (un-normalised); use [B] u8 row mask (null = all); logit_scale device scalar.
+ * fwd: loss[0]; saves nothing (bwd recomputes).  workspace >= (2*B*D + B*B + 4*B) floats. */
+int hulc2_infonce_fwd(const float* img, const float* txt, const unsigned char* use, const float* logit_scale,
+                      float* loss, int B, int D, void* workspace, long long workspace_bytes, hulc2_stream_t stream);
+int hulc2_infonce_bwd(const float* img, const float* txt, const unsigned char* use, const float* logit_scale,
+                      const float* gout, float* dimg, float* dtxt, float* dlogit_scale, int B, int D, void* workspace,
+                      long long workspace_bytes, hulc2_stream_t stream);
+
+/* ------------------------------------------------------------------ decoder recurrence (decoders/utils/rnn.py:5-14)
+ * Elman ReLU RNN layer over time-major buffers: h[t] = relu(pre[t] + h[t-1] W_hh^T), pre [S,B,H] already holds
+ * W_ih x_t + b_ih + b_hh.  bwd: dz[t] = (dh_out[t] + dz[t+1] W_hh) * (h[t] > 0), in place over dh (becomes dz). */
+int hulc2_rnn_relu_fwd(const float* pre, const float* w_hh, const float* h0, float* h, int S, int B, int H,
+                       int precision, hulc2_stream_t stream);
+int hulc2_rnn_relu_bwd(float* dh_inout, const float* w_hh, const float* h, float* dh0, int S, int B, int H,
+                       int precision, hulc2_stream_t stream);
+
+/* ------------------------------------------------------------------ optimizer + noise
+ * Adam (torch.optim.Adam semantics, conf/model/optimizer/adam.yaml): one launch over a flat arena. */
+int hulc2_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float grad_scale, hulc2_stream_t stream);
+/* Philox4x32-10 counter-based noise: uniforms in [0,1) / dropout keep masks with P(keep) = 1-p. */
+int hulc2_philox_uniform(float* out, long long n, unsigned long long seed, unsigned long long offset,
+                         hulc2_stream_t stream);
+int hulc2_dropout_mask(unsigned char* out, long long n, float p, unsigned long long seed, unsigned long long offset,
+                       hulc2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HULC2_B200_H */
