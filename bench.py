@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py -- HULC++ low-level policy train step on N B200s (BASELINE.json metric: train windows/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference --gpus N ...            # the reference algorithm on the host CPU (oracle port)
+
+A "step" = zero_grad -> Hulc2.training_step on {vis: B, lang: B} windows -> backward -> bucketed gradient
+all-reduce -> fused Adam, i.e. SURVEY.md 8d config 2 (B=64 per modality, window 32, static 200x200 +
+gripper 84x84, 7-dof actions, language as [B,384] embeddings, dropout 0.1 active).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+import torch  # noqa: E402
+
+WINDOW = 32
+FLOPS_PER_WINDOW_FWD_BWD = 13.01e9  # SURVEY.md 8d (torch FlopCounterMode on the reference graph)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="windows per modality per rank")
+    ap.add_argument("--precision", default=os.environ.get("HULC2_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--cpu-batch", type=int, default=8, help="windows per modality of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured (MEASURED_PEAKS.json, sustained)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_step_factory(B, hidden_size=2048):
+    from hulc2_b200._compat import instantiate
+    from hulc2_b200.config import hulc2_config
+    from hulc2_b200.synthetic import synthetic_batch
+    from oracle import hulc2_oracle as O
+
+    torch.manual_seed(0)
+    m = instantiate(hulc2_config(dropout_p=0.1, hidden_size=hidden_size))
+    names = {n for n, _ in m.named_parameters()}
+    P = {k: v.detach().clone().requires_grad_(k in names) for k, v in m.state_dict().items()}
+    cfg = hulc2_config(pkg="x", dropout_p=0.1, hidden_size=hidden_size)
+    batch = synthetic_batch(B, seed=1)
+    g = torch.Generator().manual_seed(3)
+    S, E, H, FF, p = WINDOW, 128, 8, 2048, 0.1
+    leaves = [v for v in P.values() if v.requires_grad]
+    opt = torch.optim.Adam(leaves, lr=2e-4)
+
+    def step():
+        noise = {}
+        for mod in batch:
+            masks = {"emb": torch.rand(B, S, E, generator=g) > p}
+            for i in range(2):
+                masks[f"attn{i}"] = torch.rand(B, H, S, S, generator=g) > p
+                masks[f"sa{i}"] = torch.rand(B, S, E, generator=g) > p
+                masks[f"ff1{i}"] = torch.rand(B, S, FF, generator=g) > p
+                masks[f"ff2{i}"] = torch.rand(B, S, E, generator=g) > p
+            noise[mod] = {"plan_idx": torch.randint(0, 32, (B, 32), generator=g), "masks": masks}
+        opt.zero_grad()
+        out = O.training_step(batch, noise, P, cfg)
+        out["loss"].backward()
+        opt.step()
+        return float(out["loss"])
+
+    return step
+
+
+def time_cpu(B, steps, warmup):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_factory(B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return 2 * B / dt, dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wps, dt, cores = time_cpu(args.cpu_batch, args.steps, args.warmup)
+    sample = f"oracle port of Hulc2.training_step+backward+Adam, fp32, {{vis:{args.cpu_batch}, lang:{args.cpu_batch}}} windows per step (bounded sample of the B={args.batch} workload), torch {torch.__version__}"
+    line = {
+        "impl": "reference", "metric": "train windows/sec", "value": wps, "unit": "windows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: Hulc2 policy train step, B=64/modality, window 32, static 200x200 + gripper 84x84, 7-dof",
+                   "windows_per_step_timed": 2 * args.cpu_batch},
+        "cpu_baseline": {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": wps, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- main arm
+def nbytes(x):
+    if isinstance(x, dict):
+        return sum(nbytes(v) for v in x.values())
+    return x.numel() * x.element_size() if isinstance(x, torch.Tensor) else 0
+
+
+def run_b200(args):
+    import torch.distributed as dist
+
+    from hulc2_b200 import _lib, ops
+    from hulc2_b200._compat import instantiate
+    from hulc2_b200.config import hulc2_config
+    from hulc2_b200.synthetic import synthetic_batch_fast, tree_map
+    from hulc2_b200.trainer import PolicyTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.set_precision(args.precision)
+    B = args.batch
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        wps, dt, cores = time_cpu(args.cpu_batch, 2, 1)
+        cpu = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
+               "sample": f"oracle port, fp32, {{vis:{args.cpu_batch}, lang:{args.cpu_batch}}} windows/step, 1 warm-up + 2 timed steps ({dt:.2f} s/step)"}
+
+    torch.manual_seed(0)
+    model = instantiate(hulc2_config(dropout_p=0.1)).to(dev).train()
+    trainer = PolicyTrainer(model)
+    batch = synthetic_batch_fast(B, seed=1 + rank, device=dev)
+    h2d = nbytes(batch)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        trainer.train_step(batch, i)
+    barrier()
+    l0 = _lib.load_library().hulc2_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for i in range(args.steps):
+            loss = trainer.train_step(batch, i)
+        e1.record()
+        torch.cuda.synchronize()
+    barrier()
+    launches = _lib.load_library().hulc2_launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    value = 2 * B * world / (ms * 1e-3)
+
+    # end-to-end: pinned host batch -> H2D inside the timed region -> step -> loss D2H
+    host = tree_map(lambda t: t.cpu().pin_memory(), batch)
+    trainer.train_step_from_host(host, 0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.e2e_steps):
+        trainer.train_step_from_host(host, i)
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.e2e_steps], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = 2 * B * world / (float(e2e_ms) * 1e-3)
+
+    # roofline of the dominant kernel: per-call CUDA-event timing over one extra step (outside the timed region)
+    roof = None
+    if rank == 0:
+        _lib.profile_begin()
+        trainer.train_step(batch, 0)
+        torch.cuda.synchronize()
+        recs = _lib.profile_end()
+        peaks = load_peaks()
+        top = max(recs.values(), key=lambda r: r["ms"]) if recs else None
+        total_ms = sum(r["ms"] for r in recs.values())
+        if top:
+            achieved = (top["flops"] / top["calls"]) / (top["ms"] / top["calls"] * 1e-3) / 1e12 if top["flops"] else 0.0
+            roof = {"bound": "tensor", "kernel": top["key"], "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
+                    "share_of_step": top["ms"] / total_ms if total_ms else None, "calls_per_step": top["calls"],
+                    "avg_ms": top["ms"] / top["calls"],
+                    "step_tflops": 2 * B * FLOPS_PER_WINDOW_FWD_BWD / (ms * 1e-3) / 1e12}
+            tops = sorted(recs.values(), key=lambda r: -r["ms"])[:8]
+            roof["top_kernels"] = [{"key": r["key"], "ms": round(r["ms"], 3), "calls": r["calls"]} for r in tops]
+
+    if rank == 0:
+        line = {
+            "metric": "train windows/sec", "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "configs[1]: Hulc2 policy train step (fwd+bwd+allreduce+Adam), B=64/modality/GPU, window 32, static 200x200 + gripper 84x84 RGB fp32, 7-dof, lang [B,384], dropout 0.1",
+                       "windows_per_step_per_gpu": 2 * B, "parallelism": f"dp{world}", "l2": "inputs (2.3 GB images/step) exceed the 126 MB L2",
+                       "precision": args.precision},
+            "clocks": clk.summary(), "gpu_launches": int(launches),
+            "e2e": {"value": e2e_val, "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+            "roofline": roof, "cpu_baseline": cpu, "loss": float(loss),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

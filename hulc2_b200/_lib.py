@@ -57,7 +57,7 @@ _SIGS = {
     "hulc2_conv2d_dgrad": [C.POINTER(ConvArgs)],
     "hulc2_permute_conv_weight": [P, P, I, I, I, I, I, I],
     "hulc2_copy2d": [P, LL, P, LL, LL, I, I],
-    "hulc2_transpose01": [P, LL, P, LL, I, I, I, I],
+    "hulc2_transpose01": [P, LL, LL, P, LL, I, I, I, I],
     "hulc2_fill": [P, LL, F],
     "hulc2_axpy": [P, P, LL, F],
     "hulc2_colsum": [P, LL, LL, I, P, I, P, LL],
@@ -93,7 +93,8 @@ _SIGS = {
     "hulc2_philox_uniform": [P, LL, C.c_ulonglong, C.c_ulonglong],
     "hulc2_dropout_mask": [P, LL, F, C.c_ulonglong, C.c_ulonglong],
 }
-_NO_STREAM = {"hulc2_last_error": (C.c_char_p, []), "hulc2_version": (I, []), "hulc2_device_supports_tcgen05": (I, [])}
+_NO_STREAM = {"hulc2_last_error": (C.c_char_p, []), "hulc2_version": (I, []), "hulc2_device_supports_tcgen05": (I, []),
+              "hulc2_launch_count": (C.c_ulonglong, [])}
 
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + list(_NO_STREAM))
 
@@ -136,11 +137,50 @@ def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_prof = None   # list of (key, flops, start_event, end_event) while profiling
+_tag = None    # (key, flops) annotation for the next call
+
+
+def tag(key: str, flops: float = 0.0) -> None:
+    """Annotates the next C-ABI call (shape key + algorithmic FLOPs) for bench.py's per-kernel timing."""
+    global _tag
+    if _prof is not None:
+        _tag = (key, flops)
+
+
+def profile_begin() -> None:
+    global _prof
+    _prof = []
+
+
+def profile_end() -> dict:
+    """Returns {key: {key, ms, calls, flops}} aggregated over the profiled region (CUDA events on the launch stream)."""
+    global _prof, _tag
+    torch.cuda.synchronize()
+    out = {}
+    for key, flops, e0, e1 in _prof:
+        r = out.setdefault(key, {"key": key, "ms": 0.0, "calls": 0, "flops": 0.0})
+        r["ms"] += e0.elapsed_time(e1)
+        r["calls"] += 1
+        r["flops"] += flops
+    _prof, _tag = None, None
+    return out
+
+
 def call(name: str, *args) -> None:
     """Invoke a C-ABI entry point on torch's current stream; raise RuntimeError on failure."""
-    global launch_count
+    global launch_count, _tag
     lib = load_library()
-    rc = getattr(lib, name)(*args, stream())
+    if _prof is not None:
+        key, flops = _tag if _tag is not None else (name, 0.0)
+        _tag = None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream())
+        e1.record()
+        _prof.append((key, flops, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args, stream())
     launch_count += 1
     if rc != 0:
         msg = lib.hulc2_last_error().decode("utf-8", "replace")

@@ -11,6 +11,7 @@ int hulc2_conv2d_wgrad_f32_impl(const hulc2_conv_args* a, cudaStream_t st);
 int hulc2_conv2d_dgrad_f32_impl(const hulc2_conv_args* a, cudaStream_t st);
 int hulc2_gemm_bf16_impl(const hulc2_gemm_args* a, cudaStream_t st);
 
+unsigned long long g_hulc2_launches = 0;
 static thread_local char g_err[512] = "";
 void hulc2_set_error(const char* msg) {
   strncpy(g_err, msg ? msg : "", sizeof(g_err) - 1);
@@ -21,6 +22,7 @@ extern "C" {
 
 const char* hulc2_last_error(void) { return g_err; }
 int hulc2_version(void) { return 100; }
+unsigned long long hulc2_launch_count(void) { return g_hulc2_launches; }
 
 int hulc2_device_supports_tcgen05(void) {
   int dev = 0;

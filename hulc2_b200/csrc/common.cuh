@@ -9,8 +9,10 @@
 #define HULC2_ENOTIMPL (-3)
 #define HULC2_EWORKSPACE (-4)
 
+extern unsigned long long g_hulc2_launches;
 #define HULC2_CHECK_LAUNCH()                                         \
   do {                                                               \
+    ++g_hulc2_launches;                                              \
     cudaError_t e__ = cudaGetLastError();                            \
     if (e__ != cudaSuccess) { hulc2_set_error(cudaGetErrorString(e__)); return HULC2_ELAUNCH; } \
   } while (0)

@@ -40,29 +40,30 @@ __global__ void relu_mask_kernel(const float* __restrict__ dy, const float* __re
 
 // stage 1: block (32 cols x 8 row-lanes) sums its row slab; partial[slab][cols]
 __global__ void colsum_partial_kernel(const float* __restrict__ x, long long ld, long long rows, int cols,
-                                      float* __restrict__ partial, long long rows_per_slab) {
-  __shared__ float red[8][33];
+                                      double* __restrict__ partial, long long rows_per_slab) {
+  // bias gradients sum up to millions of cancelling terms: accumulate in double (the kernel is HBM-bound anyway)
+  __shared__ double red[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
   long long r0 = (long long)blockIdx.y * rows_per_slab;
   long long r1 = r0 + rows_per_slab < rows ? r0 + rows_per_slab : rows;
-  float s = 0.f;
+  double s = 0.0;
   if (c < cols)
-    for (long long r = r0 + threadIdx.y; r < r1; r += 8) s += x[r * ld + c];
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) s += (double)x[r * ld + c];
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < cols) {
-    float t = 0.f;
+    double t = 0.0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
     partial[(long long)blockIdx.y * cols + c] = t;
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int slabs, int cols, float* __restrict__ out, int accumulate) {
+__global__ void colsum_final_kernel(const double* __restrict__ partial, int slabs, int cols, float* __restrict__ out, int accumulate) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
-  float s = 0.f;
+  double s = 0.0;
   for (int j = 0; j < slabs; ++j) s += partial[(long long)j * cols + c];
-  out[c] = accumulate ? out[c] + s : s;
+  out[c] = accumulate ? out[c] + (float)s : (float)s;
 }
 
 // per-frame [HW, C] <-> [C, HW] transposes through a padded shared tile
@@ -88,15 +89,15 @@ __global__ void transpose_frames_kernel(const float* __restrict__ src, float* __
   }
 }
 
-// dst[d1, d0, :D2] (+)= src[(d0*D1 + d1)*src_ld + :D2]   (batch-major <-> time-major row shuffles)
-__global__ void transpose01_kernel(const float* __restrict__ src, long long src_ld, float* __restrict__ dst, long long dst_ld,
+// dst[d1, d0, :D2] (+)= src[d0*src_s0 + d1*src_s1 + :D2]   (batch-major <-> time-major row shuffles)
+__global__ void transpose01_kernel(const float* __restrict__ src, long long src_s0, long long src_s1, float* __restrict__ dst, long long dst_ld,
                                    int D0, int D1, int D2, int accumulate) {
   long long total = (long long)D0 * D1 * D2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % D2);
     long long r = i / D2;          // r = d1*D0 + d0 (destination row)
     int d0 = (int)(r % D0), d1 = (int)(r / D0);
-    float v = src[((long long)d0 * D1 + d1) * src_ld + c];
+    float v = src[(long long)d0 * src_s0 + (long long)d1 * src_s1 + c];
     float* d = dst + r * dst_ld + c;
     *d = accumulate ? (*d + v) : v;
   }
@@ -212,7 +213,7 @@ int hulc2_colsum(const float* x, long long ld, long long rows, int cols, float* 
                  long long workspace_bytes, cudaStream_t st) {
   if (cols <= 0) return HULC2_OK;
   int colblocks = hulc2_cdiv(cols, 32);
-  long long max_slabs = workspace ? workspace_bytes / ((long long)cols * sizeof(float)) : 0;
+  long long max_slabs = workspace ? workspace_bytes / ((long long)cols * sizeof(double)) : 0;
   if (max_slabs < 1) { hulc2_set_error("colsum: workspace too small"); return HULC2_EWORKSPACE; }
   long long slabs = (2LL * kSMs + colblocks - 1) / colblocks;
   if (slabs > max_slabs) slabs = max_slabs;
@@ -222,9 +223,9 @@ int hulc2_colsum(const float* x, long long ld, long long rows, int cols, float* 
   long long per = (rows + slabs - 1) / slabs;
   if (per < 1) per = 1;
   slabs = rows > 0 ? (rows + per - 1) / per : 1;
-  colsum_partial_kernel<<<dim3(colblocks, (unsigned)slabs), dim3(32, 8), 0, st>>>(x, ld, rows, cols, (float*)workspace, per);
+  colsum_partial_kernel<<<dim3(colblocks, (unsigned)slabs), dim3(32, 8), 0, st>>>(x, ld, rows, cols, (double*)workspace, per);
   HULC2_CHECK_LAUNCH();
-  colsum_final_kernel<<<hulc2_cdiv(cols, 128), 128, 0, st>>>((const float*)workspace, (int)slabs, cols, out, accumulate);
+  colsum_final_kernel<<<hulc2_cdiv(cols, 128), 128, 0, st>>>((const double*)workspace, (int)slabs, cols, out, accumulate);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }
@@ -242,11 +243,12 @@ int hulc2_nchw_to_nhwc(const float* src, float* dst, int F, int HW, int C, const
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }
-int hulc2_transpose01(const float* src, long long src_ld, float* dst, long long dst_ld, int D0, int D1, int D2, int accumulate,
+int hulc2_transpose01(const float* src, long long src_s0, long long src_s1, float* dst, long long dst_ld, int D0, int D1, int D2,
+                      int accumulate,
                       cudaStream_t st) {
   long long total = (long long)D0 * D1 * D2;
   if (total <= 0) return HULC2_OK;
-  transpose01_kernel<<<grid_for(total, 256), 256, 0, st>>>(src, src_ld, dst, dst_ld, D0, D1, D2, accumulate);
+  transpose01_kernel<<<grid_for(total, 256), 256, 0, st>>>(src, src_s0, src_s1, dst, dst_ld, D0, D1, D2, accumulate);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

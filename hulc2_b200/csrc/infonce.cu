@@ -48,7 +48,7 @@ __device__ void infonce_forward_phases(const float* img, const float* txt, const
   __syncthreads();
 }
 
-__global__ void infonce_fwd_kernel(const float* __restrict__ img, const float* __restrict__ txt,
+__global__ void __launch_bounds__(512) infonce_fwd_kernel(const float* __restrict__ img, const float* __restrict__ txt,
                                    const unsigned char* __restrict__ use, const float* __restrict__ logit_scale,
                                    float* __restrict__ loss, int B, int D, float* __restrict__ wsp) {
   __shared__ float red[32];
@@ -62,7 +62,7 @@ __global__ void infonce_fwd_kernel(const float* __restrict__ img, const float* _
   if (threadIdx.x == 0) loss[0] = cnt > 0.f ? acc / (2.f * cnt) : 0.f;
 }
 
-__global__ void infonce_bwd_kernel(const float* __restrict__ img, const float* __restrict__ txt,
+__global__ void __launch_bounds__(512) infonce_bwd_kernel(const float* __restrict__ img, const float* __restrict__ txt,
                                    const unsigned char* __restrict__ use, const float* __restrict__ logit_scale,
                                    const float* __restrict__ gout, float* __restrict__ dimg, float* __restrict__ dtxt,
                                    float* __restrict__ dlogit_scale, int B, int D, float* __restrict__ wsp) {
@@ -126,7 +126,7 @@ int hulc2_infonce_fwd(const float* img, const float* txt, const unsigned char* u
                       int B, int D, void* workspace, long long workspace_bytes, cudaStream_t st) {
   if (B <= 0) return HULC2_OK;
   if (!workspace || workspace_bytes < ws_floats(B, D) * (long long)sizeof(float)) { hulc2_set_error("infonce: workspace too small"); return HULC2_EWORKSPACE; }
-  infonce_fwd_kernel<<<1, 1024, 0, st>>>(img, txt, use, logit_scale, loss, B, D, (float*)workspace);
+  infonce_fwd_kernel<<<1, 512, 0, st>>>(img, txt, use, logit_scale, loss, B, D, (float*)workspace);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }
@@ -135,7 +135,7 @@ int hulc2_infonce_bwd(const float* img, const float* txt, const unsigned char* u
                       cudaStream_t st) {
   if (B <= 0) return HULC2_OK;
   if (!workspace || workspace_bytes < ws_floats(B, D) * (long long)sizeof(float)) { hulc2_set_error("infonce: workspace too small"); return HULC2_EWORKSPACE; }
-  infonce_bwd_kernel<<<1, 1024, 0, st>>>(img, txt, use, logit_scale, gout, dimg, dtxt, dlogit_scale, B, D, (float*)workspace);
+  infonce_bwd_kernel<<<1, 512, 0, st>>>(img, txt, use, logit_scale, gout, dimg, dtxt, dlogit_scale, B, D, (float*)workspace);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

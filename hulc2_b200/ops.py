@@ -89,6 +89,7 @@ def gemm(M, N, K, A, a_rs, a_ks, B, b_rs, b_ks, Cout, ldc, *, a_off=0, b_off=0, 
     g.relu, g.accumulate, g.alpha = int(relu), int(accumulate), alpha
     g.precision = _precision if precision is None else precision
     g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
+    _lib.tag(f"gemm[M={int(M)},N={int(N)},K={int(K)}]", 2.0 * M * N * K)
     call("hulc2_gemm", C.byref(g))
 
 
@@ -209,6 +210,7 @@ def _conv_trunk_fwd(x, w1, b1, w2, b2, w3, b3):
         a = _conv_args(F_, cin, h, wd, cout, k, s, nhwc)
         a.x, a.w, a.bias, a.y, a.relu = xin.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), 1
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.tag(f"conv_fwd[F={F_},{cin}x{h}x{wd}->{cout},k{k}s{s}]", 2.0 * y.numel() * cin * k * k)
         call("hulc2_conv2d_fwd", C.byref(a))
     return y1, y2, y3
 
@@ -226,6 +228,7 @@ def _conv_trunk_bwd(x, y1, y2, dz3, w2, w3, need):
         dw = torch.empty(cout, cin * k * k, device=dev, dtype=torch.float32)
         a.x, a.dy, a.dw, a.accumulate = xin.data_ptr(), dz.data_ptr(), dw.data_ptr(), 0
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.tag(f"conv_wgrad[F={F_},{cin}x{h}x{wd}->{cout},k{k}s{s}]", 2.0 * dz.numel() * cin * k * k)
         call("hulc2_conv2d_wgrad", C.byref(a))
         if nhwc:
             out = torch.empty(shape_oihw, device=dev, dtype=torch.float32)
@@ -245,6 +248,7 @@ def _conv_trunk_bwd(x, y1, y2, dz3, w2, w3, need):
         a = _conv_args(F_, cin, h, wd, cout, k, s, 1)
         a.dy, a.w, a.dx, a.xmask = dz.data_ptr(), whwoi.data_ptr(), dx.data_ptr(), xmask.data_ptr()
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.tag(f"conv_dgrad[F={F_},{cin}x{h}x{wd}<-{cout},k{k}s{s}]", 2.0 * dz.numel() * cin * k * k)
         call("hulc2_conv2d_dgrad", C.byref(a))
         return dx
 
@@ -513,8 +517,8 @@ class RNNDecoderFunction(torch.autograd.Function):
         assert In == P + Es + G
         dev = plan.device
         embT = torch.empty(S, B, Es, device=dev, dtype=torch.float32)
-        assert emb.stride(2) == 1 and emb.stride(0) == S * emb.stride(1)
-        call("hulc2_transpose01", emb.data_ptr(), emb.stride(1), embT.data_ptr(), Es, B, S, Es, 0)
+        assert emb.stride(2) == 1
+        call("hulc2_transpose01", emb.data_ptr(), emb.stride(0), emb.stride(1), embT.data_ptr(), Es, B, S, Es, 0)
         bsum0 = torch.empty(H, device=dev, dtype=torch.float32)
         bsum1 = torch.empty(H, device=dev, dtype=torch.float32)
         for bs, bi, bh in ((bsum0, bi0, bh0), (bsum1, bi1, bh1)):
@@ -529,9 +533,11 @@ class RNNDecoderFunction(torch.autograd.Function):
         H0 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         h00 = h0[0].contiguous() if h0 is not None else None
         h01 = h0[1].contiguous() if h0 is not None else None
+        _lib.tag(f"rnn_relu_fwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
         call("hulc2_rnn_relu_fwd", pre.data_ptr(), wh0.data_ptr(), _p(h00), H0.data_ptr(), S, B, H, _lib_precision())
         gemm(S * B, H, H, H0, H, 1, wi1, H, 1, pre, H, bias=bsum1)
         H1 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
+        _lib.tag(f"rnn_relu_fwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
         call("hulc2_rnn_relu_fwd", pre.data_ptr(), wh1.data_ptr(), _p(h01), H1.data_ptr(), S, B, H, _lib_precision())
         hn = torch.empty(2, B, H, device=dev, dtype=torch.float32)
         call("hulc2_copy2d", H0.data_ptr() + 4 * (S - 1) * B * H, B * H, hn.data_ptr(), B * H, 1, B * H, 0)
@@ -553,6 +559,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         dH1 = dH1.contiguous()
         dz1 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         call("hulc2_copy2d", dH1.data_ptr(), step, dz1.data_ptr(), step, S, step, 0)
+        _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
         call("hulc2_rnn_relu_bwd", dz1.data_ptr(), wh1.data_ptr(), H1.data_ptr(), None, S, B, H, prec)
         dwh1 = torch.empty_like(wh1)
         if S > 1:
@@ -567,6 +574,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         colsum(dz1, H, S * B, H, db1)
         dz0 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         gemm(S * B, H, H, dz1, H, 1, wi1, 1, H, dz0, H)                      # dH0 = dz1 W_ih1
+        _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
         call("hulc2_rnn_relu_bwd", dz0.data_ptr(), wh0.data_ptr(), H0.data_ptr(), None, S, B, H, prec)
         dwh0 = torch.empty_like(wh0)
         if S > 1:
@@ -594,7 +602,7 @@ class RNNDecoderFunction(torch.autograd.Function):
             dembT = torch.empty(S, B, Es, device=dev, dtype=torch.float32)
             gemm(S * B, Es, H, dz0, H, 1, wi0, 1, In, dembT, Es, b_off=P)
             demb = torch.empty(B, S, Es, device=dev, dtype=torch.float32)
-            call("hulc2_transpose01", dembT.data_ptr(), Es, demb.data_ptr(), Es, S, B, Es, 0)
+            call("hulc2_transpose01", dembT.data_ptr(), B * Es, Es, demb.data_ptr(), Es, S, B, Es, 0)
         return (dplan, demb, dgoal, None, dwi0, dwh0, db0, db0.clone(), dwi1, dwh1, db1, db1.clone())
 
 

@@ -25,6 +25,8 @@ typedef struct CUstream_st* hulc2_stream_t; /* == cudaStream_t */
 
 const char* hulc2_last_error(void);
 int hulc2_version(void);
+/* number of kernels this library has launched in this process (evidence for bench.py's gpu_launches) */
+unsigned long long hulc2_launch_count(void);
 /* 1 when the running device is sm_100 (B200) and the tcgen05 path is usable. */
 int hulc2_device_supports_tcgen05(void);
 
@@ -76,9 +78,9 @@ int hulc2_permute_conv_weight(const float* src, float* dst, int O, int I, int KH
  * nhwc<->nchw per-frame transposes (nn.Flatten order of nature_cnn, vision_network_gripper.py:22-23). */
 int hulc2_copy2d(const float* src, long long lds, float* dst, long long ldd, long long rows, int cols, int accumulate,
                  hulc2_stream_t stream);
-/* dst[d1, d0, :D2] (+)= src[(d0*D1 + d1)*src_ld + :D2]: batch-major [B,S,*] <-> time-major [S,B,*] row shuffle */
-int hulc2_transpose01(const float* src, long long src_ld, float* dst, long long dst_ld, int D0, int D1, int D2,
-                      int accumulate, hulc2_stream_t stream);
+/* dst[d1, d0, :D2] (+)= src[d0*src_s0 + d1*src_s1 + :D2]: batch-major [B,S,*] <-> time-major [S,B,*] row shuffle */
+int hulc2_transpose01(const float* src, long long src_s0, long long src_s1, float* dst, long long dst_ld, int D0, int D1,
+                      int D2, int accumulate, hulc2_stream_t stream);
 int hulc2_fill(float* dst, long long n, float value, hulc2_stream_t stream);
 int hulc2_axpy(const float* x, float* y, long long n, float a, hulc2_stream_t stream); /* y += a*x */
 int hulc2_colsum(const float* x, long long ld, long long rows, int cols, float* out, int accumulate, void* workspace,

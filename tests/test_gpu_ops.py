@@ -1,0 +1,417 @@
+"""GPU parity tests, op level: every kernel is called through the C-ABI (hulc2_b200.ops -> ctypes) and
+compared with the CPU oracle / plain fp32 torch on the same seeded inputs.  fp32 tolerance 1e-5
+relative (max-norm) unless noted; index / argmax work is bit-exact."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import assert_close, build_model, gt, oracle_params, rel_err, to_device
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(*shape, generator=g) * 2 - 1) * scale
+
+
+# ----------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(70, 45, 33), (257, 130, 100), (3, 2048, 160), (64, 64, 2048), (1, 7, 5), (300, 32, 192)])
+def test_gemm_nt_epilogues(M, N, K):
+    from hulc2_b200 import ops
+
+    A, B, bias, add = _rand(M, K, seed=1), _rand(N, K, seed=2), _rand(N, seed=3), _rand(M, N, seed=4)
+    maskt = _rand(M, N, seed=5)
+    keep = (torch.rand(M, N, generator=torch.Generator().manual_seed(6)) > 0.3).to(torch.uint8)
+    C0 = _rand(M, N, seed=7)
+    ref = A @ B.t() + bias + add + C0
+    ref = torch.relu(ref) * (maskt > 0) * keep * 1.25
+    Cd = C0.to(DEV)
+    ops.gemm(M, N, K, A.to(DEV), K, 1, B.to(DEV), K, 1, Cd, N, bias=bias.to(DEV), add=add.to(DEV), ld_add=N,
+             mask=maskt.to(DEV), ld_mask=N, keep=keep.to(DEV), ld_keep=N, keep_scale=1.25, relu=True, accumulate=True, precision=0)
+    assert_close(Cd, ref, 1e-5)
+
+
+def test_gemm_nn_tn_and_strides():
+    from hulc2_b200 import ops
+
+    M, N, K = 90, 70, 50
+    dY, W, X = _rand(M, N, seed=1), _rand(N, K, seed=2), _rand(M, K, seed=3)
+    dX = torch.empty(M, K, device=DEV)
+    ops.gemm(M, K, N, dY.to(DEV), N, 1, W.to(DEV), 1, K, dX, K, precision=0)       # dX = dY W
+    assert_close(dX, dY @ W, 1e-5)
+    dW = torch.empty(N, K, device=DEV)
+    ops.gemm(N, K, M, dY.to(DEV), 1, N, X.to(DEV), 1, K, dW, K, precision=0)       # dW = dY^T X
+    assert_close(dW, dY.t() @ X, 1e-5)
+    # row-strided A (emb[:, 0]-style view), column-offset C block
+    big = _rand(M, 4, K, seed=4)
+    out = torch.zeros(M, N + 10, device=DEV)
+    bigd = big.to(DEV)
+    ops.gemm(M, N, K, bigd, 4 * K, 1, W.to(DEV), K, 1, out, N + 10, a_off=2 * K, c_off=5, precision=0)
+    assert_close(out[:, 5 : 5 + N], big[:, 2] @ W.t(), 1e-5)
+    assert float(out[:, :5].abs().max()) == 0.0 and float(out[:, 5 + N :].abs().max()) == 0.0
+
+
+def test_gemm_splitk_wgrad():
+    from hulc2_b200 import ops
+
+    rows, N, K = 6000, 60, 300
+    dY, X = _rand(rows, N, seed=1), _rand(rows, K, seed=2)
+    dW = torch.empty(N, K, device=DEV)
+    ops.gemm(N, K, rows, dY.to(DEV), 1, N, X.to(DEV), 1, K, dW, K, precision=0)
+    assert_close(dW, dY.double().t() @ X.double(), 2e-5)
+
+
+# ----------------------------------------------------------------------------- MLP / LayerNorm
+def test_mlp_function_grads():
+    from hulc2_b200 import ops
+
+    M = 37
+    x = _rand(M, 50, seed=1).requires_grad_()
+    Ws = [_rand(64, 50, seed=2, scale=0.2), _rand(48, 64, seed=3, scale=0.2), _rand(10, 48, seed=4, scale=0.2)]
+    bs = [_rand(64, seed=5), _rand(48, seed=6), _rand(10, seed=7)]
+    ps = [t.clone().requires_grad_() for t in Ws + bs]
+    y = F.linear(torch.relu(F.linear(torch.relu(F.linear(x, ps[0], ps[3])), ps[1], ps[4])), ps[2], ps[5])
+    gout = _rand(M, 10, seed=8)
+    y.backward(gout)
+    xd = x.detach().to(DEV).requires_grad_()
+    pd = [t.detach().to(DEV).requires_grad_() for t in Ws + bs]
+    yd = ops.mlp(xd, [(pd[0], pd[3]), (pd[1], pd[4]), (pd[2], pd[5])], [True, True, False])
+    yd.backward(gout.to(DEV))
+    assert_close(yd, y, 1e-5, "out")
+    assert_close(xd.grad, x.grad, 1e-5, "dx")
+    for a, b in zip(pd, ps):
+        assert_close(a.grad, b.grad, 1e-5, "dparam")
+
+
+def test_layernorm_residual_dropout():
+    from hulc2_b200 import ops
+
+    rows, D, p = 77, 128, 0.1
+    x, r = _rand(rows, D, seed=1).requires_grad_(), _rand(rows, D, seed=2).requires_grad_()
+    g, b = (1 + 0.1 * _rand(D, seed=3)).requires_grad_(), _rand(D, seed=4).requires_grad_()
+    keep = (torch.rand(rows, D, generator=torch.Generator().manual_seed(5)) > p)
+    y = F.layer_norm(x + r * keep / (1 - p), (D,), g, b, 1e-5)
+    gout = _rand(rows, D, seed=6)
+    y.backward(gout)
+    xd, rd, gd, bd = (t.detach().to(DEV).requires_grad_() for t in (x, r, g, b))
+    yd = ops.layer_norm(xd, gd, bd, res=rd, keep=keep.to(DEV).to(torch.uint8), keep_scale=1 / (1 - p))
+    yd.backward(gout.to(DEV))
+    for a, bb, n in ((yd, y, "y"), (xd.grad, x.grad, "dx"), (rd.grad, r.grad, "dres"), (gd.grad, g.grad, "dgamma"), (bd.grad, b.grad, "dbeta")):
+        assert_close(a, bb, 1e-5, n)
+
+
+# ----------------------------------------------------------------------------- conv encoders
+@pytest.mark.parametrize("hw", [(200, 200), (150, 200)])
+def test_static_encoder_fwd_bwd(hw):
+    from oracle import hulc2_oracle as O
+
+    m = build_model("calvin", hw)
+    enc = m.perceptual_encoder.rgb_static_encoder
+    pre = "perceptual_encoder.rgb_static_encoder."
+    P = oracle_params(m)
+    x = _rand(3, 3, hw[0], hw[1], seed=11)
+    y = O.static_encoder(x, P, pre)
+    gout = _rand(3, 64, seed=12)
+    y.backward(gout)
+    enc = enc.to(DEV)
+    yd = enc(x.to(DEV))
+    yd.backward(gout.to(DEV))
+    assert_close(yd, y, 1e-5, "static enc out")
+    for n, p in enc.named_parameters():
+        assert_close(p.grad, P[pre + n].grad, 2e-4, n)
+
+
+def test_gripper_encoder_fwd_bwd():
+    from oracle import hulc2_oracle as O
+
+    m = build_model("calvin")
+    pre = "perceptual_encoder.rgb_gripper_encoder."
+    P = oracle_params(m)
+    x = _rand(4, 3, 84, 84, seed=13)
+    y = O.gripper_encoder(x, P, pre)
+    gout = _rand(4, 64, seed=14)
+    y.backward(gout)
+    enc = m.perceptual_encoder.rgb_gripper_encoder.to(DEV)
+    yd = enc(x.to(DEV))
+    yd.backward(gout.to(DEV))
+    assert_close(yd, y, 1e-5, "gripper enc out")
+    for n, p in enc.named_parameters():
+        assert_close(p.grad, P[pre + n].grad, 2e-4, n)
+
+
+def test_conv_primitives_vs_torch():
+    """conv fwd/wgrad/dgrad individually (NHWC + stride 2, odd sizes) against F.conv2d autograd."""
+    import ctypes as C
+
+    from hulc2_b200 import ops
+    from hulc2_b200._lib import call
+
+    F_, Cin, H, W, Cout, k, s = 2, 5, 13, 11, 7, 4, 2
+    x = _rand(F_, Cin, H, W, seed=1).requires_grad_()
+    w = _rand(Cout, Cin, k, k, seed=2, scale=0.3).requires_grad_()
+    b = _rand(Cout, seed=3).requires_grad_()
+    y = F.conv2d(x, w, b, stride=s)
+    gout = _rand(*y.shape, seed=4)
+    y.backward(gout)
+    OH, OW = y.shape[2], y.shape[3]
+    xn = x.detach().permute(0, 2, 3, 1).contiguous().to(DEV)
+    wd = w.detach().to(DEV)
+    wp = torch.empty(Cout, k, k, Cin, device=DEV)
+    call("hulc2_permute_conv_weight", wd.data_ptr(), wp.data_ptr(), Cout, Cin, k, k, 0, 0)
+    assert torch.equal(wp.cpu(), w.detach().permute(0, 2, 3, 1).contiguous())
+    ws = ops.workspace(torch.device(DEV))
+    yd = torch.empty(F_, OH, OW, Cout, device=DEV)
+    a = ops._conv_args(F_, Cin, H, W, Cout, k, s, 1)
+    a.x, a.w, a.bias, a.y, a.relu = xn.data_ptr(), wp.data_ptr(), b.detach().to(DEV).data_ptr(), yd.data_ptr(), 0
+    a.precision = 0
+    call("hulc2_conv2d_fwd", C.byref(a))
+    assert_close(yd.permute(0, 3, 1, 2), y, 1e-5, "conv fwd")
+    dyn = gout.permute(0, 2, 3, 1).contiguous().to(DEV)
+    dw = torch.empty(Cout, k * k * Cin, device=DEV)
+    a.dy, a.dw, a.accumulate, a.workspace, a.workspace_bytes = dyn.data_ptr(), dw.data_ptr(), 0, ws.data_ptr(), ws.numel()
+    call("hulc2_conv2d_wgrad", C.byref(a))
+    assert_close(dw.view(Cout, k, k, Cin).permute(0, 3, 1, 2), w.grad, 1e-5, "conv wgrad")
+    whwoi = torch.empty(k, k, Cout, Cin, device=DEV)
+    call("hulc2_permute_conv_weight", wd.data_ptr(), whwoi.data_ptr(), Cout, Cin, k, k, 2, 0)
+    dx = torch.empty(F_, H, W, Cin, device=DEV)
+    ones = torch.ones(F_, H, W, Cin, device=DEV)
+    a.w, a.dx, a.xmask = whwoi.data_ptr(), dx.data_ptr(), ones.data_ptr()
+    call("hulc2_conv2d_dgrad", C.byref(a))
+    assert_close(dx.permute(0, 3, 1, 2), x.grad, 1e-5, "conv dgrad")
+
+
+def test_spatial_softmax_golden():
+    m = build_model("calvin").to(DEV)
+    out = m.perceptual_encoder.rgb_static_encoder.spatial_softmax(gt("op/ssm/x").to(DEV))
+    assert_close(out, gt("op/ssm/out"), 1e-5)
+
+
+# ----------------------------------------------------------------------------- transformer
+@pytest.mark.parametrize("dropout_p", [0.0, 0.1])
+def test_plan_recognition_vs_oracle(dropout_p):
+    from hulc2_b200 import noise
+    from oracle import hulc2_oracle as O
+
+    m = build_model("calvin", dropout_p=dropout_p)
+    P = oracle_params(m)
+    B, S, E, H, FF = 3, 32, 128, 8, 2048
+    emb = _rand(B, S, E, seed=21).requires_grad_()
+    g = torch.Generator().manual_seed(22)
+    masks, queued = {}, []
+    if dropout_p > 0:
+        def mk(name, *shape):
+            masks[name] = torch.rand(*shape, generator=g) > dropout_p
+            # the module takes token-major [B*S, *] masks for the per-token dropouts
+            queued.append(masks[name].reshape(B * S, -1) if name[:2] in ("sa", "ff") else masks[name])
+        mk("emb", B, S, E)
+        for i in range(2):
+            mk(f"attn{i}", B, H, S, S); mk(f"sa{i}", B, S, E); mk(f"ff1{i}", B, S, FF); mk(f"ff2{i}", B, S, E)
+    logit, seq = O.plan_recognition(emb, P, 8, 2, dropout_p, masks)
+    gl, gs = _rand(B, 1024, seed=23), _rand(B, 4096, seed=24)
+    (logit * gl).sum().add((seq * gs).sum()).backward()
+    net = m.plan_recognition.to(DEV).train()
+    embd = emb.detach().to(DEV).requires_grad_()
+    with noise.supplied(masks=queued):
+        st, seqd = net(embd)
+    ((st.logit * gl.to(DEV)).sum() + (seqd * gs.to(DEV)).sum()).backward()
+    assert_close(st.logit, logit, 1e-5, "logit")
+    assert_close(seqd, seq, 1e-5, "seq_feat")
+    assert_close(embd.grad, emb.grad, 2e-5, "demb")
+    for n, p in net.named_parameters():
+        ref = P["plan_recognition." + n].grad
+        if ref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0
+            continue
+        assert_close(p.grad, ref, 5e-5, n)
+
+
+def test_plan_recognition_golden():
+    m = build_model("calvin").to(DEV).eval()
+    with torch.no_grad():
+        st, seq = m.plan_recognition(gt("op/pr/emb").to(DEV))
+    assert_close(st.logit, gt("op/pr/logit"), 1e-5)
+    assert_close(seq[:, :64], gt("op/pr/seq_feat_head"), 1e-5)
+
+
+# ----------------------------------------------------------------------------- latent plan
+def test_kl_golden():
+    from hulc2_b200 import ops
+
+    pp, pr = gt("op/kl/pp").to(DEV).requires_grad_(), gt("op/kl/pr").to(DEV).requires_grad_()
+    loss = ops.KLFunction.apply(pp, pr, 32, 32, 0.8, 0.01)
+    (loss * 1.0).backward()
+    assert_close(loss, gt("op/kl/loss"), 1e-5)
+    assert_close(pp.grad, gt("op/kl/d_pp"), 1e-5)
+    assert_close(pr.grad, gt("op/kl/d_pr"), 1e-5)
+
+
+def test_straight_through_and_onehot():
+    from hulc2_b200 import ops
+    from oracle import hulc2_oracle as O
+
+    B = 5
+    logits = _rand(B, 1024, seed=31, scale=2.0).requires_grad_()
+    idx = torch.randint(0, 32, (B, 32), generator=torch.Generator().manual_seed(32))
+    gout = _rand(B, 1024, seed=33)
+    ref = O.rsample_straight_through(logits, idx, 32, 32)
+    ref.backward(gout)
+    ld = logits.detach().to(DEV).requires_grad_()
+    out = ops.PlanRSampleFunction.apply(ld, idx.to(DEV), 32, 32)
+    out.backward(gout.to(DEV))
+    assert torch.equal(out.cpu(), ref.detach())          # one-hot: bit exact
+    assert_close(ld.grad, logits.grad, 1e-5)
+
+
+def test_categorical_sample_inverse_cdf():
+    from hulc2_b200 import ops
+
+    B = 64
+    logits = _rand(B, 1024, seed=34, scale=3.0)
+    u = torch.rand(B, 32, generator=torch.Generator().manual_seed(35))
+    idx = ops.categorical_sample(logits.to(DEV), u.to(DEV), 32, 32).cpu()
+    cdf = torch.softmax(logits.view(B, 32, 32).double(), -1).cumsum(-1)
+    ref = (cdf > u.double().unsqueeze(-1)).float().argmax(-1)
+    agree = (idx == ref).float().mean().item()
+    assert agree > 0.999, agree          # fp32-vs-fp64 cdf ties only
+    assert int(idx.min()) >= 0 and int(idx.max()) < 32
+
+
+# ----------------------------------------------------------------------------- decoder head
+def test_logistic_loss_golden_public_and_fused():
+    m = build_model("calvin").to(DEV)
+    dec = m.action_decoder
+    lp, ls, mu, grip = (gt(f"op/logistic/{n}").to(DEV).requires_grad_() for n in ("lp", "ls", "mu", "grip"))
+    act = gt("op/logistic/act").to(DEV)
+    loss = dec._loss(lp, ls, mu, grip, act)
+    loss.backward()
+    assert_close(loss, gt("op/logistic/loss"), 1e-5)
+    for t, n in ((lp, "d_lp"), (ls, "d_ls"), (mu, "d_mu"), (grip, "d_grip")):
+        # the fixture stresses log_scales up to +7, where cdf_delta = sigmoid(x+) - sigmoid(x-) ~ 5e-5 is a
+        # difference of two ~0.5 values: 1-ulp sigmoid differences give 1e-3 relative noise in that component
+        assert_close(t.grad, gt(f"op/logistic/{n}"), 1e-4, n)
+
+
+def test_sample_golden_bit_exact():
+    m = build_model("calvin").to(DEV)
+    dec = m.action_decoder
+    lp, ls, mu, grip = (gt(f"op/logistic/{n}").to(DEV) for n in ("lp", "ls", "mu", "grip"))
+    out = dec._sample(lp, torch.clamp(ls, min=-7.0), mu, grip, gt("op/sample/u1").to(DEV), gt("op/sample/u2").to(DEV)).cpu()
+    ref = gt("op/sample/out")
+    assert torch.equal(out[..., -1], ref[..., -1])                       # gripper argmax: bit exact
+    # mixture argmax is exact when the selected (mean, scale) reproduce the action to rounding
+    assert_close(out[..., :-1], ref[..., :-1], 1e-5)
+
+
+def test_sample_argmax_bit_exact_large():
+    """Mixture selection (Gumbel argmax) and gripper argmax vs the oracle on 4096 rows."""
+    from oracle import hulc2_oracle as O
+
+    m = build_model("calvin")
+    P = {k: v.detach() for k, v in oracle_params(m, False).items()}
+    B, S = 128, 32
+    lp, ls, mu = _rand(B, S, 6, 10, seed=41, scale=2), _rand(B, S, 6, 10, seed=42, scale=3), _rand(B, S, 6, 10, seed=43)
+    grip = _rand(B, S, 2, seed=44)
+    g = torch.Generator().manual_seed(45)
+    u1, u2 = torch.rand(B, S, 6, 10, generator=g), torch.rand(B, S, 6, generator=g)
+    ls = torch.clamp(ls, min=-7.0)
+    ref = O.decoder_sample(lp, ls, mu, grip, u1, u2, P)
+    dec = m.action_decoder.to(DEV)
+    out = dec._sample(lp.to(DEV), ls.to(DEV), mu.to(DEV), grip.to(DEV), u1.to(DEV), u2.to(DEV)).cpu()
+    assert torch.equal(out[..., -1], ref[..., -1])
+    # a wrong mixture pick changes the action by O(1); rounding differences are O(1e-6 * scale)
+    bad = ((out[..., :-1] - ref[..., :-1]).abs() > 1e-4 * (1 + ref[..., :-1].abs())).float().mean().item()
+    assert bad == 0.0, bad
+
+
+def test_frames_golden():
+    from hulc2_b200.models.decoders.utils.gripper_control import tcp_to_world_frame, world_to_tcp_frame
+
+    act, robot = gt("op/logistic/act").to(DEV), gt("op/frames/robot_obs").to(DEV)
+    # the x100 orientation scaling amplifies fp32 rounding of the reference's LU inverse: 1e-4 absolute on O(1..100) values
+    assert_close(world_to_tcp_frame(act, robot), gt("op/frames/world_to_tcp"), 2e-5)
+    assert_close(tcp_to_world_frame(act, robot), gt("op/frames/tcp_to_world"), 2e-5)
+
+
+def test_infonce_golden_masked():
+    m = build_model("calvin").to(DEV)
+    sf, gl = gt("op/clip/seq_feat").to(DEV).requires_grad_(), gt("op/clip/goal").to(DEV).requires_grad_()
+    loss = m.clip_auxiliary_loss(sf, gl, gt("op/clip/use").to(DEV))
+    loss.backward()
+    assert_close(loss, gt("op/clip/loss"), 1e-5)
+    assert_close(gl.grad, gt("op/clip/d_goal"), 2e-5)
+    assert_close(sf.grad.norm(dim=1), gt("op/clip/d_seq_feat_norm"), 2e-5)
+    assert_close(m.logit_scale.grad, gt("op/clip/d_logit_scale"), 1e-3)     # ill-conditioned sum, see test_oracle_golden
+    # rows that are masked out get exactly zero gradient
+    assert float(sf.grad[1].abs().max()) == 0.0 and float(gl.grad[4].abs().max()) == 0.0
+
+
+# ----------------------------------------------------------------------------- recurrence
+def test_rnn_decoder_vs_oracle_small():
+    from oracle import hulc2_oracle as O
+
+    m = build_model("calvin", hidden_size=96)
+    P = oracle_params(m)
+    B, S = 3, 7
+    plan = torch.zeros(B, 1024); plan[torch.arange(B), torch.tensor([5, 100, 1000])] = 1.0
+    plan.requires_grad_()
+    emb = _rand(B, S, 128, seed=51).requires_grad_()
+    goal = _rand(B, 32, seed=52).requires_grad_()
+    act = _rand(B, S, 7, seed=53); act[..., 6] = torch.where(act[..., 6] > 0, 1.0, -1.0)
+    lp, ls, mu, grip, hn = O.decoder_forward(plan, emb, goal, P)
+    loss = O.decoder_loss(lp, ls, mu, grip, act, P)
+    loss.backward()
+    dec = m.action_decoder.to(DEV)
+    dec.gripper_control = False
+    pd, ed, gd = (t.detach().to(DEV).requires_grad_() for t in (plan, emb, goal))
+    lossd = dec.loss(pd, ed, gd, act.to(DEV), None)
+    lossd.backward()
+    assert_close(lossd, loss, 1e-5, "loss")
+    assert_close(pd.grad, plan.grad, 2e-5, "dplan")
+    assert_close(ed.grad, emb.grad, 2e-5, "demb")
+    assert_close(gd.grad, goal.grad, 2e-5, "dgoal")
+    for n, p in dec.named_parameters():
+        assert_close(p.grad, P["action_decoder." + n].grad, 5e-5, n)
+    # forward() API + carried hidden state
+    with torch.no_grad():
+        l2, s2, m2, g2, hn2 = dec(pd, ed, gd)
+        assert_close(l2, lp, 1e-5); assert_close(s2, ls, 1e-5); assert_close(m2, mu, 1e-5); assert_close(g2, grip, 1e-5)
+        assert_close(hn2, hn, 1e-5, "h_n")
+        _, _, m3, _, hn3 = dec(pd, ed[:, :1], gd, hn2)
+        _, _, mo, _, hno = O.decoder_forward(plan, emb[:, :1], goal, P, h0=hn)
+        assert_close(m3, mo, 1e-5, "carried h0 means"); assert_close(hn3, hno, 1e-5, "carried h0 hn")
+
+
+# ----------------------------------------------------------------------------- optimizer / noise
+def test_fused_adam_matches_torch():
+    from hulc2_b200.optim import FusedAdam
+
+    ps = [_rand(33, 7, seed=61), _rand(5, seed=62), _rand(2, 3, 4, seed=63)]
+    ref = [p.clone().requires_grad_() for p in ps]
+    mine = [p.clone().to(DEV).requires_grad_() for p in ps]
+    o_ref = torch.optim.Adam(ref, lr=2e-4)
+    o_me = FusedAdam(mine, lr=2e-4)
+    for step in range(3):
+        o_ref.zero_grad(); o_me.zero_grad()
+        for i, (a, b) in enumerate(zip(ref, mine)):
+            g = _rand(*a.shape, seed=70 + 3 * step + i)
+            a.grad = g.clone()
+            b.grad.add_(g.to(DEV))
+        o_ref.step(); o_me.step()
+    for a, b in zip(ref, mine):
+        assert_close(b, a, 1e-6)
+
+
+def test_philox_noise():
+    from hulc2_b200 import ops
+
+    u = ops.uniform((1 << 20,), torch.device(DEV), seed=7)
+    assert 0.0 <= float(u.min()) and float(u.max()) < 1.0
+    assert abs(float(u.mean()) - 0.5) < 2e-3 and abs(float(u.var()) - 1 / 12) < 2e-3
+    k = ops.dropout_mask((1 << 20,), 0.1, torch.device(DEV), seed=7, offset=123)
+    assert abs(float(k.float().mean()) - 0.9) < 2e-3
+    assert torch.equal(u, ops.uniform((1 << 20,), torch.device(DEV), seed=7))
+    assert not torch.equal(u, ops.uniform((1 << 20,), torch.device(DEV), seed=8))
