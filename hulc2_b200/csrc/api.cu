@@ -10,6 +10,9 @@ int hulc2_conv2d_fwd_f32_impl(const hulc2_conv_args* a, cudaStream_t st);
 int hulc2_conv2d_wgrad_f32_impl(const hulc2_conv_args* a, cudaStream_t st);
 int hulc2_conv2d_dgrad_f32_impl(const hulc2_conv_args* a, cudaStream_t st);
 int hulc2_gemm_bf16_impl(const hulc2_gemm_args* a, cudaStream_t st);
+int hulc2_conv2d_fwd_bf16_impl(const hulc2_conv_args* a, cudaStream_t st);
+int hulc2_conv2d_wgrad_bf16_impl(const hulc2_conv_args* a, cudaStream_t st);
+int hulc2_conv2d_dgrad_bf16_impl(const hulc2_conv_args* a, cudaStream_t st);
 
 unsigned long long g_hulc2_launches = 0;
 static thread_local char g_err[512] = "";
@@ -25,11 +28,14 @@ int hulc2_version(void) { return 100; }
 unsigned long long hulc2_launch_count(void) { return g_hulc2_launches; }
 
 int hulc2_device_supports_tcgen05(void) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-  cudaDeviceProp p;
-  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
-  return p.major == 10 ? 1 : 0;
+  static int cached = -1;  // one device per process (one rank per GPU)
+  if (cached < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    cached = (major == 10) ? 1 : 0;
+  }
+  return cached;
 }
 
 int hulc2_gemm(const hulc2_gemm_args* a, cudaStream_t st) {
@@ -50,20 +56,23 @@ static int check_conv(const hulc2_conv_args* a) {
 int hulc2_conv2d_fwd(const hulc2_conv_args* a, cudaStream_t st) {
   if (int e = check_conv(a)) return e;
   if (a->precision == 0) return hulc2_conv2d_fwd_f32_impl(a, st);
-  hulc2_set_error("conv2d_fwd: precision not implemented");
-  return HULC2_ENOTIMPL;
+  if (a->precision == 1) return hulc2_conv2d_fwd_bf16_impl(a, st);
+  hulc2_set_error("conv2d_fwd: unknown precision");
+  return HULC2_EINVAL;
 }
 int hulc2_conv2d_wgrad(const hulc2_conv_args* a, cudaStream_t st) {
   if (int e = check_conv(a)) return e;
   if (a->precision == 0) return hulc2_conv2d_wgrad_f32_impl(a, st);
-  hulc2_set_error("conv2d_wgrad: precision not implemented");
-  return HULC2_ENOTIMPL;
+  if (a->precision == 1) return hulc2_conv2d_wgrad_bf16_impl(a, st);
+  hulc2_set_error("conv2d_wgrad: unknown precision");
+  return HULC2_EINVAL;
 }
 int hulc2_conv2d_dgrad(const hulc2_conv_args* a, cudaStream_t st) {
   if (int e = check_conv(a)) return e;
   if (a->precision == 0) return hulc2_conv2d_dgrad_f32_impl(a, st);
-  hulc2_set_error("conv2d_dgrad: precision not implemented");
-  return HULC2_ENOTIMPL;
+  if (a->precision == 1) return hulc2_conv2d_dgrad_bf16_impl(a, st);
+  hulc2_set_error("conv2d_dgrad: unknown precision");
+  return HULC2_EINVAL;
 }
 
 // h[t] = relu(pre[t] + h[t-1] W_hh^T)      (nn.RNN, nonlinearity=relu; decoders/utils/rnn.py:5-14)

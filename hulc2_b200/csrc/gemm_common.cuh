@@ -1,0 +1,201 @@
+// Shared operand addressing / epilogue definitions of the dense-contraction kernels (fp32 CUDA-core and
+// bf16 tcgen05 backends).  Operands are addressed as off(r,k) = R(r) + Kf(k) (separable): row-major,
+// transposed, two-level row strides, both im2col layouts; the dgrad gather adds a validity predicate.
+#pragma once
+#include "common.cuh"
+#include "../../include/hulc2_b200.h"
+
+namespace hulc2 {
+
+enum { OP_DENSE = 0, OP_IM2COL = 1, OP_IM2COL_T = 2, OP_DGRAD = 3 };
+
+struct ConvGeom {
+  int C, H, W, KH, KW, OH, OW, stride, nhwc, Cout;
+};
+
+struct Operand {
+  const float* p;
+  long long rs, ks;            // dense: off = r*rs + k*ks
+  int r_inner;                 // dense: optional 2-level rows: R(r) = (r / r_inner)*rs_outer + (r % r_inner)*rs_inner
+  long long rs_outer, rs_inner;
+  ConvGeom g;
+};
+
+struct Epilogue {
+  float* C;
+  long long ldc;
+  int c_inner;
+  long long cs_outer, cs_inner;
+  const float* bias;           // [N] or null
+  const float* add;            // [M, ld_add] or null
+  long long ld_add;
+  const float* mask;           // keep where mask[m,n] > 0 (ReLU backward), or null
+  long long ld_mask;
+  const unsigned char* keep;   // dropout keep mask (u8) or null; value *= keep ? keep_scale : 0
+  long long ld_keep;
+  float keep_scale;
+  int relu, accumulate;
+  float alpha;
+};
+
+struct GemmParams {
+  int M, N, K;
+  Operand A, B;
+  Epilogue E;
+  int splits, kchunk;          // split-K: blockIdx.z handles [z*kchunk, (z+1)*kchunk)
+  float* partial;              // [splits, M, N] when splits > 1
+};
+
+__device__ __forceinline__ long long im2col_pixel_off(const ConvGeom& g, int r) {
+  int ohw = g.OH * g.OW;
+  int f = r / ohw, rem = r - f * ohw;
+  int oh = rem / g.OW, ow = rem - oh * g.OW;
+  if (g.nhwc) return (((long long)f * g.H + oh * g.stride) * g.W + ow * g.stride) * g.C;
+  return (long long)f * g.C * g.H * g.W + (long long)(oh * g.stride) * g.W + ow * g.stride;
+}
+__device__ __forceinline__ long long im2col_k_off(const ConvGeom& g, int k) {
+  if (g.nhwc) {  // k = (kh, kw, ci)
+    int kwc = g.KW * g.C;
+    int kh = k / kwc, rem = k - kh * kwc;
+    int kw = rem / g.C, ci = rem - kw * g.C;
+    return ((long long)kh * g.W + kw) * g.C + ci;
+  }
+  int khw = g.KH * g.KW;  // k = (ci, kh, kw)
+  int ci = k / khw, rem = k - ci * khw;
+  int kh = rem / g.KW, kw = rem - kh * g.KW;
+  return (long long)ci * g.H * g.W + (long long)kh * g.W + kw;
+}
+
+template <int MODE>
+__device__ __forceinline__ long long row_off(const Operand& o, int r) {
+  if (MODE == OP_DENSE) {
+    if (o.r_inner > 0) return (long long)(r / o.r_inner) * o.rs_outer + (long long)(r % o.r_inner) * o.rs_inner;
+    return (long long)r * o.rs;
+  } else if (MODE == OP_IM2COL) {
+    return im2col_pixel_off(o.g, r);
+  } else if (MODE == OP_IM2COL_T) {
+    return im2col_k_off(o.g, r);
+  }
+  return 0;
+}
+template <int MODE>
+__device__ __forceinline__ long long col_off(const Operand& o, int k) {
+  if (MODE == OP_DENSE) return (long long)k * o.ks;
+  if (MODE == OP_IM2COL) return im2col_k_off(o.g, k);
+  if (MODE == OP_IM2COL_T) return im2col_pixel_off(o.g, k);
+  return 0;
+}
+
+// dgrad gather: row r = input pixel (f, ih, iw) of the NHWC input-gradient, k = (kh, kw, co).
+// value = dZ[f, (ih-kh)/s, (iw-kw)/s, co] when the division is exact and in range, else 0.
+__device__ __forceinline__ float dgrad_load(const Operand& o, int f, int ih, int iw, int kh, int kw, int co) {
+  const ConvGeom& g = o.g;
+  int th = ih - kh, tw = iw - kw;
+  if (th < 0 || tw < 0) return 0.f;
+  int oh = th / g.stride, ow = tw / g.stride;
+  if (oh * g.stride != th || ow * g.stride != tw || oh >= g.OH || ow >= g.OW) return 0.f;
+  return o.p[(((long long)f * g.OH + oh) * g.OW + ow) * g.Cout + co];
+}
+
+
+// epilogue applied to one accumulator value
+__device__ __forceinline__ float apply_epilogue(const Epilogue& E, float acc, int m, int n, long long crow) {
+  float v = E.alpha * acc;
+  if (E.bias) v += E.bias[n];
+  if (E.add) v += E.add[(long long)m * E.ld_add + n];
+  if (E.accumulate) v += E.C[crow + n];
+  if (E.relu) v = fmaxf(v, 0.f);
+  if (E.mask) v = (E.mask[(long long)m * E.ld_mask + n] > 0.f) ? v : 0.f;
+  if (E.keep) v = E.keep[(long long)m * E.ld_keep + n] ? v * E.keep_scale : 0.f;
+  return v;
+}
+__device__ __forceinline__ long long c_row_off(const Epilogue& E, int m) {
+  return E.c_inner > 0 ? (long long)(m / E.c_inner) * E.cs_outer + (long long)(m % E.c_inner) * E.cs_inner : (long long)m * E.ldc;
+}
+
+// split-K second stage: C = (accumulate ? C : 0) + alpha * sum_z partial[z] (+ bias)
+static __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N, Epilogue E) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)M * N;
+  if (idx >= total) return;
+  int m = (int)(idx / N), n = (int)(idx - (long long)m * N);
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[(long long)z * total + idx];
+  long long crow = c_row_off(E, m);
+  float v = E.alpha * s;
+  if (E.bias) v += E.bias[n];
+  if (E.accumulate) v += E.C[crow + n];
+  E.C[crow + n] = v;
+}
+
+// ------------------------------------------------------------------ host-side parameter builders
+inline void fill_epilogue(Epilogue& E, float* C, long long ldc) {
+  E = Epilogue{};
+  E.C = C; E.ldc = ldc; E.alpha = 1.f; E.keep_scale = 1.f;
+}
+inline ConvGeom geom_of(const hulc2_conv_args* a) {
+  ConvGeom g;
+  g.C = a->C; g.H = a->H; g.W = a->W; g.KH = a->KH; g.KW = a->KW; g.stride = a->stride;
+  g.OH = (a->H - a->KH) / a->stride + 1; g.OW = (a->W - a->KW) / a->stride + 1;
+  g.nhwc = a->in_nhwc; g.Cout = a->Cout;
+  return g;
+}
+// split the contraction over `want_ctas` CTAs when the output tile grid is small; kgran = k-tile size
+inline void plan_splitk(GemmParams& p, long long out_ctas, int want_ctas, int min_k_per_split, int kgran, void* ws, long long ws_bytes) {
+  p.splits = 1; p.kchunk = ((p.K + kgran - 1) / kgran) * kgran;
+  if (p.kchunk == 0) p.kchunk = kgran;
+  p.partial = nullptr;
+  if (!ws || p.K < 2 * min_k_per_split) return;
+  int want = (int)((want_ctas + out_ctas - 1) / out_ctas);
+  int maxs = p.K / min_k_per_split; if (maxs < 1) maxs = 1;
+  int s = want < maxs ? want : maxs;
+  long long per = (long long)p.M * p.N * sizeof(float);
+  while (s > 1 && (long long)s * per > ws_bytes) s /= 2;
+  if (s <= 1) return;
+  p.kchunk = ((hulc2_cdiv(p.K, s) + kgran - 1) / kgran) * kgran;
+  p.splits = hulc2_cdiv(p.K, p.kchunk);
+  p.partial = (float*)ws;
+}
+inline bool dense_params(const hulc2_gemm_args* a, GemmParams& p) {
+  if (!a || a->M < 0 || a->N < 0 || a->K < 0 || !a->A || !a->B || !a->C) { hulc2_set_error("gemm: bad args"); return false; }
+  p = GemmParams{};
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.A.p = a->A; p.A.rs = a->a_rs; p.A.ks = a->a_ks; p.A.r_inner = a->a_inner; p.A.rs_outer = a->a_rs_outer; p.A.rs_inner = a->a_rs_inner;
+  p.B.p = a->B; p.B.rs = a->b_rs; p.B.ks = a->b_ks;
+  fill_epilogue(p.E, a->C, a->ldc);
+  p.E.c_inner = a->c_inner; p.E.cs_outer = a->c_rs_outer; p.E.cs_inner = a->c_rs_inner;
+  p.E.bias = a->bias; p.E.add = a->add; p.E.ld_add = a->ld_add; p.E.mask = a->mask; p.E.ld_mask = a->ld_mask;
+  p.E.keep = a->keep; p.E.ld_keep = a->ld_keep; p.E.keep_scale = a->keep_scale;
+  p.E.relu = a->relu; p.E.accumulate = a->accumulate; p.E.alpha = a->alpha;
+  return true;
+}
+inline bool simple_epilogue(const hulc2_gemm_args* a) { return !a->add && !a->mask && !a->keep && !a->relu; }
+inline void conv_fwd_params(const hulc2_conv_args* a, GemmParams& p) {
+  ConvGeom g = geom_of(a);
+  p = GemmParams{};
+  p.M = a->F * g.OH * g.OW; p.N = a->Cout; p.K = a->C * a->KH * a->KW;
+  p.A.p = a->x; p.A.g = g;
+  p.B.p = a->w; p.B.rs = p.K; p.B.ks = 1;
+  fill_epilogue(p.E, a->y, a->Cout);
+  p.E.bias = a->bias; p.E.relu = a->relu;
+}
+inline void conv_wgrad_params(const hulc2_conv_args* a, GemmParams& p) {
+  ConvGeom g = geom_of(a);
+  p = GemmParams{};
+  p.M = a->Cout; p.N = a->C * a->KH * a->KW; p.K = a->F * g.OH * g.OW;
+  p.A.p = a->dy; p.A.rs = 1; p.A.ks = a->Cout;       // A(m=co, k=pixel) = dZ[pixel*Cout + co]
+  p.B.p = a->x; p.B.g = g;                            // B(n=kidx, k=pixel) = x[pix_off(pixel) + k_off(kidx)]
+  fill_epilogue(p.E, a->dw, p.N);
+  p.E.accumulate = a->accumulate;
+}
+inline void conv_dgrad_params(const hulc2_conv_args* a, GemmParams& p) {
+  ConvGeom g = geom_of(a);
+  p = GemmParams{};
+  p.M = a->F * a->H * a->W; p.N = a->C; p.K = a->KH * a->KW * a->Cout;
+  p.A.p = a->dy; p.A.g = g;
+  p.B.p = a->w; p.B.rs = 1; p.B.ks = a->C;            // B(n=ci, k=(kh,kw,co)) = w_hwoi[k*C + ci]
+  fill_epilogue(p.E, a->dx, a->C);
+  p.E.mask = a->xmask; p.E.ld_mask = a->C;
+}
+
+}  // namespace hulc2
