@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8, help="windows per modality of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--dump-profile", default=None, help="write the per-call CUDA-event profile of one step to this JSON file")
     return ap.parse_args()
 
 
@@ -241,6 +242,9 @@ def run_b200(args):
         torch.cuda.synchronize()
         recs = _lib.profile_end()
         peaks = load_peaks()
+        if args.dump_profile:
+            with open(args.dump_profile, "w") as f:
+                json.dump(sorted(recs.values(), key=lambda r: -r["ms"]), f, indent=1)
         top = max(recs.values(), key=lambda r: r["ms"]) if recs else None
         total_ms = sum(r["ms"] for r in recs.values())
         if top:

@@ -87,8 +87,8 @@ _SIGS = {
     "hulc2_tcp_to_world": [P, P, I, P, LL],
     "hulc2_infonce_fwd": [P, P, P, P, P, I, I, P, LL],
     "hulc2_infonce_bwd": [P, P, P, P, P, P, P, P, I, I, P, LL],
-    "hulc2_rnn_relu_fwd": [P, P, P, P, I, I, I, I],
-    "hulc2_rnn_relu_bwd": [P, P, P, P, I, I, I, I],
+    "hulc2_rnn_relu_fwd": [P, P, P, P, I, I, I, I, P, LL],
+    "hulc2_rnn_relu_bwd": [P, P, P, P, I, I, I, I, P, LL],
     "hulc2_adam_step": [P, P, P, P, LL, F, F, F, F, F, I, F],
     "hulc2_philox_uniform": [P, LL, C.c_ulonglong, C.c_ulonglong],
     "hulc2_dropout_mask": [P, LL, F, C.c_ulonglong, C.c_ulonglong],

@@ -13,6 +13,9 @@ int hulc2_gemm_bf16_impl(const hulc2_gemm_args* a, cudaStream_t st);
 int hulc2_conv2d_fwd_bf16_impl(const hulc2_conv_args* a, cudaStream_t st);
 int hulc2_conv2d_wgrad_bf16_impl(const hulc2_conv_args* a, cudaStream_t st);
 int hulc2_conv2d_dgrad_bf16_impl(const hulc2_conv_args* a, cudaStream_t st);
+int hulc2_rnn_persistent_launch(const float* add, const float* w, const float* init, const float* mask, float* out, float* final_out,
+                                int S, int B, int H, int relu, int reverse, int transpose_w, void* workspace, long long workspace_bytes,
+                                cudaStream_t st);
 
 unsigned long long g_hulc2_launches = 0;
 static thread_local char g_err[512] = "";
@@ -77,8 +80,12 @@ int hulc2_conv2d_dgrad(const hulc2_conv_args* a, cudaStream_t st) {
 
 // h[t] = relu(pre[t] + h[t-1] W_hh^T)      (nn.RNN, nonlinearity=relu; decoders/utils/rnn.py:5-14)
 int hulc2_rnn_relu_fwd(const float* pre, const float* w_hh, const float* h0, float* h, int S, int B, int H, int precision,
-                       cudaStream_t st) {
+                       void* workspace, long long workspace_bytes, cudaStream_t st) {
   if (S <= 0 || B <= 0) return HULC2_OK;
+  if (precision == 1 && hulc2_device_supports_tcgen05()) {
+    int e = hulc2_rnn_persistent_launch(pre, w_hh, h0, nullptr, h, nullptr, S, B, H, 1, 0, 0, workspace, workspace_bytes, st);
+    if (e != HULC2_ENOTIMPL) return e;
+  }
   const long long step = (long long)B * H;
   for (int t = 0; t < S; ++t) {
     hulc2_gemm_args g;
@@ -98,8 +105,12 @@ int hulc2_rnn_relu_fwd(const float* pre, const float* w_hh, const float* h0, flo
 
 // in place: dh[t] <- dz[t] = (dh[t] + dz[t+1] W_hh) * (h[t] > 0); optional dh0 = dz[0] W_hh
 int hulc2_rnn_relu_bwd(float* dh, const float* w_hh, const float* h, float* dh0, int S, int B, int H, int precision,
-                       cudaStream_t st) {
+                       void* workspace, long long workspace_bytes, cudaStream_t st) {
   if (S <= 0 || B <= 0) return HULC2_OK;
+  if (precision == 1 && hulc2_device_supports_tcgen05()) {
+    int e = hulc2_rnn_persistent_launch(dh, w_hh, nullptr, h, dh, dh0, S, B, H, 0, 1, 1, workspace, workspace_bytes, st);
+    if (e != HULC2_ENOTIMPL) return e;
+  }
   const long long step = (long long)B * H;
   if (int e = hulc2_relu_mask(dh + (S - 1) * step, h + (S - 1) * step, dh + (S - 1) * step, step, st)) return e;
   for (int t = S - 2; t >= -1; --t) {

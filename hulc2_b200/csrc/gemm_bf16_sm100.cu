@@ -73,13 +73,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// shared-memory matrix descriptor: K-major, SWIZZLE_128B (layout_type 2), 8-row atoms of 1024 B (SBO), version 1
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// shared-memory matrix descriptor, SWIZZLE_128B (layout_type 2), version 1.  Atoms are 8 rows x 128 bytes = 1024 B (SBO).
+//  K-major : rows = M/N index, 128-byte row = 64 k; LBO unused.
+//  MN-major: rows = k index, 128-byte row = 64 M/N elements; LBO = stride between 64-wide M/N blocks (8192 B here).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
 }
-// instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), a_major @15, b_major @16
+// (0 = K-major, 1 = MN-major), N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
@@ -87,43 +92,55 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// Gathers a [ROWS x 64] operand tile (fp32 in HBM) as 16-byte bf16 chunks.  KFAST: a thread owns chunk column
-// (tid & 7) of rows (tid >> 3) + 32 i  -> 32-byte contiguous global reads per chunk (vectorised when `vec`);
-// else (row-fast operands: transposed activations, im2col^T) a thread owns one row and chunk columns
-// tid / ROWS + (NT / ROWS) i -> each of the 8 scalar loads is coalesced across the warp along the row axis.
-template <int ROWS, int MODE, bool KFAST>
+// Gathers one operand tile (fp32 in HBM) as 16-byte bf16 chunks into the canonical SWIZZLE_128B layout.
+//  K-major  (KMAJ): tile = [ROWS mn-rows][64 k]; a thread owns chunk column (tid & 7) of rows (tid >> 3) + 32 i;
+//                   8 consecutive k are contiguous in memory (row-major activations / weights, im2col, dgrad gather).
+//  MN-major (!KMAJ): tile = ROWS/64 blocks of [64 k-rows][64 mn]; a thread owns mn-chunk (tid & 7) of k-rows
+//                   (tid >> 3) + 32 j in every block; 8 consecutive mn are contiguous in memory (transposed
+//                   activations for weight gradients, W[k][n] for input gradients, im2col^T).
+// Either way a warp reads 4 rows x 256 contiguous bytes and writes 4 x 128-byte swizzled rows (conflict free).
+template <int ROWS, int MODE, bool KMAJ>
 struct TileGather {
-  static constexpr int CH = ROWS * 8 / NT;
-  static constexpr int NR = KFAST ? CH : 1;
-  static constexpr int GROUPS = (NT / ROWS) > 0 ? (NT / ROWS) : 1;
+  static constexpr int BLOCKS = (ROWS + 63) / 64;
+  static constexpr int CH = KMAJ ? ROWS * 8 / NT : BLOCKS * 2;
+  static constexpr int NR = KMAJ ? CH : BLOCKS;
+  static constexpr uint32_t BYTES = (ROWS > 64 ? ROWS : 64) * 128;
   uint4 v[CH];
-  long long roff[NR];
-  int rdec[NR][3];
-  bool rvalid[NR];
-  int r0, c0;
+  long long roff[NR];     // K-major: row offsets; MN-major: offset of the first mn element of this thread's chunk, per block
+  int rdec[KMAJ ? NR : 1][3];
+  int rvalid[NR];         // K-major: row valid (0/1); MN-major: number of valid mn elements in the chunk (0..8)
+  int r0, c0, mn0;
 
   __device__ __forceinline__ void init(const Operand& o, int row_base, int nrows_total) {
     const int tid = threadIdx.x;
-    if (KFAST) { c0 = tid & 7; r0 = tid >> 3; }
-    else { r0 = tid % ROWS; c0 = tid / ROWS; }
+    c0 = tid & 7; r0 = tid >> 3;
+    if (KMAJ) {
 #pragma unroll
-    for (int i = 0; i < NR; ++i) {
-      int r = row_base + r0 + (KFAST ? 32 * i : 0);
-      rvalid[i] = r < nrows_total;
-      int rr = rvalid[i] ? r : 0;
-      roff[i] = 0;
-      if (MODE == OP_DGRAD) {
-        int hw = o.g.H * o.g.W;
-        int f = rr / hw, rem = rr - f * hw;
-        rdec[i][0] = f; rdec[i][1] = rem / o.g.W; rdec[i][2] = rem - (rem / o.g.W) * o.g.W;
-      } else {
-        roff[i] = row_off<MODE>(o, rr);
+      for (int i = 0; i < NR; ++i) {
+        int r = row_base + r0 + 32 * i;
+        rvalid[i] = r < nrows_total;
+        int rr = rvalid[i] ? r : 0;
+        roff[i] = 0;
+        if (MODE == OP_DGRAD) {
+          dgrad_row_decode(o.g, rr, rdec[i][0], rdec[i][1], rdec[i][2]);
+        } else {
+          roff[i] = row_off<MODE>(o, rr);
+        }
+      }
+    } else {
+      mn0 = row_base;
+#pragma unroll
+      for (int b = 0; b < BLOCKS; ++b) {
+        int mn = row_base + b * 64 + c0 * 8;
+        int left = nrows_total - mn;
+        rvalid[b] = (b * 64 + c0 * 8 < ROWS) ? (left >= 8 ? 8 : (left > 0 ? left : 0)) : 0;
+        roff[b] = rvalid[b] > 0 ? row_off<MODE>(o, mn) : 0;
       }
     }
   }
 
   __device__ __forceinline__ void load(const Operand& o, int k0, int kend, bool vec) {
-    if (KFAST) {
+    if (KMAJ) {
       const int kc = k0 + c0 * 8;
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
@@ -132,23 +149,14 @@ struct TileGather {
         for (int e = 0; e < 8; ++e) f[e] = 0.f;
         if (rvalid[i] && kc < kend) {
           if (MODE == OP_DGRAD) {
-            // k = (kh, kw, co): the 8 k of a chunk share (kh, kw) when Cout % 8 == 0
-            const ConvGeom& g = o.g;
-            int kwc = g.KW * g.Cout;
-            int kh = kc / kwc, rem = kc - kh * kwc;
-            int kw = rem / g.Cout, co = rem - kw * g.Cout;
-            int th = rdec[i][1] - kh, tw = rdec[i][2] - kw;
-            int oh = th / g.stride, ow = tw / g.stride;
-            bool ok = th >= 0 && tw >= 0 && oh * g.stride == th && ow * g.stride == tw && oh < g.OH && ow < g.OW;
-            if (ok) {
-              const float* src = o.p + (((long long)rdec[i][0] * g.OH + oh) * g.OW + ow) * g.Cout + co;
-              if (vec) {
-                float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) if (kc + e < kend) f[e] = dgrad_load(o, rdec[i][0], rdec[i][1], rdec[i][2], kh, kw, co + e);
-              }
+            // k = (a, b, co): the 8 k of a chunk share the tap (a, b) because Cout % 8 == 0 (checked on the host)
+            int ta, tb, co;
+            dgrad_k_decode(o.g, kc, ta, tb, co);
+            long long off;
+            if (dgrad_src(o.g, rdec[i][0], rdec[i][1], rdec[i][2], ta, tb, off)) {
+              const float* src = o.p + off + co;
+              float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+              f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
             }
           } else if (vec && kc + 8 <= kend) {
             const float* src = o.p + roff[i] + col_off<MODE>(o, kc);
@@ -163,26 +171,39 @@ struct TileGather {
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        const int kc = k0 + (c0 + GROUPS * i) * 8;
-        float f[8];
+      for (int j = 0; j < 2; ++j) {
+        const int kg = k0 + r0 + 32 * j;
+        const bool kv = kg < kend;
+        const long long koff = kv ? col_off<MODE>(o, kg) : 0;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          f[e] = 0.f;
-          if (rvalid[0] && kc + e < kend) f[e] = __ldg(o.p + roff[0] + col_off<MODE>(o, kc + e));
+        for (int b = 0; b < BLOCKS; ++b) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = 0.f;
+          if (kv && rvalid[b] > 0) {
+            if (vec && rvalid[b] == 8) {
+              const float* src = o.p + roff[b] + koff;
+              float4 a = __ldg(reinterpret_cast<const float4*>(src)), c = __ldg(reinterpret_cast<const float4*>(src) + 1);
+              f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = c.x; f[5] = c.y; f[6] = c.z; f[7] = c.w;
+            } else {
+              const int mn = mn0 + b * 64 + c0 * 8;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) if (e < rvalid[b]) f[e] = __ldg(o.p + row_off<MODE>(o, mn + e) + koff);
+            }
+          }
+          v[b * 2 + j] = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
         }
-        v[i] = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
       }
     }
   }
 
-  // tile base is 1024-byte aligned; row r, 16-byte chunk c -> (r/8)*1024 + (r%8)*128 + ((c ^ (r%8)) * 16)
+  // tile base is 1024-byte aligned; 128-byte row r, 16-byte chunk c -> (r/8)*1024 + (r%8)*128 + ((c ^ (r%8)) * 16)
   __device__ __forceinline__ void store(uint32_t tile_base) const {
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
-      int r = KFAST ? r0 + 32 * i : r0;
-      int c = KFAST ? c0 : c0 + GROUPS * i;
-      uint32_t addr = tile_base + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+      int r = KMAJ ? r0 + 32 * i : r0 + 32 * (i & 1);
+      uint32_t blk = KMAJ ? 0u : (uint32_t)(i >> 1) * 8192u;
+      uint32_t addr = tile_base + blk + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c0 ^ (r & 7)) << 4));
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[i].x), "r"(v[i].y), "r"(v[i].z), "r"(v[i].w) : "memory");
     }
   }
@@ -199,7 +220,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_bf16_kernel(const Bf16Params bp) {
   __shared__ __align__(8) uint64_t mma_done[STAGES];
   __shared__ uint32_t tmem_base_slot;
   const GemmParams& p = bp.g;
-  constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t A_BYTES = TileGather<BM, AMODE, AKF>::BYTES, B_BYTES = TileGather<BN, BMODE, BKF>::BYTES, STAGE_BYTES = A_BYTES + B_BYTES;
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -223,7 +244,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_bf16_kernel(const Bf16Params bp) {
   TileGather<BN, BMODE, BKF> gb;
   ga.init(p.A, m0, p.M);
   gb.init(p.B, n0, p.N);
-  constexpr uint32_t IDESC = make_idesc(BN);
+  constexpr uint32_t IDESC = make_idesc(BN, !AKF, !BKF);
 
   if (ntiles > 0) {
     ga.load(p.A, kbeg, kend, bp.vecA);
@@ -243,10 +264,12 @@ __global__ void __launch_bounds__(NT, 2) gemm_bf16_kernel(const Bf16Params bp) {
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint64_t ad = make_desc(a_tile), bd = make_desc(b_tile);
+      // UMMA_K = 16: K-major advances 32 bytes inside the swizzle atom; MN-major advances 16 k-rows = 2048 bytes
+      const uint64_t ad = make_desc(a_tile, AKF ? 0u : 8192u), bd = make_desc(b_tile, BKF ? 0u : 8192u);
+      constexpr uint64_t A_STEP = (AKF ? 32u : 2048u) >> 4, B_STEP = (BKF ? 32u : 2048u) >> 4;
 #pragma unroll
-      for (int k = 0; k < BKE / 16; ++k)   // UMMA_K = 16 bf16 = 32 bytes: advance the start address inside the swizzle atom
-        umma_bf16(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), IDESC, (t > 0 || k > 0) ? 1u : 0u);
+      for (int k = 0; k < BKE / 16; ++k)
+        umma_bf16(tmem_d, ad + A_STEP * k, bd + B_STEP * k, IDESC, (t > 0 || k > 0) ? 1u : 0u);
       umma_commit(smem_u32(&mma_done[s]));
     }
   }
@@ -262,7 +285,8 @@ __global__ void __launch_bounds__(NT, 2) gemm_bf16_kernel(const Bf16Params bp) {
   constexpr int COLS = BN / 2;
   const int m = m0 + q * 32 + lane;
   const bool mvalid = m < p.M;
-  const long long crow = mvalid ? c_row_off(E, m) : 0;
+  const int mp = mvalid ? phys_row(E, m) : 0;
+  const long long crow = mvalid ? c_row_off(E, mp) : 0;
 #pragma unroll 1
   for (int c = 0; c < COLS; c += 16) {
     float acc[16];
@@ -284,7 +308,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_bf16_kernel(const Bf16Params bp) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           int n = n0 + half * COLS + c + j;
-          if (n < p.N) E.C[crow + n] = apply_epilogue(E, acc[j], m, n, crow);
+          if (n < p.N) E.C[crow + n] = apply_epilogue(E, acc[j], mp, n, crow);
         }
       }
     }
@@ -298,7 +322,7 @@ template <int BN, int AMODE, bool AKF, int BMODE, bool BKF>
 int launch_bn(const Bf16Params& bp, cudaStream_t st) {
   const GemmParams& p = bp.g;
   auto kern = gemm_bf16_kernel<BN, AMODE, AKF, BMODE, BKF>;
-  const int smem = STAGES * (BM * 128 + BN * 128) + 1024;
+  const int smem = STAGES * (int)(TileGather<BM, AMODE, AKF>::BYTES + TileGather<BN, BMODE, BKF>::BYTES) + 1024;
   static bool configured = false;  // per instantiation
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
@@ -343,16 +367,19 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 bool vec_ok(const Operand& o, int mode) {
   if (!aligned16(o.p)) return false;
   if (mode == OP_DENSE) {
-    if (o.ks != 1) return false;
-    if (o.r_inner > 0) return (o.rs_outer % 4 == 0) && (o.rs_inner % 4 == 0);
-    return o.rs % 4 == 0;
+    if (o.ks == 1) {   // K-major: 8 consecutive k
+      if (o.r_inner > 0) return (o.rs_outer % 4 == 0) && (o.rs_inner % 4 == 0);
+      return o.rs % 4 == 0;
+    }
+    return o.rs == 1 && o.r_inner == 0 && o.ks % 4 == 0;   // MN-major: 8 consecutive rows
   }
   const ConvGeom& g = o.g;
-  if (mode == OP_IM2COL) {
+  if (mode == OP_IM2COL || mode == OP_IM2COL_T) {
     if (g.nhwc) return g.C % 8 == 0;
     return g.KW == 8 && g.W % 4 == 0 && g.stride % 4 == 0 && (g.H * g.W) % 4 == 0;
   }
   if (mode == OP_DGRAD) return g.Cout % 8 == 0;
+  if (mode == OP_DGRAD_W) return g.C % 8 == 0;
   return false;
 }
 
@@ -362,9 +389,9 @@ int dispatch(GemmParams& p, int amode, int bmode, cudaStream_t st) {
   bp.g = p;
   bool akf = (amode == OP_DENSE) ? (p.A.ks == 1) : true;
   bool bkf = (bmode == OP_DENSE) ? (p.B.ks == 1) : false;
-  bp.vecA = akf && vec_ok(p.A, amode);
-  bp.vecB = bkf && vec_ok(p.B, bmode);
-  if (amode == OP_DGRAD && p.A.g.Cout % 8 != 0) { hulc2_set_error("bf16 conv dgrad needs Cout % 8 == 0"); return HULC2_EINVAL; }
+  if (amode == OP_DGRAD && (p.A.g.Cout % 8 != 0 || ((uintptr_t)p.A.p & 15))) { hulc2_set_error("bf16 conv dgrad needs Cout % 8 == 0 and 16-byte aligned dy"); return HULC2_EINVAL; }
+  bp.vecA = vec_ok(p.A, amode);
+  bp.vecB = vec_ok(p.B, bmode);
   if (amode == OP_DENSE && bmode == OP_DENSE) {
     if (akf && bkf) return launch_modes<OP_DENSE, true, OP_DENSE, true>(bp, st);
     if (akf && !bkf) return launch_modes<OP_DENSE, true, OP_DENSE, false>(bp, st);
@@ -373,7 +400,7 @@ int dispatch(GemmParams& p, int amode, int bmode, cudaStream_t st) {
   }
   if (amode == OP_IM2COL && bmode == OP_DENSE && bkf) return launch_modes<OP_IM2COL, true, OP_DENSE, true>(bp, st);
   if (amode == OP_DENSE && !akf && bmode == OP_IM2COL_T) return launch_modes<OP_DENSE, false, OP_IM2COL_T, false>(bp, st);
-  if (amode == OP_DGRAD && bmode == OP_DENSE && !bkf) return launch_modes<OP_DGRAD, true, OP_DENSE, false>(bp, st);
+  if (amode == OP_DGRAD && bmode == OP_DGRAD_W) return launch_modes<OP_DGRAD, true, OP_DGRAD_W, false>(bp, st);
   hulc2_set_error("gemm_bf16: unsupported operand mode combination");
   return HULC2_EINVAL;
 }
@@ -405,9 +432,12 @@ int hulc2_conv2d_wgrad_bf16_impl(const hulc2_conv_args* a, cudaStream_t st) {
   return dispatch(p, OP_DENSE, OP_IM2COL_T, st);
 }
 int hulc2_conv2d_dgrad_bf16_impl(const hulc2_conv_args* a, cudaStream_t st) {
-  GemmParams p;
-  conv_dgrad_params(a, p);
-  if (p.M == 0) return HULC2_OK;
-  plan_splitk(p, 1, 1, 1 << 30, BKE, nullptr, 0);
-  return dispatch(p, OP_DGRAD, OP_DENSE, st);
+  for (int ph = 0; ph < a->stride; ++ph)
+    for (int pw = 0; pw < a->stride; ++pw) {
+      GemmParams p;
+      if (!conv_dgrad_params(a, ph, pw, p)) continue;
+      plan_splitk(p, 1, 1, 1 << 30, BKE, nullptr, 0);
+      if (int e = dispatch(p, OP_DGRAD, OP_DGRAD_W, st)) return e;
+    }
+  return HULC2_OK;
 }

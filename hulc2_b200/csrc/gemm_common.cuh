@@ -7,10 +7,12 @@
 
 namespace hulc2 {
 
-enum { OP_DENSE = 0, OP_IM2COL = 1, OP_IM2COL_T = 2, OP_DGRAD = 3 };
+enum { OP_DENSE = 0, OP_IM2COL = 1, OP_IM2COL_T = 2, OP_DGRAD = 3, OP_DGRAD_W = 4 };
 
 struct ConvGeom {
   int C, H, W, KH, KW, OH, OW, stride, nhwc, Cout;
+  // input-gradient parity class (ih % stride == ph, iw % stride == pw): class extent CH x CW pixels, KA x KB taps
+  int ph, pw, CH, CW, KA, KB;
 };
 
 struct Operand {
@@ -36,6 +38,8 @@ struct Epilogue {
   float keep_scale;
   int relu, accumulate;
   float alpha;
+  // optional output-row remap for the strided input-gradient classes: m = (f, i, j) -> (f*H + i*s+ph)*W + j*s+pw
+  int rm_on, rm_chw, rm_cw, rm_s, rm_ph, rm_pw, rm_H, rm_W;
 };
 
 struct GemmParams {
@@ -75,6 +79,8 @@ __device__ __forceinline__ long long row_off(const Operand& o, int r) {
     return im2col_pixel_off(o.g, r);
   } else if (MODE == OP_IM2COL_T) {
     return im2col_k_off(o.g, r);
+  } else if (MODE == OP_DGRAD_W) {
+    return r;
   }
   return 0;
 }
@@ -83,18 +89,38 @@ __device__ __forceinline__ long long col_off(const Operand& o, int k) {
   if (MODE == OP_DENSE) return (long long)k * o.ks;
   if (MODE == OP_IM2COL) return im2col_k_off(o.g, k);
   if (MODE == OP_IM2COL_T) return im2col_pixel_off(o.g, k);
+  if (MODE == OP_DGRAD_W) {  // k = (a, b, co) of the parity class -> w_hwoi[kh = ph + a s][kw = pw + b s][co][:]
+    const ConvGeom& g = o.g;
+    int bc = g.KB * g.Cout;
+    int a = k / bc, rem = k - a * bc;
+    int b = rem / g.Cout, co = rem - b * g.Cout;
+    return ((long long)((g.ph + a * g.stride) * g.KW + (g.pw + b * g.stride)) * g.Cout + co) * g.C;
+  }
   return 0;
 }
 
-// dgrad gather: row r = input pixel (f, ih, iw) of the NHWC input-gradient, k = (kh, kw, co).
-// value = dZ[f, (ih-kh)/s, (iw-kw)/s, co] when the division is exact and in range, else 0.
-__device__ __forceinline__ float dgrad_load(const Operand& o, int f, int ih, int iw, int kh, int kw, int co) {
-  const ConvGeom& g = o.g;
-  int th = ih - kh, tw = iw - kw;
-  if (th < 0 || tw < 0) return 0.f;
-  int oh = th / g.stride, ow = tw / g.stride;
-  if (oh * g.stride != th || ow * g.stride != tw || oh >= g.OH || ow >= g.OW) return 0.f;
-  return o.p[(((long long)f * g.OH + oh) * g.OW + ow) * g.Cout + co];
+// dgrad gather within one parity class: row = class pixel (f, i, j) [input pixel ih = i s + ph, iw = j s + pw],
+// k = (a, b, co) [tap kh = ph + a s, kw = pw + b s]  ->  dZ[f, i - a, j - b, co] when in range, else 0.
+// Only taps that can reach the class are enumerated, so a stride-2 4x4 conv needs K = 2*2*Cout instead of 4*4*Cout.
+__device__ __forceinline__ bool dgrad_src(const ConvGeom& g, int f, int i, int j, int a, int b, long long& off) {
+  int oh = i - a, ow = j - b;
+  if (oh < 0 || ow < 0 || oh >= g.OH || ow >= g.OW) return false;
+  off = (((long long)f * g.OH + oh) * g.OW + ow) * g.Cout;
+  return true;
+}
+__device__ __forceinline__ void dgrad_row_decode(const ConvGeom& g, int r, int& f, int& i, int& j) {
+  int chw = g.CH * g.CW;
+  f = r / chw;
+  int rem = r - f * chw;
+  i = rem / g.CW;
+  j = rem - i * g.CW;
+}
+__device__ __forceinline__ void dgrad_k_decode(const ConvGeom& g, int k, int& a, int& b, int& co) {
+  int bc = g.KB * g.Cout;
+  a = k / bc;
+  int rem = k - a * bc;
+  b = rem / g.Cout;
+  co = rem - b * g.Cout;
 }
 
 
@@ -108,6 +134,13 @@ __device__ __forceinline__ float apply_epilogue(const Epilogue& E, float acc, in
   if (E.mask) v = (E.mask[(long long)m * E.ld_mask + n] > 0.f) ? v : 0.f;
   if (E.keep) v = E.keep[(long long)m * E.ld_keep + n] ? v * E.keep_scale : 0.f;
   return v;
+}
+// logical output row -> physical row (identity unless the strided input-gradient remap is on)
+__device__ __forceinline__ int phys_row(const Epilogue& E, int m) {
+  if (!E.rm_on) return m;
+  int f = m / E.rm_chw, rem = m - f * E.rm_chw;
+  int i = rem / E.rm_cw, j = rem - i * E.rm_cw;
+  return (f * E.rm_H + i * E.rm_s + E.rm_ph) * E.rm_W + j * E.rm_s + E.rm_pw;
 }
 __device__ __forceinline__ long long c_row_off(const Epilogue& E, int m) {
   return E.c_inner > 0 ? (long long)(m / E.c_inner) * E.cs_outer + (long long)(m % E.c_inner) * E.cs_inner : (long long)m * E.ldc;
@@ -188,14 +221,23 @@ inline void conv_wgrad_params(const hulc2_conv_args* a, GemmParams& p) {
   fill_epilogue(p.E, a->dw, p.N);
   p.E.accumulate = a->accumulate;
 }
-inline void conv_dgrad_params(const hulc2_conv_args* a, GemmParams& p) {
+// one parity class (ph, pw) of the input gradient; returns false when the class is empty
+inline bool conv_dgrad_params(const hulc2_conv_args* a, int ph, int pw, GemmParams& p) {
   ConvGeom g = geom_of(a);
+  const int s = a->stride;
+  g.ph = ph; g.pw = pw;
+  g.CH = (a->H - ph + s - 1) / s; g.CW = (a->W - pw + s - 1) / s;
+  g.KA = (a->KH - ph + s - 1) / s; g.KB = (a->KW - pw + s - 1) / s;
   p = GemmParams{};
-  p.M = a->F * a->H * a->W; p.N = a->C; p.K = a->KH * a->KW * a->Cout;
+  if (ph >= a->H || pw >= a->W || g.CH <= 0 || g.CW <= 0) return false;
+  p.M = a->F * g.CH * g.CW; p.N = a->C; p.K = (g.KA > 0 && g.KB > 0) ? g.KA * g.KB * a->Cout : 0;
   p.A.p = a->dy; p.A.g = g;
-  p.B.p = a->w; p.B.rs = 1; p.B.ks = a->C;            // B(n=ci, k=(kh,kw,co)) = w_hwoi[k*C + ci]
+  p.B.p = a->w; p.B.rs = 1; p.B.ks = a->C; p.B.g = g; // B(n=ci, k=(a,b,co)) = w_hwoi[kh][kw][co][ci]
   fill_epilogue(p.E, a->dx, a->C);
   p.E.mask = a->xmask; p.E.ld_mask = a->C;
+  p.E.rm_on = 1; p.E.rm_chw = g.CH * g.CW; p.E.rm_cw = g.CW; p.E.rm_s = s; p.E.rm_ph = ph; p.E.rm_pw = pw;
+  p.E.rm_H = a->H; p.E.rm_W = a->W;
+  return p.M > 0;
 }
 
 }  // namespace hulc2

@@ -39,9 +39,7 @@ struct TileLoader {
         rvalid[i] = r < nrows_total;
         int rr = rvalid[i] ? r : 0;
         if (MODE == OP_DGRAD) {
-          int hw = o.g.H * o.g.W;
-          int f = rr / hw, rem = rr - f * hw;
-          rdec[i][0] = f; rdec[i][1] = rem / o.g.W; rdec[i][2] = rem - (rem / o.g.W) * o.g.W;
+          dgrad_row_decode(o.g, rr, rdec[i][0], rdec[i][1], rdec[i][2]);
           roff[i] = 0;
         } else {
           roff[i] = row_off<MODE>(o, rr);
@@ -61,13 +59,13 @@ struct TileLoader {
       int kg = k0 + klane;
       bool kv = kg < kend;
       if (MODE == OP_DGRAD) {
-        int kwc = o.g.KW * o.g.Cout;
-        int kk = kv ? kg : 0;
-        int kh = kk / kwc, rem = kk - kh * kwc;
-        int kw = rem / o.g.Cout, co = rem - kw * o.g.Cout;
+        int ta, tb, co;
+        dgrad_k_decode(o.g, kv ? kg : 0, ta, tb, co);
 #pragma unroll
-        for (int i = 0; i < PER; ++i)
-          v[i] = (kv && rvalid[i]) ? dgrad_load(o, rdec[i][0], rdec[i][1], rdec[i][2], kh, kw, co) : 0.f;
+        for (int i = 0; i < PER; ++i) {
+          long long off;
+          v[i] = (kv && rvalid[i] && dgrad_src(o.g, rdec[i][0], rdec[i][1], rdec[i][2], ta, tb, off)) ? __ldg(o.p + off + co) : 0.f;
+        }
       } else {
         long long koff = col_off<MODE>(o, kv ? kg : 0);
 #pragma unroll
@@ -190,12 +188,13 @@ __global__ void __launch_bounds__(NTHREADS) gemm_f32_kernel(const GemmParams p) 
       }
       continue;
     }
-    long long crow = c_row_off(E, m);
+    const int mp = phys_row(E, m);
+    long long crow = c_row_off(E, mp);
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       int n = n0 + tile_idx<TN, BN>(tx, j);
       if (n >= p.N) continue;
-      E.C[crow + n] = apply_epilogue(E, acc[i][j], m, n, crow);
+      E.C[crow + n] = apply_epilogue(E, acc[i][j], mp, n, crow);
     }
   }
 }
@@ -235,7 +234,7 @@ int dispatch(const GemmParams& p, int amode, int bmode, cudaStream_t st) {
   }
   if (amode == OP_IM2COL && bmode == OP_DENSE && bkf) return launch_modes<OP_IM2COL, true, OP_DENSE, true>(p, st);
   if (amode == OP_DENSE && !akf && bmode == OP_IM2COL_T) return launch_modes<OP_DENSE, false, OP_IM2COL_T, false>(p, st);
-  if (amode == OP_DGRAD && bmode == OP_DENSE && !bkf) return launch_modes<OP_DGRAD, true, OP_DENSE, false>(p, st);
+  if (amode == OP_DGRAD && bmode == OP_DGRAD_W) return launch_modes<OP_DGRAD, true, OP_DGRAD_W, false>(p, st);
   hulc2_set_error("gemm_f32: unsupported operand mode combination");
   return HULC2_EINVAL;
 }
@@ -274,9 +273,12 @@ int hulc2_conv2d_wgrad_f32_impl(const hulc2_conv_args* a, cudaStream_t st) {
 
 // dx[F,H,W,C] (NHWC) = gather-conv(dZ[F,OH,OW,Cout], w_hwoi[KH,KW,Cout,C]) masked by (xmask > 0) (ReLU of the producer)
 int hulc2_conv2d_dgrad_f32_impl(const hulc2_conv_args* a, cudaStream_t st) {
-  GemmParams p;
-  conv_dgrad_params(a, p);
-  if (p.M == 0) return HULC2_OK;
-  plan_splitk(p, 1, 1, 1 << 30, BK, nullptr, 0);
-  return dispatch(p, OP_DGRAD, OP_DENSE, st);
+  for (int ph = 0; ph < a->stride; ++ph)
+    for (int pw = 0; pw < a->stride; ++pw) {
+      GemmParams p;
+      if (!conv_dgrad_params(a, ph, pw, p)) continue;
+      plan_splitk(p, 1, 1, 1 << 30, BK, nullptr, 0);
+      if (int e = dispatch(p, OP_DGRAD, OP_DGRAD_W, st)) return e;
+    }
+  return HULC2_OK;
 }

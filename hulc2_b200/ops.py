@@ -516,6 +516,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         In = wi0.shape[1]
         assert In == P + Es + G
         dev = plan.device
+        ws = workspace(dev)
         embT = torch.empty(S, B, Es, device=dev, dtype=torch.float32)
         assert emb.stride(2) == 1
         call("hulc2_transpose01", emb.data_ptr(), emb.stride(0), emb.stride(1), embT.data_ptr(), Es, B, S, Es, 0)
@@ -534,11 +535,11 @@ class RNNDecoderFunction(torch.autograd.Function):
         h00 = h0[0].contiguous() if h0 is not None else None
         h01 = h0[1].contiguous() if h0 is not None else None
         _lib.tag(f"rnn_relu_fwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
-        call("hulc2_rnn_relu_fwd", pre.data_ptr(), wh0.data_ptr(), _p(h00), H0.data_ptr(), S, B, H, _lib_precision())
+        call("hulc2_rnn_relu_fwd", pre.data_ptr(), wh0.data_ptr(), _p(h00), H0.data_ptr(), S, B, H, _lib_precision(), ws.data_ptr(), ws.numel())
         gemm(S * B, H, H, H0, H, 1, wi1, H, 1, pre, H, bias=bsum1)
         H1 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         _lib.tag(f"rnn_relu_fwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
-        call("hulc2_rnn_relu_fwd", pre.data_ptr(), wh1.data_ptr(), _p(h01), H1.data_ptr(), S, B, H, _lib_precision())
+        call("hulc2_rnn_relu_fwd", pre.data_ptr(), wh1.data_ptr(), _p(h01), H1.data_ptr(), S, B, H, _lib_precision(), ws.data_ptr(), ws.numel())
         hn = torch.empty(2, B, H, device=dev, dtype=torch.float32)
         call("hulc2_copy2d", H0.data_ptr() + 4 * (S - 1) * B * H, B * H, hn.data_ptr(), B * H, 1, B * H, 0)
         call("hulc2_copy2d", H1.data_ptr() + 4 * (S - 1) * B * H, B * H, hn.data_ptr() + 4 * B * H, B * H, 1, B * H, 0)
@@ -554,13 +555,14 @@ class RNNDecoderFunction(torch.autograd.Function):
         plan, embT, goal, H0, H1, wi0, wh0, wi1, wh1, h00, h01 = ctx.saved_tensors
         B, S, Es, P, G, H, In = ctx.dims
         dev = plan.device
+        ws = workspace(dev)
         prec = _lib_precision()
         step = B * H
         dH1 = dH1.contiguous()
         dz1 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         call("hulc2_copy2d", dH1.data_ptr(), step, dz1.data_ptr(), step, S, step, 0)
         _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
-        call("hulc2_rnn_relu_bwd", dz1.data_ptr(), wh1.data_ptr(), H1.data_ptr(), None, S, B, H, prec)
+        call("hulc2_rnn_relu_bwd", dz1.data_ptr(), wh1.data_ptr(), H1.data_ptr(), None, S, B, H, prec, ws.data_ptr(), ws.numel())
         dwh1 = torch.empty_like(wh1)
         if S > 1:
             gemm(H, H, (S - 1) * B, dz1, 1, H, H1, 1, H, dwh1, H, a_off=step)
@@ -575,7 +577,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         dz0 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         gemm(S * B, H, H, dz1, H, 1, wi1, 1, H, dz0, H)                      # dH0 = dz1 W_ih1
         _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
-        call("hulc2_rnn_relu_bwd", dz0.data_ptr(), wh0.data_ptr(), H0.data_ptr(), None, S, B, H, prec)
+        call("hulc2_rnn_relu_bwd", dz0.data_ptr(), wh0.data_ptr(), H0.data_ptr(), None, S, B, H, prec, ws.data_ptr(), ws.numel())
         dwh0 = torch.empty_like(wh0)
         if S > 1:
             gemm(H, H, (S - 1) * B, dz0, 1, H, H0, 1, H, dwh0, H, a_off=step)

@@ -179,9 +179,11 @@ int hulc2_infonce_bwd(const float* img, const float* txt, const unsigned char* u
  * Elman ReLU RNN layer over time-major buffers: h[t] = relu(pre[t] + h[t-1] W_hh^T), pre [S,B,H] already holds
  * W_ih x_t + b_ih + b_hh.  bwd: dz[t] = (dh_out[t] + dz[t+1] W_hh) * (h[t] > 0), in place over dh (becomes dz). */
 int hulc2_rnn_relu_fwd(const float* pre, const float* w_hh, const float* h0, float* h, int S, int B, int H,
-                       int precision, hulc2_stream_t stream);
+                       int precision, void* workspace, long long workspace_bytes, hulc2_stream_t stream);
 int hulc2_rnn_relu_bwd(float* dh_inout, const float* w_hh, const float* h, float* dh0, int S, int B, int H,
-                       int precision, hulc2_stream_t stream);
+                       int precision, void* workspace, long long workspace_bytes, hulc2_stream_t stream);
+/* precision 1 with B <= 128, H % 64 == 0, H/16 <= #SMs and workspace >= 2*S*B*H + 256 bytes runs all S steps in ONE
+ * persistent tcgen05 kernel (W_hh slice resident in shared memory, grid barrier per step); otherwise one GEMM per step. */
 
 /* ------------------------------------------------------------------ optimizer + noise
  * Adam (torch.optim.Adam semantics, conf/model/optimizer/adam.yaml): one launch over a flat arena. */

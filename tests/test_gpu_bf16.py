@@ -215,3 +215,35 @@ def test_rollout_bf16_argmax_and_actions():
             a = m.step(obs, goal)
         assert a.shape == (4, 1, 7) and bool(torch.isfinite(a).all())
         assert set(a[..., -1].unique().tolist()) <= {-1.0, 1.0}
+
+
+@pytest.mark.parametrize("B,S,H,with_h0", [(64, 32, 2048, False), (5, 3, 2048, True), (128, 4, 1024, True)])
+def test_persistent_rnn_matches_step_loop(B, S, H, with_h0):
+    """Persistent tcgen05 recurrence (one launch for all steps) vs the fp32 per-step kernels."""
+    from hulc2_b200 import ops
+    from hulc2_b200._lib import call
+
+    dev = torch.device(DEV)
+    pre = _rand(S, B, H, seed=1).to(dev)
+    w = _rand(H, H, seed=2, scale=0.02).to(dev)
+    h0 = _rand(B, H, seed=3).abs().to(dev) if with_h0 else None
+    ws = ops.workspace(dev)
+    outs = []
+    for prec in (0, 1):
+        h = torch.empty(S, B, H, device=dev)
+        call("hulc2_rnn_relu_fwd", pre.data_ptr(), w.data_ptr(), None if h0 is None else h0.data_ptr(), h.data_ptr(), S, B, H, prec, ws.data_ptr(), ws.numel())
+        outs.append(h)
+    torch.cuda.synchronize()
+    assert_close(outs[1], outs[0], 2e-2, "forward states")
+    dh = _rand(S, B, H, seed=4).to(dev)
+    res = []
+    for prec in (0, 1):
+        d = dh.clone()
+        dh0 = torch.empty(B, H, device=dev)
+        call("hulc2_rnn_relu_bwd", d.data_ptr(), w.data_ptr(), outs[0].data_ptr(), dh0.data_ptr(), S, B, H, prec, ws.data_ptr(), ws.numel())
+        res.append((d, dh0))
+    torch.cuda.synchronize()
+    assert_close(res[1][0], res[0][0], 2e-2, "backward dz")
+    assert_close(res[1][1], res[0][1], 2e-2, "dh0")
+    # ReLU mask is exact: zeros where h == 0
+    assert bool(((outs[0] <= 0) <= (res[1][0] == 0)).all())
