@@ -49,6 +49,16 @@ class ConvArgs(C.Structure):
     ]
 
 
+class ConvbArgs(C.Structure):
+    _fields_ = [
+        ("F", I), ("C", I), ("H", I), ("W", I), ("Cout", I), ("KH", I), ("KW", I), ("stride", I),
+        ("x", P), ("w", P), ("bias", P), ("y", P), ("relu", I),
+        ("dy", P), ("dx", P), ("xmask", P),
+        ("dw", P), ("db", P), ("dw_layout", I),
+        ("workspace", P), ("workspace_bytes", LL),
+    ]
+
+
 # name -> argtypes (without the trailing stream); every function returns int and takes a stream last
 _SIGS = {
     "hulc2_gemm": [C.POINTER(GemmArgs)],
@@ -56,6 +66,15 @@ _SIGS = {
     "hulc2_conv2d_wgrad": [C.POINTER(ConvArgs)],
     "hulc2_conv2d_dgrad": [C.POINTER(ConvArgs)],
     "hulc2_permute_conv_weight": [P, P, I, I, I, I, I, I],
+    "hulc2_pack_frames_bf16": [P, P, I, I, I, I],
+    "hulc2_convb_pack_weight": [P, P, I, I, I, I, I, I],
+    "hulc2_convb_fwd": [C.POINTER(ConvbArgs)],
+    "hulc2_convb_dgrad": [C.POINTER(ConvbArgs)],
+    "hulc2_convb_wgrad": [C.POINTER(ConvbArgs)],
+    "hulc2_spatial_softmax_fwd_bf16": [P, P, P, P, P, I, I, I],
+    "hulc2_spatial_softmax_bwd_bf16": [P, P, P, P, P, P, P, I, I, I, I],
+    "hulc2_nhwc_bf16_to_nchw": [P, P, I, I, I],
+    "hulc2_nchw_to_nhwc_bf16": [P, P, I, I, I, P],
     "hulc2_copy2d": [P, LL, P, LL, LL, I, I],
     "hulc2_transpose01": [P, LL, LL, P, LL, I, I, I, I],
     "hulc2_fill": [P, LL, F],
@@ -94,7 +113,7 @@ _SIGS = {
     "hulc2_dropout_mask": [P, LL, F, C.c_ulonglong, C.c_ulonglong],
 }
 _NO_STREAM = {"hulc2_last_error": (C.c_char_p, []), "hulc2_version": (I, []), "hulc2_device_supports_tcgen05": (I, []),
-              "hulc2_launch_count": (C.c_ulonglong, [])}
+              "hulc2_launch_count": (C.c_ulonglong, []), "hulc2_convb_supported": (I, [I, I, I, I, I])}
 
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + list(_NO_STREAM))
 

@@ -1,0 +1,643 @@
+// bf16 convolution trunk for sm_100a: persistent, warp-specialised implicit GEMMs on tcgen05/TMEM.
+//
+// Activations are bf16 NHWC in HBM (half the bytes of the fp32 path, and every im2col row is made of
+// contiguous >= 64-byte segments), so operand tiles are gathered with 16-byte cp.async (LDGSTS) straight into
+// the canonical SWIZZLE_128B layout -- no register staging, several stages in flight per SM.
+//
+//   conv_igemm_kernel (forward and input-gradient):  D[pixels, N] = A[pixels, K] . W[N, K]^T
+//     * one CTA per SM, static round-robin over 128-pixel tiles; the whole packed weight matrix (<= 72 KB) is
+//       resident in shared memory for the lifetime of the CTA, only A streams;
+//     * warps 5-8 produce A stages (6-deep ring, cp.async + per-thread wait_group/fence.proxy.async/arrive),
+//       warp 4 issues tcgen05.mma (128 x N x 16) and commits to the ring's empty barriers,
+//       warps 0-3 drain the double-buffered TMEM accumulator (tcgen05.ld), apply bias+ReLU (forward) or the
+//       ReLU mask of the producing layer (input gradient) and store bf16 rows;
+//     * the input gradient of a stride-s conv runs as s*s parity classes (only taps that reach a class are
+//       contracted), all classes of a layer in ONE launch; out-of-range taps are zero-filled by cp.async.
+//   conv_wgrad_kernel:  dW^T[kconv, Cout] = sum_pixels im2col[pixel, kconv] * dZ[pixel, Cout]
+//     * both operands are MN-major (the contraction index = pixel is the slow axis of both tensors);
+//       each CTA owns a contiguous pixel range and keeps ALL of dW^T in TMEM (<= 5 x 64 columns);
+//     * a constant block of ones appended to the im2col operand yields the bias gradient for free;
+//     * per-CTA partials go to the workspace, a second kernel reduces them and scatters into OIHW order.
+//
+// Layer 1 reads "packed frames": fp32 NCHW images re-tiled once per step by pack_frames_kernel into bf16
+// [F, H/4, W/4, 16*C] (space-to-depth by the stride), which turns the k8/s4 conv into a k2/s1 conv over 16*C
+// channels whose im2col rows are KH contiguous segments of 2*16*C elements.
+// Reference: hulc2/models/perceptual_encoders/vision_network.py:38-48, vision_network_gripper.py:11-26.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "sm100.cuh"
+#include "../../include/hulc2_b200.h"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int KT = 64;                       // k per stage (one 128-byte swizzle row)
+constexpr int STAGES = 6;
+constexpr int LAG = 3;                       // cp.async groups in flight per producer thread before a stage is published
+constexpr uint32_t A_STAGE = TILE_M * 128;   // 16 KB
+constexpr int N_EPI = 128, N_PROD = 128;
+constexpr int NT = N_EPI + 32 + N_PROD;      // 288 threads: warps 0-3 epilogue, 4 MMA, 5-8 producers
+constexpr int MAX_CLS = 4;
+constexpr int MAX_TAB = 160;
+
+struct ConvClass {
+  int M;                 // rows (pixels) of this class
+  int PH, PW;            // row r -> (f, i, j): f = r / (PH*PW), i = rem / PW, j = rem % PW
+  int tile_begin;        // first tile of this class in the launch-wide tile order
+  int K;                 // contraction length (multiple of 64)
+  int w_off;             // byte offset of this class's packed weights [N][K]
+  int tab_off;           // first chunk-table entry of this class
+  int sF, sI, sJ;        // source base of row (f,i,j) in 16-byte units
+  int oS, oPh, oPw;      // output pixel of row (f,i,j): (f*oH + i*oS + oPh)*oW + j*oS + oPw
+};
+
+struct ConvParams {
+  const uint8_t* x;      // bf16 source tensor
+  const uint8_t* w;      // packed bf16 weights, all classes
+  const float* bias;     // [N] or null
+  const uint8_t* mask;   // bf16, same shape as the output: keep where > 0 (or null)
+  uint8_t* y;            // bf16 output [*, N]
+  int ncls, ntiles, N, relu;
+  int VH, VW;            // a tap (a, b) of row (f,i,j) is valid iff 0 <= i-a < VH and 0 <= j-b < VW
+  int oH, oW;
+  int w_bytes;           // total packed weight bytes
+  int ntab;
+  ConvClass cls[MAX_CLS];
+  int2 table[MAX_TAB];   // per 16-byte chunk of K: {delta in 16-byte units, (a << 16) | b}
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int2 tab_s[MAX_TAB];
+  __shared__ float bias_s[BN];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_smem = base;                              // STAGES x 16 KB
+  const uint32_t w_smem = base + STAGES * A_STAGE;           // per class: K/64 tiles of [BN rows][128 B]
+  constexpr uint32_t W_TILE = BN * 128;
+  constexpr uint32_t TCOLS = 2 * BN;                         // double-buffered accumulator
+
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), TCOLS);
+  if (tid == 32) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), N_PROD); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), N_EPI); }
+    mbar_fence_init();
+  }
+  for (int i = tid; i < p.ntab; i += NT) tab_s[i] = p.table[i];
+  if (tid < BN) bias_s[tid] = p.bias ? p.bias[tid] : 0.f;
+  // resident weights: [N][K] bf16 per class -> K-major SWIZZLE_128B tiles
+  for (int c = 0; c < p.ncls; ++c) {
+    const int K = p.cls[c].K, cpr = K >> 3;                  // 16-byte chunks per weight row
+    const uint8_t* src = p.w + p.cls[c].w_off;
+    const uint32_t dst0 = w_smem + p.cls[c].w_off;
+    for (int ch = tid; ch < BN * cpr; ch += NT) {
+      const int n = ch / cpr, q = ch - n * cpr;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)n * K + q * 8) * 2));
+      const uint32_t dst = dst0 + (uint32_t)(q >> 3) * W_TILE + swz128(n, q & 7);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  auto class_of = [&](int tile) {
+    int c = 0;
+#pragma unroll
+    for (int k = 1; k < MAX_CLS; ++k) if (k < p.ncls && tile >= p.cls[k].tile_begin) c = k;
+    return c;
+  };
+
+  if (warp >= 5) {
+    // ===================================================== producers
+    const int t = tid - (N_EPI + 32);
+    const int c8 = t & 7, r0 = t >> 3;                       // chunk column, first row; rows r0 + 16 i
+    const uint32_t dst_t = swz128(r0, c8);                   // + i * 2048 (16 rows = 2 atoms)
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const ConvClass& cl = p.cls[class_of(tile)];
+      const int m0 = (tile - cl.tile_begin) * TILE_M;
+      int rbase[8];
+      uint32_t rij[8];
+      {
+        int r = m0 + r0;
+        const int hw = cl.PH * cl.PW;
+        int f = r / hw, rem = r - f * hw;
+        int i = rem / cl.PW, j = rem - i * cl.PW;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          rbase[q] = f * cl.sF + i * cl.sI + j * cl.sJ;
+          rij[q] = (r < cl.M) ? (((uint32_t)i << 16) | (uint32_t)j) : 0x7fff7fffu;
+          r += 16; j += 16;
+          while (j >= cl.PW) { j -= cl.PW; ++i; }
+          while (i >= cl.PH) { i -= cl.PH; ++f; }
+        }
+      }
+      const int nkt = cl.K / KT;
+      for (int kt = 0; kt < nkt; ++kt, ++it) {
+        const uint32_t s = it % STAGES;
+        mbar_wait(smem_u32(&empty_bar[s]), ((it / STAGES) & 1) ^ 1);
+        const int2 e = tab_s[cl.tab_off + kt * 8 + c8];
+        const int ta = e.y >> 16, tb = e.y & 0xffff;
+        const uint32_t dst = a_smem + s * A_STAGE + dst_t;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int ii = (int)(rij[q] >> 16) - ta, jj = (int)(rij[q] & 0xffff) - tb;
+          const bool ok = (unsigned)ii < (unsigned)p.VH && (unsigned)jj < (unsigned)p.VW;
+          const uint8_t* src = ok ? p.x + ((long long)(rbase[q] + e.x) << 4) : p.x;
+          cp_async16_ca(dst + q * 2048, src, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        if (it >= LAG) {
+          cp_async_wait<LAG>();
+          fence_proxy_async();
+          mbar_arrive(smem_u32(&full_bar[(it - LAG) % STAGES]));
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (uint32_t k = (it > LAG ? it - LAG : 0); k < it; ++k) mbar_arrive(smem_u32(&full_bar[k % STAGES]));
+  } else if (warp == 4) {
+    // ===================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t IDESC = make_idesc(TILE_M, BN, false, false);
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+        const ConvClass& cl = p.cls[class_of(tile)];
+        const uint32_t buf = ti & 1;
+        mbar_wait(smem_u32(&tempty_bar[buf]), ((ti >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+        tc_fence_after();
+        const int nkt = cl.K / KT;
+        for (int kt = 0; kt < nkt; ++kt, ++it) {
+          const uint32_t s = it % STAGES;
+          mbar_wait(smem_u32(&full_bar[s]), (it / STAGES) & 1);
+          tc_fence_after();
+          const uint64_t ad = make_desc(a_smem + s * A_STAGE, 0), bd = make_desc(w_smem + cl.w_off + kt * W_TILE, 0);
+#pragma unroll
+          for (int k = 0; k < KT / 16; ++k) umma_bf16(tmem_d + buf * BN, ad + 2 * k, bd + 2 * k, IDESC, (kt > 0 || k > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&empty_bar[s]));                          // stage reusable once these MMAs retire
+        }
+        umma_commit(smem_u32(&tfull_bar[buf]));                          // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue (warps 0-3 <-> TMEM lanes 32w..32w+31)
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+      const ConvClass& cl = p.cls[class_of(tile)];
+      const uint32_t buf = ti & 1;
+      const int r = (tile - cl.tile_begin) * TILE_M + warp * 32 + lane;
+      mbar_wait(smem_u32(&tfull_bar[buf]), (ti >> 1) & 1);
+      tc_fence_after();
+      uint32_t acc[BN];
+#pragma unroll
+      for (int c = 0; c < BN; c += 16) tmem_ld16_nowait(tmem_d + ((uint32_t)(warp * 32) << 16) + buf * BN + c, *reinterpret_cast<uint32_t(*)[16]>(&acc[c]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tempty_bar[buf]));
+      if (r < cl.M) {
+        const int hw = cl.PH * cl.PW;
+        const int f = r / hw, rem = r - f * hw;
+        const int i = rem / cl.PW, j = rem - i * cl.PW;
+        const long long opix = ((long long)f * p.oH + i * cl.oS + cl.oPh) * p.oW + j * cl.oS + cl.oPw;
+        uint4* out = reinterpret_cast<uint4*>(p.y + opix * (BN * 2));
+        const uint4* mk = p.mask ? reinterpret_cast<const uint4*>(p.mask + opix * (BN * 2)) : nullptr;
+#pragma unroll
+        for (int c = 0; c < BN; c += 8) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[c + e]) + bias_s[c + e];
+          if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (mk) {
+            const uint4 m = __ldg(mk + (c >> 3));
+            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (!(bf16_lo(mw[e]) > 0.f)) v[2 * e] = 0.f;
+              if (!(bf16_hi(mw[e]) > 0.f)) v[2 * e + 1] = 0.f;
+            }
+          }
+          out[c >> 3] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, TCOLS);
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+constexpr int WG_KP = 32;                     // pixels (contraction rows) per stage
+constexpr int WG_STAGES = 4;
+constexpr int WG_LAG = 2;
+constexpr uint32_t WG_BLK = WG_KP * 128;      // one 64-wide M/N block of a stage: 32 k-rows x 128 B = 4 KB
+constexpr int WG_MAX_BLK = 10;                // <= 5 M-tiles of 128 -> 320 TMEM columns
+
+struct WgradParams {
+  const uint8_t* x;      // bf16 NHWC input of the conv
+  const uint8_t* dz;     // bf16 [P, Cout]
+  float* partial;        // [grid][nblk*64][64] fp32
+  int P, PH, PW;         // pixels = F*OH*OW; pixel -> (f, oh, ow)
+  int sF, sI, sJ;        // im2col row base in 16-byte units
+  int K;                 // kconv (multiple of 64); data blocks = K/64; ones block = K/64; nblk (even) >= K/64 + 1
+  int nblk;
+  int cout8;             // Cout / 8 (4 or 8)
+  int nstages;           // ceil(P / 32)
+  int delta[72];         // per 16-byte chunk of kconv: offset in 16-byte units
+};
+
+__global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[WG_STAGES], empty_bar[WG_STAGES], done_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int delta_s[72];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = (uint32_t)(p.nblk + 1) * WG_BLK;          // A blocks + the dZ block
+  const int nbd = p.K / 64;                                               // data blocks
+  const int nmt = p.nblk / 2;
+  const uint32_t tcols = nmt * 64 <= 64 ? 64u : (nmt * 64 <= 128 ? 128u : (nmt * 64 <= 256 ? 256u : 512u));
+
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), tcols);
+  if (tid == 32) {
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), N_PROD); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    mbar_init(smem_u32(&done_bar), 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < p.K / 8; i += NT) delta_s[i] = p.delta[i];
+  // zero every stage, then fill the ones block (bf16 1.0 = 0x3F80) -- neither is touched by the producers
+  for (uint32_t o = tid * 16; o < WG_STAGES * stage_bytes; o += NT * 16)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(0u) : "memory");
+  __syncthreads();
+  for (int s = 0; s < WG_STAGES; ++s)
+    for (uint32_t o = tid * 16; o < WG_BLK; o += NT * 16)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + s * stage_bytes + nbd * WG_BLK + o), "r"(0x3F803F80u) : "memory");
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  // contiguous stage range of this CTA (every CTA gets at least one stage: grid <= nstages)
+  const int sbeg = (int)((long long)p.nstages * blockIdx.x / gridDim.x);
+  const int send = (int)((long long)p.nstages * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp >= 5) {
+    const int t = tid - (N_EPI + 32);
+    const int c8 = t & 7, g = t >> 3;                        // chunk-in-row; pixel group: pixels g and g + 16
+    // running decode of the two pixels this thread serves
+    int pf[2], pi[2], pj[2];
+    const int hw = p.PH * p.PW;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      long long pix = (long long)sbeg * WG_KP + g + 16 * h;
+      pf[h] = (int)(pix / hw);
+      int rem = (int)(pix - (long long)pf[h] * hw);
+      pi[h] = rem / p.PW;
+      pj[h] = rem - pi[h] * p.PW;
+    }
+    uint32_t it = 0;
+    for (int st = sbeg; st < send; ++st, ++it) {
+      const uint32_t s = it % WG_STAGES;
+      mbar_wait(smem_u32(&empty_bar[s]), ((it / WG_STAGES) & 1) ^ 1);
+      const uint32_t sb = base + s * stage_bytes;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int prow = g + 16 * h;
+        const long long pix = (long long)st * WG_KP + prow;
+        const bool ok = pix < p.P;
+        const int rb = pf[h] * p.sF + pi[h] * p.sI + pj[h] * p.sJ;
+        const uint32_t drow = sb + swz128(prow, c8);
+        for (int b = 0; b < nbd; ++b) {
+          const uint8_t* src = ok ? p.x + ((long long)(rb + delta_s[b * 8 + c8]) << 4) : p.x;
+          cp_async16_ca(drow + b * WG_BLK, src, ok ? 16u : 0u);
+        }
+        if (c8 < p.cout8) {
+          const uint8_t* src = ok ? p.dz + ((pix * p.cout8 + c8) << 4) : p.dz;
+          cp_async16(sb + p.nblk * WG_BLK + swz128(prow, c8), src, ok ? 16u : 0u);
+        }
+        // advance this pixel by one stage
+        pj[h] += WG_KP;
+        while (pj[h] >= p.PW) { pj[h] -= p.PW; ++pi[h]; }
+        while (pi[h] >= p.PH) { pi[h] -= p.PH; ++pf[h]; }
+      }
+      cp_async_commit();
+      if (it >= WG_LAG) {
+        cp_async_wait<WG_LAG>();
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&full_bar[(it - WG_LAG) % WG_STAGES]));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (uint32_t k = (it > WG_LAG ? it - WG_LAG : 0); k < it; ++k) mbar_arrive(smem_u32(&full_bar[k % WG_STAGES]));
+  } else if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = make_idesc(128, 64, true, true);
+      uint32_t it = 0;
+      for (int st = sbeg; st < send; ++st, ++it) {
+        const uint32_t s = it % WG_STAGES;
+        mbar_wait(smem_u32(&full_bar[s]), (it / WG_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sb = base + s * stage_bytes;
+#pragma unroll
+        for (int ks = 0; ks < WG_KP / 16; ++ks) {
+          const uint64_t bd = make_desc(sb + p.nblk * WG_BLK + ks * 2048, WG_BLK);
+          for (int mt = 0; mt < nmt; ++mt) {
+            const uint64_t ad = make_desc(sb + mt * 2 * WG_BLK + ks * 2048, WG_BLK);
+            umma_bf16(tmem_d + mt * 64, ad, bd, IDESC, (it > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      umma_commit(smem_u32(&done_bar));
+    }
+    __syncwarp();
+  } else {
+    mbar_wait(smem_u32(&done_bar), 0);
+    tc_fence_after();
+    float* out = p.partial + (size_t)blockIdx.x * p.nblk * 64 * 64;
+    for (int mt = 0; mt < nmt; ++mt) {
+      uint32_t acc[64];
+#pragma unroll
+      for (int c = 0; c < 64; c += 16) tmem_ld16_nowait(tmem_d + ((uint32_t)(warp * 32) << 16) + mt * 64 + c, *reinterpret_cast<uint32_t(*)[16]>(&acc[c]));
+      tmem_ld_wait();
+      float4* o4 = reinterpret_cast<float4*>(out + (size_t)(mt * 128 + warp * 32 + lane) * 64);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) o4[c] = make_float4(__uint_as_float(acc[4 * c]), __uint_as_float(acc[4 * c + 1]), __uint_as_float(acc[4 * c + 2]), __uint_as_float(acc[4 * c + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, tcols);
+}
+
+// dw (OIHW fp32) and db from the per-CTA partials.  layout 0: kconv = (kh, kw, ci);
+// layout 1 (packed frames): kconv = (dI, dJ, ci, a, b) -> kh = 4 dI + a, kw = 4 dJ + b of a [Cout, C/16, 4KH, 4KW] weight.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int rows_per_part, int K, int Cout, int C, int KH,
+                                    int KW, int layout, float* __restrict__ dw, float* __restrict__ db) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (k, co), co fastest; k == K is the ones row (bias)
+  if (idx >= (K + 1) * Cout) return;
+  const int k = idx / Cout, co = idx - k * Cout;
+  float s = 0.f;
+  for (int g = 0; g < nparts; ++g) s += partial[((size_t)g * rows_per_part + k) * 64 + co];
+  if (k == K) { if (db) db[co] = s; return; }
+  if (!dw) return;
+  int o;
+  if (layout == 0) {
+    const int ci = k % C, t = k / C, kw = t % KW, kh = t / KW;
+    o = ((co * C + ci) * KH + kh) * KW + kw;
+  } else {
+    const int c16 = k % C, t = k / C, dJ = t % KW, dI = t / KW;
+    const int ci = c16 >> 4, a = (c16 >> 2) & 3, b = c16 & 3;
+    o = ((co * (C >> 4) + ci) * (4 * KH) + 4 * dI + a) * (4 * KW) + 4 * dJ + b;
+  }
+  dw[o] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ packing
+// fp32 NCHW frames -> bf16 [F, H/4, W/4, 16 C] with channel order (ci, a, b) = x[f, ci, 4I + a, 4J + b]
+__global__ void pack_frames_kernel(const float* __restrict__ x, uint8_t* __restrict__ xs, int C, int H, int W, int H4, int W4) {
+  extern __shared__ float rows[];                      // [C][4][W4*4]
+  const int f = blockIdx.x / H4, I = blockIdx.x - f * H4;
+  const int wu = W4 * 4;
+  const int nq = C * 4 * W4;                           // float4 loads (when W % 4 == 0 and 16-byte aligned rows) else scalar
+  const bool vec = (W & 3) == 0;
+  for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+    const int j4 = q % W4, t = q / W4, a = t & 3, ci = t >> 2;
+    const float* src = x + (((size_t)f * C + ci) * H + 4 * I + a) * W + 4 * j4;
+    float4 v;
+    if (vec) v = __ldg(reinterpret_cast<const float4*>(src));
+    else v = make_float4(src[0], src[1], src[2], src[3]);
+    *reinterpret_cast<float4*>(&rows[(ci * 4 + a) * wu + 4 * j4]) = v;
+  }
+  __syncthreads();
+  const int c16 = 16 * C, cpc = c16 / 8;               // 16-byte output chunks per cell
+  uint4* out = reinterpret_cast<uint4*>(xs + ((size_t)f * H4 + I) * W4 * c16 * 2);
+  for (int q = threadIdx.x; q < W4 * cpc; q += blockDim.x) {
+    const int J = q / cpc, e0 = (q - J * cpc) * 8;     // 8 channels: ci = e0/16, a = (e0/4)&3 and a+1, b = 0..3
+    const int ci = e0 >> 4, a = (e0 >> 2) & 3;
+    const float4 lo = *reinterpret_cast<const float4*>(&rows[(ci * 4 + a) * wu + 4 * J]);
+    const float4 hi = *reinterpret_cast<const float4*>(&rows[(ci * 4 + a + 1) * wu + 4 * J]);
+    out[q] = make_uint4(pack_bf16x2(lo.x, lo.y), pack_bf16x2(lo.z, lo.w), pack_bf16x2(hi.x, hi.y), pack_bf16x2(hi.z, hi.w));
+  }
+}
+
+// mode 0: wp[co][(kh,kw,ci)] = w[co][ci][kh][kw];  mode 1: packed-frames order for a [Cout, Cin, 4KH, 4KW] weight:
+// wp[co][(dI,dJ,ci,a,b)] = w[co][ci][4dI+a][4dJ+b];  mode 2: input-gradient classes (ph,pw) of a stride-s conv:
+// wp[cls][ci][(a,b,co)] = w[co][ci][ph + a s][pw + b s].
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cout, int Cin, int KH, int KW, int mode,
+                                   int stride) {
+  const int total = Cout * Cin * KH * KW;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int kw = idx % KW, t = idx / KW, kh = t % KH, t2 = t / KH, ci = t2 % Cin, co = t2 / Cin;
+    int o;
+    if (mode == 0) {
+      o = ((co * KH + kh) * KW + kw) * Cin + ci;
+    } else if (mode == 1) {
+      const int dI = kh >> 2, a = kh & 3, dJ = kw >> 2, b = kw & 3;
+      o = (((co * (KH >> 2) + dI) * (KW >> 2) + dJ) * Cin + ci) * 16 + a * 4 + b;
+    } else {
+      const int ph = kh % stride, a = kh / stride, pw = kw % stride, b = kw / stride;
+      int off = 0;                                       // elements of the classes before (ph, pw)
+      for (int c = 0; c < ph * stride + pw; ++c) {
+        const int cph = c / stride, cpw = c % stride;
+        off += Cin * ((KH - cph + stride - 1) / stride) * ((KW - cpw + stride - 1) / stride) * Cout;
+      }
+      const int KB = (KW - pw + stride - 1) / stride, KA = (KH - ph + stride - 1) / stride;
+      o = off + ci * (KA * KB * Cout) + (a * KB + b) * Cout + co;
+    }
+    wp[o] = __float2bfloat16(w[idx]);
+  }
+}
+
+int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+template <int BN>
+int launch_igemm(const ConvParams& p, cudaStream_t st) {
+  auto kern = conv_igemm_kernel<BN>;
+  const int smem = STAGES * (int)A_STAGE + p.w_bytes + 1024;
+  if (smem > 227 * 1024) { hulc2_set_error("convb: packed weights do not fit in shared memory"); return HULC2_EINVAL; }
+  static int configured = 0;
+  if (configured < smem) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      hulc2_set_error("convb: cannot raise dynamic shared memory limit");
+      return HULC2_ELAUNCH;
+    }
+    configured = smem;
+  }
+  const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
+  kern<<<grid, NT, smem, st>>>(p);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+int check_convb(const hulc2_convb_args* a) {
+  if (!a || a->F < 0 || a->C <= 0 || a->Cout <= 0 || a->KH <= 0 || a->KW <= 0 || a->stride <= 0 || a->H < a->KH || a->W < a->KW) {
+    hulc2_set_error("convb: bad geometry");
+    return HULC2_EINVAL;
+  }
+  if (!hulc2_device_supports_tcgen05()) { hulc2_set_error("convb: needs an sm_100 device (tcgen05)"); return HULC2_ENOTIMPL; }
+  return HULC2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hulc2_convb_supported(int C, int Cout, int KH, int KW, int stride) {
+  if (C % 8 != 0 || (KH * KW * C) % 64 != 0) return 0;
+  if (Cout != 32 && Cout != 64) return 0;
+  if (KH * KW * C * Cout * 2 > 100 * 1024) return 0;
+  if (KH * KW * C / 8 > 72) return 0;
+  if (stride > 2 || stride < 1) return 0;
+  return 1;
+}
+
+int hulc2_pack_frames_bf16(const float* x, void* xs, int F, int C, int H, int W, cudaStream_t st) {
+  if (F <= 0) return HULC2_OK;
+  const int H4 = H / 4, W4 = W / 4;
+  if (H4 <= 0 || W4 <= 0 || C <= 0 || (16 * C) % 8 != 0) { hulc2_set_error("pack_frames: bad geometry"); return HULC2_EINVAL; }
+  const int smem = C * 4 * W4 * 4 * (int)sizeof(float);
+  if (smem > 48 * 1024) { hulc2_set_error("pack_frames: frame row too wide"); return HULC2_EINVAL; }
+  pack_frames_kernel<<<F * H4, 256, smem, st>>>(x, (uint8_t*)xs, C, H, W, H4, W4);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+int hulc2_convb_pack_weight(const float* w, void* wp, int Cout, int Cin, int KH, int KW, int mode, int stride, cudaStream_t st) {
+  if (mode < 0 || mode > 2 || (mode == 1 && ((KH & 3) || (KW & 3)))) { hulc2_set_error("convb_pack_weight: bad mode"); return HULC2_EINVAL; }
+  const int total = Cout * Cin * KH * KW;
+  if (total <= 0) return HULC2_OK;
+  pack_weight_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(w, (__nv_bfloat16*)wp, Cout, Cin, KH, KW, mode, stride > 0 ? stride : 1);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+int hulc2_convb_fwd(const hulc2_convb_args* a, cudaStream_t st) {
+  if (int e = check_convb(a)) return e;
+  if (!hulc2_convb_supported(a->C, a->Cout, a->KH, a->KW, a->stride)) { hulc2_set_error("convb_fwd: unsupported shape"); return HULC2_ENOTIMPL; }
+  const int OH = (a->H - a->KH) / a->stride + 1, OW = (a->W - a->KW) / a->stride + 1;
+  ConvParams p{};
+  p.x = (const uint8_t*)a->x; p.w = (const uint8_t*)a->w; p.bias = a->bias; p.mask = nullptr; p.y = (uint8_t*)a->y;
+  p.ncls = 1; p.N = a->Cout; p.relu = a->relu;
+  p.VH = OH; p.VW = OW; p.oH = OH; p.oW = OW;
+  ConvClass& c = p.cls[0];
+  c.M = a->F * OH * OW; c.PH = OH; c.PW = OW; c.tile_begin = 0; c.K = a->KH * a->KW * a->C; c.w_off = 0; c.tab_off = 0;
+  c.sF = a->H * a->W * a->C / 8; c.sI = a->stride * a->W * a->C / 8; c.sJ = a->stride * a->C / 8;
+  c.oS = 1; c.oPh = 0; c.oPw = 0;
+  if (c.M == 0) return HULC2_OK;
+  p.ntiles = hulc2_cdiv(c.M, TILE_M);
+  p.w_bytes = a->Cout * c.K * 2;
+  const int cpr = a->KW * a->C / 8;                    // chunks per kernel row (contiguous in memory)
+  p.ntab = c.K / 8;
+  for (int q = 0; q < p.ntab; ++q) {
+    const int kh = q / cpr;
+    p.table[q] = make_int2(kh * a->W * a->C / 8 + (q - kh * cpr), 0);
+  }
+  return a->Cout == 32 ? launch_igemm<32>(p, st) : launch_igemm<64>(p, st);
+}
+
+int hulc2_convb_dgrad(const hulc2_convb_args* a, cudaStream_t st) {
+  if (int e = check_convb(a)) return e;
+  // as a GEMM: N = C (input channels), K = taps * Cout
+  if (a->Cout % 8 != 0 || (a->C != 32 && a->C != 64) || a->stride > 2) { hulc2_set_error("convb_dgrad: unsupported shape"); return HULC2_ENOTIMPL; }
+  const int s = a->stride;
+  const int OH = (a->H - a->KH) / s + 1, OW = (a->W - a->KW) / s + 1;
+  ConvParams p{};
+  p.x = (const uint8_t*)a->dy; p.w = (const uint8_t*)a->w; p.bias = nullptr; p.mask = (const uint8_t*)a->xmask; p.y = (uint8_t*)a->dx;
+  p.N = a->C; p.relu = 0;
+  p.VH = OH; p.VW = OW; p.oH = a->H; p.oW = a->W;
+  int ncls = 0, tiles = 0, woff = 0, tab = 0;
+  const int co8 = a->Cout / 8;
+  for (int ph = 0; ph < s; ++ph)
+    for (int pw = 0; pw < s; ++pw) {
+      const int CH = (a->H - ph + s - 1) / s, CW = (a->W - pw + s - 1) / s;
+      const int KA = (a->KH - ph + s - 1) / s, KB = (a->KW - pw + s - 1) / s;
+      const int K = KA * KB * a->Cout;
+      if (CH <= 0 || CW <= 0) { woff += a->C * K * 2; continue; }
+      if (K <= 0 || K % 64 != 0 || tab + K / 8 > MAX_TAB || ncls >= MAX_CLS) { hulc2_set_error("convb_dgrad: unsupported class shape"); return HULC2_ENOTIMPL; }
+      ConvClass& c = p.cls[ncls++];
+      c.M = a->F * CH * CW; c.PH = CH; c.PW = CW; c.tile_begin = tiles; c.K = K; c.w_off = woff; c.tab_off = tab;
+      c.sF = OH * OW * co8; c.sI = OW * co8; c.sJ = co8;
+      c.oS = s; c.oPh = ph; c.oPw = pw;
+      for (int q = 0; q < K / 8; ++q) {
+        const int tap = q / co8, u = q - tap * co8, ta = tap / KB, tb = tap - ta * KB;
+        p.table[tab + q] = make_int2(-(ta * OW + tb) * co8 + u, (ta << 16) | tb);
+      }
+      tab += K / 8; woff += a->C * K * 2; tiles += hulc2_cdiv(c.M, TILE_M);
+    }
+  p.ncls = ncls; p.ntiles = tiles; p.w_bytes = woff; p.ntab = tab;
+  if (tiles == 0) return HULC2_OK;
+  return a->C == 32 ? launch_igemm<32>(p, st) : launch_igemm<64>(p, st);
+}
+
+int hulc2_convb_wgrad(const hulc2_convb_args* a, cudaStream_t st) {
+  if (int e = check_convb(a)) return e;
+  if (!hulc2_convb_supported(a->C, a->Cout, a->KH, a->KW, a->stride)) { hulc2_set_error("convb_wgrad: unsupported shape"); return HULC2_ENOTIMPL; }
+  const int OH = (a->H - a->KH) / a->stride + 1, OW = (a->W - a->KW) / a->stride + 1;
+  WgradParams p{};
+  p.x = (const uint8_t*)a->x; p.dz = (const uint8_t*)a->dy;
+  p.P = a->F * OH * OW; p.PH = OH; p.PW = OW;
+  p.sF = a->H * a->W * a->C / 8; p.sI = a->stride * a->W * a->C / 8; p.sJ = a->stride * a->C / 8;
+  p.K = a->KH * a->KW * a->C;
+  p.nblk = p.K / 64 + 1; if (p.nblk & 1) ++p.nblk;
+  if (p.nblk > WG_MAX_BLK) { hulc2_set_error("convb_wgrad: kconv too large"); return HULC2_ENOTIMPL; }
+  p.cout8 = a->Cout / 8;
+  p.nstages = hulc2_cdiv(p.P, WG_KP);
+  const int cpr = a->KW * a->C / 8;
+  for (int q = 0; q < p.K / 8; ++q) {
+    const int kh = q / cpr;
+    p.delta[q] = kh * a->W * a->C / 8 + (q - kh * cpr);
+  }
+  if (p.P == 0) {
+    if (a->dw) cudaMemsetAsync(a->dw, 0, sizeof(float) * a->Cout * p.K, st);
+    if (a->db) cudaMemsetAsync(a->db, 0, sizeof(float) * a->Cout, st);
+    return HULC2_OK;
+  }
+  const int grid = p.nstages < sm_count() ? p.nstages : sm_count();
+  const long long need = (long long)grid * p.nblk * 64 * 64 * sizeof(float);
+  if (!a->workspace || a->workspace_bytes < need) { hulc2_set_error("convb_wgrad: workspace too small"); return HULC2_EWORKSPACE; }
+  p.partial = (float*)a->workspace;
+  const int smem = WG_STAGES * (p.nblk + 1) * (int)WG_BLK + 1024;
+  static int configured = 0;
+  if (configured < smem) {
+    if (cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      hulc2_set_error("convb_wgrad: cannot raise dynamic shared memory limit");
+      return HULC2_ELAUNCH;
+    }
+    configured = smem;
+  }
+  conv_wgrad_kernel<<<grid, NT, smem, st>>>(p);
+  HULC2_CHECK_LAUNCH();
+  const int total = (p.K + 1) * a->Cout;
+  wgrad_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(p.partial, grid, p.nblk * 64, p.K, a->Cout, a->C, a->KH, a->KW, a->dw_layout,
+                                                               a->dw, a->db);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+}  // extern "C"

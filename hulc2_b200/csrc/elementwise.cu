@@ -1,5 +1,7 @@
 // Memory-bound utility kernels: strided copies, column sums (bias gradients), layout shuffles,
 // Philox noise, fused Adam.  All are grid-stride, coalesced, sized in multiples of the SM count.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "../../include/hulc2_b200.h"
 
@@ -67,15 +69,21 @@ __global__ void colsum_final_kernel(const double* __restrict__ partial, int slab
 }
 
 // per-frame [HW, C] <-> [C, HW] transposes through a padded shared tile
-__global__ void transpose_frames_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols,
-                                        const float* __restrict__ mask) {
+__device__ __forceinline__ float ld_el(const float* p) { return *p; }
+__device__ __forceinline__ float ld_el(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st_el(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_el(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+template <typename TI, typename TO, typename TM>
+__global__ void transpose_frames_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int rows, int cols,
+                                        const TM* __restrict__ mask) {
   // src frame is [rows, cols] row-major, dst frame is [cols, rows]; mask (optional) has dst layout
   __shared__ float tile[32][33];
   long long fbase = (long long)blockIdx.z * rows * cols;
   int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int j = threadIdx.y; j < 32; j += 8) {
     int r = r0 + j, c = c0 + threadIdx.x;
-    tile[j][threadIdx.x] = (r < rows && c < cols) ? src[fbase + (long long)r * cols + c] : 0.f;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? ld_el(src + fbase + (long long)r * cols + c) : 0.f;
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += 8) {
@@ -83,8 +91,8 @@ __global__ void transpose_frames_kernel(const float* __restrict__ src, float* __
     if (r < rows && c < cols) {
       long long o = fbase + (long long)c * rows + r;
       float v = tile[threadIdx.x][j];
-      if (mask) v = mask[o] > 0.f ? v : 0.f;
-      dst[o] = v;
+      if (mask) v = ld_el(mask + o) > 0.f ? v : 0.f;
+      st_el(dst + o, v);
     }
   }
 }
@@ -232,14 +240,29 @@ int hulc2_colsum(const float* x, long long ld, long long rows, int cols, float* 
 int hulc2_nhwc_to_nchw(const float* src, float* dst, int F, int HW, int C, cudaStream_t st) {
   if (F <= 0) return HULC2_OK;
   dim3 grid(hulc2_cdiv(C, 32), hulc2_cdiv(HW, 32), F);
-  transpose_frames_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, HW, C, nullptr);
+  transpose_frames_kernel<float, float, float><<<grid, dim3(32, 8), 0, st>>>(src, dst, HW, C, nullptr);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }
 int hulc2_nchw_to_nhwc(const float* src, float* dst, int F, int HW, int C, const float* mask, cudaStream_t st) {
   if (F <= 0) return HULC2_OK;
   dim3 grid(hulc2_cdiv(HW, 32), hulc2_cdiv(C, 32), F);
-  transpose_frames_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, C, HW, mask);
+  transpose_frames_kernel<float, float, float><<<grid, dim3(32, 8), 0, st>>>(src, dst, C, HW, mask);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+// bf16 conv trunk <-> fp32 heads: y3 (bf16 NHWC) -> nn.Flatten order (fp32 [F, C*HW]) and its gradient back (ReLU-masked by y3)
+int hulc2_nhwc_bf16_to_nchw(const void* src, float* dst, int F, int HW, int C, cudaStream_t st) {
+  if (F <= 0) return HULC2_OK;
+  dim3 grid(hulc2_cdiv(C, 32), hulc2_cdiv(HW, 32), F);
+  transpose_frames_kernel<__nv_bfloat16, float, float><<<grid, dim3(32, 8), 0, st>>>((const __nv_bfloat16*)src, dst, HW, C, nullptr);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_nchw_to_nhwc_bf16(const float* src, void* dst, int F, int HW, int C, const void* mask, cudaStream_t st) {
+  if (F <= 0) return HULC2_OK;
+  dim3 grid(hulc2_cdiv(HW, 32), hulc2_cdiv(C, 32), F);
+  transpose_frames_kernel<float, __nv_bfloat16, __nv_bfloat16><<<grid, dim3(32, 8), 0, st>>>(src, (__nv_bfloat16*)dst, C, HW, (const __nv_bfloat16*)mask);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

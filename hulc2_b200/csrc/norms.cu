@@ -1,5 +1,7 @@
 // LayerNorm (+residual +dropout) and SpatialSoftmax, forward and backward.  Memory-bound: one pass
 // over HBM per tensor, warp-shuffle reductions, coalesced along the feature/channel axis.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "../../include/hulc2_b200.h"
 
@@ -113,21 +115,27 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, long long ldy
 
 // --------------------------------------------------------------------------- SpatialSoftmax (NHWC)
 // block = one frame; thread (c, g): channel c, position group g of G = blockDim.x / C.
-template <bool BWD>
-__global__ void spatial_softmax_kernel(const float* __restrict__ x, const float* __restrict__ x_map,
+__device__ __forceinline__ float ld_act(const float* p) { return *p; }
+__device__ __forceinline__ float ld_act(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st_act(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_act(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+// T = float (fp32 path) or __nv_bfloat16 (bf16 conv trunk: activations and their gradients live in HBM as bf16)
+template <bool BWD, typename T>
+__global__ void spatial_softmax_kernel(const T* __restrict__ x, const float* __restrict__ x_map,
                                        const float* __restrict__ y_map, const float* __restrict__ temperature,
-                                       float* __restrict__ out, const float* __restrict__ dout, float* __restrict__ dx,
+                                       float* __restrict__ out, const float* __restrict__ dout, T* __restrict__ dx,
                                        float* __restrict__ dtemp, int HW, int C, int relu_mask) {
   extern __shared__ float sm[];  // [G][C] x 3
   const int G = blockDim.x / C;
   const int c = threadIdx.x % C, g = threadIdx.x / C;
   const bool active = g < G;
   const float invT = 1.f / temperature[0];
-  const float* xf = x + (long long)blockIdx.x * HW * C;
+  const T* xf = x + (long long)blockIdx.x * HW * C;
   float* s0 = sm; float* s1 = sm + G * C; float* s2 = sm + 2 * G * C;
 
   float mx = -INFINITY;
-  if (active) for (int i = g; i < HW; i += G) mx = fmaxf(mx, xf[(long long)i * C + c] * invT);
+  if (active) for (int i = g; i < HW; i += G) mx = fmaxf(mx, ld_act(xf + (long long)i * C + c) * invT);
   if (active) s0[g * C + c] = mx;
   __syncthreads();
   if (active) { mx = s0[c]; for (int k = 1; k < G; ++k) mx = fmaxf(mx, s0[k * C + c]); }
@@ -136,7 +144,7 @@ __global__ void spatial_softmax_kernel(const float* __restrict__ x, const float*
   float se = 0.f, sx = 0.f, sy = 0.f;
   if (active)
     for (int i = g; i < HW; i += G) {
-      float e = expf(xf[(long long)i * C + c] * invT - mx);
+      float e = expf(ld_act(xf + (long long)i * C + c) * invT - mx);
       se += e; sx += e * x_map[i]; sy += e * y_map[i];
     }
   if (active) { s0[g * C + c] = se; s1[g * C + c] = sx; s2[g * C + c] = sy; }
@@ -156,16 +164,16 @@ __global__ void spatial_softmax_kernel(const float* __restrict__ x, const float*
   }
   if (!active) return;
   const float gx = dout[(long long)blockIdx.x * 2 * C + 2 * c], gy = dout[(long long)blockIdx.x * 2 * C + 2 * c + 1];
-  float* dxf = dx + (long long)blockIdx.x * HW * C;
+  T* dxf = dx + (long long)blockIdx.x * HW * C;
   float dt = 0.f;
   for (int i = g; i < HW; i += G) {
-    float xv = xf[(long long)i * C + c];
+    float xv = ld_act(xf + (long long)i * C + c);
     float p = expf(xv * invT - mx) * inv;
     float dl = p * (gx * (x_map[i] - ex) + gy * (y_map[i] - ey));  // d/d(logit_i), logit = x/T
     dt += dl * xv;
     float v = dl * invT;
     if (relu_mask && !(xv > 0.f)) v = 0.f;
-    dxf[(long long)i * C + c] = v;
+    st_act(dxf + (long long)i * C + c, v);
   }
   if (dtemp) atomicAdd(dtemp, -dt * invT * invT);
 }
@@ -209,7 +217,7 @@ int hulc2_spatial_softmax_fwd(const float* x, const float* x_map, const float* y
   if (F <= 0) return HULC2_OK;
   if (!ssm_threads(C)) { hulc2_set_error("spatial_softmax: C must be <= 256"); return HULC2_EINVAL; }
   int G = 256 / C;
-  spatial_softmax_kernel<false><<<F, 256, 3 * G * C * sizeof(float), st>>>(x, x_map, y_map, temperature, out, nullptr, nullptr, nullptr, HW, C, 0);
+  spatial_softmax_kernel<false, float><<<F, 256, 3 * G * C * sizeof(float), st>>>(x, x_map, y_map, temperature, out, nullptr, nullptr, nullptr, HW, C, 0);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }
@@ -221,7 +229,31 @@ int hulc2_spatial_softmax_bwd(const float* x, const float* x_map, const float* y
   if (F <= 0) return HULC2_OK;
   if (!ssm_threads(C)) { hulc2_set_error("spatial_softmax: C must be <= 256"); return HULC2_EINVAL; }
   int G = 256 / C;
-  spatial_softmax_kernel<true><<<F, 256, 3 * G * C * sizeof(float), st>>>(x, x_map, y_map, temperature, nullptr, dout, dx, dtemperature, HW, C, relu_mask);
+  spatial_softmax_kernel<true, float><<<F, 256, 3 * G * C * sizeof(float), st>>>(x, x_map, y_map, temperature, nullptr, dout, dx, dtemperature, HW, C, relu_mask);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+
+int hulc2_spatial_softmax_fwd_bf16(const void* x, const float* x_map, const float* y_map, const float* temperature, float* out,
+                                   int F, int HW, int C, cudaStream_t st) {
+  if (F <= 0) return HULC2_OK;
+  if (!ssm_threads(C)) { hulc2_set_error("spatial_softmax: C must be <= 256"); return HULC2_EINVAL; }
+  int G = 256 / C;
+  spatial_softmax_kernel<false, __nv_bfloat16><<<F, 256, 3 * G * C * sizeof(float), st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, out,
+                                                                                          nullptr, nullptr, nullptr, HW, C, 0);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+int hulc2_spatial_softmax_bwd_bf16(const void* x, const float* x_map, const float* y_map, const float* temperature,
+                                   const float* dout, void* dx, float* dtemperature, int F, int HW, int C, int relu_mask,
+                                   cudaStream_t st) {
+  if (F <= 0) return HULC2_OK;
+  if (!ssm_threads(C)) { hulc2_set_error("spatial_softmax: C must be <= 256"); return HULC2_EINVAL; }
+  int G = 256 / C;
+  spatial_softmax_kernel<true, __nv_bfloat16><<<F, 256, 3 * G * C * sizeof(float), st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, nullptr,
+                                                                                         dout, (__nv_bfloat16*)dx, dtemperature, HW, C, relu_mask);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

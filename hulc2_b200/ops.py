@@ -13,12 +13,13 @@ Layout notes
 from __future__ import annotations
 
 import ctypes as C
+from ctypes import byref as C_byref
 from typing import List, Optional, Sequence, Tuple
 
 import torch
 
 from . import _lib
-from ._lib import ConvArgs, GemmArgs, call
+from ._lib import ConvArgs, ConvbArgs, GemmArgs, call
 
 _PRECISION = {"fp32": 0, "bf16": 1}
 _precision = 0
@@ -267,16 +268,125 @@ def _conv_trunk_bwd(x, y1, y2, dz3, w2, w3, need):
     return g
 
 
+# ----------------------------------------------------------------------------- bf16 conv trunk (csrc/conv_sm100.cu)
+def _osz(h, k, s):
+    return (h - k) // s + 1
+
+
+def convb_trunk_supported(x: torch.Tensor) -> bool:
+    """The persistent tcgen05 trunk serves precision 'bf16' on the 3-conv stacks of the reference (k8s4 -> k4s2 -> k3s1)."""
+    if _precision != 1 or x.dim() != 4:
+        return False
+    lib = _lib.load_library()
+    Cin = x.shape[1]
+    return bool(lib.hulc2_convb_supported(16 * Cin, 32, 2, 2, 1) and lib.hulc2_convb_supported(32, 64, 4, 4, 2)
+                and lib.hulc2_convb_supported(64, 64, 3, 3, 1) and x.shape[2] >= 8 and x.shape[3] >= 8)
+
+
+def _cb(F, C, H, W, Cout, k, stride) -> ConvbArgs:
+    a = ConvbArgs()
+    a.F, a.C, a.H, a.W, a.Cout, a.KH, a.KW, a.stride = F, C, H, W, Cout, k, k, stride
+    return a
+
+
+def _bf16(*shape, device):
+    return torch.empty(*shape, device=device, dtype=torch.bfloat16)
+
+
+def pack_conv_weight(w: torch.Tensor, mode: int, stride: int = 1) -> torch.Tensor:
+    Cout, Cin, KH, KW = w.shape
+    wp = torch.empty(w.numel(), device=w.device, dtype=torch.bfloat16)
+    call("hulc2_convb_pack_weight", w.data_ptr(), wp.data_ptr(), Cout, Cin, KH, KW, mode, stride)
+    return wp
+
+
+def convb_fwd(x, wp, bias, F, C, H, W, Cout, k, stride, relu=True, name="conv") -> torch.Tensor:
+    """x bf16 NHWC [F,H,W,C] -> bf16 NHWC [F,OH,OW,Cout]."""
+    OH, OW = _osz(H, k, stride), _osz(W, k, stride)
+    y = _bf16(F, OH, OW, Cout, device=x.device)
+    a = _cb(F, C, H, W, Cout, k, stride)
+    a.x, a.w, a.bias, a.y, a.relu = x.data_ptr(), wp.data_ptr(), _p(bias), y.data_ptr(), int(relu)
+    _lib.tag(f"convb_fwd[{name},F={F},{C}x{H}x{W}->{Cout},k{k}s{stride}]", 2.0 * y.numel() * C * k * k)
+    call("hulc2_convb_fwd", C_byref(a))
+    return y
+
+
+def convb_dgrad(dy, w_oihw, xmask, F, C, H, W, Cout, k, stride, name="conv") -> torch.Tensor:
+    """dy bf16 [F,OH,OW,Cout] -> dx bf16 [F,H,W,C], zeroed where xmask <= 0."""
+    wp = pack_conv_weight(w_oihw, 2, stride)
+    dx = _bf16(F, H, W, C, device=dy.device)
+    a = _cb(F, C, H, W, Cout, k, stride)
+    a.dy, a.w, a.dx, a.xmask = dy.data_ptr(), wp.data_ptr(), dx.data_ptr(), _p(xmask)
+    _lib.tag(f"convb_dgrad[{name},F={F},{C}x{H}x{W}<-{Cout},k{k}s{stride}]", 2.0 * dy.numel() * C * k * k)
+    call("hulc2_convb_dgrad", C_byref(a))
+    return dx
+
+
+def convb_wgrad(x, dy, F, C, H, W, Cout, k, stride, dw_shape, dw_layout=0, name="conv"):
+    """(dw fp32 in dw_shape (OIHW), db fp32 [Cout]) from the bf16 NHWC input x and output gradient dy."""
+    ws = workspace(x.device)
+    dw = torch.empty(dw_shape, device=x.device, dtype=torch.float32)
+    db = torch.empty(Cout, device=x.device, dtype=torch.float32)
+    a = _cb(F, C, H, W, Cout, k, stride)
+    a.x, a.dy, a.dw, a.db, a.dw_layout = x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), dw_layout
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    _lib.tag(f"convb_wgrad[{name},F={F},{C}x{H}x{W}->{Cout},k{k}s{stride}]", 2.0 * dy.numel() * C * k * k)
+    call("hulc2_convb_wgrad", C_byref(a))
+    return dw, db
+
+
+def pack_frames(x: torch.Tensor) -> torch.Tensor:
+    """fp32 NCHW frames -> bf16 [F, H/4, W/4, 16*C] (space-to-depth by the first conv's stride)."""
+    F_, Cin, H, W = x.shape
+    xs = _bf16(F_, H // 4, W // 4, 16 * Cin, device=x.device)
+    _lib.tag(f"pack_frames[F={F_},{Cin}x{H}x{W}]", 0.0)
+    call("hulc2_pack_frames_bf16", x.data_ptr(), xs.data_ptr(), F_, Cin, H, W)
+    return xs
+
+
+def _convb_trunk_fwd(x, w1, b1, w2, b2, w3, b3):
+    F_, Cin, H, W = x.shape
+    xs = pack_frames(x)
+    H4, W4 = H // 4, W // 4
+    H1, W1 = H4 - 1, W4 - 1
+    H2, W2 = _osz(H1, 4, 2), _osz(W1, 4, 2)
+    y1 = convb_fwd(xs, pack_conv_weight(w1, 1), b1, F_, 16 * Cin, H4, W4, 32, 2, 1, name="c1")
+    y2 = convb_fwd(y1, pack_conv_weight(w2, 0), b2, F_, 32, H1, W1, 64, 4, 2, name="c2")
+    y3 = convb_fwd(y2, pack_conv_weight(w3, 0), b3, F_, 64, H2, W2, 64, 3, 1, name="c3")
+    return xs, y1, y2, y3
+
+
+def _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3):
+    """dz3 = bf16 gradient wrt conv3's pre-activation (already ReLU-masked).  Returns the six parameter gradients."""
+    F_, H4, W4, C16 = xs.shape
+    H1, W1, H2, W2 = y1.shape[1], y1.shape[2], y2.shape[1], y2.shape[2]
+    dw3, db3 = convb_wgrad(y2, dz3, F_, 64, H2, W2, 64, 3, 1, tuple(w3.shape), name="c3")
+    dz2 = convb_dgrad(dz3, w3, y2, F_, 64, H2, W2, 64, 3, 1, name="c3")
+    dw2, db2 = convb_wgrad(y1, dz2, F_, 32, H1, W1, 64, 4, 2, tuple(w2.shape), name="c2")
+    dz1 = convb_dgrad(dz2, w2, y1, F_, 32, H1, W1, 64, 4, 2, name="c2")
+    dw1, db1 = convb_wgrad(xs, dz1, F_, C16, H4, W4, 32, 2, 1, tuple(w1.shape), dw_layout=1, name="c1")
+    return {"w1": dw1, "b1": db1, "w2": dw2, "b2": db2, "w3": dw3, "b3": db3}
+
+
 class StaticConvSSM(torch.autograd.Function):
     """Static-camera trunk: 3 convs + SpatialSoftmax (vision_network.py:55-58, 100-108) -> [F, 2*64]."""
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, w3, b3, x_map, y_map, temperature):
         x = _f32(x).contiguous()
-        y1, y2, y3 = _conv_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
         F_ = x.shape[0]
-        HW = y3.shape[1] * y3.shape[2]
         out = torch.empty(F_, 128, device=x.device, dtype=torch.float32)
+        ctx.bf16 = convb_trunk_supported(x)
+        if ctx.bf16:
+            xs, y1, y2, y3 = _convb_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
+            HW = y3.shape[1] * y3.shape[2]
+            _lib.tag(f"spatial_softmax_fwd_bf16[F={F_},HW={HW}]", 0.0)
+            call("hulc2_spatial_softmax_fwd_bf16", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
+                 out.data_ptr(), F_, HW, 64)
+            ctx.save_for_backward(xs, y1, y2, y3, w1, w2, w3, x_map, y_map, temperature)
+            return out
+        y1, y2, y3 = _conv_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
+        HW = y3.shape[1] * y3.shape[2]
         call("hulc2_spatial_softmax_fwd", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
              out.data_ptr(), F_, HW, 64)
         ctx.save_for_backward(x, y1, y2, y3, w2, w3, x_map, y_map, temperature, out)
@@ -284,8 +394,19 @@ class StaticConvSSM(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        x, y1, y2, y3, w2, w3, x_map, y_map, temperature, out = ctx.saved_tensors
         dout = dout.contiguous()
+        if ctx.bf16:
+            xs, y1, y2, y3, w1, w2, w3, x_map, y_map, temperature = ctx.saved_tensors
+            F_ = xs.shape[0]
+            HW = y3.shape[1] * y3.shape[2]
+            dz3 = torch.empty_like(y3)
+            dtemp = torch.zeros(1, device=xs.device, dtype=torch.float32) if ctx.needs_input_grad[9] else None
+            _lib.tag(f"spatial_softmax_bwd_bf16[F={F_},HW={HW}]", 0.0)
+            call("hulc2_spatial_softmax_bwd_bf16", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
+                 dout.data_ptr(), dz3.data_ptr(), _p(dtemp), F_, HW, 64, 1)
+            g = _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3)
+            return (None, g["w1"], g["b1"], g["w2"], g["b2"], g["w3"], g["b3"], None, None, dtemp)
+        x, y1, y2, y3, w2, w3, x_map, y_map, temperature, out = ctx.saved_tensors
         F_ = x.shape[0]
         HW = y3.shape[1] * y3.shape[2]
         dz3 = torch.empty_like(y3)
@@ -304,8 +425,16 @@ class GripperConvFlatten(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, w3, b3):
         x = _f32(x).contiguous()
-        y1, y2, y3 = _conv_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
         F_ = x.shape[0]
+        ctx.bf16 = convb_trunk_supported(x)
+        if ctx.bf16:
+            xs, y1, y2, y3 = _convb_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
+            HW = y3.shape[1] * y3.shape[2]
+            flat = torch.empty(F_, 64 * HW, device=x.device, dtype=torch.float32)
+            call("hulc2_nhwc_bf16_to_nchw", y3.data_ptr(), flat.data_ptr(), F_, HW, 64)
+            ctx.save_for_backward(xs, y1, y2, y3, w1, w2, w3)
+            return flat
+        y1, y2, y3 = _conv_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
         HW = y3.shape[1] * y3.shape[2]
         flat = torch.empty(F_, 64 * HW, device=x.device, dtype=torch.float32)
         call("hulc2_nhwc_to_nchw", y3.data_ptr(), flat.data_ptr(), F_, HW, 64)
@@ -314,8 +443,16 @@ class GripperConvFlatten(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dflat):
-        x, y1, y2, y3, w2, w3 = ctx.saved_tensors
         dflat = dflat.contiguous()
+        if ctx.bf16:
+            xs, y1, y2, y3, w1, w2, w3 = ctx.saved_tensors
+            F_ = xs.shape[0]
+            HW = y3.shape[1] * y3.shape[2]
+            dz3 = torch.empty_like(y3)
+            call("hulc2_nchw_to_nhwc_bf16", dflat.data_ptr(), dz3.data_ptr(), F_, HW, 64, y3.data_ptr())
+            g = _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3)
+            return (None, g["w1"], g["b1"], g["w2"], g["b2"], g["w3"], g["b3"])
+        x, y1, y2, y3, w2, w3 = ctx.saved_tensors
         F_ = x.shape[0]
         HW = y3.shape[1] * y3.shape[2]
         dz3 = torch.empty_like(y3)

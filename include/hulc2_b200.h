@@ -73,6 +73,42 @@ int hulc2_conv2d_dgrad(const hulc2_conv_args* a, hulc2_stream_t stream);
 int hulc2_permute_conv_weight(const float* src, float* dst, int O, int I, int KH, int KW, int dir, int accumulate,
                               hulc2_stream_t stream);
 
+/* ------------------------------------------------------------------ bf16 conv trunk (sm_100a, precision 1)
+ * Persistent warp-specialised tcgen05 implicit GEMMs over bf16 NHWC activations (csrc/conv_sm100.cu); replaces the
+ * conv stacks of vision_network.py:38-48 / vision_network_gripper.py:11-26 and their autograd.
+ *  pack_frames : fp32 NCHW frames [F,C,H,W] -> bf16 [F, H/4, W/4, 16C], channel (ci,a,b) = x[f,ci,4I+a,4J+b]; the
+ *                k8/s4 first conv becomes a k2/s1 conv over 16C channels (describe it that way in hulc2_convb_args).
+ *  pack_weight : fp32 OIHW -> bf16.  mode 0: [Cout][(kh,kw,ci)];  mode 1: first conv over packed frames, dims are the
+ *                ORIGINAL [Cout,Cin,8,8]: [Cout][(dI,dJ,ci,a,b)];  mode 2: input-gradient operand, one [Cin][(a,b,co)]
+ *                matrix per stride-parity class (ph,pw), classes concatenated in (ph,pw) order.
+ *  fwd   : y[F,OH,OW,Cout] = relu?(conv(x, w) + bias), x/y bf16 NHWC, w from pack_weight mode 0/1.
+ *  dgrad : dx[F,H,W,C] = conv^T(dy, w) zeroed where xmask <= 0 (xmask = forward activation x, may be null); w mode 2.
+ *  wgrad : dw (fp32, OIHW; dw_layout 1 = ORIGINAL [Cout, C/16, 4KH, 4KW] of a packed-frames conv) and db[Cout]
+ *          from x and dy; workspace >= 148 * (KH*KW*C + 128) * 64 * 4 bytes.
+ * hulc2_convb_supported() says whether a layer shape is served (C % 8 == 0, KH*KW*C % 64 == 0, Cout in {32,64}, stride <= 2). */
+typedef struct {
+  int F, C, H, W, Cout, KH, KW, stride;
+  const void* x; const void* w; const float* bias; void* y; int relu;
+  const void* dy; void* dx; const void* xmask;
+  float* dw; float* db; int dw_layout;
+  void* workspace; long long workspace_bytes;
+} hulc2_convb_args;
+int hulc2_convb_supported(int C, int Cout, int KH, int KW, int stride);
+int hulc2_pack_frames_bf16(const float* x, void* xs, int F, int C, int H, int W, hulc2_stream_t stream);
+int hulc2_convb_pack_weight(const float* w_oihw, void* wp, int Cout, int Cin, int KH, int KW, int mode, int stride,
+                            hulc2_stream_t stream);
+int hulc2_convb_fwd(const hulc2_convb_args* a, hulc2_stream_t stream);
+int hulc2_convb_dgrad(const hulc2_convb_args* a, hulc2_stream_t stream);
+int hulc2_convb_wgrad(const hulc2_convb_args* a, hulc2_stream_t stream);
+/* SpatialSoftmax / nn.Flatten boundaries of the bf16 trunk (x, dx bf16 NHWC; everything else fp32) */
+int hulc2_spatial_softmax_fwd_bf16(const void* x, const float* x_map, const float* y_map, const float* temperature,
+                                   float* out, int F, int HW, int C, hulc2_stream_t stream);
+int hulc2_spatial_softmax_bwd_bf16(const void* x, const float* x_map, const float* y_map, const float* temperature,
+                                   const float* dout, void* dx, float* dtemperature, int F, int HW, int C, int relu_mask,
+                                   hulc2_stream_t stream);
+int hulc2_nhwc_bf16_to_nchw(const void* src, float* dst, int F, int HW, int C, hulc2_stream_t stream);
+int hulc2_nchw_to_nhwc_bf16(const float* src, void* dst, int F, int HW, int C, const void* mask, hulc2_stream_t stream);
+
 /* ------------------------------------------------------------------ small data movement
  * copy2d: dst[r*ldd + c] (+)= src[r*lds + c];  colsum: out[c] (+)= sum_r x[r*ld + c] (bias gradients);
  * nhwc<->nchw per-frame transposes (nn.Flatten order of nature_cnn, vision_network_gripper.py:22-23). */

@@ -1,0 +1,199 @@
+"""GPU parity tests of the persistent tcgen05 conv trunk (csrc/conv_sm100.cu, bf16 NHWC activations).
+
+Every primitive is checked against torch's fp32 convolution (and its autograd) evaluated on the SAME bf16-rounded
+operands, so only the fp32 summation order and the final bf16 rounding of the stored activation differ:
+tolerance 1e-2 of the tensor's max-norm for bf16 outputs (bf16 has 8 mantissa bits: 2^-9 = 2e-3 per element),
+2e-3 for fp32 weight/bias gradients.  Reference semantics: vision_network.py:38-48, vision_network_gripper.py:11-26.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(*shape, generator=g) * 2 - 1) * scale
+
+
+def _bf(x):
+    return x.bfloat16().float()
+
+
+@pytest.fixture(autouse=True)
+def _precision():
+    from hulc2_b200 import ops
+
+    ops.set_precision("bf16")
+    yield
+    ops.set_precision("fp32")
+
+
+def _assert_grad_close(g, r, what):
+    """bf16 path-level gradient criterion (same as test_training_step_bf16_all_gradients_vs_oracle): norm within 3e-2
+    and cosine >= 0.99 against the un-rounded fp32 reference.  Element-wise max-norm checks are done per primitive
+    above, against references evaluated on the same bf16-rounded operands."""
+    g, r = g.detach().cpu().double().flatten(), r.detach().cpu().double().flatten()
+    ratio = float(g.norm() / (r.norm() + 1e-30))
+    cos = float((g * r).sum() / (g.norm() * r.norm() + 1e-30))
+    assert abs(ratio - 1) <= 3e-2 and cos >= 0.99, f"{what}: norm ratio {ratio:.4f}, cosine {cos:.5f}"
+
+
+def _nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(x_nhwc):
+    return x_nhwc.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("Fr,C,H,W", [(3, 3, 200, 200), (2, 3, 84, 84), (2, 3, 150, 200), (2, 1, 150, 200)])
+def test_pack_frames_exact(Fr, C, H, W):
+    from hulc2_b200 import ops
+
+    x = _rand(Fr, C, H, W, seed=1)
+    xs = ops.pack_frames(x.to(DEV))
+    torch.cuda.synchronize()
+    H4, W4 = H // 4, W // 4
+    ref = x[:, :, : 4 * H4, : 4 * W4].reshape(Fr, C, H4, 4, W4, 4).permute(0, 2, 4, 1, 3, 5).reshape(Fr, H4, W4, 16 * C).bfloat16()
+    assert torch.equal(xs.cpu(), ref)
+
+
+@pytest.mark.parametrize("Fr,H,W", [(5, 200, 200), (3, 84, 84), (2, 150, 200)])
+def test_conv1_over_packed_frames(Fr, H, W):
+    from hulc2_b200 import ops
+
+    x, w, b = _rand(Fr, 3, H, W, seed=1), _rand(32, 3, 8, 8, seed=2, scale=0.1), _rand(32, seed=3, scale=0.1)
+    xs = ops.pack_frames(x.to(DEV))
+    wp = ops.pack_conv_weight(w.to(DEV), 1)
+    y = ops.convb_fwd(xs, wp, b.to(DEV), Fr, 48, H // 4, W // 4, 32, 2, 1, name="t")
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(_bf(x), _bf(w), b, stride=4))
+    assert y.shape == (Fr, ref.shape[2], ref.shape[3], 32)
+    assert_close(_nchw(y.float().cpu()), ref, 1e-2, "conv1 fwd")
+
+
+@pytest.mark.parametrize("Fr,C,H,W,Cout,k,s", [(7, 32, 49, 49, 64, 4, 2), (7, 64, 23, 23, 64, 3, 1), (3, 32, 20, 20, 64, 4, 2),
+                                               (3, 64, 9, 9, 64, 3, 1), (2, 32, 36, 49, 64, 4, 2), (1, 64, 17, 23, 64, 3, 1)])
+def test_conv_fwd_dgrad_wgrad_nhwc(Fr, C, H, W, Cout, k, s):
+    from hulc2_b200 import ops
+
+    x = F.relu(_rand(Fr, C, H, W, seed=1))                       # a post-ReLU activation (has exact zeros for the mask)
+    w, b = _rand(Cout, C, k, k, seed=2, scale=0.05), _rand(Cout, seed=3, scale=0.1)
+    xb = _nhwc(x).bfloat16().to(DEV)
+    y = ops.convb_fwd(xb, ops.pack_conv_weight(w.to(DEV), 0), b.to(DEV), Fr, C, H, W, Cout, k, s, name="t")
+    xr = _bf(x).requires_grad_(True)
+    wr = _bf(w).requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    pre = F.conv2d(xr, wr, br, stride=s)
+    ref = F.relu(pre)
+    torch.cuda.synchronize()
+    assert_close(_nchw(y.float().cpu()), ref, 1e-2, "fwd")
+
+    dy = _rand(*ref.shape, seed=4) * (ref > 0)                   # gradient wrt the pre-activation
+    dyb = _nhwc(dy).bfloat16()
+    pre.backward(dyb.float().permute(0, 3, 1, 2))
+    dx = ops.convb_dgrad(dyb.to(DEV), w.to(DEV), xb, Fr, C, H, W, Cout, k, s, name="t")
+    dw, db = ops.convb_wgrad(xb, dyb.to(DEV), Fr, C, H, W, Cout, k, s, (Cout, C, k, k), name="t")
+    torch.cuda.synchronize()
+    assert_close(_nchw(dx.float().cpu()), xr.grad * (x > 0), 1e-2, "dgrad")
+    assert_close(dw.cpu(), wr.grad, 2e-3, "wgrad")
+    assert_close(db.cpu(), br.grad, 2e-3, "bgrad")
+
+
+def test_conv1_wgrad_packed_frames():
+    from hulc2_b200 import ops
+
+    Fr, H, W = 3, 84, 84
+    x, w = _rand(Fr, 3, H, W, seed=1), _rand(32, 3, 8, 8, seed=2, scale=0.1)
+    xr, wr = _bf(x), _bf(w).requires_grad_(True)
+    br = torch.zeros(32, requires_grad=True)
+    pre = F.conv2d(xr, wr, br, stride=4)
+    dy = _rand(*pre.shape, seed=4)
+    dyb = _nhwc(dy).bfloat16()
+    pre.backward(dyb.float().permute(0, 3, 1, 2))
+    xs = ops.pack_frames(x.to(DEV))
+    dw, db = ops.convb_wgrad(xs, dyb.to(DEV), Fr, 48, H // 4, W // 4, 32, 2, 1, (32, 3, 8, 8), dw_layout=1, name="t")
+    torch.cuda.synchronize()
+    assert_close(dw.cpu(), wr.grad, 2e-3, "wgrad1")
+    assert_close(db.cpu(), br.grad, 2e-3, "bgrad1")
+
+
+@pytest.mark.parametrize("Fr,H,W", [(150, 200, 200), (40, 150, 200)])
+def test_static_trunk_many_tiles(Fr, H, W):
+    """More tiles than SMs x stages: exercises the persistent tile loop, ring wrap-around and TMEM double buffering."""
+    from hulc2_b200 import ops
+
+    x = _rand(Fr, 3, H, W, seed=1)
+    ws = [_rand(32, 3, 8, 8, seed=2, scale=0.08), _rand(64, 32, 4, 4, seed=3, scale=0.05), _rand(64, 64, 3, 3, seed=4, scale=0.05)]
+    bs = [_rand(32, seed=5, scale=0.1), _rand(64, seed=6, scale=0.1), _rand(64, seed=7, scale=0.1)]
+    d = [t.to(DEV) for t in (x, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2])]
+    xs, y1, y2, y3 = ops._convb_trunk_fwd(*d)
+    torch.cuda.synchronize()
+    r1 = F.relu(F.conv2d(_bf(x), _bf(ws[0]), bs[0], stride=4))
+    assert_close(_nchw(y1.float().cpu()), r1, 1e-2, "y1")
+    r2 = F.relu(F.conv2d(_nchw(y1.float().cpu()), _bf(ws[1]), bs[1], stride=2))
+    assert_close(_nchw(y2.float().cpu()), r2, 1e-2, "y2")
+    r3 = F.relu(F.conv2d(_nchw(y2.float().cpu()), _bf(ws[2]), bs[2], stride=1))
+    assert_close(_nchw(y3.float().cpu()), r3, 1e-2, "y3")
+
+
+@pytest.mark.parametrize("hw", [(200, 200), (150, 200)])
+def test_static_encoder_bf16_trunk_vs_torch(hw):
+    """StaticConvSSM (conv trunk + SpatialSoftmax) forward and all six parameter gradients vs torch fp32: 2e-2."""
+    from hulc2_b200 import ops
+    from hulc2_b200.models.perceptual_encoders.vision_network import SpatialSoftmax
+
+    Fr = 6
+    H, W = hw
+    x = _rand(Fr, 3, H, W, seed=1)
+    ws = [_rand(32, 3, 8, 8, seed=2, scale=0.08), _rand(64, 32, 4, 4, seed=3, scale=0.05), _rand(64, 64, 3, 3, seed=4, scale=0.05)]
+    bs = [_rand(32, seed=5, scale=0.1), _rand(64, seed=6, scale=0.1), _rand(64, seed=7, scale=0.1)]
+    oh = lambda h, k, s: (h - k) // s + 1
+    h3, w3 = oh(oh(oh(H, 8, 4), 4, 2), 3, 1), oh(oh(oh(W, 8, 4), 4, 2), 3, 1)
+    ssm = SpatialSoftmax(num_rows=w3, num_cols=h3, temperature=1.0)
+    dev = [t.to(DEV).requires_grad_(True) for pair in zip(ws, bs) for t in pair]
+    out = ops.StaticConvSSM.apply(x.to(DEV), *dev, ssm.x_map.to(DEV), ssm.y_map.to(DEV), ssm.temperature.to(DEV))
+    g = _rand(Fr, 128, seed=9)
+    out.backward(g.to(DEV))
+    torch.cuda.synchronize()
+
+    ref_p = [t.clone().requires_grad_(True) for pair in zip(ws, bs) for t in pair]
+    a = F.relu(F.conv2d(x, ref_p[0], ref_p[1], stride=4))
+    a = F.relu(F.conv2d(a, ref_p[2], ref_p[3], stride=2))
+    a = F.relu(F.conv2d(a, ref_p[4], ref_p[5], stride=1))
+    n, c, h, w = a.shape
+    sm = torch.softmax(a.reshape(-1, h * w), dim=1)
+    ex = (sm * ssm.x_map).sum(1, keepdim=True)
+    ey = (sm * ssm.y_map).sum(1, keepdim=True)
+    ref = torch.cat((ex, ey), 1).view(n, 2 * c)
+    ref.backward(g)
+    assert_close(out.cpu(), ref, 2e-2, "keypoints")
+    for d, r, nm in zip(dev, ref_p, ("w1", "b1", "w2", "b2", "w3", "b3")):
+        _assert_grad_close(d.grad, r.grad, nm)
+
+
+def test_gripper_trunk_bf16_vs_torch():
+    from hulc2_b200 import ops
+
+    Fr = 5
+    x = _rand(Fr, 3, 84, 84, seed=1)
+    ws = [_rand(32, 3, 8, 8, seed=2, scale=0.08), _rand(64, 32, 4, 4, seed=3, scale=0.05), _rand(64, 64, 3, 3, seed=4, scale=0.05)]
+    bs = [_rand(32, seed=5, scale=0.1), _rand(64, seed=6, scale=0.1), _rand(64, seed=7, scale=0.1)]
+    dev = [t.to(DEV).requires_grad_(True) for pair in zip(ws, bs) for t in pair]
+    flat = ops.GripperConvFlatten.apply(x.to(DEV), *dev)
+    g = _rand(Fr, 3136, seed=9)
+    flat.backward(g.to(DEV))
+    torch.cuda.synchronize()
+    ref_p = [t.clone().requires_grad_(True) for pair in zip(ws, bs) for t in pair]
+    a = F.relu(F.conv2d(x, ref_p[0], ref_p[1], stride=4))
+    a = F.relu(F.conv2d(a, ref_p[2], ref_p[3], stride=2))
+    a = F.relu(F.conv2d(a, ref_p[4], ref_p[5], stride=1)).flatten(1)
+    a.backward(g)
+    assert_close(flat.cpu(), a, 2e-2, "flatten")
+    for d, r, nm in zip(dev, ref_p, ("w1", "b1", "w2", "b2", "w3", "b3")):
+        _assert_grad_close(d.grad, r.grad, nm)
