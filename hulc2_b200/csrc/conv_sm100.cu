@@ -24,6 +24,7 @@
 // channels whose im2col rows are KH contiguous segments of 2*16*C elements.
 // Reference: hulc2/models/perceptual_encoders/vision_network.py:38-48, vision_network_gripper.py:11-26.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sm100.cuh"
@@ -35,17 +36,59 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int KT = 64;                       // k per stage (one 128-byte swizzle row)
-constexpr int STAGES = 6;
-constexpr int LAG = 3;                       // cp.async groups in flight per producer thread before a stage is published
+constexpr int MAX_STAGES = 12;               // ring depth is chosen at launch from the shared memory left after the weights
+// a stage is published once `lag` younger cp.async groups have been issued by the same thread (lag = stages - 2)
 constexpr uint32_t A_STAGE = TILE_M * 128;   // 16 KB
-constexpr int N_EPI = 128, N_PROD = 128;
-constexpr int NT = N_EPI + 32 + N_PROD;      // 288 threads: warps 0-3 epilogue, 4 MMA, 5-8 producers
+// warp roles: 0-7 epilogue (TMEM lanes 32*(w%4).., column half w/4), 8 MMA issuer, 9-16 producers.
+// Profiling the first version (4 producer warps, one per SM sub-partition) showed the producers ~80 % busy issuing
+// address arithmetic at ~0.2 IPC per warp with every memory pipe < 30 % utilised: the gather is instruction-latency
+// bound, so it is spread over two warps per sub-partition and the per-copy instruction count is kept minimal.
+constexpr int EPI_WARPS = 8, PROD_WARPS = 8;
+constexpr int N_EPI = EPI_WARPS * 32, N_PROD = PROD_WARPS * 32;
+constexpr int MMA_WARP = EPI_WARPS;
+constexpr int NT = N_EPI + 32 + N_PROD;      // 544 threads
 constexpr int MAX_CLS = 4;
 constexpr int MAX_TAB = 160;
 
+// cp.async.wait_group takes an immediate: dispatch on the (warp-uniform) runtime lag
+__device__ __forceinline__ void cp_async_wait_dyn(uint32_t n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    case 7: cp_async_wait<7>(); break;
+    case 8: cp_async_wait<8>(); break;
+    case 9: cp_async_wait<9>(); break;
+    default: cp_async_wait<10>(); break;
+  }
+}
+
+// exact unsigned division by a runtime constant (Granlund-Montgomery round-up method), n < 2^31
+struct FastDiv {
+  uint32_t mul, sh1, sh2, d;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.sh1 = l > 1 ? 1 : l;
+  f.sh2 = l > 0 ? l - 1 : 0;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(f.mul, n);
+  return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+
 struct ConvClass {
   int M;                 // rows (pixels) of this class
-  int PH, PW;            // row r -> (f, i, j): f = r / (PH*PW), i = rem / PW, j = rem % PW
+  FastDiv dHW, dW;       // row r -> (f, i, j): f = r / (PH*PW), i = rem / PW, j = rem % PW
   int tile_begin;        // first tile of this class in the launch-wide tile order
   int K;                 // contraction length (multiple of 64)
   int w_off;             // byte offset of this class's packed weights [N][K]
@@ -65,20 +108,24 @@ struct ConvParams {
   int oH, oW;
   int w_bytes;           // total packed weight bytes
   int ntab;
+  int stages, lag;       // A ring depth and publish lag (lag <= stages - 2)
   ConvClass cls[MAX_CLS];
   int2 table[MAX_TAB];   // per 16-byte chunk of K: {delta in 16-byte units, (a << 16) | b}
 };
 
-template <int BN>
+// DGRAD = false: forward conv (every tap of a valid row is in range, output rows are dense: pixel = row)
+// DGRAD = true : input gradient (per-tap validity -> zero fill, strided output pixels, optional ReLU mask)
+template <int BN, bool DGRAD>
 __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_slot;
   __shared__ int2 tab_s[MAX_TAB];
   __shared__ float bias_s[BN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t STAGES = (uint32_t)p.stages, LAG = (uint32_t)p.lag;
   const uint32_t a_smem = base;                              // STAGES x 16 KB
   const uint32_t w_smem = base + STAGES * A_STAGE;           // per class: K/64 tiles of [BN rows][128 B]
   constexpr uint32_t W_TILE = BN * 128;
@@ -86,7 +133,7 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), TCOLS);
   if (tid == 32) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), N_PROD); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (uint32_t s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), N_PROD); mbar_init(smem_u32(&empty_bar[s]), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), N_EPI); }
     mbar_fence_init();
   }
@@ -112,53 +159,55 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
 
   auto class_of = [&](int tile) {
     int c = 0;
+    if (DGRAD) {
 #pragma unroll
-    for (int k = 1; k < MAX_CLS; ++k) if (k < p.ncls && tile >= p.cls[k].tile_begin) c = k;
+      for (int k = 1; k < MAX_CLS; ++k) if (k < p.ncls && tile >= p.cls[k].tile_begin) c = k;
+    }
     return c;
   };
 
-  if (warp >= 5) {
-    // ===================================================== producers
+  if (warp > MMA_WARP) {
+    // ===================================================== producers (256 threads: 32 rows x 8 chunks per pass, 4 passes)
     const int t = tid - (N_EPI + 32);
-    const int c8 = t & 7, r0 = t >> 3;                       // chunk column, first row; rows r0 + 16 i
-    const uint32_t dst_t = swz128(r0, c8);                   // + i * 2048 (16 rows = 2 atoms)
+    const int c8 = t & 7, r0 = t >> 3;
+    const uint32_t dst_t = swz128(r0, c8);                   // + q * 4096 (32 rows = 4 atoms)
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const ConvClass& cl = p.cls[class_of(tile)];
       const int m0 = (tile - cl.tile_begin) * TILE_M;
-      int rbase[8];
-      uint32_t rij[8];
-      {
-        int r = m0 + r0;
-        const int hw = cl.PH * cl.PW;
-        int f = r / hw, rem = r - f * hw;
-        int i = rem / cl.PW, j = rem - i * cl.PW;
+      const uint8_t* rptr[4];
+      uint32_t rij[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          rbase[q] = f * cl.sF + i * cl.sI + j * cl.sJ;
-          rij[q] = (r < cl.M) ? (((uint32_t)i << 16) | (uint32_t)j) : 0x7fff7fffu;
-          r += 16; j += 16;
-          while (j >= cl.PW) { j -= cl.PW; ++i; }
-          while (i >= cl.PH) { i -= cl.PH; ++f; }
-        }
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t r = (uint32_t)(m0 + r0 + 32 * q);
+        const uint32_t f = fdiv(r, cl.dHW), rem = r - f * cl.dHW.d;
+        const uint32_t i = fdiv(rem, cl.dW), j = rem - i * cl.dW.d;
+        const bool rv = r < (uint32_t)cl.M;
+        rptr[q] = p.x + ((long long)(rv ? (int)(f * cl.sF + i * cl.sI + j * cl.sJ) : 0) << 4);
+        rij[q] = rv ? ((i << 16) | j) : 0x7fff7fffu;
       }
       const int nkt = cl.K / KT;
       for (int kt = 0; kt < nkt; ++kt, ++it) {
         const uint32_t s = it % STAGES;
         mbar_wait(smem_u32(&empty_bar[s]), ((it / STAGES) & 1) ^ 1);
         const int2 e = tab_s[cl.tab_off + kt * 8 + c8];
-        const int ta = e.y >> 16, tb = e.y & 0xffff;
+        const long long doff = (long long)e.x << 4;
         const uint32_t dst = a_smem + s * A_STAGE + dst_t;
+        if (DGRAD) {
+          const int ta = e.y >> 16, tb = e.y & 0xffff;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int ii = (int)(rij[q] >> 16) - ta, jj = (int)(rij[q] & 0xffff) - tb;
-          const bool ok = (unsigned)ii < (unsigned)p.VH && (unsigned)jj < (unsigned)p.VW;
-          const uint8_t* src = ok ? p.x + ((long long)(rbase[q] + e.x) << 4) : p.x;
-          cp_async16_ca(dst + q * 2048, src, ok ? 16u : 0u);
+          for (int q = 0; q < 4; ++q) {
+            const int ii = (int)(rij[q] >> 16) - ta, jj = (int)(rij[q] & 0xffff) - tb;
+            const bool ok = (unsigned)ii < (unsigned)p.VH && (unsigned)jj < (unsigned)p.VW;
+            cp_async16_ca(dst + q * 4096, ok ? rptr[q] + doff : p.x, ok ? 16u : 0u);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cp_async16_ca(dst + q * 4096, rptr[q] + doff, rij[q] == 0x7fff7fffu ? 0u : 16u);
         }
         cp_async_commit();
         if (it >= LAG) {
-          cp_async_wait<LAG>();
+          cp_async_wait_dyn(LAG);
           fence_proxy_async();
           mbar_arrive(smem_u32(&full_bar[(it - LAG) % STAGES]));
         }
@@ -167,7 +216,7 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
     cp_async_wait<0>();
     fence_proxy_async();
     for (uint32_t k = (it > LAG ? it - LAG : 0); k < it; ++k) mbar_arrive(smem_u32(&full_bar[k % STAGES]));
-  } else if (warp == 4) {
+  } else if (warp == MMA_WARP) {
     // ===================================================== MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc(TILE_M, BN, false, false);
@@ -192,46 +241,61 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
     }
     __syncwarp();
   } else {
-    // ===================================================== epilogue (warps 0-3 <-> TMEM lanes 32w..32w+31)
+    // ===================================================== epilogue: warp w <-> TMEM lanes 32*(w%4).., columns (w/4)*BN/2..
+    constexpr int HC = BN / 2;                                           // columns per thread
+    const int lq = warp & 3, half = warp >> 2;
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
       const ConvClass& cl = p.cls[class_of(tile)];
       const uint32_t buf = ti & 1;
-      const int r = (tile - cl.tile_begin) * TILE_M + warp * 32 + lane;
+      const uint32_t r = (uint32_t)((tile - cl.tile_begin) * TILE_M + lq * 32 + lane);
+      long long opix = r;
+      if (DGRAD) {
+        const uint32_t f = fdiv(r, cl.dHW), rem = r - f * cl.dHW.d;
+        const uint32_t i = fdiv(rem, cl.dW), j = rem - i * cl.dW.d;
+        opix = ((long long)f * p.oH + i * cl.oS + cl.oPh) * p.oW + j * cl.oS + cl.oPw;
+      }
+      const bool rv = r < (uint32_t)cl.M;
+      uint4 mk[HC / 8];
+      if (DGRAD && p.mask && rv) {
+#pragma unroll
+        for (int c = 0; c < HC / 8; ++c) mk[c] = __ldg(reinterpret_cast<const uint4*>(p.mask + opix * (BN * 2) + half * HC * 2) + c);
+      }
       mbar_wait(smem_u32(&tfull_bar[buf]), (ti >> 1) & 1);
       tc_fence_after();
-      uint32_t acc[BN];
+      uint32_t acc[HC];
 #pragma unroll
-      for (int c = 0; c < BN; c += 16) tmem_ld16_nowait(tmem_d + ((uint32_t)(warp * 32) << 16) + buf * BN + c, *reinterpret_cast<uint32_t(*)[16]>(&acc[c]));
+      for (int c = 0; c < HC; c += 16)
+        tmem_ld16_nowait(tmem_d + ((uint32_t)(lq * 32) << 16) + buf * BN + half * HC + c, *reinterpret_cast<uint32_t(*)[16]>(&acc[c]));
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(&tempty_bar[buf]));
-      if (r < cl.M) {
-        const int hw = cl.PH * cl.PW;
-        const int f = r / hw, rem = r - f * hw;
-        const int i = rem / cl.PW, j = rem - i * cl.PW;
-        const long long opix = ((long long)f * p.oH + i * cl.oS + cl.oPh) * p.oW + j * cl.oS + cl.oPw;
-        uint4* out = reinterpret_cast<uint4*>(p.y + opix * (BN * 2));
-        const uint4* mk = p.mask ? reinterpret_cast<const uint4*>(p.mask + opix * (BN * 2)) : nullptr;
+      if (rv) {
+        uint4* out = reinterpret_cast<uint4*>(p.y + opix * (BN * 2) + half * HC * 2);
 #pragma unroll
-        for (int c = 0; c < BN; c += 8) {
-          float v[8];
+        for (int c = 0; c < HC; c += 8) {
+          uint32_t o[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[c + e]) + bias_s[c + e];
-          if (p.relu) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+          for (int e = 0; e < 4; ++e) {
+            float lo = __uint_as_float(acc[c + 2 * e]), hi = __uint_as_float(acc[c + 2 * e + 1]);
+            if (!DGRAD) {
+              lo += bias_s[half * HC + c + 2 * e]; hi += bias_s[half * HC + c + 2 * e + 1];
+              if (p.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+            }
+            o[e] = pack_bf16x2(lo, hi);
           }
-          if (mk) {
-            const uint4 m = __ldg(mk + (c >> 3));
-            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+          if (DGRAD && p.mask) {
+            const uint32_t mw[4] = {mk[c >> 3].x, mk[c >> 3].y, mk[c >> 3].z, mk[c >> 3].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              if (!(bf16_lo(mw[e]) > 0.f)) v[2 * e] = 0.f;
-              if (!(bf16_hi(mw[e]) > 0.f)) v[2 * e + 1] = 0.f;
+              // bf16 activations are >= 0 after ReLU: keep a half-word where the mask half-word is a positive number
+              const uint32_t m = mw[e];
+              const uint32_t keep = (((m & 0x7fffu) != 0 && !(m & 0x8000u)) ? 0x0000ffffu : 0u) |
+                                    (((m & 0x7fff0000u) != 0 && !(m & 0x80000000u)) ? 0xffff0000u : 0u);
+              o[e] &= keep;
             }
           }
-          out[c >> 3] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          out[c >> 3] = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
     }
@@ -243,8 +307,7 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
 
 // ------------------------------------------------------------------------------------------------ wgrad
 constexpr int WG_KP = 32;                     // pixels (contraction rows) per stage
-constexpr int WG_STAGES = 4;
-constexpr int WG_LAG = 2;
+constexpr int WG_MAX_STAGES = 12;
 constexpr uint32_t WG_BLK = WG_KP * 128;      // one 64-wide M/N block of a stage: 32 k-rows x 128 B = 4 KB
 constexpr int WG_MAX_BLK = 10;                // <= 5 M-tiles of 128 -> 320 TMEM columns
 
@@ -252,39 +315,40 @@ struct WgradParams {
   const uint8_t* x;      // bf16 NHWC input of the conv
   const uint8_t* dz;     // bf16 [P, Cout]
   float* partial;        // [grid][nblk*64][64] fp32
-  int P, PH, PW;         // pixels = F*OH*OW; pixel -> (f, oh, ow)
+  int P;                 // pixels = F*OH*OW
+  FastDiv dHW, dW;       // pixel -> (f, oh, ow)
   int sF, sI, sJ;        // im2col row base in 16-byte units
   int K;                 // kconv (multiple of 64); data blocks = K/64; ones block = K/64; nblk (even) >= K/64 + 1
   int nblk;
   int cout8;             // Cout / 8 (4 or 8)
   int nstages;           // ceil(P / 32)
+  int stages, lag;       // ring depth / publish lag (see conv_igemm_kernel)
   int delta[72];         // per 16-byte chunk of kconv: offset in 16-byte units
 };
 
 __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[WG_STAGES], empty_bar[WG_STAGES], done_bar;
+  __shared__ __align__(8) uint64_t full_bar[WG_MAX_STAGES], empty_bar[WG_MAX_STAGES], done_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ int delta_s[72];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = (uint32_t)(p.nblk + 1) * WG_BLK;          // A blocks + the dZ block
+  const uint32_t WG_STAGES = (uint32_t)p.stages, WG_LAG = (uint32_t)p.lag;
   const int nbd = p.K / 64;                                               // data blocks
   const int nmt = p.nblk / 2;
   const uint32_t tcols = nmt * 64 <= 64 ? 64u : (nmt * 64 <= 128 ? 128u : (nmt * 64 <= 256 ? 256u : 512u));
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), tcols);
   if (tid == 32) {
-    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), N_PROD); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (uint32_t s = 0; s < WG_STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), N_PROD); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(&done_bar), 1);
     mbar_fence_init();
   }
-  for (int i = tid; i < p.K / 8; i += NT) delta_s[i] = p.delta[i];
   // zero every stage, then fill the ones block (bf16 1.0 = 0x3F80) -- neither is touched by the producers
   for (uint32_t o = tid * 16; o < WG_STAGES * stage_bytes; o += NT * 16)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(0u) : "memory");
   __syncthreads();
-  for (int s = 0; s < WG_STAGES; ++s)
+  for (uint32_t s = 0; s < WG_STAGES; ++s)
     for (uint32_t o = tid * 16; o < WG_BLK; o += NT * 16)
       asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + s * stage_bytes + nbd * WG_BLK + o), "r"(0x3F803F80u) : "memory");
   fence_proxy_async();
@@ -297,48 +361,34 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant
   const int sbeg = (int)((long long)p.nstages * blockIdx.x / gridDim.x);
   const int send = (int)((long long)p.nstages * (blockIdx.x + 1) / gridDim.x);
 
-  if (warp >= 5) {
+  if (warp > MMA_WARP) {
+    // producers: 256 threads = 32 pixels x 8 chunks; each thread copies its chunk column of every block of its pixel
     const int t = tid - (N_EPI + 32);
-    const int c8 = t & 7, g = t >> 3;                        // chunk-in-row; pixel group: pixels g and g + 16
-    // running decode of the two pixels this thread serves
-    int pf[2], pi[2], pj[2];
-    const int hw = p.PH * p.PW;
+    const int c8 = t & 7, g = t >> 3;
+    const uint32_t drow = swz128(g, c8);
+    int dl[9];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      long long pix = (long long)sbeg * WG_KP + g + 16 * h;
-      pf[h] = (int)(pix / hw);
-      int rem = (int)(pix - (long long)pf[h] * hw);
-      pi[h] = rem / p.PW;
-      pj[h] = rem - pi[h] * p.PW;
-    }
+    for (int b = 0; b < 9; ++b) dl[b] = b < nbd ? p.delta[b * 8 + c8] : 0;
+    const bool has_dz = c8 < p.cout8;
     uint32_t it = 0;
     for (int st = sbeg; st < send; ++st, ++it) {
       const uint32_t s = it % WG_STAGES;
+      const long long pix = (long long)st * WG_KP + g;
+      const bool ok = pix < p.P;
+      const uint32_t pu = ok ? (uint32_t)pix : 0u;
+      const uint32_t f = fdiv(pu, p.dHW), rem = pu - f * p.dHW.d;
+      const uint32_t i = fdiv(rem, p.dW), j = rem - i * p.dW.d;
+      const uint8_t* rp = p.x + ((long long)(int)(f * p.sF + i * p.sI + j * p.sJ) << 4);
+      const uint32_t nb = ok ? 16u : 0u;
       mbar_wait(smem_u32(&empty_bar[s]), ((it / WG_STAGES) & 1) ^ 1);
-      const uint32_t sb = base + s * stage_bytes;
+      const uint32_t sb = base + s * stage_bytes + drow;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int prow = g + 16 * h;
-        const long long pix = (long long)st * WG_KP + prow;
-        const bool ok = pix < p.P;
-        const int rb = pf[h] * p.sF + pi[h] * p.sI + pj[h] * p.sJ;
-        const uint32_t drow = sb + swz128(prow, c8);
-        for (int b = 0; b < nbd; ++b) {
-          const uint8_t* src = ok ? p.x + ((long long)(rb + delta_s[b * 8 + c8]) << 4) : p.x;
-          cp_async16_ca(drow + b * WG_BLK, src, ok ? 16u : 0u);
-        }
-        if (c8 < p.cout8) {
-          const uint8_t* src = ok ? p.dz + ((pix * p.cout8 + c8) << 4) : p.dz;
-          cp_async16(sb + p.nblk * WG_BLK + swz128(prow, c8), src, ok ? 16u : 0u);
-        }
-        // advance this pixel by one stage
-        pj[h] += WG_KP;
-        while (pj[h] >= p.PW) { pj[h] -= p.PW; ++pi[h]; }
-        while (pi[h] >= p.PH) { pi[h] -= p.PH; ++pf[h]; }
-      }
+      for (int b = 0; b < 9; ++b)
+        if (b < nbd) cp_async16_ca(sb + b * WG_BLK, rp + ((long long)dl[b] << 4), nb);
+      if (has_dz) cp_async16(sb + p.nblk * WG_BLK, p.dz + (((long long)pu * p.cout8 + c8) << 4), nb);
       cp_async_commit();
       if (it >= WG_LAG) {
-        cp_async_wait<WG_LAG>();
+        cp_async_wait_dyn(WG_LAG);
         fence_proxy_async();
         mbar_arrive(smem_u32(&full_bar[(it - WG_LAG) % WG_STAGES]));
       }
@@ -346,7 +396,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant
     cp_async_wait<0>();
     fence_proxy_async();
     for (uint32_t k = (it > WG_LAG ? it - WG_LAG : 0); k < it; ++k) mbar_arrive(smem_u32(&full_bar[k % WG_STAGES]));
-  } else if (warp == 4) {
+  } else if (warp == MMA_WARP) {
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc(128, 64, true, true);
       uint32_t it = 0;
@@ -369,17 +419,20 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant
     }
     __syncwarp();
   } else {
+    // dump: warp w <-> TMEM lanes 32*(w%4).., columns (w/4)*32..+32 of every M-tile
+    const int lq = warp & 3, half = warp >> 2;
     mbar_wait(smem_u32(&done_bar), 0);
     tc_fence_after();
     float* out = p.partial + (size_t)blockIdx.x * p.nblk * 64 * 64;
     for (int mt = 0; mt < nmt; ++mt) {
-      uint32_t acc[64];
+      uint32_t acc[32];
 #pragma unroll
-      for (int c = 0; c < 64; c += 16) tmem_ld16_nowait(tmem_d + ((uint32_t)(warp * 32) << 16) + mt * 64 + c, *reinterpret_cast<uint32_t(*)[16]>(&acc[c]));
+      for (int c = 0; c < 32; c += 16)
+        tmem_ld16_nowait(tmem_d + ((uint32_t)(lq * 32) << 16) + mt * 64 + half * 32 + c, *reinterpret_cast<uint32_t(*)[16]>(&acc[c]));
       tmem_ld_wait();
-      float4* o4 = reinterpret_cast<float4*>(out + (size_t)(mt * 128 + warp * 32 + lane) * 64);
+      float4* o4 = reinterpret_cast<float4*>(out + (size_t)(mt * 128 + lq * 32 + lane) * 64 + half * 32);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) o4[c] = make_float4(__uint_as_float(acc[4 * c]), __uint_as_float(acc[4 * c + 1]), __uint_as_float(acc[4 * c + 2]), __uint_as_float(acc[4 * c + 3]));
+      for (int c = 0; c < 8; ++c) o4[c] = make_float4(__uint_as_float(acc[4 * c]), __uint_as_float(acc[4 * c + 1]), __uint_as_float(acc[4 * c + 2]), __uint_as_float(acc[4 * c + 3]));
     }
   }
   tc_fence_before();
@@ -476,11 +529,16 @@ int sm_count() {
   return sms;
 }
 
-template <int BN>
+template <int BN, bool DGRAD>
 int launch_igemm(const ConvParams& p, cudaStream_t st) {
-  auto kern = conv_igemm_kernel<BN>;
-  const int smem = STAGES * (int)A_STAGE + p.w_bytes + 1024;
-  if (smem > 227 * 1024) { hulc2_set_error("convb: packed weights do not fit in shared memory"); return HULC2_EINVAL; }
+  auto kern = conv_igemm_kernel<BN, DGRAD>;
+  int stages = (227 * 1024 - 2048 - p.w_bytes - 1024) / (int)A_STAGE;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (const char* e = getenv("HULC2_CONV_STAGES")) { int v = atoi(e); if (v >= 3 && v < stages) stages = v; }
+  if (stages < 3) { hulc2_set_error("convb: packed weights do not fit in shared memory"); return HULC2_EINVAL; }
+  ConvParams q = p;
+  q.stages = stages; q.lag = stages - 2;
+  const int smem = stages * (int)A_STAGE + p.w_bytes + 1024;
   static int configured = 0;
   if (configured < smem) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
@@ -490,7 +548,7 @@ int launch_igemm(const ConvParams& p, cudaStream_t st) {
     configured = smem;
   }
   const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
-  kern<<<grid, NT, smem, st>>>(p);
+  kern<<<grid, NT, smem, st>>>(q);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }
@@ -546,7 +604,7 @@ int hulc2_convb_fwd(const hulc2_convb_args* a, cudaStream_t st) {
   p.ncls = 1; p.N = a->Cout; p.relu = a->relu;
   p.VH = OH; p.VW = OW; p.oH = OH; p.oW = OW;
   ConvClass& c = p.cls[0];
-  c.M = a->F * OH * OW; c.PH = OH; c.PW = OW; c.tile_begin = 0; c.K = a->KH * a->KW * a->C; c.w_off = 0; c.tab_off = 0;
+  c.M = a->F * OH * OW; c.dHW = make_fastdiv(OH * OW); c.dW = make_fastdiv(OW); c.tile_begin = 0; c.K = a->KH * a->KW * a->C; c.w_off = 0; c.tab_off = 0;
   c.sF = a->H * a->W * a->C / 8; c.sI = a->stride * a->W * a->C / 8; c.sJ = a->stride * a->C / 8;
   c.oS = 1; c.oPh = 0; c.oPw = 0;
   if (c.M == 0) return HULC2_OK;
@@ -558,7 +616,7 @@ int hulc2_convb_fwd(const hulc2_convb_args* a, cudaStream_t st) {
     const int kh = q / cpr;
     p.table[q] = make_int2(kh * a->W * a->C / 8 + (q - kh * cpr), 0);
   }
-  return a->Cout == 32 ? launch_igemm<32>(p, st) : launch_igemm<64>(p, st);
+  return a->Cout == 32 ? launch_igemm<32, false>(p, st) : launch_igemm<64, false>(p, st);
 }
 
 int hulc2_convb_dgrad(const hulc2_convb_args* a, cudaStream_t st) {
@@ -581,7 +639,7 @@ int hulc2_convb_dgrad(const hulc2_convb_args* a, cudaStream_t st) {
       if (CH <= 0 || CW <= 0) { woff += a->C * K * 2; continue; }
       if (K <= 0 || K % 64 != 0 || tab + K / 8 > MAX_TAB || ncls >= MAX_CLS) { hulc2_set_error("convb_dgrad: unsupported class shape"); return HULC2_ENOTIMPL; }
       ConvClass& c = p.cls[ncls++];
-      c.M = a->F * CH * CW; c.PH = CH; c.PW = CW; c.tile_begin = tiles; c.K = K; c.w_off = woff; c.tab_off = tab;
+      c.M = a->F * CH * CW; c.dHW = make_fastdiv(CH * CW); c.dW = make_fastdiv(CW); c.tile_begin = tiles; c.K = K; c.w_off = woff; c.tab_off = tab;
       c.sF = OH * OW * co8; c.sI = OW * co8; c.sJ = co8;
       c.oS = s; c.oPh = ph; c.oPw = pw;
       for (int q = 0; q < K / 8; ++q) {
@@ -592,7 +650,7 @@ int hulc2_convb_dgrad(const hulc2_convb_args* a, cudaStream_t st) {
     }
   p.ncls = ncls; p.ntiles = tiles; p.w_bytes = woff; p.ntab = tab;
   if (tiles == 0) return HULC2_OK;
-  return a->C == 32 ? launch_igemm<32>(p, st) : launch_igemm<64>(p, st);
+  return a->C == 32 ? launch_igemm<32, true>(p, st) : launch_igemm<64, true>(p, st);
 }
 
 int hulc2_convb_wgrad(const hulc2_convb_args* a, cudaStream_t st) {
@@ -601,7 +659,7 @@ int hulc2_convb_wgrad(const hulc2_convb_args* a, cudaStream_t st) {
   const int OH = (a->H - a->KH) / a->stride + 1, OW = (a->W - a->KW) / a->stride + 1;
   WgradParams p{};
   p.x = (const uint8_t*)a->x; p.dz = (const uint8_t*)a->dy;
-  p.P = a->F * OH * OW; p.PH = OH; p.PW = OW;
+  p.P = a->F * OH * OW; p.dHW = make_fastdiv(OH * OW); p.dW = make_fastdiv(OW);
   p.sF = a->H * a->W * a->C / 8; p.sI = a->stride * a->W * a->C / 8; p.sJ = a->stride * a->C / 8;
   p.K = a->KH * a->KW * a->C;
   p.nblk = p.K / 64 + 1; if (p.nblk & 1) ++p.nblk;
@@ -622,7 +680,11 @@ int hulc2_convb_wgrad(const hulc2_convb_args* a, cudaStream_t st) {
   const long long need = (long long)grid * p.nblk * 64 * 64 * sizeof(float);
   if (!a->workspace || a->workspace_bytes < need) { hulc2_set_error("convb_wgrad: workspace too small"); return HULC2_EWORKSPACE; }
   p.partial = (float*)a->workspace;
-  const int smem = WG_STAGES * (p.nblk + 1) * (int)WG_BLK + 1024;
+  int stages = (227 * 1024 - 2048 - 1024) / ((p.nblk + 1) * (int)WG_BLK);
+  if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
+  if (const char* e = getenv("HULC2_CONV_STAGES")) { int v = atoi(e); if (v >= 3 && v < stages) stages = v; }
+  p.stages = stages; p.lag = stages - 2;
+  const int smem = stages * (p.nblk + 1) * (int)WG_BLK + 1024;
   static int configured = 0;
   if (configured < smem) {
     if (cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {

@@ -33,14 +33,21 @@ def _precision():
     ops.set_precision("fp32")
 
 
-def _assert_grad_close(g, r, what):
-    """bf16 path-level gradient criterion (same as test_training_step_bf16_all_gradients_vs_oracle): norm within 3e-2
-    and cosine >= 0.99 against the un-rounded fp32 reference.  Element-wise max-norm checks are done per primitive
-    above, against references evaluated on the same bf16-rounded operands."""
-    g, r = g.detach().cpu().double().flatten(), r.detach().cpu().double().flatten()
-    ratio = float(g.norm() / (r.norm() + 1e-30))
-    cos = float((g * r).sum() / (g.norm() * r.norm() + 1e-30))
-    assert abs(ratio - 1) <= 3e-2 and cos >= 0.99, f"{what}: norm ratio {ratio:.4f}, cosine {cos:.5f}"
+def _ste_bf16(t):
+    """Round to bf16 in the forward pass, identity in the backward pass (the trunk stores activations as bf16)."""
+    return t + (_bf(t) - t).detach()
+
+
+def _ref_trunk(x, params):
+    """fp32 torch model of the bf16 trunk with the SAME rounding points: bf16 weights, bf16 activations after every
+    ReLU, bf16 gradients w.r.t. every pre-activation.  Only summation order differs from the kernels."""
+    w1, b1, w2, b2, w3, b3 = params
+    a = _bf(x)
+    for w, b, s in ((w1, b1, 4), (w2, b2, 2), (w3, b3, 1)):
+        z = F.conv2d(a, _ste_bf16(w), b, stride=s)
+        z.register_hook(lambda g: _bf(g))
+        a = _ste_bf16(F.relu(z))
+    return a
 
 
 def _nhwc(x_nchw):
@@ -144,11 +151,12 @@ def test_static_trunk_many_tiles(Fr, H, W):
 
 @pytest.mark.parametrize("hw", [(200, 200), (150, 200)])
 def test_static_encoder_bf16_trunk_vs_torch(hw):
-    """StaticConvSSM (conv trunk + SpatialSoftmax) forward and all six parameter gradients vs torch fp32: 2e-2."""
+    """StaticConvSSM (conv trunk + SpatialSoftmax) forward and all six parameter gradients vs the fp32 torch model of
+    the trunk with identical bf16 rounding points (step-level parity vs the un-rounded reference is in test_gpu_bf16.py)."""
     from hulc2_b200 import ops
     from hulc2_b200.models.perceptual_encoders.vision_network import SpatialSoftmax
 
-    Fr = 6
+    Fr = 16
     H, W = hw
     x = _rand(Fr, 3, H, W, seed=1)
     ws = [_rand(32, 3, 8, 8, seed=2, scale=0.08), _rand(64, 32, 4, 4, seed=3, scale=0.05), _rand(64, 64, 3, 3, seed=4, scale=0.05)]
@@ -163,18 +171,16 @@ def test_static_encoder_bf16_trunk_vs_torch(hw):
     torch.cuda.synchronize()
 
     ref_p = [t.clone().requires_grad_(True) for pair in zip(ws, bs) for t in pair]
-    a = F.relu(F.conv2d(x, ref_p[0], ref_p[1], stride=4))
-    a = F.relu(F.conv2d(a, ref_p[2], ref_p[3], stride=2))
-    a = F.relu(F.conv2d(a, ref_p[4], ref_p[5], stride=1))
+    a = _ref_trunk(x, ref_p)
     n, c, h, w = a.shape
     sm = torch.softmax(a.reshape(-1, h * w), dim=1)
     ex = (sm * ssm.x_map).sum(1, keepdim=True)
     ey = (sm * ssm.y_map).sum(1, keepdim=True)
     ref = torch.cat((ex, ey), 1).view(n, 2 * c)
     ref.backward(g)
-    assert_close(out.cpu(), ref, 2e-2, "keypoints")
+    assert_close(out.cpu(), ref, 5e-3, "keypoints")
     for d, r, nm in zip(dev, ref_p, ("w1", "b1", "w2", "b2", "w3", "b3")):
-        _assert_grad_close(d.grad, r.grad, nm)
+        assert_close(d.grad.cpu(), r.grad, 2e-2, nm)
 
 
 def test_gripper_trunk_bf16_vs_torch():
@@ -190,10 +196,8 @@ def test_gripper_trunk_bf16_vs_torch():
     flat.backward(g.to(DEV))
     torch.cuda.synchronize()
     ref_p = [t.clone().requires_grad_(True) for pair in zip(ws, bs) for t in pair]
-    a = F.relu(F.conv2d(x, ref_p[0], ref_p[1], stride=4))
-    a = F.relu(F.conv2d(a, ref_p[2], ref_p[3], stride=2))
-    a = F.relu(F.conv2d(a, ref_p[4], ref_p[5], stride=1)).flatten(1)
+    a = _ref_trunk(x, ref_p).flatten(1)
     a.backward(g)
-    assert_close(flat.cpu(), a, 2e-2, "flatten")
+    assert_close(flat.cpu(), a, 1e-2, "flatten")
     for d, r, nm in zip(dev, ref_p, ("w1", "b1", "w2", "b2", "w3", "b3")):
-        _assert_grad_close(d.grad, r.grad, nm)
+        assert_close(d.grad.cpu(), r.grad, 2e-2, nm)
