@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
     const int t = tid - (N_EPI + 32);
     const int c8 = t & 7, r0 = t >> 3;
     const uint32_t dst_t = swz128(r0, c8);                   // + q * 4096 (32 rows = 4 atoms)
-    uint32_t it = 0;
+    // ring bookkeeping without runtime divisions: s/ph = stage being filled and its empty-barrier parity,
+    // ps = oldest stage not yet published, inflight = committed-but-unpublished groups (<= LAG)
+    uint32_t s = 0, ph = 1, ps = 0, inflight = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const ConvClass& cl = p.cls[class_of(tile)];
       const int m0 = (tile - cl.tile_begin) * TILE_M;
@@ -187,10 +189,10 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
         rij[q] = rv ? ((i << 16) | j) : 0x7fff7fffu;
       }
       const int nkt = cl.K / KT;
-      for (int kt = 0; kt < nkt; ++kt, ++it) {
-        const uint32_t s = it % STAGES;
-        mbar_wait(smem_u32(&empty_bar[s]), ((it / STAGES) & 1) ^ 1);
-        const int2 e = tab_s[cl.tab_off + kt * 8 + c8];
+      const int2* tab = tab_s + cl.tab_off + c8;
+      for (int kt = 0; kt < nkt; ++kt) {
+        mbar_wait(smem_u32(&empty_bar[s]), ph);
+        const int2 e = tab[kt * 8];
         const long long doff = (long long)e.x << 4;
         const uint32_t dst = a_smem + s * A_STAGE + dst_t;
         if (DGRAD) {
@@ -206,35 +208,42 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
           for (int q = 0; q < 4; ++q) cp_async16_ca(dst + q * 4096, rptr[q] + doff, rij[q] == 0x7fff7fffu ? 0u : 16u);
         }
         cp_async_commit();
-        if (it >= LAG) {
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (inflight == LAG) {
           cp_async_wait_dyn(LAG);
           fence_proxy_async();
-          mbar_arrive(smem_u32(&full_bar[(it - LAG) % STAGES]));
+          mbar_arrive(smem_u32(&full_bar[ps]));
+          if (++ps == STAGES) ps = 0;
+        } else {
+          ++inflight;
         }
       }
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    for (uint32_t k = (it > LAG ? it - LAG : 0); k < it; ++k) mbar_arrive(smem_u32(&full_bar[k % STAGES]));
+    for (; inflight > 0; --inflight) {
+      mbar_arrive(smem_u32(&full_bar[ps]));
+      if (++ps == STAGES) ps = 0;
+    }
   } else if (warp == MMA_WARP) {
     // ===================================================== MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc(TILE_M, BN, false, false);
-      uint32_t it = 0, ti = 0;
+      uint32_t s = 0, ph = 0, ti = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
         const ConvClass& cl = p.cls[class_of(tile)];
         const uint32_t buf = ti & 1;
         mbar_wait(smem_u32(&tempty_bar[buf]), ((ti >> 1) & 1) ^ 1);      // epilogue drained this accumulator
         tc_fence_after();
         const int nkt = cl.K / KT;
-        for (int kt = 0; kt < nkt; ++kt, ++it) {
-          const uint32_t s = it % STAGES;
-          mbar_wait(smem_u32(&full_bar[s]), (it / STAGES) & 1);
+        for (int kt = 0; kt < nkt; ++kt) {
+          mbar_wait(smem_u32(&full_bar[s]), ph);
           tc_fence_after();
           const uint64_t ad = make_desc(a_smem + s * A_STAGE, 0), bd = make_desc(w_smem + cl.w_off + kt * W_TILE, 0);
 #pragma unroll
           for (int k = 0; k < KT / 16; ++k) umma_bf16(tmem_d + buf * BN, ad + 2 * k, bd + 2 * k, IDESC, (kt > 0 || k > 0) ? 1u : 0u);
           umma_commit(smem_u32(&empty_bar[s]));                          // stage reusable once these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(smem_u32(&tfull_bar[buf]));                          // accumulator complete
       }
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
 #pragma unroll
         for (int c = 0; c < HC / 8; ++c) mk[c] = __ldg(reinterpret_cast<const uint4*>(p.mask + opix * (BN * 2) + half * HC * 2) + c);
       }
-      mbar_wait(smem_u32(&tfull_bar[buf]), (ti >> 1) & 1);
+      mbar_wait_relaxed(smem_u32(&tfull_bar[buf]), (ti >> 1) & 1);
       tc_fence_after();
       uint32_t acc[HC];
 #pragma unroll
@@ -370,9 +379,8 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant
 #pragma unroll
     for (int b = 0; b < 9; ++b) dl[b] = b < nbd ? p.delta[b * 8 + c8] : 0;
     const bool has_dz = c8 < p.cout8;
-    uint32_t it = 0;
-    for (int st = sbeg; st < send; ++st, ++it) {
-      const uint32_t s = it % WG_STAGES;
+    uint32_t s = 0, ph = 1, ps = 0, inflight = 0;
+    for (int st = sbeg; st < send; ++st) {
       const long long pix = (long long)st * WG_KP + g;
       const bool ok = pix < p.P;
       const uint32_t pu = ok ? (uint32_t)pix : 0u;
@@ -380,29 +388,35 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant
       const uint32_t i = fdiv(rem, p.dW), j = rem - i * p.dW.d;
       const uint8_t* rp = p.x + ((long long)(int)(f * p.sF + i * p.sI + j * p.sJ) << 4);
       const uint32_t nb = ok ? 16u : 0u;
-      mbar_wait(smem_u32(&empty_bar[s]), ((it / WG_STAGES) & 1) ^ 1);
+      mbar_wait(smem_u32(&empty_bar[s]), ph);
       const uint32_t sb = base + s * stage_bytes + drow;
 #pragma unroll
       for (int b = 0; b < 9; ++b)
         if (b < nbd) cp_async16_ca(sb + b * WG_BLK, rp + ((long long)dl[b] << 4), nb);
       if (has_dz) cp_async16(sb + p.nblk * WG_BLK, p.dz + (((long long)pu * p.cout8 + c8) << 4), nb);
       cp_async_commit();
-      if (it >= WG_LAG) {
+      if (++s == WG_STAGES) { s = 0; ph ^= 1; }
+      if (inflight == WG_LAG) {
         cp_async_wait_dyn(WG_LAG);
         fence_proxy_async();
-        mbar_arrive(smem_u32(&full_bar[(it - WG_LAG) % WG_STAGES]));
+        mbar_arrive(smem_u32(&full_bar[ps]));
+        if (++ps == WG_STAGES) ps = 0;
+      } else {
+        ++inflight;
       }
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    for (uint32_t k = (it > WG_LAG ? it - WG_LAG : 0); k < it; ++k) mbar_arrive(smem_u32(&full_bar[k % WG_STAGES]));
+    for (; inflight > 0; --inflight) {
+      mbar_arrive(smem_u32(&full_bar[ps]));
+      if (++ps == WG_STAGES) ps = 0;
+    }
   } else if (warp == MMA_WARP) {
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc(128, 64, true, true);
-      uint32_t it = 0;
-      for (int st = sbeg; st < send; ++st, ++it) {
-        const uint32_t s = it % WG_STAGES;
-        mbar_wait(smem_u32(&full_bar[s]), (it / WG_STAGES) & 1);
+      uint32_t s = 0, ph = 0;
+      for (int st = sbeg; st < send; ++st) {
+        mbar_wait(smem_u32(&full_bar[s]), ph);
         tc_fence_after();
         const uint32_t sb = base + s * stage_bytes;
 #pragma unroll
@@ -410,10 +424,11 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant
           const uint64_t bd = make_desc(sb + p.nblk * WG_BLK + ks * 2048, WG_BLK);
           for (int mt = 0; mt < nmt; ++mt) {
             const uint64_t ad = make_desc(sb + mt * 2 * WG_BLK + ks * 2048, WG_BLK);
-            umma_bf16(tmem_d + mt * 64, ad, bd, IDESC, (it > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16(tmem_d + mt * 64, ad, bd, IDESC, (st > sbeg || ks > 0) ? 1u : 0u);
           }
         }
         umma_commit(smem_u32(&empty_bar[s]));
+        if (++s == WG_STAGES) { s = 0; ph ^= 1; }
       }
       umma_commit(smem_u32(&done_bar));
     }
@@ -421,7 +436,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant
   } else {
     // dump: warp w <-> TMEM lanes 32*(w%4).., columns (w/4)*32..+32 of every M-tile
     const int lq = warp & 3, half = warp >> 2;
-    mbar_wait(smem_u32(&done_bar), 0);
+    mbar_wait_relaxed(smem_u32(&done_bar), 0);
     tc_fence_after();
     float* out = p.partial + (size_t)blockIdx.x * p.nblk * 64 * 64;
     for (int mt = 0; mt < nmt; ++mt) {
@@ -532,9 +547,12 @@ int sm_count() {
 template <int BN, bool DGRAD>
 int launch_igemm(const ConvParams& p, cudaStream_t st) {
   auto kern = conv_igemm_kernel<BN, DGRAD>;
+  // Measured on B200: ring depth beyond 4 does not help (the gather is issue-bound, not latency-bound) while every
+  // 16 KB stage is taken from the unified L1 that serves the overlapping im2col windows (dgrad k4s2: 0.72 -> 0.58 ms).
   int stages = (227 * 1024 - 2048 - p.w_bytes - 1024) / (int)A_STAGE;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (const char* e = getenv("HULC2_CONV_STAGES")) { int v = atoi(e); if (v >= 3 && v < stages) stages = v; }
+  int want = 4;
+  if (const char* e = getenv("HULC2_CONV_STAGES")) { int v = atoi(e); if (v >= 3 && v <= MAX_STAGES) want = v; }
+  if (stages > want) stages = want;
   if (stages < 3) { hulc2_set_error("convb: packed weights do not fit in shared memory"); return HULC2_EINVAL; }
   ConvParams q = p;
   q.stages = stages; q.lag = stages - 2;
@@ -681,8 +699,9 @@ int hulc2_convb_wgrad(const hulc2_convb_args* a, cudaStream_t st) {
   if (!a->workspace || a->workspace_bytes < need) { hulc2_set_error("convb_wgrad: workspace too small"); return HULC2_EWORKSPACE; }
   p.partial = (float*)a->workspace;
   int stages = (227 * 1024 - 2048 - 1024) / ((p.nblk + 1) * (int)WG_BLK);
-  if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
-  if (const char* e = getenv("HULC2_CONV_STAGES")) { int v = atoi(e); if (v >= 3 && v < stages) stages = v; }
+  int want = 4;
+  if (const char* e = getenv("HULC2_CONV_STAGES")) { int v = atoi(e); if (v >= 3 && v <= WG_MAX_STAGES) want = v; }
+  if (stages > want) stages = want;
   p.stages = stages; p.lag = stages - 2;
   const int smem = stages * (p.nblk + 1) * (int)WG_BLK + 1024;
   static int configured = 0;

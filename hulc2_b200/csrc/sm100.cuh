@@ -27,6 +27,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// same, for waiters that are off the critical path (epilogue warps): back off between polls so the spinning warp
+// does not compete for issue slots with the producer warps of its SM sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spins = 0; !ok; ++spins) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok) __nanosleep(128);
+    if (spins > (1u << 22)) __trap();
+  }
+}
+
 // ---------------------------------------------------------------- async copies (LDGSTS) and proxy fences
 // 16-byte global -> shared copy; src_bytes = 0 writes zeros (nothing is read from src)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
