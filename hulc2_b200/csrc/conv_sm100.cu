@@ -89,7 +89,6 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
 struct ConvClass {
   int M;                 // rows (pixels) of this class
   FastDiv dHW, dW;       // row r -> (f, i, j): f = r / (PH*PW), i = rem / PW, j = rem % PW
-  int tile_begin;        // first tile of this class in the launch-wide tile order
   int K;                 // contraction length (multiple of 64)
   int w_off;             // byte offset of this class's packed weights [N][K]
   int tab_off;           // first chunk-table entry of this class
@@ -103,7 +102,8 @@ struct ConvParams {
   const float* bias;     // [N] or null
   const uint8_t* mask;   // bf16, same shape as the output: keep where > 0 (or null)
   uint8_t* y;            // bf16 output [*, N]
-  int ncls, ntiles, N, relu;
+  int ncls, ntiles, N, relu;  // ntiles = (max tiles of a class) << cls_shift: tile vt -> class vt & (ncls-1), tile-in-class vt >> cls_shift
+  int cls_shift;         // classes are interleaved so the s*s parity classes of one image region run back to back (dZ stays in L2)
   int VH, VW;            // a tap (a, b) of row (f,i,j) is valid iff 0 <= i-a < VH and 0 <= j-b < VW
   int oH, oW;
   int w_bytes;           // total packed weight bytes
@@ -157,14 +157,7 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
 
-  auto class_of = [&](int tile) {
-    int c = 0;
-    if (DGRAD) {
-#pragma unroll
-      for (int k = 1; k < MAX_CLS; ++k) if (k < p.ncls && tile >= p.cls[k].tile_begin) c = k;
-    }
-    return c;
-  };
+  const int cls_mask = (1 << p.cls_shift) - 1;
 
   if (warp > MMA_WARP) {
     // ===================================================== producers (256 threads: 32 rows x 8 chunks per pass, 4 passes)
@@ -175,8 +168,9 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
     // ps = oldest stage not yet published, inflight = committed-but-unpublished groups (<= LAG)
     uint32_t s = 0, ph = 1, ps = 0, inflight = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      const ConvClass& cl = p.cls[class_of(tile)];
-      const int m0 = (tile - cl.tile_begin) * TILE_M;
+      const ConvClass& cl = p.cls[DGRAD ? (tile & cls_mask) : 0];
+      const int m0 = (DGRAD ? (tile >> p.cls_shift) : tile) * TILE_M;
+      if (m0 >= cl.M) continue;
       const uint8_t* rptr[4];
       uint32_t rij[4];
 #pragma unroll
@@ -230,8 +224,9 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc(TILE_M, BN, false, false);
       uint32_t s = 0, ph = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
-        const ConvClass& cl = p.cls[class_of(tile)];
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const ConvClass& cl = p.cls[DGRAD ? (tile & cls_mask) : 0];
+        if ((DGRAD ? (tile >> p.cls_shift) : tile) * TILE_M >= cl.M) continue;
         const uint32_t buf = ti & 1;
         mbar_wait(smem_u32(&tempty_bar[buf]), ((ti >> 1) & 1) ^ 1);      // epilogue drained this accumulator
         tc_fence_after();
@@ -246,6 +241,7 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(smem_u32(&tfull_bar[buf]));                          // accumulator complete
+        ++ti;
       }
     }
     __syncwarp();
@@ -254,10 +250,12 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
     constexpr int HC = BN / 2;                                           // columns per thread
     const int lq = warp & 3, half = warp >> 2;
     uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
-      const ConvClass& cl = p.cls[class_of(tile)];
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const ConvClass& cl = p.cls[DGRAD ? (tile & cls_mask) : 0];
+      const int m0 = (DGRAD ? (tile >> p.cls_shift) : tile) * TILE_M;
+      if (m0 >= cl.M) continue;
       const uint32_t buf = ti & 1;
-      const uint32_t r = (uint32_t)((tile - cl.tile_begin) * TILE_M + lq * 32 + lane);
+      const uint32_t r = (uint32_t)(m0 + lq * 32 + lane);
       long long opix = r;
       if (DGRAD) {
         const uint32_t f = fdiv(r, cl.dHW), rem = r - f * cl.dHW.d;
@@ -307,6 +305,7 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
           out[c >> 3] = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
+      ++ti;
     }
   }
   tc_fence_before();
@@ -622,11 +621,11 @@ int hulc2_convb_fwd(const hulc2_convb_args* a, cudaStream_t st) {
   p.ncls = 1; p.N = a->Cout; p.relu = a->relu;
   p.VH = OH; p.VW = OW; p.oH = OH; p.oW = OW;
   ConvClass& c = p.cls[0];
-  c.M = a->F * OH * OW; c.dHW = make_fastdiv(OH * OW); c.dW = make_fastdiv(OW); c.tile_begin = 0; c.K = a->KH * a->KW * a->C; c.w_off = 0; c.tab_off = 0;
+  c.M = a->F * OH * OW; c.dHW = make_fastdiv(OH * OW); c.dW = make_fastdiv(OW); c.K = a->KH * a->KW * a->C; c.w_off = 0; c.tab_off = 0;
   c.sF = a->H * a->W * a->C / 8; c.sI = a->stride * a->W * a->C / 8; c.sJ = a->stride * a->C / 8;
   c.oS = 1; c.oPh = 0; c.oPw = 0;
   if (c.M == 0) return HULC2_OK;
-  p.ntiles = hulc2_cdiv(c.M, TILE_M);
+  p.ntiles = hulc2_cdiv(c.M, TILE_M); p.cls_shift = 0;
   p.w_bytes = a->Cout * c.K * 2;
   const int cpr = a->KW * a->C / 8;                    // chunks per kernel row (contiguous in memory)
   p.ntab = c.K / 8;
@@ -657,16 +656,19 @@ int hulc2_convb_dgrad(const hulc2_convb_args* a, cudaStream_t st) {
       if (CH <= 0 || CW <= 0) { woff += a->C * K * 2; continue; }
       if (K <= 0 || K % 64 != 0 || tab + K / 8 > MAX_TAB || ncls >= MAX_CLS) { hulc2_set_error("convb_dgrad: unsupported class shape"); return HULC2_ENOTIMPL; }
       ConvClass& c = p.cls[ncls++];
-      c.M = a->F * CH * CW; c.dHW = make_fastdiv(CH * CW); c.dW = make_fastdiv(CW); c.tile_begin = tiles; c.K = K; c.w_off = woff; c.tab_off = tab;
+      c.M = a->F * CH * CW; c.dHW = make_fastdiv(CH * CW); c.dW = make_fastdiv(CW); c.K = K; c.w_off = woff; c.tab_off = tab;
       c.sF = OH * OW * co8; c.sI = OW * co8; c.sJ = co8;
       c.oS = s; c.oPh = ph; c.oPw = pw;
       for (int q = 0; q < K / 8; ++q) {
         const int tap = q / co8, u = q - tap * co8, ta = tap / KB, tb = tap - ta * KB;
         p.table[tab + q] = make_int2(-(ta * OW + tb) * co8 + u, (ta << 16) | tb);
       }
-      tab += K / 8; woff += a->C * K * 2; tiles += hulc2_cdiv(c.M, TILE_M);
+      tab += K / 8; woff += a->C * K * 2;
+      if (hulc2_cdiv(c.M, TILE_M) > tiles) tiles = hulc2_cdiv(c.M, TILE_M);
     }
-  p.ncls = ncls; p.ntiles = tiles; p.w_bytes = woff; p.ntab = tab;
+  if (ncls != s * s) { hulc2_set_error("convb_dgrad: degenerate parity classes"); return HULC2_ENOTIMPL; }
+  p.cls_shift = s == 1 ? 0 : 2;
+  p.ncls = ncls; p.ntiles = tiles << p.cls_shift; p.w_bytes = woff; p.ntab = tab;
   if (tiles == 0) return HULC2_OK;
   return a->C == 32 ? launch_igemm<32, true>(p, st) : launch_igemm<64, true>(p, st);
 }
