@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8, help="windows per modality of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-graph", action="store_true", help="drive every step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--dump-profile", default=None, help="write the per-call CUDA-event profile of one step to this JSON file")
     return ap.parse_args()
 
@@ -193,7 +194,7 @@ def run_b200(args):
 
     torch.manual_seed(0)
     model = instantiate(hulc2_config(dropout_p=0.1)).to(dev).train()
-    trainer = PolicyTrainer(model)
+    trainer = PolicyTrainer(model, use_graph=not args.no_graph)
     batch = synthetic_batch_fast(B, seed=1 + rank, device=dev)
     h2d = nbytes(batch)
 
@@ -206,6 +207,7 @@ def run_b200(args):
         trainer.train_step(batch, i)
     barrier()
     l0 = _lib.load_library().hulc2_launch_count()
+    r0 = trainer.replays
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         e0.record()
@@ -216,7 +218,8 @@ def run_b200(args):
         e1.record()
         torch.cuda.synchronize()
     barrier()
-    launches = _lib.load_library().hulc2_launch_count() - l0
+    # kernels of this library launched in the timed region: direct C-ABI launches + (graph replays x kernels captured per replay)
+    launches = _lib.load_library().hulc2_launch_count() - l0 + (trainer.replays - r0) * trainer.launches_per_replay
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -241,7 +244,7 @@ def run_b200(args):
     # every rank runs the step (it contains the gradient all-reduce); only rank 0 records the per-call events
     if rank == 0:
         _lib.profile_begin()
-    trainer.train_step(batch, 0)
+    trainer.eager_step(batch, 0)           # eager pass of the same step (per-call events cannot be taken inside a graph replay)
     torch.cuda.synchronize()
     if rank == 0:
         recs = _lib.profile_end()
@@ -268,14 +271,18 @@ def run_b200(args):
             "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": "configs[1]: Hulc2 policy train step (fwd+bwd+allreduce+Adam), B=64/modality/GPU, window 32, static 200x200 + gripper 84x84 RGB fp32, 7-dof, lang [B,384], dropout 0.1",
                        "windows_per_step_per_gpu": 2 * B, "parallelism": f"dp{world}", "l2": "inputs (2.3 GB images/step) exceed the 126 MB L2",
-                       "precision": args.precision},
+                       "precision": args.precision, "cuda_graph": bool(trainer._graph is not None)},
             "clocks": clk.summary(), "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
             "e2e": {"value": e2e_val, "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
             "roofline": roof, "cpu_baseline": cpu, "loss": float(loss),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # a captured step holds NCCL work; tear down without the collective destroy (observed to hang at exit)
+        sys.stdout.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -147,7 +147,11 @@ __device__ __forceinline__ void philox4(uint64_t seed, uint64_t ctr, uint32_t (&
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
-__global__ void philox_uniform_kernel(float* __restrict__ out, long long n, uint64_t seed, uint64_t offset) {
+// `epoch` (optional device counter, bumped once per training step) moves the whole counter range: a step captured in
+// a CUDA graph draws fresh noise on every replay although its launch arguments are frozen.
+__global__ void philox_uniform_kernel(float* __restrict__ out, long long n, uint64_t seed, uint64_t offset,
+                                      const unsigned long long* __restrict__ epoch) {
+  if (epoch) offset += (uint64_t)(*epoch) << 40;
   long long nq = (n + 3) / 4;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
     uint32_t r[4];
@@ -159,7 +163,9 @@ __global__ void philox_uniform_kernel(float* __restrict__ out, long long n, uint
     }
   }
 }
-__global__ void dropout_mask_kernel(unsigned char* __restrict__ out, long long n, float p, uint64_t seed, uint64_t offset) {
+__global__ void dropout_mask_kernel(unsigned char* __restrict__ out, long long n, float p, uint64_t seed, uint64_t offset,
+                                    const unsigned long long* __restrict__ epoch) {
+  if (epoch) offset += (uint64_t)(*epoch) << 40;
   long long nq = (n + 3) / 4;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
     uint32_t r[4];
@@ -172,10 +178,17 @@ __global__ void dropout_mask_kernel(unsigned char* __restrict__ out, long long n
   }
 }
 
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+
 // ---------------------------------------------------------------- Adam (torch.optim.Adam, amsgrad=False, maximize=False)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
-                            float grad_scale) {
+                            float grad_scale, const unsigned long long* __restrict__ step_dev, int step_bias) {
+  if (step_dev) {  // step number lives on the device (CUDA-graph replays): bias corrections computed here
+    const double st = (double)(*step_dev) + (double)step_bias;
+    bc1 = (float)(1.0 - pow((double)b1, st));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, st));
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float gi = g[i] * grad_scale;
     float pi = p[i];
@@ -285,14 +298,14 @@ int hulc2_permute_conv_weight(const float* src, float* dst, int O, int I, int KH
 }
 int hulc2_philox_uniform(float* out, long long n, unsigned long long seed, unsigned long long offset, cudaStream_t st) {
   if (n <= 0) return HULC2_OK;
-  philox_uniform_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(out, n, seed, offset);
+  philox_uniform_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(out, n, seed, offset, nullptr);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }
 int hulc2_dropout_mask(unsigned char* out, long long n, float p, unsigned long long seed, unsigned long long offset,
                        cudaStream_t st) {
   if (n <= 0) return HULC2_OK;
-  dropout_mask_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(out, n, p, seed, offset);
+  dropout_mask_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(out, n, p, seed, offset, nullptr);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }
@@ -303,7 +316,37 @@ int hulc2_adam_step(float* p, const float* g, float* m, float* v, long long n, f
   double bc1 = 1.0 - pow((double)beta1, (double)step);
   double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
-                                                    (float)sqrt(bc2), grad_scale);
+                                                    (float)sqrt(bc2), grad_scale, nullptr, 0);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+// ---- CUDA-graph friendly variants: the step / noise epoch is a device counter
+int hulc2_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, const unsigned long long* step_counter, int step_bias,
+                        float grad_scale, cudaStream_t st) {
+  if (n <= 0) return HULC2_OK;
+  if (!step_counter) { hulc2_set_error("adam_step_dev: null step counter"); return HULC2_EINVAL; }
+  adam_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1.f, 1.f, grad_scale,
+                                                    step_counter, step_bias);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_philox_uniform_ep(float* out, long long n, unsigned long long seed, unsigned long long offset,
+                            const unsigned long long* epoch, cudaStream_t st) {
+  if (n <= 0) return HULC2_OK;
+  philox_uniform_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(out, n, seed, offset, epoch);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_dropout_mask_ep(unsigned char* out, long long n, float p, unsigned long long seed, unsigned long long offset,
+                          const unsigned long long* epoch, cudaStream_t st) {
+  if (n <= 0) return HULC2_OK;
+  dropout_mask_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(out, n, p, seed, offset, epoch);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_counter_add(unsigned long long* counter, unsigned long long inc, cudaStream_t st) {
+  counter_add_kernel<<<1, 1, 0, st>>>(counter, inc);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

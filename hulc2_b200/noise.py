@@ -17,11 +17,28 @@ import torch
 from . import ops
 
 _state = {"seed": 0x5EED, "counter": 0}
+_epochs: Dict[tuple, torch.Tensor] = {}   # per device: u64 step counter read by the Philox kernels (CUDA-graph replays)
 _queues: Dict[str, Deque[torch.Tensor]] = {"categories": deque(), "uniforms": deque(), "masks": deque()}
 
 
 def manual_seed(seed: int) -> None:
     _state["seed"] = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _state["counter"] = 0
+
+
+def epoch_tensor(device) -> torch.Tensor:
+    """Device-resident noise epoch (int64[1], starts at 0).  The Philox kernels add ``epoch << 40`` to their counter,
+    so a train step captured in a CUDA graph draws fresh noise on every replay; ``trainer`` bumps it once per step."""
+    device = torch.device(device)
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _epochs:
+        _epochs[key] = torch.zeros(1, dtype=torch.int64, device=device)
+    return _epochs[key]
+
+
+def begin_step() -> None:
+    """Restart the host-side counter: with the device epoch distinguishing steps, every step issues the same sequence
+    of (seed, offset) launch arguments -- what a captured graph replays."""
     _state["counter"] = 0
 
 
@@ -55,7 +72,7 @@ def uniform(shape, device) -> torch.Tensor:
     n = 1
     for s in shape:
         n *= int(s)
-    return ops.uniform(tuple(shape), device, _state["seed"], _next_offset(n))
+    return ops.uniform(tuple(shape), device, _state["seed"], _next_offset(n), epoch=epoch_tensor(device))
 
 
 def categories(logits: torch.Tensor, cats: int, classes: int) -> torch.Tensor:
@@ -77,4 +94,4 @@ def keep_mask(shape, p: float, device) -> Optional[torch.Tensor]:
     n = 1
     for s in shape:
         n *= int(s)
-    return ops.dropout_mask(tuple(shape), p, device, _state["seed"], _next_offset(n))
+    return ops.dropout_mask(tuple(shape), p, device, _state["seed"], _next_offset(n), epoch=epoch_tensor(device))

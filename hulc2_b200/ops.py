@@ -625,15 +625,15 @@ def categorical_sample(logits: torch.Tensor, u: torch.Tensor, cats: int, classes
     return idx
 
 
-def uniform(shape, device, seed: int, offset: int = 0) -> torch.Tensor:
+def uniform(shape, device, seed: int, offset: int = 0, epoch: Optional[torch.Tensor] = None) -> torch.Tensor:
     out = torch.empty(shape, device=device, dtype=torch.float32)
-    call("hulc2_philox_uniform", out.data_ptr(), out.numel(), seed, offset)
+    call("hulc2_philox_uniform_ep", out.data_ptr(), out.numel(), seed, offset, _p(epoch))
     return out
 
 
-def dropout_mask(shape, p: float, device, seed: int, offset: int = 0) -> torch.Tensor:
+def dropout_mask(shape, p: float, device, seed: int, offset: int = 0, epoch: Optional[torch.Tensor] = None) -> torch.Tensor:
     out = torch.empty(shape, device=device, dtype=torch.uint8)
-    call("hulc2_dropout_mask", out.data_ptr(), out.numel(), p, seed, offset)
+    call("hulc2_dropout_mask_ep", out.data_ptr(), out.numel(), p, seed, offset, _p(epoch))
     return out
 
 

@@ -22,6 +22,8 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self._arenas: List[Dict] = []
         self.grad_scale = 1.0  # multiplied into gradients inside the kernel (e.g. 1/world_size)
+        self.capturable = False  # True: the step number is read from a device counter (CUDA-graph replays)
+        self._step_dev = None
         for group in self.param_groups:
             self._arenas.append(self._build_arena(group))
 
@@ -90,12 +92,32 @@ class FusedAdam(torch.optim.Optimizer):
             if not a["n"]:
                 continue
             self._attach_grads(a)
+            ctr = self.step_counter(a["p"].device) if self.capturable else None
             a["step"] += 1
             b1, b2 = group["betas"]
-            call("hulc2_adam_step", a["p"].data_ptr(), a["g"].data_ptr(), a["m"].data_ptr(), a["v"].data_ptr(), a["n"],
-                 float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(a["step"]),
-                 float(self.grad_scale))
+            if self.capturable:
+                # step = (device counter of completed steps) + 1; the trainer bumps the counter after every step
+                call("hulc2_adam_step_dev", a["p"].data_ptr(), a["g"].data_ptr(), a["m"].data_ptr(), a["v"].data_ptr(), a["n"],
+                     float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                     ctr.data_ptr(), 1, float(self.grad_scale))
+            else:
+                call("hulc2_adam_step", a["p"].data_ptr(), a["g"].data_ptr(), a["m"].data_ptr(), a["v"].data_ptr(), a["n"],
+                     float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(a["step"]),
+                     float(self.grad_scale))
         return loss
+
+    def step_counter(self, device) -> torch.Tensor:
+        """int64[1] device counter of completed optimizer steps (used when ``capturable``)."""
+        if self._step_dev is None:
+            done = max((a["step"] for a in self._arenas if a["n"]), default=0)
+            self._step_dev = torch.full((1,), int(done), dtype=torch.int64, device=device)
+        return self._step_dev
+
+    def note_replayed_step(self) -> None:
+        """A captured step was replayed: keep the host-side step numbers (state_dict) in sync with the device counter."""
+        for a in self._arenas:
+            if a["n"]:
+                a["step"] += 1
 
     # ------------------------------------------------------------------ checkpointing (torch.optim.Adam-compatible layout)
     def state_dict(self):

@@ -231,6 +231,18 @@ int hulc2_philox_uniform(float* out, long long n, unsigned long long seed, unsig
 int hulc2_dropout_mask(unsigned char* out, long long n, float p, unsigned long long seed, unsigned long long offset,
                        hulc2_stream_t stream);
 
+/* CUDA-graph friendly variants: a whole train step (forward, backward, all-reduce, Adam) is captured once and replayed,
+ * so per-step scalars live in device counters.  epoch: noise counter offset += *epoch << 40 (null = 0);
+ * step_counter: Adam bias corrections use step = *step_counter + step_bias.  counter_add: *counter += inc. */
+int hulc2_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, const unsigned long long* step_counter, int step_bias,
+                        float grad_scale, hulc2_stream_t stream);
+int hulc2_philox_uniform_ep(float* out, long long n, unsigned long long seed, unsigned long long offset,
+                            const unsigned long long* epoch, hulc2_stream_t stream);
+int hulc2_dropout_mask_ep(unsigned char* out, long long n, float p, unsigned long long seed, unsigned long long offset,
+                          const unsigned long long* epoch, hulc2_stream_t stream);
+int hulc2_counter_add(unsigned long long* counter, unsigned long long inc, hulc2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
