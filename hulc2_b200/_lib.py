@@ -100,6 +100,8 @@ _SIGS = {
     "hulc2_categorical_sample": [P, P, P, I, I, I],
     "hulc2_logistic_loss_fwd": [P, LL, P, P, P, P, I, I, I, I, I, F, F, I, P, LL],
     "hulc2_logistic_loss_bwd": [P, LL, P, P, P, P, P, I, I, I, I, I, F, F, I],
+    "hulc2_logistic_loss_seg_fwd": [P, LL, P, P, P, P, I, I, I, I, I, F, F, I, I, P, LL],
+    "hulc2_logistic_loss_seg_bwd": [P, LL, P, P, P, P, P, I, I, I, I, I, F, F, I, I],
     "hulc2_logistic_sample": [P, LL, P, P, P, P, I, I, I, I, F, I],
     "hulc2_heads_unpack": [P, LL, P, P, P, P, I, I, I, I, F, I],
     "hulc2_world_to_tcp": [P, P, I, P, LL],

@@ -13,7 +13,11 @@ struct HeadGeom {
   int B, S, A, M;
   long long ld;
   int time_major;
+  int Bt;   // batch size of the heads buffer the rows live in (>= B: a segment [b0, b0+B) of a wider time-major buffer)
 };
+__device__ __forceinline__ long long head_row(const HeadGeom& g, int b, int s) {
+  return g.time_major ? (long long)s * g.Bt + b : (long long)b * g.S + s;
+}
 __device__ __forceinline__ void row_to_bs(const HeadGeom& g, long long row, int& b, int& s) {
   if (g.time_major) { s = (int)(row / g.B); b = (int)(row - (long long)s * g.B); }
   else { b = (int)(row / g.S); s = (int)(row - (long long)b * g.S); }
@@ -70,7 +74,8 @@ __global__ void logistic_loss_kernel(const float* __restrict__ heads, HeadGeom g
     int a = (int)(i - row * g.A);
     int b, s;
     row_to_bs(g, row, b, s);
-    const float* h = heads + row * g.ld;
+    const long long hrow = head_row(g, b, s);
+    const float* h = heads + hrow * g.ld;
     const float* arow = actions + ((long long)b * g.S + s) * (g.A + 1);
     float act = arow[a];
     float lpv[MAXM], dmu[MAXM], dls[MAXM];
@@ -101,7 +106,7 @@ __global__ void logistic_loss_kernel(const float* __restrict__ heads, HeadGeom g
     if (MODE == 0) {
       sum_ll += -lse;
     } else {
-      float* d = dheads + row * g.ld;
+      float* d = dheads + hrow * g.ld;
 #pragma unroll
       for (int m = 0; m < MAXM; ++m) {
         if (m < g.M) {
@@ -122,7 +127,7 @@ __global__ void logistic_loss_kernel(const float* __restrict__ heads, HeadGeom g
       if (MODE == 0) {
         sum_ce += lz - (label == 0 ? g0 : g1);
       } else {
-        float* d = dheads + row * g.ld;
+        float* d = dheads + hrow * g.ld;
         float p0 = expf(g0 - lz), p1 = expf(g1 - lz);
         d[3 * AM] = gscale * gripper_alpha * (p0 - (label == 0 ? 1.f : 0.f));
         d[3 * AM + 1] = gscale * gripper_alpha * (p1 - (label == 1 ? 1.f : 0.f));
@@ -285,12 +290,13 @@ inline int grid_for(long long n, int block) {
 
 extern "C" {
 
-int hulc2_logistic_loss_fwd(const float* heads, long long ld, const float* actions, const float* act_min, const float* act_max,
-                            float* out, int B, int S, int A, int M, int num_classes, float log_scale_min, float gripper_alpha,
-                            int time_major, void* workspace, long long workspace_bytes, cudaStream_t st) {
+int hulc2_logistic_loss_seg_fwd(const float* heads, long long ld, const float* actions, const float* act_min, const float* act_max,
+                                float* out, int B, int S, int A, int M, int num_classes, float log_scale_min, float gripper_alpha,
+                                int time_major, int B_total, void* workspace, long long workspace_bytes, cudaStream_t st) {
   if (M > MAXM || M <= 0) { hulc2_set_error("logistic_loss: n_mixtures must be in [1,16]"); return HULC2_EINVAL; }
+  if (B_total < B) { hulc2_set_error("logistic_loss: B_total < B"); return HULC2_EINVAL; }
   if ((long long)B * S <= 0) return HULC2_OK;
-  HeadGeom g{B, S, A, M, ld, time_major};
+  HeadGeom g{B, S, A, M, ld, time_major, B_total};
   int blocks = grid_for((long long)B * S * A, 128);
   if (!workspace || workspace_bytes < (long long)blocks * 2 * (long long)sizeof(float)) { hulc2_set_error("logistic_loss: workspace too small"); return HULC2_EWORKSPACE; }
   float lhc = (float)log((double)(num_classes - 1) / 2.0);
@@ -302,12 +308,20 @@ int hulc2_logistic_loss_fwd(const float* heads, long long ld, const float* actio
   return HULC2_OK;
 }
 
-int hulc2_logistic_loss_bwd(const float* heads, long long ld, const float* actions, const float* act_min, const float* act_max,
-                            const float* gout, float* dheads, int B, int S, int A, int M, int num_classes, float log_scale_min,
-                            float gripper_alpha, int time_major, cudaStream_t st) {
+int hulc2_logistic_loss_fwd(const float* heads, long long ld, const float* actions, const float* act_min, const float* act_max,
+                            float* out, int B, int S, int A, int M, int num_classes, float log_scale_min, float gripper_alpha,
+                            int time_major, void* workspace, long long workspace_bytes, cudaStream_t st) {
+  return hulc2_logistic_loss_seg_fwd(heads, ld, actions, act_min, act_max, out, B, S, A, M, num_classes, log_scale_min, gripper_alpha,
+                                     time_major, B, workspace, workspace_bytes, st);
+}
+
+int hulc2_logistic_loss_seg_bwd(const float* heads, long long ld, const float* actions, const float* act_min, const float* act_max,
+                                const float* gout, float* dheads, int B, int S, int A, int M, int num_classes, float log_scale_min,
+                                float gripper_alpha, int time_major, int B_total, cudaStream_t st) {
   if (M > MAXM || M <= 0) { hulc2_set_error("logistic_loss: n_mixtures must be in [1,16]"); return HULC2_EINVAL; }
+  if (B_total < B) { hulc2_set_error("logistic_loss: B_total < B"); return HULC2_EINVAL; }
   if ((long long)B * S <= 0) return HULC2_OK;
-  HeadGeom g{B, S, A, M, ld, time_major};
+  HeadGeom g{B, S, A, M, ld, time_major, B_total};
   int blocks = grid_for((long long)B * S * A, 128);
   float lhc = (float)log((double)(num_classes - 1) / 2.0);
   logistic_loss_kernel<1><<<blocks, 128, 0, st>>>(heads, g, actions, act_min, act_max, num_classes, log_scale_min, gripper_alpha, lhc,
@@ -316,10 +330,17 @@ int hulc2_logistic_loss_bwd(const float* heads, long long ld, const float* actio
   return HULC2_OK;
 }
 
+int hulc2_logistic_loss_bwd(const float* heads, long long ld, const float* actions, const float* act_min, const float* act_max,
+                            const float* gout, float* dheads, int B, int S, int A, int M, int num_classes, float log_scale_min,
+                            float gripper_alpha, int time_major, cudaStream_t st) {
+  return hulc2_logistic_loss_seg_bwd(heads, ld, actions, act_min, act_max, gout, dheads, B, S, A, M, num_classes, log_scale_min,
+                                     gripper_alpha, time_major, B, st);
+}
+
 int hulc2_logistic_sample(const float* heads, long long ld, const float* u1, const float* u2, const float* gripper_bounds,
                           float* act, int B, int S, int A, int M, float log_scale_min, int time_major, cudaStream_t st) {
   if ((long long)B * S <= 0) return HULC2_OK;
-  HeadGeom g{B, S, A, M, ld, time_major};
+  HeadGeom g{B, S, A, M, ld, time_major, B};
   logistic_sample_kernel<<<grid_for((long long)B * S * A, 128), 128, 0, st>>>(heads, g, u1, u2, gripper_bounds, act, log_scale_min);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
@@ -328,7 +349,7 @@ int hulc2_logistic_sample(const float* heads, long long ld, const float* u1, con
 int hulc2_heads_unpack(const float* heads, long long ld, float* logit_probs, float* log_scales, float* means, float* gripper,
                        int B, int S, int A, int M, float log_scale_min, int time_major, cudaStream_t st) {
   if ((long long)B * S <= 0) return HULC2_OK;
-  HeadGeom g{B, S, A, M, ld, time_major};
+  HeadGeom g{B, S, A, M, ld, time_major, B};
   heads_unpack_kernel<<<grid_for((long long)B * S * (A * M + 2), 256), 256, 0, st>>>(heads, g, logit_probs, log_scales, means, gripper, log_scale_min);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;

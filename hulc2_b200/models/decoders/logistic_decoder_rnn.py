@@ -7,7 +7,7 @@ loss / sampling kernels read once; ``forward`` unpacks it into the reference's `
 """
 import logging
 from pathlib import Path
-from typing import List, Optional, Tuple, Union
+from typing import Sequence, List, Optional, Tuple, Union
 
 import torch
 import torch.nn as nn
@@ -129,6 +129,16 @@ class LogisticDecoderRNN(ActionDecoder):
         if self.gripper_control:
             actions = world_to_tcp_frame(actions, robot_obs)
         return self._fused_loss(Hs, actions)
+
+    def loss_modalities(self, latent_plan, perceptual_emb, latent_goal, actions: Sequence[torch.Tensor],
+                        robot_obs: Sequence[torch.Tensor]) -> torch.Tensor:
+        """``loss`` for windows of several modalities decoded by ONE recurrence call: ``latent_plan``, ``perceptual_emb``
+        and ``latent_goal`` hold all windows in modality order, ``actions[i]`` / ``robot_obs[i]`` are modality i's own
+        tensors.  Returns the vector of per-modality mean losses (each exactly what ``loss`` returns for that modality)."""
+        Hs, _ = self._run_rnn(latent_plan, perceptual_emb, latent_goal)
+        if self.gripper_control:
+            actions = [world_to_tcp_frame(a, r) for a, r in zip(actions, robot_obs)]
+        return self._fused_loss(Hs, tuple(actions))
 
     def _loss(self, logit_probs, log_scales, means, gripper_act, actions) -> torch.Tensor:
         return ops.LogisticLossFunction.apply(logit_probs, log_scales, means, gripper_act, actions,

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import noise, ops
 from .._compat import DictConfig, LightningModule, as_config, instantiate, rank_zero_info, rank_zero_only
 from ..utils.distributions import State
 from .decoders.action_decoder import ActionDecoder
@@ -183,7 +183,13 @@ class Hulc2(LightningModule):
 
     # ------------------------------------------------------------------ train / val steps
     def training_step(self, batch: Dict[str, Dict], batch_idx: int) -> torch.Tensor:  # type: ignore
-        """hulc2.py:336-442.  batch = {"vis": {...}, "lang": {...}} as documented there."""
+        """hulc2.py:336-442.  batch = {"vis": {...}, "lang": {...}} as documented there.
+
+        When the modalities carry the same cameras (every shipped config), their windows run through the network as ONE
+        batch (``_training_step_batched``): same per-modality losses, logged scalars and gradients as the reference's
+        modality loop below, half the kernel launches and M=128 instead of M=64 rows for every contraction."""
+        if self.batch_modalities and self._can_batch_modalities(batch):
+            return self._training_step_batched(batch)
         n_mod = len(batch)
         terms, weights = [], []
         kls, acts = [], []
@@ -215,6 +221,79 @@ class Hulc2(LightningModule):
             self.log(f"train/kl_loss_scaled_{self.modality_scope}", kl.detach(), on_step=False, on_epoch=True, batch_size=bs)
             self.log(f"train/action_loss_{self.modality_scope}", act_loss.detach(), on_step=False, on_epoch=True, batch_size=bs)
             self.log(f"train/total_loss_{self.modality_scope}", mod_loss.detach(), on_step=False, on_epoch=True, batch_size=bs)
+        if self.use_clip_auxiliary_loss and clip is not None:
+            terms.append(clip)
+            weights.append(float(self.clip_auxiliary_loss_beta))
+        total_loss = ops.weighted_sum(weights, terms)
+        with torch.no_grad():
+            if self.use_clip_auxiliary_loss and clip is not None:
+                self.log("train/lang_clip_loss", ops.weighted_sum((float(self.clip_auxiliary_loss_beta),), (clip.detach(),)),
+                         on_step=False, on_epoch=True, batch_size=batch_size.get("aux_lang", 1), sync_dist=True)
+            w = (1.0 / n_mod,) * n_mod
+            self.log("train/kl_loss", ops.weighted_sum(w, [k.detach() for k in kls]), on_step=False, on_epoch=True, batch_size=total_bs)
+            self.log("train/action_loss", ops.weighted_sum(w, [a.detach() for a in acts]), on_step=False, on_epoch=True, batch_size=total_bs)
+        self.log("train/total_loss", total_loss.detach(), on_step=False, on_epoch=True, batch_size=total_bs)
+        return total_loss
+
+    # ------------------------------------------------------------------ all modalities in one pass
+    batch_modalities = True
+
+    def _can_batch_modalities(self, batch) -> bool:
+        if len(batch) < 2 or self.dist.dist != "discrete" or not hasattr(self.action_decoder, "loss_modalities"):
+            return False
+        mods = list(batch.values())
+
+        def cams(d):
+            return sorted((k, tuple(v.shape[1:])) for k, v in (d or {}).items() if v is not None)
+
+        return all(cams(m["rgb_obs"]) == cams(mods[0]["rgb_obs"]) and cams(m["depth_obs"]) == cams(mods[0]["depth_obs"])
+                   for m in mods[1:])
+
+    def _training_step_batched(self, batch: Dict[str, Dict]) -> torch.Tensor:
+        """Same arithmetic as the loop in ``training_step`` (hulc2.py:336-442 with lmp_train :200-245 inlined): windows
+        are independent, so encoders, plan networks and the decoder see the concatenated batch; every loss is still a
+        mean over its own modality's windows (segment reductions), and the InfoNCE term only sees the language rows."""
+        names = list(batch.keys())
+        mods = [batch[n] for n in names]
+        n_mod = len(mods)
+        sizes = [m["actions"].shape[0] for m in mods]
+        offs = [sum(sizes[:i]) for i in range(n_mod)]
+        noise.fuse_supplied(n_mod)
+        emb = self.perceptual_encoder.forward_modalities([m["rgb_obs"] for m in mods], [m["depth_obs"] for m in mods], None)
+        goals = []
+        for name, m, o, n in zip(names, mods, offs, sizes):
+            self.modality_scope = name
+            goals.append(self.language_goal(m["lang"]) if "lang" in name else self.visual_goal(emb[o : o + n, -1]))
+        latent_goal = ops.concat_rows(goals)
+        pp_state = self.plan_proposal(emb[:, 0], latent_goal)
+        pr_state, seq_feat = self.plan_recognition(emb)
+        sampled_plan = torch.flatten(self.dist.get_dist(pr_state).rsample(), start_dim=-2, end_dim=-1)
+        act_losses = self.action_decoder.loss_modalities(
+            sampled_plan, emb, latent_goal, [m["actions"] for m in mods], [m["state_info"]["robot_obs"] for m in mods])
+        kl_losses = ops.KLFunction.apply(pp_state.logit, pr_state.logit, self.dist.category_size, self.dist.class_size,
+                                         float(self.kl_balancing_mix), float(self.kl_beta), tuple(sizes))
+        clip = None
+        batch_size: Dict[str, Any] = {}
+        terms, weights, kls, acts = [], [], [], []
+        for i, (name, m, o, n) in enumerate(zip(names, mods, offs, sizes)):
+            self.modality_scope = name
+            kl, act_loss = kl_losses[i], act_losses[i]
+            if "lang" in name:
+                use = m.get("use_for_aux_lang_loss")
+                batch_size["aux_lang"] = use.shape[0] if use is not None else 1
+                if self.use_clip_auxiliary_loss:
+                    c = self.clip_auxiliary_loss(seq_feat[o : o + n], goals[i], use)
+                    clip = c if clip is None else ops.weighted_sum((1.0, 1.0), (clip, c))
+            terms += [act_loss, kl]
+            weights += [1.0 / n_mod, 1.0 / n_mod]
+            kls.append(kl)
+            acts.append(act_loss)
+            batch_size[name] = n
+            self.log(f"train/kl_loss_scaled_{name}", kl.detach(), on_step=False, on_epoch=True, batch_size=n)
+            self.log(f"train/action_loss_{name}", act_loss.detach(), on_step=False, on_epoch=True, batch_size=n)
+            self.log(f"train/total_loss_{name}", ops.weighted_sum((1.0, 1.0), (act_loss.detach(), kl.detach())),
+                     on_step=False, on_epoch=True, batch_size=n)
+        total_bs = sum(sizes)
         if self.use_clip_auxiliary_loss and clip is not None:
             terms.append(clip)
             weights.append(float(self.clip_auxiliary_loss_beta))

@@ -4,7 +4,7 @@ Runs the per-camera encoders on ``[B*S, C, H, W]`` frames; each encoder's final 
 64 features straight into its column block of the ``[B, S, latent]`` embedding (no ``torch.cat``).
 Tactile / proprio / state-decoder branches of the reference are not on the scoped path.
 """
-from typing import Dict, Optional
+from typing import Dict, Optional, Sequence
 
 import torch
 import torch.nn as nn
@@ -101,18 +101,40 @@ class ConcatEncoders(nn.Module):
         return self._latent_size
 
     def forward(self, imgs: Dict[str, torch.Tensor], depth_imgs: Dict[str, torch.Tensor], state_obs: torch.Tensor) -> torch.Tensor:
-        rgb_static = imgs["rgb_static"]
-        b, s, c, h, w = rgb_static.shape
-        encs = [(self.rgb_static_encoder, rgb_static.reshape(-1, c, h, w))]
-        if depth_imgs and "depth_static" in depth_imgs and depth_imgs["depth_static"] is not None:
-            encs.append((self.depth_static_encoder, depth_imgs["depth_static"].reshape(-1, 1, h, w)))
-        if "rgb_gripper" in imgs and imgs["rgb_gripper"] is not None:
-            rg = imgs["rgb_gripper"]
-            _, _, cg, hg, wg = rg.shape
-            encs.append((self.rgb_gripper_encoder, rg.reshape(-1, cg, hg, wg)))
-            if depth_imgs and "depth_gripper" in depth_imgs and depth_imgs["depth_gripper"] is not None:
-                encs.append((self.depth_gripper_encoder, depth_imgs["depth_gripper"].reshape(-1, 1, hg, wg)))
-        feats = [enc.features(x) for enc, x in encs]
+        return self.forward_modalities([imgs], [depth_imgs], state_obs)
+
+    def forward_modalities(self, imgs: Sequence[Dict[str, torch.Tensor]], depth_imgs: Sequence[Dict[str, torch.Tensor]],
+                           state_obs=None) -> torch.Tensor:
+        """concat_encoders.py:59-109 for the windows of several modalities at once: every camera's frames go through
+        ONE trunk call (frame groups are packed back to back, never concatenated in fp32), returning the embeddings of
+        all windows ``[sum(B_i), S, latent]`` in modality order.  All modalities must carry the same cameras."""
+        def cam(dicts, key):
+            vals = [d.get(key) if d else None for d in dicts]
+            if all(v is None for v in vals):
+                return None
+            if any(v is None for v in vals):
+                raise ValueError(f"camera '{key}' is missing from some modalities; encode them separately")
+            return vals
+
+        rgb_static = cam(imgs, "rgb_static")
+        s, c, h, w = rgb_static[0].shape[1:]
+        b = sum(t.shape[0] for t in rgb_static)
+
+        def frames(ts, ch, hh, ww):
+            return tuple(t.reshape(-1, ch, hh, ww) for t in ts)
+
+        encs = [(self.rgb_static_encoder, frames(rgb_static, c, h, w))]
+        depth_static = cam(depth_imgs, "depth_static")
+        if depth_static is not None:
+            encs.append((self.depth_static_encoder, frames(depth_static, 1, h, w)))
+        rgb_gripper = cam(imgs, "rgb_gripper")
+        if rgb_gripper is not None:
+            cg, hg, wg = rgb_gripper[0].shape[2:]
+            encs.append((self.rgb_gripper_encoder, frames(rgb_gripper, cg, hg, wg)))
+            depth_gripper = cam(depth_imgs, "depth_gripper")
+            if depth_gripper is not None:
+                encs.append((self.depth_gripper_encoder, frames(depth_gripper, 1, hg, wg)))
+        feats = [enc.features(x if len(x) > 1 else x[0]) for enc, x in encs]
         gammas = [enc.ln.weight for enc, _ in encs]
         betas = [enc.ln.bias for enc, _ in encs]
         out = _ConcatLayerNorm.apply(float(encs[0][0].ln.eps), *feats, *gammas, *betas)

@@ -64,6 +64,21 @@ def supplied(categories=(), uniforms=(), masks=()):
             raise AssertionError(f"unused supplied noise: {left}")
 
 
+def fuse_supplied(n: int) -> None:
+    """A step that runs the windows of ``n`` modalities as one batch consumes one draw where the per-modality loop
+    consumed ``n``.  Supplied category/mask tensors are queued per modality (modality 0's draws, then modality 1's, ...):
+    regroup them into batch-concatenated tensors in draw order."""
+    for key in ("categories", "masks"):
+        q = _queues[key]
+        if not q:
+            continue
+        items = list(q)
+        assert len(items) % n == 0, f"supplied {key}: {len(items)} tensors cannot be split over {n} modalities"
+        per = len(items) // n
+        q.clear()
+        q.extend(torch.cat([items[m * per + i] for m in range(n)], 0) for i in range(per))
+
+
 def uniform(shape, device) -> torch.Tensor:
     if _queues["uniforms"]:
         t = _queues["uniforms"].popleft()

@@ -273,8 +273,9 @@ def _osz(h, k, s):
     return (h - k) // s + 1
 
 
-def convb_trunk_supported(x: torch.Tensor) -> bool:
+def convb_trunk_supported(x) -> bool:
     """The persistent tcgen05 trunk serves precision 'bf16' on the 3-conv stacks of the reference (k8s4 -> k4s2 -> k3s1)."""
+    x = x[0] if isinstance(x, (tuple, list)) else x
     if _precision != 1 or x.dim() != 4:
         return False
     lib = _lib.load_library()
@@ -335,17 +336,36 @@ def convb_wgrad(x, dy, F, C, H, W, Cout, k, stride, dw_shape, dw_layout=0, name=
     return dw, db
 
 
-def pack_frames(x: torch.Tensor) -> torch.Tensor:
-    """fp32 NCHW frames -> bf16 [F, H/4, W/4, 16*C] (space-to-depth by the first conv's stride)."""
-    F_, Cin, H, W = x.shape
-    xs = _bf16(F_, H // 4, W // 4, 16 * Cin, device=x.device)
-    _lib.tag(f"pack_frames[F={F_},{Cin}x{H}x{W}]", 0.0)
-    call("hulc2_pack_frames_bf16", x.data_ptr(), xs.data_ptr(), F_, Cin, H, W)
+def _frame_groups(x):
+    """A frame operand is one NCHW tensor or a tuple of them (the same camera of several modalities, encoded by one
+    trunk call).  -> (list of contiguous fp32 [F_i,C,H,W] tensors, (F_total, C, H, W))."""
+    groups = [_f32(t).contiguous() for t in (x if isinstance(x, (tuple, list)) else (x,))]
+    shp = groups[0].shape[1:]
+    assert all(t.dim() == 4 and t.shape[1:] == shp for t in groups), "frame groups must share C,H,W"
+    return groups, (sum(t.shape[0] for t in groups), *shp)
+
+
+def _frames_tensor(x) -> torch.Tensor:
+    groups, _ = _frame_groups(x)
+    return groups[0] if len(groups) == 1 else torch.cat(groups, 0)   # fp32 reference-precision path only
+
+
+def pack_frames(x) -> torch.Tensor:
+    """fp32 NCHW frames (one tensor or a tuple of frame groups) -> bf16 [F, H/4, W/4, 16*C] (space-to-depth by the
+    first conv's stride); groups are packed back to back, so no concatenated fp32 copy is ever made."""
+    groups, (F_, Cin, H, W) = _frame_groups(x)
+    xs = _bf16(F_, H // 4, W // 4, 16 * Cin, device=groups[0].device)
+    per_frame = (H // 4) * (W // 4) * 16 * Cin
+    f0 = 0
+    for t in groups:
+        _lib.tag(f"pack_frames[F={t.shape[0]},{Cin}x{H}x{W}]", 0.0)
+        call("hulc2_pack_frames_bf16", t.data_ptr(), xs.data_ptr() + 2 * f0 * per_frame, t.shape[0], Cin, H, W)
+        f0 += t.shape[0]
     return xs
 
 
 def _convb_trunk_fwd(x, w1, b1, w2, b2, w3, b3):
-    F_, Cin, H, W = x.shape
+    _, (F_, Cin, H, W) = _frame_groups(x)
     xs = pack_frames(x)
     H4, W4 = H // 4, W // 4
     H1, W1 = H4 - 1, W4 - 1
@@ -373,10 +393,11 @@ class StaticConvSSM(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, w3, b3, x_map, y_map, temperature):
-        x = _f32(x).contiguous()
-        F_ = x.shape[0]
-        out = torch.empty(F_, 128, device=x.device, dtype=torch.float32)
+        _, (F_, _c, _h, _w) = _frame_groups(x)
+        out = torch.empty(F_, 128, device=w1.device, dtype=torch.float32)
         ctx.bf16 = convb_trunk_supported(x)
+        if not ctx.bf16:
+            x = _frames_tensor(x)
         if ctx.bf16:
             xs, y1, y2, y3 = _convb_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
             HW = y3.shape[1] * y3.shape[2]
@@ -424,13 +445,14 @@ class GripperConvFlatten(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, w3, b3):
-        x = _f32(x).contiguous()
-        F_ = x.shape[0]
+        _, (F_, _c, _h, _w) = _frame_groups(x)
         ctx.bf16 = convb_trunk_supported(x)
+        if not ctx.bf16:
+            x = _frames_tensor(x)
         if ctx.bf16:
             xs, y1, y2, y3 = _convb_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
             HW = y3.shape[1] * y3.shape[2]
-            flat = torch.empty(F_, 64 * HW, device=x.device, dtype=torch.float32)
+            flat = torch.empty(F_, 64 * HW, device=w1.device, dtype=torch.float32)
             call("hulc2_nhwc_bf16_to_nchw", y3.data_ptr(), flat.data_ptr(), F_, HW, 64)
             ctx.save_for_backward(xs, y1, y2, y3, w1, w2, w3)
             return flat
@@ -566,26 +588,38 @@ class MeanSeqFunction(torch.autograd.Function):
 
 # ----------------------------------------------------------------------------- latent plan
 class KLFunction(torch.autograd.Function):
-    """hulc2.py:444-466 for the discrete plan: balanced categorical KL, scaled by kl_beta."""
+    """hulc2.py:444-466 for the discrete plan: balanced categorical KL, scaled by kl_beta -> scalar.
+    With ``segments`` (row counts per modality, summing to B) the result is the vector of per-modality batch means."""
 
     @staticmethod
-    def forward(ctx, pp, pr, cats, classes, alpha, beta):
+    def forward(ctx, pp, pr, cats, classes, alpha, beta, segments=None):
         pp, pr = _f32(pp).contiguous(), _f32(pr).contiguous()
         B = pp.shape[0]
-        loss = torch.empty(1, device=pp.device, dtype=torch.float32)
-        call("hulc2_kl_fwd", pp.data_ptr(), pr.data_ptr(), loss.data_ptr(), B, cats, classes, alpha, beta)
+        segs = tuple(int(n) for n in segments) if segments is not None else (B,)
+        assert sum(segs) == B
+        loss = torch.empty(len(segs), device=pp.device, dtype=torch.float32)
+        row = pp.shape[1] * 4
+        b0 = 0
+        for i, n in enumerate(segs):
+            call("hulc2_kl_fwd", pp.data_ptr() + b0 * row, pr.data_ptr() + b0 * row, loss.data_ptr() + 4 * i, n, cats, classes, alpha, beta)
+            b0 += n
         ctx.save_for_backward(pp, pr)
-        ctx.cfg = (B, cats, classes, alpha, beta)
-        return loss.view(())
+        ctx.cfg = (segs, cats, classes, alpha, beta)
+        return loss if segments is not None else loss.view(())
 
     @staticmethod
     def backward(ctx, g):
         pp, pr = ctx.saved_tensors
-        B, cats, classes, alpha, beta = ctx.cfg
-        g = g.contiguous()
+        segs, cats, classes, alpha, beta = ctx.cfg
+        g = g.contiguous().view(-1)
         dpp, dpr = torch.empty_like(pp), torch.empty_like(pr)
-        call("hulc2_kl_bwd", pp.data_ptr(), pr.data_ptr(), g.data_ptr(), dpp.data_ptr(), dpr.data_ptr(), B, cats, classes, alpha, beta)
-        return dpp, dpr, None, None, None, None
+        row = pp.shape[1] * 4
+        b0 = 0
+        for i, n in enumerate(segs):
+            call("hulc2_kl_bwd", pp.data_ptr() + b0 * row, pr.data_ptr() + b0 * row, g.data_ptr() + 4 * i, dpp.data_ptr() + b0 * row,
+                 dpr.data_ptr() + b0 * row, n, cats, classes, alpha, beta)
+            b0 += n
+        return dpp, dpr, None, None, None, None, None
 
 
 class PlanRSampleFunction(torch.autograd.Function):
@@ -768,7 +802,9 @@ def heads_forward(Hs, wp, bp, wm, bm, wsc, bsc, wg, bg) -> torch.Tensor:
 
 class DecoderLossFunction(torch.autograd.Function):
     """heads + discretised logistic-mixture NLL + gripper cross-entropy (logistic_decoder_rnn.py:133-152,181-228).
-    Hs is time-major [S,B,H]; actions [B,S,A+1] (already in the tcp frame)."""
+    Hs is time-major [S,B,H]; actions [B,S,A+1] (already in the tcp frame) -> scalar loss.
+    ``actions`` may also be a tuple of per-modality tensors [B_i,S,A+1] with sum(B_i) = B (windows of several
+    modalities decoded by one recurrence call): the result is then the vector of per-modality mean losses [n]."""
 
     @staticmethod
     def forward(ctx, Hs, actions, amin, amax, cfg, wp, bp, wm, bm, wsc, bsc, wg, bg):
@@ -776,27 +812,36 @@ class DecoderLossFunction(torch.autograd.Function):
         S, B, H = Hs.shape
         A, M, num_classes, ls_min, alpha = cfg
         heads = heads_forward(Hs, wp, bp, wm, bm, wsc, bsc, wg, bg)
-        out = torch.empty(3, device=Hs.device, dtype=torch.float32)
         ws = workspace(Hs.device)
-        actions = _f32(actions).contiguous()
-        call("hulc2_logistic_loss_fwd", heads.data_ptr(), HEAD_LD, actions.data_ptr(), amin.data_ptr(), amax.data_ptr(),
-             out.data_ptr(), B, S, A, M, num_classes, ls_min, alpha, 1, ws.data_ptr(), ws.numel())
-        ctx.save_for_backward(Hs, heads, actions, amin, amax, wp, wm, wsc, wg)
+        segmented = isinstance(actions, (tuple, list))
+        segs = [_f32(a).contiguous() for a in (actions if segmented else (actions,))]
+        assert sum(a.shape[0] for a in segs) == B, "per-modality actions must cover the decoded batch"
+        out = torch.empty(len(segs), 3, device=Hs.device, dtype=torch.float32)
+        b0 = 0
+        for i, a in enumerate(segs):
+            call("hulc2_logistic_loss_seg_fwd", heads.data_ptr() + 4 * b0 * HEAD_LD, HEAD_LD, a.data_ptr(), amin.data_ptr(),
+                 amax.data_ptr(), out.data_ptr() + 12 * i, a.shape[0], S, A, M, num_classes, ls_min, alpha, 1, B, ws.data_ptr(), ws.numel())
+            b0 += a.shape[0]
+        ctx.save_for_backward(Hs, heads, amin, amax, wp, wm, wsc, wg, *segs)
         ctx.cfg = cfg
-        return out[0]
+        return out[:, 0] if segmented else out[0, 0]
 
     @staticmethod
     def backward(ctx, g):
-        Hs, heads, actions, amin, amax, wp, wm, wsc, wg = ctx.saved_tensors
+        Hs, heads, amin, amax, wp, wm, wsc, wg, *segs = ctx.saved_tensors
         S, B, H = Hs.shape
         A, M, num_classes, ls_min, alpha = ctx.cfg
         AM = A * M
         rows = S * B
         dev = Hs.device
-        g = g.contiguous()
+        g = g.contiguous().view(-1)
         dheads = torch.empty_like(heads)
-        call("hulc2_logistic_loss_bwd", heads.data_ptr(), HEAD_LD, actions.data_ptr(), amin.data_ptr(), amax.data_ptr(),
-             g.data_ptr(), dheads.data_ptr(), B, S, A, M, num_classes, ls_min, alpha, 1)
+        b0 = 0
+        for i, a in enumerate(segs):
+            call("hulc2_logistic_loss_seg_bwd", heads.data_ptr() + 4 * b0 * HEAD_LD, HEAD_LD, a.data_ptr(), amin.data_ptr(),
+                 amax.data_ptr(), g.data_ptr() + 4 * i, dheads.data_ptr() + 4 * b0 * HEAD_LD, a.shape[0], S, A, M, num_classes,
+                 ls_min, alpha, 1, B)
+            b0 += a.shape[0]
         dbias = torch.empty(3 * AM + 2, device=dev, dtype=torch.float32)
         colsum(dheads, HEAD_LD, rows, 3 * AM + 2, dbias)
         dH = torch.empty(S, B, H, device=dev, dtype=torch.float32)
@@ -971,3 +1016,32 @@ class ConcatColsFunction(torch.autograd.Function):
 
 def concat_cols(a, b):
     return ConcatColsFunction.apply(a, b)
+
+
+class ConcatRowsFunction(torch.autograd.Function):
+    """Stacks 2-D row blocks [B_i, D] into [sum B_i, D] (latent goals of several modalities -> one decoder batch)."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        xs2 = [_rows2d(_f32(x)) for x in xs]
+        D = xs2[0].shape[1]
+        out = torch.empty(sum(x.shape[0] for x in xs2), D, device=xs2[0].device, dtype=torch.float32)
+        r0 = 0
+        for x in xs2:
+            call("hulc2_copy2d", x.data_ptr(), _ld(x), out.data_ptr() + 4 * r0 * D, D, x.shape[0], D, 0)
+            r0 += x.shape[0]
+        ctx.rows = [x.shape[0] for x in xs2]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        outs, r0 = [], 0
+        for n in ctx.rows:
+            outs.append(dout[r0 : r0 + n])
+            r0 += n
+        return tuple(outs)
+
+
+def concat_rows(xs):
+    return xs[0] if len(xs) == 1 else ConcatRowsFunction.apply(*xs)

@@ -12,7 +12,7 @@ is copied into them (device->device or pinned host->device) before the replay.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict, Iterable, List, Optional
 
 import torch
 import torch.distributed as dist
@@ -135,3 +135,67 @@ class PolicyTrainer:
             batch = tree_map(lambda t: t.to(self.device, non_blocking=True), host_batch)
             loss = self.train_step(batch, batch_idx)
         return float(loss)  # device->host read of the step's result
+
+    # ------------------------------------------------------------------ pipelined host loop (what Trainer.fit does)
+    def fit_host(self, host_batches: Iterable[Dict[str, dict]]) -> List[float]:
+        """Trains on an iterable of PINNED host batches and returns every step's loss (read back to the host).
+
+        Software pipeline over three streams: the H2D copy of batch i+1 (copy stream, into one of two device staging
+        buffers) runs while the trainer stream computes step i; the loss of step i is copied to a pinned slot right
+        behind the step and read by the host one step later, so neither PCIe nor the host read stalls the kernels.
+        Every step still moves its own inputs host->device and its own result device->host."""
+        if self.stream is None:
+            return [self.train_step_from_host(b, i) for i, b in enumerate(host_batches)]
+        dev = self.device
+        copy = self._copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(device=dev)
+        it = iter(host_batches)
+        first = next(it, None)
+        if first is None:
+            return []
+        if getattr(self, "_staging", None) is None or not _same_shapes(self._staging[0], first):
+            self._staging = [tree_map(lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev), first) for _ in range(2)]
+            self._pipe_static = tree_map(lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev), first)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+        loss_slots = torch.empty(2, dtype=torch.float32).pin_memory()
+        loss_done = [torch.cuda.Event() for _ in range(2)]
+        losses: List[float] = []
+
+        def upload(i, hb):
+            with torch.cuda.stream(copy):
+                if i >= 2:
+                    copy.wait_event(free[i % 2])          # the step that consumed this staging buffer has read it
+                _zip_copy(self._staging[i % 2], hb)
+                ready[i % 2].record(copy)
+
+        upload(0, first)
+        i, cur = 0, first
+        while cur is not None:
+            nxt = next(it, None)
+            if nxt is not None:
+                upload(i + 1, nxt)                        # overlaps with step i below
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ready[i % 2])
+                # the tensors the step reads: the captured graph's static inputs once a graph exists
+                target = self.static_batch if self._graph is not None else self._pipe_static
+                _zip_copy(target, self._staging[i % 2])
+                free[i % 2].record(self.stream)
+                loss = self._train_step_on_stream(target, i)
+                loss_slots[i % 2 : i % 2 + 1].copy_(loss.reshape(1), non_blocking=True)
+                loss_done[i % 2].record(self.stream)
+            if i >= 1:
+                loss_done[(i - 1) % 2].synchronize()
+                losses.append(float(loss_slots[(i - 1) % 2]))
+            i, cur = i + 1, nxt
+        loss_done[(i - 1) % 2].synchronize()
+        losses.append(float(loss_slots[(i - 1) % 2]))
+        torch.cuda.current_stream(dev).wait_stream(self.stream)
+        return losses
+
+
+def _same_shapes(a, b) -> bool:
+    if isinstance(a, dict):
+        return isinstance(b, dict) and a.keys() == b.keys() and all(_same_shapes(a[k], b[k]) for k in a)
+    if isinstance(a, torch.Tensor):
+        return isinstance(b, torch.Tensor) and a.shape == b.shape and a.dtype == b.dtype
+    return True

@@ -188,6 +188,18 @@ int hulc2_logistic_loss_bwd(const float* heads, long long ld, const float* actio
                             const float* act_max, const float* gout, float* dheads, int B, int S, int A, int M,
                             int num_classes, float log_scale_min, float gripper_alpha, int time_major,
                             hulc2_stream_t stream);
+/* Segment variants: the B windows are columns [b0, b0+B) of a wider buffer holding B_total windows (several modalities
+ * decoded in one recurrence call); `heads`/`dheads` point at the segment's first row (time-major: + b0*ld, batch-major:
+ * + b0*S*ld), `actions` is the segment's own [B,S,A+1]; the mean is over the segment's B*S rows (hulc2.py:386-400 keeps
+ * one action loss per modality). */
+int hulc2_logistic_loss_seg_fwd(const float* heads, long long ld, const float* actions, const float* act_min,
+                                const float* act_max, float* out, int B, int S, int A, int M, int num_classes,
+                                float log_scale_min, float gripper_alpha, int time_major, int B_total, void* workspace,
+                                long long workspace_bytes, hulc2_stream_t stream);
+int hulc2_logistic_loss_seg_bwd(const float* heads, long long ld, const float* actions, const float* act_min,
+                                const float* act_max, const float* gout, float* dheads, int B, int S, int A, int M,
+                                int num_classes, float log_scale_min, float gripper_alpha, int time_major, int B_total,
+                                hulc2_stream_t stream);
 int hulc2_logistic_sample(const float* heads, long long ld, const float* u1, const float* u2,
                           const float* gripper_bounds, float* act, int B, int S, int A, int M, float log_scale_min,
                           int time_major, hulc2_stream_t stream);
