@@ -36,6 +36,7 @@ class GemmArgs(C.Structure):
         ("alpha", F),
         ("precision", I),
         ("workspace", P), ("workspace_bytes", LL),
+        ("A16", P), ("B16", P), ("C16", P), ("ld16", LL),
     ]
 
 
@@ -62,6 +63,7 @@ class ConvbArgs(C.Structure):
 # name -> argtypes (without the trailing stream); every function returns int and takes a stream last
 _SIGS = {
     "hulc2_gemm": [C.POINTER(GemmArgs)],
+    "hulc2_f32_to_bf16": [P, P, LL],
     "hulc2_conv2d_fwd": [C.POINTER(ConvArgs)],
     "hulc2_conv2d_wgrad": [C.POINTER(ConvArgs)],
     "hulc2_conv2d_dgrad": [C.POINTER(ConvArgs)],
@@ -119,7 +121,7 @@ _SIGS = {
     "hulc2_counter_add": [P, C.c_ulonglong],
 }
 _NO_STREAM = {"hulc2_last_error": (C.c_char_p, []), "hulc2_version": (I, []), "hulc2_device_supports_tcgen05": (I, []),
-              "hulc2_launch_count": (C.c_ulonglong, []), "hulc2_convb_supported": (I, [I, I, I, I, I])}
+              "hulc2_launch_count": (C.c_ulonglong, []), "hulc2_tma_gemm_count": (C.c_ulonglong, []), "hulc2_convb_supported": (I, [I, I, I, I, I])}
 
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + list(_NO_STREAM))
 

@@ -201,6 +201,26 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// flat fp32 -> bf16 mirror (GEMM operand copies); 8 elements per thread when both pointers are 16-byte aligned
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n, int vec) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+    const long long n8 = n >> 3;
+    for (long long i = tid; i < n8; i += nthreads) {
+      float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+      uint4 o;
+      o.x = *reinterpret_cast<unsigned*>(&h0); o.y = *reinterpret_cast<unsigned*>(&h1);
+      o.z = *reinterpret_cast<unsigned*>(&h2); o.w = *reinterpret_cast<unsigned*>(&h3);
+      reinterpret_cast<uint4*>(dst)[i] = o;
+    }
+    for (long long i = (n8 << 3) + tid; i < n; i += nthreads) dst[i] = __float2bfloat16_rn(src[i]);
+  } else {
+    for (long long i = tid; i < n; i += nthreads) dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -209,6 +229,16 @@ int hulc2_copy2d(const float* src, long long lds, float* dst, long long ldd, lon
                  cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return HULC2_OK;
   copy2d_kernel<<<grid_for(rows * cols, 256), 256, 0, st>>>(src, lds, dst, ldd, rows, cols, accumulate);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t st) {
+  if (n <= 0) return HULC2_OK;
+  const int vec = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+  long long blocks = ((vec ? (n >> 3) : n) + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  f32_to_bf16_kernel<<<(int)blocks, 256, 0, st>>>(src, (__nv_bfloat16*)dst, n, vec);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

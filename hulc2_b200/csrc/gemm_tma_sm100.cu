@@ -1,0 +1,336 @@
+// bf16 dense contractions for sm_100a, second generation: operands are bf16 in HBM (row-major mirrors of the fp32
+// master tensors, written once by their producer), moved by TMA (cp.async.bulk.tensor, SWIZZLE_128B boxes) into a
+// multi-stage shared-memory ring, multiplied by tcgen05.mma (UMMA 128 x BN x 16, fp32 accumulators in TMEM) and
+// drained by four epilogue warps with 16-byte loads/stores.
+//
+// Warp roles (192 threads):  warp 0 = TMA producer (one elected lane),  warp 1 = TMEM owner + MMA issuer (one lane),
+// warps 2-5 = epilogue (TMEM lane quarter = warp & 3).  full/empty mbarriers per stage; the MMA warp recycles a stage
+// with tcgen05.commit, so loads run STAGES k-tiles ahead of the tensor core and nothing in the main loop touches
+// registers.  One output tile per CTA; small-smem configurations co-reside 2 per SM so one CTA's epilogue overlaps the
+// other's main loop.  Skinny problems (weight-streaming M=B layers, weight gradients) are split along K over ~2 waves
+// of CTAs and reduced by splitk_reduce_kernel.
+//
+// The same row-major bf16 matrix serves as a K-major operand (contraction along its rows' fast axis: forward /
+// input-gradient A) or as an MN-major operand (contraction along its slow axis: W in the input gradient, both
+// operands of a weight gradient); the only difference is the TMA box orientation and the UMMA descriptor.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "gemm_common.cuh"
+#include "sm100.cuh"
+
+using namespace hulc2;
+using namespace sm100;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;          // bf16 elements per k-tile = one 128-byte swizzle row
+constexpr int NT = 192;
+constexpr int MAX_STAGES = 8;
+constexpr uint32_t A_BYTES = BM * 128;
+unsigned long long g_tma_gemms = 0;
+
+struct TmaParams {
+  int M, N, K;
+  int ktiles, kt_per_split, splits, stages;
+  Epilogue E;
+  float* partial;               // [splits, M, N] when splits > 1
+  __nv_bfloat16* C16;           // optional bf16 mirror of the output (same row addressing with ld16)
+  long long ld16;
+  int vec;                      // 16-byte epilogue accesses are legal for every pointer involved
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
+}
+
+// one output element through the shared epilogue (+ optional bf16 mirror)
+__device__ __forceinline__ void store_scalar(const TmaParams& p, float acc, int m, int n, long long crow) {
+  float v = apply_epilogue(p.E, acc, m, n, crow);
+  p.E.C[crow + n] = v;
+  if (p.C16) p.C16[(long long)m * p.ld16 + n] = __float2bfloat16_rn(v);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB, const TmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_slot;
+  constexpr uint32_t B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kt0 = blockIdx.z * p.kt_per_split;
+  const int nkt = min(p.ktiles, kt0 + p.kt_per_split) - kt0;
+  const int ST = p.stages;
+
+  if (tid == 0) {
+    for (int s = 0; s < ST; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    mbar_init(smem_u32(&acc_bar), 1);
+    mbar_fence_init();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkt; ++i) {
+        const int s = i % ST;
+        if (i >= ST) mbar_wait(smem_u32(&empty_bar[s]), (uint32_t)((i / ST - 1) & 1));
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        const uint32_t a_tile = tiles + s * STAGE_BYTES, b_tile = a_tile + A_BYTES;
+        const int k0 = (kt0 + i) * BK;
+        mbar_arrive_expect_tx(bar, STAGE_BYTES);
+        if (A_MN) {
+          tma_load_2d(a_tile, &tmA, bar, m0, k0);
+          tma_load_2d(a_tile + 8192, &tmA, bar, m0 + 64, k0);
+        } else {
+          tma_load_2d(a_tile, &tmA, bar, k0, m0);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_tile + j * 8192, &tmB, bar, n0 + 64 * j, k0);
+        } else {
+          tma_load_2d(b_tile, &tmB, bar, k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = make_idesc(BM, BN, A_MN, B_MN);
+      constexpr uint64_t A_STEP = (A_MN ? 2048u : 32u) >> 4, B_STEP = (B_MN ? 2048u : 32u) >> 4;
+      for (int i = 0; i < nkt; ++i) {
+        const int s = i % ST;
+        mbar_wait(smem_u32(&full_bar[s]), (uint32_t)((i / ST) & 1));
+        tc_fence_after();
+        const uint32_t a_tile = tiles + s * STAGE_BYTES, b_tile = a_tile + A_BYTES;
+        const uint64_t ad = make_desc(a_tile, A_MN ? 8192u : 0u), bd = make_desc(b_tile, B_MN ? 8192u : 0u);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, ad + A_STEP * k, bd + B_STEP * k, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit(smem_u32(&empty_bar[s]));     // stage free once these MMAs have read it
+      }
+      umma_commit(smem_u32(&acc_bar));            // accumulator complete
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    const bool mvalid = m < p.M;
+    const Epilogue& E = p.E;
+    const long long crow = mvalid ? c_row_off(E, m) : 0;
+    mbar_wait_relaxed(smem_u32(&acc_bar), 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      if (n0 + c >= p.N) break;                   // warp-uniform
+      uint32_t r[32];
+      tmem_ld16_nowait(trow + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+      tmem_ld16_nowait(trow + (uint32_t)(c + 16), *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+      tmem_ld_wait();
+      if (!mvalid) continue;
+      if (p.splits > 1) {
+        float* prow = p.partial + ((long long)blockIdx.z * p.M + m) * p.N;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + c + j;
+          if (n >= p.N) break;
+          if (p.vec && n + 4 <= p.N) {
+            *reinterpret_cast<float4*>(prow + n) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          } else {
+            for (int e = 0; e < 4; ++e) if (n + e < p.N) prow[n + e] = __uint_as_float(r[j + e]);
+          }
+        }
+        continue;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int n = n0 + c + j;
+        if (n >= p.N) break;
+        if (p.vec && n + 4 <= p.N) {
+          float v[4] = {E.alpha * __uint_as_float(r[j]), E.alpha * __uint_as_float(r[j + 1]), E.alpha * __uint_as_float(r[j + 2]), E.alpha * __uint_as_float(r[j + 3])};
+          if (E.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(E.bias + n)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+          if (E.add) { float4 t = *reinterpret_cast<const float4*>(E.add + (long long)m * E.ld_add + n); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+          if (E.accumulate) { float4 t = *reinterpret_cast<const float4*>(E.C + crow + n); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+          if (E.relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+          if (E.mask) {
+            float4 t = *reinterpret_cast<const float4*>(E.mask + (long long)m * E.ld_mask + n);
+            v[0] = t.x > 0.f ? v[0] : 0.f; v[1] = t.y > 0.f ? v[1] : 0.f; v[2] = t.z > 0.f ? v[2] : 0.f; v[3] = t.w > 0.f ? v[3] : 0.f;
+          }
+          if (E.keep) {
+            uchar4 t = *reinterpret_cast<const uchar4*>(E.keep + (long long)m * E.ld_keep + n);
+            v[0] = t.x ? v[0] * E.keep_scale : 0.f; v[1] = t.y ? v[1] * E.keep_scale : 0.f;
+            v[2] = t.z ? v[2] * E.keep_scale : 0.f; v[3] = t.w ? v[3] * E.keep_scale : 0.f;
+          }
+          *reinterpret_cast<float4*>(E.C + crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+          if (p.C16) {
+            uint2 h = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+            *reinterpret_cast<uint2*>(p.C16 + (long long)m * p.ld16 + n) = h;
+          }
+        } else {
+          for (int e = 0; e < 4; ++e) if (n + e < p.N) store_scalar(p, __uint_as_float(r[j + e]), m, n + e, crow);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, BN);
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+// cuTensorMapEncodeTiled comes from the driver at run time (cudaGetDriverEntryPoint), so the library still loads --
+// and exports every symbol -- on hosts without libcuda (build / CPU test containers).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+bool encode_map(CUtensorMap* tm, const void* base, long long inner, long long outer, long long ld_elems, int box_outer) {
+  EncodeTiledFn cuTensorMapEncodeTiled = encode_fn();
+  if (!cuTensorMapEncodeTiled) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TmaParams& p, int smem, cudaStream_t st) {
+  auto kern = gemm_tma_kernel<BN, A_MN, B_MN>;
+  static int configured = 0;  // per instantiation: largest dynamic smem opted in so far
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      hulc2_set_error("gemm_tma: cannot raise the dynamic shared memory limit");
+      return HULC2_ELAUNCH;
+    }
+    configured = smem;
+  }
+  dim3 grid(hulc2_cdiv(p.M, BM), hulc2_cdiv(p.N, BN), p.splits);
+  kern<<<grid, NT, smem, st>>>(ta, tb, p);
+  HULC2_CHECK_LAUNCH();
+  ++g_tma_gemms;
+  if (p.splits > 1) {
+    long long total = (long long)p.M * p.N;
+    splitk_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(p.partial, p.splits, p.M, p.N, p.E);
+    HULC2_CHECK_LAUNCH();
+    if (p.C16) { hulc2_set_error("gemm_tma: internal: bf16 mirror with split-K"); return HULC2_EINVAL; }
+  }
+  return HULC2_OK;
+}
+
+template <int BN>
+int launch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TmaParams& p, int smem, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch<BN, false, false>(ta, tb, p, smem, st);
+  if (!a_mn && b_mn) return launch<BN, false, true>(ta, tb, p, smem, st);
+  if (a_mn && b_mn) return launch<BN, true, true>(ta, tb, p, smem, st);
+  return launch<BN, true, false>(ta, tb, p, smem, st);
+}
+
+bool al(const void* p, uintptr_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
+
+}  // namespace
+
+// Returns HULC2_ENOTIMPL when the problem does not fit the TMA path (the caller then uses the gather kernel).
+int hulc2_gemm_tma_impl(const hulc2_gemm_args* a, cudaStream_t st) {
+  if (!a->A16 || !a->B16 || a->a_inner > 0 || a->K <= 0 || a->M <= 0 || a->N <= 0) return HULC2_ENOTIMPL;
+  if (!hulc2_device_supports_tcgen05()) return HULC2_ENOTIMPL;
+  // operand orientation: K-major when the contraction index is the unit-stride axis, MN-major when the row index is
+  bool a_mn, b_mn;
+  long long a_ld, b_ld;
+  if (a->a_ks == 1) { a_mn = false; a_ld = a->a_rs; } else if (a->a_rs == 1) { a_mn = true; a_ld = a->a_ks; } else return HULC2_ENOTIMPL;
+  if (a->b_ks == 1) { b_mn = false; b_ld = a->b_rs; } else if (a->b_rs == 1) { b_mn = true; b_ld = a->b_ks; } else return HULC2_ENOTIMPL;
+  if (!al(a->A16, 16) || !al(a->B16, 16) || a_ld % 8 || b_ld % 8 || a_ld <= 0 || b_ld <= 0) return HULC2_ENOTIMPL;
+
+  TmaParams p{};
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  fill_epilogue(p.E, a->C, a->ldc);
+  p.E.c_inner = a->c_inner; p.E.cs_outer = a->c_rs_outer; p.E.cs_inner = a->c_rs_inner;
+  p.E.bias = a->bias; p.E.add = a->add; p.E.ld_add = a->ld_add; p.E.mask = a->mask; p.E.ld_mask = a->ld_mask;
+  p.E.keep = a->keep; p.E.ld_keep = a->ld_keep; p.E.keep_scale = a->keep_scale;
+  p.E.relu = a->relu; p.E.accumulate = a->accumulate; p.E.alpha = a->alpha;
+  p.C16 = (__nv_bfloat16*)a->C16; p.ld16 = a->ld16;
+  p.ktiles = hulc2_cdiv(a->K, BK);
+
+  const int mt = hulc2_cdiv(a->M, BM);
+  int BN = a->N <= 64 ? 64 : (a->N <= 128 ? 128 : 256);
+  if (BN == 256 && (long long)mt * hulc2_cdiv(a->N, 256) < 148) BN = 128;   // more, smaller tiles when the grid is short
+  if (BN == 128 && a->N > 64 && (long long)mt * hulc2_cdiv(a->N, 128) < 74 && p.ktiles <= 8) BN = 64;
+  const long long tiles = (long long)mt * hulc2_cdiv(a->N, BN);
+
+  // split-K: skinny outputs with a long contraction get ~2 waves of CTAs, >= 4 k-tiles each
+  p.splits = 1; p.kt_per_split = p.ktiles; p.partial = nullptr;
+  const bool simple = simple_epilogue(a) && !a->C16 && a->c_inner == 0;
+  if (simple && tiles < 100 && p.ktiles >= 8 && a->workspace) {
+    int want = (int)((296 + tiles - 1) / tiles);
+    int maxs = p.ktiles / 4;
+    int s = want < maxs ? want : maxs;
+    const long long per = (long long)a->M * a->N * (long long)sizeof(float);
+    while (s > 1 && (long long)s * per > a->workspace_bytes) --s;
+    if (s > 1) {
+      p.kt_per_split = hulc2_cdiv(p.ktiles, s);
+      p.splits = hulc2_cdiv(p.ktiles, p.kt_per_split);
+      p.partial = (float*)a->workspace;
+    }
+  }
+  const int stage_bytes = (int)A_BYTES + BN * 128;
+  const long long ctas = tiles * p.splits;
+  const int budget = (ctas > 148 && stage_bytes * 3 <= 110 * 1024) ? 110 * 1024 : 200 * 1024;   // 2 CTAs/SM when they exist
+  int stages = budget / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > p.kt_per_split) stages = p.kt_per_split;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  const int smem = stages * stage_bytes + 1024;
+
+  // 16-byte epilogue accesses
+  bool vec = al(a->C, 16) && a->ldc % 4 == 0;
+  if (a->bias) vec = vec && al(a->bias, 16);
+  if (a->add) vec = vec && al(a->add, 16) && a->ld_add % 4 == 0;
+  if (a->mask) vec = vec && al(a->mask, 16) && a->ld_mask % 4 == 0;
+  if (a->keep) vec = vec && al(a->keep, 4) && a->ld_keep % 4 == 0;
+  if (a->C16) vec = vec && al(a->C16, 8) && a->ld16 % 4 == 0;
+  if (p.splits > 1) vec = al(p.partial, 16) && a->N % 4 == 0;
+  p.vec = vec ? 1 : 0;
+
+  CUtensorMap ta, tb;
+  bool ok = a_mn ? encode_map(&ta, a->A16, a->M, a->K, a_ld, 64) : encode_map(&ta, a->A16, a->K, a->M, a_ld, BM);
+  ok = ok && (b_mn ? encode_map(&tb, a->B16, a->N, a->K, b_ld, 64) : encode_map(&tb, a->B16, a->K, a->N, b_ld, BN));
+  if (!ok) return HULC2_ENOTIMPL;
+
+  switch (BN) {
+    case 64: return launch_major<64>(a_mn, b_mn, ta, tb, p, smem, st);
+    case 128: return launch_major<128>(a_mn, b_mn, ta, tb, p, smem, st);
+    default: return launch_major<256>(a_mn, b_mn, ta, tb, p, smem, st);
+  }
+}
+
+extern "C" unsigned long long hulc2_tma_gemm_count(void) { return g_tma_gemms; }

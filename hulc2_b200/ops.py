@@ -72,8 +72,11 @@ def _ld(t: torch.Tensor) -> int:
 # ----------------------------------------------------------------------------- raw kernel wrappers
 def gemm(M, N, K, A, a_rs, a_ks, B, b_rs, b_ks, Cout, ldc, *, a_off=0, b_off=0, c_off=0, bias=None, add=None, ld_add=0,
          mask=None, ld_mask=0, keep=None, ld_keep=0, keep_scale=1.0, relu=False, accumulate=False, alpha=1.0,
-         a_inner=0, a_rs_outer=0, a_rs_inner=0, c_inner=0, c_rs_outer=0, c_rs_inner=0, precision=None):
-    """C[m,n] = epi(alpha * sum_k A(m,k) B(n,k)); offsets are in elements."""
+         a_inner=0, a_rs_outer=0, a_rs_inner=0, c_inner=0, c_rs_outer=0, c_rs_inner=0, precision=None,
+         A16=None, B16=None, C16=None, ld16=0, c16_off=0):
+    """C[m,n] = epi(alpha * sum_k A(m,k) B(n,k)); offsets are in elements.
+    A16/B16: bf16 mirrors of the tensors A/B (same flat layout, see :func:`to_bf16`) -> TMA-fed tcgen05 kernel;
+    C16: bf16 tensor that additionally receives the result (row stride ld16)."""
     ws = workspace(Cout.device)
     g = GemmArgs()
     g.M, g.N, g.K = int(M), int(N), int(K)
@@ -90,8 +93,22 @@ def gemm(M, N, K, A, a_rs, a_ks, B, b_rs, b_ks, Cout, ldc, *, a_off=0, b_off=0, 
     g.relu, g.accumulate, g.alpha = int(relu), int(accumulate), alpha
     g.precision = _precision if precision is None else precision
     g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
+    if g.precision == 1:
+        g.A16 = None if A16 is None else A16.data_ptr() + 2 * a_off
+        g.B16 = None if B16 is None else B16.data_ptr() + 2 * b_off
+        g.C16 = None if C16 is None else C16.data_ptr() + 2 * c16_off
+        g.ld16 = ld16
     _lib.tag(f"gemm[M={int(M)},N={int(N)},K={int(K)}]", 2.0 * M * N * K)
     call("hulc2_gemm", C.byref(g))
+
+
+def to_bf16(t: torch.Tensor) -> torch.Tensor:
+    """bf16 mirror of a dense fp32 tensor (same shape, element i <-> element i): the GEMM operand copies."""
+    t = _f32(t)
+    assert t.is_contiguous(), "to_bf16 mirrors dense tensors"
+    out = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
+    call("hulc2_f32_to_bf16", t.data_ptr(), out.data_ptr(), t.numel())
+    return out
 
 
 def _conv_args(F, Cin, H, W, Cout, k, stride, in_nhwc) -> ConvArgs:

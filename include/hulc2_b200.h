@@ -35,7 +35,12 @@ int hulc2_device_supports_tcgen05(void);
  * R(m) = m*a_rs, or (m / a_inner)*a_rs_outer + (m % a_inner)*a_rs_inner when a_inner > 0 (same for C rows).
  * epilogue: +bias[n]; +add[m,n]; +C (accumulate); relu; zero where mask[m,n] <= 0; dropout keep (u8) * keep_scale.
  * Serves nn.Linear forward / input-grad / weight-grad everywhere on the path, e.g.
- * plan_proposal_net.py:42-47, goal_encoders.py:29-34, logistic_decoder_rnn.py:269-274. */
+ * plan_proposal_net.py:42-47, goal_encoders.py:29-34, logistic_decoder_rnn.py:269-274.
+ * A16 / B16 / C16 / ld16 (precision 1 only, all optional): row-major bf16 mirrors of the operands -- element i of A16 is
+ * bf16(A[i]) -- so the strides and offsets above address them unchanged; written by hulc2_f32_to_bf16 or by a producing
+ * GEMM through its C16.  With both mirrors present and 16-byte-aligned rows the contraction runs on the TMA-fed tcgen05
+ * kernel (csrc/gemm_tma_sm100.cu); otherwise the gather kernel converts the fp32 operands on the fly.  C16 (row stride
+ * ld16) additionally receives the epilogue result as bf16: the next layer's operand. */
 typedef struct {
   int M, N, K;
   const float* A; long long a_rs, a_ks; int a_inner; long long a_rs_outer, a_rs_inner;
@@ -49,8 +54,14 @@ typedef struct {
   float alpha;
   int precision;
   void* workspace; long long workspace_bytes;
+  const void* A16; const void* B16;
+  void* C16; long long ld16;
 } hulc2_gemm_args;
 int hulc2_gemm(const hulc2_gemm_args* a, hulc2_stream_t stream);
+/* number of contractions served by the TMA-fed kernel so far (tests assert the fast path was taken) */
+unsigned long long hulc2_tma_gemm_count(void);
+/* dst[i] = bf16(src[i]) (round to nearest even), the operand mirrors of hulc2_gemm_args */
+int hulc2_f32_to_bf16(const float* src, void* dst, long long n, hulc2_stream_t stream);
 
 /* ------------------------------------------------------------------ convolutions (implicit GEMM)
  * vision_network.py:38-48 and vision_network_gripper.py:11-26 (valid padding, square stride).
