@@ -64,6 +64,7 @@ class ConvbArgs(C.Structure):
 _SIGS = {
     "hulc2_gemm": [C.POINTER(GemmArgs)],
     "hulc2_f32_to_bf16": [P, P, LL],
+    "hulc2_f32_to_bf16_2d": [P, LL, P, LL, LL, I],
     "hulc2_conv2d_fwd": [C.POINTER(ConvArgs)],
     "hulc2_conv2d_wgrad": [C.POINTER(ConvArgs)],
     "hulc2_conv2d_dgrad": [C.POINTER(ConvArgs)],

@@ -221,6 +221,32 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
   }
 }
 
+// strided rows -> compact bf16 rows: dst[r*ld_dst + c] = bf16(src[r*ld_src + c]), c < cols (pad columns are not written)
+__global__ void f32_to_bf16_2d_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst,
+                                      long long ld_dst, long long rows, int cols, int vec) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+    const int c4 = cols >> 2;
+    const long long total = rows * c4;
+    for (long long i = tid; i < total; i += nthreads) {
+      const long long r = i / c4;
+      const int c = (int)(i - r * c4) << 2;
+      float4 a = __ldg(reinterpret_cast<const float4*>(src + r * ld_src + c));
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+      uint2 o;
+      o.x = *reinterpret_cast<unsigned*>(&h0); o.y = *reinterpret_cast<unsigned*>(&h1);
+      *reinterpret_cast<uint2*>(dst + r * ld_dst + c) = o;
+    }
+  } else {
+    const long long total = rows * cols;
+    for (long long i = tid; i < total; i += nthreads) {
+      const long long r = i / cols;
+      const int c = (int)(i - r * cols);
+      dst[r * ld_dst + c] = __float2bfloat16_rn(src[r * ld_src + c]);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -239,6 +265,16 @@ int hulc2_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t st)
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   f32_to_bf16_kernel<<<(int)blocks, 256, 0, st>>>(src, (__nv_bfloat16*)dst, n, vec);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_f32_to_bf16_2d(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return HULC2_OK;
+  const int vec = ((((uintptr_t)src) & 15) == 0) && ((((uintptr_t)dst) & 7) == 0) && cols % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0;
+  long long work = vec ? rows * (cols >> 2) : rows * (long long)cols;
+  long long blocks = (work + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  f32_to_bf16_2d_kernel<<<(int)blocks, 256, 0, st>>>(src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols, vec);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

@@ -410,10 +410,12 @@ int dispatch(GemmParams& p, int amode, int bmode, cudaStream_t st) {
 int hulc2_gemm_tma_impl(const hulc2_gemm_args* a, cudaStream_t st);
 
 int hulc2_gemm_bf16_impl(const hulc2_gemm_args* a, cudaStream_t st) {
+  if (a && (a->M == 0 || a->N == 0)) return HULC2_OK;
   if (a && a->A16 && a->B16) {   // bf16 operand mirrors: TMA-fed kernel when the layout allows it
     int e = hulc2_gemm_tma_impl(a, st);
     if (e != HULC2_ENOTIMPL) return e;
   }
+  if (a && (!a->A || !a->B)) { hulc2_set_error("gemm: bf16-only operands (A/B NULL) need a TMA-compatible layout: 16-byte aligned base, row stride % 8 == 0, K > 0"); return HULC2_EINVAL; }
   if (a && a->C16) { hulc2_set_error("gemm: a bf16 output mirror (C16) needs the TMA path (aligned bf16 operand mirrors)"); return HULC2_EINVAL; }
   GemmParams p;
   if (!dense_params(a, p)) return HULC2_EINVAL;

@@ -188,6 +188,7 @@ class Hulc2(LightningModule):
         When the modalities carry the same cameras (every shipped config), their windows run through the network as ONE
         batch (``_training_step_batched``): same per-modality losses, logged scalars and gradients as the reference's
         modality loop below, half the kernel launches and M=128 instead of M=64 rows for every contraction."""
+        ops.invalidate_weight_mirrors()
         if self.batch_modalities and self._can_batch_modalities(batch):
             return self._training_step_batched(batch)
         n_mod = len(batch)
@@ -310,6 +311,7 @@ class Hulc2(LightningModule):
 
     def validation_step(self, batch: Dict[str, Dict], batch_idx: int) -> Dict[str, torch.Tensor]:  # type: ignore
         """hulc2.py:510-598."""
+        ops.invalidate_weight_mirrors()
         output = {}
         act_pp = []
         n_mod = len(getattr(getattr(self.trainer, "datamodule", None), "modalities", None) or batch)
@@ -346,12 +348,14 @@ class Hulc2(LightningModule):
 
     # ------------------------------------------------------------------ inference (hulc2.py:600-707)
     def reset(self):
+        ops.invalidate_weight_mirrors()
         self.plan = None
         self.latent_goal = None
         self.rollout_step_counter = 0
 
     def step(self, obs, goal):
         if self.rollout_step_counter % self.replan_freq == 0:
+            ops.invalidate_weight_mirrors()   # parameters may have been trained / loaded since the last plan
             if "lang" in goal:
                 self.plan, self.latent_goal = self.get_pp_plan_lang(obs, goal)
             else:

@@ -111,6 +111,83 @@ def to_bf16(t: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _pad8(n: int) -> int:
+    return (int(n) + 7) & ~7
+
+
+def mirror2d(x2: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """Compact bf16 mirror [rows, pad8(cols)] of a 2-D fp32 tensor with unit inner stride (rows may be strided)."""
+    x2 = _f32(x2)
+    rows, cols = x2.shape
+    ld = _pad8(cols)
+    out = torch.empty(rows, ld, device=x2.device, dtype=torch.bfloat16)
+    if x2.is_contiguous() and ld == cols:
+        call("hulc2_f32_to_bf16", x2.data_ptr(), out.data_ptr(), x2.numel())
+    elif rows > 0:
+        assert x2.stride(1) == 1
+        call("hulc2_f32_to_bf16_2d", x2.data_ptr(), _ld(x2), out.data_ptr(), ld, rows, cols)
+    return out, ld
+
+
+# bf16 mirrors of the parameters: one flat conversion of the optimizer's parameter arena (registered by FusedAdam) or
+# one per tensor, reused by every contraction of the step; invalidated whenever the fp32 masters may have changed
+# (start of every training / validation step and rollout re-plan, optimizer.step, load_state_dict).
+_w16: dict = {}
+_arenas: list = []      # [fp32 arena tensor, bf16 mirror or None, arena._version at conversion]
+
+
+def register_param_arena(arena: torch.Tensor) -> None:
+    _arenas[:] = [a for a in _arenas if a[0].data_ptr() != arena.data_ptr()]
+    _arenas.append([arena, None, -1])
+
+
+def invalidate_weight_mirrors() -> None:
+    _w16.clear()
+    for a in _arenas:
+        a[1] = None
+
+
+def weight16(W: torch.Tensor) -> torch.Tensor:
+    """bf16 mirror of a (contiguous) parameter tensor, same shape."""
+    ptr, n = W.data_ptr(), W.numel()
+    for a in _arenas:
+        base = a[0].data_ptr()
+        if base <= ptr and ptr + 4 * n <= base + 4 * a[0].numel() and a[0].device == W.device:
+            if a[1] is None or a[2] != a[0]._version:     # torch in-place writes through any view bump the version
+                a[1], a[2] = to_bf16(a[0]), a[0]._version
+            off = (ptr - base) // 4
+            return a[1][off : off + n].view(W.shape)
+    key = (ptr, n, W._version)
+    hit = _w16.get(key)
+    if hit is None:
+        hit = _w16[key] = to_bf16(W.detach().contiguous())
+    return hit
+
+
+def gemm16(M, N, K, A16, a_rs, a_ks, B16, b_rs, b_ks, Cout, ldc, *, a_off=0, b_off=0, c_off=0, bias=None, add=None, ld_add=0,
+           mask=None, ld_mask=0, keep=None, ld_keep=0, keep_scale=1.0, relu=False, accumulate=False, alpha=1.0,
+           C16=None, ld16=0):
+    """C[m,n] = epi(alpha * sum_k A(m,k) B(n,k)) with bf16-only operands (TMA-fed tcgen05 kernel): A(m,k) =
+    A16[a_off + m*a_rs + k*a_ks], one of (a_rs, a_ks) being 1; same for B.  C fp32 (+ optional bf16 copy C16)."""
+    ws = workspace(Cout.device)
+    g = GemmArgs()
+    g.M, g.N, g.K = int(M), int(N), int(K)
+    g.A, g.B = None, None
+    g.A16, g.a_rs, g.a_ks = A16.data_ptr() + 2 * a_off, a_rs, a_ks
+    g.B16, g.b_rs, g.b_ks = B16.data_ptr() + 2 * b_off, b_rs, b_ks
+    g.C, g.ldc = Cout.data_ptr() + 4 * c_off, ldc
+    g.bias = _p(bias)
+    g.add, g.ld_add = _p(add), ld_add
+    g.mask, g.ld_mask = _p(mask), ld_mask
+    g.keep, g.ld_keep, g.keep_scale = _p(keep), ld_keep, keep_scale
+    g.relu, g.accumulate, g.alpha = int(relu), int(accumulate), alpha
+    g.precision = 1
+    g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
+    g.C16, g.ld16 = _p(C16), ld16
+    _lib.tag(f"gemm16[M={int(M)},N={int(N)},K={int(K)}]", 2.0 * M * N * K)
+    call("hulc2_gemm", C.byref(g))
+
+
 def _conv_args(F, Cin, H, W, Cout, k, stride, in_nhwc) -> ConvArgs:
     a = ConvArgs()
     a.F, a.C, a.H, a.W, a.Cout, a.KH, a.KW, a.stride, a.in_nhwc = F, Cin, H, W, Cout, k, k, stride, int(in_nhwc)
@@ -134,6 +211,28 @@ class MLPFunction(torch.autograd.Function):
         x2 = _rows2d(_f32(x))
         M = x2.shape[0]
         n = len(wb) // 2
+        ctx.b16 = _precision == 1 and M > 0 and all(wb[2 * i].shape[1] % 8 == 0 for i in range(n))
+        if ctx.b16:
+            # bf16 operand mirrors: every layer's epilogue also emits the bf16 copy the next layer (and the weight
+            # gradient) multiplies; the fp32 activations stay for the ReLU masks and non-GEMM consumers
+            cur16, ld = mirror2d(x2)
+            acts, mirrors = [], [cur16]
+            for i in range(n):
+                W, b = wb[2 * i], wb[2 * i + 1]
+                N, K = W.shape
+                y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+                last = i == n - 1
+                y16 = None if last else torch.empty(M, _pad8(N), device=x.device, dtype=torch.bfloat16)
+                gemm16(M, N, K, cur16, ld, 1, weight16(W), K, 1, y, N, bias=b, relu=relus[i], keep=keeps[i], ld_keep=N,
+                       keep_scale=keep_scale, C16=y16, ld16=_pad8(N))
+                acts.append(y)
+                if not last:
+                    mirrors.append(y16)
+                    cur16, ld = y16, _pad8(N)
+            ctx.relus, ctx.keeps, ctx.keep_scale, ctx.n = relus, keeps, keep_scale, n
+            ctx.x_shape = x.shape
+            ctx.save_for_backward(x2, *acts, *wb, *mirrors)
+            return acts[-1].view(*x.shape[:-1], acts[-1].shape[1])
         acts = []
         cur, ld = x2, _ld(x2)
         for i in range(n):
@@ -153,7 +252,8 @@ class MLPFunction(torch.autograd.Function):
     def backward(ctx, dout):
         n = ctx.n
         saved = ctx.saved_tensors
-        x2, acts, wb = saved[0], saved[1 : 1 + n], saved[1 + n :]
+        x2, acts, wb = saved[0], saved[1 : 1 + n], saved[1 + n : 1 + 3 * n]
+        mirrors = saved[1 + 3 * n :]
         M = x2.shape[0]
         g = _rows2d(dout.contiguous())
         if g.data_ptr() == dout.data_ptr() and (ctx.relus[n - 1] or ctx.keeps[n - 1] is not None):
@@ -163,6 +263,33 @@ class MLPFunction(torch.autograd.Function):
             call("hulc2_relu_mask", g.data_ptr(), acts[n - 1].data_ptr(), g.data_ptr(), g.numel())
         grads: List[Optional[torch.Tensor]] = [None] * (2 * n)
         dx = None
+        if ctx.b16:
+            g16, ldg = mirror2d(g)
+            for i in range(n - 1, -1, -1):
+                W = wb[2 * i]
+                N, K = W.shape
+                in16 = mirrors[i]
+                ld_in = in16.shape[1]
+                if ctx.needs_input_grad[4 + 2 * i]:
+                    dW = torch.empty_like(W)
+                    gemm16(N, K, M, g16, 1, ldg, in16, 1, ld_in, dW, K)          # dW = g^T inp (both MN-major)
+                    grads[2 * i] = dW
+                if ctx.needs_input_grad[5 + 2 * i]:
+                    db = torch.empty(N, device=W.device, dtype=torch.float32)
+                    colsum(g, N, M, N, db)
+                    grads[2 * i + 1] = db
+                if i > 0 or ctx.needs_input_grad[0]:
+                    gi = torch.empty(M, K, device=W.device, dtype=torch.float32)
+                    gi16 = torch.empty(M, _pad8(K), device=W.device, dtype=torch.bfloat16) if i > 0 else None
+                    if i > 0:
+                        gemm16(M, K, N, g16, ldg, 1, weight16(W), 1, K, gi, K, mask=acts[i - 1] if ctx.relus[i - 1] else None,
+                               ld_mask=K, keep=ctx.keeps[i - 1], ld_keep=K, keep_scale=ctx.keep_scale, C16=gi16, ld16=_pad8(K))
+                    else:
+                        gemm16(M, K, N, g16, ldg, 1, weight16(W), 1, K, gi, K)
+                    g, g16, ldg = gi, gi16, _pad8(K)
+                    if i == 0:
+                        dx = gi.view(ctx.x_shape)
+            return (dx, None, None, None, *grads)
         for i in range(n - 1, -1, -1):
             W = wb[2 * i]
             N, K = W.shape
@@ -713,26 +840,44 @@ class RNNDecoderFunction(torch.autograd.Function):
         for bs, bi, bh in ((bsum0, bi0, bh0), (bsum1, bi1, bh1)):
             call("hulc2_copy2d", bi.data_ptr(), H, bs.data_ptr(), H, 1, H, 0)
             call("hulc2_axpy", bh.data_ptr(), bs.data_ptr(), H, 1.0)
+        b16 = _precision == 1 and In % 8 == 0 and P % 8 == 0 and Es % 8 == 0 and H % 8 == 0
         base = torch.empty(B, H, device=dev, dtype=torch.float32)
-        gemm(B, H, P, plan, P, 1, wi0, In, 1, base, H, bias=bsum0)
-        gemm(B, H, G, goal, G, 1, wi0, In, 1, base, H, b_off=P + Es, accumulate=True)
         pre = torch.empty(S, B, H, device=dev, dtype=torch.float32)
-        call("hulc2_copy2d", base.data_ptr(), 0, pre.data_ptr(), B * H, S, B * H, 0)
-        gemm(S * B, H, Es, embT, Es, 1, wi0, In, 1, pre, H, b_off=P, accumulate=True)
+        if b16:
+            wi0h, wi1h = weight16(wi0), weight16(wi1)
+            plan16, _ = mirror2d(plan)
+            goal16, ldg = mirror2d(goal)
+            embT16, _ = mirror2d(embT.view(S * B, Es))
+            gemm16(B, H, P, plan16, P, 1, wi0h, In, 1, base, H, bias=bsum0)
+            gemm16(B, H, G, goal16, ldg, 1, wi0h, In, 1, base, H, b_off=P + Es, accumulate=True)
+            call("hulc2_copy2d", base.data_ptr(), 0, pre.data_ptr(), B * H, S, B * H, 0)
+            gemm16(S * B, H, Es, embT16, Es, 1, wi0h, In, 1, pre, H, b_off=P, accumulate=True)
+        else:
+            gemm(B, H, P, plan, P, 1, wi0, In, 1, base, H, bias=bsum0)
+            gemm(B, H, G, goal, G, 1, wi0, In, 1, base, H, b_off=P + Es, accumulate=True)
+            call("hulc2_copy2d", base.data_ptr(), 0, pre.data_ptr(), B * H, S, B * H, 0)
+            gemm(S * B, H, Es, embT, Es, 1, wi0, In, 1, pre, H, b_off=P, accumulate=True)
         H0 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         h00 = h0[0].contiguous() if h0 is not None else None
         h01 = h0[1].contiguous() if h0 is not None else None
         _lib.tag(f"rnn_relu_fwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
         call("hulc2_rnn_relu_fwd", pre.data_ptr(), wh0.data_ptr(), _p(h00), H0.data_ptr(), S, B, H, _lib_precision(), ws.data_ptr(), ws.numel())
-        gemm(S * B, H, H, H0, H, 1, wi1, H, 1, pre, H, bias=bsum1)
+        H0h = None
+        if b16:
+            H0h = to_bf16(H0)
+            gemm16(S * B, H, H, H0h, H, 1, wi1h, H, 1, pre, H, bias=bsum1)
+        else:
+            gemm(S * B, H, H, H0, H, 1, wi1, H, 1, pre, H, bias=bsum1)
         H1 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         _lib.tag(f"rnn_relu_fwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
         call("hulc2_rnn_relu_fwd", pre.data_ptr(), wh1.data_ptr(), _p(h01), H1.data_ptr(), S, B, H, _lib_precision(), ws.data_ptr(), ws.numel())
         hn = torch.empty(2, B, H, device=dev, dtype=torch.float32)
         call("hulc2_copy2d", H0.data_ptr() + 4 * (S - 1) * B * H, B * H, hn.data_ptr(), B * H, 1, B * H, 0)
         call("hulc2_copy2d", H1.data_ptr() + 4 * (S - 1) * B * H, B * H, hn.data_ptr() + 4 * B * H, B * H, 1, B * H, 0)
+        ctx.b16 = b16
+        extra = (plan16, goal16, embT16, H0h) if b16 else ()
         ctx.save_for_backward(plan, embT, goal, H0, H1, wi0, wh0, wi1, wh1, h00 if h00 is not None else plan.new_empty(0),
-                              h01 if h01 is not None else plan.new_empty(0))
+                              h01 if h01 is not None else plan.new_empty(0), *extra)
         ctx.dims = (B, S, Es, P, G, H, In)
         ctx.has_h0 = h0 is not None
         ctx.mark_non_differentiable(hn)
@@ -740,6 +885,8 @@ class RNNDecoderFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dH1, _dhn):
+        if ctx.b16:
+            return RNNDecoderFunction._backward16(ctx, dH1)
         plan, embT, goal, H0, H1, wi0, wh0, wi1, wh1, h00, h01 = ctx.saved_tensors
         B, S, Es, P, G, H, In = ctx.dims
         dev = plan.device
@@ -795,6 +942,68 @@ class RNNDecoderFunction(torch.autograd.Function):
             call("hulc2_transpose01", dembT.data_ptr(), B * Es, Es, demb.data_ptr(), Es, S, B, Es, 0)
         return (dplan, demb, dgoal, None, dwi0, dwh0, db0, db0.clone(), dwi1, dwh1, db1, db1.clone())
 
+    @staticmethod
+    def _backward16(ctx, dH1):
+        """Same gradient algebra as ``backward`` on bf16 operand mirrors (TMA-fed contractions)."""
+        plan, embT, goal, H0, H1, wi0, wh0, wi1, wh1, h00, h01, plan16, goal16, embT16, H0h = ctx.saved_tensors
+        B, S, Es, P, G, H, In = ctx.dims
+        dev = plan.device
+        ws = workspace(dev)
+        step = B * H
+        ldg = goal16.shape[1]
+        wi0h, wi1h = weight16(wi0), weight16(wi1)
+        dH1 = dH1.contiguous()
+        dz1 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
+        call("hulc2_copy2d", dH1.data_ptr(), step, dz1.data_ptr(), step, S, step, 0)
+        _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
+        call("hulc2_rnn_relu_bwd", dz1.data_ptr(), wh1.data_ptr(), H1.data_ptr(), None, S, B, H, 1, ws.data_ptr(), ws.numel())
+        dz1h, H1h = to_bf16(dz1), to_bf16(H1)
+        dwh1 = torch.empty_like(wh1)
+        if S > 1:
+            gemm16(H, H, (S - 1) * B, dz1h, 1, H, H1h, 1, H, dwh1, H, a_off=step)
+        else:
+            call("hulc2_fill", dwh1.data_ptr(), dwh1.numel(), 0.0)
+        if ctx.has_h0:
+            gemm(H, H, B, dz1, 1, H, h01, 1, H, dwh1, H, accumulate=True)
+        dwi1 = torch.empty_like(wi1)
+        gemm16(H, H, S * B, dz1h, 1, H, H0h, 1, H, dwi1, H)
+        db1 = torch.empty(H, device=dev, dtype=torch.float32)
+        colsum(dz1, H, S * B, H, db1)
+        dz0 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
+        gemm16(S * B, H, H, dz1h, H, 1, wi1h, 1, H, dz0, H)                      # dH0 = dz1 W_ih1
+        _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
+        call("hulc2_rnn_relu_bwd", dz0.data_ptr(), wh0.data_ptr(), H0.data_ptr(), None, S, B, H, 1, ws.data_ptr(), ws.numel())
+        dz0h = to_bf16(dz0)
+        dwh0 = torch.empty_like(wh0)
+        if S > 1:
+            gemm16(H, H, (S - 1) * B, dz0h, 1, H, H0h, 1, H, dwh0, H, a_off=step)
+        else:
+            call("hulc2_fill", dwh0.data_ptr(), dwh0.numel(), 0.0)
+        if ctx.has_h0:
+            gemm(H, H, B, dz0, 1, H, h00, 1, H, dwh0, H, accumulate=True)
+        db0 = torch.empty(H, device=dev, dtype=torch.float32)
+        colsum(dz0, H, S * B, H, db0)
+        dzsum = torch.empty(B, H, device=dev, dtype=torch.float32)
+        colsum(dz0, B * H, S, B * H, dzsum)                                      # sum over time
+        dzsumh = to_bf16(dzsum)
+        dwi0 = torch.empty_like(wi0)
+        gemm16(H, P, B, dzsumh, 1, H, plan16, 1, P, dwi0, In)
+        gemm16(H, Es, S * B, dz0h, 1, H, embT16, 1, Es, dwi0, In, c_off=P)
+        gemm16(H, G, B, dzsumh, 1, H, goal16, 1, ldg, dwi0, In, c_off=P + Es)
+        dplan = dgoal = demb = None
+        if ctx.needs_input_grad[0]:
+            dplan = torch.empty(B, P, device=dev, dtype=torch.float32)
+            gemm16(B, P, H, dzsumh, H, 1, wi0h, 1, In, dplan, P)
+        if ctx.needs_input_grad[2]:
+            dgoal = torch.empty(B, G, device=dev, dtype=torch.float32)
+            gemm16(B, G, H, dzsumh, H, 1, wi0h, 1, In, dgoal, G, b_off=P + Es)
+        if ctx.needs_input_grad[1]:
+            dembT = torch.empty(S, B, Es, device=dev, dtype=torch.float32)
+            gemm16(S * B, Es, H, dz0h, H, 1, wi0h, 1, In, dembT, Es, b_off=P)
+            demb = torch.empty(B, S, Es, device=dev, dtype=torch.float32)
+            call("hulc2_transpose01", dembT.data_ptr(), B * Es, Es, demb.data_ptr(), Es, S, B, Es, 0)
+        return (dplan, demb, dgoal, None, dwi0, dwh0, db0, db0.clone(), dwi1, dwh1, db1, db1.clone())
+
 
 def _lib_precision() -> int:
     return _precision
@@ -804,12 +1013,23 @@ def _lib_precision() -> int:
 HEAD_LD = 184  # 3*A*M + 2 = 182 columns, row-padded to 16 bytes
 
 
-def heads_forward(Hs, wp, bp, wm, bm, wsc, bsc, wg, bg) -> torch.Tensor:
+def _heads16_ok(Hs, wp, wg) -> bool:
+    return _precision == 1 and wg is not None and Hs.shape[-1] % 8 == 0 and 3 * wp.shape[0] + 2 <= HEAD_LD and Hs.numel() > 0
+
+
+def heads_forward(Hs, wp, bp, wm, bm, wsc, bsc, wg, bg, Hs16=None) -> torch.Tensor:
     """Four nn.Linear heads (logistic_decoder_rnn.py:269-274) into one [rows, 184] buffer
     [logit_probs | means | log_scales | gripper]."""
     rows, H = Hs.shape[0] * Hs.shape[1], Hs.shape[2]
     AM = wp.shape[0]
     heads = torch.empty(rows, HEAD_LD, device=Hs.device, dtype=torch.float32)
+    if _heads16_ok(Hs, wp, wg):
+        # one contraction over the stacked head weights [3*A*M + 2, H] (bf16 mirrors)
+        Wcat = torch.cat([weight16(wp), weight16(wm), weight16(wsc), weight16(wg)], 0)
+        bcat = torch.cat([bp, bm, bsc, bg], 0)
+        Hs16 = Hs16 if Hs16 is not None else to_bf16(Hs.contiguous())
+        gemm16(rows, 3 * AM + 2, H, Hs16, H, 1, Wcat, H, 1, heads, HEAD_LD, bias=bcat)
+        return heads
     for W, b, off in ((wp, bp, 0), (wm, bm, AM), (wsc, bsc, 2 * AM)):
         gemm(rows, AM, H, Hs, H, 1, W, H, 1, heads, HEAD_LD, c_off=off, bias=b)
     if wg is not None:
@@ -828,7 +1048,9 @@ class DecoderLossFunction(torch.autograd.Function):
         Hs = _f32(Hs).contiguous()
         S, B, H = Hs.shape
         A, M, num_classes, ls_min, alpha = cfg
-        heads = heads_forward(Hs, wp, bp, wm, bm, wsc, bsc, wg, bg)
+        ctx.b16 = _heads16_ok(Hs, wp, wg)
+        Hs16 = to_bf16(Hs) if ctx.b16 else None
+        heads = heads_forward(Hs, wp, bp, wm, bm, wsc, bsc, wg, bg, Hs16=Hs16)
         ws = workspace(Hs.device)
         segmented = isinstance(actions, (tuple, list))
         segs = [_f32(a).contiguous() for a in (actions if segmented else (actions,))]
@@ -839,7 +1061,7 @@ class DecoderLossFunction(torch.autograd.Function):
             call("hulc2_logistic_loss_seg_fwd", heads.data_ptr() + 4 * b0 * HEAD_LD, HEAD_LD, a.data_ptr(), amin.data_ptr(),
                  amax.data_ptr(), out.data_ptr() + 12 * i, a.shape[0], S, A, M, num_classes, ls_min, alpha, 1, B, ws.data_ptr(), ws.numel())
             b0 += a.shape[0]
-        ctx.save_for_backward(Hs, heads, amin, amax, wp, wm, wsc, wg, *segs)
+        ctx.save_for_backward(Hs if Hs16 is None else Hs16, heads, amin, amax, wp, wm, wsc, wg, *segs)
         ctx.cfg = cfg
         return out[:, 0] if segmented else out[0, 0]
 
@@ -862,6 +1084,16 @@ class DecoderLossFunction(torch.autograd.Function):
         dbias = torch.empty(3 * AM + 2, device=dev, dtype=torch.float32)
         colsum(dheads, HEAD_LD, rows, 3 * AM + 2, dbias)
         dH = torch.empty(S, B, H, device=dev, dtype=torch.float32)
+        if ctx.b16:
+            NH = 3 * AM + 2
+            Hs16 = Hs                                                     # the bf16 mirror was saved instead of the fp32 states
+            dh16, ldh = mirror2d(dheads[:, :NH])
+            Wcat = torch.cat([weight16(wp), weight16(wm), weight16(wsc), weight16(wg)], 0)
+            gemm16(rows, H, NH, dh16, ldh, 1, Wcat, 1, H, dH, H)          # dH = dheads Wcat
+            dW = torch.empty(NH, H, device=dev, dtype=torch.float32)
+            gemm16(NH, H, rows, dh16, 1, ldh, Hs16, 1, H, dW, H)          # dWcat = dheads^T Hs
+            return (dH, None, None, None, None, dW[0:AM], dbias[0:AM], dW[AM : 2 * AM], dbias[AM : 2 * AM], dW[2 * AM : 3 * AM],
+                    dbias[2 * AM : 3 * AM], dW[3 * AM :], dbias[3 * AM :])
         wgrads = []
         for i, (W, n) in enumerate(((wp, AM), (wm, AM), (wsc, AM), (wg, 2))):
             off = i * AM

@@ -13,7 +13,7 @@ import torch
 
 from ._lib import call
 
-_ALIGN = 4  # elements (16 bytes)
+_ALIGN = 8  # elements: every parameter starts 32-byte aligned, so its bf16 mirror (ops.weight16) is a legal TMA base
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -49,6 +49,9 @@ class FusedAdam(torch.optim.Optimizer):
                 view.copy_(p.data)
                 p.data = view
         arena["step"] = 0
+        from . import ops
+
+        ops.register_param_arena(arena["p"])   # one flat f32->bf16 conversion per step serves every contraction
         return arena
 
     def _attach_grads(self, arena) -> None:
@@ -104,6 +107,9 @@ class FusedAdam(torch.optim.Optimizer):
                 call("hulc2_adam_step", a["p"].data_ptr(), a["g"].data_ptr(), a["m"].data_ptr(), a["v"].data_ptr(), a["n"],
                      float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(a["step"]),
                      float(self.grad_scale))
+        from . import ops
+
+        ops.invalidate_weight_mirrors()
         return loss
 
     def step_counter(self, device) -> torch.Tensor:

@@ -39,8 +39,10 @@ int hulc2_device_supports_tcgen05(void);
  * A16 / B16 / C16 / ld16 (precision 1 only, all optional): row-major bf16 mirrors of the operands -- element i of A16 is
  * bf16(A[i]) -- so the strides and offsets above address them unchanged; written by hulc2_f32_to_bf16 or by a producing
  * GEMM through its C16.  With both mirrors present and 16-byte-aligned rows the contraction runs on the TMA-fed tcgen05
- * kernel (csrc/gemm_tma_sm100.cu); otherwise the gather kernel converts the fp32 operands on the fly.  C16 (row stride
- * ld16) additionally receives the epilogue result as bf16: the next layer's operand. */
+ * kernel (csrc/gemm_tma_sm100.cu); otherwise the gather kernel converts the fp32 operands on the fly.  A and/or B may be
+ * NULL when the mirror is the only copy (then the strides describe the mirror and a layout the TMA path cannot take is
+ * an error, not a fallback).  C16 (row stride ld16) additionally receives the epilogue result as bf16: the next layer's
+ * operand. */
 typedef struct {
   int M, N, K;
   const float* A; long long a_rs, a_ks; int a_inner; long long a_rs_outer, a_rs_inner;
@@ -62,6 +64,9 @@ int hulc2_gemm(const hulc2_gemm_args* a, hulc2_stream_t stream);
 unsigned long long hulc2_tma_gemm_count(void);
 /* dst[i] = bf16(src[i]) (round to nearest even), the operand mirrors of hulc2_gemm_args */
 int hulc2_f32_to_bf16(const float* src, void* dst, long long n, hulc2_stream_t stream);
+/* strided fp32 rows -> compact bf16 rows: dst[r*ld_dst + c] = bf16(src[r*ld_src + c]) for c < cols */
+int hulc2_f32_to_bf16_2d(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols,
+                         hulc2_stream_t stream);
 
 /* ------------------------------------------------------------------ convolutions (implicit GEMM)
  * vision_network.py:38-48 and vision_network_gripper.py:11-26 (valid padding, square stride).
