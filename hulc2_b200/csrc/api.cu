@@ -17,6 +17,10 @@ int hulc2_rnn_persistent_launch(const float* add, const float* w, const float* i
                                 int S, int B, int H, int relu, int reverse, int transpose_w, void* workspace, long long workspace_bytes,
                                 cudaStream_t st);
 
+int hulc2_rnn_cluster_launch(const float* add, const float* w, const float* init, const float* mask, float* out, float* final_out,
+                             int S, int B, int H, int relu, int reverse, int transpose_w, void* workspace, long long workspace_bytes,
+                             cudaStream_t st);
+
 unsigned long long g_hulc2_launches = 0;
 static thread_local char g_err[512] = "";
 void hulc2_set_error(const char* msg) {
@@ -78,12 +82,22 @@ int hulc2_conv2d_dgrad(const hulc2_conv_args* a, cudaStream_t st) {
   return HULC2_EINVAL;
 }
 
+static int g_rnn_kernel = 0;
+int hulc2_rnn_select_kernel(int which) {
+  int prev = g_rnn_kernel;
+  g_rnn_kernel = which;
+  return prev;
+}
+
 // h[t] = relu(pre[t] + h[t-1] W_hh^T)      (nn.RNN, nonlinearity=relu; decoders/utils/rnn.py:5-14)
 int hulc2_rnn_relu_fwd(const float* pre, const float* w_hh, const float* h0, float* h, int S, int B, int H, int precision,
                        void* workspace, long long workspace_bytes, cudaStream_t st) {
   if (S <= 0 || B <= 0) return HULC2_OK;
   if (precision == 1 && hulc2_device_supports_tcgen05()) {
-    int e = hulc2_rnn_persistent_launch(pre, w_hh, h0, nullptr, h, nullptr, S, B, H, 1, 0, 0, workspace, workspace_bytes, st);
+    int e = HULC2_ENOTIMPL;
+    if (g_rnn_kernel < 1) e = hulc2_rnn_cluster_launch(pre, w_hh, h0, nullptr, h, nullptr, S, B, H, 1, 0, 0, workspace, workspace_bytes, st);
+    if (e != HULC2_ENOTIMPL) return e;
+    if (g_rnn_kernel < 2) e = hulc2_rnn_persistent_launch(pre, w_hh, h0, nullptr, h, nullptr, S, B, H, 1, 0, 0, workspace, workspace_bytes, st);
     if (e != HULC2_ENOTIMPL) return e;
   }
   const long long step = (long long)B * H;
@@ -108,7 +122,10 @@ int hulc2_rnn_relu_bwd(float* dh, const float* w_hh, const float* h, float* dh0,
                        void* workspace, long long workspace_bytes, cudaStream_t st) {
   if (S <= 0 || B <= 0) return HULC2_OK;
   if (precision == 1 && hulc2_device_supports_tcgen05()) {
-    int e = hulc2_rnn_persistent_launch(dh, w_hh, nullptr, h, dh, dh0, S, B, H, 0, 1, 1, workspace, workspace_bytes, st);
+    int e = HULC2_ENOTIMPL;
+    if (g_rnn_kernel < 1) e = hulc2_rnn_cluster_launch(dh, w_hh, nullptr, h, dh, dh0, S, B, H, 0, 1, 1, workspace, workspace_bytes, st);
+    if (e != HULC2_ENOTIMPL) return e;
+    if (g_rnn_kernel < 2) e = hulc2_rnn_persistent_launch(dh, w_hh, nullptr, h, dh, dh0, S, B, H, 0, 1, 1, workspace, workspace_bytes, st);
     if (e != HULC2_ENOTIMPL) return e;
   }
   const long long step = (long long)B * H;

@@ -246,8 +246,17 @@ int hulc2_rnn_relu_fwd(const float* pre, const float* w_hh, const float* h0, flo
                        int precision, void* workspace, long long workspace_bytes, hulc2_stream_t stream);
 int hulc2_rnn_relu_bwd(float* dh_inout, const float* w_hh, const float* h, float* dh0, int S, int B, int H,
                        int precision, void* workspace, long long workspace_bytes, hulc2_stream_t stream);
-/* precision 1 with B <= 128, H % 64 == 0, H/16 <= #SMs and workspace >= 2*S*B*H + 256 bytes runs all S steps in ONE
- * persistent tcgen05 kernel (W_hh slice resident in shared memory, grid barrier per step); otherwise one GEMM per step. */
+/* precision 1 runs all S steps in ONE persistent tcgen05 kernel when the shape fits, tried in this order:
+ *  (a) cluster split-K kernel (rnn_cluster_sm100.cu): B <= 128, H % 512 == 0, H <= 2048, workspace >= 2*S*B*H + 1024
+ *      bytes, H/16 CTAs in clusters of 8 or 4 all co-resident -- W_hh block resident in shared memory, partial sums reduced
+ *      through distributed shared memory, per-K-slice release/acquire flags between steps;
+ *  (b) 1-D persistent kernel (rnn_persistent_sm100.cu): B <= 128, H % 64 == 0, H/16 <= #SMs, workspace >= 2*S*B*H + 256;
+ *  otherwise one GEMM per step. */
+/* test / benchmark hook: 0 = automatic (default), 1 = skip (a), 2 = skip (a) and (b). Returns the previous value. */
+int hulc2_rnn_select_kernel(int which);
+/* number of cluster_size-CTA (8 or 4) clusters of kernel (a) that can be co-resident on the current device; (a) runs with
+ * clusters of 8 when H/128 of them fit, else with clusters of 4 when H/64 fit (a 148-SM B200 reports 15 clusters of 8) */
+int hulc2_rnn_cluster_capacity(int cluster_size);
 
 /* ------------------------------------------------------------------ optimizer + noise
  * Adam (torch.optim.Adam semantics, conf/model/optimizer/adam.yaml): one launch over a flat arena. */

@@ -217,11 +217,24 @@ def test_rollout_bf16_argmax_and_actions():
         assert set(a[..., -1].unique().tolist()) <= {-1.0, 1.0}
 
 
-@pytest.mark.parametrize("B,S,H,with_h0", [(64, 32, 2048, False), (5, 3, 2048, True), (128, 4, 1024, True)])
-def test_persistent_rnn_matches_step_loop(B, S, H, with_h0):
-    """Persistent tcgen05 recurrence (one launch for all steps) vs the fp32 per-step kernels."""
-    from hulc2_b200 import ops
+@pytest.fixture
+def rnn_kernel_reset():
+    yield
+    from hulc2_b200 import _lib
+
+    _lib.load_library().hulc2_rnn_select_kernel(0)
+
+
+@pytest.mark.parametrize("kernel", [0, 1], ids=["cluster", "persistent1d"])
+@pytest.mark.parametrize("B,S,H,with_h0", [(64, 32, 2048, False), (128, 32, 2048, False), (5, 3, 2048, True), (128, 4, 1024, True),
+                                           (33, 5, 512, True), (16, 5, 256, True)])
+def test_persistent_rnn_matches_step_loop(B, S, H, with_h0, kernel, rnn_kernel_reset):
+    """Persistent tcgen05 recurrences (one launch for all steps: cluster split-K kernel, or the 1-D kernel it falls
+    back to) vs the fp32 per-step kernels."""
+    from hulc2_b200 import ops, _lib
     from hulc2_b200._lib import call
+
+    _lib.load_library().hulc2_rnn_select_kernel(kernel)
 
     dev = torch.device(DEV)
     pre = _rand(S, B, H, seed=1).to(dev)
