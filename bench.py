@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-graph", action="store_true", help="drive every step eagerly instead of replaying the captured CUDA graph")
+    ap.add_argument("--frames", default="uint8", choices=["uint8", "fp32"],
+                    help="camera frames in the batch: uint8 HWC + RandomShiftsAug draw, scaled/normalised/shifted on the device "
+                         "(datamodule kernel, SURVEY 8f-1), or the reference batch contract's fp32 NCHW tensors")
     ap.add_argument("--dump-profile", default=None, help="write the per-call CUDA-event profile of one step to this JSON file")
     return ap.parse_args()
 
@@ -195,7 +198,7 @@ def run_b200(args):
     torch.manual_seed(0)
     model = instantiate(hulc2_config(dropout_p=0.1)).to(dev).train()
     trainer = PolicyTrainer(model, use_graph=not args.no_graph)
-    batch = synthetic_batch_fast(B, seed=1 + rank, device=dev)
+    batch = synthetic_batch_fast(B, seed=1 + rank, device=dev, frames=args.frames)
     h2d = nbytes(batch)
 
     def barrier():
@@ -276,12 +279,14 @@ def run_b200(args):
             "metric": "train windows/sec", "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-            "config": {"workload": "configs[1]: Hulc2 policy train step (fwd+bwd+allreduce+Adam), B=64/modality/GPU, window 32, static 200x200 + gripper 84x84 RGB fp32, 7-dof, lang [B,384], dropout 0.1",
-                       "windows_per_step_per_gpu": 2 * B, "parallelism": f"dp{world}", "l2": "inputs (2.3 GB images/step) exceed the 126 MB L2",
+            "config": {"workload": f"configs[1]: Hulc2 policy train step (fwd+bwd+allreduce+Adam), B={B}/modality/GPU, window 32, static 200x200 + gripper 84x84 RGB, 7-dof, lang [B,384], dropout 0.1",
+                       "frames": ("uint8 HWC frames + per-frame RandomShiftsAug draw in the batch; scale/normalise/shift run on the device inside the step (fused into the trunk's pack kernel)"
+                                  if args.frames == "uint8" else "fp32 NCHW frames in [-1,1] (reference batch contract; transforms already applied)"),
+                       "windows_per_step_per_gpu": 2 * B, "parallelism": f"dp{world}", "l2": f"inputs ({h2d / 1e9:.2f} GB of frames/step) exceed the 126 MB L2",
                        "precision": args.precision, "cuda_graph": bool(trainer._graph is not None)},
             "clocks": clk.summary(), "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
             "e2e": {"value": e2e_val, "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                    "api": "PolicyTrainer.fit_host(pinned fp32 batches): H2D of step i+1 overlapped with step i",
+                    "api": f"PolicyTrainer.fit_host(pinned host batches, frames {args.frames}): H2D of step i+1 overlapped with step i",
                     "pcie_gbs": h2d * world / (float(e2e_ms) * 1e-3) / 1e9 / world, "blocking_call_value": e2e_blocking},
             "roofline": roof, "cpu_baseline": cpu, "loss": float(loss),
         }

@@ -70,6 +70,9 @@ _SIGS = {
     "hulc2_conv2d_dgrad": [C.POINTER(ConvArgs)],
     "hulc2_permute_conv_weight": [P, P, I, I, I, I, I, I],
     "hulc2_pack_frames_bf16": [P, P, I, I, I, I],
+    "hulc2_frames_u8_pack_bf16": [P, P, P, P, P, I, I, I, I, I],
+    "hulc2_frames_u8_to_f32": [P, P, P, P, P, I, I, I, I, I],
+    "hulc2_window_gather_f32": [P, P, P, P, I, I, I, I],
     "hulc2_convb_pack_weight": [P, P, I, I, I, I, I, I],
     "hulc2_convb_fwd": [C.POINTER(ConvbArgs)],
     "hulc2_convb_dgrad": [C.POINTER(ConvbArgs)],
@@ -196,12 +199,22 @@ def profile_end() -> dict:
     return out
 
 
+_AUTO_KEY = {"hulc2_f32_to_bf16": (2,), "hulc2_f32_to_bf16_2d": (4, 5), "hulc2_axpy": (2,), "hulc2_copy2d": (4, 5), "hulc2_colsum": (2, 3),
+             "hulc2_fill": (1,), "hulc2_layernorm_fwd": (14, 15), "hulc2_layernorm_bwd": (14, 15), "hulc2_dropout_mask_ep": (1,)}
+
+
+def _auto_key(name: str, args) -> str:
+    """Profile key of an untagged call: the entry point plus its size arguments (profiling only)."""
+    idx = _AUTO_KEY.get(name)
+    return name if idx is None else f"{name}[{','.join(str(args[i]) for i in idx)}]"
+
+
 def call(name: str, *args) -> None:
     """Invoke a C-ABI entry point on torch's current stream; raise RuntimeError on failure."""
     global launch_count, _tag
     lib = load_library()
     if _prof is not None:
-        key, flops = _tag if _tag is not None else (name, 0.0)
+        key, flops = _tag if _tag is not None else (_auto_key(name, args), 0.0)
         _tag = None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

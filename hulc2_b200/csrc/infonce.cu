@@ -9,14 +9,17 @@
 namespace {
 
 struct Ws {
-  float *imn, *txn, *sim, *rlse, *clse, *inorm, *tnorm;
+  float *imn, *txn, *sim, *rlse, *clse, *inorm, *tnorm, *dsm;
 };
+// intermediates live in shared memory when they fit (B <= ~140 at D = 32: every shipped batch size), else in the workspace
 __device__ __forceinline__ Ws carve(float* w, int B, int D) {
   Ws s;
   s.imn = w; s.txn = s.imn + (long long)B * D; s.sim = s.txn + (long long)B * D;
   s.rlse = s.sim + (long long)B * B; s.clse = s.rlse + B; s.inorm = s.clse + B; s.tnorm = s.inorm + B;
+  s.dsm = s.tnorm + B;
   return s;
 }
+extern __shared__ __align__(16) float infonce_smem[];
 
 __device__ void infonce_forward_phases(const float* img, const float* txt, const unsigned char* use, float scale, int B, int D,
                                        const Ws& w) {
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(512) infonce_fwd_kernel(const float* __restric
                                    const unsigned char* __restrict__ use, const float* __restrict__ logit_scale,
                                    float* __restrict__ loss, int B, int D, float* __restrict__ wsp) {
   __shared__ float red[32];
-  Ws w = carve(wsp, B, D);
+  Ws w = carve(wsp ? wsp : infonce_smem, B, D);
   infonce_forward_phases(img, txt, use, expf(logit_scale[0]), B, D, w);
   float acc = 0.f, cnt = 0.f;
   for (int r = threadIdx.x; r < B; r += blockDim.x)
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(512) infonce_bwd_kernel(const float* __restric
                                    const float* __restrict__ gout, float* __restrict__ dimg, float* __restrict__ dtxt,
                                    float* __restrict__ dlogit_scale, int B, int D, float* __restrict__ wsp) {
   __shared__ float red[32];
-  Ws w = carve(wsp, B, D);
+  Ws w = carve(wsp ? wsp : infonce_smem, B, D);
   const float scale = expf(logit_scale[0]);
   infonce_forward_phases(img, txt, use, scale, B, D, w);
   float cnt = 0.f;
@@ -85,9 +88,10 @@ __global__ void __launch_bounds__(512) infonce_bwd_kernel(const float* __restric
   float dsc = 0.f;
   for (int i = threadIdx.x; i < B * B; i += blockDim.x) {
     float dv = dsim(i / B, i % B);
+    w.dsm[i] = dv;
     if (dv != 0.f) dsc += dv * w.sim[i];
   }
-  dsc = block_sum(dsc, red);
+  dsc = block_sum(dsc, red);            // (block_sum's barriers also publish dsm)
   if (threadIdx.x == 0 && dlogit_scale) dlogit_scale[0] += dsc;  // d/d(log scale) = sum dsim*sim
   // gradients wrt the normalised features, then through x/||x||
   for (int i = threadIdx.x; i < B * D; i += blockDim.x) {
@@ -95,8 +99,8 @@ __global__ void __launch_bounds__(512) infonce_bwd_kernel(const float* __restric
     float a = 0.f, b = 0.f;
     for (int c = 0; c < B; ++c) {
       if (use && (!use[c] || !use[r])) continue;
-      a = fmaf(dsim(r, c), w.txn[(long long)c * D + d], a);
-      b = fmaf(dsim(c, r), w.imn[(long long)c * D + d], b);
+      a = fmaf(w.dsm[(long long)r * B + c], w.txn[(long long)c * D + d], a);
+      b = fmaf(w.dsm[(long long)c * B + r], w.imn[(long long)c * D + d], b);
     }
     dimg[i] = scale * a;   // temporarily d(imn)
     dtxt[i] = scale * b;   // temporarily d(txn)
@@ -116,7 +120,8 @@ __global__ void __launch_bounds__(512) infonce_bwd_kernel(const float* __restric
   }
 }
 
-long long ws_floats(int B, int D) { return 2LL * B * D + (long long)B * B + 4LL * B; }
+long long ws_floats(int B, int D) { return 2LL * B * D + 2LL * B * B + 4LL * B; }
+const long long kSmemMax = 200 * 1024;
 
 }  // namespace
 
@@ -125,7 +130,15 @@ extern "C" {
 int hulc2_infonce_fwd(const float* img, const float* txt, const unsigned char* use, const float* logit_scale, float* loss,
                       int B, int D, void* workspace, long long workspace_bytes, cudaStream_t st) {
   if (B <= 0) return HULC2_OK;
-  if (!workspace || workspace_bytes < ws_floats(B, D) * (long long)sizeof(float)) { hulc2_set_error("infonce: workspace too small"); return HULC2_EWORKSPACE; }
+  const long long need = ws_floats(B, D) * (long long)sizeof(float);
+  if (need <= kSmemMax) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(infonce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax); attr = true; }
+    infonce_fwd_kernel<<<1, 512, need, st>>>(img, txt, use, logit_scale, loss, B, D, nullptr);
+    HULC2_CHECK_LAUNCH();
+    return HULC2_OK;
+  }
+  if (!workspace || workspace_bytes < need) { hulc2_set_error("infonce: workspace too small"); return HULC2_EWORKSPACE; }
   infonce_fwd_kernel<<<1, 512, 0, st>>>(img, txt, use, logit_scale, loss, B, D, (float*)workspace);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
@@ -134,7 +147,15 @@ int hulc2_infonce_bwd(const float* img, const float* txt, const unsigned char* u
                       float* dimg, float* dtxt, float* dlogit_scale, int B, int D, void* workspace, long long workspace_bytes,
                       cudaStream_t st) {
   if (B <= 0) return HULC2_OK;
-  if (!workspace || workspace_bytes < ws_floats(B, D) * (long long)sizeof(float)) { hulc2_set_error("infonce: workspace too small"); return HULC2_EWORKSPACE; }
+  const long long need = ws_floats(B, D) * (long long)sizeof(float);
+  if (need <= kSmemMax) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(infonce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax); attr = true; }
+    infonce_bwd_kernel<<<1, 512, need, st>>>(img, txt, use, logit_scale, gout, dimg, dtxt, dlogit_scale, B, D, nullptr);
+    HULC2_CHECK_LAUNCH();
+    return HULC2_OK;
+  }
+  if (!workspace || workspace_bytes < need) { hulc2_set_error("infonce: workspace too small"); return HULC2_EWORKSPACE; }
   infonce_bwd_kernel<<<1, 512, 0, st>>>(img, txt, use, logit_scale, gout, dimg, dtxt, dlogit_scale, B, D, (float*)workspace);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;

@@ -178,6 +178,99 @@ __global__ void spatial_softmax_kernel(const T* __restrict__ x, const float* __r
   if (dtemp) atomicAdd(dtemp, -dt * invT * invT);
 }
 
+// bf16 trunk variant: the whole frame [HW][C] is staged in shared memory with 16-byte loads (one HBM read), every pass
+// (max, sums, gradient) runs from shared memory, and the gradient is written back in place and stored with 16-byte
+// stores (one HBM write).  Thread (cp, g): channel pair cp = tid % (C/2), position group g of G = blockDim / (C/2).
+template <bool BWD>
+__global__ void __launch_bounds__(256) ssm_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ x_map,
+                                                       const float* __restrict__ y_map, const float* __restrict__ temperature,
+                                                       float* __restrict__ out, const float* __restrict__ dout,
+                                                       __nv_bfloat16* __restrict__ dx, float* __restrict__ dtemp, int HW, int C,
+                                                       int relu_mask) {
+  extern __shared__ __align__(16) unsigned char ssm_raw[];
+  __nv_bfloat162* tile = reinterpret_cast<__nv_bfloat162*>(ssm_raw);               // [HW][C/2]
+  const int C2 = C >> 1, G = blockDim.x / C2;
+  float* red = reinterpret_cast<float*>(ssm_raw + (((size_t)HW * C * 2 + 15) & ~(size_t)15));   // [6][G][C2]
+  float* maps = red + 6 * G * C2;                                                   // x_map | y_map
+  const int n16 = HW * C / 8;
+  const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)blockIdx.x * HW * C);
+  for (int q = threadIdx.x; q < n16; q += blockDim.x) reinterpret_cast<uint4*>(ssm_raw)[q] = __ldg(src + q);
+  for (int q = threadIdx.x; q < HW; q += blockDim.x) { maps[q] = x_map[q]; maps[HW + q] = y_map[q]; }
+  const float invT = 1.f / temperature[0];
+  __syncthreads();
+  const int cp = threadIdx.x % C2, g = threadIdx.x / C2;
+  const bool active = g < G;
+  float m0 = -INFINITY, m1 = -INFINITY;
+  if (active)
+    for (int i = g; i < HW; i += G) {
+      const float2 v = __bfloat1622float2(tile[i * C2 + cp]);
+      m0 = fmaxf(m0, v.x * invT); m1 = fmaxf(m1, v.y * invT);
+    }
+  if (active) { red[g * C2 + cp] = m0; red[(G + g) * C2 + cp] = m1; }
+  __syncthreads();
+  if (active)
+    for (int k = 0; k < G; ++k) { m0 = fmaxf(m0, red[k * C2 + cp]); m1 = fmaxf(m1, red[(G + k) * C2 + cp]); }
+  __syncthreads();
+  float se0 = 0.f, sx0 = 0.f, sy0 = 0.f, se1 = 0.f, sx1 = 0.f, sy1 = 0.f;
+  if (active)
+    for (int i = g; i < HW; i += G) {
+      const float2 v = __bfloat1622float2(tile[i * C2 + cp]);
+      const float xm = maps[i], ym = maps[HW + i];
+      const float e0 = expf(v.x * invT - m0), e1 = expf(v.y * invT - m1);
+      se0 += e0; sx0 += e0 * xm; sy0 += e0 * ym;
+      se1 += e1; sx1 += e1 * xm; sy1 += e1 * ym;
+    }
+  if (active) {
+    float* r = red + g * C2 + cp;
+    r[0] = se0; r[G * C2] = sx0; r[2 * G * C2] = sy0; r[3 * G * C2] = se1; r[4 * G * C2] = sx1; r[5 * G * C2] = sy1;
+  }
+  __syncthreads();
+  if (active) {
+    se0 = sx0 = sy0 = se1 = sx1 = sy1 = 0.f;
+    for (int k = 0; k < G; ++k) {
+      const float* r = red + k * C2 + cp;
+      se0 += r[0]; sx0 += r[G * C2]; sy0 += r[2 * G * C2]; se1 += r[3 * G * C2]; sx1 += r[4 * G * C2]; sy1 += r[5 * G * C2];
+    }
+  }
+  const float inv0 = active ? 1.f / se0 : 0.f, inv1 = active ? 1.f / se1 : 0.f;
+  const float ex0 = sx0 * inv0, ey0 = sy0 * inv0, ex1 = sx1 * inv1, ey1 = sy1 * inv1;
+  if (!BWD) {
+    if (active && g == 0)
+      *reinterpret_cast<float4*>(out + (size_t)blockIdx.x * 2 * C + 4 * cp) = make_float4(ex0, ey0, ex1, ey1);
+    return;
+  }
+  float dt = 0.f;
+  if (active) {
+    const float4 gq = *reinterpret_cast<const float4*>(dout + (size_t)blockIdx.x * 2 * C + 4 * cp);   // (gx0, gy0, gx1, gy1)
+    for (int i = g; i < HW; i += G) {
+      const float2 v = __bfloat1622float2(tile[i * C2 + cp]);
+      const float xm = maps[i], ym = maps[HW + i];
+      const float p0 = expf(v.x * invT - m0) * inv0, p1 = expf(v.y * invT - m1) * inv1;
+      const float dl0 = p0 * (gq.x * (xm - ex0) + gq.y * (ym - ey0)), dl1 = p1 * (gq.z * (xm - ex1) + gq.w * (ym - ey1));
+      dt += dl0 * v.x + dl1 * v.y;
+      float o0 = dl0 * invT, o1 = dl1 * invT;
+      if (relu_mask) { if (!(v.x > 0.f)) o0 = 0.f; if (!(v.y > 0.f)) o1 = 0.f; }
+      tile[i * C2 + cp] = __floats2bfloat162_rn(o0, o1);        // only this thread ever touches element (i, cp)
+    }
+  }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(dx + (size_t)blockIdx.x * HW * C);
+  for (int q = threadIdx.x; q < n16; q += blockDim.x) dst[q] = reinterpret_cast<const uint4*>(ssm_raw)[q];
+  if (dtemp) {
+    dt = block_sum(dt, red);
+    if (threadIdx.x == 0) atomicAdd(dtemp, -dt * invT * invT);
+  }
+}
+
+static size_t ssm_bf16_smem(int HW, int C) {
+  const int C2 = C / 2, G = 256 / C2;
+  return (((size_t)HW * C * 2 + 15) & ~(size_t)15) + (size_t)(6 * G * C2 + 2 * HW) * sizeof(float);
+}
+// served when channel pairs tile a 256-thread block, rows are 16-byte multiples and 2 frames fit one SM's shared memory
+static bool ssm_bf16_ok(int HW, int C) {
+  return C >= 8 && C % 8 == 0 && C <= 512 && 256 % (C / 2) == 0 && ssm_bf16_smem(HW, C) <= 100 * 1024;
+}
+
 }  // namespace
 
 extern "C" {
@@ -239,6 +332,14 @@ int hulc2_spatial_softmax_fwd_bf16(const void* x, const float* x_map, const floa
                                    int F, int HW, int C, cudaStream_t st) {
   if (F <= 0) return HULC2_OK;
   if (!ssm_threads(C)) { hulc2_set_error("spatial_softmax: C must be <= 256"); return HULC2_EINVAL; }
+  if (ssm_bf16_ok(HW, C)) {
+    const size_t smem = ssm_bf16_smem(HW, C);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(ssm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
+    ssm_bf16_kernel<false><<<F, 256, smem, st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, out, nullptr, nullptr, nullptr, HW, C, 0);
+    HULC2_CHECK_LAUNCH();
+    return HULC2_OK;
+  }
   int G = 256 / C;
   spatial_softmax_kernel<false, __nv_bfloat16><<<F, 256, 3 * G * C * sizeof(float), st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, out,
                                                                                           nullptr, nullptr, nullptr, HW, C, 0);
@@ -251,6 +352,15 @@ int hulc2_spatial_softmax_bwd_bf16(const void* x, const float* x_map, const floa
                                    cudaStream_t st) {
   if (F <= 0) return HULC2_OK;
   if (!ssm_threads(C)) { hulc2_set_error("spatial_softmax: C must be <= 256"); return HULC2_EINVAL; }
+  if (ssm_bf16_ok(HW, C)) {
+    const size_t smem = ssm_bf16_smem(HW, C);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(ssm_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
+    ssm_bf16_kernel<true><<<F, 256, smem, st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, nullptr, dout, (__nv_bfloat16*)dx, dtemperature,
+                                                HW, C, relu_mask);
+    HULC2_CHECK_LAUNCH();
+    return HULC2_OK;
+  }
   int G = 256 / C;
   spatial_softmax_kernel<true, __nv_bfloat16><<<F, 256, 3 * G * C * sizeof(float), st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, nullptr,
                                                                                          dout, (__nv_bfloat16*)dx, dtemperature, HW, C, relu_mask);

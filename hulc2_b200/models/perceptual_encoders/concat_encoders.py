@@ -116,24 +116,43 @@ class ConcatEncoders(nn.Module):
                 raise ValueError(f"camera '{key}' is missing from some modalities; encode them separately")
             return vals
 
-        rgb_static = cam(imgs, "rgb_static")
-        s, c, h, w = rgb_static[0].shape[1:]
-        b = sum(t.shape[0] for t in rgb_static)
+        def frames(dicts, key):
+            """Per modality: fp32 [B,S,C,H,W] (the reference batch contract) -> [B*S,C,H,W]; uint8 [B,S,H,W,C] (frames as
+            the dataset stores them, optional ``<key>_shift`` int32 [B,S,2] RandomShiftsAug draw) or a ready
+            ``ops.U8Frames`` (window gather from a resident store) -> U8Frames, converted inside the trunk."""
+            vals = cam(dicts, key)
+            if vals is None:
+                return None, None
+            out, bs = [], []
+            for d, t in zip(dicts, vals):
+                if isinstance(t, ops.U8Frames):
+                    out.append(t)
+                    bs.append((t.F // t.S, t.S))
+                elif t.dtype == torch.uint8:
+                    if t.dim() == 4:                      # depth-like single channel [B,S,H,W] is not a uint8 format
+                        raise ValueError(f"uint8 camera '{key}' must be [B,S,H,W,C]")
+                    shift = d.get(key + "_shift")
+                    out.append(ops.U8Frames(t.reshape(-1, *t.shape[2:]), None if shift is None else shift.reshape(-1, 2), S=t.shape[1]))
+                    bs.append((t.shape[0], t.shape[1]))
+                else:
+                    chw = t.shape[2:] if t.dim() == 5 else (1, *t.shape[2:])
+                    out.append(t.reshape(-1, *chw))
+                    bs.append((t.shape[0], t.shape[1]))
+            return tuple(out), bs
 
-        def frames(ts, ch, hh, ww):
-            return tuple(t.reshape(-1, ch, hh, ww) for t in ts)
-
-        encs = [(self.rgb_static_encoder, frames(rgb_static, c, h, w))]
-        depth_static = cam(depth_imgs, "depth_static")
+        rgb_static, bs = frames(imgs, "rgb_static")
+        s = bs[0][1]
+        b = sum(n for n, _ in bs)
+        encs = [(self.rgb_static_encoder, rgb_static)]
+        depth_static, _ = frames(depth_imgs, "depth_static")
         if depth_static is not None:
-            encs.append((self.depth_static_encoder, frames(depth_static, 1, h, w)))
-        rgb_gripper = cam(imgs, "rgb_gripper")
+            encs.append((self.depth_static_encoder, depth_static))
+        rgb_gripper, _ = frames(imgs, "rgb_gripper")
         if rgb_gripper is not None:
-            cg, hg, wg = rgb_gripper[0].shape[2:]
-            encs.append((self.rgb_gripper_encoder, frames(rgb_gripper, cg, hg, wg)))
-            depth_gripper = cam(depth_imgs, "depth_gripper")
+            encs.append((self.rgb_gripper_encoder, rgb_gripper))
+            depth_gripper, _ = frames(depth_imgs, "depth_gripper")
             if depth_gripper is not None:
-                encs.append((self.depth_gripper_encoder, frames(depth_gripper, 1, hg, wg)))
+                encs.append((self.depth_gripper_encoder, depth_gripper))
         feats = [enc.features(x if len(x) > 1 else x[0]) for enc, x in encs]
         gammas = [enc.ln.weight for enc, _ in encs]
         betas = [enc.ln.bias for enc, _ in encs]

@@ -480,30 +480,87 @@ def convb_wgrad(x, dy, F, C, H, W, Cout, k, stride, dw_shape, dw_layout=0, name=
     return dw, db
 
 
+class U8Frames:
+    """Camera frames as the dataset stores them: uint8 HWC ``[N,H,W,C]`` (episode_utils.py:61-86), plus what the
+    reference's dataloader workers would apply before the encoder sees them -- the window slice with
+    pad_with_repetition (``win_start [B]`` int64 / ``win_len [B]`` int32 into a resident frame store;
+    base_dataset.py:121-163) and the RandomShiftsAug draw (``shift [F,2]`` int32 = (dx,dy) in [-pad,pad];
+    transforms.py:85-106).  Scale + Normalize(0.5,0.5) always apply.  Quacks like an NCHW tensor for shape queries;
+    the conversion happens inside the trunk's pack kernel (bf16) or ``to_f32`` (fp32 precision)."""
+
+    def __init__(self, u8: torch.Tensor, shift: Optional[torch.Tensor] = None, win_start: Optional[torch.Tensor] = None,
+                 win_len: Optional[torch.Tensor] = None, S: int = 1):
+        if u8.dtype != torch.uint8 or u8.dim() != 4:
+            raise ValueError("U8Frames expects a uint8 [N,H,W,C] tensor")
+        if not u8.is_cuda:
+            raise RuntimeError("hulc2_b200: frames must be CUDA tensors (no CPU fallback)")
+        self.u8 = u8.contiguous()
+        self.S = int(S)
+        self.win_start = None if win_start is None else win_start.to(torch.int64).contiguous()
+        self.win_len = None if win_len is None else win_len.to(torch.int32).contiguous()
+        self.F = int(self.win_start.numel()) * self.S if self.win_start is not None else int(u8.shape[0])
+        self.shift = None if shift is None else shift.to(torch.int32).reshape(-1, 2).contiguous()
+        if self.shift is not None and self.shift.shape[0] != self.F:
+            raise ValueError(f"shift must hold one (dx,dy) per output frame: {tuple(self.shift.shape)} vs F={self.F}")
+        self.device = u8.device
+
+    @property
+    def shape(self):
+        _, H, W, C = self.u8.shape
+        return (self.F, C, H, W)
+
+    def dim(self) -> int:
+        return 4
+
+    def _args(self):
+        F_, C, H, W = self.shape
+        return (self.u8.data_ptr(), _p(self.win_start), _p(self.win_len), _p(self.shift)), (F_, self.S, C, H, W)
+
+    def to_f32(self) -> torch.Tensor:
+        """fp32 NCHW frames in [-1,1]: exactly the tensor the reference's dataloader would have produced."""
+        F_, C, H, W = self.shape
+        out = torch.empty(F_, C, H, W, device=self.device, dtype=torch.float32)
+        ptrs, dims = self._args()
+        _lib.tag(f"frames_u8_to_f32[F={F_},{C}x{H}x{W}]", 0.0)
+        call("hulc2_frames_u8_to_f32", *ptrs, out.data_ptr(), *dims)
+        return out
+
+    def pack_into(self, xs_ptr: int) -> None:
+        F_, C, H, W = self.shape
+        ptrs, dims = self._args()
+        _lib.tag(f"frames_u8_pack[F={F_},{C}x{H}x{W}]", 0.0)
+        call("hulc2_frames_u8_pack_bf16", *ptrs, xs_ptr, *dims)
+
+
 def _frame_groups(x):
-    """A frame operand is one NCHW tensor or a tuple of them (the same camera of several modalities, encoded by one
-    trunk call).  -> (list of contiguous fp32 [F_i,C,H,W] tensors, (F_total, C, H, W))."""
-    groups = [_f32(t).contiguous() for t in (x if isinstance(x, (tuple, list)) else (x,))]
-    shp = groups[0].shape[1:]
-    assert all(t.dim() == 4 and t.shape[1:] == shp for t in groups), "frame groups must share C,H,W"
+    """A frame operand is one NCHW tensor, a ``U8Frames``, or a tuple of them (the same camera of several modalities,
+    encoded by one trunk call).  -> (list of contiguous fp32 [F_i,C,H,W] tensors / U8Frames, (F_total, C, H, W))."""
+    groups = [t if isinstance(t, U8Frames) else _f32(t).contiguous() for t in (x if isinstance(x, (tuple, list)) else (x,))]
+    shp = tuple(groups[0].shape[1:])
+    assert all(t.dim() == 4 and tuple(t.shape[1:]) == shp for t in groups), "frame groups must share C,H,W"
     return groups, (sum(t.shape[0] for t in groups), *shp)
 
 
 def _frames_tensor(x) -> torch.Tensor:
     groups, _ = _frame_groups(x)
+    groups = [t.to_f32() if isinstance(t, U8Frames) else t for t in groups]
     return groups[0] if len(groups) == 1 else torch.cat(groups, 0)   # fp32 reference-precision path only
 
 
 def pack_frames(x) -> torch.Tensor:
-    """fp32 NCHW frames (one tensor or a tuple of frame groups) -> bf16 [F, H/4, W/4, 16*C] (space-to-depth by the
-    first conv's stride); groups are packed back to back, so no concatenated fp32 copy is ever made."""
+    """Frames (fp32 NCHW tensors or uint8 ``U8Frames``; one or a tuple of frame groups) -> bf16 [F, H/4, W/4, 16*C]
+    (space-to-depth by the first conv's stride); groups are packed back to back, so no concatenated fp32 copy is ever
+    made -- and for uint8 frames no fp32 frame exists at all."""
     groups, (F_, Cin, H, W) = _frame_groups(x)
     xs = _bf16(F_, H // 4, W // 4, 16 * Cin, device=groups[0].device)
     per_frame = (H // 4) * (W // 4) * 16 * Cin
     f0 = 0
     for t in groups:
-        _lib.tag(f"pack_frames[F={t.shape[0]},{Cin}x{H}x{W}]", 0.0)
-        call("hulc2_pack_frames_bf16", t.data_ptr(), xs.data_ptr() + 2 * f0 * per_frame, t.shape[0], Cin, H, W)
+        if isinstance(t, U8Frames):
+            t.pack_into(xs.data_ptr() + 2 * f0 * per_frame)
+        else:
+            _lib.tag(f"pack_frames[F={t.shape[0]},{Cin}x{H}x{W}]", 0.0)
+            call("hulc2_pack_frames_bf16", t.data_ptr(), xs.data_ptr() + 2 * f0 * per_frame, t.shape[0], Cin, H, W)
         f0 += t.shape[0]
     return xs
 

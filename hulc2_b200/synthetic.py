@@ -72,8 +72,10 @@ def synthetic_batch(
     return out
 
 
-def synthetic_batch_fast(B, S=32, seed=1, static_hw=(200, 200), device="cuda", modalities=("vis", "lang"), pin=False):
-    """Same shapes/ranges drawn with a torch generator (used for the full-size benchmark)."""
+def synthetic_batch_fast(B, S=32, seed=1, static_hw=(200, 200), device="cuda", modalities=("vis", "lang"), pin=False, frames="fp32"):
+    """Same shapes/ranges drawn with a torch generator (used for the full-size benchmark).  ``frames="uint8"`` gives the
+    cameras as the dataset stores them (uint8 ``[B,S,H,W,3]``) plus the RandomShiftsAug draw ``<cam>_shift`` int32
+    ``[B,S,2]`` (pad 10 static / 4 gripper, rand_shift.yaml); scale + normalise + shift then run on the device."""
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -91,7 +93,12 @@ def synthetic_batch_fast(B, S=32, seed=1, static_hw=(200, 200), device="cuda", m
         raw = U(B, S, 15)
         raw[..., 3:6] = U(B, S, 3, lo=-0.9 * math.pi / 2, hi=0.9 * math.pi / 2)
         d = {
-            "rgb_obs": {"rgb_static": U(B, S, 3, H, W), "rgb_gripper": U(B, S, 3, 84, 84)},
+            "rgb_obs": {"rgb_static": U(B, S, 3, H, W), "rgb_gripper": U(B, S, 3, 84, 84)} if frames == "fp32" else {
+                "rgb_static": torch.randint(0, 256, (B, S, H, W, 3), generator=g, device=dev, dtype=torch.uint8),
+                "rgb_static_shift": torch.randint(-10, 11, (B, S, 2), generator=g, device=dev, dtype=torch.int32),
+                "rgb_gripper": torch.randint(0, 256, (B, S, 84, 84, 3), generator=g, device=dev, dtype=torch.uint8),
+                "rgb_gripper_shift": torch.randint(-4, 5, (B, S, 2), generator=g, device=dev, dtype=torch.int32),
+            },
             "depth_obs": {},
             "robot_obs": U(B, S, 8),
             "actions": actions,

@@ -125,6 +125,27 @@ int hulc2_spatial_softmax_bwd_bf16(const void* x, const float* x_map, const floa
 int hulc2_nhwc_bf16_to_nchw(const void* src, float* dst, int F, int HW, int C, hulc2_stream_t stream);
 int hulc2_nchw_to_nhwc_bf16(const float* src, void* dst, int F, int HW, int C, const void* mask, hulc2_stream_t stream);
 
+/* ------------------------------------------------------------------ datamodule: uint8 frames -> trunk operand (csrc/frames.cu)
+ * Replaces, per camera, what the reference's CPU dataloader workers do for every window:
+ *   window slice + pad_with_repetition   hulc2/datasets/base_dataset.py:121-163, npz_dataset.py:117-143
+ *   HWC uint8 -> CHW                     hulc2/datasets/utils/episode_utils.py:61-86 (process_rgb)
+ *   RandomShiftsAug(pad)                 hulc2/utils/transforms.py:85-106  (integer crop of the replicate-padded frame)
+ *   ScaleImageTensor + Normalize(.5,.5)  hulc2/utils/transforms.py:8-19, conf/datamodule/transforms/rand_shift.yaml:2-10
+ * store  : uint8 [N,H,W,C] frames (an episode store resident in HBM, or the B*S frames of one batch);
+ * win_start[B] (int64, first frame of window b) / win_len[B] (int32 valid steps, null = S): output frame f=(b,t) reads
+ *          store[win_start[b] + min(t, win_len[b]-1)]; win_start null = identity (frame f reads store[f]);
+ * shift  : int32 [F,2] = (dx,dy) per output frame, each in [-pad,pad] (the reference's randint draw minus pad), null = none:
+ *          out[y,x] = in[clamp(y+dy,0,H-1), clamp(x+dx,0,W-1)];  value = ((u8/255) - 0.5)/0.5 in fp32, reference op order.
+ * pack_bf16 writes the packed-frames layout of hulc2_pack_frames_bf16 directly; to_f32 writes fp32 NCHW [F,C,H,W].
+ * window_gather_f32: out[b,t,:] = store[win_start[b]+t, :] (fp32 [N,D]) for t < win_len[b]; padded steps by mode:
+ *          0 repeat the last valid row, 1 zeros, 2 zeros except the last component which repeats (relative actions). */
+int hulc2_frames_u8_pack_bf16(const void* store, const long long* win_start, const int* win_len, const int* shift, void* xs,
+                              int F, int S, int C, int H, int W, hulc2_stream_t stream);
+int hulc2_frames_u8_to_f32(const void* store, const long long* win_start, const int* win_len, const int* shift, float* out,
+                           int F, int S, int C, int H, int W, hulc2_stream_t stream);
+int hulc2_window_gather_f32(const float* store, const long long* win_start, const int* win_len, float* out, int B, int S, int D,
+                            int mode, hulc2_stream_t stream);
+
 /* ------------------------------------------------------------------ small data movement
  * copy2d: dst[r*ldd + c] (+)= src[r*lds + c];  colsum: out[c] (+)= sum_r x[r*ld + c] (bias gradients);
  * nhwc<->nchw per-frame transposes (nn.Flatten order of nature_cnn, vision_network_gripper.py:22-23). */
