@@ -25,6 +25,14 @@ import torch  # noqa: E402
 
 WINDOW = 32
 FLOPS_PER_WINDOW_FWD_BWD = 13.01e9  # SURVEY.md 8d (torch FlopCounterMode on the reference graph)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the conv trunk at
+# the bench shape (profiles/r01_f_ncu_conv_trunk.md); keyed like the per-call profile
+NCU_TRAFFIC_BYTES = {
+    "convb_fwd[c1,F=4096,48x50x50->32,k2s1]": 1.577e9, "convb_fwd[c2,F=4096,32x49x49->64,k4s2]": 0.867e9,
+    "convb_fwd[c3,F=4096,64x23x23->64,k3s1]": 0.466e9, "convb_wgrad[c3,F=4096,64x23x23->64,k3s1]": 0.514e9,
+    "convb_dgrad[c3,F=4096,64x23x23<-64,k3s1]": 0.753e9, "convb_wgrad[c2,F=4096,32x49x49->64,k4s2]": 0.899e9,
+    "convb_dgrad[c2,F=4096,32x49x49<-64,k4s2]": 1.702e9, "convb_wgrad[c1,F=4096,48x50x50->32,k2s1]": 1.617e9,
+}
 
 
 def parse():
@@ -265,12 +273,23 @@ def run_b200(args):
         top = max(recs.values(), key=lambda r: r["ms"]) if recs else None
         total_ms = sum(r["ms"] for r in recs.values())
         if top:
-            achieved = (top["flops"] / top["calls"]) / (top["ms"] / top["calls"] * 1e-3) / 1e12 if top["flops"] else 0.0
-            roof = {"bound": "tensor", "kernel": top["key"], "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
-                    "share_of_step": top["ms"] / total_ms if total_ms else None, "calls_per_step": top["calls"],
-                    "avg_ms": top["ms"] / top["calls"],
-                    "step_tflops": 2 * B * FLOPS_PER_WINDOW_FWD_BWD / (ms * 1e-3) / 1e12}
+            sec = top["ms"] / top["calls"] * 1e-3
+            tflops = (top["flops"] / top["calls"]) / sec / 1e12 if top["flops"] else 0.0
+            gbs = (top.get("bytes", 0.0) / top["calls"]) / sec / 1e9
+            # which roof bounds this kernel: algorithmic FLOP/byte against the machine's ridge point (measured peaks)
+            ridge = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+            intensity = top["flops"] / top["bytes"] if top.get("bytes") else float("inf")
+            if intensity < ridge:
+                roof = {"bound": "hbm", "kernel": top["key"], "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": gbs / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC_BYTES.get(top["key"]),
+                        "algorithmic_bytes_per_launch": top["bytes"] / top["calls"], "flop_per_byte": intensity,
+                        "ridge_flop_per_byte": ridge, "tflops": tflops}
+            else:
+                roof = {"bound": "tensor", "kernel": top["key"], "achieved": tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                        "frac": tflops / peaks["tflops"], "traffic": None}
+            roof.update({"peak_source": peaks["src"], "share_of_step": top["ms"] / total_ms if total_ms else None,
+                         "calls_per_step": top["calls"], "avg_ms": top["ms"] / top["calls"],
+                         "step_tflops": 2 * B * FLOPS_PER_WINDOW_FWD_BWD / (ms * 1e-3) / 1e12})
             tops = sorted(recs.values(), key=lambda r: -r["ms"])[:8]
             roof["top_kernels"] = [{"key": r["key"], "ms": round(r["ms"], 3), "calls": r["calls"]} for r in tops]
 

@@ -116,6 +116,15 @@ _SIGS = {
     "hulc2_infonce_bwd": [P, P, P, P, P, P, P, P, I, I, P, LL],
     "hulc2_rnn_relu_fwd": [P, P, P, P, I, I, I, I, P, LL],
     "hulc2_rnn_relu_bwd": [P, P, P, P, I, I, I, I, P, LL],
+    "hulc2_gru_cell_fwd": [P, LL, P, P, P, P, I, I],
+    "hulc2_gru_cell_bwd": [P, P, P, P, P, LL, P, P, I, I],
+    "hulc2_lstm_cell_fwd": [P, LL, P, P, P, P, P, I, I],
+    "hulc2_lstm_cell_bwd": [P, P, P, P, P, P, P, LL, P, I, I],
+    "hulc2_gauss_state_fwd": [P, P, P, I, I],
+    "hulc2_gauss_state_bwd": [P, P, P, P, I, I],
+    "hulc2_gauss_rsample": [P, P, P, P, LL],
+    "hulc2_gauss_kl_fwd": [P, P, P, P, P, I, I, F, F],
+    "hulc2_gauss_kl_bwd": [P, P, P, P, P, P, P, P, P, I, I, F, F],
     "hulc2_adam_step": [P, P, P, P, LL, F, F, F, F, F, I, F],
     "hulc2_philox_uniform": [P, LL, C.c_ulonglong, C.c_ulonglong],
     "hulc2_dropout_mask": [P, LL, F, C.c_ulonglong, C.c_ulonglong],
@@ -173,11 +182,11 @@ _prof = None   # list of (key, flops, start_event, end_event) while profiling
 _tag = None    # (key, flops) annotation for the next call
 
 
-def tag(key: str, flops: float = 0.0) -> None:
-    """Annotates the next C-ABI call (shape key + algorithmic FLOPs) for bench.py's per-kernel timing."""
+def tag(key: str, flops: float = 0.0, nbytes: float = 0.0) -> None:
+    """Annotates the next C-ABI call (shape key + algorithmic FLOPs and HBM bytes) for bench.py's per-kernel timing."""
     global _tag
     if _prof is not None:
-        _tag = (key, flops)
+        _tag = (key, flops, nbytes)
 
 
 def profile_begin() -> None:
@@ -190,11 +199,12 @@ def profile_end() -> dict:
     global _prof, _tag
     torch.cuda.synchronize()
     out = {}
-    for key, flops, e0, e1 in _prof:
-        r = out.setdefault(key, {"key": key, "ms": 0.0, "calls": 0, "flops": 0.0})
+    for key, flops, nbytes, e0, e1 in _prof:
+        r = out.setdefault(key, {"key": key, "ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0})
         r["ms"] += e0.elapsed_time(e1)
         r["calls"] += 1
         r["flops"] += flops
+        r["bytes"] += nbytes
     _prof, _tag = None, None
     return out
 
@@ -214,13 +224,13 @@ def call(name: str, *args) -> None:
     global launch_count, _tag
     lib = load_library()
     if _prof is not None:
-        key, flops = _tag if _tag is not None else (_auto_key(name, args), 0.0)
+        key, flops, nbytes = _tag if _tag is not None else (_auto_key(name, args), 0.0, 0.0)
         _tag = None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = getattr(lib, name)(*args, stream())
         e1.record()
-        _prof.append((key, flops, e0, e1))
+        _prof.append((key, flops, nbytes, e0, e1))
     else:
         rc = getattr(lib, name)(*args, stream())
     launch_count += 1

@@ -451,7 +451,8 @@ def convb_fwd(x, wp, bias, F, C, H, W, Cout, k, stride, relu=True, name="conv") 
     y = _bf16(F, OH, OW, Cout, device=x.device)
     a = _cb(F, C, H, W, Cout, k, stride)
     a.x, a.w, a.bias, a.y, a.relu = x.data_ptr(), wp.data_ptr(), _p(bias), y.data_ptr(), int(relu)
-    _lib.tag(f"convb_fwd[{name},F={F},{C}x{H}x{W}->{Cout},k{k}s{stride}]", 2.0 * y.numel() * C * k * k)
+    _lib.tag(f"convb_fwd[{name},F={F},{C}x{H}x{W}->{Cout},k{k}s{stride}]", 2.0 * y.numel() * C * k * k,
+             2.0 * (x.numel() + y.numel()))
     call("hulc2_convb_fwd", C_byref(a))
     return y
 
@@ -462,7 +463,8 @@ def convb_dgrad(dy, w_oihw, xmask, F, C, H, W, Cout, k, stride, name="conv") -> 
     dx = _bf16(F, H, W, C, device=dy.device)
     a = _cb(F, C, H, W, Cout, k, stride)
     a.dy, a.w, a.dx, a.xmask = dy.data_ptr(), wp.data_ptr(), dx.data_ptr(), _p(xmask)
-    _lib.tag(f"convb_dgrad[{name},F={F},{C}x{H}x{W}<-{Cout},k{k}s{stride}]", 2.0 * dy.numel() * C * k * k)
+    _lib.tag(f"convb_dgrad[{name},F={F},{C}x{H}x{W}<-{Cout},k{k}s{stride}]", 2.0 * dy.numel() * C * k * k,
+             2.0 * (dy.numel() + dx.numel() * (2 if xmask is not None else 1)))
     call("hulc2_convb_dgrad", C_byref(a))
     return dx
 
@@ -475,7 +477,8 @@ def convb_wgrad(x, dy, F, C, H, W, Cout, k, stride, dw_shape, dw_layout=0, name=
     a = _cb(F, C, H, W, Cout, k, stride)
     a.x, a.dy, a.dw, a.db, a.dw_layout = x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), dw_layout
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-    _lib.tag(f"convb_wgrad[{name},F={F},{C}x{H}x{W}->{Cout},k{k}s{stride}]", 2.0 * dy.numel() * C * k * k)
+    _lib.tag(f"convb_wgrad[{name},F={F},{C}x{H}x{W}->{Cout},k{k}s{stride}]", 2.0 * dy.numel() * C * k * k,
+             2.0 * (F * H * W * C + dy.numel()))
     call("hulc2_convb_wgrad", C_byref(a))
     return dw, db
 
@@ -1060,6 +1063,155 @@ class RNNDecoderFunction(torch.autograd.Function):
             demb = torch.empty(B, S, Es, device=dev, dtype=torch.float32)
             call("hulc2_transpose01", dembT.data_ptr(), B * Es, Es, demb.data_ptr(), Es, S, B, Es, 0)
         return (dplan, demb, dgoal, None, dwi0, dwh0, db0, db0.clone(), dwi1, dwh1, db1, db1.clone())
+
+
+class GatedRNNDecoderFunction(torch.autograd.Function):
+    """2-layer nn.GRU / nn.LSTM decoder (decoders/utils/rnn.py:17-36) over x_t = [plan | emb_t | goal]
+    (logistic_decoder_rnn.py:262-268).  Same split of W_ih x_t into a per-window base term and a per-step embedding
+    term as the ReLU RNN.  Per step: one recurrent contraction h_{t-1} W_hh^T (+ b_hh) and one fused cell kernel
+    (csrc/cells.cu).  Returns time-major hidden states of the last layer [S,B,H], h_n [2,B,H] and c_n [2,B,H]
+    (LSTM; empty for GRU)."""
+
+    @staticmethod
+    def forward(ctx, kind, plan, emb, goal, h0, c0, wi0, wh0, bi0, bh0, wi1, wh1, bi1, bh1):
+        assert kind in ("gru", "lstm")
+        Gn = 3 if kind == "gru" else 4
+        plan, goal = _f32(plan).contiguous(), _f32(goal).contiguous()
+        B, S, Es = emb.shape
+        P, G = plan.shape[1], goal.shape[1]
+        H = wh0.shape[1]
+        GH = Gn * H
+        In = wi0.shape[1]
+        assert In == P + Es + G and wi0.shape[0] == GH and wh0.shape[0] == GH
+        dev = plan.device
+        embT = torch.empty(S, B, Es, device=dev, dtype=torch.float32)
+        assert emb.stride(2) == 1
+        call("hulc2_transpose01", emb.data_ptr(), emb.stride(0), emb.stride(1), embT.data_ptr(), Es, B, S, Es, 0)
+        # layer-0 input gates: per-window base (plan, goal, b_ih) broadcast over time + per-step embedding term
+        base = torch.empty(B, GH, device=dev, dtype=torch.float32)
+        gi = torch.empty(S, B, GH, device=dev, dtype=torch.float32)
+        gemm(B, GH, P, plan, P, 1, wi0, In, 1, base, GH, bias=bi0)
+        gemm(B, GH, G, goal, G, 1, wi0, In, 1, base, GH, b_off=P + Es, accumulate=True)
+        call("hulc2_copy2d", base.data_ptr(), 0, gi.data_ptr(), B * GH, S, B * GH, 0)
+        gemm(S * B, GH, Es, embT, Es, 1, wi0, In, 1, gi, GH, b_off=P, accumulate=True)
+        gh = torch.empty(B, GH, device=dev, dtype=torch.float32)
+        Hs, Cs, saves = [], [], []
+        hn = torch.empty(2, B, H, device=dev, dtype=torch.float32)
+        cn = torch.empty(2 if kind == "lstm" else 0, B, H, device=dev, dtype=torch.float32)
+        h0s = [h0[l].contiguous() if h0 is not None else None for l in range(2)]
+        c0s = [c0[l].contiguous() if c0 is not None else None for l in range(2)]
+        for l, (wi, wh, bi, bh) in enumerate(((wi0, wh0, bi0, bh0), (wi1, wh1, bi1, bh1))):
+            if l == 1:
+                gemm(S * B, GH, H, Hs[0], H, 1, wi, H, 1, gi, GH, bias=bi)
+            Hl = torch.empty(S, B, H, device=dev, dtype=torch.float32)
+            Cl = torch.empty(S, B, H, device=dev, dtype=torch.float32) if kind == "lstm" else None
+            sv = torch.empty(S, B, 4 * H, device=dev, dtype=torch.float32)
+            for t in range(S):
+                hp = Hl[t - 1] if t > 0 else h0s[l]
+                if hp is None:
+                    call("hulc2_copy2d", bh.data_ptr(), 0, gh.data_ptr(), GH, B, GH, 0)
+                else:
+                    gemm(B, GH, H, hp, H, 1, wh, H, 1, gh, GH, bias=bh)
+                _lib.tag(f"{kind}_cell_fwd[B={B},H={H}]")
+                if kind == "gru":
+                    call("hulc2_gru_cell_fwd", gi[t].data_ptr(), GH, gh.data_ptr(), _p(hp), Hl[t].data_ptr(), sv[t].data_ptr(), B, H)
+                else:
+                    cp = Cl[t - 1] if t > 0 else c0s[l]
+                    call("hulc2_lstm_cell_fwd", gi[t].data_ptr(), GH, gh.data_ptr(), _p(cp), Hl[t].data_ptr(), Cl[t].data_ptr(),
+                         sv[t].data_ptr(), B, H)
+            Hs.append(Hl)
+            Cs.append(Cl)
+            saves.append(sv)
+            call("hulc2_copy2d", Hl[S - 1].data_ptr(), B * H, hn[l].data_ptr(), B * H, 1, B * H, 0)
+            if kind == "lstm":
+                call("hulc2_copy2d", Cl[S - 1].data_ptr(), B * H, cn[l].data_ptr(), B * H, 1, B * H, 0)
+        empty = plan.new_empty(0)
+        ctx.save_for_backward(plan, embT, goal, wi0, wh0, wi1, wh1, Hs[0], Hs[1], saves[0], saves[1],
+                              *(Cs if kind == "lstm" else (empty, empty)),
+                              *(h if h is not None else empty for h in h0s), *(c if c is not None else empty for c in c0s))
+        ctx.kind, ctx.dims = kind, (B, S, Es, P, G, H, In)
+        ctx.has_h0, ctx.has_c0 = h0 is not None, c0 is not None
+        ctx.mark_non_differentiable(hn, cn)
+        return Hs[1], hn, cn
+
+    @staticmethod
+    def backward(ctx, dH1, _dhn, _dcn):
+        (plan, embT, goal, wi0, wh0, wi1, wh1, H0, H1, sv0, sv1, C0, C1, h00, h01, c00, c01) = ctx.saved_tensors
+        kind = ctx.kind
+        B, S, Es, P, G, H, In = ctx.dims
+        Gn = 3 if kind == "gru" else 4
+        GH = Gn * H
+        dev = plan.device
+        f32 = dict(device=dev, dtype=torch.float32)
+
+        def layer_bwd(dHs, Hl, Cl, sv, wh, h0l, c0l):
+            """-> dgi [S,B,GH] (gradient of the input gates), dW_hh, db_hh."""
+            dgi = torch.empty(S, B, GH, **f32)
+            dgh = torch.empty(S, B, GH, **f32) if kind == "gru" else dgi
+            rec = [torch.empty(B, H, **f32), torch.empty(B, H, **f32)]
+            dc = torch.empty(B, H, **f32) if kind == "lstm" else None
+            for t in range(S - 1, -1, -1):
+                hp = Hl[t - 1] if t > 0 else h0l
+                dhb = rec[(t + 1) & 1] if t < S - 1 else None
+                _lib.tag(f"{kind}_cell_bwd[B={B},H={H}]")
+                if kind == "gru":
+                    call("hulc2_gru_cell_bwd", dHs[t].data_ptr(), _p(dhb), sv[t].data_ptr(), _p(hp), dgi[t].data_ptr(), GH,
+                         dgh[t].data_ptr(), rec[t & 1].data_ptr(), B, H)
+                else:
+                    cp = Cl[t - 1] if t > 0 else c0l
+                    call("hulc2_lstm_cell_bwd", dHs[t].data_ptr(), _p(dhb), dc.data_ptr() if t < S - 1 else None, sv[t].data_ptr(),
+                         Cl[t].data_ptr(), _p(cp), dgi[t].data_ptr(), GH, dc.data_ptr(), B, H)
+                if t > 0:   # gradient into h_{t-1} through the recurrent contraction (h_0 itself needs no gradient)
+                    gemm(B, H, GH, dgh[t], GH, 1, wh, 1, H, rec[t & 1], H, accumulate=(kind == "gru"))
+            dwh = torch.empty_like(wh)
+            if S > 1:
+                gemm(GH, H, (S - 1) * B, dgh, 1, GH, Hl, 1, H, dwh, H, a_off=B * GH)
+            else:
+                call("hulc2_fill", dwh.data_ptr(), dwh.numel(), 0.0)
+            if h0l is not None:
+                gemm(GH, H, B, dgh, 1, GH, h0l, 1, H, dwh, H, accumulate=True)
+            dbh = torch.empty(GH, **f32)
+            colsum(dgh, GH, S * B, GH, dbh)
+            return dgi, dwh, dbh
+
+        dH1 = dH1.contiguous()
+        dg1, dwh1, dbh1 = layer_bwd(dH1, H1, C1 if kind == "lstm" else None, sv1, wh1,
+                                    h01 if ctx.has_h0 else None, c01 if ctx.has_c0 else None)
+        dwi1 = torch.empty_like(wi1)
+        gemm(GH, H, S * B, dg1, 1, GH, H0, 1, H, dwi1, H)
+        if kind == "gru":
+            dbi1 = torch.empty(GH, **f32)
+            colsum(dg1, GH, S * B, GH, dbi1)
+        else:
+            dbi1 = dbh1.clone()
+        dH0 = torch.empty(S, B, H, **f32)
+        gemm(S * B, H, GH, dg1, GH, 1, wi1, 1, H, dH0, H)
+        dg0, dwh0, dbh0 = layer_bwd(dH0, H0, C0 if kind == "lstm" else None, sv0, wh0,
+                                    h00 if ctx.has_h0 else None, c00 if ctx.has_c0 else None)
+        if kind == "gru":
+            dbi0 = torch.empty(GH, **f32)
+            colsum(dg0, GH, S * B, GH, dbi0)
+        else:
+            dbi0 = dbh0.clone()
+        dgsum = torch.empty(B, GH, **f32)
+        colsum(dg0, B * GH, S, B * GH, dgsum)                                   # sum over time
+        dwi0 = torch.empty_like(wi0)
+        gemm(GH, P, B, dgsum, 1, GH, plan, 1, P, dwi0, In)
+        gemm(GH, Es, S * B, dg0, 1, GH, embT, 1, Es, dwi0, In, c_off=P)
+        gemm(GH, G, B, dgsum, 1, GH, goal, 1, G, dwi0, In, c_off=P + Es)
+        dplan = dgoal = demb = None
+        if ctx.needs_input_grad[1]:
+            dplan = torch.empty(B, P, **f32)
+            gemm(B, P, GH, dgsum, GH, 1, wi0, 1, In, dplan, P)
+        if ctx.needs_input_grad[3]:
+            dgoal = torch.empty(B, G, **f32)
+            gemm(B, G, GH, dgsum, GH, 1, wi0, 1, In, dgoal, G, b_off=P + Es)
+        if ctx.needs_input_grad[2]:
+            dembT = torch.empty(S, B, Es, **f32)
+            gemm(S * B, Es, GH, dg0, GH, 1, wi0, 1, In, dembT, Es, b_off=P)
+            demb = torch.empty(B, S, Es, **f32)
+            call("hulc2_transpose01", dembT.data_ptr(), B * Es, Es, demb.data_ptr(), Es, S, B, Es, 0)
+        return (None, dplan, demb, dgoal, None, None, dwi0, dwh0, dbi0, dbh0, dwi1, dwh1, dbi1, dbh1)
 
 
 def _lib_precision() -> int:

@@ -279,6 +279,39 @@ int hulc2_rnn_select_kernel(int which);
  * clusters of 8 when H/128 of them fit, else with clusters of 4 when H/64 fit (a 148-SM B200 reports 15 clusters of 8) */
 int hulc2_rnn_cluster_capacity(int cluster_size);
 
+/* ------------------------------------------------------------------ gated recurrence cells (decoders/utils/rnn.py:17-36)
+ * One step of nn.GRU (gate order r,z,n) / nn.LSTM (i,f,g,o); the contractions are hulc2_gemm calls, these are the
+ * fused elementwise cells.  gi [B,G*H] (row stride ldgi) = W_ih x_t + b_ih, gh [B,G*H] dense = W_hh h_{t-1} + b_hh.
+ * GRU fwd: h = (1-z) n + z h_prev, save [B,4H] = r|z|n|gh_n.  GRU bwd: dh = dh_a + dh_b (either may be null) ->
+ *   dgi [B,3H] (row stride lddgi), dgh [B,3H], dh_prev [B,H] = dh*z (the recurrent GEMM then accumulates dgh W_hh).
+ * LSTM fwd: c = f c_prev + i g, h = o tanh(c), save [B,4H] = activated i|f|g|o.  LSTM bwd: dc (null = 0) is the
+ *   gradient into c_t from step t+1; writes dgates [B,4H] (row stride lddg; same for gi and gh) and dc_prev (may alias dc).
+ * h_prev / c_prev null = zeros (h_0 is None).  H and the row strides must be multiples of 4. */
+int hulc2_gru_cell_fwd(const float* gi, long long ldgi, const float* gh, const float* h_prev, float* h, float* save,
+                       int B, int H, hulc2_stream_t stream);
+int hulc2_gru_cell_bwd(const float* dh_a, const float* dh_b, const float* save, const float* h_prev, float* dgi,
+                       long long lddgi, float* dgh, float* dh_prev, int B, int H, hulc2_stream_t stream);
+int hulc2_lstm_cell_fwd(const float* gi, long long ldgi, const float* gh, const float* c_prev, float* h, float* c,
+                        float* save, int B, int H, hulc2_stream_t stream);
+int hulc2_lstm_cell_bwd(const float* dh_a, const float* dh_b, const float* dc, const float* save, const float* c,
+                        const float* c_prev, float* dgates, long long lddg, float* dc_prev, int B, int H,
+                        hulc2_stream_t stream);
+
+/* ------------------------------------------------------------------ continuous latent plan (distributions.py:28-29,55-59)
+ * state: x [B,2P] -> mean = x[:, :P], std = softplus(x[:, P:]) + 1e-4 (and its gradient);  rsample: mean + std*eps with
+ * caller-supplied standard-normal eps;  kl: beta*(alpha*KL(sg(pr)||pp) + (1-alpha)*KL(pr||sg(pp))) for diagonal normals,
+ * summed over P, mean over B (hulc2.py:444-466); gradients scaled by *gout (device scalar, null = 1), null outputs skipped. */
+int hulc2_gauss_state_fwd(const float* x, float* mean, float* std, int B, int P, hulc2_stream_t stream);
+int hulc2_gauss_state_bwd(const float* x, const float* dmean, const float* dstd, float* dx, int B, int P,
+                          hulc2_stream_t stream);
+int hulc2_gauss_rsample(const float* mean, const float* std, const float* eps, float* plan, long long n,
+                        hulc2_stream_t stream);
+int hulc2_gauss_kl_fwd(const float* pp_mean, const float* pp_std, const float* pr_mean, const float* pr_std, float* loss,
+                       int B, int P, float alpha, float beta, hulc2_stream_t stream);
+int hulc2_gauss_kl_bwd(const float* pp_mean, const float* pp_std, const float* pr_mean, const float* pr_std,
+                       const float* gout, float* dpp_mean, float* dpp_std, float* dpr_mean, float* dpr_std, int B, int P,
+                       float alpha, float beta, hulc2_stream_t stream);
+
 /* ------------------------------------------------------------------ optimizer + noise
  * Adam (torch.optim.Adam semantics, conf/model/optimizer/adam.yaml): one launch over a flat arena. */
 int hulc2_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
