@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--frames", default="uint8", choices=["uint8", "fp32"],
                     help="camera frames in the batch: uint8 HWC + RandomShiftsAug draw, scaled/normalised/shifted on the device "
                          "(datamodule kernel, SURVEY 8f-1), or the reference batch contract's fp32 NCHW tensors")
+    ap.add_argument("--workload", default="train", choices=["train", "rollout"],
+                    help="train = configs[1] (the headline metric); rollout = configs[4]: batched policy inference, --envs parallel "
+                         "environments, one re-plan + 29 plain control steps per bench step (a separate metric, never the default)")
+    ap.add_argument("--envs", type=int, default=1024)
     ap.add_argument("--dump-profile", default=None, help="write the per-call CUDA-event profile of one step to this JSON file")
     return ap.parse_args()
 
@@ -318,9 +322,112 @@ def run_b200(args):
         os._exit(0)
 
 
+# ----------------------------------------------------------------------------- configs[4]: batched rollout inference
+def run_rollout(args):
+    """N envs, S=1, replan_freq 30 -> one bench step = 1 re-plan + 29 plain control steps for all
+    envs through hulc2_b200.rollout.RolloutServer (two CUDA graphs).  `value`: observations already on the device;
+    `e2e`: every control step copies its uint8 camera frames + proprioception from pinned host memory and reads the
+    [N,1,7] action back (what an environment loop does)."""
+    from hulc2_b200 import _lib, ops
+    from hulc2_b200._compat import instantiate
+    from hulc2_b200.config import hulc2_config
+    from hulc2_b200.rollout import RolloutServer
+    from hulc2_b200.synthetic import synthetic_obs, tree_map
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    ops.set_precision(args.precision)
+    N, CYCLE = args.envs, 30
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import hulc2_oracle as O
+
+        torch.manual_seed(0)
+        n_cpu = 16
+        mc = instantiate(hulc2_config(dropout_p=0.0))
+        P = {k: v.detach().clone() for k, v in mc.state_dict().items()}
+        obs_c, goal_c = synthetic_obs(n_cpu, seed=2)
+        ro = O.OracleRollout(P, hulc2_config(pkg="x", dropout_p=0.0))
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        g = torch.Generator().manual_seed(1)
+        t0 = time.perf_counter()
+        for s in range(6):
+            ro.step(obs_c, goal_c, torch.randint(0, 32, (n_cpu, 32), generator=g), torch.rand(n_cpu, 1, 6, 10, generator=g),
+                    torch.rand(n_cpu, 1, 6, generator=g))
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_cpu * 6 / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
+               "sample": f"oracle port of Hulc2.step, fp32, {n_cpu} envs x 6 control steps (1 re-plan + 5 plain)"}
+
+    torch.manual_seed(0)
+    model = instantiate(hulc2_config(dropout_p=0.1)).to(dev).eval()
+    srv = RolloutServer(model, use_graph=not args.no_graph)
+    g = torch.Generator().manual_seed(3)
+    obs_f, goal = synthetic_obs(N, seed=2)
+    host = [dict(obs_f, rgb_obs={"rgb_static": torch.randint(0, 256, (N, 1, 200, 200, 3), generator=g, dtype=torch.uint8),
+                                 "rgb_gripper": torch.randint(0, 256, (N, 1, 84, 84, 3), generator=g, dtype=torch.uint8)})
+            for _ in range(2)]
+    host = [tree_map(lambda t: t.pin_memory(), h) for h in host]
+    goal_h = tree_map(lambda t: t.pin_memory(), goal)
+    devobs = [tree_map(lambda t: t.to(dev), h) for h in host]
+    goal_d = tree_map(lambda t: t.to(dev), goal)
+    h2d = nbytes(host[0])
+
+    def cycle(obs_list, gl, read_back):
+        srv.reset()
+        for s in range(CYCLE):
+            a = srv.step(obs_list[s % 2], gl)
+            if read_back:
+                a_host.copy_(a, non_blocking=False)
+
+    a_host = torch.empty(N, 1, 7).pin_memory()
+    for _ in range(max(args.warmup, 1)):
+        cycle(devobs, goal_d, False)
+    torch.cuda.synchronize()
+    l0 = _lib.load_library().hulc2_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev.index) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            cycle(devobs, goal_d, False)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (_lib.load_library().hulc2_launch_count() - l0) + args.steps * (srv.launches["replan"] + CYCLE * srv.launches["act"])
+    value = N * CYCLE / (ms * 1e-3)
+    cycle(host, goal_h, True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(max(args.e2e_steps // 2, 2)):
+        cycle(host, goal_h, True)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / max(args.e2e_steps // 2, 2)
+    line = {
+        "metric": "rollout env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": f"configs[4]: policy rollout inference, {N} parallel envs, S=1, language goal, replan_freq 30; one bench step = "
+                               f"1 re-plan + 29 plain control steps ({CYCLE} x {N} env-steps)",
+                   "frames": "uint8 HWC camera frames, scaled/normalised on the device", "precision": args.precision,
+                   "cuda_graph": bool(srv._graphs), "ms_per_control_step": ms / CYCLE,
+                   "l2": f"observations ({h2d / 1e6:.0f} MB per control step) exceed the 126 MB L2"},
+        "clocks": clk.summary(), "gpu_launches": int(launches),
+        "e2e": {"value": N * CYCLE / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d * CYCLE),
+                "d2h_bytes_per_step": N * 7 * 4 * CYCLE, "api": "RolloutServer.step(pinned host obs) + action read-back, every control step",
+                "ms_per_control_step": e2e_ms / CYCLE},
+        "roofline": None, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "rollout":
+        run_rollout(a)
     else:
         run_b200(a)

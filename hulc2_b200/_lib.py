@@ -123,6 +123,7 @@ _SIGS = {
     "hulc2_gauss_state_fwd": [P, P, P, I, I],
     "hulc2_gauss_state_bwd": [P, P, P, P, I, I],
     "hulc2_gauss_rsample": [P, P, P, P, LL],
+    "hulc2_box_muller": [P, P, P, LL],
     "hulc2_gauss_kl_fwd": [P, P, P, P, P, I, I, F, F],
     "hulc2_gauss_kl_bwd": [P, P, P, P, P, P, P, P, P, I, I, F, F],
     "hulc2_adam_step": [P, P, P, P, LL, F, F, F, F, F, I, F],

@@ -158,11 +158,16 @@ __global__ void gauss_state_bwd_kernel(const float* __restrict__ x, const float*
     dx[b * 2 * P + P + k] = dstd ? dstd[i] * (v > 20.f ? 1.f : sigmoid_t(v)) : 0.f;
   }
 }
-// Normal.rsample / sample: plan = mean + std * eps
+// Normal.rsample / sample: plan = mean + std * eps (mean null = 0: the std-gradient g * eps of rsample)
 __global__ void gauss_rsample_kernel(const float* __restrict__ mean, const float* __restrict__ std, const float* __restrict__ eps,
                                      float* __restrict__ plan, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    plan[i] = mean[i] + std[i] * eps[i];
+    plan[i] = (mean ? mean[i] : 0.f) + std[i] * eps[i];
+}
+// standard normals from two uniform streams in (0,1]: eps = sqrt(-2 ln u1) cos(2 pi u2)
+__global__ void box_muller_kernel(const float* __restrict__ u1, const float* __restrict__ u2, float* __restrict__ eps, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    eps[i] = sqrtf(-2.f * logf(fmaxf(u1[i], 1e-30f))) * cospif(2.f * u2[i]);
 }
 
 // KL(N(mp, sp) || N(mq, sq)) per element (torch.distributions.kl._kl_normal_normal):
@@ -258,6 +263,12 @@ int hulc2_gauss_state_bwd(const float* x, const float* dmean, const float* dstd,
 int hulc2_gauss_rsample(const float* mean, const float* std, const float* eps, float* plan, long long n, cudaStream_t st) {
   if (n <= 0) return HULC2_OK;
   gauss_rsample_kernel<<<ew_grid(n), 256, 0, st>>>(mean, std, eps, plan, n);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_box_muller(const float* u1, const float* u2, float* eps, long long n, cudaStream_t st) {
+  if (n <= 0) return HULC2_OK;
+  box_muller_kernel<<<ew_grid(n), 256, 0, st>>>(u1, u2, eps, n);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

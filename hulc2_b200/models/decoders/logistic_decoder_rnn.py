@@ -84,6 +84,14 @@ class LogisticDecoderRNN(ActionDecoder):
         """-> time-major hidden states [S,B,H] of the top layer and h_n [2,B,H]."""
         pe = perceptual_emb[..., slice(*self.perceptual_emb_slice)]
         r = self.rnn
+        if isinstance(r, (nn.GRU, nn.LSTM)):
+            # h_0 follows torch: a [2,B,H] tensor for nn.GRU, an (h_0, c_0) pair for nn.LSTM; so does the returned h_n
+            lstm = isinstance(r, nn.LSTM)
+            h0, c0 = (h_0 if lstm else (h_0, None)) if h_0 is not None else (None, None)
+            Hs, hn, cn = ops.GatedRNNDecoderFunction.apply(
+                "lstm" if lstm else "gru", latent_plan, pe, latent_goal, h0, c0, r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0,
+                r.bias_hh_l0, r.weight_ih_l1, r.weight_hh_l1, r.bias_ih_l1, r.bias_hh_l1)
+            return Hs, ((hn, cn) if lstm else hn)
         return ops.RNNDecoderFunction.apply(
             latent_plan, pe, latent_goal, h_0, r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0,
             r.weight_ih_l1, r.weight_hh_l1, r.bias_ih_l1, r.bias_hh_l1,

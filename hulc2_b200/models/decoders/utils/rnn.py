@@ -1,6 +1,7 @@
 """RNN factories (mirror of hulc2/models/decoders/utils/rnn.py:5-46).  The returned torch modules are
-parameter containers (``weight_ih_l0`` ...); the recurrence itself runs in the CUDA library.  Only the
-default ``rnn_decoder`` (ReLU Elman RNN) has kernels this round; GRU/LSTM/MLP are SURVEY 8f row 4."""
+parameter containers (``weight_ih_l0`` ...); the recurrence itself runs in the CUDA library: persistent
+tcgen05 kernels for the default ``rnn_decoder`` (ReLU Elman RNN), per-step contraction + fused gate cell
+(csrc/cells.cu) for ``gru_decoder`` / ``lstm_decoder``."""
 import torch
 import torch.nn as nn
 
@@ -18,11 +19,25 @@ def rnn_decoder(in_features: int, hidden_size: int, num_layers: int, policy_rnn_
 
 
 def lstm_decoder(in_features: int, hidden_size: int, num_layers: int, policy_rnn_dropout_p: float) -> torch.nn.Module:
-    raise NotImplementedError("lstm_decoder: recurrence cell not built yet (SURVEY.md 8f row 4)")
+    return nn.LSTM(
+        input_size=in_features,
+        hidden_size=hidden_size,
+        num_layers=num_layers,
+        bidirectional=False,
+        batch_first=True,
+        dropout=policy_rnn_dropout_p,
+    )
 
 
 def gru_decoder(in_features: int, hidden_size: int, num_layers: int, policy_rnn_dropout_p: float) -> torch.nn.Module:
-    raise NotImplementedError("gru_decoder: recurrence cell not built yet (SURVEY.md 8f row 4)")
+    return nn.GRU(
+        input_size=in_features,
+        hidden_size=hidden_size,
+        num_layers=num_layers,
+        bidirectional=False,
+        batch_first=True,
+        dropout=policy_rnn_dropout_p,
+    )
 
 
 def mlp_decoder(in_features: int, hidden_size: int, num_layers: int, policy_rnn_dropout_p: float) -> torch.nn.Module:

@@ -137,6 +137,9 @@ class Hulc2(LightningModule):
     # ------------------------------------------------------------------ losses
     def compute_kl_loss(self, pp_state: State, pr_state: State) -> torch.Tensor:
         """hulc2.py:444-466 (KL balancing, alpha -> prior, 1-alpha -> posterior), scaled by kl_beta."""
+        if self.dist.dist == "continuous":
+            return ops.GaussKLFunction.apply(pp_state.mean, pp_state.std, pr_state.mean, pr_state.std,
+                                             float(self.kl_balancing_mix), float(self.kl_beta))
         return ops.KLFunction.apply(pp_state.logit, pr_state.logit, self.dist.category_size, self.dist.class_size,
                                     float(self.kl_balancing_mix), float(self.kl_beta))
 

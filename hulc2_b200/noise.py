@@ -18,7 +18,7 @@ from . import ops
 
 _state = {"seed": 0x5EED, "counter": 0}
 _epochs: Dict[tuple, torch.Tensor] = {}   # per device: u64 step counter read by the Philox kernels (CUDA-graph replays)
-_queues: Dict[str, Deque[torch.Tensor]] = {"categories": deque(), "uniforms": deque(), "masks": deque()}
+_queues: Dict[str, Deque[torch.Tensor]] = {"categories": deque(), "uniforms": deque(), "masks": deque(), "normals": deque()}
 
 
 def manual_seed(seed: int) -> None:
@@ -49,8 +49,9 @@ def _next_offset(n: int) -> int:
 
 
 @contextlib.contextmanager
-def supplied(categories=(), uniforms=(), masks=()):
+def supplied(categories=(), uniforms=(), masks=(), normals=()):
     """Queue tensors to be consumed (in call order) instead of fresh draws."""
+    _queues["normals"].extend(normals)
     _queues["categories"].extend(categories)
     _queues["uniforms"].extend(uniforms)
     _queues["masks"].extend(masks)
@@ -68,7 +69,7 @@ def fuse_supplied(n: int) -> None:
     """A step that runs the windows of ``n`` modalities as one batch consumes one draw where the per-modality loop
     consumed ``n``.  Supplied category/mask tensors are queued per modality (modality 0's draws, then modality 1's, ...):
     regroup them into batch-concatenated tensors in draw order."""
-    for key in ("categories", "masks"):
+    for key in ("categories", "masks", "normals"):
         q = _queues[key]
         if not q:
             continue
@@ -88,6 +89,21 @@ def uniform(shape, device) -> torch.Tensor:
     for s in shape:
         n *= int(s)
     return ops.uniform(tuple(shape), device, _state["seed"], _next_offset(n), epoch=epoch_tensor(device))
+
+
+def normal(shape, device) -> torch.Tensor:
+    """Standard normals (the eps of Normal.rsample/sample, distributions.py:28-29): the next supplied tensor, or
+    Box-Muller over two Philox uniform draws."""
+    if _queues["normals"]:
+        t = _queues["normals"].popleft()
+        assert tuple(t.shape) == tuple(shape), (tuple(t.shape), tuple(shape))
+        return t.to(device=device, dtype=torch.float32)
+    n = 1
+    for s in shape:
+        n *= int(s)
+    u1 = ops.uniform(tuple(shape), device, _state["seed"], _next_offset(n), epoch=epoch_tensor(device))
+    u2 = ops.uniform(tuple(shape), device, _state["seed"], _next_offset(n), epoch=epoch_tensor(device))
+    return ops.box_muller(u1, u2)
 
 
 def categories(logits: torch.Tensor, cats: int, classes: int) -> torch.Tensor:

@@ -826,6 +826,92 @@ class KLFunction(torch.autograd.Function):
         return dpp, dpr, None, None, None, None, None
 
 
+class GaussStateFunction(torch.autograd.Function):
+    """distributions.py:55-59: x [B,2P] -> (mean, std = softplus(var) + 1e-4)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32(x).contiguous()
+        B, P2 = x.shape
+        P = P2 // 2
+        mean = torch.empty(B, P, device=x.device, dtype=torch.float32)
+        std = torch.empty(B, P, device=x.device, dtype=torch.float32)
+        call("hulc2_gauss_state_fwd", x.data_ptr(), mean.data_ptr(), std.data_ptr(), B, P)
+        ctx.save_for_backward(x)
+        return mean, std
+
+    @staticmethod
+    def backward(ctx, dmean, dstd):
+        (x,) = ctx.saved_tensors
+        B, P2 = x.shape
+        dx = torch.empty_like(x)
+        call("hulc2_gauss_state_bwd", x.data_ptr(), _p(dmean.contiguous() if dmean is not None else None),
+             _p(dstd.contiguous() if dstd is not None else None), dx.data_ptr(), B, P2 // 2)
+        return dx
+
+
+class GaussRSampleFunction(torch.autograd.Function):
+    """Independent(Normal(mean, std), 1).rsample() with caller-visible noise: plan = mean + std * eps (hulc2.py:235)."""
+
+    @staticmethod
+    def forward(ctx, mean, std, eps):
+        mean, std, eps = _f32(mean).contiguous(), _f32(std).contiguous(), _f32(eps).contiguous()
+        plan = torch.empty_like(mean)
+        call("hulc2_gauss_rsample", mean.data_ptr(), std.data_ptr(), eps.data_ptr(), plan.data_ptr(), mean.numel())
+        ctx.save_for_backward(eps)
+        return plan
+
+    @staticmethod
+    def backward(ctx, g):
+        (eps,) = ctx.saved_tensors
+        g = g.contiguous()
+        dstd = torch.empty_like(g)
+        call("hulc2_gauss_rsample", None, g.data_ptr(), eps.data_ptr(), dstd.data_ptr(), g.numel())
+        return g, dstd, None
+
+
+def box_muller(u1: torch.Tensor, u2: torch.Tensor) -> torch.Tensor:
+    eps = torch.empty_like(u1)
+    call("hulc2_box_muller", u1.contiguous().data_ptr(), u2.contiguous().data_ptr(), eps.data_ptr(), eps.numel())
+    return eps
+
+
+class GaussKLFunction(torch.autograd.Function):
+    """hulc2.py:444-466 for the continuous plan: balanced KL between diagonal normals, scaled by kl_beta -> scalar
+    (or the vector of per-modality batch means with ``segments``)."""
+
+    @staticmethod
+    def forward(ctx, pp_mean, pp_std, pr_mean, pr_std, alpha, beta, segments=None):
+        ts = [_f32(t).contiguous() for t in (pp_mean, pp_std, pr_mean, pr_std)]
+        B, P = ts[0].shape
+        segs = tuple(int(n) for n in segments) if segments is not None else (B,)
+        assert sum(segs) == B
+        loss = torch.empty(len(segs), device=ts[0].device, dtype=torch.float32)
+        b0 = 0
+        for i, n in enumerate(segs):
+            off = 4 * b0 * P
+            call("hulc2_gauss_kl_fwd", *(t.data_ptr() + off for t in ts), loss.data_ptr() + 4 * i, n, P, alpha, beta)
+            b0 += n
+        ctx.save_for_backward(*ts)
+        ctx.cfg = (segs, alpha, beta)
+        return loss if segments is not None else loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        ts = ctx.saved_tensors
+        segs, alpha, beta = ctx.cfg
+        B, P = ts[0].shape
+        g = g.contiguous().view(-1)
+        ds = [torch.empty_like(t) for t in ts]
+        b0 = 0
+        for i, n in enumerate(segs):
+            off = 4 * b0 * P
+            call("hulc2_gauss_kl_bwd", *(t.data_ptr() + off for t in ts), g.data_ptr() + 4 * i, *(d.data_ptr() + off for d in ds),
+                 n, P, alpha, beta)
+            b0 += n
+        return (*ds, None, None, None)
+
+
 class PlanRSampleFunction(torch.autograd.Function):
     """OneHotCategoricalStraightThrough.rsample given the drawn indices (hulc2.py:235, distributions.py:23-26)."""
 

@@ -40,6 +40,22 @@ class PlanDist:
         return ops.onehot(idx, self.category_size, self.class_size).view(-1, self.category_size, self.class_size)
 
 
+class GaussPlanDist:
+    """Independent(Normal(mean, std), 1) restricted to what the policy uses (distributions.py:28-29)."""
+
+    def __init__(self, mean: torch.Tensor, std: torch.Tensor):
+        self.mean, self.stddev = mean, std
+
+    def rsample(self, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if eps is None:
+            eps = noise.normal(self.mean.shape, self.mean.device)
+        return ops.GaussRSampleFunction.apply(self.mean, self.stddev, eps)
+
+    def sample(self, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        with torch.no_grad():
+            return self.rsample(eps)
+
+
 class Distribution:
     def __init__(self, **kwargs):
         self.dist = kwargs.get("dist")
@@ -47,22 +63,30 @@ class Distribution:
         if self.dist == "discrete":
             self.category_size = kwargs.get("category_size")
             self.class_size = kwargs.get("class_size")
-        else:
-            raise NotImplementedError(
-                "continuous latent plans (conf/model/distribution/continuous.yaml) are a SURVEY 8f 'next' row"
-            )
 
     def get_dist(self, state):
-        return PlanDist(state.logit, self.category_size, self.class_size)
+        if self.dist == "discrete":
+            return PlanDist(state.logit, self.category_size, self.class_size)
+        return GaussPlanDist(state.mean, state.std)
 
     def detach_state(self, state):
-        return DiscState(state.logit.detach())
+        if self.dist == "discrete":
+            return DiscState(state.logit.detach())
+        return ContState(state.mean.detach(), state.std.detach())
 
-    def sample_latent_plan(self, distribution: PlanDist) -> torch.Tensor:
-        return torch.flatten(distribution.sample(), start_dim=-2, end_dim=-1)
+    def sample_latent_plan(self, distribution) -> torch.Tensor:
+        sampled_plan = distribution.sample()
+        if self.dist == "discrete":
+            sampled_plan = torch.flatten(sampled_plan, start_dim=-2, end_dim=-1)
+        return sampled_plan
 
     def build_state(self, hidden_size, plan_features):
-        return nn.Sequential(nn.Linear(hidden_size, plan_features))
+        if self.dist == "discrete":
+            return nn.Sequential(nn.Linear(hidden_size, plan_features))
+        return nn.Sequential(nn.Linear(hidden_size, 2 * plan_features))
 
     def forward_dist(self, x):
-        return DiscState(x)
+        if self.dist == "discrete":
+            return DiscState(x)
+        mean, std = ops.GaussStateFunction.apply(x)
+        return ContState(mean, std)

@@ -300,12 +300,14 @@ int hulc2_lstm_cell_bwd(const float* dh_a, const float* dh_b, const float* dc, c
 /* ------------------------------------------------------------------ continuous latent plan (distributions.py:28-29,55-59)
  * state: x [B,2P] -> mean = x[:, :P], std = softplus(x[:, P:]) + 1e-4 (and its gradient);  rsample: mean + std*eps with
  * caller-supplied standard-normal eps;  kl: beta*(alpha*KL(sg(pr)||pp) + (1-alpha)*KL(pr||sg(pp))) for diagonal normals,
- * summed over P, mean over B (hulc2.py:444-466); gradients scaled by *gout (device scalar, null = 1), null outputs skipped. */
+ * summed over P, mean over B (hulc2.py:444-466; rsample's mean may be null = 0); gradients scaled by *gout (device scalar, null = 1), null outputs skipped. */
 int hulc2_gauss_state_fwd(const float* x, float* mean, float* std, int B, int P, hulc2_stream_t stream);
 int hulc2_gauss_state_bwd(const float* x, const float* dmean, const float* dstd, float* dx, int B, int P,
                           hulc2_stream_t stream);
 int hulc2_gauss_rsample(const float* mean, const float* std, const float* eps, float* plan, long long n,
                         hulc2_stream_t stream);
+/* eps = sqrt(-2 ln u1) cos(2 pi u2): standard normals from two Philox uniform streams (the library's default draw) */
+int hulc2_box_muller(const float* u1, const float* u2, float* eps, long long n, hulc2_stream_t stream);
 int hulc2_gauss_kl_fwd(const float* pp_mean, const float* pp_std, const float* pr_mean, const float* pr_std, float* loss,
                        int B, int P, float alpha, float beta, hulc2_stream_t stream);
 int hulc2_gauss_kl_bwd(const float* pp_mean, const float* pp_std, const float* pr_mean, const float* pr_std,

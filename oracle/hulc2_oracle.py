@@ -218,6 +218,26 @@ def kl_loss(pp_logits, pr_logits, kl_beta, alpha, category_size=32, class_size=3
     return (alpha * lhs + (1 - alpha) * rhs) * kl_beta
 
 
+def gauss_state(x: Tensor) -> Tuple[Tensor, Tensor]:
+    """distributions.py:55-59 (continuous): chunk -> mean, softplus(var) + 1e-4."""
+    mean, var = torch.chunk(x, 2, dim=-1)
+    return mean, F.softplus(var) + 0.0001
+
+
+def _kl_normal(mp: Tensor, sp: Tensor, mq: Tensor, sq: Tensor) -> Tensor:
+    """torch.distributions.kl._kl_normal_normal summed over the plan dims (Independent(Normal, 1)) -> [B]."""
+    var_ratio = (sp / sq).pow(2)
+    t1 = ((mp - mq) / sq).pow(2)
+    return (0.5 * (var_ratio + t1 - 1 - var_ratio.log())).sum(-1)
+
+
+def kl_loss_gauss(pp: Tuple[Tensor, Tensor], pr: Tuple[Tensor, Tensor], kl_beta, alpha) -> Tensor:
+    """hulc2.py:444-466 with the continuous plan (distributions.py:28-29): p = pr (posterior), q = pp (prior)."""
+    lhs = _kl_normal(pr[0].detach(), pr[1].detach(), pp[0], pp[1]).mean()
+    rhs = _kl_normal(pr[0], pr[1], pp[0].detach(), pp[1].detach()).mean()
+    return (alpha * lhs + (1 - alpha) * rhs) * kl_beta
+
+
 # ----------------------------------------------------------------------------- a16 tcp frames
 def _rot(axis: str, a: Tensor) -> Tensor:
     c, s = torch.cos(a), torch.sin(a)
@@ -429,13 +449,24 @@ def clip_loss(seq_feat: Tensor, goal: Tensor, use: Optional[Tensor], P) -> Tenso
 
 # ----------------------------------------------------------------------------- a19/a20 train step
 def lmp_train(emb, goal, actions, robot_obs_raw, plan_idx, P, cfg, masks=None):
-    """hulc2.py:200-245.  plan_idx [B,32] = the category indices pr_dist.rsample() drew."""
+    """hulc2.py:200-245.  plan_idx [B,32] = the category indices pr_dist.rsample() drew (discrete plan), or the
+    standard-normal eps [B,plan_features] of Normal.rsample() (continuous plan)."""
     dec = cfg["action_decoder"]
     pp_logits = plan_proposal(emb[:, 0], goal, P)
     pr_logits, seq_feat = plan_recognition(
         emb, P, cfg["plan_recognition"]["num_heads"], cfg["plan_recognition"]["num_layers"],
         cfg["plan_recognition"]["dropout_p"], masks,
     )
+    if cfg["distribution"]["dist"] == "continuous":
+        pp, pr = gauss_state(pp_logits), gauss_state(pr_logits)
+        plan = pr[0] + pr[1] * plan_idx
+        lp, ls, mu, grip, _ = decoder_forward(
+            plan, emb, goal, P, tuple(dec["perceptual_emb_slice"]), None, dec["n_mixtures"], dec["log_scale_min"], dec["rnn_model"]
+        )
+        acts = world_to_tcp_frame(actions, robot_obs_raw) if dec["gripper_control"] else actions
+        action_loss = decoder_loss(lp, ls, mu, grip, acts, P, dec["gripper_alpha"])
+        kl = kl_loss_gauss(pp, pr, cfg["kl_beta"], cfg["kl_balancing_mix"])
+        return kl, action_loss, action_loss + kl, pp_logits, pr_logits, seq_feat
     plan = rsample_straight_through(pr_logits, plan_idx, 32, 32)
     lp, ls, mu, grip, _ = decoder_forward(
         plan, emb, goal, P, tuple(dec["perceptual_emb_slice"]), None, dec["n_mixtures"], dec["log_scale_min"], dec["rnn_model"]

@@ -52,3 +52,31 @@ def supplied_categories(queue: List[torch.Tensor]):
     finally:
         Categorical.sample = orig
     assert not q, "unused category draws"
+
+
+@contextlib.contextmanager
+def supplied_normals(queue: List[torch.Tensor]):
+    """``Normal.rsample()`` / ``sample()`` (continuous plan, distributions.py:28-29) consume queued standard-normal
+    tensors instead of drawing (``torch.distributions.normal._standard_normal`` for rsample, ``torch.normal`` for sample)."""
+    import torch.distributions.normal as N
+
+    orig_std, orig_normal = N._standard_normal, torch.normal
+    q = list(queue)
+
+    def fake_standard_normal(shape, dtype, device):
+        t = q.pop(0)
+        assert tuple(t.shape) == tuple(shape), (t.shape, shape)
+        return t.clone().to(dtype=dtype, device=device)
+
+    def fake_normal(mean, std, *a, **kw):
+        t = q.pop(0)
+        return mean + std * t
+
+    N._standard_normal = fake_standard_normal
+    torch.normal = fake_normal
+    try:
+        yield
+    finally:
+        N._standard_normal = orig_std
+        torch.normal = orig_normal
+    assert not q, "unused normal draws"

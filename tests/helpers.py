@@ -58,3 +58,54 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 def assert_close(a, b, tol, what=""):
     e = rel_err(a, b)
     assert e <= tol, f"{what}: rel err {e:.3e} > {tol:.1e}"
+
+
+# ----------------------------------------------------------------------------- alternate blocks
+ALT_GOLDEN_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hulc2_alt_golden.npz")
+# tag -> config kwargs; B=2 windows per modality, hidden_size 256 keeps fixture generation and the oracle check fast
+ALT_CASES = {
+    "gru": dict(variant="calvin", static_hw=(200, 200), rnn_model="gru_decoder", distribution="discrete"),
+    "lstm": dict(variant="calvin", static_hw=(200, 200), rnn_model="lstm_decoder", distribution="discrete"),
+    "gauss_rw": dict(variant="real_world", static_hw=(150, 200), rnn_model="rnn_decoder", distribution="continuous"),
+    "gauss_gru": dict(variant="calvin", static_hw=(200, 200), rnn_model="gru_decoder", distribution="continuous"),
+    "rgbd_rw": dict(variant="real_world", static_hw=(150, 200), rnn_model="rnn_decoder", distribution="discrete", depth_static=True),
+}
+ALT_B, ALT_HIDDEN, ALT_WEIGHT_SEED, ALT_BATCH_SEED, ALT_NOISE_SEED = 2, 256, 5, 17, 19
+_alt_golden = None
+
+
+def alt_gt(name) -> torch.Tensor:
+    global _alt_golden
+    if _alt_golden is None:
+        _alt_golden = np.load(ALT_GOLDEN_PATH)
+    return torch.from_numpy(np.asarray(_alt_golden[name]))
+
+
+def alt_keys(prefix):
+    alt_gt(next(iter(np.load(ALT_GOLDEN_PATH).files)))
+    return [k for k in _alt_golden.files if k.startswith(prefix)]
+
+
+def alt_case_inputs(tag):
+    """(config kwargs, batch, per-modality plan draw): category indices [B,32] for the discrete plan, standard-normal
+    eps [B,256] for the continuous one.  Shared by tests/golden/make_golden_alt.py and the tests."""
+    from hulc2_b200.synthetic import synthetic_batch
+
+    kw = dict(ALT_CASES[tag], dropout_p=0.0, hidden_size=ALT_HIDDEN)
+    batch = synthetic_batch(ALT_B, seed=ALT_BATCH_SEED, static_hw=kw["static_hw"], aux="all", depth_static=kw.get("depth_static", False))
+    g = torch.Generator().manual_seed(ALT_NOISE_SEED)
+    if kw["distribution"] == "discrete":
+        draw = {mod: torch.randint(0, 32, (ALT_B, 32), generator=g) for mod in batch}
+    else:
+        draw = {mod: torch.randn(ALT_B, 256, generator=g) for mod in batch}
+    return kw, batch, draw
+
+
+def build_alt_model(tag, device="cpu"):
+    kw = dict(ALT_CASES[tag], dropout_p=0.0, hidden_size=ALT_HIDDEN)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = instantiate(hulc2_config(pkg="hulc2_b200", **kw))
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if v.dtype.is_floating_point}
+    m.load_state_dict(synthetic_state_dict(shapes, seed=ALT_WEIGHT_SEED, skip=NON_LEARNED), strict=False)
+    return m.to(device)

@@ -128,7 +128,7 @@ def test_unsupported_config_values_raise_not_fallback():
     from hulc2_b200._compat import instantiate
 
     with pytest.raises(NotImplementedError):
-        instantiate(hulc2_config(rnn_model="gru_decoder", hidden_size=64))
+        instantiate(hulc2_config(rnn_model="mlp_decoder", hidden_size=64))
     cfg = hulc2_config(hidden_size=64)
     cfg["visual_goal"]["activation_function"] = "ELU"
     with pytest.raises(NotImplementedError):
