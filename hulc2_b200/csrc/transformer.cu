@@ -32,10 +32,9 @@ __global__ void add_pos_bwd_kernel(const float* __restrict__ dout, const unsigne
   if (dpos) dpos[i] += s;
 }
 
-template <int DH>
+template <int DH, int WARPS>
 __global__ void attention_fwd_kernel(const float* __restrict__ qkv, const unsigned char* __restrict__ keep, float keep_scale,
                                      float* __restrict__ out, float* __restrict__ probs, int B, int S, int H) {
-  constexpr int WARPS = 4;
   __shared__ float Ks[WARPS][32][DH + 1];
   __shared__ float Vs[WARPS][32][DH + 1];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -95,11 +94,10 @@ __global__ void attention_fwd_kernel(const float* __restrict__ qkv, const unsign
   for (int d = 0; d < DH; ++d) orow[d] = o[d];
 }
 
-template <int DH>
+template <int DH, int WARPS>
 __global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
                                      const unsigned char* __restrict__ keep, float keep_scale,
                                      const float* __restrict__ dout, float* __restrict__ dqkv, int B, int S, int H) {
-  constexpr int WARPS = 2;
   __shared__ float Qs[WARPS][32][DH + 1];
   __shared__ float Ks[WARPS][32][DH + 1];
   __shared__ float Vs[WARPS][32][DH + 1];
@@ -229,10 +227,13 @@ int hulc2_attention_fwd(const float* qkv, const unsigned char* keep, float keep_
                         int H, int Dh, cudaStream_t st) {
   if (B <= 0) return HULC2_OK;
   if (S > 32 || S <= 0) { hulc2_set_error("attention: window length must be in [1,32]"); return HULC2_EINVAL; }
+  // head_dim = latent / num_heads: 16 (RGB static + gripper, 128/8), 24 (+ depth_static, 192/8), 32 (RGBD_both, 256/8)
   int blocks = hulc2_cdiv(B * H, 4);
-  if (Dh == 16) attention_fwd_kernel<16><<<blocks, 128, 0, st>>>(qkv, keep, keep_scale, out, probs, B, S, H);
-  else if (Dh == 8) attention_fwd_kernel<8><<<blocks, 128, 0, st>>>(qkv, keep, keep_scale, out, probs, B, S, H);
-  else { hulc2_set_error("attention: head_dim must be 8 or 16"); return HULC2_EINVAL; }
+  if (Dh == 16) attention_fwd_kernel<16, 4><<<blocks, 128, 0, st>>>(qkv, keep, keep_scale, out, probs, B, S, H);
+  else if (Dh == 8) attention_fwd_kernel<8, 4><<<blocks, 128, 0, st>>>(qkv, keep, keep_scale, out, probs, B, S, H);
+  else if (Dh == 24) attention_fwd_kernel<24, 4><<<blocks, 128, 0, st>>>(qkv, keep, keep_scale, out, probs, B, S, H);
+  else if (Dh == 32) attention_fwd_kernel<32, 4><<<blocks, 128, 0, st>>>(qkv, keep, keep_scale, out, probs, B, S, H);
+  else { hulc2_set_error("attention: head_dim must be 8, 16, 24 or 32"); return HULC2_EINVAL; }
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }
@@ -241,9 +242,11 @@ int hulc2_attention_bwd(const float* qkv, const float* probs, const unsigned cha
   if (B <= 0) return HULC2_OK;
   if (S > 32 || S <= 0) { hulc2_set_error("attention: window length must be in [1,32]"); return HULC2_EINVAL; }
   int blocks = hulc2_cdiv(B * H, 2);
-  if (Dh == 16) attention_bwd_kernel<16><<<blocks, 64, 0, st>>>(qkv, probs, keep, keep_scale, dout, dqkv, B, S, H);
-  else if (Dh == 8) attention_bwd_kernel<8><<<blocks, 64, 0, st>>>(qkv, probs, keep, keep_scale, dout, dqkv, B, S, H);
-  else { hulc2_set_error("attention: head_dim must be 8 or 16"); return HULC2_EINVAL; }
+  if (Dh == 16) attention_bwd_kernel<16, 2><<<blocks, 64, 0, st>>>(qkv, probs, keep, keep_scale, dout, dqkv, B, S, H);
+  else if (Dh == 8) attention_bwd_kernel<8, 2><<<blocks, 64, 0, st>>>(qkv, probs, keep, keep_scale, dout, dqkv, B, S, H);
+  else if (Dh == 24) attention_bwd_kernel<24, 2><<<blocks, 64, 0, st>>>(qkv, probs, keep, keep_scale, dout, dqkv, B, S, H);
+  else if (Dh == 32) attention_bwd_kernel<32, 1><<<B * H, 32, 0, st>>>(qkv, probs, keep, keep_scale, dout, dqkv, B, S, H);  // 1 warp: 48 KB static smem limit
+  else { hulc2_set_error("attention: head_dim must be 8, 16, 24 or 32"); return HULC2_EINVAL; }
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

@@ -57,12 +57,15 @@ def supplied(categories=(), uniforms=(), masks=(), normals=()):
     _queues["masks"].extend(masks)
     try:
         yield
-    finally:
-        left = {k: len(v) for k, v in _queues.items() if len(v)}
-        for q in _queues.values():
+    except BaseException:
+        for q in _queues.values():      # the body failed: report ITS error, not the draws it left behind
             q.clear()
-        if left:
-            raise AssertionError(f"unused supplied noise: {left}")
+        raise
+    left = {k: len(v) for k, v in _queues.items() if len(v)}
+    for q in _queues.values():
+        q.clear()
+    if left:
+        raise AssertionError(f"unused supplied noise: {left}")
 
 
 def fuse_supplied(n: int) -> None:
