@@ -54,6 +54,9 @@ def parse():
                     help="train = configs[1] (the headline metric); rollout = configs[4]: batched policy inference, --envs parallel "
                          "environments, one re-plan + 29 plain control steps per bench step (a separate metric, never the default)")
     ap.add_argument("--envs", type=int, default=1024)
+    ap.add_argument("--variant", default="calvin", choices=["calvin", "real_world", "real_world_rgbd"],
+                    help="calvin = configs[1] (default, the headline); real_world[_rgbd] = configs[3]: cfg_low_level_rw shape, "
+                         "150x200 static RGB (+ depth_static), no clip loss, decoder slice [0,128]")
     ap.add_argument("--dump-profile", default=None, help="write the per-call CUDA-event profile of one step to this JSON file")
     return ap.parse_args()
 
@@ -208,9 +211,11 @@ def run_b200(args):
                "sample": f"oracle port, fp32, {{vis:{args.cpu_batch}, lang:{args.cpu_batch}}} windows/step, 1 warm-up + 2 timed steps ({dt:.2f} s/step)"}
 
     torch.manual_seed(0)
-    model = instantiate(hulc2_config(dropout_p=0.1)).to(dev).train()
+    rw, rgbd = args.variant != "calvin", args.variant == "real_world_rgbd"
+    hw = (150, 200) if rw else (200, 200)
+    model = instantiate(hulc2_config(dropout_p=0.1, variant="real_world" if rw else "calvin", static_hw=hw, depth_static=rgbd)).to(dev).train()
     trainer = PolicyTrainer(model, use_graph=not args.no_graph)
-    batch = synthetic_batch_fast(B, seed=1 + rank, device=dev, frames=args.frames)
+    batch = synthetic_batch_fast(B, seed=1 + rank, device=dev, frames=args.frames, static_hw=hw, depth_static=rgbd)
     h2d = nbytes(batch)
 
     def barrier():
@@ -302,7 +307,9 @@ def run_b200(args):
             "metric": "train windows/sec", "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-            "config": {"workload": f"configs[1]: Hulc2 policy train step (fwd+bwd+allreduce+Adam), B={B}/modality/GPU, window 32, static 200x200 + gripper 84x84 RGB, 7-dof, lang [B,384], dropout 0.1",
+            "config": {"workload": (f"configs[1]: Hulc2 policy train step (fwd+bwd+allreduce+Adam), B={B}/modality/GPU, window 32, static 200x200 + gripper 84x84 RGB, 7-dof, lang [B,384], dropout 0.1"
+                                    if not rw else
+                                    f"configs[3]: cfg_low_level_rw-shaped Hulc2 train step, B={B}/modality/GPU, window 32, static 150x200 RGB{' + depth_static' if rgbd else ''} + gripper 84x84, 7-dof, no clip loss, dropout 0.1"),
                        "frames": ("uint8 HWC frames + per-frame RandomShiftsAug draw in the batch; scale/normalise/shift run on the device inside the step (fused into the trunk's pack kernel)"
                                   if args.frames == "uint8" else "fp32 NCHW frames in [-1,1] (reference batch contract; transforms already applied)"),
                        "windows_per_step_per_gpu": 2 * B, "parallelism": f"dp{world}", "l2": f"inputs ({h2d / 1e9:.2f} GB of frames/step) exceed the 126 MB L2",

@@ -103,6 +103,7 @@ struct ConvParams {
   const uint8_t* mask;   // bf16, same shape as the output: keep where > 0 (or null)
   uint8_t* y;            // bf16 output [*, N]
   int ncls, ntiles, N, relu;  // ntiles = (max tiles of a class) << cls_shift: tile vt -> class vt & (ncls-1), tile-in-class vt >> cls_shift
+  int ngroups, grp_shift; // work items of (1 << grp_shift) consecutive tiles: grp_shift = cls_shift, or 0 with HULC2_DGRAD_SPREAD=1 (old order)
   int cls_shift;         // classes are interleaved so the s*s parity classes of one image region run back to back (dZ stays in L2)
   int VH, VW;            // a tap (a, b) of row (f,i,j) is valid iff 0 <= i-a < VH and 0 <= j-b < VW
   int oH, oW;
@@ -167,7 +168,10 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
     // ring bookkeeping without runtime divisions: s/ph = stage being filled and its empty-barrier parity,
     // ps = oldest stage not yet published, inflight = committed-but-unpublished groups (<= LAG)
     uint32_t s = 0, ph = 1, ps = 0, inflight = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    // work order of a CTA: its tile groups round-robin, and inside a group the s*s parity classes of the same image
+    // region back to back (the classes read the same dZ pixels: the second..fourth pass hit in this SM's L1)
+    for (int grp = blockIdx.x; grp < p.ngroups; grp += gridDim.x)
+    for (int tile = grp << p.grp_shift, tend = tile + (1 << p.grp_shift); tile < tend; ++tile) {
       const ConvClass& cl = p.cls[DGRAD ? (tile & cls_mask) : 0];
       const int m0 = (DGRAD ? (tile >> p.cls_shift) : tile) * TILE_M;
       if (m0 >= cl.M) continue;
@@ -224,7 +228,10 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc(TILE_M, BN, false, false);
       uint32_t s = 0, ph = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      // work order of a CTA: its tile groups round-robin, and inside a group the s*s parity classes of the same image
+    // region back to back (the classes read the same dZ pixels: the second..fourth pass hit in this SM's L1)
+    for (int grp = blockIdx.x; grp < p.ngroups; grp += gridDim.x)
+    for (int tile = grp << p.grp_shift, tend = tile + (1 << p.grp_shift); tile < tend; ++tile) {
         const ConvClass& cl = p.cls[DGRAD ? (tile & cls_mask) : 0];
         if ((DGRAD ? (tile >> p.cls_shift) : tile) * TILE_M >= cl.M) continue;
         const uint32_t buf = ti & 1;
@@ -250,7 +257,10 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
     constexpr int HC = BN / 2;                                           // columns per thread
     const int lq = warp & 3, half = warp >> 2;
     uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    // work order of a CTA: its tile groups round-robin, and inside a group the s*s parity classes of the same image
+    // region back to back (the classes read the same dZ pixels: the second..fourth pass hit in this SM's L1)
+    for (int grp = blockIdx.x; grp < p.ngroups; grp += gridDim.x)
+    for (int tile = grp << p.grp_shift, tend = tile + (1 << p.grp_shift); tile < tend; ++tile) {
       const ConvClass& cl = p.cls[DGRAD ? (tile & cls_mask) : 0];
       const int m0 = (DGRAD ? (tile >> p.cls_shift) : tile) * TILE_M;
       if (m0 >= cl.M) continue;
@@ -564,7 +574,15 @@ int launch_igemm(const ConvParams& p, cudaStream_t st) {
     }
     configured = smem;
   }
-  const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
+  static const bool spread = getenv("HULC2_DGRAD_SPREAD") && atoi(getenv("HULC2_DGRAD_SPREAD")) != 0;
+  if (spread) {            // A/B switch: one tile per work item, classes of a region on neighbouring CTAs (L2 reuse only)
+    q.ngroups = p.ntiles;
+    q.grp_shift = 0;
+  } else {
+    q.ngroups = p.ntiles >> p.cls_shift;
+    q.grp_shift = p.cls_shift;
+  }
+  const int grid = q.ngroups < sm_count() ? q.ngroups : sm_count();
   kern<<<grid, NT, smem, st>>>(q);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;

@@ -23,12 +23,14 @@ extern __shared__ __align__(16) float infonce_smem[];
 
 __device__ void infonce_forward_phases(const float* img, const float* txt, const unsigned char* use, float scale, int B, int D,
                                        const Ws& w) {
-  for (int r = threadIdx.x; r < B; r += blockDim.x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // row norms + normalised features: one warp per row, lanes over the feature dim (same sqrt / division as x / x.norm())
+  for (int r = warp; r < B; r += nwarps) {
     float a = 0.f, b = 0.f;
-    for (int d = 0; d < D; ++d) { float x = img[(long long)r * D + d], y = txt[(long long)r * D + d]; a += x * x; b += y * y; }
-    a = sqrtf(a); b = sqrtf(b);
-    w.inorm[r] = a; w.tnorm[r] = b;
-    for (int d = 0; d < D; ++d) { w.imn[(long long)r * D + d] = img[(long long)r * D + d] / a; w.txn[(long long)r * D + d] = txt[(long long)r * D + d] / b; }
+    for (int d = lane; d < D; d += 32) { float x = img[(long long)r * D + d], y = txt[(long long)r * D + d]; a += x * x; b += y * y; }
+    a = sqrtf(warp_sum(a)); b = sqrtf(warp_sum(b));
+    if (lane == 0) { w.inorm[r] = a; w.tnorm[r] = b; }
+    for (int d = lane; d < D; d += 32) { w.imn[(long long)r * D + d] = img[(long long)r * D + d] / a; w.txn[(long long)r * D + d] = txt[(long long)r * D + d] / b; }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < B * B; i += blockDim.x) {
@@ -38,15 +40,17 @@ __device__ void infonce_forward_phases(const float* img, const float* txt, const
     w.sim[i] = s;
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < B; r += blockDim.x) {
+  // row / column log-sum-exp over the selected columns: one warp per row, lanes over the columns
+  for (int r = warp; r < B; r += nwarps) {
     float m1 = -INFINITY, m2 = -INFINITY;
-    for (int c = 0; c < B; ++c)
+    for (int c = lane; c < B; c += 32)
       if (!use || use[c]) { m1 = fmaxf(m1, w.sim[(long long)r * B + c]); m2 = fmaxf(m2, w.sim[(long long)c * B + r]); }
+    m1 = warp_max(m1); m2 = warp_max(m2);
     float s1 = 0.f, s2 = 0.f;
-    for (int c = 0; c < B; ++c)
+    for (int c = lane; c < B; c += 32)
       if (!use || use[c]) { s1 += expf(w.sim[(long long)r * B + c] - m1); s2 += expf(w.sim[(long long)c * B + r] - m2); }
-    w.rlse[r] = m1 + logf(s1);
-    w.clse[r] = m2 + logf(s2);
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) { w.rlse[r] = m1 + logf(s1); w.clse[r] = m2 + logf(s2); }
   }
   __syncthreads();
 }
@@ -106,14 +110,16 @@ __global__ void __launch_bounds__(512) infonce_bwd_kernel(const float* __restric
     dtxt[i] = scale * b;   // temporarily d(txn)
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < B; r += blockDim.x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < B; r += nwarps) {                 // through x / ||x||: one warp per row
     if (use && !use[r]) {
-      for (int d = 0; d < D; ++d) dimg[(long long)r * D + d] = dtxt[(long long)r * D + d] = 0.f;
+      for (int d = lane; d < D; d += 32) dimg[(long long)r * D + d] = dtxt[(long long)r * D + d] = 0.f;
       continue;
     }
     float da = 0.f, db = 0.f;
-    for (int d = 0; d < D; ++d) { da += w.imn[(long long)r * D + d] * dimg[(long long)r * D + d]; db += w.txn[(long long)r * D + d] * dtxt[(long long)r * D + d]; }
-    for (int d = 0; d < D; ++d) {
+    for (int d = lane; d < D; d += 32) { da += w.imn[(long long)r * D + d] * dimg[(long long)r * D + d]; db += w.txn[(long long)r * D + d] * dtxt[(long long)r * D + d]; }
+    da = warp_sum(da); db = warp_sum(db);
+    for (int d = lane; d < D; d += 32) {
       dimg[(long long)r * D + d] = (dimg[(long long)r * D + d] - w.imn[(long long)r * D + d] * da) / w.inorm[r];
       dtxt[(long long)r * D + d] = (dtxt[(long long)r * D + d] - w.txn[(long long)r * D + d] * db) / w.tnorm[r];
     }

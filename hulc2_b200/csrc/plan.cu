@@ -25,49 +25,20 @@ __device__ __forceinline__ float kl_term(float p, float lp, float q, float lq, b
   return t;
 }
 
-// single block, deterministic: one THREAD per (b, cat) row (classes <= 32 values in registers, no shuffles on the
-// critical path), then one block reduction.  rows = B * cats is 2048-4096: 2-4 rows per thread.
+// single block, deterministic: one WARP per (b, cat) row at a time (lane = class, shuffle reductions; 32 warps walk the
+// 2048-4096 rows), per-warp partial sums combined by one block reduction in a fixed order.
 __global__ void __launch_bounds__(1024) kl_fwd_kernel(const float* __restrict__ pp, const float* __restrict__ pr, float* __restrict__ loss,
                                                       int rows, int classes, int B, float alpha, float beta) {
   __shared__ float red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const bool valid = lane < classes;
   float acc = 0.f;
-  const bool vec = (classes & 3) == 0;
-  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
-    float zp[32], zq[32];
-    const float* a = pr + (long long)r * classes;
-    const float* b = pp + (long long)r * classes;
-    if (vec) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (4 * k < classes) {
-          const float4 u = __ldg(reinterpret_cast<const float4*>(a) + k), v = __ldg(reinterpret_cast<const float4*>(b) + k);
-          zp[4 * k] = u.x; zp[4 * k + 1] = u.y; zp[4 * k + 2] = u.z; zp[4 * k + 3] = u.w;
-          zq[4 * k] = v.x; zq[4 * k + 1] = v.y; zq[4 * k + 2] = v.z; zq[4 * k + 3] = v.w;
-        }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 32; ++k)
-        if (k < classes) { zp[k] = a[k]; zq[k] = b[k]; }
-    }
-    float mp = -INFINITY, mq = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < 32; ++k)
-      if (k < classes) { mp = fmaxf(mp, zp[k]); mq = fmaxf(mq, zq[k]); }
-    float sp = 0.f, sq = 0.f;
-#pragma unroll
-    for (int k = 0; k < 32; ++k)
-      if (k < classes) { zp[k] -= mp; zq[k] -= mq; sp += expf(zp[k]); sq += expf(zq[k]); }
-    const float lsp = logf(sp), lsq = logf(sq);
-    float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 32; ++k)
-      if (k < classes) {
-        const float lp = zp[k] - lsp, lq = zq[k] - lsq;
-        t += kl_term(expf(zp[k]) / sp, lp, expf(zq[k]) / sq, lq, true);
-      }
-    acc += t;
+  for (int r = warp; r < rows; r += nwarps) {
+    LogSm P = log_softmax_lane(valid ? pr[(long long)r * classes + lane] : 0.f, valid);
+    LogSm Q = log_softmax_lane(valid ? pp[(long long)r * classes + lane] : 0.f, valid);
+    acc += kl_term(P.p, P.lp, Q.p, Q.lp, valid);          // lane-local partial of this row
   }
-  float tot = block_sum(acc, red);
+  const float tot = block_sum(acc, red);
   if (threadIdx.x == 0) {
     float kl = tot / (float)B;
     loss[0] = (alpha * kl + (1.f - alpha) * kl) * beta;

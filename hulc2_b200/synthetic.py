@@ -72,7 +72,8 @@ def synthetic_batch(
     return out
 
 
-def synthetic_batch_fast(B, S=32, seed=1, static_hw=(200, 200), device="cuda", modalities=("vis", "lang"), pin=False, frames="fp32"):
+def synthetic_batch_fast(B, S=32, seed=1, static_hw=(200, 200), device="cuda", modalities=("vis", "lang"), pin=False, frames="fp32",
+                         depth_static=False):
     """Same shapes/ranges drawn with a torch generator (used for the full-size benchmark).  ``frames="uint8"`` gives the
     cameras as the dataset stores them (uint8 ``[B,S,H,W,3]``) plus the RandomShiftsAug draw ``<cam>_shift`` int32
     ``[B,S,2]`` (pad 10 static / 4 gripper, rand_shift.yaml); scale + normalise + shift then run on the device."""
@@ -99,7 +100,7 @@ def synthetic_batch_fast(B, S=32, seed=1, static_hw=(200, 200), device="cuda", m
                 "rgb_gripper": torch.randint(0, 256, (B, S, 84, 84, 3), generator=g, device=dev, dtype=torch.uint8),
                 "rgb_gripper_shift": torch.randint(-4, 5, (B, S, 2), generator=g, device=dev, dtype=torch.int32),
             },
-            "depth_obs": {},
+            "depth_obs": {"depth_static": U(B, S, H, W, lo=0.0, hi=1.0)} if depth_static else {},
             "robot_obs": U(B, S, 8),
             "actions": actions,
             "state_info": {"robot_obs": raw, "scene_obs": U(B, S, 24)},
