@@ -1,0 +1,27 @@
+// Parameters of the halo-tile convolution kernels (conv_halo_sm100.cu); geometry is filled by the C entry points in
+// conv_sm100.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct HaloParams {
+  const uint8_t* w;        // packed bf16 weights [NT][ntaps * 64], tap-major contraction index
+  const float* bias;       // [NT] or null (forward only)
+  const uint8_t* mask;     // bf16, output-shaped: keep where > 0 (input gradient) or null
+  uint8_t* y;              // bf16 output [F, oH, oW, BNc]
+  int NT;                  // accumulator columns = ncls * BNc (64 or 128)
+  int BNc;                 // channels per output pixel
+  int ncls;                // 1, or 4 = the stride-2 parity classes stacked along N
+  int relu;
+  int F, tiles_per_frame, ntiles;
+  int BH, PW, PH;          // a tile = BH rows of the (class-)output; halo tile = PH x PW source pixels (raster pitch PW)
+  int i_min, j_min;        // source coordinates of the halo tile's first pixel relative to (tile row 0, column 0)
+  int ntaps;
+  int oH, oW, oS;          // output tensor dims; pixel stride of a class (1, or 2 for stacked classes)
+  int stages, stage_bytes;
+  short delta[16];         // per tap: raster offset of its window inside the halo tile
+  short clsH[4], clsW[4], clsPh[4], clsPw[4];  // valid rows / columns of each class and its pixel parity offsets
+};
+
+bool hulc2_conv_halo_enabled();
+int hulc2_conv_halo_launch(const void* src, int F, int Hs, int Ws, HaloParams p, bool dgrad, cudaStream_t st);

@@ -1,0 +1,264 @@
+// Halo-tile implicit-GEMM convolutions for sm_100a: the im2col operand is never gathered.
+//
+// For a stride-1 correlation over a 64-channel bf16 NHWC source (conv3 forward, conv3 input gradient, and -- per stride
+// parity class -- conv2's input gradient), the A operand of tap (a, b) is the SAME source tile read at a row offset:
+// with the tile stored as a raster of PW pixels per row (128 bytes = 64 channels per pixel, SWIZZLE_128B), output
+// position m = il * PW + jl needs source row m + delta(a, b), delta = (a - a_min) * PW + (b - b_min).  So
+//   * ONE 4-D TMA box load {64 ch, PW, PH, 1 frame} per tile brings the halo tile into shared memory (out-of-range
+//     rows / columns are zero-filled by TMA: the zero padding of the input-gradient correlation comes for free);
+//   * the MMA thread issues, per tap, tcgen05.mma with the A descriptor's start address advanced by delta * 128 bytes.
+//     The swizzle is a function of the absolute shared-memory address, so a start address that is not a multiple of the
+//     8-row atom reads the shifted rows correctly (measured: tools/probes/umma_shift_probe.cu, all offsets 0..127 exact);
+//   * positions with jl >= (valid width) are garbage columns (the window wraps into the next raster row): computed,
+//     never stored.  M = 128 positions per tile = BH full rows of the (class-)output.
+// Each source byte is fetched from HBM/L2 once per tile (+ halo rows) instead of once per tap by 16-byte cp.async:
+// no producer warps, no per-thread address arithmetic.  Weights stay resident in shared memory as in conv_sm100.cu.
+// The s*s = 4 parity classes of conv2's input gradient share one halo tile: their packed weights are stacked along N
+// (4 x 32 input channels = one 128-column accumulator), the epilogue scatters the classes to their strided pixels.
+//
+// Warp roles (320 threads): warps 0-7 epilogue (TMEM lane quarter = w % 4, column half = w / 4), warp 8 MMA issuer,
+// warp 9 TMA producer.  Reference: hulc2/models/perceptual_encoders/vision_network.py:38-48 (+ autograd).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "sm100.cuh"
+#include "conv_halo.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int NT_HALO = 320;
+constexpr int MAX_ST = 8;
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+template <int NTOT, bool DGRAD>
+__global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_ST], empty_bar[MAX_ST], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float bias_s[NTOT];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ST = (uint32_t)p.stages;
+  const uint32_t a_smem = base;                                 // ST halo tiles
+  const uint32_t w_smem = base + ST * (uint32_t)p.stage_bytes;  // ntaps tiles of [NTOT rows][128 B]
+  constexpr uint32_t W_TILE = NTOT * 128;
+  constexpr uint32_t TCOLS = 2 * NTOT;                          // double-buffered accumulator
+
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), TCOLS);
+  if (tid == 32) {
+    for (uint32_t s = 0; s < ST; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 256); }
+    mbar_fence_init();
+  }
+  if (tid < NTOT) bias_s[tid] = (!DGRAD && p.bias) ? p.bias[tid] : 0.f;
+  {  // resident weights: [NTOT][K] bf16, K = ntaps * 64 -> per tap a K-major SWIZZLE_128B tile
+    const int cpr = p.ntaps * 8;                                // 16-byte chunks per weight row
+    for (int ch = tid; ch < NTOT * cpr; ch += NT_HALO) {
+      const int n = ch / cpr, q = ch - n * cpr;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.w + ((size_t)n * cpr + q) * 16));
+      const uint32_t dst = w_smem + (uint32_t)(q >> 3) * W_TILE + swz128(n, q & 7);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  if (warp == 9) {
+    // ===================================================== TMA producer (one thread): one halo tile per output tile
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm) : "memory");
+      uint32_t s = 0, ph = 1;
+      const uint32_t bytes = (uint32_t)(p.PH * p.PW) * 128u;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int f = tile / p.tiles_per_frame, ti = tile - f * p.tiles_per_frame;
+        mbar_wait(smem_u32(&empty_bar[s]), ph);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        mbar_expect_tx(bar, bytes);
+        tma_load_4d(a_smem + s * (uint32_t)p.stage_bytes, &tm, bar, 0, p.j_min, ti * p.BH + p.i_min, f);
+        if (++s == ST) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    // ===================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t IDESC = make_idesc(128, NTOT, false, false);
+      uint32_t s = 0, ph = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const uint32_t buf = ti & 1;
+        mbar_wait(smem_u32(&tempty_bar[buf]), ((ti >> 1) & 1) ^ 1);       // epilogue drained this accumulator
+        mbar_wait(smem_u32(&full_bar[s]), ph);                           // halo tile landed
+        tc_fence_after();
+        const uint32_t tile_addr = a_smem + s * (uint32_t)p.stage_bytes;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const uint64_t ad = make_desc(tile_addr + (uint32_t)p.delta[t] * 128u, 0), bd = make_desc(w_smem + t * W_TILE, 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_d + buf * NTOT, ad + 2 * k, bd + 2 * k, IDESC, (t > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));                            // halo tile reusable once these MMAs retire
+        umma_commit(smem_u32(&tfull_bar[buf]));                          // accumulator complete
+        if (++s == ST) { s = 0; ph ^= 1; }
+        ++ti;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue: row m = 32 * (w % 4) + lane, columns (w / 4) * NTOT/2 ..
+    constexpr int HC = NTOT / 2;
+    const int lq = warp & 3, half = warp >> 2;
+    const int m = lq * 32 + lane;
+    const int il = m / p.PW, jl = m - il * p.PW;
+    const int BNc = p.BNc;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int f = tile / p.tiles_per_frame, tr = tile - f * p.tiles_per_frame;
+      const int i = tr * p.BH + il;
+      const uint32_t buf = ti & 1;
+      mbar_wait_relaxed(smem_u32(&tfull_bar[buf]), (ti >> 1) & 1);
+      tc_fence_after();
+      uint32_t acc[HC];
+#pragma unroll
+      for (int c = 0; c < HC; c += 16)
+        tmem_ld16_nowait(tmem_d + ((uint32_t)(lq * 32) << 16) + buf * NTOT + half * HC + c, *reinterpret_cast<uint32_t(*)[16]>(&acc[c]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tempty_bar[buf]));
+#pragma unroll
+      for (int c = 0; c < HC; c += 16) {
+        const int col = half * HC + c;                  // first of 16 accumulator columns: one class, 16 channels
+        const int cls = col / BNc, ch = col - cls * BNc;
+        const bool ok = il < p.BH && i < p.clsH[cls] && jl < p.clsW[cls];
+        if (!ok) continue;
+        const long long opix = ((long long)f * p.oH + i * p.oS + p.clsPh[cls]) * p.oW + jl * p.oS + p.clsPw[cls];
+        const long long off = (opix * BNc + ch) * 2;
+        uint32_t o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float lo = __uint_as_float(acc[c + 2 * e]), hi = __uint_as_float(acc[c + 2 * e + 1]);
+          if (!DGRAD) {
+            lo += bias_s[col + 2 * e]; hi += bias_s[col + 2 * e + 1];
+            if (p.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+          }
+          o[e] = pack_bf16x2(lo, hi);
+        }
+        if (DGRAD && p.mask) {
+          const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(p.mask + off)), m1 = __ldg(reinterpret_cast<const uint4*>(p.mask + off) + 1);
+          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            // bf16 activations are >= 0 after ReLU: keep a half-word where the mask half-word is a positive number
+            const uint32_t mm = mw[e];
+            const uint32_t keep = (((mm & 0x7fffu) != 0 && !(mm & 0x8000u)) ? 0x0000ffffu : 0u) |
+                                  (((mm & 0x7fff0000u) != 0 && !(mm & 0x80000000u)) ? 0xffff0000u : 0u);
+            o[e] &= keep;
+          }
+        }
+        uint4* out = reinterpret_cast<uint4*>(p.y + off);
+        out[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        out[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+      ++ti;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, TCOLS);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn halo_encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+int halo_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+template <int NTOT, bool DGRAD>
+int launch_halo(const CUtensorMap& tm, const HaloParams& p, int smem, cudaStream_t st) {
+  auto kern = conv_halo_kernel<NTOT, DGRAD>;
+  static int configured = 0;
+  if (configured < smem) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      hulc2_set_error("conv_halo: cannot raise dynamic shared memory limit");
+      return HULC2_ELAUNCH;
+    }
+    configured = smem;
+  }
+  const int grid = p.ntiles < halo_sms() ? p.ntiles : halo_sms();
+  kern<<<grid, NT_HALO, smem, st>>>(tm, p);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+}  // namespace
+
+bool hulc2_conv_halo_enabled() {
+  static const bool off = getenv("HULC2_CONV_HALO") && atoi(getenv("HULC2_CONV_HALO")) == 0;
+  return !off && halo_encode_fn() != nullptr;
+}
+
+// src: bf16 NHWC [F, Hs, Ws, 64].  Fills the geometry-derived fields of `p` (tiles, stages, deltas must be set by the
+// caller: BH, PW, PH, i_min, j_min, ntaps, delta[], cls*[], NT, BNc, ncls, oH, oW, oS) and launches.
+// Returns HULC2_ENOTIMPL when the shape does not fit (the caller then uses the gather kernel).
+int hulc2_conv_halo_launch(const void* src, int F, int Hs, int Ws, HaloParams p, bool dgrad, cudaStream_t st) {
+  EncodeTiledFn encode = halo_encode_fn();
+  if (!encode) return HULC2_ENOTIMPL;
+  if (p.PW > 256 || p.PH > 256 || p.BH < 1 || p.BH * p.PW > 128 || p.ntaps < 1 || p.ntaps > 16) return HULC2_ENOTIMPL;
+  if (p.NT != 64 && p.NT != 128) return HULC2_ENOTIMPL;
+  if (((uintptr_t)src & 15) != 0) return HULC2_ENOTIMPL;
+  int dmax = 0;
+  for (int t = 0; t < p.ntaps; ++t) dmax = p.delta[t] > dmax ? p.delta[t] : dmax;
+  int rows = p.PH * p.PW > dmax + 128 ? p.PH * p.PW : dmax + 128;
+  p.stage_bytes = ((rows * 128) + 1023) & ~1023;
+  const int w_bytes = p.NT * p.ntaps * 128;
+  int stages = (227 * 1024 - 2048 - w_bytes - 1024) / p.stage_bytes;
+  if (stages > MAX_ST) stages = MAX_ST;
+  if (stages < 2) return HULC2_ENOTIMPL;
+  p.stages = stages;
+  p.F = F;
+  p.ntiles = F * p.tiles_per_frame;
+  if (p.ntiles <= 0) return HULC2_OK;
+
+  CUtensorMap tm;
+  cuuint64_t dims[4] = {64u, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)F};
+  cuuint64_t strides[3] = {128u, (cuuint64_t)Ws * 128u, (cuuint64_t)Hs * Ws * 128u};
+  cuuint32_t box[4] = {64u, (cuuint32_t)p.PW, (cuuint32_t)p.PH, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return HULC2_ENOTIMPL;
+  const int smem = stages * p.stage_bytes + w_bytes + 1024;
+  if (!dgrad) return p.NT == 64 ? launch_halo<64, false>(tm, p, smem, st) : HULC2_ENOTIMPL;
+  return p.NT == 64 ? launch_halo<64, true>(tm, p, smem, st) : launch_halo<128, true>(tm, p, smem, st);
+}

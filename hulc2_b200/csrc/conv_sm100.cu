@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "sm100.cuh"
+#include "conv_halo.cuh"
 #include "../../include/hulc2_b200.h"
 
 using namespace sm100;
@@ -634,6 +635,20 @@ int hulc2_convb_fwd(const hulc2_convb_args* a, cudaStream_t st) {
   if (int e = check_convb(a)) return e;
   if (!hulc2_convb_supported(a->C, a->Cout, a->KH, a->KW, a->stride)) { hulc2_set_error("convb_fwd: unsupported shape"); return HULC2_ENOTIMPL; }
   const int OH = (a->H - a->KH) / a->stride + 1, OW = (a->W - a->KW) / a->stride + 1;
+  if (a->C == 64 && a->Cout == 64 && a->stride == 1 && a->KH * a->KW <= 16 && a->W <= 128 && hulc2_conv_halo_enabled()) {
+    // halo-tile path: one TMA box per tile, tap windows addressed by shifted UMMA descriptors (conv_halo_sm100.cu)
+    HaloParams h{};
+    h.w = (const uint8_t*)a->w; h.bias = a->bias; h.mask = nullptr; h.y = (uint8_t*)a->y; h.relu = a->relu;
+    h.NT = h.BNc = 64; h.ncls = 1;
+    h.PW = a->W; h.BH = 128 / h.PW < OH ? 128 / h.PW : OH; h.PH = h.BH + a->KH - 1;
+    h.i_min = 0; h.j_min = 0; h.ntaps = a->KH * a->KW;
+    for (int t = 0; t < h.ntaps; ++t) h.delta[t] = (short)((t / a->KW) * h.PW + t % a->KW);
+    h.tiles_per_frame = hulc2_cdiv(OH, h.BH);
+    h.oH = OH; h.oW = OW; h.oS = 1;
+    h.clsH[0] = (short)OH; h.clsW[0] = (short)OW; h.clsPh[0] = h.clsPw[0] = 0;
+    const int rc = hulc2_conv_halo_launch(a->x, a->F, a->H, a->W, h, false, st);
+    if (rc != HULC2_ENOTIMPL) return rc;
+  }
   ConvParams p{};
   p.x = (const uint8_t*)a->x; p.w = (const uint8_t*)a->w; p.bias = a->bias; p.mask = nullptr; p.y = (uint8_t*)a->y;
   p.ncls = 1; p.N = a->Cout; p.relu = a->relu;
@@ -660,6 +675,32 @@ int hulc2_convb_dgrad(const hulc2_convb_args* a, cudaStream_t st) {
   if (a->Cout % 8 != 0 || (a->C != 32 && a->C != 64) || a->stride > 2) { hulc2_set_error("convb_dgrad: unsupported shape"); return HULC2_ENOTIMPL; }
   const int s = a->stride;
   const int OH = (a->H - a->KH) / s + 1, OW = (a->W - a->KW) / s + 1;
+  if (a->Cout == 64 && hulc2_conv_halo_enabled() &&
+      ((s == 1 && a->C == 64 && a->KH * a->KW <= 16) || (s == 2 && a->C == 32 && a->KH == 4 && a->KW == 4))) {
+    // halo-tile path over dZ (64 channels per pixel); zero padding = TMA out-of-range fill.  s == 2: the four parity
+    // classes (2 x 2 taps each) share one halo tile, their packed weights are stacked along N.
+    HaloParams h{};
+    h.w = (const uint8_t*)a->w; h.bias = nullptr; h.mask = (const uint8_t*)a->xmask; h.y = (uint8_t*)a->dx; h.relu = 0;
+    h.BNc = a->C; h.ncls = s * s; h.NT = h.ncls * h.BNc;
+    const int KA = a->KH / s, KB = a->KW / s;                    // taps per class along each axis
+    const int mH = (a->H + s - 1) / s, mW = (a->W + s - 1) / s;  // largest class
+    h.PW = mW + KB - 1; h.i_min = -(KA - 1); h.j_min = -(KB - 1);
+    if (h.PW <= 128) {
+      h.BH = 128 / h.PW < mH ? 128 / h.PW : mH; h.PH = h.BH + KA - 1;
+      h.ntaps = KA * KB;
+      for (int t = 0; t < h.ntaps; ++t) h.delta[t] = (short)((KA - 1 - t / KB) * h.PW + (KB - 1 - t % KB));
+      h.tiles_per_frame = hulc2_cdiv(mH, h.BH);
+      h.oH = a->H; h.oW = a->W; h.oS = s;
+      for (int ph = 0; ph < s; ++ph)
+        for (int pw = 0; pw < s; ++pw) {
+          const int c = ph * s + pw;
+          h.clsH[c] = (short)((a->H - ph + s - 1) / s); h.clsW[c] = (short)((a->W - pw + s - 1) / s);
+          h.clsPh[c] = (short)ph; h.clsPw[c] = (short)pw;
+        }
+      const int rc = hulc2_conv_halo_launch(a->dy, a->F, OH, OW, h, true, st);
+      if (rc != HULC2_ENOTIMPL) return rc;
+    }
+  }
   ConvParams p{};
   p.x = (const uint8_t*)a->dy; p.w = (const uint8_t*)a->w; p.bias = nullptr; p.mask = (const uint8_t*)a->xmask; p.y = (uint8_t*)a->dx;
   p.N = a->C; p.relu = 0;
