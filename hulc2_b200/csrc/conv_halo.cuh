@@ -24,4 +24,5 @@ struct HaloParams {
 };
 
 bool hulc2_conv_halo_enabled();
+int hulc2_conv_halo_pitch(int pw);
 int hulc2_conv_halo_launch(const void* src, int F, int Hs, int Ws, HaloParams p, bool dgrad, cudaStream_t st);

@@ -44,7 +44,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 template <int NTOT, bool DGRAD>
 __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[MAX_ST], empty_bar[MAX_ST], tfull_bar[2], tempty_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[MAX_ST], empty_bar[MAX_ST], tfull_bar[8], tempty_bar[8];
   __shared__ uint32_t tmem_slot;
   __shared__ float bias_s[NTOT];
 
@@ -54,12 +54,18 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
   const uint32_t a_smem = base;                                 // ST halo tiles
   const uint32_t w_smem = base + ST * (uint32_t)p.stage_bytes;  // ntaps tiles of [NTOT rows][128 B]
   constexpr uint32_t W_TILE = NTOT * 128;
-  constexpr uint32_t TCOLS = 2 * NTOT;                          // double-buffered accumulator
+  // G tiles can be in flight at once with their MMAs interleaved tap by tap (each into its own accumulator).  Measured:
+  // G = 4 is SLOWER than G = 1 (conv3 fwd 0.283 -> 0.334 ms), i.e. the ~110 cycles per 128 x 64 x 16 MMA seen in ncu
+  // (tensor pipe 32 % active) are not accumulator-chain latency but the operand fetch from shared memory: 4 KB of A +
+  // 2 KB of B per MMA (SS mode, ~64 B/clk).  Kept generic; G = 1 is the double-buffered pipeline.
+  constexpr int G = 1;
+  constexpr int NB = 2 * G;
+  constexpr uint32_t TCOLS = NB * NTOT;
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), TCOLS);
   if (tid == 32) {
     for (uint32_t s = 0; s < ST; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 256); }
+    for (int b = 0; b < NB; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 256); }
     mbar_fence_init();
   }
   if (tid < NTOT) bias_s[tid] = (!DGRAD && p.bias) ? p.bias[tid] : 0.f;
@@ -95,25 +101,42 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
     }
     __syncwarp();
   } else if (warp == 8) {
-    // ===================================================== MMA issuer (one thread)
+    // ===================================================== MMA issuer (one thread): groups of G tiles, interleaved
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc(128, NTOT, false, false);
-      uint32_t s = 0, ph = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const uint32_t buf = ti & 1;
-        mbar_wait(smem_u32(&tempty_bar[buf]), ((ti >> 1) & 1) ^ 1);       // epilogue drained this accumulator
-        mbar_wait(smem_u32(&full_bar[s]), ph);                           // halo tile landed
-        tc_fence_after();
-        const uint32_t tile_addr = a_smem + s * (uint32_t)p.stage_bytes;
-        for (int t = 0; t < p.ntaps; ++t) {
-          const uint64_t ad = make_desc(tile_addr + (uint32_t)p.delta[t] * 128u, 0), bd = make_desc(w_smem + t * W_TILE, 0);
+      const int step = (int)gridDim.x;
+      uint32_t cnt = 0;                                          // tiles of this CTA issued so far
+      for (int tile0 = blockIdx.x; tile0 < p.ntiles; tile0 += G * step) {
+        uint32_t taddr[G], acc[G], sidx[G], bidx[G];
+        int n = 0;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_d + buf * NTOT, ad + 2 * k, bd + 2 * k, IDESC, (t > 0 || k > 0) ? 1u : 0u);
+        for (int j = 0; j < G; ++j) {
+          if (tile0 + j * step >= p.ntiles) break;
+          const uint32_t c = cnt + j;
+          bidx[j] = c % NB; sidx[j] = c % ST;
+          mbar_wait(smem_u32(&tempty_bar[bidx[j]]), ((c / NB) & 1) ^ 1);   // epilogue drained this accumulator
+          mbar_wait(smem_u32(&full_bar[sidx[j]]), (c / ST) & 1);          // halo tile landed
+          taddr[j] = a_smem + sidx[j] * (uint32_t)p.stage_bytes;
+          acc[j] = tmem_d + bidx[j] * NTOT;
+          n = j + 1;
         }
-        umma_commit(smem_u32(&empty_bar[s]));                            // halo tile reusable once these MMAs retire
-        umma_commit(smem_u32(&tfull_bar[buf]));                          // accumulator complete
-        if (++s == ST) { s = 0; ph ^= 1; }
-        ++ti;
+        tc_fence_after();
+        for (int t = 0; t < p.ntaps; ++t) {
+          const uint32_t doff = (uint32_t)p.delta[t] * 128u;
+          const uint64_t bd = make_desc(w_smem + t * W_TILE, 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+              if (j < n) umma_bf16(acc[j], make_desc(taddr[j] + doff, 0) + 2 * k, bd + 2 * k, IDESC, (t > 0 || k > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j)
+          if (j < n) {
+            umma_commit(smem_u32(&empty_bar[sidx[j]]));          // halo tile reusable once these MMAs retire
+            umma_commit(smem_u32(&tfull_bar[bidx[j]]));          // accumulator complete
+          }
+        cnt += n;
       }
     }
     __syncwarp();
@@ -128,8 +151,26 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int f = tile / p.tiles_per_frame, tr = tile - f * p.tiles_per_frame;
       const int i = tr * p.BH + il;
-      const uint32_t buf = ti & 1;
-      mbar_wait_relaxed(smem_u32(&tfull_bar[buf]), (ti >> 1) & 1);
+      const uint32_t buf = ti % NB, par = (ti / NB) & 1;
+      // output addresses and the ReLU-mask words of this thread's chunks BEFORE waiting for the accumulator: the loads'
+      // latency hides behind the tile's MMAs
+      constexpr int NCH = HC / 16;
+      long long off[NCH];
+      bool ok[NCH];
+      uint4 mk[NCH][2];
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        const int col = half * HC + q * 16;             // first of 16 accumulator columns: one class, 16 channels
+        const int cls = col / BNc, ch = col - cls * BNc;
+        ok[q] = il < p.BH && i < p.clsH[cls] && jl < p.clsW[cls];
+        const long long opix = ((long long)f * p.oH + i * p.oS + p.clsPh[cls]) * p.oW + jl * p.oS + p.clsPw[cls];
+        off[q] = (opix * BNc + ch) * 2;
+        if (DGRAD && p.mask && ok[q]) {
+          mk[q][0] = __ldg(reinterpret_cast<const uint4*>(p.mask + off[q]));
+          mk[q][1] = __ldg(reinterpret_cast<const uint4*>(p.mask + off[q]) + 1);
+        }
+      }
+      mbar_wait_relaxed(smem_u32(&tfull_bar[buf]), par);
       tc_fence_after();
       uint32_t acc[HC];
 #pragma unroll
@@ -139,13 +180,9 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
       tc_fence_before();
       mbar_arrive(smem_u32(&tempty_bar[buf]));
 #pragma unroll
-      for (int c = 0; c < HC; c += 16) {
-        const int col = half * HC + c;                  // first of 16 accumulator columns: one class, 16 channels
-        const int cls = col / BNc, ch = col - cls * BNc;
-        const bool ok = il < p.BH && i < p.clsH[cls] && jl < p.clsW[cls];
-        if (!ok) continue;
-        const long long opix = ((long long)f * p.oH + i * p.oS + p.clsPh[cls]) * p.oW + jl * p.oS + p.clsPw[cls];
-        const long long off = (opix * BNc + ch) * 2;
+      for (int q = 0; q < NCH; ++q) {
+        if (!ok[q]) continue;
+        const int c = q * 16, col = half * HC + c;
         uint32_t o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -157,8 +194,7 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
           o[e] = pack_bf16x2(lo, hi);
         }
         if (DGRAD && p.mask) {
-          const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(p.mask + off)), m1 = __ldg(reinterpret_cast<const uint4*>(p.mask + off) + 1);
-          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          const uint32_t mw[8] = {mk[q][0].x, mk[q][0].y, mk[q][0].z, mk[q][0].w, mk[q][1].x, mk[q][1].y, mk[q][1].z, mk[q][1].w};
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             // bf16 activations are >= 0 after ReLU: keep a half-word where the mask half-word is a positive number
@@ -168,7 +204,7 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
             o[e] &= keep;
           }
         }
-        uint4* out = reinterpret_cast<uint4*>(p.y + off);
+        uint4* out = reinterpret_cast<uint4*>(p.y + off[q]);
         out[0] = make_uint4(o[0], o[1], o[2], o[3]);
         out[1] = make_uint4(o[4], o[5], o[6], o[7]);
       }
@@ -221,6 +257,12 @@ int launch_halo(const CUtensorMap& tm, const HaloParams& p, int smem, cudaStream
 }
 
 }  // namespace
+
+int hulc2_conv_halo_pitch(int pw) {
+  // experiment knob: round the raster pitch up to a multiple of HULC2_HALO_PITCH_ALIGN (extra columns are TMA zero fill)
+  static const int al = getenv("HULC2_HALO_PITCH_ALIGN") ? atoi(getenv("HULC2_HALO_PITCH_ALIGN")) : 1;
+  return al > 1 ? (pw + al - 1) / al * al : pw;
+}
 
 bool hulc2_conv_halo_enabled() {
   static const bool off = getenv("HULC2_CONV_HALO") && atoi(getenv("HULC2_CONV_HALO")) == 0;

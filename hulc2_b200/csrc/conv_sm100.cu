@@ -640,7 +640,7 @@ int hulc2_convb_fwd(const hulc2_convb_args* a, cudaStream_t st) {
     HaloParams h{};
     h.w = (const uint8_t*)a->w; h.bias = a->bias; h.mask = nullptr; h.y = (uint8_t*)a->y; h.relu = a->relu;
     h.NT = h.BNc = 64; h.ncls = 1;
-    h.PW = a->W; h.BH = 128 / h.PW < OH ? 128 / h.PW : OH; h.PH = h.BH + a->KH - 1;
+    h.PW = hulc2_conv_halo_pitch(a->W); h.BH = 128 / h.PW < OH ? 128 / h.PW : OH; h.PH = h.BH + a->KH - 1;
     h.i_min = 0; h.j_min = 0; h.ntaps = a->KH * a->KW;
     for (int t = 0; t < h.ntaps; ++t) h.delta[t] = (short)((t / a->KW) * h.PW + t % a->KW);
     h.tiles_per_frame = hulc2_cdiv(OH, h.BH);
@@ -684,7 +684,7 @@ int hulc2_convb_dgrad(const hulc2_convb_args* a, cudaStream_t st) {
     h.BNc = a->C; h.ncls = s * s; h.NT = h.ncls * h.BNc;
     const int KA = a->KH / s, KB = a->KW / s;                    // taps per class along each axis
     const int mH = (a->H + s - 1) / s, mW = (a->W + s - 1) / s;  // largest class
-    h.PW = mW + KB - 1; h.i_min = -(KA - 1); h.j_min = -(KB - 1);
+    h.PW = hulc2_conv_halo_pitch(mW + KB - 1); h.i_min = -(KA - 1); h.j_min = -(KB - 1);
     if (h.PW <= 128) {
       h.BH = 128 / h.PW < mH ? 128 / h.PW : mH; h.PH = h.BH + KA - 1;
       h.ntaps = KA * KB;
