@@ -312,10 +312,13 @@ int hulc2_rnn_persistent_launch(const float* add, const float* w, const float* i
        (uintptr_t)(final_out ? final_out : out)) & 15)
     return HULC2_ENOTIMPL;
   const int smem = (H / KT) * (int)W_TILE + STAGES * (int)A_TILE + 1024;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(rnn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return HULC2_ENOTIMPL;
-    configured = true;
+  static int configured = 0;               // largest dynamic shared memory size opted in so far (it grows with H)
+  if (configured < smem) {
+    if (cudaFuncSetAttribute(rnn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      cudaGetLastError();
+      return HULC2_ENOTIMPL;
+    }
+    configured = smem;
   }
   RnnParams p;
   p.add = add; p.w = w; p.init = init; p.mask = mask; p.out = out; p.final_out = final_out;

