@@ -10,11 +10,14 @@ namespace {
 
 struct Ws {
   float *imn, *txn, *sim, *rlse, *clse, *inorm, *tnorm, *dsm;
+  int P;   // row pitch of imn / txn = D + 1: the similarity phase reads txn[c * P + d] with c across lanes -- a pitch of D = 32
+           // floats would put all 32 lanes on one shared-memory bank (measured: 67 of the kernel's 92 us)
 };
 // intermediates live in shared memory when they fit (B <= ~140 at D = 32: every shipped batch size), else in the workspace
 __device__ __forceinline__ Ws carve(float* w, int B, int D) {
   Ws s;
-  s.imn = w; s.txn = s.imn + (long long)B * D; s.sim = s.txn + (long long)B * D;
+  s.P = D + 1;
+  s.imn = w; s.txn = s.imn + (long long)B * s.P; s.sim = s.txn + (long long)B * s.P;
   s.rlse = s.sim + (long long)B * B; s.clse = s.rlse + B; s.inorm = s.clse + B; s.tnorm = s.inorm + B;
   s.dsm = s.tnorm + B;
   return s;
@@ -30,13 +33,13 @@ __device__ void infonce_forward_phases(const float* img, const float* txt, const
     for (int d = lane; d < D; d += 32) { float x = img[(long long)r * D + d], y = txt[(long long)r * D + d]; a += x * x; b += y * y; }
     a = sqrtf(warp_sum(a)); b = sqrtf(warp_sum(b));
     if (lane == 0) { w.inorm[r] = a; w.tnorm[r] = b; }
-    for (int d = lane; d < D; d += 32) { w.imn[(long long)r * D + d] = img[(long long)r * D + d] / a; w.txn[(long long)r * D + d] = txt[(long long)r * D + d] / b; }
+    for (int d = lane; d < D; d += 32) { w.imn[(long long)r * w.P + d] = img[(long long)r * D + d] / a; w.txn[(long long)r * w.P + d] = txt[(long long)r * D + d] / b; }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < B * B; i += blockDim.x) {
     int r = i / B, c = i - r * B;
     float s = 0.f;
-    for (int d = 0; d < D; ++d) s = fmaf(scale * w.imn[(long long)r * D + d], w.txn[(long long)c * D + d], s);
+    for (int d = 0; d < D; ++d) s = fmaf(scale * w.imn[(long long)r * w.P + d], w.txn[(long long)c * w.P + d], s);
     w.sim[i] = s;
   }
   __syncthreads();
@@ -103,8 +106,8 @@ __global__ void __launch_bounds__(512) infonce_bwd_kernel(const float* __restric
     float a = 0.f, b = 0.f;
     for (int c = 0; c < B; ++c) {
       if (use && (!use[c] || !use[r])) continue;
-      a = fmaf(w.dsm[(long long)r * B + c], w.txn[(long long)c * D + d], a);
-      b = fmaf(w.dsm[(long long)c * B + r], w.imn[(long long)c * D + d], b);
+      a = fmaf(w.dsm[(long long)r * B + c], w.txn[(long long)c * w.P + d], a);
+      b = fmaf(w.dsm[(long long)c * B + r], w.imn[(long long)c * w.P + d], b);
     }
     dimg[i] = scale * a;   // temporarily d(imn)
     dtxt[i] = scale * b;   // temporarily d(txn)
@@ -117,16 +120,16 @@ __global__ void __launch_bounds__(512) infonce_bwd_kernel(const float* __restric
       continue;
     }
     float da = 0.f, db = 0.f;
-    for (int d = lane; d < D; d += 32) { da += w.imn[(long long)r * D + d] * dimg[(long long)r * D + d]; db += w.txn[(long long)r * D + d] * dtxt[(long long)r * D + d]; }
+    for (int d = lane; d < D; d += 32) { da += w.imn[(long long)r * w.P + d] * dimg[(long long)r * D + d]; db += w.txn[(long long)r * w.P + d] * dtxt[(long long)r * D + d]; }
     da = warp_sum(da); db = warp_sum(db);
     for (int d = lane; d < D; d += 32) {
-      dimg[(long long)r * D + d] = (dimg[(long long)r * D + d] - w.imn[(long long)r * D + d] * da) / w.inorm[r];
-      dtxt[(long long)r * D + d] = (dtxt[(long long)r * D + d] - w.txn[(long long)r * D + d] * db) / w.tnorm[r];
+      dimg[(long long)r * D + d] = (dimg[(long long)r * D + d] - w.imn[(long long)r * w.P + d] * da) / w.inorm[r];
+      dtxt[(long long)r * D + d] = (dtxt[(long long)r * D + d] - w.txn[(long long)r * w.P + d] * db) / w.tnorm[r];
     }
   }
 }
 
-long long ws_floats(int B, int D) { return 2LL * B * D + 2LL * B * B + 4LL * B; }
+long long ws_floats(int B, int D) { return 2LL * B * (D + 1) + 2LL * B * B + 4LL * B; }
 const long long kSmemMax = 200 * 1024;
 
 }  // namespace

@@ -253,7 +253,8 @@ int hulc2_tcp_to_world(const float* action, const float* robot_obs, int robot_di
 
 /* ------------------------------------------------------------------ InfoNCE (hulc2.py:472-508)
  * img,txt [B,D] projected features (un-normalised); use [B] u8 row mask (null = all); logit_scale device scalar.
- * fwd: loss[0]; saves nothing (bwd recomputes).  workspace >= (2*B*D + B*B + 4*B) floats. */
+ * fwd: loss[0]; saves nothing (bwd recomputes).  workspace >= (2*B*(D+1) + 2*B*B + 4*B) floats (only
+ * used when that exceeds 200 KB of shared memory). */
 int hulc2_infonce_fwd(const float* img, const float* txt, const unsigned char* use, const float* logit_scale,
                       float* loss, int B, int D, void* workspace, long long workspace_bytes, hulc2_stream_t stream);
 int hulc2_infonce_bwd(const float* img, const float* txt, const unsigned char* use, const float* logit_scale,
