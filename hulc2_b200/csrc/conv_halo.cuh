@@ -19,10 +19,14 @@ struct HaloParams {
   int ntaps;
   int oH, oW, oS;          // output tensor dims; pixel stride of a class (1, or 2 for stacked classes)
   int stages, stage_bytes;
-  short delta[16];         // per tap: raster offset of its window inside the halo tile
+  int nparts, part_bytes;  // sub-tiles per stage (2 = even / odd source rows of a stride-2 forward conv) and their byte pitch
+  short delta[16];         // per tap: raster offset of its window inside its sub-tile
+  short part[16];          // per tap: sub-tile index
   short clsH[4], clsW[4], clsPh[4], clsPw[4];  // valid rows / columns of each class and its pixel parity offsets
 };
 
 bool hulc2_conv_halo_enabled();
 int hulc2_conv_halo_pitch(int pw);
 int hulc2_conv_halo_launch(const void* src, int F, int Hs, int Ws, HaloParams p, bool dgrad, cudaStream_t st);
+// stride-2 forward conv over a 32-channel source (two pixels = one 128-byte row; even / odd source rows = two sub-tiles)
+int hulc2_conv_halo_launch_s2(const void* src, int F, int Hs, int Ws, HaloParams p, cudaStream_t st);

@@ -37,6 +37,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -89,13 +93,19 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm) : "memory");
       uint32_t s = 0, ph = 1;
-      const uint32_t bytes = (uint32_t)(p.PH * p.PW) * 128u;
+      const uint32_t bytes = (uint32_t)(p.PH * p.PW) * 128u * (uint32_t)p.nparts;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const int f = tile / p.tiles_per_frame, ti = tile - f * p.tiles_per_frame;
         mbar_wait(smem_u32(&empty_bar[s]), ph);
         const uint32_t bar = smem_u32(&full_bar[s]);
         mbar_expect_tx(bar, bytes);
-        tma_load_4d(a_smem + s * (uint32_t)p.stage_bytes, &tm, bar, 0, p.j_min, ti * p.BH + p.i_min, f);
+        const uint32_t dst = a_smem + s * (uint32_t)p.stage_bytes;
+        if (p.nparts == 1) {
+          tma_load_4d(dst, &tm, bar, 0, p.j_min, ti * p.BH + p.i_min, f);
+        } else {            // 5-D view (64 = 2 pixels x 32 ch, pixel pair, row parity, half row, frame): one box per row parity
+          tma_load_5d(dst, &tm, bar, 0, p.j_min, 0, ti * p.BH + p.i_min, f);
+          tma_load_5d(dst + (uint32_t)p.part_bytes, &tm, bar, 0, p.j_min, 1, ti * p.BH + p.i_min, f);
+        }
         if (++s == ST) { s = 0; ph ^= 1; }
       }
     }
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
         }
         tc_fence_after();
         for (int t = 0; t < p.ntaps; ++t) {
-          const uint32_t doff = (uint32_t)p.delta[t] * 128u;
+          const uint32_t doff = (uint32_t)p.delta[t] * 128u + (uint32_t)p.part[t] * (uint32_t)p.part_bytes;
           const uint64_t bd = make_desc(w_smem + t * W_TILE, 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -269,38 +279,64 @@ bool hulc2_conv_halo_enabled() {
   return !off && halo_encode_fn() != nullptr;
 }
 
-// src: bf16 NHWC [F, Hs, Ws, 64].  Fills the geometry-derived fields of `p` (tiles, stages, deltas must be set by the
-// caller: BH, PW, PH, i_min, j_min, ntaps, delta[], cls*[], NT, BNc, ncls, oH, oW, oS) and launches.
-// Returns HULC2_ENOTIMPL when the shape does not fit (the caller then uses the gather kernel).
-int hulc2_conv_halo_launch(const void* src, int F, int Hs, int Ws, HaloParams p, bool dgrad, cudaStream_t st) {
-  EncodeTiledFn encode = halo_encode_fn();
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Common tail of the launchers: ring sizing + launch.  `rank`-D tensor map already described by dims/strides/box.
+static int halo_finish(const void* src, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box, HaloParams p,
+                       bool dgrad, cudaStream_t st) {
+  EncodeTiledFn2 encode = (EncodeTiledFn2)halo_encode_fn();
   if (!encode) return HULC2_ENOTIMPL;
   if (p.PW > 256 || p.PH > 256 || p.BH < 1 || p.BH * p.PW > 128 || p.ntaps < 1 || p.ntaps > 16) return HULC2_ENOTIMPL;
   if (p.NT != 64 && p.NT != 128) return HULC2_ENOTIMPL;
   if (((uintptr_t)src & 15) != 0) return HULC2_ENOTIMPL;
   int dmax = 0;
   for (int t = 0; t < p.ntaps; ++t) dmax = p.delta[t] > dmax ? p.delta[t] : dmax;
-  int rows = p.PH * p.PW > dmax + 128 ? p.PH * p.PW : dmax + 128;
-  p.stage_bytes = ((rows * 128) + 1023) & ~1023;
+  const int rows = p.PH * p.PW > dmax + 128 ? p.PH * p.PW : dmax + 128;
+  p.part_bytes = ((rows * 128) + 1023) & ~1023;
+  p.stage_bytes = p.part_bytes * p.nparts;
   const int w_bytes = p.NT * p.ntaps * 128;
   int stages = (227 * 1024 - 2048 - w_bytes - 1024) / p.stage_bytes;
   if (stages > MAX_ST) stages = MAX_ST;
   if (stages < 2) return HULC2_ENOTIMPL;
   p.stages = stages;
-  p.F = F;
-  p.ntiles = F * p.tiles_per_frame;
+  p.ntiles = p.F * p.tiles_per_frame;
   if (p.ntiles <= 0) return HULC2_OK;
-
   CUtensorMap tm;
-  cuuint64_t dims[4] = {64u, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)F};
-  cuuint64_t strides[3] = {128u, (cuuint64_t)Ws * 128u, (cuuint64_t)Hs * Ws * 128u};
-  cuuint32_t box[4] = {64u, (cuuint32_t)p.PW, (cuuint32_t)p.PH, 1u};
-  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-  CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), dims, strides, box, estr,
+  cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(src), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return HULC2_ENOTIMPL;
   const int smem = stages * p.stage_bytes + w_bytes + 1024;
   if (!dgrad) return p.NT == 64 ? launch_halo<64, false>(tm, p, smem, st) : HULC2_ENOTIMPL;
   return p.NT == 64 ? launch_halo<64, true>(tm, p, smem, st) : launch_halo<128, true>(tm, p, smem, st);
+}
+
+// src: bf16 NHWC [F, Hs, Ws, 64].  The caller sets the geometry (BH, PW, PH, i_min, j_min, ntaps, delta[], cls*[], NT, BNc,
+// ncls, oH, oW, oS, tiles_per_frame).  Returns HULC2_ENOTIMPL when the shape does not fit (the caller then uses the
+// gather kernel).
+int hulc2_conv_halo_launch(const void* src, int F, int Hs, int Ws, HaloParams p, bool dgrad, cudaStream_t st) {
+  p.F = F; p.nparts = 1;
+  for (int t = 0; t < 16; ++t) p.part[t] = 0;
+  cuuint64_t dims[4] = {64u, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)F};
+  cuuint64_t strides[3] = {128u, (cuuint64_t)Ws * 128u, (cuuint64_t)Hs * Ws * 128u};
+  cuuint32_t box[4] = {64u, (cuuint32_t)p.PW, (cuuint32_t)p.PH, 1u};
+  return halo_finish(src, 4, dims, strides, box, p, dgrad, st);
+}
+
+// src: bf16 NHWC [F, Hs, Ws, 32], stride-2 forward conv.  View (64 = 2 pixels x 32 ch | pixel pair | row parity | half row |
+// frame): output column j reads pairs j + b/2, output row i reads half rows i + a/2 of parity a & 1 -- two sub-tiles per
+// stage, every tap again a uniform raster shift.  p.part[] / p.delta[] are set by the caller.
+int hulc2_conv_halo_launch_s2(const void* src, int F, int Hs, int Ws, HaloParams p, cudaStream_t st) {
+  p.F = F; p.nparts = 2;
+  const cuuint64_t row = (cuuint64_t)Ws * 64u;      // bytes per source row
+  if (row % 16) return HULC2_ENOTIMPL;
+  // Hs / 2 half rows and Ws / 2 pairs (floor): every coordinate inside these bounds addresses a pixel of its own frame, and a
+  // valid output never needs more (largest source row read is 2 (OH - 1) + 3 <= Hs - 1)
+  cuuint64_t dims[5] = {64u, (cuuint64_t)(Ws / 2), 2u, (cuuint64_t)(Hs / 2), (cuuint64_t)F};
+  cuuint64_t strides[4] = {128u, row, 2u * row, (cuuint64_t)Hs * row};
+  cuuint32_t box[5] = {64u, (cuuint32_t)p.PW, 1u, (cuuint32_t)p.PH, 1u};
+  return halo_finish(src, 5, dims, strides, box, p, false, st);
 }

@@ -649,6 +649,25 @@ int hulc2_convb_fwd(const hulc2_convb_args* a, cudaStream_t st) {
     const int rc = hulc2_conv_halo_launch(a->x, a->F, a->H, a->W, h, false, st);
     if (rc != HULC2_ENOTIMPL) return rc;
   }
+  if (a->C == 32 && a->Cout == 64 && a->stride == 2 && a->KH == 4 && a->KW == 4 && OW + 1 <= 128 && hulc2_conv_halo_enabled()) {
+    // stride-2 halo path: two pixels = one 128-byte row, even / odd source rows in two sub-tiles (conv_halo_sm100.cu);
+    // tap t = kh * 2 + kw / 2 <-> the t-th 64-element chunk of the packed weight rows [(kh, kw, ci)]
+    HaloParams h{};
+    h.w = (const uint8_t*)a->w; h.bias = a->bias; h.mask = nullptr; h.y = (uint8_t*)a->y; h.relu = a->relu;
+    h.NT = h.BNc = 64; h.ncls = 1;
+    h.PW = OW + 1; h.BH = 128 / h.PW < OH ? 128 / h.PW : OH; h.PH = h.BH + 1;
+    h.i_min = 0; h.j_min = 0; h.ntaps = 8;
+    for (int t = 0; t < 8; ++t) {
+      const int kh = t >> 1, bp = t & 1;
+      h.part[t] = (short)(kh & 1);
+      h.delta[t] = (short)((kh >> 1) * h.PW + bp);
+    }
+    h.tiles_per_frame = hulc2_cdiv(OH, h.BH);
+    h.oH = OH; h.oW = OW; h.oS = 1;
+    h.clsH[0] = (short)OH; h.clsW[0] = (short)OW; h.clsPh[0] = h.clsPw[0] = 0;
+    const int rc = hulc2_conv_halo_launch_s2(a->x, a->F, a->H, a->W, h, st);
+    if (rc != HULC2_ENOTIMPL) return rc;
+  }
   ConvParams p{};
   p.x = (const uint8_t*)a->x; p.w = (const uint8_t*)a->w; p.bias = a->bias; p.mask = nullptr; p.y = (uint8_t*)a->y;
   p.ncls = 1; p.N = a->Cout; p.relu = a->relu;
