@@ -16,8 +16,8 @@
 // The s*s = 4 parity classes of conv2's input gradient share one halo tile: their packed weights are stacked along N
 // (4 x 32 input channels = one 128-column accumulator), the epilogue scatters the classes to their strided pixels.
 //
-// Warp roles (320 threads): warps 0-7 epilogue (TMEM lane quarter = w % 4, column half = w / 4), warp 8 MMA issuer,
-// warp 9 TMA producer.  Reference: hulc2/models/perceptual_encoders/vision_network.py:38-48 (+ autograd).
+// Warp roles (416 threads): warps 0-7 epilogue (TMEM lane quarter = w % 4, column half = w / 4), warp 8 TMA producer,
+// warps 9-12 MMA issuers (4 for N = 64, 2 for N = 128; round-robin over the CTA's tiles, one TMEM accumulator each).  Reference: hulc2/models/perceptual_encoders/vision_network.py:38-48 (+ autograd).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -30,7 +30,7 @@ using namespace sm100;
 
 namespace {
 
-constexpr int NT_HALO = 320;
+constexpr int NT_HALO = 416;     // 8 epilogue warps + TMA producer (warp 8) + 4 MMA issuers (warps 9-12)
 constexpr int MAX_ST = 8;
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -48,7 +48,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 template <int NTOT, bool DGRAD>
 __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[MAX_ST], empty_bar[MAX_ST], tfull_bar[8], tempty_bar[8];
+  __shared__ __align__(8) uint64_t full_bar[MAX_ST], empty_bar[MAX_ST], tfull_bar[4], tempty_bar[4];
   __shared__ uint32_t tmem_slot;
   __shared__ float bias_s[NTOT];
 
@@ -58,12 +58,12 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
   const uint32_t a_smem = base;                                 // ST halo tiles
   const uint32_t w_smem = base + ST * (uint32_t)p.stage_bytes;  // ntaps tiles of [NTOT rows][128 B]
   constexpr uint32_t W_TILE = NTOT * 128;
-  // G tiles can be in flight at once with their MMAs interleaved tap by tap (each into its own accumulator).  Measured:
-  // G = 4 is SLOWER than G = 1 (conv3 fwd 0.283 -> 0.334 ms), i.e. the ~110 cycles per 128 x 64 x 16 MMA seen in ncu
-  // (tensor pipe 32 % active) are not accumulator-chain latency but the operand fetch from shared memory: 4 KB of A +
-  // 2 KB of B per MMA (SS mode, ~64 B/clk).  Kept generic; G = 1 is the double-buffered pipeline.
-  constexpr int G = 1;
-  constexpr int NB = 2 * G;
+  // Several MMA issuer threads take the CTA's tiles round-robin, each with its own TMEM accumulator: with N <= 128 a
+  // 128 x N x 16 MMA occupies the tensor pipe for only 32-64 cycles while ONE thread issues a tcgen05.mma every ~110 cycles
+  // (measured: 1 -> 2 issuers, conv3 forward 0.332 -> 0.179 ms, conv2 forward 0.308 -> 0.197 ms).
+  // (Interleaving several tiles' MMAs from ONE thread was measured and does not help: 0.283 -> 0.334 ms on conv3 forward.)
+  constexpr int NISS = 256 / NTOT >= 4 ? 4 : 2;   // N = 64: 4 issuers x 64 columns; N = 128: 2 issuers (TMEM: NB x N <= 512)
+  constexpr int NB = NISS < 2 ? 2 : NISS;
   constexpr uint32_t TCOLS = NB * NTOT;
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), TCOLS);
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
 
-  if (warp == 9) {
+  if (warp == 8) {
     // ===================================================== TMA producer (one thread): one halo tile per output tile
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm) : "memory");
@@ -110,47 +110,33 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
       }
     }
     __syncwarp();
-  } else if (warp == 8) {
-    // ===================================================== MMA issuer (one thread): groups of G tiles, interleaved
+  } else if (warp >= 9 && warp < 9 + NISS) {
+    // ===================================================== MMA issuers (one thread each): issuer w takes tiles c = w, w + NISS, ..
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc(128, NTOT, false, false);
-      const int step = (int)gridDim.x;
-      uint32_t cnt = 0;                                          // tiles of this CTA issued so far
-      for (int tile0 = blockIdx.x; tile0 < p.ntiles; tile0 += G * step) {
-        uint32_t taddr[G], acc[G], sidx[G], bidx[G];
-        int n = 0;
+      const uint32_t w = (uint32_t)(warp - 9);
+      uint32_t c = 0, s = 0, ph = 0;                             // c: tiles of this CTA so far; s / ph: ring slot and parity of tile c
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++c) {
+        if ((c & (NISS - 1)) == w) {
+          const uint32_t buf = c % NB;                           // == w: each issuer owns one accumulator
+          mbar_wait(smem_u32(&tempty_bar[buf]), ((c / NB) & 1) ^ 1);     // epilogue drained this accumulator
+          mbar_wait(smem_u32(&full_bar[s]), ph);                         // halo tile landed
+          tc_fence_after();
+          const uint32_t tile_addr = a_smem + s * (uint32_t)p.stage_bytes;
+          for (int t = 0; t < p.ntaps; ++t) {
+            const uint64_t ad = make_desc(tile_addr + (uint32_t)p.delta[t] * 128u + (uint32_t)p.part[t] * (uint32_t)p.part_bytes, 0);
+            const uint64_t bd = make_desc(w_smem + t * W_TILE, 0);
 #pragma unroll
-        for (int j = 0; j < G; ++j) {
-          if (tile0 + j * step >= p.ntiles) break;
-          const uint32_t c = cnt + j;
-          bidx[j] = c % NB; sidx[j] = c % ST;
-          mbar_wait(smem_u32(&tempty_bar[bidx[j]]), ((c / NB) & 1) ^ 1);   // epilogue drained this accumulator
-          mbar_wait(smem_u32(&full_bar[sidx[j]]), (c / ST) & 1);          // halo tile landed
-          taddr[j] = a_smem + sidx[j] * (uint32_t)p.stage_bytes;
-          acc[j] = tmem_d + bidx[j] * NTOT;
-          n = j + 1;
-        }
-        tc_fence_after();
-        for (int t = 0; t < p.ntaps; ++t) {
-          const uint32_t doff = (uint32_t)p.delta[t] * 128u + (uint32_t)p.part[t] * (uint32_t)p.part_bytes;
-          const uint64_t bd = make_desc(w_smem + t * W_TILE, 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int j = 0; j < G; ++j)
-              if (j < n) umma_bf16(acc[j], make_desc(taddr[j] + doff, 0) + 2 * k, bd + 2 * k, IDESC, (t > 0 || k > 0) ? 1u : 0u);
-        }
-#pragma unroll
-        for (int j = 0; j < G; ++j)
-          if (j < n) {
-            umma_commit(smem_u32(&empty_bar[sidx[j]]));          // halo tile reusable once these MMAs retire
-            umma_commit(smem_u32(&tfull_bar[bidx[j]]));          // accumulator complete
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_d + buf * NTOT, ad + 2 * k, bd + 2 * k, IDESC, (t > 0 || k > 0) ? 1u : 0u);
           }
-        cnt += n;
+          umma_commit(smem_u32(&empty_bar[s]));                          // halo tile reusable once these MMAs retire
+          umma_commit(smem_u32(&tfull_bar[buf]));                        // accumulator complete
+        }
+        if (++s == ST) { s = 0; ph ^= 1; }
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < 8) {
     // ===================================================== epilogue: row m = 32 * (w % 4) + lane, columns (w / 4) * NTOT/2 ..
     constexpr int HC = NTOT / 2;
     const int lq = warp & 3, half = warp >> 2;
@@ -299,7 +285,9 @@ static int halo_finish(const void* src, int rank, const cuuint64_t* dims, const 
   const int w_bytes = p.NT * p.ntaps * 128;
   int stages = (227 * 1024 - 2048 - w_bytes - 1024) / p.stage_bytes;
   if (stages > MAX_ST) stages = MAX_ST;
-  if (stages < 2) return HULC2_ENOTIMPL;
+  // >= one ring slot per MMA issuer (4 for N = 64, 2 for N = 128): an issuer then never waits on a slot whose previous fill is
+  // still pending, which is what keeps the parity waits of several issuers unambiguous
+  if (stages < (p.NT == 64 ? 4 : 2)) return HULC2_ENOTIMPL;
   p.stages = stages;
   p.ntiles = p.F * p.tiles_per_frame;
   if (p.ntiles <= 0) return HULC2_OK;
