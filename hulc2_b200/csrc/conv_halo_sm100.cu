@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
       constexpr int NCH = HC / 16;
       long long off[NCH];
       bool ok[NCH];
-      uint4 mk[NCH][2];
+      uint32_t mk[NCH][8];
 #pragma unroll
       for (int q = 0; q < NCH; ++q) {
         const int col = half * HC + q * 16;             // first of 16 accumulator columns: one class, 16 channels
@@ -161,10 +161,7 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
         ok[q] = il < p.BH && i < p.clsH[cls] && jl < p.clsW[cls];
         const long long opix = ((long long)f * p.oH + i * p.oS + p.clsPh[cls]) * p.oW + jl * p.oS + p.clsPw[cls];
         off[q] = (opix * BNc + ch) * 2;
-        if (DGRAD && p.mask && ok[q]) {
-          mk[q][0] = __ldg(reinterpret_cast<const uint4*>(p.mask + off[q]));
-          mk[q][1] = __ldg(reinterpret_cast<const uint4*>(p.mask + off[q]) + 1);
-        }
+        if (DGRAD && p.mask && ok[q]) ldg256_nc(p.mask + off[q], mk[q]);      // 32 bytes = this chunk's 16 channels
       }
       mbar_wait_relaxed(smem_u32(&tfull_bar[buf]), par);
       tc_fence_after();
@@ -190,19 +187,16 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
           o[e] = pack_bf16x2(lo, hi);
         }
         if (DGRAD && p.mask) {
-          const uint32_t mw[8] = {mk[q][0].x, mk[q][0].y, mk[q][0].z, mk[q][0].w, mk[q][1].x, mk[q][1].y, mk[q][1].z, mk[q][1].w};
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             // bf16 activations are >= 0 after ReLU: keep a half-word where the mask half-word is a positive number
-            const uint32_t mm = mw[e];
+            const uint32_t mm = mk[q][e];
             const uint32_t keep = (((mm & 0x7fffu) != 0 && !(mm & 0x8000u)) ? 0x0000ffffu : 0u) |
                                   (((mm & 0x7fff0000u) != 0 && !(mm & 0x80000000u)) ? 0xffff0000u : 0u);
             o[e] &= keep;
           }
         }
-        uint4* out = reinterpret_cast<uint4*>(p.y + off[q]);
-        out[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        out[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        stg256(p.y + off[q], o);
       }
       ++ti;
     }

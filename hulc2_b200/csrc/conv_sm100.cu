@@ -289,12 +289,12 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
       tc_fence_before();
       mbar_arrive(smem_u32(&tempty_bar[buf]));
       if (rv) {
-        uint4* out = reinterpret_cast<uint4*>(p.y + opix * (BN * 2) + half * HC * 2);
+        uint8_t* out = p.y + opix * (BN * 2) + half * HC * 2;
 #pragma unroll
-        for (int c = 0; c < HC; c += 8) {
-          uint32_t o[4];
+        for (int c = 0; c < HC; c += 16) {                     // 16 channels = 32 bytes per 256-bit store
+          uint32_t o[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
+          for (int e = 0; e < 8; ++e) {
             float lo = __uint_as_float(acc[c + 2 * e]), hi = __uint_as_float(acc[c + 2 * e + 1]);
             if (!DGRAD) {
               lo += bias_s[half * HC + c + 2 * e]; hi += bias_s[half * HC + c + 2 * e + 1];
@@ -303,9 +303,10 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
             o[e] = pack_bf16x2(lo, hi);
           }
           if (DGRAD && p.mask) {
-            const uint32_t mw[4] = {mk[c >> 3].x, mk[c >> 3].y, mk[c >> 3].z, mk[c >> 3].w};
+            const uint32_t mw[8] = {mk[c >> 3].x, mk[c >> 3].y, mk[c >> 3].z, mk[c >> 3].w,
+                                    mk[(c >> 3) + 1].x, mk[(c >> 3) + 1].y, mk[(c >> 3) + 1].z, mk[(c >> 3) + 1].w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < 8; ++e) {
               // bf16 activations are >= 0 after ReLU: keep a half-word where the mask half-word is a positive number
               const uint32_t m = mw[e];
               const uint32_t keep = (((m & 0x7fffu) != 0 && !(m & 0x8000u)) ? 0x0000ffffu : 0u) |
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
               o[e] &= keep;
             }
           }
-          out[c >> 3] = make_uint4(o[0], o[1], o[2], o[3]);
+          stg256(out + c * 2, o);
         }
       }
       ++ti;
