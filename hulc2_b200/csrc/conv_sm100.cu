@@ -326,9 +326,9 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad
-constexpr int WG_KP = 32;                     // pixels (contraction rows) per stage
+// pixels (contraction rows) per stage = template parameter KP: 32, or 64 (two per producer thread, which halves the per-stage
+// bookkeeping -- barrier round trip, wait_group, proxy fence -- per byte moved) when four 64-pixel stages fit in shared memory
 constexpr int WG_MAX_STAGES = 12;
-constexpr uint32_t WG_BLK = WG_KP * 128;      // one 64-wide M/N block of a stage: 32 k-rows x 128 B = 4 KB
 constexpr int WG_MAX_BLK = 10;                // <= 5 M-tiles of 128 -> 320 TMEM columns
 
 struct WgradParams {
@@ -341,12 +341,14 @@ struct WgradParams {
   int K;                 // kconv (multiple of 64); data blocks = K/64; ones block = K/64; nblk (even) >= K/64 + 1
   int nblk;
   int cout8;             // Cout / 8 (4 or 8)
-  int nstages;           // ceil(P / 32)
+  int nstages;           // ceil(P / WG_KP)
   int stages, lag;       // ring depth / publish lag (see conv_igemm_kernel)
   int delta[72];         // per 16-byte chunk of kconv: offset in 16-byte units
 };
 
+template <int WG_KP>
 __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  constexpr uint32_t WG_BLK = WG_KP * 128;      // one 64-wide M/N block of a stage: KP k-rows x 128 B
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[WG_MAX_STAGES], empty_bar[WG_MAX_STAGES], done_bar;
   __shared__ uint32_t tmem_slot;
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant
   const int send = (int)((long long)p.nstages * (blockIdx.x + 1) / gridDim.x);
 
   if (warp > MMA_WARP) {
-    // producers: 256 threads = 32 pixels x 8 chunks; each thread copies its chunk column of every block of its pixel
+    // producers: 256 threads = 32 pixels x 8 chunks, WG_KP / 32 passes; each thread copies its chunk column of every block of its pixels
     const int t = tid - (N_EPI + 32);
     const int c8 = t & 7, g = t >> 3;
     const uint32_t drow = swz128(g, c8);
@@ -392,19 +394,27 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant
     const bool has_dz = c8 < p.cout8;
     uint32_t s = 0, ph = 1, ps = 0, inflight = 0;
     for (int st = sbeg; st < send; ++st) {
-      const long long pix = (long long)st * WG_KP + g;
-      const bool ok = pix < p.P;
-      const uint32_t pu = ok ? (uint32_t)pix : 0u;
-      const uint32_t f = fdiv(pu, p.dHW), rem = pu - f * p.dHW.d;
-      const uint32_t i = fdiv(rem, p.dW), j = rem - i * p.dW.d;
-      const uint8_t* rp = p.x + ((long long)(int)(f * p.sF + i * p.sI + j * p.sJ) << 4);
-      const uint32_t nb = ok ? 16u : 0u;
+      const uint8_t* rp[WG_KP / 32];
+      uint32_t pu[WG_KP / 32], nb[WG_KP / 32];
+#pragma unroll
+      for (int q = 0; q < WG_KP / 32; ++q) {                  // this thread's pixels g, g + 32, ..: rows 32 q + g of every block
+        const long long pix = (long long)st * WG_KP + g + 32 * q;
+        const bool ok = pix < p.P;
+        pu[q] = ok ? (uint32_t)pix : 0u;
+        const uint32_t f = fdiv(pu[q], p.dHW), rem = pu[q] - f * p.dHW.d;
+        const uint32_t i = fdiv(rem, p.dW), j = rem - i * p.dW.d;
+        rp[q] = p.x + ((long long)(int)(f * p.sF + i * p.sI + j * p.sJ) << 4);
+        nb[q] = ok ? 16u : 0u;
+      }
       mbar_wait(smem_u32(&empty_bar[s]), ph);
       const uint32_t sb = base + s * stage_bytes + drow;
 #pragma unroll
-      for (int b = 0; b < 9; ++b)
-        if (b < nbd) cp_async16_ca(sb + b * WG_BLK, rp + ((long long)dl[b] << 4), nb);
-      if (has_dz) cp_async16(sb + p.nblk * WG_BLK, p.dz + (((long long)pu * p.cout8 + c8) << 4), nb);
+      for (int q = 0; q < WG_KP / 32; ++q) {
+#pragma unroll
+        for (int b = 0; b < 9; ++b)
+          if (b < nbd) cp_async16_ca(sb + b * WG_BLK + q * 4096, rp[q] + ((long long)dl[b] << 4), nb[q]);
+        if (has_dz) cp_async16(sb + p.nblk * WG_BLK + q * 4096, p.dz + (((long long)pu[q] * p.cout8 + c8) << 4), nb[q]);
+      }
       cp_async_commit();
       if (++s == WG_STAGES) { s = 0; ph ^= 1; }
       if (inflight == WG_LAG) {
@@ -764,7 +774,10 @@ int hulc2_convb_wgrad(const hulc2_convb_args* a, cudaStream_t st) {
   p.nblk = p.K / 64 + 1; if (p.nblk & 1) ++p.nblk;
   if (p.nblk > WG_MAX_BLK) { hulc2_set_error("convb_wgrad: kconv too large"); return HULC2_ENOTIMPL; }
   p.cout8 = a->Cout / 8;
-  p.nstages = hulc2_cdiv(p.P, WG_KP);
+  // 64-pixel stages when four of them fit (conv1: 5 blocks x 8 KB), else 32-pixel stages
+  const int KP = (p.nblk + 1) * 64 * 128 * 4 + 4096 <= 227 * 1024 ? 64 : 32;
+  const int WG_BLK = KP * 128;
+  p.nstages = hulc2_cdiv(p.P, KP);
   const int cpr = a->KW * a->C / 8;
   for (int q = 0; q < p.K / 8; ++q) {
     const int kh = q / cpr;
@@ -787,13 +800,15 @@ int hulc2_convb_wgrad(const hulc2_convb_args* a, cudaStream_t st) {
   const int smem = stages * (p.nblk + 1) * (int)WG_BLK + 1024;
   static int configured = 0;
   if (configured < smem) {
-    if (cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       hulc2_set_error("convb_wgrad: cannot raise dynamic shared memory limit");
       return HULC2_ELAUNCH;
     }
     configured = smem;
   }
-  conv_wgrad_kernel<<<grid, NT, smem, st>>>(p);
+  if (KP == 64) conv_wgrad_kernel<64><<<grid, NT, smem, st>>>(p);
+  else conv_wgrad_kernel<32><<<grid, NT, smem, st>>>(p);
   HULC2_CHECK_LAUNCH();
   const int total = (p.K + 1) * a->Cout;
   wgrad_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(p.partial, grid, p.nblk * 64, p.K, a->Cout, a->C, a->KH, a->KW, a->dw_layout,
