@@ -111,6 +111,8 @@ struct ConvParams {
   int w_bytes;           // total packed weight bytes
   int ntab;
   int stages, lag;       // A ring depth and publish lag (lag <= stages - 2)
+  int kts;               // k-tiles (64 k each) per ring slot: 1, or the whole K of a tile when that fits (one barrier round trip,
+                         // wait_group and proxy fence per tile instead of per k-tile: the producers are bookkeeping-bound)
   ConvClass cls[MAX_CLS];
   int2 table[MAX_TAB];   // per 16-byte chunk of K: {delta in 16-byte units, (a << 16) | b}
 };
@@ -128,8 +130,9 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t STAGES = (uint32_t)p.stages, LAG = (uint32_t)p.lag;
-  const uint32_t a_smem = base;                              // STAGES x 16 KB
-  const uint32_t w_smem = base + STAGES * A_STAGE;           // per class: K/64 tiles of [BN rows][128 B]
+  const uint32_t KTS = (uint32_t)p.kts, SLOT = KTS * A_STAGE;
+  const uint32_t a_smem = base;                              // STAGES x KTS x 16 KB
+  const uint32_t w_smem = base + STAGES * SLOT;              // per class: K/64 tiles of [BN rows][128 B]
   constexpr uint32_t W_TILE = BN * 128;
   constexpr uint32_t TCOLS = 2 * BN;                         // double-buffered accumulator
 
@@ -189,11 +192,12 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
       }
       const int nkt = cl.K / KT;
       const int2* tab = tab_s + cl.tab_off + c8;
-      for (int kt = 0; kt < nkt; ++kt) {
+      for (int kt0 = 0; kt0 < nkt; kt0 += (int)KTS) {
         mbar_wait(smem_u32(&empty_bar[s]), ph);
-        const int2 e = tab[kt * 8];
+        for (uint32_t kk = 0; kk < KTS; ++kk) {
+        const int2 e = tab[(kt0 + (int)kk) * 8];
         const long long doff = (long long)e.x << 4;
-        const uint32_t dst = a_smem + s * A_STAGE + dst_t;
+        const uint32_t dst = a_smem + s * SLOT + kk * A_STAGE + dst_t;
         if (DGRAD) {
           const int ta = e.y >> 16, tb = e.y & 0xffff;
 #pragma unroll
@@ -205,6 +209,7 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
         } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q) cp_async16_ca(dst + q * 4096, rptr[q] + doff, rij[q] == 0x7fff7fffu ? 0u : 16u);
+        }
         }
         cp_async_commit();
         if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -239,13 +244,16 @@ __global__ void __launch_bounds__(NT, 1) conv_igemm_kernel(const __grid_constant
         mbar_wait(smem_u32(&tempty_bar[buf]), ((ti >> 1) & 1) ^ 1);      // epilogue drained this accumulator
         tc_fence_after();
         const int nkt = cl.K / KT;
-        for (int kt = 0; kt < nkt; ++kt) {
+        for (int kt0 = 0; kt0 < nkt; kt0 += (int)KTS) {
           mbar_wait(smem_u32(&full_bar[s]), ph);
           tc_fence_after();
-          const uint64_t ad = make_desc(a_smem + s * A_STAGE, 0), bd = make_desc(w_smem + cl.w_off + kt * W_TILE, 0);
+          for (uint32_t kk = 0; kk < KTS; ++kk) {
+            const int kt = kt0 + (int)kk;
+            const uint64_t ad = make_desc(a_smem + s * SLOT + kk * A_STAGE, 0), bd = make_desc(w_smem + cl.w_off + kt * W_TILE, 0);
 #pragma unroll
-          for (int k = 0; k < KT / 16; ++k) umma_bf16(tmem_d + buf * BN, ad + 2 * k, bd + 2 * k, IDESC, (kt > 0 || k > 0) ? 1u : 0u);
-          umma_commit(smem_u32(&empty_bar[s]));                          // stage reusable once these MMAs retire
+            for (int k = 0; k < KT / 16; ++k) umma_bf16(tmem_d + buf * BN, ad + 2 * k, bd + 2 * k, IDESC, (kt > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));                          // slot reusable once these MMAs retire
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(smem_u32(&tfull_bar[buf]));                          // accumulator complete
@@ -570,14 +578,22 @@ int launch_igemm(const ConvParams& p, cudaStream_t st) {
   auto kern = conv_igemm_kernel<BN, DGRAD>;
   // Measured on B200: ring depth beyond 4 does not help (the gather is issue-bound, not latency-bound) while every
   // 16 KB stage is taken from the unified L1 that serves the overlapping im2col windows (dgrad k4s2: 0.72 -> 0.58 ms).
-  int stages = (227 * 1024 - 2048 - p.w_bytes - 1024) / (int)A_STAGE;
+  // whole-K ring slots when every class has the same, small number of k-tiles and 4 such slots fit next to the weights
+  int kts = 1;
+  {
+    const int nkt0 = p.cls[0].K / KT;
+    bool same = nkt0 >= 2 && nkt0 <= 4;
+    for (int c = 1; c < p.ncls; ++c) same = same && p.cls[c].K / KT == nkt0;
+    if (same && 4 * nkt0 * (int)A_STAGE + p.w_bytes + 4096 <= 227 * 1024 && !(getenv("HULC2_CONV_KTS1") && atoi(getenv("HULC2_CONV_KTS1")))) kts = nkt0;
+  }
+  int stages = (227 * 1024 - 2048 - p.w_bytes - 1024) / (kts * (int)A_STAGE);
   int want = 4;
   if (const char* e = getenv("HULC2_CONV_STAGES")) { int v = atoi(e); if (v >= 3 && v <= MAX_STAGES) want = v; }
   if (stages > want) stages = want;
   if (stages < 3) { hulc2_set_error("convb: packed weights do not fit in shared memory"); return HULC2_EINVAL; }
   ConvParams q = p;
-  q.stages = stages; q.lag = stages - 2;
-  const int smem = stages * (int)A_STAGE + p.w_bytes + 1024;
+  q.stages = stages; q.lag = stages - 2; q.kts = kts;
+  const int smem = stages * kts * (int)A_STAGE + p.w_bytes + 1024;
   static int configured = 0;
   if (configured < smem) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
