@@ -48,6 +48,8 @@ constexpr int EPI_WARPS = 8, PROD_WARPS = 8;
 constexpr int N_EPI = EPI_WARPS * 32, N_PROD = PROD_WARPS * 32;
 constexpr int MMA_WARP = EPI_WARPS;
 constexpr int NT = N_EPI + 32 + N_PROD;      // 544 threads
+constexpr int WG_MMA_WARP2 = EPI_WARPS + 1 + PROD_WARPS;  // weight-gradient kernel: second MMA issuer (warp 17)
+constexpr int NT_WG = NT + 32;                // 576 threads
 constexpr int MAX_CLS = 4;
 constexpr int MAX_TAB = 160;
 
@@ -355,7 +357,7 @@ struct WgradParams {
 };
 
 template <int WG_KP>
-__global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+__global__ void __launch_bounds__(NT_WG, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   constexpr uint32_t WG_BLK = WG_KP * 128;      // one 64-wide M/N block of a stage: KP k-rows x 128 B
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[WG_MAX_STAGES], empty_bar[WG_MAX_STAGES], done_bar;
@@ -370,16 +372,17 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), tcols);
   if (tid == 32) {
-    for (uint32_t s = 0; s < WG_STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), N_PROD); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    mbar_init(smem_u32(&done_bar), 1);
+    // two MMA issuers (below) each commit once per stage / at the end
+    for (uint32_t s = 0; s < WG_STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), N_PROD); mbar_init(smem_u32(&empty_bar[s]), 2); }
+    mbar_init(smem_u32(&done_bar), 2);
     mbar_fence_init();
   }
   // zero every stage, then fill the ones block (bf16 1.0 = 0x3F80) -- neither is touched by the producers
-  for (uint32_t o = tid * 16; o < WG_STAGES * stage_bytes; o += NT * 16)
+  for (uint32_t o = tid * 16; o < WG_STAGES * stage_bytes; o += NT_WG * 16)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(0u) : "memory");
   __syncthreads();
   for (uint32_t s = 0; s < WG_STAGES; ++s)
-    for (uint32_t o = tid * 16; o < WG_BLK; o += NT * 16)
+    for (uint32_t o = tid * 16; o < WG_BLK; o += NT_WG * 16)
       asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + s * stage_bytes + nbd * WG_BLK + o), "r"(0x3F803F80u) : "memory");
   fence_proxy_async();
   tc_fence_before();
@@ -391,7 +394,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant
   const int sbeg = (int)((long long)p.nstages * blockIdx.x / gridDim.x);
   const int send = (int)((long long)p.nstages * (blockIdx.x + 1) / gridDim.x);
 
-  if (warp > MMA_WARP) {
+  if (warp > MMA_WARP && warp < WG_MMA_WARP2) {
     // producers: 256 threads = 32 pixels x 8 chunks, WG_KP / 32 passes; each thread copies its chunk column of every block of its pixels
     const int t = tid - (N_EPI + 32);
     const int c8 = t & 7, g = t >> 3;
@@ -440,9 +443,13 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant
       mbar_arrive(smem_u32(&full_bar[ps]));
       if (++ps == WG_STAGES) ps = 0;
     }
-  } else if (warp == MMA_WARP) {
+  } else if (warp == MMA_WARP || warp == WG_MMA_WARP2) {
+    // Two MMA issuer threads split the M-tiles of dW^T (disjoint TMEM columns): one thread issues a tcgen05.mma only every
+    // ~110 cycles, and a 32-pixel stage of conv2 / conv3 needs 10 of them (K = 512 / 576) -- the issue time was the stage time.
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc(128, 64, true, true);
+      const int half = (nmt + 1) / 2;
+      const int mt0 = warp == MMA_WARP ? 0 : half, mt1 = warp == MMA_WARP ? half : nmt;
       uint32_t s = 0, ph = 0;
       for (int st = sbeg; st < send; ++st) {
         mbar_wait(smem_u32(&full_bar[s]), ph);
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_kernel(const __grid_constant
 #pragma unroll
         for (int ks = 0; ks < WG_KP / 16; ++ks) {
           const uint64_t bd = make_desc(sb + p.nblk * WG_BLK + ks * 2048, WG_BLK);
-          for (int mt = 0; mt < nmt; ++mt) {
+          for (int mt = mt0; mt < mt1; ++mt) {
             const uint64_t ad = make_desc(sb + mt * 2 * WG_BLK + ks * 2048, WG_BLK);
             umma_bf16(tmem_d + mt * 64, ad, bd, IDESC, (st > sbeg || ks > 0) ? 1u : 0u);
           }
@@ -823,8 +830,8 @@ int hulc2_convb_wgrad(const hulc2_convb_args* a, cudaStream_t st) {
     }
     configured = smem;
   }
-  if (KP == 64) conv_wgrad_kernel<64><<<grid, NT, smem, st>>>(p);
-  else conv_wgrad_kernel<32><<<grid, NT, smem, st>>>(p);
+  if (KP == 64) conv_wgrad_kernel<64><<<grid, NT_WG, smem, st>>>(p);
+  else conv_wgrad_kernel<32><<<grid, NT_WG, smem, st>>>(p);
   HULC2_CHECK_LAUNCH();
   const int total = (p.K + 1) * a->Cout;
   wgrad_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(p.partial, grid, p.nblk * 64, p.K, a->Cout, a->C, a->KH, a->KW, a->dw_layout,
