@@ -64,8 +64,6 @@ __global__ void __launch_bounds__(256) frames_u8_pack_kernel(const uint8_t* __re
                                                              uint8_t* __restrict__ xs, int S, int C, int H, int W, int H4, int W4, int R,
                                                              int nseg) {
   extern __shared__ __align__(16) uint8_t rows[];           // [4R][W*C]
-  __shared__ float lut[256];                                // 256 exact values instead of two IEEE divisions per element
-  lut[threadIdx.x & 255] = norm_u8(threadIdx.x & 255);
   const int f = blockIdx.x / nseg, I0 = (blockIdx.x - f * nseg) * R;
   const int nI = min(R, H4 - I0);
   const uint8_t* frame = store + (size_t)src_frame(f, S, start, len) * H * W * C;
@@ -78,12 +76,14 @@ __global__ void __launch_bounds__(256) frames_u8_pack_kernel(const uint8_t* __re
     const int Il = q / per_row, r = q - Il * per_row;
     const int J = r / cpc, e0 = (r - J * cpc) * 8;
     const int ci = e0 >> 4, a = 4 * Il + ((e0 >> 2) & 3);
+    // bf16 output: (2 v - 255) * fp32(1/255) rounds to the SAME bf16 as the reference chain ((v / 255) - 0.5) / 0.5 for all 256
+    // grey levels (checked exhaustively on the host and by test_all_256_grey_levels_exact), without a table lookup per element
     float v[8];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int x = min(max(4 * J + b + dx, 0), W - 1);
-      v[b] = lut[rows[a * rb + x * C + ci]];
-      v[4 + b] = lut[rows[(a + 1) * rb + x * C + ci]];
+      v[b] = __fmul_rn(__int2float_rn(2 * (int)rows[a * rb + x * C + ci] - 255), 1.0f / 255.0f);
+      v[4 + b] = __fmul_rn(__int2float_rn(2 * (int)rows[(a + 1) * rb + x * C + ci] - 255), 1.0f / 255.0f);
     }
     out[q] = make_uint4(bf16x2(v[0], v[1]), bf16x2(v[2], v[3]), bf16x2(v[4], v[5]), bf16x2(v[6], v[7]));
   }
