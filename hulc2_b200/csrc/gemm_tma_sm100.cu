@@ -39,6 +39,7 @@ struct TmaParams {
   __nv_bfloat16* C16;           // optional bf16 mirror of the output (same row addressing with ld16)
   long long ld16;
   int vec;                      // 16-byte epilogue accesses are legal for every pointer involved
+  int vec8;                     // ... and so are 32-byte ones (8 fp32 columns per 256-bit access)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
@@ -156,6 +157,47 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
           } else {
             for (int e = 0; e < 4; ++e) if (n + e < p.N) prow[n + e] = __uint_as_float(r[j + e]);
           }
+        }
+        continue;
+      }
+      if (p.vec8 && n0 + c + 32 <= p.N) {
+        // 8 columns per access: rows are >= 128 bytes apart across lanes, so every access is its own L1 wavefront -- 256-bit
+        // LDG/STG halve them (the big-output, small-K contractions are bound by exactly this: 4096x2048x128 took 80 us)
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const int n = n0 + c + j;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = E.alpha * __uint_as_float(r[j + e]);
+          uint32_t t[8];
+          if (E.bias) { ldg256_nc(E.bias + n, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += __uint_as_float(t[e]); }
+          if (E.add) { ldg256_nc(E.add + (long long)m * E.ld_add + n, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += __uint_as_float(t[e]); }
+          if (E.accumulate) {
+            const float4 t0 = *reinterpret_cast<const float4*>(E.C + crow + n), t1 = *reinterpret_cast<const float4*>(E.C + crow + n + 4);
+            v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w; v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+          }
+          if (E.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (E.mask) { ldg256_nc(E.mask + (long long)m * E.ld_mask + n, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(t[e]) > 0.f ? v[e] : 0.f; }
+          if (E.keep) {
+            const uint2 k2 = *reinterpret_cast<const uint2*>(E.keep + (long long)m * E.ld_keep + n);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = (((e < 4 ? k2.x : k2.y) >> (8 * (e & 3))) & 0xffu) ? v[e] * E.keep_scale : 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t[e] = __float_as_uint(v[e]);
+          stg256(E.C + crow + n, t);
+          if (p.C16)
+            *reinterpret_cast<uint4*>(p.C16 + (long long)m * p.ld16 + n) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
         continue;
       }
@@ -320,6 +362,13 @@ int hulc2_gemm_tma_impl(const hulc2_gemm_args* a, cudaStream_t st) {
   if (a->C16) vec = vec && al(a->C16, 8) && a->ld16 % 4 == 0;
   if (p.splits > 1) vec = al(p.partial, 16) && a->N % 4 == 0;
   p.vec = vec ? 1 : 0;
+  bool vec8 = vec && p.splits == 1 && al(a->C, 32) && a->ldc % 8 == 0 && a->c_inner == 0;
+  if (a->bias) vec8 = vec8 && al(a->bias, 32);
+  if (a->add) vec8 = vec8 && al(a->add, 32) && a->ld_add % 8 == 0;
+  if (a->mask) vec8 = vec8 && al(a->mask, 32) && a->ld_mask % 8 == 0;
+  if (a->keep) vec8 = vec8 && al(a->keep, 8) && a->ld_keep % 8 == 0;
+  if (a->C16) vec8 = vec8 && al(a->C16, 16) && a->ld16 % 8 == 0;
+  p.vec8 = vec8 ? 1 : 0;
 
   CUtensorMap ta, tb;
   bool ok = a_mn ? encode_map(&ta, a->A16, a->M, a->K, a_ld, 64) : encode_map(&ta, a->A16, a->K, a->M, a_ld, BM);
