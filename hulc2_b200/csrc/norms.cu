@@ -181,8 +181,9 @@ __global__ void spatial_softmax_kernel(const T* __restrict__ x, const float* __r
 // bf16 trunk variant: the whole frame [HW][C] is staged in shared memory with 16-byte loads (one HBM read), every pass
 // (max, sums, gradient) runs from shared memory, and the gradient is written back in place and stored with 16-byte
 // stores (one HBM write).  Thread (cp, g): channel pair cp = tid % (C/2), position group g of G = blockDim / (C/2).
+constexpr int SSM_NT = 512;   // threads per frame: 16 position groups x 32 channel pairs at C = 64; 3 frames (72 KB each) per SM
 template <bool BWD>
-__global__ void __launch_bounds__(256) ssm_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ x_map,
+__global__ void __launch_bounds__(SSM_NT, 3) ssm_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ x_map,
                                                        const float* __restrict__ y_map, const float* __restrict__ temperature,
                                                        float* __restrict__ out, const float* __restrict__ dout,
                                                        __nv_bfloat16* __restrict__ dx, float* __restrict__ dtemp, int HW, int C,
@@ -263,12 +264,12 @@ __global__ void __launch_bounds__(256) ssm_bf16_kernel(const __nv_bfloat16* __re
 }
 
 static size_t ssm_bf16_smem(int HW, int C) {
-  const int C2 = C / 2, G = 256 / C2;
+  const int C2 = C / 2, G = SSM_NT / C2;
   return (((size_t)HW * C * 2 + 15) & ~(size_t)15) + (size_t)(6 * G * C2 + 2 * HW) * sizeof(float);
 }
 // served when channel pairs tile a 256-thread block, rows are 16-byte multiples and 2 frames fit one SM's shared memory
 static bool ssm_bf16_ok(int HW, int C) {
-  return C >= 8 && C % 8 == 0 && C <= 512 && 256 % (C / 2) == 0 && ssm_bf16_smem(HW, C) <= 100 * 1024;
+  return C >= 8 && C % 8 == 0 && C <= 512 && SSM_NT % (C / 2) == 0 && ssm_bf16_smem(HW, C) <= 100 * 1024;
 }
 
 }  // namespace
@@ -336,7 +337,7 @@ int hulc2_spatial_softmax_fwd_bf16(const void* x, const float* x_map, const floa
     const size_t smem = ssm_bf16_smem(HW, C);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(ssm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
-    ssm_bf16_kernel<false><<<F, 256, smem, st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, out, nullptr, nullptr, nullptr, HW, C, 0);
+    ssm_bf16_kernel<false><<<F, SSM_NT, smem, st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, out, nullptr, nullptr, nullptr, HW, C, 0);
     HULC2_CHECK_LAUNCH();
     return HULC2_OK;
   }
@@ -356,7 +357,7 @@ int hulc2_spatial_softmax_bwd_bf16(const void* x, const float* x_map, const floa
     const size_t smem = ssm_bf16_smem(HW, C);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(ssm_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
-    ssm_bf16_kernel<true><<<F, 256, smem, st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, nullptr, dout, (__nv_bfloat16*)dx, dtemperature,
+    ssm_bf16_kernel<true><<<F, SSM_NT, smem, st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, nullptr, dout, (__nv_bfloat16*)dx, dtemperature,
                                                 HW, C, relu_mask);
     HULC2_CHECK_LAUNCH();
     return HULC2_OK;
