@@ -55,6 +55,7 @@ class GradBucketReducer:
 
     def _make_hook(self, bucket):
         def hook(param):
+            self.opt.land_grad(param)          # the gradient must sit in the arena before its bucket is reduced
             self._fired.add(id(param))
             bucket["pending"] -= 1
             if bucket["pending"] == 0:
@@ -86,6 +87,7 @@ class GradBucketReducer:
         for h in self._handles:
             h.wait()
         self._handles = []
+        self.opt.attach()                      # parameters without a gradient this step read as (reduced) zeros
         if self.used is None:
             self.used = set(self._fired)
 

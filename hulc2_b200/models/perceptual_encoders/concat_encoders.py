@@ -51,7 +51,7 @@ class _ConcatLayerNorm(torch.autograd.Function):
         for i, D in enumerate(ctx.Ds):
             f, g, mean, rstd = saved[4 * i : 4 * i + 4]
             dx = torch.empty(rows, D, device=dout.device, dtype=torch.float32)
-            dg = torch.zeros(D, device=dout.device, dtype=torch.float32)
+            dg = ops.grad_buffer(g, zero=True)
             db = torch.zeros(D, device=dout.device, dtype=torch.float32)
             call("hulc2_layernorm_bwd", dout.data_ptr() + 4 * off, ctx.total, f.data_ptr(), D, g.data_ptr(), mean.data_ptr(),
                  rstd.data_ptr(), dx.data_ptr(), D, None, None, 1.0, dg.data_ptr(), db.data_ptr(), rows, D)

@@ -147,6 +147,47 @@ def invalidate_weight_mirrors() -> None:
         a[1] = None
 
 
+# Gradient sinks: when the optimizer keeps all gradients in one arena (optim.FusedAdam), the FIRST gradient a backward
+# kernel produces for a parameter in a step is written straight into that parameter's arena slice and returned as the
+# gradient; with ``param.grad is None`` autograd's AccumulateGrad then adopts the tensor instead of launching
+# ``grad += new`` (108 parameters = ~120 tiny kernels per step).  Later contributions in the same step (a parameter used
+# twice) get fresh buffers and are accumulated by autograd as usual.
+_grad_views: dict = {}      # parameter data_ptr -> (gradient arena, offset, numel)
+_grad_claimed: set = set()
+direct_grads = True
+
+
+def register_grad_views(arena_g: torch.Tensor, params, offs) -> list:
+    keys = []
+    for prm, o in zip(params, offs):
+        _grad_views[prm.data_ptr()] = (arena_g, int(o), prm.numel())
+        keys.append(prm.data_ptr())
+    return keys
+
+
+def unregister_grad_views(keys) -> None:
+    for k in keys:
+        _grad_views.pop(k, None)
+
+
+def begin_grad_step() -> None:
+    """Start of a step (the gradient arena has just been zero-filled): every parameter's slice can be claimed again."""
+    _grad_claimed.clear()
+
+
+def grad_buffer(W: torch.Tensor, zero: bool = False) -> torch.Tensor:
+    """Buffer for a gradient of parameter ``W`` (same shape): its gradient-arena slice on the first request of a step,
+    else a fresh tensor (zero-filled when ``zero``; an arena slice is zero at the start of a step)."""
+    if direct_grads:
+        key = W.data_ptr()
+        ent = _grad_views.get(key)
+        if ent is not None and key not in _grad_claimed and ent[2] == W.numel() and ent[0].device == W.device:
+            _grad_claimed.add(key)
+            g, o, n = ent
+            return g[o : o + n].view(W.shape)
+    return torch.zeros_like(W, dtype=torch.float32) if zero else torch.empty_like(W, dtype=torch.float32)
+
+
 def weight16(W: torch.Tensor) -> torch.Tensor:
     """bf16 mirror of a (contiguous) parameter tensor, same shape."""
     ptr, n = W.data_ptr(), W.numel()
@@ -271,11 +312,11 @@ class MLPFunction(torch.autograd.Function):
                 in16 = mirrors[i]
                 ld_in = in16.shape[1]
                 if ctx.needs_input_grad[4 + 2 * i]:
-                    dW = torch.empty_like(W)
+                    dW = grad_buffer(W)
                     gemm16(N, K, M, g16, 1, ldg, in16, 1, ld_in, dW, K)          # dW = g^T inp (both MN-major)
                     grads[2 * i] = dW
                 if ctx.needs_input_grad[5 + 2 * i]:
-                    db = torch.empty(N, device=W.device, dtype=torch.float32)
+                    db = grad_buffer(wb[2 * i + 1])
                     colsum(g, N, M, N, db)
                     grads[2 * i + 1] = db
                 if i > 0 or ctx.needs_input_grad[0]:
@@ -296,11 +337,11 @@ class MLPFunction(torch.autograd.Function):
             inp = x2 if i == 0 else acts[i - 1]
             ld_in = _ld(x2) if i == 0 else K
             if ctx.needs_input_grad[4 + 2 * i]:
-                dW = torch.empty_like(W)
+                dW = grad_buffer(W)
                 gemm(N, K, M, g, 1, N, inp, 1, ld_in, dW, K)           # dW = g^T inp
                 grads[2 * i] = dW
             if ctx.needs_input_grad[5 + 2 * i]:
-                db = torch.empty(N, device=W.device, dtype=torch.float32)
+                db = grad_buffer(wb[2 * i + 1])
                 colsum(g, N, M, N, db)
                 grads[2 * i + 1] = db
             if i > 0 or ctx.needs_input_grad[0]:
@@ -469,10 +510,11 @@ def convb_dgrad(dy, w_oihw, xmask, F, C, H, W, Cout, k, stride, name="conv") -> 
     return dx
 
 
-def convb_wgrad(x, dy, F, C, H, W, Cout, k, stride, dw_shape, dw_layout=0, name="conv"):
-    """(dw fp32 in dw_shape (OIHW), db fp32 [Cout]) from the bf16 NHWC input x and output gradient dy."""
+def convb_wgrad(x, dy, F, C, H, W, Cout, k, stride, dw_shape, dw_layout=0, name="conv", param=None):
+    """(dw fp32 in dw_shape (OIHW), db fp32 [Cout]) from the bf16 NHWC input x and output gradient dy.  ``param``: the weight
+    tensor the gradient belongs to (lets the result land directly in the optimizer's gradient arena, see grad_buffer)."""
     ws = workspace(x.device)
-    dw = torch.empty(dw_shape, device=x.device, dtype=torch.float32)
+    dw = grad_buffer(param) if param is not None and tuple(param.shape) == tuple(dw_shape) else torch.empty(dw_shape, device=x.device, dtype=torch.float32)
     db = torch.empty(Cout, device=x.device, dtype=torch.float32)
     a = _cb(F, C, H, W, Cout, k, stride)
     a.x, a.dy, a.dw, a.db, a.dw_layout = x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), dw_layout
@@ -584,11 +626,11 @@ def _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3):
     """dz3 = bf16 gradient wrt conv3's pre-activation (already ReLU-masked).  Returns the six parameter gradients."""
     F_, H4, W4, C16 = xs.shape
     H1, W1, H2, W2 = y1.shape[1], y1.shape[2], y2.shape[1], y2.shape[2]
-    dw3, db3 = convb_wgrad(y2, dz3, F_, 64, H2, W2, 64, 3, 1, tuple(w3.shape), name="c3")
+    dw3, db3 = convb_wgrad(y2, dz3, F_, 64, H2, W2, 64, 3, 1, tuple(w3.shape), name="c3", param=w3)
     dz2 = convb_dgrad(dz3, w3, y2, F_, 64, H2, W2, 64, 3, 1, name="c3")
-    dw2, db2 = convb_wgrad(y1, dz2, F_, 32, H1, W1, 64, 4, 2, tuple(w2.shape), name="c2")
+    dw2, db2 = convb_wgrad(y1, dz2, F_, 32, H1, W1, 64, 4, 2, tuple(w2.shape), name="c2", param=w2)
     dz1 = convb_dgrad(dz2, w2, y1, F_, 32, H1, W1, 64, 4, 2, name="c2")
-    dw1, db1 = convb_wgrad(xs, dz1, F_, C16, H4, W4, 32, 2, 1, tuple(w1.shape), dw_layout=1, name="c1")
+    dw1, db1 = convb_wgrad(xs, dz1, F_, C16, H4, W4, 32, 2, 1, tuple(w1.shape), dw_layout=1, name="c1", param=w1)
     return {"w1": dw1, "b1": db1, "w2": dw2, "b2": db2, "w3": dw3, "b3": db3}
 
 
@@ -714,7 +756,7 @@ class LayerNormFunction(torch.autograd.Function):
         dy2 = _rows2d(dy.contiguous())
         dx = torch.empty(rows, D, device=dy.device, dtype=torch.float32)
         dres = torch.empty(rows, D, device=dy.device, dtype=torch.float32) if ctx.has_res else None
-        dgamma = torch.zeros(D, device=dy.device, dtype=torch.float32)
+        dgamma = grad_buffer(gamma, zero=True)
         dbeta = torch.zeros(D, device=dy.device, dtype=torch.float32)
         call("hulc2_layernorm_bwd", dy2.data_ptr(), D, t.data_ptr(), _ld(t), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
              dx.data_ptr(), D, _p(dres), _p(ctx.keep), ctx.keep_scale, dgamma.data_ptr(), dbeta.data_ptr(), rows, D)
@@ -1044,14 +1086,14 @@ class RNNDecoderFunction(torch.autograd.Function):
         call("hulc2_copy2d", dH1.data_ptr(), step, dz1.data_ptr(), step, S, step, 0)
         _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
         call("hulc2_rnn_relu_bwd", dz1.data_ptr(), wh1.data_ptr(), H1.data_ptr(), None, S, B, H, prec, ws.data_ptr(), ws.numel())
-        dwh1 = torch.empty_like(wh1)
+        dwh1 = grad_buffer(wh1)
         if S > 1:
             gemm(H, H, (S - 1) * B, dz1, 1, H, H1, 1, H, dwh1, H, a_off=step)
         else:
             call("hulc2_fill", dwh1.data_ptr(), dwh1.numel(), 0.0)
         if ctx.has_h0:
             gemm(H, H, B, dz1, 1, H, h01, 1, H, dwh1, H, accumulate=True)
-        dwi1 = torch.empty_like(wi1)
+        dwi1 = grad_buffer(wi1)
         gemm(H, H, S * B, dz1, 1, H, H0, 1, H, dwi1, H)
         db1 = torch.empty(H, device=dev, dtype=torch.float32)
         colsum(dz1, H, S * B, H, db1)
@@ -1059,7 +1101,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         gemm(S * B, H, H, dz1, H, 1, wi1, 1, H, dz0, H)                      # dH0 = dz1 W_ih1
         _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
         call("hulc2_rnn_relu_bwd", dz0.data_ptr(), wh0.data_ptr(), H0.data_ptr(), None, S, B, H, prec, ws.data_ptr(), ws.numel())
-        dwh0 = torch.empty_like(wh0)
+        dwh0 = grad_buffer(wh0)
         if S > 1:
             gemm(H, H, (S - 1) * B, dz0, 1, H, H0, 1, H, dwh0, H, a_off=step)
         else:
@@ -1070,7 +1112,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         colsum(dz0, H, S * B, H, db0)
         dzsum = torch.empty(B, H, device=dev, dtype=torch.float32)
         colsum(dz0, B * H, S, B * H, dzsum)                                  # sum over time
-        dwi0 = torch.empty_like(wi0)
+        dwi0 = grad_buffer(wi0)
         gemm(H, P, B, dzsum, 1, H, plan, 1, P, dwi0, In)
         gemm(H, Es, S * B, dz0, 1, H, embT, 1, Es, dwi0, In, c_off=P)
         gemm(H, G, B, dzsum, 1, H, goal, 1, G, dwi0, In, c_off=P + Es)
@@ -1104,14 +1146,14 @@ class RNNDecoderFunction(torch.autograd.Function):
         _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
         call("hulc2_rnn_relu_bwd", dz1.data_ptr(), wh1.data_ptr(), H1.data_ptr(), None, S, B, H, 1, ws.data_ptr(), ws.numel())
         dz1h, H1h = to_bf16(dz1), to_bf16(H1)
-        dwh1 = torch.empty_like(wh1)
+        dwh1 = grad_buffer(wh1)
         if S > 1:
             gemm16(H, H, (S - 1) * B, dz1h, 1, H, H1h, 1, H, dwh1, H, a_off=step)
         else:
             call("hulc2_fill", dwh1.data_ptr(), dwh1.numel(), 0.0)
         if ctx.has_h0:
             gemm(H, H, B, dz1, 1, H, h01, 1, H, dwh1, H, accumulate=True)
-        dwi1 = torch.empty_like(wi1)
+        dwi1 = grad_buffer(wi1)
         gemm16(H, H, S * B, dz1h, 1, H, H0h, 1, H, dwi1, H)
         db1 = torch.empty(H, device=dev, dtype=torch.float32)
         colsum(dz1, H, S * B, H, db1)
@@ -1120,7 +1162,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
         call("hulc2_rnn_relu_bwd", dz0.data_ptr(), wh0.data_ptr(), H0.data_ptr(), None, S, B, H, 1, ws.data_ptr(), ws.numel())
         dz0h = to_bf16(dz0)
-        dwh0 = torch.empty_like(wh0)
+        dwh0 = grad_buffer(wh0)
         if S > 1:
             gemm16(H, H, (S - 1) * B, dz0h, 1, H, H0h, 1, H, dwh0, H, a_off=step)
         else:
@@ -1132,7 +1174,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         dzsum = torch.empty(B, H, device=dev, dtype=torch.float32)
         colsum(dz0, B * H, S, B * H, dzsum)                                      # sum over time
         dzsumh = to_bf16(dzsum)
-        dwi0 = torch.empty_like(wi0)
+        dwi0 = grad_buffer(wi0)
         gemm16(H, P, B, dzsumh, 1, H, plan16, 1, P, dwi0, In)
         gemm16(H, Es, S * B, dz0h, 1, H, embT16, 1, Es, dwi0, In, c_off=P)
         gemm16(H, G, B, dzsumh, 1, H, goal16, 1, ldg, dwi0, In, c_off=P + Es)
@@ -1263,7 +1305,7 @@ class GatedRNNDecoderFunction(torch.autograd.Function):
         dH1 = dH1.contiguous()
         dg1, dwh1, dbh1 = layer_bwd(dH1, H1, C1 if kind == "lstm" else None, sv1, wh1,
                                     h01 if ctx.has_h0 else None, c01 if ctx.has_c0 else None)
-        dwi1 = torch.empty_like(wi1)
+        dwi1 = grad_buffer(wi1)
         gemm(GH, H, S * B, dg1, 1, GH, H0, 1, H, dwi1, H)
         if kind == "gru":
             dbi1 = torch.empty(GH, **f32)
@@ -1281,7 +1323,7 @@ class GatedRNNDecoderFunction(torch.autograd.Function):
             dbi0 = dbh0.clone()
         dgsum = torch.empty(B, GH, **f32)
         colsum(dg0, B * GH, S, B * GH, dgsum)                                   # sum over time
-        dwi0 = torch.empty_like(wi0)
+        dwi0 = grad_buffer(wi0)
         gemm(GH, P, B, dgsum, 1, GH, plan, 1, P, dwi0, In)
         gemm(GH, Es, S * B, dg0, 1, GH, embT, 1, Es, dwi0, In, c_off=P)
         gemm(GH, G, B, dgsum, 1, GH, goal, 1, G, dwi0, In, c_off=P + Es)

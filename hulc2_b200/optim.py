@@ -49,9 +49,15 @@ class FusedAdam(torch.optim.Optimizer):
                 view.copy_(p.data)
                 p.data = view
         arena["step"] = 0
+        arena["views"] = {id(p): arena["g"][o : o + p.numel()].view(p.shape) for p, o in zip(ps, offs)}
         from . import ops
 
         ops.register_param_arena(arena["p"])   # one flat f32->bf16 conversion per step serves every contraction
+        # gradient sinks: backward kernels write the first gradient of a parameter straight into its arena slice
+        import weakref
+
+        keys = ops.register_grad_views(arena["g"], ps, offs)
+        arena["_fin"] = weakref.finalize(arena["g"], ops.unregister_grad_views, keys)
         return arena
 
     def _attach_grads(self, arena) -> None:
@@ -70,20 +76,41 @@ class FusedAdam(torch.optim.Optimizer):
             if a["n"]:
                 self._attach_grads(a)
 
+    def land_grad(self, p) -> None:
+        """Make ``p.grad`` the arena slice of ``p`` (copying a gradient that autograd adopted from elsewhere).  Called from
+        the reducer's post-accumulate hook so that every gradient is in the arena before its bucket is all-reduced."""
+        for a in self._arenas:
+            view = a["views"].get(id(p)) if a["n"] else None
+            if view is not None:
+                if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+                    g = p.grad.contiguous()
+                    if g.is_cuda:
+                        call("hulc2_copy2d", g.data_ptr(), g.numel(), view.data_ptr(), g.numel(), 1, g.numel(), 0)
+                    else:                       # host tensors only occur in the gloo reducer tests
+                        view.copy_(g)
+                    p.grad = view
+                return
+
     def grad_arenas(self) -> List[torch.Tensor]:
         return [a["g"] for a in self._arenas if a["n"]]
 
     # ------------------------------------------------------------------ optimizer API
     def zero_grad(self, set_to_none: bool = False) -> None:  # noqa: D401
-        """Zero-fills the gradient arena and keeps ``param.grad`` attached (``set_to_none`` is ignored so
-        the next backward accumulates in place into contiguous buckets)."""
+        """Zero-fills the gradient arena.  ``param.grad`` is reset to None: the backward kernels write the first gradient
+        of every parameter directly into its arena slice (``ops.grad_buffer``) and autograd adopts that tensor as
+        ``param.grad`` without an accumulate kernel; ``step()`` / ``attach()`` re-attach whatever did not arrive that way
+        (parameters without a gradient this step read as zeros)."""
+        from . import ops
+
         for a in self._arenas:
             if a["n"]:
-                call("hulc2_fill", a["g"].data_ptr(), a["n"], 0.0)
-                for p, o in zip(a["params"], a["offs"]):
-                    view = a["g"][o : o + p.numel()].view(p.shape)
-                    if p.grad is None or p.grad.data_ptr() != view.data_ptr():
-                        p.grad = view
+                if a["g"].is_cuda:
+                    call("hulc2_fill", a["g"].data_ptr(), a["n"], 0.0)
+                else:                           # host tensors only occur in the gloo reducer tests
+                    a["g"].zero_()
+                for p in a["params"]:
+                    p.grad = None
+        ops.begin_grad_step()
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -61,8 +61,11 @@ def _worker(rank: int, world: int, port: int, out):
         orig = red._launch
         red._launch = lambda b: (launched.append(b["index"]), orig(b))[1]
 
-        for step in range(2):                       # step 0 learns which parameters are used; step 1 overlaps
-            arena["g"].zero_()
+        for step in range(3):                       # step 0 learns which parameters are used; steps 1, 2 overlap
+            if step < 2:
+                arena["g"].zero_()                  # param.grad stays the arena view: autograd accumulates in place
+            else:
+                opt.zero_grad()                     # param.grad = None: autograd adopts its own tensors, the hook lands them
             x, y = _rank_batch(rank)
             loss = ((net(x) - y) ** 2).mean()
             red.prepare()
@@ -72,7 +75,7 @@ def _worker(rank: int, world: int, port: int, out):
             red.finish()
             assert all(b["launched"] for b in red.buckets)
             assert sorted(launched) == list(range(len(red.buckets)))
-            if step == 1:
+            if step >= 1:
                 # every bucket without an unused parameter fired from its hook, the decoder-side bucket first
                 assert during_backward and during_backward[0] == 0, during_backward
                 assert len(during_backward) == len(red.buckets), (during_backward, len(red.buckets))

@@ -189,3 +189,36 @@ def test_ops_fail_loudly_on_cpu_tensors():
 
     with pytest.raises(RuntimeError):
         ops.linear(torch.zeros(2, 3), torch.zeros(4, 3), torch.zeros(4))
+
+
+def test_gradients_written_directly_into_the_optimizer_arena():
+    """The first gradient of a parameter is produced inside FusedAdam's gradient arena and adopted by autograd without an
+    accumulate kernel (ops.grad_buffer); the parameters after two optimizer steps are bit-identical to the path where
+    every gradient is accumulated by autograd."""
+    from hulc2_b200 import ops
+    from hulc2_b200.trainer import PolicyTrainer
+
+    batch = to_device(synthetic_batch(2, seed=4, aux="all"), DEV)
+    g = torch.Generator().manual_seed(9)
+    cats = [torch.randint(0, 32, (2, 32), generator=g) for _ in range(4)]
+    results = []
+    for direct in (True, False):
+        ops.direct_grads = direct
+        try:
+            m = build_model("calvin").to(DEV).train()
+            tr = PolicyTrainer(m, use_graph=False)
+            for s in range(2):
+                with noise.supplied(categories=cats[2 * s: 2 * s + 2]):
+                    loss = tr.train_step(batch, s)
+            torch.cuda.synchronize()
+            if direct:
+                arena = tr.optimizer._arenas[0]
+                lo, hi = arena["g"].data_ptr(), arena["g"].data_ptr() + 4 * arena["n"]
+                assert all(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in m.parameters())
+                assert len(ops._grad_claimed) >= 60, len(ops._grad_claimed)
+            results.append((float(loss), {n: p.detach().clone() for n, p in m.named_parameters()}))
+        finally:
+            ops.direct_grads = True
+    assert results[0][0] == results[1][0]
+    for n, p in results[0][1].items():
+        assert torch.equal(p, results[1][1][n]), n
