@@ -399,7 +399,7 @@ def test_fused_adam_matches_torch():
         for i, (a, b) in enumerate(zip(ref, mine)):
             g = _rand(*a.shape, seed=70 + 3 * step + i)
             a.grad = g.clone()
-            b.grad.add_(g.to(DEV))
+            b.grad = g.to(DEV)            # a gradient produced outside the arena: step() copies it in (zero_grad leaves None, like torch)
         o_ref.step(); o_me.step()
     for a, b in zip(ref, mine):
         assert_close(b, a, 1e-6)

@@ -193,8 +193,9 @@ def test_ops_fail_loudly_on_cpu_tensors():
 
 def test_gradients_written_directly_into_the_optimizer_arena():
     """The first gradient of a parameter is produced inside FusedAdam's gradient arena and adopted by autograd without an
-    accumulate kernel (ops.grad_buffer); the parameters after two optimizer steps are bit-identical to the path where
-    every gradient is accumulated by autograd."""
+    accumulate kernel (ops.grad_buffer); the parameters after two optimizer steps equal those of the path where every
+    gradient is accumulated by autograd (to fp32 rounding: LayerNorm's weight gradient is an atomic sum whose order varies
+    from run to run either way)."""
     from hulc2_b200 import ops
     from hulc2_b200.trainer import PolicyTrainer
 
@@ -219,6 +220,6 @@ def test_gradients_written_directly_into_the_optimizer_arena():
             results.append((float(loss), {n: p.detach().clone() for n, p in m.named_parameters()}))
         finally:
             ops.direct_grads = True
-    assert results[0][0] == results[1][0]
+    assert abs(results[0][0] - results[1][0]) <= 1e-6 * abs(results[1][0])
     for n, p in results[0][1].items():
-        assert torch.equal(p, results[1][1][n]), n
+        assert_close(p, results[1][1][n], 1e-5, n)
