@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), TCOLS);
   if (tid == 32) {
     for (uint32_t s = 0; s < ST; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    for (int b = 0; b < NB; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 256); }
+    for (int b = 0; b < NB; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 8); }   // tempty: one arrival per epilogue warp
     mbar_fence_init();
   }
   if (tid < NTOT) bias_s[tid] = (!DGRAD && p.bias) ? p.bias[tid] : 0.f;
@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
         tmem_ld16_nowait(tmem_d + ((uint32_t)(lq * 32) << 16) + buf * NTOT + half * HC + c, *reinterpret_cast<uint32_t(*)[16]>(&acc[c]));
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(smem_u32(&tempty_bar[buf]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
 #pragma unroll
       for (int q = 0; q < NCH; ++q) {
         if (!ok[q]) continue;
