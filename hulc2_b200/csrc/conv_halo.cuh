@@ -29,4 +29,6 @@ bool hulc2_conv_halo_enabled();
 int hulc2_conv_halo_pitch(int pw);
 int hulc2_conv_halo_launch(const void* src, int F, int Hs, int Ws, HaloParams p, bool dgrad, cudaStream_t st);
 // stride-2 forward conv over a 32-channel source (two pixels = one 128-byte row; even / odd source rows = two sub-tiles)
+// forward conv over packed pixels narrower than 64 channels (overlapping 64-element rows, zero weights for the overlap)
+int hulc2_conv_halo_launch_packed(const void* src, int F, int Hs, int Ws, int pixel_elems, HaloParams p, cudaStream_t st);
 int hulc2_conv_halo_launch_s2(const void* src, int F, int Hs, int Ws, HaloParams p, cudaStream_t st);

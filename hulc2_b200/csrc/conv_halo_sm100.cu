@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
   // 128 x N x 16 MMA occupies the tensor pipe for only 32-64 cycles while ONE thread issues a tcgen05.mma every ~110 cycles
   // (measured: 1 -> 2 issuers, conv3 forward 0.332 -> 0.179 ms, conv2 forward 0.308 -> 0.197 ms).
   // (Interleaving several tiles' MMAs from ONE thread was measured and does not help: 0.283 -> 0.334 ms on conv3 forward.)
-  constexpr int NISS = 256 / NTOT >= 4 ? 4 : 2;   // N = 64: 4 issuers x 64 columns; N = 128: 2 issuers (TMEM: NB x N <= 512)
+  constexpr int NISS = 256 / NTOT >= 4 ? 4 : 2;   // N <= 64: 4 issuers; N = 128: 2 issuers (TMEM: NB x N <= 512 columns)
   constexpr int NB = NISS < 2 ? 2 : NISS;
   constexpr uint32_t TCOLS = NB * NTOT;
 
@@ -270,7 +270,7 @@ static int halo_finish(const void* src, int rank, const cuuint64_t* dims, const 
   EncodeTiledFn2 encode = (EncodeTiledFn2)halo_encode_fn();
   if (!encode) return HULC2_ENOTIMPL;
   if (p.PW > 256 || p.PH > 256 || p.BH < 1 || p.BH * p.PW > 128 || p.ntaps < 1 || p.ntaps > 16) return HULC2_ENOTIMPL;
-  if (p.NT != 64 && p.NT != 128) return HULC2_ENOTIMPL;
+  if (p.NT != 32 && p.NT != 64 && p.NT != 128) return HULC2_ENOTIMPL;
   if (((uintptr_t)src & 15) != 0) return HULC2_ENOTIMPL;
   int dmax = 0;
   for (int t = 0; t < p.ntaps; ++t) dmax = p.delta[t] > dmax ? p.delta[t] : dmax;
@@ -282,7 +282,7 @@ static int halo_finish(const void* src, int rank, const cuuint64_t* dims, const 
   if (stages > MAX_ST) stages = MAX_ST;
   // >= one ring slot per MMA issuer (4 for N = 64, 2 for N = 128): an issuer then never waits on a slot whose previous fill is
   // still pending, which is what keeps the parity waits of several issuers unambiguous
-  if (stages < (p.NT == 64 ? 4 : 2)) return HULC2_ENOTIMPL;
+  if (stages < (p.NT <= 64 ? 4 : 2)) return HULC2_ENOTIMPL;
   p.stages = stages;
   p.ntiles = p.F * p.tiles_per_frame;
   if (p.ntiles <= 0) return HULC2_OK;
@@ -293,7 +293,8 @@ static int halo_finish(const void* src, int rank, const cuuint64_t* dims, const 
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return HULC2_ENOTIMPL;
   const int smem = stages * p.stage_bytes + w_bytes + 1024;
-  if (!dgrad) return p.NT == 64 ? launch_halo<64, false>(tm, p, smem, st) : HULC2_ENOTIMPL;
+  if (!dgrad) return p.NT == 64 ? launch_halo<64, false>(tm, p, smem, st) : (p.NT == 32 ? launch_halo<32, false>(tm, p, smem, st) : HULC2_ENOTIMPL);
+  if (p.NT == 32) return HULC2_ENOTIMPL;
   return p.NT == 64 ? launch_halo<64, true>(tm, p, smem, st) : launch_halo<128, true>(tm, p, smem, st);
 }
 
@@ -322,4 +323,20 @@ int hulc2_conv_halo_launch_s2(const void* src, int F, int Hs, int Ws, HaloParams
   cuuint64_t strides[4] = {128u, row, 2u * row, (cuuint64_t)Hs * row};
   cuuint32_t box[5] = {64u, (cuuint32_t)p.PW, 1u, (cuuint32_t)p.PH, 1u};
   return halo_finish(src, 5, dims, strides, box, p, false, st);
+}
+
+// Forward conv over "packed" pixels of `pixel_elems` (< 64) bf16 channels: the tensor map describes 64-element rows at a
+// pitch of pixel_elems elements, i.e. every shared-memory row holds one pixel plus the first 64 - pixel_elems channels of its
+// right neighbour; the caller's weights are zero for those K positions, so the overlap contributes nothing.  This puts
+// conv1 (48 channels per space-to-depth pixel, 2 x 2 taps) on the halo path without changing the packed-frame layout.
+// The source must have >= 128 bytes of slack behind its last pixel.
+int hulc2_conv_halo_launch_packed(const void* src, int F, int Hs, int Ws, int pixel_elems, HaloParams p, cudaStream_t st) {
+  p.F = F; p.nparts = 1;
+  for (int t = 0; t < 16; ++t) p.part[t] = 0;
+  const cuuint64_t pb = (cuuint64_t)pixel_elems * 2;
+  if (pb % 16 || pixel_elems > 64) return HULC2_ENOTIMPL;
+  cuuint64_t dims[4] = {64u, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)F};
+  cuuint64_t strides[3] = {pb, (cuuint64_t)Ws * pb, (cuuint64_t)Hs * Ws * pb};
+  cuuint32_t box[4] = {64u, (cuuint32_t)p.PW, (cuuint32_t)p.PH, 1u};
+  return halo_finish(src, 4, dims, strides, box, p, false, st);
 }

@@ -570,6 +570,15 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
+// [N][taps * C] -> [N][taps * 64], zero for the 64 - C trailing positions of every tap (conv1 on the halo path)
+__global__ void pad_taps_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wp, int N, int taps, int C) {
+  const int total = N * taps * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i & 63, t = (i >> 6) % taps, n = i / (64 * taps);
+    wp[i] = c < C ? w[((size_t)n * taps + t) * C + c] : __float2bfloat16(0.f);
+  }
+}
+
 int sm_count() {
   static int sms = 0;
   if (!sms) {
@@ -681,6 +690,26 @@ int hulc2_convb_fwd(const hulc2_convb_args* a, cudaStream_t st) {
     h.oH = OH; h.oW = OW; h.oS = 1;
     h.clsH[0] = (short)OH; h.clsW[0] = (short)OW; h.clsPh[0] = h.clsPw[0] = 0;
     const int rc = hulc2_conv_halo_launch(a->x, a->F, a->H, a->W, h, false, st);
+    if (rc != HULC2_ENOTIMPL) return rc;
+  }
+  if (a->C % 8 == 0 && a->C < 64 && a->C >= 32 && a->Cout == 32 && a->stride == 1 && a->KH * a->KW <= 4 && a->W <= 128 &&
+      a->workspace && a->workspace_bytes >= (long long)a->Cout * a->KH * a->KW * 128 && hulc2_conv_halo_enabled() &&
+      !(getenv("HULC2_CONV1_GATHER") && atoi(getenv("HULC2_CONV1_GATHER")))) {
+    // conv1 over space-to-depth pixels of C = 48 channels: 64-element rows at a C-element pitch + weights zero-padded per tap
+    // (the caller guarantees slack behind the last pixel: ops.pack_frames)
+    const int taps = a->KH * a->KW;
+    pad_taps_kernel<<<hulc2_cdiv(a->Cout * taps * 64, 256), 256, 0, st>>>((const __nv_bfloat16*)a->w, (__nv_bfloat16*)a->workspace, a->Cout, taps, a->C);
+    HULC2_CHECK_LAUNCH();
+    HaloParams h{};
+    h.w = (const uint8_t*)a->workspace; h.bias = a->bias; h.mask = nullptr; h.y = (uint8_t*)a->y; h.relu = a->relu;
+    h.NT = h.BNc = 32; h.ncls = 1;
+    h.PW = a->W; h.BH = 128 / h.PW < OH ? 128 / h.PW : OH; h.PH = h.BH + a->KH - 1;
+    h.i_min = 0; h.j_min = 0; h.ntaps = taps;
+    for (int t = 0; t < taps; ++t) h.delta[t] = (short)((t / a->KW) * h.PW + t % a->KW);
+    h.tiles_per_frame = hulc2_cdiv(OH, h.BH);
+    h.oH = OH; h.oW = OW; h.oS = 1;
+    h.clsH[0] = (short)OH; h.clsW[0] = (short)OW; h.clsPh[0] = h.clsPw[0] = 0;
+    const int rc = hulc2_conv_halo_launch_packed(a->x, a->F, a->H, a->W, a->C, h, st);
     if (rc != HULC2_ENOTIMPL) return rc;
   }
   if (a->C == 32 && a->Cout == 64 && a->stride == 2 && a->KH == 4 && a->KW == 4 && OW + 1 <= 128 && hulc2_conv_halo_enabled()) {

@@ -492,6 +492,8 @@ def convb_fwd(x, wp, bias, F, C, H, W, Cout, k, stride, relu=True, name="conv") 
     y = _bf16(F, OH, OW, Cout, device=x.device)
     a = _cb(F, C, H, W, Cout, k, stride)
     a.x, a.w, a.bias, a.y, a.relu = x.data_ptr(), wp.data_ptr(), _p(bias), y.data_ptr(), int(relu)
+    ws = workspace(x.device)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()        # scratch for re-tiled weights (conv1 halo path)
     _lib.tag(f"convb_fwd[{name},F={F},{C}x{H}x{W}->{Cout},k{k}s{stride}]", 2.0 * y.numel() * C * k * k,
              2.0 * (x.numel() + y.numel()))
     call("hulc2_convb_fwd", C_byref(a))
@@ -597,8 +599,10 @@ def pack_frames(x) -> torch.Tensor:
     (space-to-depth by the first conv's stride); groups are packed back to back, so no concatenated fp32 copy is ever
     made -- and for uint8 frames no fp32 frame exists at all."""
     groups, (F_, Cin, H, W) = _frame_groups(x)
-    xs = _bf16(F_, H // 4, W // 4, 16 * Cin, device=groups[0].device)
     per_frame = (H // 4) * (W // 4) * 16 * Cin
+    # 64 elements of slack behind the last pixel: conv1's halo path reads packed pixels as 64-element rows at a 48-element pitch
+    # (the 16 extra elements meet zero weights), so the row of the very last pixel ends 32 bytes past the tensor
+    xs = _bf16(F_ * per_frame + 64, device=groups[0].device)[: F_ * per_frame].view(F_, H // 4, W // 4, 16 * Cin)
     f0 = 0
     for t in groups:
         if isinstance(t, U8Frames):
