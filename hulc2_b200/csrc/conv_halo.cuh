@@ -32,3 +32,17 @@ int hulc2_conv_halo_launch(const void* src, int F, int Hs, int Ws, HaloParams p,
 // forward conv over packed pixels narrower than 64 channels (overlapping 64-element rows, zero weights for the overlap)
 int hulc2_conv_halo_launch_packed(const void* src, int F, int Hs, int Ws, int pixel_elems, HaloParams p, cudaStream_t st);
 int hulc2_conv_halo_launch_s2(const void* src, int F, int Hs, int Ws, HaloParams p, cudaStream_t st);
+
+// Halo-tile weight gradient (stride-1 convs): dW^T[(tap, ch), co] = sum over pixels of X[pixel + delta(tap), ch] * dZ[pixel, co].
+struct HaloWgradParams {
+  float* partial;          // [grid][nblk * 64][64] fp32 per-CTA partial sums (rows: tap * 64 + ch; row ntaps * 64 = sum of dZ)
+  int F, tiles_per_frame, ntiles;
+  int BH, PW;              // a tile = BH rows of PW raster positions (PW >= source width; the extra columns are TMA zero fill)
+  int KH;                  // source rows per tile = BH + KH - 1
+  int ntaps, nmt;          // taps; M-tiles of 128 = 2 blocks of 64: ceil((ntaps + 1) / 2), the +1 is the block of ones
+  int a_bytes, b_bytes;    // sub-tile sizes (1024-byte multiples); stage = a_bytes + b_bytes
+  int stages;
+  short delta[16];         // per tap: raster offset of its window in the source tile
+};
+int hulc2_conv_halo_wgrad(const void* x, int x_pixel_elems, const void* dz, int dz_pixel_elems, int F, int H, int W, int KH, int KW,
+                          float* partial, long long partial_bytes, int* grid_out, int* nblk_out, cudaStream_t st);

@@ -340,3 +340,196 @@ int hulc2_conv_halo_launch_packed(const void* src, int F, int Hs, int Ws, int pi
   cuuint32_t box[4] = {64u, (cuuint32_t)p.PW, (cuuint32_t)p.PH, 1u};
   return halo_finish(src, 4, dims, strides, box, p, false, st);
 }
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+// Both operands MN-major (tile rows = pixel positions = the contraction index).  Per tile: ONE TMA box of the source
+// (BH + KH - 1 rows) and ONE of dZ (BH rows, out-of-range columns / rows zero-filled, so garbage raster positions contribute
+// nothing); tap (a, b) is the source tile read at row offset a * PW + b.  An M = 128 MMA covers two taps: the descriptor's
+// leading-dimension offset is the distance between the two taps' windows (measured: tools/probes/umma_mn_shift_probe.cu);
+// the last block is a constant 16-row tile of ones (its LBO is recomputed per k-step), which yields the bias gradient.
+// dW^T stays in TMEM for the CTA's lifetime; up to 3 issuer threads own disjoint M-tiles.
+// Warp roles (416 threads): warps 0-7 dump, warp 8 TMA producer, warps 9-11 MMA issuers.
+namespace {
+
+template <int DUMMY>
+__global__ void __launch_bounds__(NT_HALO, 1) conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmz,
+                                                                     const __grid_constant__ HaloWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_ST], empty_bar[MAX_ST], done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ST = (uint32_t)p.stages;
+  const uint32_t stage_bytes = (uint32_t)(p.a_bytes + p.b_bytes);
+  const uint32_t ones_smem = base + ST * stage_bytes;           // 32 rows x 128 B of bf16 1.0 (16 used; a dummy second block may start at row 1)
+  const int nmt = p.nmt;
+  const int niss = nmt < 3 ? nmt : 3;
+  const uint32_t tcols = nmt * 64 <= 64 ? 64u : (nmt * 64 <= 128 ? 128u : (nmt * 64 <= 256 ? 256u : 512u));
+
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), tcols);
+  if (tid == 32) {
+    for (uint32_t s = 0; s < ST; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), (uint32_t)niss); }
+    mbar_init(smem_u32(&done_bar), (uint32_t)niss);
+    mbar_fence_init();
+  }
+  // zero all stages once (rows behind a TMA box are read by the last taps' windows: they must be finite), then the ones tile
+  for (uint32_t o = tid * 16; o < ST * stage_bytes; o += NT_HALO * 16)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(0u) : "memory");
+  for (uint32_t o = tid * 16; o < 32 * 128; o += NT_HALO * 16)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ones_smem + o), "r"(0x3F803F80u) : "memory");
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+  const int KL = p.BH * p.PW;                                    // contraction positions per tile (multiple of 16)
+
+  if (warp == 8) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmx) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmz) : "memory");
+      uint32_t s = 0, ph = 1;
+      const uint32_t bytes = (uint32_t)((p.BH + p.KH - 1) * p.PW + p.BH * p.PW) * 128u;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int f = tile / p.tiles_per_frame, ti = tile - f * p.tiles_per_frame;
+        mbar_wait(smem_u32(&empty_bar[s]), ph);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        mbar_expect_tx(bar, bytes);
+        const uint32_t dst = base + s * stage_bytes;
+        tma_load_4d(dst, &tmx, bar, 0, 0, ti * p.BH, f);
+        tma_load_4d(dst + (uint32_t)p.a_bytes, &tmz, bar, 0, 0, ti * p.BH, f);
+        if (++s == ST) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 9 && warp < 9 + niss) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = make_idesc(128, 64, true, true);
+      const int me = warp - 9;
+      // M-tiles of this issuer: a contiguous share
+      const int mt0 = (nmt * me) / niss, mt1 = (nmt * (me + 1)) / niss;
+      uint32_t s = 0, ph = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        const uint32_t a_tile = base + s * stage_bytes, b_tile = a_tile + (uint32_t)p.a_bytes;
+        for (int ks = 0; ks < KL / 16; ++ks) {
+          const uint64_t bd = make_desc(b_tile + ks * 2048, 0);
+          for (int mt = mt0; mt < mt1; ++mt) {
+            const int t0 = 2 * mt, t1 = 2 * mt + 1;
+            // block addresses: a tap's window at this k-step, or the (k-step independent) ones tile
+            const uint32_t a0 = t0 < p.ntaps ? a_tile + (uint32_t)p.delta[t0] * 128u + ks * 2048 : ones_smem;
+            const uint32_t a1 = t1 < p.ntaps ? a_tile + (uint32_t)p.delta[t1] * 128u + ks * 2048 : ones_smem;
+            // LBO = byte distance from block 0 to block 1 (the ones tile lies behind every stage, so it is positive; two
+            // blocks on the ones tile -- only when ntaps is even and this is the last M-tile -- use a dummy 128)
+            const uint32_t lbo = a1 > a0 ? a1 - a0 : 128u;
+            umma_bf16(tmem_d + mt * 64, make_desc(a0, lbo), bd, IDESC, (first && ks == 0) ? 0u : 1u);
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[s]));
+        first = false;
+        if (++s == ST) { s = 0; ph ^= 1; }
+      }
+      umma_commit(smem_u32(&done_bar));
+    }
+    __syncwarp();
+  } else if (warp < 8) {
+    // dump: warp w <-> TMEM lanes 32*(w%4).., columns (w/4)*32..+32 of every M-tile
+    const int lq = warp & 3, half = warp >> 2;
+    mbar_wait_relaxed(smem_u32(&done_bar), 0);
+    tc_fence_after();
+    float* out = p.partial + (size_t)blockIdx.x * nmt * 128 * 64;
+    for (int mt = 0; mt < nmt; ++mt) {
+      uint32_t acc[32];
+#pragma unroll
+      for (int c = 0; c < 32; c += 16)
+        tmem_ld16_nowait(tmem_d + ((uint32_t)(lq * 32) << 16) + mt * 64 + half * 32 + c, *reinterpret_cast<uint32_t(*)[16]>(&acc[c]));
+      tmem_ld_wait();
+      float4* o4 = reinterpret_cast<float4*>(out + (size_t)(mt * 128 + lq * 32 + lane) * 64 + half * 32);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o4[c] = make_float4(__uint_as_float(acc[4 * c]), __uint_as_float(acc[4 * c + 1]), __uint_as_float(acc[4 * c + 2]), __uint_as_float(acc[4 * c + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, tcols);
+}
+
+}  // namespace
+
+// Returns HULC2_ENOTIMPL when the shape does not fit.  On success *grid_out CTAs wrote partial[g][nblk*64][64] with
+// nblk = 2 * nmt blocks of 64 rows: rows tap * 64 + ch, and row ntaps * 64 = column sums of dZ.
+int hulc2_conv_halo_wgrad(const void* x, int xpe, const void* dz, int zpe, int F, int H, int W, int KH, int KW, float* partial,
+                          long long partial_bytes, int* grid_out, int* nblk_out, cudaStream_t st) {
+  EncodeTiledFn encode = halo_encode_fn();
+  if (!encode || KH * KW > 15 || xpe > 64 || zpe > 64 || (xpe * 2) % 16 || (zpe * 2) % 16) return HULC2_ENOTIMPL;
+  if (((uintptr_t)x & 15) || ((uintptr_t)dz & 15)) return HULC2_ENOTIMPL;
+  const int OH = H - KH + 1, OW = W - KW + 1;
+  HaloWgradParams p{};
+  p.KH = KH; p.ntaps = KH * KW; p.nmt = (p.ntaps + 2) / 2;
+  if (p.nmt > 8) return HULC2_ENOTIMPL;
+  // raster pitch >= W and rows per tile such that BH * PW is a multiple of 16 and 2+ stages fit; prefer more rows per tile
+  int best_bh = 0, best_pw = 0;
+  for (int pw = W; pw <= W + 3 && pw <= 256; ++pw)
+    for (int bh = 1; bh <= 16 && bh <= OH + 15; ++bh) {
+      if ((bh * pw) % 16) continue;
+      const int a_rows = (bh + KH - 1) * pw + 16, b_rows = bh * pw;
+      const long long stage = (((long long)a_rows * 128 + 1023) & ~1023LL) + (((long long)b_rows * 128 + 1023) & ~1023LL);
+      if (bh + KH - 1 > 256 || 2 * stage + 8192 > 227 * 1024 - 2048) continue;
+      // efficiency: useful rows per tile row budget
+      const int tiles = (OH + bh - 1) / bh;
+      const double eff = (double)OH / (tiles * bh) * (double)W / pw;
+      const int btiles = best_bh ? (OH + best_bh - 1) / best_bh : 1;
+      const double beff = best_bh ? (double)OH / (btiles * best_bh) * (double)W / best_pw : 0.0;
+      if (eff > beff + 1e-9 || (eff > beff - 1e-9 && bh > best_bh)) { best_bh = bh; best_pw = pw; }
+    }
+  if (!best_bh) return HULC2_ENOTIMPL;
+  p.BH = best_bh; p.PW = best_pw;
+  for (int t = 0; t < p.ntaps; ++t) p.delta[t] = (short)((t / KW) * p.PW + t % KW);
+  const int a_rows = (p.BH + KH - 1) * p.PW + 16, b_rows = p.BH * p.PW;
+  p.a_bytes = ((a_rows * 128) + 1023) & ~1023;
+  p.b_bytes = ((b_rows * 128) + 1023) & ~1023;
+  int stages = (227 * 1024 - 2048 - 8192) / (p.a_bytes + p.b_bytes);
+  if (stages > 4) stages = 4;
+  if (stages < 2) return HULC2_ENOTIMPL;
+  p.stages = stages;
+  p.F = F; p.tiles_per_frame = hulc2_cdiv(OH, p.BH); p.ntiles = F * p.tiles_per_frame;
+  const int grid = p.ntiles < halo_sms() ? p.ntiles : halo_sms();
+  const long long need = (long long)grid * p.nmt * 128 * 64 * sizeof(float);
+  if (!partial || partial_bytes < need) return HULC2_ENOTIMPL;
+  p.partial = partial;
+
+  CUtensorMap tmx, tmz;
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  {
+    const cuuint64_t pb = (cuuint64_t)xpe * 2;
+    cuuint64_t dims[4] = {64u, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)F};
+    cuuint64_t strides[3] = {pb, (cuuint64_t)W * pb, (cuuint64_t)H * W * pb};
+    cuuint32_t box[4] = {64u, (cuuint32_t)p.PW, (cuuint32_t)(p.BH + KH - 1), 1u};
+    if (encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return HULC2_ENOTIMPL;
+  }
+  {
+    const cuuint64_t pb = (cuuint64_t)zpe * 2;
+    cuuint64_t dims[4] = {64u, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)F};
+    cuuint64_t strides[3] = {pb, (cuuint64_t)OW * pb, (cuuint64_t)OH * OW * pb};
+    cuuint32_t box[4] = {64u, (cuuint32_t)p.PW, (cuuint32_t)p.BH, 1u};
+    if (encode(&tmz, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dz), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return HULC2_ENOTIMPL;
+  }
+  const int smem = stages * (p.a_bytes + p.b_bytes) + 32 * 128 + 1024;
+  auto kern = conv_halo_wgrad_kernel<0>;
+  static int configured = 0;
+  if (configured < smem) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { cudaGetLastError(); return HULC2_ENOTIMPL; }
+    configured = smem;
+  }
+  kern<<<grid, NT_HALO, smem, st>>>(tmx, tmz, p);
+  HULC2_CHECK_LAUNCH();
+  *grid_out = grid;
+  *nblk_out = 2 * p.nmt;
+  return HULC2_OK;
+}

@@ -493,13 +493,15 @@ __global__ void __launch_bounds__(NT_WG, 1) conv_wgrad_kernel(const __grid_const
 
 // dw (OIHW fp32) and db from the per-CTA partials.  layout 0: kconv = (kh, kw, ci);
 // layout 1 (packed frames): kconv = (dI, dJ, ci, a, b) -> kh = 4 dI + a, kw = 4 dJ + b of a [Cout, C/16, 4KH, 4KW] weight.
+// `pitch`: rows per tap in the partials (C for the gather kernel's dense rows, 64 for the halo kernel's padded tap blocks).
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int rows_per_part, int K, int Cout, int C, int KH,
-                                    int KW, int layout, float* __restrict__ dw, float* __restrict__ db) {
+                                    int KW, int layout, float* __restrict__ dw, float* __restrict__ db, int pitch) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (k, co), co fastest; k == K is the ones row (bias)
   if (idx >= (K + 1) * Cout) return;
   const int k = idx / Cout, co = idx - k * Cout;
+  const int row = (k / C) * pitch + k % C;                 // k == K -> (K / C) * pitch: the block of ones
   float s = 0.f;
-  for (int g = 0; g < nparts; ++g) s += partial[((size_t)g * rows_per_part + k) * 64 + co];
+  for (int g = 0; g < nparts; ++g) s += partial[((size_t)g * rows_per_part + row) * 64 + co];
   if (k == K) { if (db) db[co] = s; return; }
   if (!dw) return;
   int o;
@@ -818,6 +820,24 @@ int hulc2_convb_wgrad(const hulc2_convb_args* a, cudaStream_t st) {
   if (int e = check_convb(a)) return e;
   if (!hulc2_convb_supported(a->C, a->Cout, a->KH, a->KW, a->stride)) { hulc2_set_error("convb_wgrad: unsupported shape"); return HULC2_ENOTIMPL; }
   const int OH = (a->H - a->KH) / a->stride + 1, OW = (a->W - a->KW) / a->stride + 1;
+  if (a->stride == 1 && a->C >= 32 && a->C <= 64 && (a->Cout == 32 || a->Cout == 64) && a->F * OH * OW > 0 && hulc2_conv_halo_enabled() &&
+      getenv("HULC2_WGRAD_HALO") && atoi(getenv("HULC2_WGRAD_HALO"))) {
+    // halo-tile weight gradient: both operands by TMA, taps through shifted MN-major descriptors (conv_halo_sm100.cu).
+    // Correct (same tests) but OPT-IN: measured slower than the gather kernel (conv1 0.92 vs 0.80 ms, conv3 0.33 vs 0.27 ms) --
+    // a tile needs 850 TMA rows of 128 bytes and the TMA unit delivers one row per ~7-10 cycles, so the loads, not the MMAs,
+    // pace it.
+    int grid = 0, nblk = 0;
+    const int rc = hulc2_conv_halo_wgrad(a->x, a->C, a->dy, a->Cout, a->F, a->H, a->W, a->KH, a->KW, (float*)a->workspace, a->workspace_bytes,
+                                         &grid, &nblk, st);
+    if (rc == HULC2_OK) {
+      const int K = a->KH * a->KW * a->C, total = (K + 1) * a->Cout;
+      wgrad_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>((const float*)a->workspace, grid, nblk * 64, K, a->Cout, a->C, a->KH, a->KW,
+                                                                   a->dw_layout, a->dw, a->db, 64);
+      HULC2_CHECK_LAUNCH();
+      return HULC2_OK;
+    }
+    if (rc != HULC2_ENOTIMPL) return rc;
+  }
   WgradParams p{};
   p.x = (const uint8_t*)a->x; p.dz = (const uint8_t*)a->dy;
   p.P = a->F * OH * OW; p.dHW = make_fastdiv(OH * OW); p.dW = make_fastdiv(OW);
@@ -864,7 +884,7 @@ int hulc2_convb_wgrad(const hulc2_convb_args* a, cudaStream_t st) {
   HULC2_CHECK_LAUNCH();
   const int total = (p.K + 1) * a->Cout;
   wgrad_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(p.partial, grid, p.nblk * 64, p.K, a->Cout, a->C, a->KH, a->KW, a->dw_layout,
-                                                               a->dw, a->db);
+                                                               a->dw, a->db, a->C);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

@@ -476,7 +476,12 @@ def _cb(F, C, H, W, Cout, k, stride) -> ConvbArgs:
 
 
 def _bf16(*shape, device):
-    return torch.empty(*shape, device=device, dtype=torch.bfloat16)
+    """bf16 activation buffer with 64 elements of slack behind it: the halo kernels read 32/48-channel pixels as 64-element TMA
+    rows (the overlap meets zero weights / ignored accumulator columns), so the last pixel's row ends past the tensor."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return torch.empty(n + 64, device=device, dtype=torch.bfloat16)[:n].view(*shape)
 
 
 def pack_conv_weight(w: torch.Tensor, mode: int, stride: int = 1) -> torch.Tensor:
@@ -600,9 +605,8 @@ def pack_frames(x) -> torch.Tensor:
     made -- and for uint8 frames no fp32 frame exists at all."""
     groups, (F_, Cin, H, W) = _frame_groups(x)
     per_frame = (H // 4) * (W // 4) * 16 * Cin
-    # 64 elements of slack behind the last pixel: conv1's halo path reads packed pixels as 64-element rows at a 48-element pitch
-    # (the 16 extra elements meet zero weights), so the row of the very last pixel ends 32 bytes past the tensor
-    xs = _bf16(F_ * per_frame + 64, device=groups[0].device)[: F_ * per_frame].view(F_, H // 4, W // 4, 16 * Cin)
+    # (_bf16 leaves slack behind the last pixel: conv1's halo path reads packed pixels as 64-element rows at a 48-element pitch)
+    xs = _bf16(F_, H // 4, W // 4, 16 * Cin, device=groups[0].device)
     f0 = 0
     for t in groups:
         if isinstance(t, U8Frames):
