@@ -101,7 +101,11 @@ int hulc2_permute_conv_weight(const float* src, float* dst, int O, int I, int KH
  *  dgrad : dx[F,H,W,C] = conv^T(dy, w) zeroed where xmask <= 0 (xmask = forward activation x, may be null); w mode 2.
  *  wgrad : dw (fp32, OIHW; dw_layout 1 = ORIGINAL [Cout, C/16, 4KH, 4KW] of a packed-frames conv) and db[Cout]
  *          from x and dy; workspace >= 148 * (KH*KW*C + 128) * 64 * 4 bytes.
- * hulc2_convb_supported() says whether a layer shape is served (C % 8 == 0, KH*KW*C % 64 == 0, Cout in {32,64}, stride <= 2). */
+ * hulc2_convb_supported() says whether a layer shape is served (C % 8 == 0, KH*KW*C % 64 == 0, Cout in {32,64}, stride <= 2).
+ * Kernel selection is internal (csrc/conv_halo_sm100.cu: one TMA box per tile + shifted UMMA descriptors for stride-1 / the
+ * stride-2 layers of this trunk; csrc/conv_sm100.cu: cp.async gather otherwise; HULC2_CONV_HALO=0 forces the gather kernels).
+ * The halo path reads pixels narrower than 64 channels as 64-element rows: `x` (fwd, C < 64) must be followed by >= 128
+ * readable bytes (any content); fwd passes `workspace` (>= Cout*KH*KW*128 bytes) for the re-tiled weights of that case. */
 typedef struct {
   int F, C, H, W, Cout, KH, KW, stride;
   const void* x; const void* w; const float* bias; void* y; int relu;
