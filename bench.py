@@ -26,9 +26,9 @@ import torch  # noqa: E402
 WINDOW = 32
 FLOPS_PER_WINDOW_FWD_BWD = 13.01e9  # SURVEY.md 8d (torch FlopCounterMode on the reference graph)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the conv trunk at
-# the bench shape (profiles/r01_h_ncu_conv_trunk.md); keyed like the per-call profile
+# the bench shape (profiles/r01_j_ncu_conv_trunk.md); keyed like the per-call profile
 NCU_TRAFFIC_BYTES = {
-    "convb_fwd[c1,F=4096,48x50x50->32,k2s1]": 1.582e9, "convb_fwd[c2,F=4096,32x49x49->64,k4s2]": 0.868e9,
+    "convb_fwd[c1,F=4096,48x50x50->32,k2s1]": 1.581e9, "convb_fwd[c2,F=4096,32x49x49->64,k4s2]": 0.868e9,
     "convb_fwd[c3,F=4096,64x23x23->64,k3s1]": 0.468e9, "convb_wgrad[c3,F=4096,64x23x23->64,k3s1]": 0.514e9,
     "convb_dgrad[c3,F=4096,64x23x23<-64,k3s1]": 0.756e9, "convb_wgrad[c2,F=4096,32x49x49->64,k4s2]": 0.900e9,
     "convb_dgrad[c2,F=4096,32x49x49<-64,k4s2]": 1.499e9, "convb_wgrad[c1,F=4096,48x50x50->32,k2s1]": 1.617e9,
