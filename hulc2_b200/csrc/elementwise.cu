@@ -97,6 +97,57 @@ __global__ void __launch_bounds__(256) colsum_partial4_kernel(const float* __res
     partial[(long long)blockIdx.y * cols + blockIdx.x * 128 + t] = acc;
   }
 }
+// One-launch column sum for the bias gradients (rows <= a few thousand): a thread-block cluster of 8 CTAs splits the rows of a
+// 128-column block, every CTA writes its 128 double partials into rank 0's shared memory (DSMEM), rank 0 adds them in rank order.
+// Deterministic, no global scratch, no second kernel (33 of these per train step).
+constexpr int CS_CLUSTER = 8;
+__global__ void __cluster_dims__(1, CS_CLUSTER, 1) __launch_bounds__(256)
+    colsum_cluster_kernel(const float* __restrict__ x, long long ld, long long rows, int cols, float* __restrict__ out, int accumulate) {
+  __shared__ double red[8][32][4];
+  __shared__ double part[CS_CLUSTER][128];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const long long per = (rows + CS_CLUSTER - 1) / CS_CLUSTER;
+  const long long r0 = (long long)blockIdx.y * per;
+  const long long r1 = r0 + per < rows ? r0 + per : rows;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (c < cols) {
+    long long r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(x + (r + 8) * ld + c));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(x + (r + 16) * ld + c));
+      const float4 e = __ldg(reinterpret_cast<const float4*>(x + (r + 24) * ld + c));
+      s0 += ((double)a.x + (double)b.x) + ((double)d.x + (double)e.x);
+      s1 += ((double)a.y + (double)b.y) + ((double)d.y + (double)e.y);
+      s2 += ((double)a.z + (double)b.z) + ((double)d.z + (double)e.z);
+      s3 += ((double)a.w + (double)b.w) + ((double)d.w + (double)e.w);
+    }
+    for (; r < r1; r += 8) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+      s0 += (double)a.x; s1 += (double)a.y; s2 += (double)a.z; s3 += (double)a.w;
+    }
+  }
+  red[threadIdx.y][threadIdx.x][0] = s0; red[threadIdx.y][threadIdx.x][1] = s1;
+  red[threadIdx.y][threadIdx.x][2] = s2; red[threadIdx.y][threadIdx.x][3] = s3;
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;          // 128 columns of the block, one per thread
+  if (t < 128) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += red[j][t >> 2][t & 3];
+    uint32_t local = (uint32_t)__cvta_generic_to_shared(&part[blockIdx.y][t]), remote;   // blockIdx.y == rank (grid.y == cluster size)
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(acc) : "memory");
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (blockIdx.y == 0 && t < 128 && blockIdx.x * 128 + t < cols) {
+    double tot = 0.0;
+#pragma unroll
+    for (int j = 0; j < CS_CLUSTER; ++j) tot += part[j][t];
+    float* o = out + blockIdx.x * 128 + t;
+    *o = accumulate ? *o + (float)tot : (float)tot;
+  }
+}
 __global__ void colsum_final_kernel(const double* __restrict__ partial, int slabs, int cols, float* __restrict__ out, int accumulate) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
@@ -338,6 +389,11 @@ int hulc2_colsum(const float* x, long long ld, long long rows, int cols, float* 
   if (cols <= 0) return HULC2_OK;
   const bool vec4 = (cols % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   int colblocks = hulc2_cdiv(cols, vec4 ? 128 : 32);
+  if (vec4 && rows <= 32768 && rows > 0) {
+    colsum_cluster_kernel<<<dim3(colblocks, CS_CLUSTER), dim3(32, 8), 0, st>>>(x, ld, rows, cols, out, accumulate);
+    HULC2_CHECK_LAUNCH();
+    return HULC2_OK;
+  }
   long long max_slabs = workspace ? workspace_bytes / ((long long)cols * sizeof(double)) : 0;
   if (max_slabs < 1) { hulc2_set_error("colsum: workspace too small"); return HULC2_EWORKSPACE; }
   long long slabs = ((vec4 ? 6LL : 2LL) * kSMs + colblocks - 1) / colblocks;
