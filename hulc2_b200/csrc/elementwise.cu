@@ -277,15 +277,28 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     bc1 = (float)(1.0 - pow((double)b1, st));
     bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, st));
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float gi = g[i] * grad_scale;
-    float pi = p[i];
+  auto upd = [&](float gi, float& pi, float& mi, float& vi) {
+    gi *= grad_scale;
     if (wd != 0.f) gi = fmaf(wd, pi, gi);
-    float mi = m[i] + (1.f - b1) * (gi - m[i]);          // exp_avg.lerp_(grad, 1-beta1)
-    float vi = b2 * v[i] + (1.f - b2) * gi * gi;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
-    float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = pi - (lr / bc1) * (mi / denom);
-    m[i] = mi; v[i] = vi;
+    mi = mi + (1.f - b1) * (gi - mi);                     // exp_avg.lerp_(grad, 1-beta1)
+    vi = b2 * vi + (1.f - b2) * gi * gi;                  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi = pi - (lr / bc1) * (mi / denom);
+  };
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  // 16-byte accesses (the arenas are 32-byte aligned): 4 parameters per thread and iteration, same arithmetic per element
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const long long n4 = vec ? n >> 2 : 0;
+  for (long long i = tid; i < n4; i += nth) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+    upd(g4.x, p4.x, m4.x, v4.x); upd(g4.y, p4.y, m4.y, v4.y); upd(g4.z, p4.z, m4.z, v4.z); upd(g4.w, p4.w, m4.w, v4.w);
+    reinterpret_cast<float4*>(p)[i] = p4; reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4;
+  }
+  for (long long i = (n4 << 2) + tid; i < n; i += nth) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(g[i], pi, mi, vi);
+    p[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
 
