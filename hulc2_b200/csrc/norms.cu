@@ -178,7 +178,8 @@ __global__ void spatial_softmax_kernel(const T* __restrict__ x, const float* __r
   if (dtemp) atomicAdd(dtemp, -dt * invT * invT);
 }
 
-// bf16 trunk variant: the whole frame [HW][C] is staged in shared memory with 16-byte loads (one HBM read), every pass
+// bf16 trunk variant (exponentials with ex2.approx: the inputs are bf16 activations and the kernel was instruction-bound on the
+// accurate expf -- 2 x 441 x 64 of them per frame and pass; the fp32 parity path keeps expf): the whole frame [HW][C] is staged in shared memory with 16-byte loads (one HBM read), every pass
 // (max, sums, gradient) runs from shared memory, and the gradient is written back in place and stored with 16-byte
 // stores (one HBM write).  Thread (cp, g): channel pair cp = tid % (C/2), position group g of G = blockDim / (C/2).
 constexpr int SSM_NT = 256;   // threads per frame (512 with 3 frames per SM measured slower: 0.28 -> 0.32 ms backward)
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(SSM_NT) ssm_bf16_kernel(const __nv_bfloat16* _
     for (int i = g; i < HW; i += G) {
       const float2 v = __bfloat1622float2(tile[i * C2 + cp]);
       const float xm = maps[i], ym = maps[HW + i];
-      const float e0 = expf(v.x * invT - m0), e1 = expf(v.y * invT - m1);
+      const float e0 = __expf(v.x * invT - m0), e1 = __expf(v.y * invT - m1);
       se0 += e0; sx0 += e0 * xm; sy0 += e0 * ym;
       se1 += e1; sx1 += e1 * xm; sy1 += e1 * ym;
     }
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(SSM_NT) ssm_bf16_kernel(const __nv_bfloat16* _
     for (int i = g; i < HW; i += G) {
       const float2 v = __bfloat1622float2(tile[i * C2 + cp]);
       const float xm = maps[i], ym = maps[HW + i];
-      const float p0 = expf(v.x * invT - m0) * inv0, p1 = expf(v.y * invT - m1) * inv1;
+      const float p0 = __expf(v.x * invT - m0) * inv0, p1 = __expf(v.y * invT - m1) * inv1;
       const float dl0 = p0 * (gq.x * (xm - ex0) + gq.y * (ym - ey0)), dl1 = p1 * (gq.z * (xm - ex1) + gq.w * (ym - ey1));
       dt += dl0 * v.x + dl1 * v.y;
       float o0 = dl0 * invT, o1 = dl1 * invT;
