@@ -38,8 +38,8 @@ NCU_TRAFFIC_BYTES = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="windows per modality per rank")
     ap.add_argument("--precision", default=os.environ.get("HULC2_PRECISION", "bf16"), choices=["fp32", "bf16"])
