@@ -526,15 +526,25 @@ def lmp_val(emb, goal, actions, robot_obs_raw, noise, P, cfg):
         g = torch.where(sample[..., -1] > 0, 1.0, -1.0)
         return mae, torch.mean((actions[..., -1] == g).float())
 
+    cont = cfg["distribution"]["dist"] == "continuous"      # plan_idx_* then hold the standard-normal eps of Normal.sample()
     pp_logits = plan_proposal(emb[:, 0], goal, P)
-    plan_pp = onehot_from_index(noise["plan_idx_pp"], 32).flatten(-2, -1)
+    if cont:
+        pp = gauss_state(pp_logits)
+        plan_pp = pp[0] + pp[1] * noise["plan_idx_pp"]
+    else:
+        plan_pp = onehot_from_index(noise["plan_idx_pp"], 32).flatten(-2, -1)
     loss_pp, act_pp = loss_and_act(plan_pp, noise["u1_pp"], noise["u2_pp"])
     mae_pp, sr_pp = metrics(act_pp)
     pr_logits, seq_feat = plan_recognition(emb, P, cfg["plan_recognition"]["num_heads"], cfg["plan_recognition"]["num_layers"], 0.0, None)
-    plan_pr = onehot_from_index(noise["plan_idx_pr"], 32).flatten(-2, -1)
+    if cont:
+        pr = gauss_state(pr_logits)
+        plan_pr = pr[0] + pr[1] * noise["plan_idx_pr"]
+    else:
+        plan_pr = onehot_from_index(noise["plan_idx_pr"], 32).flatten(-2, -1)
     loss_pr, act_pr = loss_and_act(plan_pr, noise["u1_pr"], noise["u2_pr"])
     mae_pr, sr_pr = metrics(act_pr)
-    kl = kl_loss(pp_logits, pr_logits, cfg["kl_beta"], cfg["kl_balancing_mix"])
+    kl = (kl_loss_gauss(pp, pr, cfg["kl_beta"], cfg["kl_balancing_mix"]) if cont
+          else kl_loss(pp_logits, pr_logits, cfg["kl_beta"], cfg["kl_balancing_mix"]))
     return plan_pp, loss_pp, plan_pr, loss_pr, kl, mae_pp, mae_pr, sr_pp, sr_pr, seq_feat
 
 

@@ -24,7 +24,8 @@ from oracle.ref_import import make_reference_model  # noqa: E402
 from oracle.ref_noise import supplied_categories, supplied_normals  # noqa: E402
 
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from helpers import ALT_CASES as CASES, ALT_WEIGHT_SEED as WEIGHT_SEED, NON_LEARNED, alt_case_inputs  # noqa: E402
+from helpers import ALT_CASES as CASES, ALT_VAL_TAGS, ALT_WEIGHT_SEED as WEIGHT_SEED, NON_LEARNED, alt_case_inputs, alt_val_inputs  # noqa: E402
+from oracle.ref_noise import supplied_uniforms  # noqa: E402
 
 
 def main():
@@ -50,6 +51,33 @@ def main():
             if p is not None and p.grad is not None:
                 G[f"{tag}/grad/{n}"] = p.grad.numpy()
         print(tag, float(loss), sum(1 for k in G if k.startswith(f"{tag}/grad_norm/")))
+    for tag in ALT_VAL_TAGS:                     # validation_step (hulc2.py:510-598) with the alternate blocks
+        kw, batch, noise = alt_val_inputs(tag)
+        m = make_reference_model(hulc2_config(pkg="hulc2", **kw))
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if v.dtype.is_floating_point}
+        m.load_state_dict(synthetic_state_dict(shapes, seed=WEIGHT_SEED, skip=NON_LEARNED), strict=False)
+        m.eval()
+
+        class _DM:
+            modalities = ["vis", "lang"]
+
+        class _Tr:
+            datamodule = _DM()
+
+        m.trainer = _Tr()
+        draws, unis = [], []
+        for mod in batch:
+            draws += [noise[mod]["plan_idx_pp"], noise[mod]["plan_idx_pr"]]
+            unis += [noise[mod][k] for k in ("u1_pp", "u2_pp", "u1_pr", "u2_pr")]
+        ctx = supplied_categories if kw["distribution"] == "discrete" else supplied_normals
+        with torch.no_grad(), ctx(draws), supplied_uniforms(unis):
+            out_d = m.validation_step(batch, 0)
+        for k, v in m.logged.items():
+            if k.startswith("val"):
+                G[f"{tag}/val/log/{k}"] = v.detach().numpy()
+        for k, v in out_d.items():
+            G[f"{tag}/val/out/{k}"] = v.detach().numpy()
+        print(tag, "val", sum(1 for k in G if k.startswith(f"{tag}/val/")))
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hulc2_alt_golden.npz")
     np.savez_compressed(out, **G)
     print("wrote", out, os.path.getsize(out), "bytes")

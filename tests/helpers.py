@@ -109,3 +109,26 @@ def build_alt_model(tag, device="cpu"):
     shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if v.dtype.is_floating_point}
     m.load_state_dict(synthetic_state_dict(shapes, seed=ALT_WEIGHT_SEED, skip=NON_LEARNED), strict=False)
     return m.to(device)
+
+
+ALT_VAL_TAGS = ("lstm", "gauss_gru")
+
+
+def alt_val_inputs(tag):
+    """Validation batch + per-modality noise for the alternate-block fixtures: plan draws (category indices or normal eps)
+    for the proposal and recognition plans, and the sampling uniforms of the two loss_and_act calls, in call order."""
+    from hulc2_b200.synthetic import synthetic_batch
+
+    kw = dict(ALT_CASES[tag], dropout_p=0.0, hidden_size=ALT_HIDDEN)
+    batch = synthetic_batch(ALT_B, seed=ALT_BATCH_SEED + 1, static_hw=kw["static_hw"], aux="all", depth_static=kw.get("depth_static", False))
+    g = torch.Generator().manual_seed(ALT_NOISE_SEED + 1)
+    noise = {}
+    for mod in batch:
+        if kw["distribution"] == "discrete":
+            d = [torch.randint(0, 32, (ALT_B, 32), generator=g) for _ in range(2)]
+        else:
+            d = [torch.randn(ALT_B, 256, generator=g) for _ in range(2)]
+        u = [torch.rand(ALT_B, 32, 6, 10, generator=g), torch.rand(ALT_B, 32, 6, generator=g),
+             torch.rand(ALT_B, 32, 6, 10, generator=g), torch.rand(ALT_B, 32, 6, generator=g)]
+        noise[mod] = {"plan_idx_pp": d[0], "plan_idx_pr": d[1], "u1_pp": u[0], "u2_pp": u[1], "u1_pr": u[2], "u2_pr": u[3]}
+    return kw, batch, noise

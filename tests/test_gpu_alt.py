@@ -248,3 +248,30 @@ def test_gated_decoder_act_carries_hidden_state(rnn_model):
         hr = hid if isinstance(hid, tuple) else (hid,)
         for a, b in zip(hs, hr):
             assert_close(a, b, 1e-5, f"hidden state after step {step}")
+
+
+@pytest.mark.parametrize("tag", ["lstm", "gauss_gru"])
+def test_alt_validation_step_vs_reference_fixture(tag):
+    """Hulc2.validation_step (hulc2.py:510-598) with an LSTM decoder / a continuous plan + GRU decoder, same supplied noise as
+    the unmodified reference: sampled plans, losses, MAE and gripper success-rate metrics."""
+    from helpers import alt_val_inputs
+
+    kw, batch, nz = alt_val_inputs(tag)
+    m = build_alt_model(tag).to(DEV).eval()
+    draws, unis = [], []
+    for mod in batch:
+        draws += [nz[mod]["plan_idx_pp"], nz[mod]["plan_idx_pr"]]
+        unis += [nz[mod][k] for k in ("u1_pp", "u2_pp", "u1_pr", "u2_pr")]
+    key = "categories" if kw["distribution"] == "discrete" else "normals"
+    with torch.no_grad(), noise.supplied(uniforms=unis, **{key: draws}):
+        out = m.validation_step(to_device(batch, DEV), 0)
+    for k in alt_keys(f"{tag}/val/out/"):
+        ref, mine = alt_gt(k), out[k[len(tag) + 9:]].cpu()
+        if ref.dtype.is_floating_point:
+            assert_close(mine, ref, 1e-5, k)
+        else:
+            assert torch.equal(mine, ref), k
+    for k in alt_keys(f"{tag}/val/log/"):
+        name = k[len(tag) + 9:]
+        tol = 2e-4 if "mae" in name else 1e-5            # MAE of x100-scaled orientation deltas (see test_gpu_step)
+        assert_close(m.logged[name], alt_gt(k), tol, name)

@@ -38,3 +38,28 @@ def test_model_state_dict_names_of_alternate_blocks():
     assert tuple(sd["action_decoder.rnn.weight_ih_l0"].shape) == (4 * 256, 64 + 32 + 1024)
     sd = build_alt_model("rgbd_rw").state_dict()
     assert tuple(sd["perceptual_encoder.depth_static_encoder.conv_model.0.weight"].shape) == (32, 1, 8, 8)
+
+
+@pytest.mark.parametrize("tag", ["lstm", "gauss_gru"])
+def test_alt_validation_matches_reference(tag):
+    """lmp_val (hulc2.py:247-334) with an LSTM decoder / a continuous plan + GRU decoder against the reference's validation_step."""
+    import torch
+
+    from helpers import alt_val_inputs
+
+    kw, batch, noise = alt_val_inputs(tag)
+    P = {k: v.detach() for k, v in oracle_params(build_alt_model(tag), requires_grad=False).items()}
+    cfg = hulc2_config(pkg="x", **kw)
+    for mod, db in batch.items():
+        with torch.no_grad():
+            emb = O.perceptual_encoder(db["rgb_obs"], db["depth_obs"], P)
+            goal = O.language_goal(db["lang"], P) if "lang" in mod else O.visual_goal(emb[:, -1], P)
+            (ppp, lpp, ppr, lpr, kl, mae_pp, mae_pr, sr_pp, sr_pr, _) = O.lmp_val(emb, goal, db["actions"], db["state_info"]["robot_obs"], noise[mod], P, cfg)
+        assert_close(ppp, alt_gt(f"{tag}/val/out/sampled_plan_pp_{mod}"), 1e-6, "plan pp")
+        assert_close(ppr, alt_gt(f"{tag}/val/out/sampled_plan_pr_{mod}"), 1e-6, "plan pr")
+        assert_close(lpp, alt_gt(f"{tag}/val/log/val_act/{mod}_act_loss_pp"), 1e-5)
+        assert_close(lpr, alt_gt(f"{tag}/val/log/val_act/{mod}_act_loss_pr"), 1e-5)
+        assert_close(kl, alt_gt(f"{tag}/val/log/val_kl/{mod}_kl_loss"), 1e-5)
+        assert_close(mae_pp.mean(), alt_gt(f"{tag}/val/log/val_total_mae/{mod}_total_mae_pp"), 1e-4)
+        assert_close(mae_pr.mean(), alt_gt(f"{tag}/val/log/val_total_mae/{mod}_total_mae_pr"), 1e-4)
+        assert_close(sr_pp, alt_gt(f"{tag}/val/log/val_grip/{mod}_grip_sr_pp"), 1e-6)
