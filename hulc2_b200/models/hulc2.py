@@ -243,7 +243,7 @@ class Hulc2(LightningModule):
     batch_modalities = True
 
     def _can_batch_modalities(self, batch) -> bool:
-        if len(batch) < 2 or self.dist.dist != "discrete" or not hasattr(self.action_decoder, "loss_modalities"):
+        if len(batch) < 2 or not hasattr(self.action_decoder, "loss_modalities"):
             return False
         mods = list(batch.values())
 
@@ -271,11 +271,17 @@ class Hulc2(LightningModule):
         latent_goal = ops.concat_rows(goals)
         pp_state = self.plan_proposal(emb[:, 0], latent_goal)
         pr_state, seq_feat = self.plan_recognition(emb)
-        sampled_plan = torch.flatten(self.dist.get_dist(pr_state).rsample(), start_dim=-2, end_dim=-1)
+        sampled_plan = self.dist.get_dist(pr_state).rsample()
+        if self.dist.dist == "discrete":
+            sampled_plan = torch.flatten(sampled_plan, start_dim=-2, end_dim=-1)
         act_losses = self.action_decoder.loss_modalities(
             sampled_plan, emb, latent_goal, [m["actions"] for m in mods], [m["state_info"]["robot_obs"] for m in mods])
-        kl_losses = ops.KLFunction.apply(pp_state.logit, pr_state.logit, self.dist.category_size, self.dist.class_size,
-                                         float(self.kl_balancing_mix), float(self.kl_beta), tuple(sizes))
+        if self.dist.dist == "discrete":
+            kl_losses = ops.KLFunction.apply(pp_state.logit, pr_state.logit, self.dist.category_size, self.dist.class_size,
+                                             float(self.kl_balancing_mix), float(self.kl_beta), tuple(sizes))
+        else:
+            kl_losses = ops.GaussKLFunction.apply(pp_state.mean, pp_state.std, pr_state.mean, pr_state.std,
+                                                  float(self.kl_balancing_mix), float(self.kl_beta), tuple(sizes))
         clip = None
         batch_size: Dict[str, Any] = {}
         terms, weights, kls, acts = [], [], [], []
