@@ -84,6 +84,12 @@ class LogisticDecoderRNN(ActionDecoder):
         """-> time-major hidden states [S,B,H] of the top layer and h_n [2,B,H]."""
         pe = perceptual_emb[..., slice(*self.perceptual_emb_slice)]
         r = self.rnn
+        if isinstance(r, nn.Sequential):
+            # mlp_decoder (logistic_decoder_rnn.py:270-272: ``x = self.rnn(x); h_n = None``): no state, every step independent
+            B, S = pe.shape[:2]
+            x = ops.DecoderInputFunction.apply(latent_plan, pe, latent_goal)
+            Hs = ops.mlp(x, [(r[0].weight, r[0].bias), (r[2].weight, r[2].bias), (r[4].weight, r[4].bias)], [True, True, False])
+            return Hs.view(S, B, -1), None
         if isinstance(r, (nn.GRU, nn.LSTM)):
             # h_0 follows torch: a [2,B,H] tensor for nn.GRU, an (h_0, c_0) pair for nn.LSTM; so does the returned h_n
             lstm = isinstance(r, nn.LSTM)

@@ -1612,6 +1612,49 @@ def concat_cols(a, b):
     return ConcatColsFunction.apply(a, b)
 
 
+class DecoderInputFunction(torch.autograd.Function):
+    """x_t = [plan | emb_t | goal] for every step (logistic_decoder_rnn.py:262-268), TIME-major rows [S*B, P+Es+G].  Used by the
+    MLP decoder (decoders/utils/rnn.py:39-46), which has no recurrence to fold the constant terms into."""
+
+    @staticmethod
+    def forward(ctx, plan, emb, goal):
+        plan, goal = _f32(plan).contiguous(), _f32(goal).contiguous()
+        B, S, Es = emb.shape
+        P, G = plan.shape[1], goal.shape[1]
+        In = P + Es + G
+        assert emb.stride(2) == 1
+        x = torch.empty(S * B, In, device=plan.device, dtype=torch.float32)
+        # dst[d1 = s, d0 = b, :D2] = src[b * s0 + s * s1 + :D2]: s1 = 0 broadcasts plan / goal over time
+        call("hulc2_transpose01", plan.data_ptr(), P, 0, x.data_ptr(), In, B, S, P, 0)
+        call("hulc2_transpose01", emb.data_ptr(), emb.stride(0), emb.stride(1), x.data_ptr() + 4 * P, In, B, S, Es, 0)
+        call("hulc2_transpose01", goal.data_ptr(), G, 0, x.data_ptr() + 4 * (P + Es), In, B, S, G, 0)
+        ctx.dims = (B, S, Es, P, G)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        B, S, Es, P, G = ctx.dims
+        In = P + Es + G
+        dx = dx.contiguous()
+        dev = dx.device
+        dplan = demb = dgoal = None
+        tsum = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[2]:
+            tsum = torch.empty(B, In, device=dev, dtype=torch.float32)
+            colsum(dx, B * In, S, B * In, tsum)                                  # sum over time, per window
+        if ctx.needs_input_grad[0]:
+            dplan = torch.empty(B, P, device=dev, dtype=torch.float32)
+            call("hulc2_copy2d", tsum.data_ptr(), In, dplan.data_ptr(), P, B, P, 0)
+        if ctx.needs_input_grad[2]:
+            dgoal = torch.empty(B, G, device=dev, dtype=torch.float32)
+            call("hulc2_copy2d", tsum.data_ptr() + 4 * (P + Es), In, dgoal.data_ptr(), G, B, G, 0)
+        if ctx.needs_input_grad[1]:
+            demb = torch.empty(B, S, Es, device=dev, dtype=torch.float32)
+            # dst[d1 = b, d0 = s, :Es] = dx[s * (B*In) + b * In + P + :Es]
+            call("hulc2_transpose01", dx.data_ptr() + 4 * P, B * In, In, demb.data_ptr(), Es, S, B, Es, 0)
+        return dplan, demb, dgoal
+
+
 class ConcatRowsFunction(torch.autograd.Function):
     """Stacks 2-D row blocks [B_i, D] into [sum B_i, D] (latent goals of several modalities -> one decoder batch)."""
 

@@ -355,12 +355,19 @@ def rnn_lstm(x: Tensor, P, hc0, num_layers: int = 2):
     return inp, (torch.stack(hn, 0), torch.stack(cn, 0))
 
 
+def mlp_dec(x: Tensor, P, h0=None):
+    """decoders/utils/rnn.py:39-46 (mlp_decoder): Linear-ReLU-Linear-ReLU-Linear per step, no state (h_n = None)."""
+    x = F.relu(linear(x, P, "action_decoder.rnn.0"))
+    x = F.relu(linear(x, P, "action_decoder.rnn.2"))
+    return linear(x, P, "action_decoder.rnn.4"), None
+
+
 def decoder_forward(plan, emb, goal, P, emb_slice=(64, 128), h0=None, n_dist=10, log_scale_min=-7.0, rnn="rnn_decoder"):
     """logistic_decoder_rnn.py:257-284."""
     pe = emb[..., emb_slice[0] : emb_slice[1]]
     B, S = pe.shape[:2]
     x = torch.cat([plan.unsqueeze(1).expand(-1, S, -1), pe, goal.unsqueeze(1).expand(-1, S, -1)], -1)
-    fn = {"rnn_decoder": rnn_relu, "gru_decoder": rnn_gru, "lstm_decoder": rnn_lstm}[rnn]
+    fn = {"rnn_decoder": rnn_relu, "gru_decoder": rnn_gru, "lstm_decoder": rnn_lstm, "mlp_decoder": mlp_dec}[rnn]
     x, hn = fn(x, P, h0)
     probs = linear(x, P, "action_decoder.prob_fc")
     means = linear(x, P, "action_decoder.mean_fc")

@@ -69,6 +69,7 @@ ALT_CASES = {
     "gauss_rw": dict(variant="real_world", static_hw=(150, 200), rnn_model="rnn_decoder", distribution="continuous"),
     "gauss_gru": dict(variant="calvin", static_hw=(200, 200), rnn_model="gru_decoder", distribution="continuous"),
     "rgbd_rw": dict(variant="real_world", static_hw=(150, 200), rnn_model="rnn_decoder", distribution="discrete", depth_static=True),
+    "mlp": dict(variant="calvin", static_hw=(200, 200), rnn_model="mlp_decoder", distribution="discrete"),
 }
 ALT_B, ALT_HIDDEN, ALT_WEIGHT_SEED, ALT_BATCH_SEED, ALT_NOISE_SEED = 2, 256, 5, 17, 19
 _alt_golden = None

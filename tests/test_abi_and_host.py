@@ -127,8 +127,10 @@ def test_synthetic_batch_contract_and_determinism():
 def test_unsupported_config_values_raise_not_fallback():
     from hulc2_b200._compat import instantiate
 
+    cfg = hulc2_config(hidden_size=64)
+    cfg["action_decoder"]["discrete_gripper"] = False
     with pytest.raises(NotImplementedError):
-        instantiate(hulc2_config(rnn_model="mlp_decoder", hidden_size=64))
+        instantiate(cfg)
     cfg = hulc2_config(hidden_size=64)
     cfg["visual_goal"]["activation_function"] = "ELU"
     with pytest.raises(NotImplementedError):
