@@ -130,13 +130,14 @@ _SIGS = {
     "hulc2_philox_uniform": [P, LL, C.c_ulonglong, C.c_ulonglong],
     "hulc2_dropout_mask": [P, LL, F, C.c_ulonglong, C.c_ulonglong],
     "hulc2_adam_step_dev": [P, P, P, P, LL, F, F, F, F, F, P, I, F],
+    "hulc2_adam_step_graph": [P, P, P, P, LL, P, F, F, F, F, P, I, F],
     "hulc2_philox_uniform_ep": [P, LL, C.c_ulonglong, C.c_ulonglong, P],
     "hulc2_dropout_mask_ep": [P, LL, F, C.c_ulonglong, C.c_ulonglong, P],
     "hulc2_counter_add": [P, C.c_ulonglong],
 }
 _NO_STREAM = {"hulc2_last_error": (C.c_char_p, []), "hulc2_version": (I, []), "hulc2_device_supports_tcgen05": (I, []),
               "hulc2_launch_count": (C.c_ulonglong, []), "hulc2_tma_gemm_count": (C.c_ulonglong, []), "hulc2_convb_supported": (I, [I, I, I, I, I]),
-              "hulc2_rnn_select_kernel": (I, [I]), "hulc2_rnn_cluster_capacity": (I, [I])}
+              "hulc2_rnn_select_kernel": (I, [I]), "hulc2_rnn_cluster_capacity": (I, [I]), "hulc2_rnn_device_error": (I, [I])}
 
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + list(_NO_STREAM))
 

@@ -17,6 +17,8 @@ int hulc2_rnn_persistent_launch(const float* add, const float* w, const float* i
                                 int S, int B, int H, int relu, int reverse, int transpose_w, void* workspace, long long workspace_bytes,
                                 cudaStream_t st);
 
+int hulc2_rnn_cluster_device_error(int clear);
+int hulc2_rnn_persistent_device_error(int clear);
 int hulc2_rnn_cluster_launch(const float* add, const float* w, const float* init, const float* mask, float* out, float* final_out,
                              int S, int B, int H, int relu, int reverse, int transpose_w, void* workspace, long long workspace_bytes,
                              cudaStream_t st);
@@ -87,6 +89,12 @@ int hulc2_rnn_select_kernel(int which) {
   int prev = g_rnn_kernel;
   g_rnn_kernel = which;
   return prev;
+}
+
+int hulc2_rnn_device_error(int clear) {
+  const int a = hulc2_rnn_cluster_device_error(clear), b = hulc2_rnn_persistent_device_error(clear);
+  if (a < 0 || b < 0) return -1;
+  return a | (b << 1);
 }
 
 // h[t] = relu(pre[t] + h[t-1] W_hh^T)      (nn.RNN, nonlinearity=relu; decoders/utils/rnn.py:5-14)

@@ -271,7 +271,9 @@ __global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc
 // ---------------------------------------------------------------- Adam (torch.optim.Adam, amsgrad=False, maximize=False)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
-                            float grad_scale, const unsigned long long* __restrict__ step_dev, int step_bias) {
+                            float grad_scale, const unsigned long long* __restrict__ step_dev, int step_bias,
+                            const float* __restrict__ lr_dev) {
+  if (lr_dev) lr = *lr_dev;   // learning rate lives on the device: an LR scheduler keeps working across graph replays
   if (step_dev) {  // step number lives on the device (CUDA-graph replays): bias corrections computed here
     const double st = (double)(*step_dev) + (double)step_bias;
     bc1 = (float)(1.0 - pow((double)b1, st));
@@ -490,7 +492,7 @@ int hulc2_adam_step(float* p, const float* g, float* m, float* v, long long n, f
   double bc1 = 1.0 - pow((double)beta1, (double)step);
   double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
-                                                    (float)sqrt(bc2), grad_scale, nullptr, 0);
+                                                    (float)sqrt(bc2), grad_scale, nullptr, 0, nullptr);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }
@@ -501,7 +503,17 @@ int hulc2_adam_step_dev(float* p, const float* g, float* m, float* v, long long 
   if (n <= 0) return HULC2_OK;
   if (!step_counter) { hulc2_set_error("adam_step_dev: null step counter"); return HULC2_EINVAL; }
   adam_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1.f, 1.f, grad_scale,
-                                                    step_counter, step_bias);
+                                                    step_counter, step_bias, nullptr);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_adam_step_graph(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev, float beta1, float beta2,
+                          float eps, float weight_decay, const unsigned long long* step_counter, int step_bias,
+                          float grad_scale, cudaStream_t st) {
+  if (n <= 0) return HULC2_OK;
+  if (!step_counter || !lr_dev) { hulc2_set_error("adam_step_graph: null step counter / learning-rate pointer"); return HULC2_EINVAL; }
+  adam_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, grad_scale,
+                                                    step_counter, step_bias, lr_dev);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

@@ -18,6 +18,7 @@
 //     H/128 CTAs producing those columns increment (16 arrivals per counter instead of 128 on one address).
 // H/128 clusters x 8 CTAs = 128 CTAs at H = 2048, all co-resident (checked with cudaOccupancyMaxActiveClusters).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -89,6 +90,12 @@ __device__ __forceinline__ void wait_pending(int n) {   // cp.async.wait_group n
     default: cp_async_wait<7>(); break;
   }
 }
+
+// Set when a flag wait gives up (co-residency of all clusters is guaranteed by the cooperative launch, so this only fires
+// on a protocol bug or a dying peer).  The waiter then proceeds with whatever state is there -- every barrier of the
+// step protocol is still matched, so the kernel terminates with wrong numbers instead of trapping the context; the host
+// reads the flag through hulc2_rnn_device_error().
+__device__ unsigned int g_cluster_rnn_error = 0;
 
 template <int CS>
 __global__ void __launch_bounds__(NT, 1) rnn_cluster_kernel(const ClusterRnnParams p) {
@@ -208,7 +215,10 @@ __global__ void __launch_bounds__(NT, 1) rnn_cluster_kernel(const ClusterRnnPara
           unsigned int v, spins = 0;
           do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
-            if (++spins > (1u << 23)) __trap();   // ~seconds: never hang the GPU
+            if ((++spins & 1023u) == 0) {          // never hang the GPU, never kill the context: flag the error and go on
+              if (spins > (1u << 23)) atomicExch(&g_cluster_rnn_error, 1u);
+              if (*reinterpret_cast<volatile unsigned int*>(&g_cluster_rnn_error)) break;
+            }
           } while (v < target);
         }
         __syncthreads();
@@ -312,22 +322,39 @@ __global__ void __launch_bounds__(NT, 1) rnn_cluster_kernel(const ClusterRnnPara
   if (warp == 0) tmem_dealloc(tmem_d, (uint32_t)NC);
 }
 
+static bool rnn_cooperative() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HULC2_RNN_COOP"); v = (e && e[0] == '0') ? 0 : 1; }   // A/B switch, read once
+  return v == 1;
+}
+
 template <int CS>
 static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int grid, cudaStream_t st) {
   memset(cfg, 0, sizeof(*cfg));
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  // cooperative: the launch only succeeds if EVERY cluster of the grid is co-resident (the per-slice flags are a grid-wide
+  // dependency); under concurrent work that takes SMs away the launch fails cleanly and the caller falls back
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = 1;
   cfg->gridDim = dim3(grid); cfg->blockDim = dim3(NT); cfg->dynamicSmemBytes = Geo<CS>::SMEM; cfg->stream = st;
-  cfg->attrs = attr; cfg->numAttrs = 1;
+  cfg->attrs = attr; cfg->numAttrs = rnn_cooperative() ? 2 : 1;
 }
 
 // how many CS-CTA clusters of the kernel can be co-resident on this device (one device per process); 0 = unusable
 template <int CS>
 static int cluster_capacity() {
-  static int max_clusters = -1;
-  if (max_clusters < 0) {
+  // per device (a process may drive several): index = cudaGetDevice()
+  static int cap[64];
+  static bool known[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  int& max_clusters = cap[dev];
+  if (!known[dev]) {
+    known[dev] = true;
     cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     cluster_config<CS>(&cfg, attr, MAX_H / NR, 0);
     cudaError_t e = cudaFuncSetAttribute(rnn_cluster_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<CS>::SMEM);
     int n = 0;
@@ -345,13 +372,27 @@ static int cluster_capacity() {
 template <int CS>
 static int cluster_launch(const ClusterRnnParams& p, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   cluster_config<CS>(&cfg, attr, p.H / NR, st);
-  if (cudaLaunchKernelEx(&cfg, rnn_cluster_kernel<CS>, p) != cudaSuccess) { cudaGetLastError(); return HULC2_ELAUNCH; }
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, rnn_cluster_kernel<CS>, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    // not all clusters can be co-resident right now (SMs held by concurrent work): let the caller take the next kernel
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) return HULC2_ENOTIMPL;
+    hulc2_set_error(cudaGetErrorString(e));
+    return HULC2_ELAUNCH;
+  }
   return HULC2_OK;
 }
 
 }  // namespace
+
+int hulc2_rnn_cluster_device_error(int clear) {
+  unsigned int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_cluster_rnn_error, sizeof(v)) != cudaSuccess) { cudaGetLastError(); return -1; }
+  if (clear && v) { const unsigned int z = 0; cudaMemcpyToSymbol(g_cluster_rnn_error, &z, sizeof(z)); }
+  return (int)v;
+}
 
 extern "C" int hulc2_rnn_cluster_capacity(int cluster_size) {
   if (cluster_size == 8) return cluster_capacity<8>();

@@ -14,6 +14,7 @@
 //   * steps are separated by a grid-wide release/acquire barrier on a global counter (all CTAs co-resident:
 //     grid <= SM count, 1 CTA per SM by shared-memory footprint).
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "../../include/hulc2_b200.h"
@@ -71,6 +72,8 @@ struct RnnParams {
   int relu, reverse, transpose_w;
 };
 
+__device__ unsigned int g_persistent_rnn_error = 0;   // see rnn_cluster_sm100.cu: flagged instead of trapping the context
+
 // grid-wide barrier: every CTA arrives once per call; generation g waits for g * gridDim.x arrivals
 __device__ __forceinline__ void grid_arrive(unsigned int* counter) {
   __syncthreads();
@@ -85,7 +88,10 @@ __device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int ta
     unsigned int spins = 0;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-      if (++spins > (1u << 23)) __trap();   // ~seconds: never hang the GPU
+      if ((++spins & 1023u) == 0) {
+        if (spins > (1u << 23)) atomicExch(&g_persistent_rnn_error, 1u);
+        if (*reinterpret_cast<volatile unsigned int*>(&g_persistent_rnn_error)) break;
+      }
     } while (v < target);
   }
   __syncthreads();
@@ -326,7 +332,28 @@ int hulc2_rnn_persistent_launch(const float* add, const float* w, const float* i
   p.outb = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + 256);
   p.S = S; p.B = B; p.H = H; p.relu = relu; p.reverse = reverse; p.transpose_w = transpose_w;
   if (cudaMemsetAsync(p.counter, 0, 4, st) != cudaSuccess) return HULC2_ELAUNCH;
-  rnn_persistent_kernel<<<grid, NT, smem, st>>>(p);
+  // cooperative launch: the grid barrier needs every CTA resident; if concurrent work holds SMs the launch fails cleanly
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  memset(&cfg, 0, sizeof(cfg));
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, rnn_persistent_kernel, p);
+  if (le != cudaSuccess) {
+    cudaGetLastError();
+    if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) return HULC2_ENOTIMPL;
+    hulc2_set_error(cudaGetErrorString(le));
+    return HULC2_ELAUNCH;
+  }
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
+}
+
+int hulc2_rnn_persistent_device_error(int clear) {
+  unsigned int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_persistent_rnn_error, sizeof(v)) != cudaSuccess) { cudaGetLastError(); return -1; }
+  if (clear && v) { const unsigned int z = 0; cudaMemcpyToSymbol(g_persistent_rnn_error, &z, sizeof(z)); }
+  return (int)v;
 }

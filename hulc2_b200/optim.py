@@ -22,8 +22,10 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self._arenas: List[Dict] = []
         self.grad_scale = 1.0  # multiplied into gradients inside the kernel (e.g. 1/world_size)
-        self.capturable = False  # True: the step number is read from a device counter (CUDA-graph replays)
+        self.capturable = False  # True: step number and learning rate are read from device memory (CUDA-graph replays)
         self._step_dev = None
+        self._lr_dev = None      # float32[n_groups] on the device, mirrors group["lr"] (see sync_lr)
+        self._lr_host: List[float] = []
         for group in self.param_groups:
             self._arenas.append(self._build_arena(group))
 
@@ -92,6 +94,9 @@ class FusedAdam(torch.optim.Optimizer):
                 return
 
     def grad_arenas(self) -> List[torch.Tensor]:
+        """Gradient arenas.  NOTE for data-parallel runs: after ``GradBucketReducer.finish()`` they (and every ``param.grad``)
+        hold the SUM over ranks; the 1/world mean is applied inside the Adam kernel (``grad_scale``).  Scale by
+        ``grad_scale`` before clipping or logging gradient norms."""
         return [a["g"] for a in self._arenas if a["n"]]
 
     # ------------------------------------------------------------------ optimizer API
@@ -118,17 +123,24 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        for group, a in zip(self.param_groups, self._arenas):
+        if self.capturable:
+            if not torch.cuda.is_current_stream_capturing():
+                self.sync_lr()              # (a fill captured into a graph would pin the learning rate at its capture-time value)
+            elif self._lr_dev is None or any(h != float(g["lr"]) for h, g in zip(self._lr_host, self.param_groups)):
+                raise RuntimeError("FusedAdam: call sync_lr() before capturing a step")
+        for gi, (group, a) in enumerate(zip(self.param_groups, self._arenas)):
             if not a["n"]:
                 continue
+            self._check_bound(a)
             self._attach_grads(a)
             ctr = self.step_counter(a["p"].device) if self.capturable else None
             a["step"] += 1
             b1, b2 = group["betas"]
             if self.capturable:
-                # step = (device counter of completed steps) + 1; the trainer bumps the counter after every step
-                call("hulc2_adam_step_dev", a["p"].data_ptr(), a["g"].data_ptr(), a["m"].data_ptr(), a["v"].data_ptr(), a["n"],
-                     float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                # step = (device counter of completed steps) + 1; the trainer bumps the counter after every step.  The
+                # learning rate is read from device memory, so schedulers keep working when this launch is replayed.
+                call("hulc2_adam_step_graph", a["p"].data_ptr(), a["g"].data_ptr(), a["m"].data_ptr(), a["v"].data_ptr(), a["n"],
+                     self._lr_dev.data_ptr() + 4 * gi, float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
                      ctr.data_ptr(), 1, float(self.grad_scale))
             else:
                 call("hulc2_adam_step", a["p"].data_ptr(), a["g"].data_ptr(), a["m"].data_ptr(), a["v"].data_ptr(), a["n"],
@@ -138,6 +150,36 @@ class FusedAdam(torch.optim.Optimizer):
 
         ops.invalidate_weight_mirrors()
         return loss
+
+    @staticmethod
+    def _check_bound(a) -> None:
+        """``param.data`` must still be the arena view: ``model.to()/.half()`` after construction rebinds it and the update
+        would silently go nowhere."""
+        lo = a["p"].data_ptr()
+        hi = lo + 4 * a["n"]
+        for p in a["params"]:
+            if not (lo <= p.data_ptr() < hi) or p.dtype != torch.float32:
+                raise RuntimeError("FusedAdam: a parameter no longer lives in the optimizer's arena (model.to()/.half() after "
+                                   "configure_optimizers?) -- build the optimizer after moving the model")
+
+    def captured_scalars(self) -> tuple:
+        """Host scalars a captured step freezes into kernel arguments (everything but lr and the step number)."""
+        return tuple((tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"])) for g in self.param_groups) + (float(self.grad_scale),)
+
+    def sync_lr(self) -> None:
+        """Mirror ``group["lr"]`` into the device vector the capturable Adam launch reads (one 4-byte fill per changed group,
+        on the current stream -- ordered before the step / replay that follows)."""
+        dev = next((a["p"].device for a in self._arenas if a["n"]), None)
+        if dev is None:
+            return
+        if self._lr_dev is None:
+            self._lr_dev = torch.zeros(len(self.param_groups), dtype=torch.float32, device=dev)
+            self._lr_host = [None] * len(self.param_groups)
+        for gi, group in enumerate(self.param_groups):
+            lr = float(group["lr"])
+            if self._lr_host[gi] != lr:
+                call("hulc2_fill", self._lr_dev.data_ptr() + 4 * gi, 1, lr)
+                self._lr_host[gi] = lr
 
     def step_counter(self, device) -> torch.Tensor:
         """int64[1] device counter of completed optimizer steps (used when ``capturable``)."""
@@ -187,3 +229,7 @@ class FusedAdam(torch.optim.Optimizer):
                     a["v"][o : o + p.numel()].view(p.shape).copy_(st["exp_avg_sq"])
                     a["step"] = int(float(st["step"]))
                 idx += 1
+        if self._step_dev is not None:          # resume: the device counter of completed steps follows the loaded state
+            done = max((a["step"] for a in self._arenas if a["n"]), default=0)
+            self._step_dev.fill_(int(done))
+        self._lr_host = [None] * len(self._lr_host)

@@ -116,10 +116,17 @@ def synthetic_batch_fast(B, S=32, seed=1, static_hw=(200, 200), device="cuda", m
 
 
 def tree_map(fn, x):
+    """Applies ``fn`` to every tensor leaf of a batch dict.  ``ops.U8Frames`` leaves (datamodule batches) keep viewing their
+    resident frame store; ``fn`` maps their index tensors (window starts / lengths / shift draws)."""
     if isinstance(x, dict):
         return {k: tree_map(fn, v) for k, v in x.items()}
     if isinstance(x, torch.Tensor):
         return fn(x)
+    if type(x).__name__ == "U8Frames":
+        from .ops import U8Frames
+
+        opt = lambda t: None if t is None else fn(t)  # noqa: E731
+        return U8Frames(x.u8, opt(x.shift), opt(x.win_start), opt(x.win_len), x.S)
     return x
 
 

@@ -17,32 +17,68 @@ from typing import Dict, Iterable, List, Optional
 import torch
 import torch.distributed as dist
 
-from . import noise
+from . import noise, ops
 from ._lib import call
 from .ddp import GradBucketReducer
 from .synthetic import tree_map
 
 
 def _zip_copy(dst, src, non_blocking=True):
+    """Copies the leaves of batch ``src`` into the same-shaped static batch ``dst`` (the tensors a captured step reads).
+    Camera frames delivered as ``ops.U8Frames`` (datamodule batches) keep pointing at the same resident frame store; their
+    window starts / lengths / shift draws are index tensors and are copied like any other leaf.  Any leaf that cannot be
+    refreshed in place raises: a replay must never silently pair old frames with new actions."""
     if isinstance(dst, dict):
+        if not isinstance(src, dict) or dst.keys() != src.keys():
+            raise KeyError(f"batch layout changed under a captured step: {sorted(dst)} vs {sorted(src) if isinstance(src, dict) else type(src)}")
         for k in dst:
             _zip_copy(dst[k], src[k], non_blocking)
     elif isinstance(dst, torch.Tensor):
+        if not isinstance(src, torch.Tensor) or dst.shape != src.shape or dst.dtype != src.dtype:
+            raise ValueError(f"batch leaf changed shape/dtype under a captured step: {tuple(dst.shape)} {dst.dtype} vs "
+                             f"{tuple(src.shape) if isinstance(src, torch.Tensor) else type(src)}")
         if dst.data_ptr() != src.data_ptr():
             dst.copy_(src, non_blocking=non_blocking)
+    elif isinstance(dst, ops.U8Frames):
+        if not isinstance(src, ops.U8Frames) or src.u8.data_ptr() != dst.u8.data_ptr() or src.u8.shape != dst.u8.shape or src.S != dst.S:
+            raise ValueError("U8Frames of a captured step must view the same resident frame store (pointer, shape, window length)")
+        for name in ("win_start", "win_len", "shift"):
+            d, s_ = getattr(dst, name), getattr(src, name)
+            if (d is None) != (s_ is None):
+                raise ValueError(f"U8Frames.{name} appeared/disappeared under a captured step")
+            if d is not None:
+                _zip_copy(d, s_, non_blocking)
+    elif dst is None and src is None:
+        pass
+    elif isinstance(dst, (int, float, bool, str)) and dst == src:
+        pass
+    else:
+        raise TypeError(f"cannot refresh a batch leaf of type {type(dst).__name__} in place for a captured step")
 
 
 class PolicyTrainer:
-    def __init__(self, model, bucket_mb: float = 25.0, use_graph: bool = False, graph_warmup: int = 2):
+    def __init__(self, model, bucket_mb: float = 25.0, use_graph: bool = False, graph_warmup: int = 2,
+                 device_counters: Optional[bool] = None):
         self.model = model
-        self.optimizer = model.configure_optimizers()["optimizer"]
+        opt_cfg = model.configure_optimizers()
+        self.optimizer = opt_cfg["optimizer"]
+        sched = opt_cfg.get("lr_scheduler")
+        # Lightning steps {"scheduler", "interval": "step", "frequency": 1} after every optimizer step (hulc2.py:185-198)
+        self.scheduler = sched["scheduler"] if isinstance(sched, dict) else sched
+        self._sched_every = int(sched.get("frequency", 1)) if isinstance(sched, dict) else 1
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.reducer: Optional[GradBucketReducer] = None
         if hasattr(self.optimizer, "grad_arenas"):
             self.reducer = GradBucketReducer(self.optimizer, bucket_mb)
         self.device = next(model.parameters()).device
         self.use_graph = bool(use_graph) and hasattr(self.optimizer, "step_counter")
+        # device_counters: drive the eager step exactly like the captured body (noise epoch + Adam step number on the
+        # device, host noise counter restarted per step) -- what the graph-vs-eager parity tests compare against
+        self.device_counters = self.use_graph if device_counters is None else (bool(device_counters) and hasattr(self.optimizer, "step_counter"))
         self.graph_warmup = graph_warmup
+        self.steps_done = 0
+        self.recaptures = 0
+        self._captured_scalars = None
         self._eager_steps = 0
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.static_batch = None
@@ -52,12 +88,12 @@ class PolicyTrainer:
         # Every step runs on ONE side stream: autograd's AccumulateGrad nodes remember the stream they were created on,
         # and a node created on the legacy default stream cannot take part in a stream capture.
         self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
-        if self.use_graph:
+        if self.device_counters:
             self.optimizer.capturable = True
 
     # ------------------------------------------------------------------ one step (eager body; also what gets captured)
     def _step_body(self, batch: Dict[str, dict], batch_idx: int) -> torch.Tensor:
-        noise.begin_step() if self.use_graph else None
+        noise.begin_step() if self.device_counters else None
         self.optimizer.zero_grad()
         loss = self.model.training_step(batch, batch_idx)
         if self.reducer is not None:
@@ -66,7 +102,7 @@ class PolicyTrainer:
         if self.reducer is not None:
             self.reducer.finish()
         self.optimizer.step()
-        if self.use_graph:
+        if self.device_counters:
             # completed-step counters on the device: Adam bias correction and the noise epoch of the NEXT step
             call("hulc2_counter_add", self.optimizer.step_counter(self.device).data_ptr(), 1)
             call("hulc2_counter_add", noise.epoch_tensor(self.device).data_ptr(), 1)
@@ -77,7 +113,7 @@ class PolicyTrainer:
         Stream semantics are those of an ordinary call: the work is ordered after the caller's current stream and the
         caller's stream waits for it."""
         if self.stream is None:
-            return self._step_body(batch, batch_idx)
+            return self._train_step_on_stream(batch, batch_idx)
         caller = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(caller)
         with torch.cuda.stream(self.stream):
@@ -85,9 +121,35 @@ class PolicyTrainer:
         caller.wait_stream(self.stream)
         return loss
 
+    def _host_scalars(self) -> tuple:
+        """Host-side scalars that a capture freezes into kernel arguments: the KL / clip loss weights (``set_kl_beta`` is
+        called by the KL-annealing callbacks once per epoch, utils/kl_callbacks.py:19-22) and Adam's betas / eps / weight
+        decay / gradient scale.  The learning rate is NOT among them (device-resident, ``FusedAdam.sync_lr``)."""
+        m = self.model
+        opt = self.optimizer.captured_scalars() if hasattr(self.optimizer, "captured_scalars") else ()
+        return (float(getattr(m, "kl_beta", 0.0)), float(getattr(m, "kl_balancing_mix", 0.0)),
+                float(getattr(m, "clip_auxiliary_loss_beta", 0.0)), bool(m.training), ops.get_precision(), opt)
+
+    def _after_step(self) -> None:
+        self.steps_done += 1
+        if self.scheduler is not None and self.steps_done % self._sched_every == 0:
+            self.scheduler.step()
+
     def _train_step_on_stream(self, batch, batch_idx):
+        loss = self._train_step_inner(batch, batch_idx)
+        self._after_step()
+        return loss
+
+    def _train_step_inner(self, batch, batch_idx):
         if not self.use_graph:
             return self._step_body(batch, batch_idx)
+        self.optimizer.sync_lr()                        # group["lr"] -> device (a scheduler may have moved it)
+        if self._graph is not None and self._captured_scalars != self._host_scalars():
+            # a frozen scalar changed (e.g. set_kl_beta at an epoch boundary): capture again over the same static batch
+            _zip_copy(self.static_batch, batch)
+            batch = self.static_batch
+            self._graph = None
+            self.recaptures += 1
         if self._graph is None:
             if self._eager_steps < self.graph_warmup:
                 self._eager_steps += 1
@@ -113,6 +175,7 @@ class PolicyTrainer:
         self.static_batch = batch               # the tensors the graph reads; later batches are copied into them
         from ._lib import load_library
 
+        self._captured_scalars = self._host_scalars()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         n0 = load_library().hulc2_launch_count()

@@ -283,6 +283,11 @@ int hulc2_rnn_select_kernel(int which);
 /* number of cluster_size-CTA (8 or 4) clusters of kernel (a) that can be co-resident on the current device; (a) runs with
  * clusters of 8 when H/128 of them fit, else with clusters of 4 when H/64 fit (a 148-SM B200 reports 15 clusters of 8) */
 int hulc2_rnn_cluster_capacity(int cluster_size);
+/* The persistent kernels (a)/(b) are launched cooperatively (every CTA / cluster co-resident or the launch is refused and the
+ * next kernel in the list runs).  Should a step-flag wait still give up, the kernel flags the error on the device and finishes
+ * (no trap, the context survives).  This reads the flags -- SYNCHRONISES the device: bit 0 = kernel (a), bit 1 = kernel (b);
+ * clear != 0 resets them; -1 on a CUDA error. */
+int hulc2_rnn_device_error(int clear);
 
 /* ------------------------------------------------------------------ gated recurrence cells (decoders/utils/rnn.py:17-36)
  * One step of nn.GRU (gate order r,z,n) / nn.LSTM (i,f,g,o); the contractions are hulc2_gemm calls, these are the
@@ -335,6 +340,11 @@ int hulc2_dropout_mask(unsigned char* out, long long n, float p, unsigned long l
 int hulc2_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                         float eps, float weight_decay, const unsigned long long* step_counter, int step_bias,
                         float grad_scale, hulc2_stream_t stream);
+/* As adam_step_dev with the learning rate read from device memory (*lr_dev) at run time, so that an LR scheduler
+ * (hulc2.py:185-198, conf/model/lr_scheduler) keeps steering a captured train step. */
+int hulc2_adam_step_graph(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev, float beta1, float beta2,
+                          float eps, float weight_decay, const unsigned long long* step_counter, int step_bias,
+                          float grad_scale, hulc2_stream_t stream);
 int hulc2_philox_uniform_ep(float* out, long long n, unsigned long long seed, unsigned long long offset,
                             const unsigned long long* epoch, hulc2_stream_t stream);
 int hulc2_dropout_mask_ep(unsigned char* out, long long n, float p, unsigned long long seed, unsigned long long offset,

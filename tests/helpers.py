@@ -60,6 +60,17 @@ def assert_close(a, b, tol, what=""):
     assert e <= tol, f"{what}: rel err {e:.3e} > {tol:.1e}"
 
 
+GRAD_SAMPLE = 4096
+
+
+def grad_sample_index(name: str, numel: int) -> np.ndarray:
+    """Seeded flat positions at which big gradients are compared with the fp64 fixture (tests/golden/make_grad_noise_floor.py)."""
+    if numel <= GRAD_SAMPLE:
+        return np.arange(numel, dtype=np.int64)
+    seed = int.from_bytes(name.encode()[-8:].rjust(8, b"\0"), "little") % (2**31)
+    return np.sort(np.random.default_rng(seed).choice(numel, GRAD_SAMPLE, replace=False)).astype(np.int64)
+
+
 # ----------------------------------------------------------------------------- alternate blocks (SURVEY 8f row 4)
 ALT_GOLDEN_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hulc2_alt_golden.npz")
 # tag -> config kwargs; B=2 windows per modality, hidden_size 256 keeps fixture generation and the oracle check fast

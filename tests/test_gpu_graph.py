@@ -1,0 +1,212 @@
+"""GPU parity of the path bench.py TIMES: ``PolicyTrainer(use_graph=True)`` -- two eager warm-up steps, one capture, then
+CUDA-graph replays with the Adam step number, the noise epoch and the learning rate living on the device
+(hulc2/models/hulc2.py:336-442 + :185-198 driven as Lightning's loop does).
+
+  * replay == eager: the same step driven call by call with the same device counters (dropout 0.1 ACTIVE, Philox noise),
+    parameters compared after every step, fp32 and bf16;
+  * replay == oracle + torch.optim.Adam over 4 steps (supplied plan draws refreshed in place between replays);
+  * replay on datamodule batches (``ops.U8Frames`` leaves: window starts / lengths / shift draws are refreshed, the frame
+    store pointer is asserted) == eager;
+  * scalars a capture would freeze: learning rate (device-resident, scheduler honoured) and ``set_kl_beta`` (re-capture).
+"""
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+
+from hulc2_b200 import noise, ops
+from hulc2_b200.config import hulc2_config
+from hulc2_b200.synthetic import synthetic_batch
+from hulc2_b200.trainer import PolicyTrainer
+
+from helpers import build_model, oracle_params, to_device
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+LR = 2e-4
+
+
+@pytest.fixture(autouse=True)
+def _restore_precision():
+    yield
+    ops.set_precision("fp32")
+
+
+def _params(m):
+    return {n: p.detach().clone() for n, p in m.named_parameters()}
+
+
+def _compare_params(a, b, k, what, frac_tol=2e-3):
+    """Adam's update is lr * m / (sqrt(v) + eps): an element whose gradient is at rounding level may move by up to lr in
+    either direction per step, so two runs that differ only by fp32 summation order (atomics in LayerNorm's weight
+    gradient) agree on all but a tiny fraction of elements; none may differ by more than k sign flips of one update."""
+    bad = tot = 0
+    for n in a:
+        d = (a[n] - b[n]).abs()
+        bad += int((d > 1e-6).sum())
+        tot += d.numel()
+        assert float(d.max()) <= 2.0 * LR * k + 1e-6, f"{what}: {n} moved by {float(d.max()):.3e} after {k} steps"
+    assert bad / tot < frac_tol, f"{what}: {bad}/{tot} elements differ after {k} steps"
+    return bad / tot
+
+
+def _drive(use_graph, batches, steps, precision, dropout_p, hidden=256, hooks=None):
+    """Runs `steps` train steps; returns [(loss, params)] per step and the trainer.  Both modes use the device counters."""
+    ops.set_precision(precision)
+    noise.manual_seed(1234)
+    noise.epoch_tensor(torch.device(DEV)).zero_()
+    m = build_model("calvin", dropout_p=dropout_p, hidden_size=hidden).to(DEV).train()
+    tr = PolicyTrainer(m, use_graph=use_graph, device_counters=True)
+    out = []
+    for i in range(steps):
+        if hooks and i in hooks:
+            hooks[i](m, tr)
+        loss = tr.train_step(batches[i % len(batches)], i)
+        torch.cuda.synchronize()
+        out.append((float(loss), _params(m)))
+    return out, tr
+
+
+@pytest.mark.parametrize("precision,loss_tol", [("fp32", 1e-5), ("bf16", 1e-5)])
+def test_graph_replay_equals_eager_steps(precision, loss_tol):
+    """6 steps (2 eager, capture + 4 replays) vs 6 eager steps with identical device-side noise epochs: dropout masks and the
+    plan draw come from the Philox kernels in both, so every loss and every parameter must agree step by step."""
+    batches = [to_device(synthetic_batch(2, seed=40 + i, aux="half"), DEV) for i in range(3)]
+    g, trg = _drive(True, batches, 6, precision, 0.1)
+    e, tre = _drive(False, batches, 6, precision, 0.1)
+    assert trg._graph is not None and trg.replays == 4 and tre._graph is None
+    assert trg.launches_per_replay > 100
+    for k, ((lg, pg), (le, pe)) in enumerate(zip(g, e), 1):
+        assert abs(lg - le) <= loss_tol * abs(le), f"step {k}: loss {lg} (graph) vs {le} (eager)"
+        _compare_params(pg, pe, k, f"{precision} graph vs eager")
+    # the device counters advanced once per step in both runs
+    assert int(trg.optimizer.step_counter(torch.device(DEV))) == 6 and int(tre.optimizer.step_counter(torch.device(DEV))) == 6
+    assert trg.optimizer._arenas[0]["step"] == 6
+    assert ops_rnn_error() == 0
+
+
+def ops_rnn_error():
+    from hulc2_b200 import _lib
+
+    return int(_lib.load_library().hulc2_rnn_device_error(1))
+
+
+def test_graph_replay_vs_oracle_and_torch_adam():
+    """4 optimizer steps through the captured graph (plan draws supplied in device tensors that are refreshed in place
+    before each replay) against the CPU oracle + torch.optim.Adam stepping the same parameters."""
+    from oracle import hulc2_oracle as O
+
+    B, hidden, steps = 2, 256, 4
+    m = build_model("calvin", hidden_size=hidden)
+    P = oracle_params(m)
+    cfg = hulc2_config(pkg="x", dropout_p=0.0, hidden_size=hidden)
+    cpu_batches = [synthetic_batch(B, seed=50 + i, aux="all") for i in range(steps)]
+    g = torch.Generator().manual_seed(51)
+    draws = [{mod: torch.randint(0, 32, (B, 32), generator=g) for mod in cpu_batches[0]} for _ in range(steps)]
+    leaves = [v for v in P.values() if v.requires_grad]
+    opt = torch.optim.Adam(leaves, lr=LR)
+    ref = []
+    for i in range(steps):
+        opt.zero_grad()
+        out = O.training_step(cpu_batches[i], {mod: {"plan_idx": draws[i][mod]} for mod in cpu_batches[i]}, P, cfg)
+        out["loss"].backward()
+        opt.step()
+        ref.append((float(out["loss"]), {k: v.detach().clone() for k, v in P.items() if v.requires_grad}))
+
+    noise.epoch_tensor(torch.device(DEV)).zero_()
+    m = m.to(DEV).train()
+    tr = PolicyTrainer(m, use_graph=True)
+    static_draw = [torch.zeros(B, 32, dtype=torch.int64, device=DEV) for _ in cpu_batches[0]]
+    for i in range(steps):
+        for t, mod in zip(static_draw, cpu_batches[i]):
+            t.copy_(draws[i][mod])
+        ctx = noise.supplied(categories=static_draw) if tr._graph is None else contextlib.nullcontext()
+        with ctx:   # eager warm-up steps and the capture consume the queue once; replays re-read the same device tensors
+            loss = tr.train_step(to_device(cpu_batches[i], DEV), i)
+        torch.cuda.synchronize()
+        # step 1 sees identical parameters (1e-5); later steps see parameters that already differ by Adam-amplified rounding
+        # noise (a sign flip of an lr-sized update on < 0.5 % of the elements, bounded below), so their losses agree to ~1e-4
+        tol = 1e-5 if i == 0 else 1e-3
+        assert abs(float(loss) - ref[i][0]) <= tol * abs(ref[i][0]), f"step {i + 1}: {float(loss)} vs {ref[i][0]}"
+        print(f"[graph vs oracle] step {i + 1}: loss rel err {abs(float(loss) - ref[i][0]) / abs(ref[i][0]):.2e}")
+        mine = {n: p.detach().cpu() for n, p in m.named_parameters() if n in ref[i][1]}
+        _compare_params(mine, ref[i][1], i + 1, "graph vs oracle+torch.optim.Adam", frac_tol=5e-3)
+    assert tr.replays == steps - 2
+
+
+def test_graph_replay_on_datamodule_batches():
+    """Batches described by index tensors over a resident uint8 frame store (``ops.U8Frames``): a replay must read the NEW
+    windows / shifts, not the ones of the captured batch (the copy used to skip U8Frames leaves)."""
+    from hulc2_b200.datamodule import Hulc2DeviceDataModule, synthetic_store
+
+    store = synthetic_store(200, device=DEV, seed=3)
+    rng = np.random.default_rng(0)
+    lang_emb = torch.from_numpy(rng.standard_normal((3, 384)).astype(np.float32))
+    split = {"store": store, "ep_start_end_ids": [(0, 99), (100, 199)], "lang_start_end": [(0, 60), (60, 130), (130, 190)], "lang_emb": lang_emb}
+    cfg = {"vis": dict(batch_size=2, min_window_size=16, max_window_size=32), "lang": dict(batch_size=2, min_window_size=20, max_window_size=32)}
+
+    def batches():
+        dm = Hulc2DeviceDataModule(cfg, split, None, seed=1)
+        dm.setup()
+        it = iter(dm.train_dataloader())
+        return [next(it) for _ in range(5)]
+
+    bs = batches()
+    starts = [b["vis"]["rgb_obs"]["rgb_static"].win_start.tolist() for b in bs]
+    assert len({tuple(s) for s in starts}) > 1, "the test needs batches over different windows"
+    g, trg = _drive(True, bs, 5, "bf16", 0.1)
+    e, _ = _drive(False, batches(), 5, "bf16", 0.1)
+    assert trg.replays == 3
+    for k, ((lg, pg), (le, pe)) in enumerate(zip(g, e), 1):
+        assert abs(lg - le) <= 1e-5 * abs(le), f"step {k}: loss {lg} (graph) vs {le} (eager)"
+        _compare_params(pg, pe, k, "datamodule batches, graph vs eager")
+    # a batch over a different frame store cannot be replayed in place: loud error, not stale frames
+    other = synthetic_store(200, device=DEV, seed=4)
+    bad = dict(bs[0])
+    bad["vis"] = dict(bad["vis"], rgb_obs={k: ops.U8Frames(other.rgb[k], v.shift, v.win_start, v.win_len, v.S)
+                                           for k, v in bs[0]["vis"]["rgb_obs"].items()})
+    with pytest.raises(ValueError):
+        trg.train_step(bad, 0)
+
+
+def test_graph_honours_lr_schedule_and_kl_beta_changes():
+    """Scalars a capture freezes into kernel arguments: the learning rate is device-resident and follows
+    ``param_groups[..]["lr"]`` (an LR scheduler) across replays; ``set_kl_beta`` (kl_callbacks.py:19-22, once per epoch)
+    triggers a re-capture.  Both must track the eager run."""
+    batches = [to_device(synthetic_batch(2, seed=60 + i, aux="all"), DEV) for i in range(2)]
+
+    def halve_lr(m, tr):
+        for grp in tr.optimizer.param_groups:
+            grp["lr"] = LR / 2
+
+    def new_beta(m, tr):
+        m.set_kl_beta(0.05)
+
+    hooks = {3: halve_lr, 5: new_beta}
+    g, trg = _drive(True, batches, 7, "fp32", 0.0, hooks=hooks)
+    e, _ = _drive(False, batches, 7, "fp32", 0.0, hooks=hooks)
+    assert trg.recaptures == 1 and trg.replays == 5
+    for k, ((lg, pg), (le, pe)) in enumerate(zip(g, e), 1):
+        assert abs(lg - le) <= 1e-5 * abs(le), f"step {k}: loss {lg} (graph) vs {le} (eager)"
+        _compare_params(pg, pe, k, "lr / kl_beta changes, graph vs eager")
+    # the KL term really changed at step 6 (beta 0.01 -> 0.05) and the halved rate really applied at step 4
+    assert abs(g[5][0] - g[4][0]) > 0
+    moved_full = max(float((g[2][1][n] - g[1][1][n]).abs().max()) for n in g[0][1])
+    moved_half = max(float((g[3][1][n] - g[2][1][n]).abs().max()) for n in g[0][1])
+    assert moved_half < 0.75 * moved_full, (moved_half, moved_full)
+
+
+def test_scheduler_is_stepped_by_the_trainer():
+    """configure_optimizers' {"scheduler", "interval": "step"} entry (hulc2.py:185-198) is stepped once per train step."""
+    m = build_model("calvin", hidden_size=256).to(DEV).train()
+    m.lr_scheduler = {"_target_": "torch.optim.lr_scheduler.StepLR", "step_size": 1, "gamma": 0.5}
+    tr = PolicyTrainer(m, use_graph=True)
+    batch = to_device(synthetic_batch(2, seed=70, aux="all"), DEV)
+    lrs = []
+    for i in range(4):
+        tr.train_step(batch, i)
+        lrs.append(tr.optimizer.param_groups[0]["lr"])
+    torch.cuda.synchronize()
+    assert lrs == [LR * 0.5 ** (i + 1) for i in range(4)]
+    assert abs(float(tr.optimizer._lr_dev[0]) - LR * 0.5 ** 3) < 1e-12   # the value the last replay read
