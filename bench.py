@@ -43,14 +43,17 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="windows per modality per rank")
     ap.add_argument("--precision", default=os.environ.get("HULC2_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    ap.add_argument("--cpu-batch", type=int, default=8, help="windows per modality of the bounded CPU sample")
+    ap.add_argument("--cpu-batch", type=int, default=None,
+                    help="windows per modality of the bounded CPU sample (default: 8 for the in-run cpu_baseline, 32 = configs[0] for --impl reference)")
+    ap.add_argument("--profile-passes", type=int, default=3, help="eager per-call profiling passes behind the timed region (median per call)")
+    ap.add_argument("--no-fp32-frames", action="store_true", help="skip the secondary value_fp32_frames measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-graph", action="store_true", help="drive every step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--frames", default="uint8", choices=["uint8", "fp32"],
                     help="camera frames in the batch: uint8 HWC + RandomShiftsAug draw, scaled/normalised/shifted on the device "
                          "(datamodule kernel, SURVEY 8f-1), or the reference batch contract's fp32 NCHW tensors")
-    ap.add_argument("--workload", default="train", choices=["train", "rollout"],
+    ap.add_argument("--workload", default="train", choices=["train", "rollout", "validation"],
                     help="train = configs[1] (the headline metric); rollout = configs[4]: batched policy inference, --envs parallel "
                          "environments, one re-plan + 29 plain control steps per bench step (a separate metric, never the default)")
     ap.add_argument("--envs", type=int, default=1024)
@@ -119,19 +122,48 @@ def time_cpu(B, steps, warmup):
     return 2 * B / dt, dt, cores
 
 
+def bench_config(args, world, h2d_bytes=None, cuda_graph=True):
+    """`config` of the JSON line: names the WORKLOAD (BASELINE.json configs[1] / configs[3]); both arms print the same dict."""
+    B = args.batch
+    rw, rgbd = args.variant != "calvin", args.variant == "real_world_rgbd"
+    per_win = 32 * ((3 * (150 if rw else 200) * 200 + 3 * 84 * 84) * (1 if args.frames == "uint8" else 4) + ((150 * 200 * 4) if rgbd else 0))
+    frames_gb = 2 * B * per_win / 1e9
+    return {"workload": (f"configs[1]: Hulc2 policy train step (fwd+bwd+allreduce+Adam), B={B}/modality/GPU, window 32, static 200x200 + gripper 84x84 RGB, 7-dof, lang [B,384], dropout 0.1"
+                         if not rw else
+                         f"configs[3]: cfg_low_level_rw-shaped Hulc2 train step, B={B}/modality/GPU, window 32, static 150x200 RGB{' + depth_static' if rgbd else ''} + gripper 84x84, 7-dof, no clip loss, dropout 0.1"),
+            "frames": ("uint8 HWC frames + per-frame RandomShiftsAug draw in the batch; scale/normalise/shift run on the device inside the step (fused into the trunk's pack kernel)"
+                       if args.frames == "uint8" else "fp32 NCHW frames in [-1,1] (reference batch contract; transforms already applied)"),
+            "windows_per_step_per_gpu": 2 * B, "parallelism": f"dp{world}", "l2": f"inputs ({frames_gb:.2f} GB of frames/step) exceed the 126 MB L2",
+            "precision": args.precision, "cuda_graph": bool(cuda_graph)}
+
+
+def cpu_baseline(args, B, steps, warmup, check_config_batch):
+    """The oracle port on the host cores: `steps` timed steps of {vis:B, lang:B} windows after `warmup`; optionally ONE timed
+    step (after one warm-up) at the reference's own CPU config batch B=32 (configs[0]) so the bias of the small sample is stated."""
+    wps, dt, cores = time_cpu(B, steps, warmup)
+    cpu = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
+           "sample": f"oracle port of Hulc2.training_step+backward+Adam (CPU restatement pinned to the unmodified reference), fp32, {{vis:{B}, lang:{B}}} windows/step "
+                     f"(bounded sample of the B={args.batch} workload), {warmup} warm-up + {steps} timed steps ({dt:.2f} s/step), torch {torch.__version__}, {cores} threads"}
+    if check_config_batch and B != 32:
+        wps32, dt32, _ = time_cpu(32, 1, 1)
+        cpu["config_batch_check"] = {"windows_per_step": 64, "value": wps32, "s_per_step": dt32, "bias_of_sample": wps / wps32,
+                                     "note": "one timed step (after one warm-up) at the reference's own CPU config, configs[0] = {vis:32, lang:32}"}
+    return cpu
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wps, dt, cores = time_cpu(args.cpu_batch, args.steps, args.warmup)
-    sample = f"oracle port of Hulc2.training_step+backward+Adam, fp32, {{vis:{args.cpu_batch}, lang:{args.cpu_batch}}} windows per step (bounded sample of the B={args.batch} workload), torch {torch.__version__}"
+    B = args.cpu_batch or 32          # configs[0]: the reference's own CPU-runnable case
+    cpu = cpu_baseline(args, B, args.steps, args.warmup, False)
+    wps = cpu["value"]
     line = {
         "impl": "reference", "metric": "train windows/sec", "value": wps, "unit": "windows/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 2 * B / wps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: Hulc2 policy train step, B=64/modality, window 32, static 200x200 + gripper 84x84, 7-dof",
-                   "windows_per_step_timed": 2 * args.cpu_batch},
-        "cpu_baseline": {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": bench_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
+        "cpu_baseline": cpu,
         "e2e": {"value": wps, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -183,6 +215,100 @@ def nbytes(x):
     return x.numel() * x.element_size() if isinstance(x, torch.Tensor) else 0
 
 
+def family_of(key: str) -> str:
+    """Kernel family of a per-call profile key: the entry point, with the two directions of the recurrence merged."""
+    base = key.split("[")[0]
+    return {"rnn_relu_fwd": "rnn_relu", "rnn_relu_bwd": "rnn_relu"}.get(base, base)
+
+
+def median_profile(passes):
+    """{key: rec} per pass -> {key: rec} with the MEDIAN time over passes (calls / flops / bytes are identical per pass)."""
+    out = {}
+    for key in passes[0]:
+        ms = sorted(p[key]["ms"] for p in passes if key in p)
+        out[key] = dict(passes[0][key], ms=ms[len(ms) // 2])
+    return out
+
+
+def roofline_from_profile(recs, peaks, step_tflops, n_passes):
+    """Groups the per-call records into kernel families, places every family that has an algorithmic work model against the
+    roof that bounds it (FLOP/byte vs the measured ridge), and reports the family with the largest share of the step."""
+    ridge = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    fams = {}
+    for r in recs.values():
+        f = fams.setdefault(family_of(r["key"]), {"family": family_of(r["key"]), "ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0, "members": []})
+        f["ms"] += r["ms"]
+        f["calls"] += r["calls"]
+        f["flops"] += r["flops"]
+        f["bytes"] += r.get("bytes", 0.0)
+        f["members"].append(r["key"])
+    total_ms = sum(f["ms"] for f in fams.values())
+    for f in fams.values():
+        sec = f["ms"] * 1e-3
+        f["share_of_step"] = f["ms"] / total_ms if total_ms else None
+        if (f["bytes"] <= 0 and f["flops"] <= 0) or sec <= 0:
+            f["bound"] = None                                   # no work model: never a roofline candidate
+            continue
+        intensity = f["flops"] / f["bytes"] if f["bytes"] > 0 else float("inf")
+        if intensity < ridge:
+            f.update(bound="hbm", achieved=f["bytes"] / sec / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
+        else:
+            f.update(bound="tensor", achieved=f["flops"] / sec / 1e12, peak=peaks["tflops"], unit="TFLOP/s")
+        f["frac"] = f["achieved"] / f["peak"]
+        f["flop_per_byte"] = None if intensity == float("inf") else intensity
+    ranked = sorted((f for f in fams.values() if f["bound"]), key=lambda f: -f["ms"])
+    if not ranked:
+        return None
+    top = ranked[0]
+    traffic = [NCU_TRAFFIC_BYTES.get(k) for k in top["members"]]
+    roof = {"bound": top["bound"], "kernel": top["family"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
+            "frac": top["frac"], "traffic": (sum(traffic) / top["calls"]) if traffic and all(t is not None for t in traffic) else None,
+            "algorithmic_bytes_per_launch": top["bytes"] / top["calls"], "algorithmic_flops_per_launch": top["flops"] / top["calls"],
+            "flop_per_byte": top["flop_per_byte"], "ridge_flop_per_byte": ridge, "peak_source": peaks["src"],
+            "share_of_step": top["share_of_step"], "calls_per_step": top["calls"], "avg_ms": top["ms"] / top["calls"], "members": top["members"],
+            "step_tflops": step_tflops,
+            "timing": f"CUDA events per C-ABI call on the launch stream, eager step behind the timed region, L2 flushed (256 MB write) before every call, "
+                      f"median of {n_passes} passes; family = all calls of one kernel entry point; achieved = sum of algorithmic bytes (or FLOPs) / sum of durations"}
+    roof["top_kernels"] = [{"family": f["family"], "ms": round(f["ms"], 4), "calls": f["calls"], "share_of_step": round(f["share_of_step"], 4), "bound": f["bound"],
+                            "achieved": round(f["achieved"], 1), "unit": f["unit"], "frac": round(f["frac"], 4)} for f in ranked[:8]]
+    roof["profiled_step_ms"] = total_ms
+    return roof
+
+
+def measure_fp32_frames(args, dev, world, rank, rw, rgbd, hw, barrier, steps=20, warmup=4):
+    """The same step with the reference batch contract (fp32 NCHW frames, transforms already applied) in the batch."""
+    import torch.distributed as dist
+
+    from hulc2_b200._compat import instantiate
+    from hulc2_b200.config import hulc2_config
+    from hulc2_b200.synthetic import synthetic_batch_fast
+    from hulc2_b200.trainer import PolicyTrainer
+
+    torch.manual_seed(0)
+    model = instantiate(hulc2_config(dropout_p=0.1, variant="real_world" if rw else "calvin", static_hw=hw, depth_static=rgbd)).to(dev).train()
+    trainer = PolicyTrainer(model, use_graph=not args.no_graph)
+    batch = synthetic_batch_fast(args.batch, seed=1 + rank, device=dev, frames="fp32", static_hw=hw, depth_static=rgbd)
+    for i in range(warmup):
+        trainer.train_step(batch, i)
+    if trainer.static_batch is not None:
+        batch = trainer.static_batch
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        trainer.train_step(batch, i)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    del trainer, model, batch
+    torch.cuda.empty_cache()
+    return {"value": 2 * args.batch * world / (float(ms) * 1e-3), "unit": "windows/s", "ms_per_step": float(ms), "steps": steps, "warmup": warmup,
+            "frames": "fp32 NCHW frames in [-1,1] in the batch (reference batch contract), inputs resident in HBM"}
+
+
 def run_b200(args):
     import torch.distributed as dist
 
@@ -206,9 +332,7 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        wps, dt, cores = time_cpu(args.cpu_batch, 2, 1)
-        cpu = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
-               "sample": f"oracle port, fp32, {{vis:{args.cpu_batch}, lang:{args.cpu_batch}}} windows/step, 1 warm-up + 2 timed steps ({dt:.2f} s/step)"}
+        cpu = cpu_baseline(args, args.cpu_batch or 8, 5, 3, True)      # 3 warm-up + 5 timed steps
 
     torch.manual_seed(0)
     rw, rgbd = args.variant != "calvin", args.variant == "real_world_rgbd"
@@ -225,6 +349,10 @@ def run_b200(args):
 
     for i in range(args.warmup):
         trainer.train_step(batch, i)
+    if trainer.static_batch is not None:
+        # the captured graph reads the trainer's own static input buffers (a clone of `batch` made at capture): time the step
+        # on inputs resident THERE, as a device-side producer (datamodule) would fill them -- no per-step device-to-device copy
+        batch = trainer.static_batch
     barrier()
     l0 = _lib.load_library().hulc2_launch_count()
     r0 = trainer.replays
@@ -266,54 +394,40 @@ def run_b200(args):
     torch.cuda.synchronize()
     e2e_blocking = 2 * B * world / ((time.perf_counter() - t0) / 2)
 
-    # roofline of the dominant kernel: per-call CUDA-event timing over one extra step (outside the timed region)
+    # secondary number on the reference batch contract: fp32 NCHW frames in the batch instead of uint8 (+ on-device transform)
+    value_fp32 = None
+    if args.frames == "uint8" and not args.no_fp32_frames:
+        value_fp32 = measure_fp32_frames(args, dev, world, rank, rw, rgbd, hw, barrier)
+
+    # roofline: per-call CUDA-event timing of the same step driven eagerly behind the timed region.  Every profiled call is
+    # preceded by a write of a buffer larger than L2 (cold cache as under ncu, and the GPU stays behind the host so no launch
+    # latency lands inside an event pair); median per call over `--profile-passes` passes; kernels grouped into families.
     roof = None
-    # every rank runs the step (it contains the gradient all-reduce); only rank 0 records the per-call events
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)          # 256 MB > 126 MB L2
+    passes = []
+    for _ in range(max(args.profile_passes, 1)):
+        # every rank runs the step (it contains the gradient all-reduce); only rank 0 records the per-call events
+        if rank == 0:
+            _lib.profile_begin(flush)
+        trainer.eager_step(batch, 0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            passes.append(_lib.profile_end())
+    del flush
     if rank == 0:
-        _lib.profile_begin()
-    trainer.eager_step(batch, 0)           # eager pass of the same step (per-call events cannot be taken inside a graph replay)
-    torch.cuda.synchronize()
-    if rank == 0:
-        recs = _lib.profile_end()
-        peaks = load_peaks()
+        recs = median_profile(passes)
         if args.dump_profile:
             with open(args.dump_profile, "w") as f:
                 json.dump(sorted(recs.values(), key=lambda r: -r["ms"]), f, indent=1)
-        top = max(recs.values(), key=lambda r: r["ms"]) if recs else None
-        total_ms = sum(r["ms"] for r in recs.values())
-        if top:
-            sec = top["ms"] / top["calls"] * 1e-3
-            tflops = (top["flops"] / top["calls"]) / sec / 1e12 if top["flops"] else 0.0
-            gbs = (top.get("bytes", 0.0) / top["calls"]) / sec / 1e9
-            # which roof bounds this kernel: algorithmic FLOP/byte against the machine's ridge point (measured peaks)
-            ridge = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
-            intensity = top["flops"] / top["bytes"] if top.get("bytes") else float("inf")
-            if intensity < ridge:
-                roof = {"bound": "hbm", "kernel": top["key"], "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": gbs / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC_BYTES.get(top["key"]),
-                        "algorithmic_bytes_per_launch": top["bytes"] / top["calls"], "flop_per_byte": intensity,
-                        "ridge_flop_per_byte": ridge, "tflops": tflops}
-            else:
-                roof = {"bound": "tensor", "kernel": top["key"], "achieved": tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                        "frac": tflops / peaks["tflops"], "traffic": None}
-            roof.update({"peak_source": peaks["src"], "share_of_step": top["ms"] / total_ms if total_ms else None,
-                         "calls_per_step": top["calls"], "avg_ms": top["ms"] / top["calls"],
-                         "step_tflops": 2 * B * FLOPS_PER_WINDOW_FWD_BWD / (ms * 1e-3) / 1e12})
-            tops = sorted(recs.values(), key=lambda r: -r["ms"])[:8]
-            roof["top_kernels"] = [{"key": r["key"], "ms": round(r["ms"], 3), "calls": r["calls"]} for r in tops]
+        roof = roofline_from_profile(recs, load_peaks(), 2 * B * FLOPS_PER_WINDOW_FWD_BWD / (ms * 1e-3) / 1e12, len(passes))
 
     if rank == 0:
         line = {
             "metric": "train windows/sec", "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-            "config": {"workload": (f"configs[1]: Hulc2 policy train step (fwd+bwd+allreduce+Adam), B={B}/modality/GPU, window 32, static 200x200 + gripper 84x84 RGB, 7-dof, lang [B,384], dropout 0.1"
-                                    if not rw else
-                                    f"configs[3]: cfg_low_level_rw-shaped Hulc2 train step, B={B}/modality/GPU, window 32, static 150x200 RGB{' + depth_static' if rgbd else ''} + gripper 84x84, 7-dof, no clip loss, dropout 0.1"),
-                       "frames": ("uint8 HWC frames + per-frame RandomShiftsAug draw in the batch; scale/normalise/shift run on the device inside the step (fused into the trunk's pack kernel)"
-                                  if args.frames == "uint8" else "fp32 NCHW frames in [-1,1] (reference batch contract; transforms already applied)"),
-                       "windows_per_step_per_gpu": 2 * B, "parallelism": f"dp{world}", "l2": f"inputs ({h2d / 1e9:.2f} GB of frames/step) exceed the 126 MB L2",
-                       "precision": args.precision, "cuda_graph": bool(trainer._graph is not None)},
+            "config": bench_config(args, world, cuda_graph=trainer._graph is not None),
+            "value_fp32_frames": value_fp32,
             "clocks": clk.summary(), "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
             "e2e": {"value": e2e_val, "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "steps": e2e_steps,
                     "api": f"PolicyTrainer.fit_host(pinned host batches, frames {args.frames}): H2D of step i+1 overlapped with step i",
@@ -412,6 +526,18 @@ def run_rollout(args):
         cycle(host, goal_h, True)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / max(args.e2e_steps // 2, 2)
+    # roofline of the dominant kernel family over one re-plan + one plain control step, driven eagerly with per-call events
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    eager = RolloutServer(model, use_graph=False)
+    passes = []
+    for _ in range(max(args.profile_passes, 1)):
+        eager.reset()
+        _lib.profile_begin(flush)
+        eager.step(devobs[0], goal_d)
+        eager.step(devobs[1], goal_d)
+        torch.cuda.synchronize()
+        passes.append(_lib.profile_end())
+    roof = roofline_from_profile(median_profile(passes), load_peaks(), None, len(passes))
     line = {
         "metric": "rollout env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -425,7 +551,132 @@ def run_rollout(args):
         "e2e": {"value": N * CYCLE / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d * CYCLE),
                 "d2h_bytes_per_step": N * 7 * 4 * CYCLE, "api": "RolloutServer.step(pinned host obs) + action read-back, every control step",
                 "ms_per_control_step": e2e_ms / CYCLE},
-        "roofline": None, "cpu_baseline": cpu,
+        "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- validation_step
+def cpu_validation_factory(B):
+    """Oracle port of Hulc2.validation_step (hulc2.py:510-598): per modality encoders + goal + lmp_val, no_grad."""
+    from hulc2_b200._compat import instantiate
+    from hulc2_b200.config import hulc2_config
+    from hulc2_b200.synthetic import synthetic_batch
+    from oracle import hulc2_oracle as O
+
+    torch.manual_seed(0)
+    m = instantiate(hulc2_config(dropout_p=0.0))
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    cfg = hulc2_config(pkg="x", dropout_p=0.0)
+    batch = synthetic_batch(B, seed=1)
+    g = torch.Generator().manual_seed(3)
+
+    def step():
+        with torch.no_grad():
+            for mod, db in batch.items():
+                nz = {"plan_idx_pp": torch.randint(0, 32, (B, 32), generator=g), "plan_idx_pr": torch.randint(0, 32, (B, 32), generator=g),
+                      "u1_pp": torch.rand(B, WINDOW, 6, 10, generator=g), "u2_pp": torch.rand(B, WINDOW, 6, generator=g),
+                      "u1_pr": torch.rand(B, WINDOW, 6, 10, generator=g), "u2_pr": torch.rand(B, WINDOW, 6, generator=g)}
+                emb = O.perceptual_encoder(db["rgb_obs"], db["depth_obs"], P)
+                goal = O.language_goal(db["lang"], P) if "lang" in mod else O.visual_goal(emb[:, -1], P)
+                out = O.lmp_val(emb, goal, db["actions"], db["state_info"]["robot_obs"], nz, P, cfg)
+                if "lang" in mod:
+                    O.clip_loss(out[-1], goal, db["use_for_aux_lang_loss"], P)
+        return float(out[1])
+
+    return step
+
+
+def run_validation(args):
+    """`validation_step` on {vis: B, lang: B} windows of the configs[1] shape through PolicyValidator (one captured graph):
+    a separate metric (validation windows/sec), never the default bench line."""
+    from hulc2_b200 import _lib, ops
+    from hulc2_b200._compat import instantiate
+    from hulc2_b200.config import hulc2_config
+    from hulc2_b200.synthetic import synthetic_batch_fast, tree_map
+    from hulc2_b200.trainer import PolicyValidator, _zip_copy
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    ops.set_precision(args.precision)
+    B = args.batch
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        Bc = args.cpu_batch or 8
+        step = cpu_validation_factory(Bc)
+        for _ in range(2):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            step()
+        dt = (time.perf_counter() - t0) / 5
+        cpu = {"value": 2 * Bc / dt, "unit": "windows/s", "cores": cores, "kind": "port",
+               "sample": f"oracle port of Hulc2.validation_step, fp32, no_grad, {{vis:{Bc}, lang:{Bc}}} windows/step, 2 warm-up + 5 timed steps ({dt:.2f} s/step)"}
+    torch.manual_seed(0)
+    model = instantiate(hulc2_config(dropout_p=0.1)).to(dev).eval()
+    val = PolicyValidator(model, use_graph=not args.no_graph)
+    batch = synthetic_batch_fast(B, seed=1, device=dev, frames=args.frames)
+    h2d = nbytes(batch)
+    for i in range(max(args.warmup, 3)):
+        val.validate(batch, i)
+    if val.static_batch is not None:
+        batch = val.static_batch
+    torch.cuda.synchronize()
+    l0, r0 = _lib.load_library().hulc2_launch_count(), val.replays
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev.index) as clk:
+        e0.record()
+        for i in range(args.steps):
+            out, logged = val.validate(batch, i)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = _lib.load_library().hulc2_launch_count() - l0 + (val.replays - r0) * val.launches_per_replay
+    # end to end: pinned host batch -> static device batch -> replay -> one logged scalar read back, every step
+    host = [tree_map(lambda t: t.cpu().pin_memory(), batch) for _ in range(2)]
+    key = "val_act/action_loss_pp"
+
+    def e2e_step(i):
+        with torch.cuda.stream(val.stream):
+            _zip_copy(val.static_batch if val.static_batch is not None else batch, host[i % 2])
+        _, lg = val.validate(val.static_batch if val.static_batch is not None else batch, i)
+        return float(lg[key])
+
+    e2e_step(0)
+    torch.cuda.synchronize()
+    n_e2e = max(args.e2e_steps, 2)
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+    # roofline of the dominant kernel family: eager validation passes with per-call events (see run_b200)
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    eager = PolicyValidator(model, use_graph=False)
+    passes = []
+    for _ in range(max(args.profile_passes, 1)):
+        _lib.profile_begin(flush)
+        eager.validate(batch, 0)
+        torch.cuda.synchronize()
+        passes.append(_lib.profile_end())
+    roof = roofline_from_profile(median_profile(passes), load_peaks(), None, len(passes))
+    line = {
+        "metric": "validation windows/sec", "value": 2 * B / (ms * 1e-3), "unit": "windows/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"Hulc2.validation_step (lmp_val: proposal + recognition plans, two decoder passes with action sampling, KL, MAE / gripper metrics), "
+                               f"configs[1] shape, B={B}/modality, window 32, static 200x200 + gripper 84x84",
+                   "frames": args.frames, "precision": args.precision, "cuda_graph": bool(val._graph is not None),
+                   "l2": f"inputs ({h2d / 1e9:.2f} GB of frames/step) exceed the 126 MB L2"},
+        "clocks": clk.summary(), "gpu_launches": int(launches),
+        "e2e": {"value": 2 * B / (e2e_ms * 1e-3), "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "steps": n_e2e,
+                "api": "PolicyValidator.validate(pinned host batch) + read-back of val_act/action_loss_pp, blocking per step"},
+        "roofline": roof, "cpu_baseline": cpu,
+        "logged": {k: float(v) for k, v in logged.items()},
     }
     print(json.dumps(line), flush=True)
 
@@ -436,5 +687,7 @@ if __name__ == "__main__":
         run_reference(a)
     elif a.workload == "rollout":
         run_rollout(a)
+    elif a.workload == "validation":
+        run_validation(a)
     else:
         run_b200(a)

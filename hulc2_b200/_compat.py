@@ -127,9 +127,27 @@ except ImportError:
             self.logged[name] = value
 
         def save_hyperparameters(self, *a, **kw):
-            pass
+            """Records the constructor arguments of the calling ``__init__`` in ``self.hparams`` (what Lightning stores under
+            the checkpoint key ``hyper_parameters`` and feeds back to ``cls(**hparams)`` in ``load_from_checkpoint``)."""
+            import inspect
+
+            frame = inspect.currentframe().f_back
+            try:
+                while frame is not None and frame.f_code.co_name != "__init__":
+                    frame = frame.f_back
+                if frame is None:
+                    return
+                info = inspect.getargvalues(frame)
+                self.hparams = {k: info.locals[k] for k in info.args if k not in ("self", "__class__")}
+            finally:
+                del frame
 
         def freeze(self):
             for p in self.parameters():
                 p.requires_grad = False
             self.eval()
+
+        def unfreeze(self):
+            for p in self.parameters():
+                p.requires_grad = True
+            self.train()

@@ -280,6 +280,43 @@ __global__ void frame_kernel(const float* __restrict__ action, const float* __re
   }
 }
 
+// --------------------------------------------------------------------------- validation metrics (hulc2.py:292-302, 559-575)
+// One CTA per call (a modality's B windows): thread per (b, dim) takes the mean over the window like torch.mean(l1, 1), then
+// block sums give total / position / orientation MAE (means over [B,6] / [B,3] / [B,3]) and the discrete-gripper success rate
+// mean(gt == (pred > 0 ? 1 : -1)) over [B,S].  out[4] = {total_mae, pos_mae, orn_mae, grip_sr}.  pred / gt [B,S,A+1].
+__global__ void val_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt, float* __restrict__ out, int B, int S, int A) {
+  __shared__ float red[32];
+  const int A1 = A + 1;
+  float tot = 0.f, pos = 0.f, orn = 0.f, hit = 0.f;
+  for (int i = threadIdx.x; i < B * A; i += blockDim.x) {
+    const int b = i / A, d = i - b * A;
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const long long o = ((long long)b * S + s) * A1 + d;
+      acc += fabsf(pred[o] - gt[o]);
+    }
+    acc /= (float)S;
+    tot += acc;
+    if (d < 3) pos += acc;
+    else if (d < 6) orn += acc;
+  }
+  for (int i = threadIdx.x; i < B * S; i += blockDim.x) {
+    const long long o = (long long)i * A1 + A;
+    const float g = pred[o] > 0.f ? 1.f : -1.f;
+    hit += (gt[o] == g) ? 1.f : 0.f;
+  }
+  tot = block_sum(tot, red);
+  pos = block_sum(pos, red);
+  orn = block_sum(orn, red);
+  hit = block_sum(hit, red);
+  if (threadIdx.x == 0) {
+    out[0] = tot / (float)(B * A);
+    out[1] = pos / (float)(B * 3);
+    out[2] = orn / (float)(B * (A >= 6 ? 3 : (A > 3 ? A - 3 : 1)));
+    out[3] = hit / (float)(B * S);
+  }
+}
+
 inline int grid_for(long long n, int block) {
   long long want = (n + block - 1) / block;
   long long cap = 148LL * 4;
@@ -351,6 +388,14 @@ int hulc2_heads_unpack(const float* heads, long long ld, float* logit_probs, flo
   if ((long long)B * S <= 0) return HULC2_OK;
   HeadGeom g{B, S, A, M, ld, time_major, B};
   heads_unpack_kernel<<<grid_for((long long)B * S * (A * M + 2), 256), 256, 0, st>>>(heads, g, logit_probs, log_scales, means, gripper, log_scale_min);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+int hulc2_val_metrics(const float* pred, const float* actions, float* out, int B, int S, int A, cudaStream_t st) {
+  if (B <= 0 || S <= 0) return HULC2_OK;
+  if (A < 3) { hulc2_set_error("val_metrics: needs at least 3 continuous action dims"); return HULC2_EINVAL; }
+  val_metrics_kernel<<<1, 256, 0, st>>>(pred, actions, out, B, S, A);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

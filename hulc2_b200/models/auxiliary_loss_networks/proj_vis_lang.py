@@ -21,8 +21,8 @@ class ProjVisLang(nn.Module):
 
     def forward(self, vis_emb: torch.Tensor, lang_emb: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         m = self.mlp_im
-        vis_emb = ops.mlp(vis_emb, [(m[0].weight, m[0].bias), (m[2].weight, m[2].bias)], [True, False])
+        vis_emb = ops.mlp(vis_emb, [(m[0].weight, m[0].bias), (m[2].weight, m[2].bias)], [True, False], fp32=ops.clip_fp32)
         if self.mlp_lang is not None:
             m = self.mlp_lang
-            lang_emb = ops.mlp(lang_emb, [(m[0].weight, m[0].bias), (m[2].weight, m[2].bias)], [True, False])
+            lang_emb = ops.mlp(lang_emb, [(m[0].weight, m[0].bias), (m[2].weight, m[2].bias)], [True, False], fp32=ops.clip_fp32)
         return vis_emb, lang_emb

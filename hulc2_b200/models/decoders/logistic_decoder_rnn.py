@@ -128,6 +128,24 @@ class LogisticDecoderRNN(ActionDecoder):
             return loss, tcp_to_world_frame(pred_actions, robot_obs)
         return self._fused_loss(Hs, actions), pred_actions
 
+    def loss_and_act_modalities(self, latent_plan, perceptual_emb, latent_goal, actions: Sequence[torch.Tensor],
+                                robot_obs: Sequence[torch.Tensor]) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+        """``loss_and_act`` for windows of several modalities decoded by ONE recurrence call (validation, hulc2.py:268-291):
+        returns the vector of per-modality mean losses and the per-modality sampled actions (world frame when
+        ``gripper_control``), each exactly what ``loss_and_act`` returns for that modality."""
+        B, S = perceptual_emb.shape[:2]
+        Hs, _ = self._run_rnn(latent_plan, perceptual_emb, latent_goal)
+        with torch.no_grad():
+            heads = ops.heads_forward(Hs.detach(), *self._head_params())
+            pred = self._fused_sample(heads, B, S, True)
+        sizes = [a.shape[0] for a in actions]
+        offs = [sum(sizes[:i]) for i in range(len(sizes))]
+        preds = [pred[o : o + n] for o, n in zip(offs, sizes)]
+        if self.gripper_control:
+            losses = self._fused_loss(Hs, tuple(world_to_tcp_frame(a, r) for a, r in zip(actions, robot_obs)))
+            return losses, [tcp_to_world_frame(p, r) for p, r in zip(preds, robot_obs)]
+        return self._fused_loss(Hs, tuple(actions)), preds
+
     def act(self, latent_plan, perceptual_emb, latent_goal, robot_obs) -> torch.Tensor:
         B, S = perceptual_emb.shape[:2]
         with torch.no_grad():

@@ -86,6 +86,37 @@ class Hulc2(LightningModule):
         self.latent_goal = None
         self.plan = None
 
+    # ------------------------------------------------------------------ checkpoints
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, hparams_file=None, strict: bool = True, **kwargs):
+        """``LightningModule.load_from_checkpoint`` for Lightning-format checkpoints written by the REFERENCE model or by this
+        mirror (``{"state_dict", "hyper_parameters", ...}``): the saved constructor arguments are re-used (keyword arguments
+        override them, e.g. ``perceptual_encoder=...`` in evaluation/manager_lmp.py:91-103), ``_target_`` strings of the
+        reference's model modules are pointed at this package's mirror classes, and the ``state_dict`` -- whose names and
+        shapes are the reference's -- is loaded into them.  Weights of a frozen language encoder stored in the checkpoint
+        (``lang_encoder.*``, absent here with ``language_encoder=none``) are skipped."""
+        from ..utils.checkpoint import read_checkpoint, retarget
+
+        ckpt = read_checkpoint(checkpoint_path, map_location)
+        hp = dict(ckpt.get("hyper_parameters") or {})
+        hp.update(kwargs)
+        hp = {k: retarget(v) for k, v in hp.items() if k not in ("_target_", "_recursive_")}
+        model = cls(**hp)
+        sd = {k: v for k, v in ckpt["state_dict"].items() if model.lang_encoder is not None or not k.startswith("lang_encoder.")}
+        model.load_state_dict(sd, strict=strict)
+        for k in ("epoch", "global_step"):
+            if k in ckpt:
+                try:
+                    setattr(model, "current_epoch" if k == "epoch" else k, int(ckpt[k]))
+                except AttributeError:           # read-only properties under real Lightning
+                    pass
+        return model
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        ops.invalidate_weight_mirrors()          # bf16 operand mirrors of the old weights are stale
+        return out
+
     # ------------------------------------------------------------------ setup
     @staticmethod
     def setup_input_sizes(perceptual_encoder, plan_proposal, plan_recognition, visual_goal, action_decoder, distribution):
@@ -318,9 +349,68 @@ class Hulc2(LightningModule):
         self.log("train/total_loss", total_loss.detach(), on_step=False, on_epoch=True, batch_size=total_bs)
         return total_loss
 
+    def _validation_step_batched(self, batch: Dict[str, Dict]) -> Dict[str, torch.Tensor]:
+        """hulc2.py:510-598 with lmp_val (:247-334) inlined, all modalities as ONE batch (as ``_training_step_batched``): one
+        encoder pass, one plan-proposal / plan-recognition pass, two decoder passes (proposal plan, recognition plan), segment
+        losses, and the MAE / gripper-success reductions of every modality in one kernel each.  Same logged names and values
+        as the modality loop in ``validation_step``; no host synchronisation, so the whole step can be captured in a graph."""
+        names = list(batch.keys())
+        mods = [batch[n] for n in names]
+        n_mod = len(mods)
+        n_log = len(getattr(getattr(self.trainer, "datamodule", None), "modalities", None) or batch)
+        sizes = [m["actions"].shape[0] for m in mods]
+        offs = [sum(sizes[:i]) for i in range(n_mod)]
+        noise.fuse_supplied(n_mod)
+        emb = self.perceptual_encoder.forward_modalities([m["rgb_obs"] for m in mods], [m["depth_obs"] for m in mods], None)
+        goals = []
+        for name, m, o, n in zip(names, mods, offs, sizes):
+            self.modality_scope = name
+            goals.append(self.language_goal(m["lang"]) if "lang" in name else self.visual_goal(emb[o : o + n, -1]))
+        latent_goal = ops.concat_rows(goals)
+        actions = [m["actions"] for m in mods]
+        robot = [m["state_info"]["robot_obs"] for m in mods]
+        # draw order of lmp_val: proposal plan, its action sample, recognition plan, its action sample
+        pp_state = self.plan_proposal(emb[:, 0], latent_goal)
+        plan_pp = self.dist.sample_latent_plan(self.dist.get_dist(pp_state))
+        loss_pp, acts_pp = self.action_decoder.loss_and_act_modalities(plan_pp, emb, latent_goal, actions, robot)
+        pr_state, seq_feat = self.plan_recognition(emb)
+        plan_pr = self.dist.sample_latent_plan(self.dist.get_dist(pr_state))
+        loss_pr, acts_pr = self.action_decoder.loss_and_act_modalities(plan_pr, emb, latent_goal, actions, robot)
+        if self.dist.dist == "discrete":
+            kl = ops.KLFunction.apply(pp_state.logit, pr_state.logit, self.dist.category_size, self.dist.class_size,
+                                      float(self.kl_balancing_mix), float(self.kl_beta), tuple(sizes))
+        else:
+            kl = ops.GaussKLFunction.apply(pp_state.mean, pp_state.std, pr_state.mean, pr_state.std,
+                                           float(self.kl_balancing_mix), float(self.kl_beta), tuple(sizes))
+        output, act_pp = {}, []
+        for i, (m, d, o, n) in enumerate(zip(names, mods, offs, sizes)):
+            self.modality_scope = m
+            met_pp, met_pr = ops.val_metrics(acts_pp[i], d["actions"]), ops.val_metrics(acts_pr[i], d["actions"])
+            if "lang" in m and self.use_clip_auxiliary_loss:
+                self.log("val/val_pred_clip_loss", self.clip_auxiliary_loss(seq_feat[o : o + n], goals[i], d.get("use_for_aux_lang_loss")), sync_dist=True)
+            act_pp.append(loss_pp[i])
+            self.log(f"val_total_mae/{m}_total_mae_pr", met_pr[0], sync_dist=True)
+            self.log(f"val_total_mae/{m}_total_mae_pp", met_pp[0], sync_dist=True)
+            self.log(f"val_pos_mae/{m}_pos_mae_pr", met_pr[1], sync_dist=True)
+            self.log(f"val_pos_mae/{m}_pos_mae_pp", met_pp[1], sync_dist=True)
+            self.log(f"val_orn_mae/{m}_orn_mae_pr", met_pr[2], sync_dist=True)
+            self.log(f"val_orn_mae/{m}_orn_mae_pp", met_pp[2], sync_dist=True)
+            self.log(f"val_kl/{m}_kl_loss", kl[i], sync_dist=True)
+            self.log(f"val_act/{m}_act_loss_pp", loss_pp[i], sync_dist=True)
+            self.log(f"val_act/{m}_act_loss_pr", loss_pr[i], sync_dist=True)
+            self.log(f"val_grip/{m}_grip_sr_pr", met_pr[3], sync_dist=True)
+            self.log(f"val_grip/{m}_grip_sr_pp", met_pp[3], sync_dist=True)
+            self.log("val_act/action_loss_pp", ops.weighted_sum((1.0 / n_log,) * len(act_pp), [a.detach() for a in act_pp]), sync_dist=True)
+            output[f"sampled_plan_pp_{m}"] = plan_pp[o : o + n]
+            output[f"sampled_plan_pr_{m}"] = plan_pr[o : o + n]
+            output[f"idx_{m}"] = d["idx"]
+        return output
+
     def validation_step(self, batch: Dict[str, Dict], batch_idx: int) -> Dict[str, torch.Tensor]:  # type: ignore
-        """hulc2.py:510-598."""
+        """hulc2.py:510-598.  Modalities with the same cameras run as ONE batch (``_validation_step_batched``)."""
         ops.invalidate_weight_mirrors()
+        if self.batch_modalities and self._can_batch_modalities(batch) and hasattr(self.action_decoder, "loss_and_act_modalities"):
+            return self._validation_step_batched(batch)
         output = {}
         act_pp = []
         n_mod = len(getattr(getattr(self.trainer, "datamodule", None), "modalities", None) or batch)

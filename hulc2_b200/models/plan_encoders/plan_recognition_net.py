@@ -84,6 +84,6 @@ class PlanRecognitionTransformersNetwork(nn.Module):
             x = ops.layer_norm(x, layer.norm2.weight, layer.norm2.bias, res=ff, keep=self._keep((B * S, E), dev),
                                keep_scale=scale, eps=layer.norm2.eps)
         xm = ops.MeanSeqFunction.apply(x.view(B, S, E))
-        seq_feat = ops.linear(xm, self.fc.weight, self.fc.bias)
+        seq_feat = ops.linear(xm, self.fc.weight, self.fc.bias, fp32=ops.clip_fp32 and ops.clip_fp32_level >= 2)
         my_state = ops.linear(seq_feat, self.fc_state[0].weight, self.fc_state[0].bias)
         return self.dist.forward_dist(my_state), seq_feat

@@ -70,9 +70,9 @@ def supplied(categories=(), uniforms=(), masks=(), normals=()):
 
 def fuse_supplied(n: int) -> None:
     """A step that runs the windows of ``n`` modalities as one batch consumes one draw where the per-modality loop
-    consumed ``n``.  Supplied category/mask tensors are queued per modality (modality 0's draws, then modality 1's, ...):
+    consumed ``n``.  Supplied category/mask/uniform tensors are queued per modality (modality 0's draws, then modality 1's, ...):
     regroup them into batch-concatenated tensors in draw order."""
-    for key in ("categories", "masks", "normals"):
+    for key in ("categories", "masks", "normals", "uniforms"):
         q = _queues[key]
         if not q:
             continue

@@ -98,7 +98,7 @@ def gemm(M, N, K, A, a_rs, a_ks, B, b_rs, b_ks, Cout, ldc, *, a_off=0, b_off=0, 
         g.B16 = None if B16 is None else B16.data_ptr() + 2 * b_off
         g.C16 = None if C16 is None else C16.data_ptr() + 2 * c16_off
         g.ld16 = ld16
-    _lib.tag(f"gemm[M={int(M)},N={int(N)},K={int(K)}]", 2.0 * M * N * K)
+    _lib.tag(f"gemm[M={int(M)},N={int(N)},K={int(K)}]", 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N))
     call("hulc2_gemm", C.byref(g))
 
 
@@ -225,7 +225,8 @@ def gemm16(M, N, K, A16, a_rs, a_ks, B16, b_rs, b_ks, Cout, ldc, *, a_off=0, b_o
     g.precision = 1
     g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
     g.C16, g.ld16 = _p(C16), ld16
-    _lib.tag(f"gemm16[M={int(M)},N={int(N)},K={int(K)}]", 2.0 * M * N * K)
+    _lib.tag(f"gemm16[M={int(M)},N={int(N)},K={int(K)}]", 2.0 * M * N * K,
+             2.0 * (M * K + N * K) + M * N * (4.0 + (2.0 if C16 is not None else 0.0) + (4.0 if accumulate or add is not None else 0.0)))
     call("hulc2_gemm", C.byref(g))
 
 
@@ -252,7 +253,8 @@ class MLPFunction(torch.autograd.Function):
         x2 = _rows2d(_f32(x))
         M = x2.shape[0]
         n = len(wb) // 2
-        ctx.b16 = _precision == 1 and M > 0 and all(wb[2 * i].shape[1] % 8 == 0 for i in range(n))
+        fp32_only = isinstance(relus, _Fp32Flags)      # see mlp(..., fp32=True)
+        ctx.b16 = _precision == 1 and not fp32_only and M > 0 and all(wb[2 * i].shape[1] % 8 == 0 for i in range(n))
         if ctx.b16:
             # bf16 operand mirrors: every layer's epilogue also emits the bf16 copy the next layer (and the weight
             # gradient) multiplies; the fp32 activations stay for the ReLU masks and non-GEMM consumers
@@ -281,9 +283,11 @@ class MLPFunction(torch.autograd.Function):
             N, K = W.shape
             y = torch.empty(M, N, device=x.device, dtype=torch.float32)
             if M > 0:
-                gemm(M, N, K, cur, ld, 1, W, K, 1, y, N, bias=b, relu=relus[i], keep=keeps[i], ld_keep=N, keep_scale=keep_scale)
+                gemm(M, N, K, cur, ld, 1, W, K, 1, y, N, bias=b, relu=relus[i], keep=keeps[i], ld_keep=N, keep_scale=keep_scale,
+                     precision=0 if fp32_only else None)
             acts.append(y)
             cur, ld = y, N
+        ctx.fp32_only = fp32_only
         ctx.relus, ctx.keeps, ctx.keep_scale, ctx.n = relus, keeps, keep_scale, n
         ctx.x_shape = x.shape
         ctx.save_for_backward(x2, *acts, *wb)
@@ -331,6 +335,7 @@ class MLPFunction(torch.autograd.Function):
                     if i == 0:
                         dx = gi.view(ctx.x_shape)
             return (dx, None, None, None, *grads)
+        prec = 0 if ctx.fp32_only else None
         for i in range(n - 1, -1, -1):
             W = wb[2 * i]
             N, K = W.shape
@@ -338,7 +343,7 @@ class MLPFunction(torch.autograd.Function):
             ld_in = _ld(x2) if i == 0 else K
             if ctx.needs_input_grad[4 + 2 * i]:
                 dW = grad_buffer(W)
-                gemm(N, K, M, g, 1, N, inp, 1, ld_in, dW, K)           # dW = g^T inp
+                gemm(N, K, M, g, 1, N, inp, 1, ld_in, dW, K, precision=prec)           # dW = g^T inp
                 grads[2 * i] = dW
             if ctx.needs_input_grad[5 + 2 * i]:
                 db = grad_buffer(wb[2 * i + 1])
@@ -349,23 +354,39 @@ class MLPFunction(torch.autograd.Function):
                 if M > 0:
                     if i > 0:
                         gemm(M, K, N, g, N, 1, W, 1, K, gi, K, mask=acts[i - 1] if ctx.relus[i - 1] else None, ld_mask=K,
-                             keep=ctx.keeps[i - 1], ld_keep=K, keep_scale=ctx.keep_scale)
+                             keep=ctx.keeps[i - 1], ld_keep=K, keep_scale=ctx.keep_scale, precision=prec)
                     else:
-                        gemm(M, K, N, g, N, 1, W, 1, K, gi, K)
+                        gemm(M, K, N, g, N, 1, W, 1, K, gi, K, precision=prec)
                 g = gi
                 if i == 0:
                     dx = gi.view(ctx.x_shape)
         return (dx, None, None, None, *grads)
 
 
-def mlp(x, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], relus: Sequence[bool], keeps=None, keep_scale=1.0):
+class _Fp32Flags(tuple):
+    """ReLU flags of an MLP stack that must run on the fp32 CUDA-core GEMM even under precision 'bf16'."""
+
+
+# Under precision 'bf16' the visuo-lingual contrastive path (hulc2.py:472-508) -- plan_recognition.fc (128 -> 4096, M = B rows),
+# ProjVisLang (4096 -> 128 -> 32, 32 -> 128 -> 32) -- runs on the fp32 GEMM: InfoNCE only sees the DIFFERENCE between the rows
+# of a batch whose common mode is ~100x larger, so bf16 operand rounding (2^-9 of the common mode) reaches 4-6 % of every
+# gradient that flows back through it (measured at B = 64: static-encoder tail 5.7 % off, cosine 0.994; with these ~400 MFLOP
+# of M <= 128 contractions in fp32: see profiles/parity_r02_bf16_oracle_B64.json).  HULC2_CLIP_FP32=0 restores bf16 (A/B switch).
+import os as _os
+
+clip_fp32 = _os.environ.get("HULC2_CLIP_FP32", "1") != "0"
+clip_fp32_level = int(_os.environ.get("HULC2_CLIP_FP32", "2") or 0)     # 1 = ProjVisLang only, 2 = + plan_recognition.fc
+
+
+def mlp(x, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], relus: Sequence[bool], keeps=None, keep_scale=1.0, fp32: bool = False):
     keeps = tuple(keeps) if keeps is not None else (None,) * len(layers)
     flat = [t for wb in layers for t in wb]
-    return MLPFunction.apply(x, tuple(bool(r) for r in relus), keeps, float(keep_scale), *flat)
+    flags = tuple(bool(r) for r in relus)
+    return MLPFunction.apply(x, _Fp32Flags(flags) if fp32 else flags, keeps, float(keep_scale), *flat)
 
 
-def linear(x, W, b, relu=False):
-    return mlp(x, [(W, b)], [relu])
+def linear(x, W, b, relu=False, fp32: bool = False):
+    return mlp(x, [(W, b)], [relu], fp32=fp32)
 
 
 # ----------------------------------------------------------------------------- conv trunks
@@ -573,14 +594,14 @@ class U8Frames:
         F_, C, H, W = self.shape
         out = torch.empty(F_, C, H, W, device=self.device, dtype=torch.float32)
         ptrs, dims = self._args()
-        _lib.tag(f"frames_u8_to_f32[F={F_},{C}x{H}x{W}]", 0.0)
+        _lib.tag(f"frames_u8_to_f32[F={F_},{C}x{H}x{W}]", 0.0, 5.0 * F_ * C * H * W)
         call("hulc2_frames_u8_to_f32", *ptrs, out.data_ptr(), *dims)
         return out
 
     def pack_into(self, xs_ptr: int) -> None:
         F_, C, H, W = self.shape
         ptrs, dims = self._args()
-        _lib.tag(f"frames_u8_pack[F={F_},{C}x{H}x{W}]", 0.0)
+        _lib.tag(f"frames_u8_pack[F={F_},{C}x{H}x{W}]", 0.0, 3.0 * F_ * C * H * W)            # 1 B in, 2 B out per pixel-channel
         call("hulc2_frames_u8_pack_bf16", *ptrs, xs_ptr, *dims)
 
 
@@ -612,7 +633,7 @@ def pack_frames(x) -> torch.Tensor:
         if isinstance(t, U8Frames):
             t.pack_into(xs.data_ptr() + 2 * f0 * per_frame)
         else:
-            _lib.tag(f"pack_frames[F={t.shape[0]},{Cin}x{H}x{W}]", 0.0)
+            _lib.tag(f"pack_frames[F={t.shape[0]},{Cin}x{H}x{W}]", 0.0, 6.0 * t.numel())
             call("hulc2_pack_frames_bf16", t.data_ptr(), xs.data_ptr() + 2 * f0 * per_frame, t.shape[0], Cin, H, W)
         f0 += t.shape[0]
     return xs
@@ -655,7 +676,7 @@ class StaticConvSSM(torch.autograd.Function):
         if ctx.bf16:
             xs, y1, y2, y3 = _convb_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
             HW = y3.shape[1] * y3.shape[2]
-            _lib.tag(f"spatial_softmax_fwd_bf16[F={F_},HW={HW}]", 0.0)
+            _lib.tag(f"spatial_softmax_fwd_bf16[F={F_},HW={HW}]", 0.0, 2.0 * y3.numel() + 4.0 * out.numel())
             call("hulc2_spatial_softmax_fwd_bf16", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
                  out.data_ptr(), F_, HW, 64)
             ctx.save_for_backward(xs, y1, y2, y3, w1, w2, w3, x_map, y_map, temperature)
@@ -676,7 +697,7 @@ class StaticConvSSM(torch.autograd.Function):
             HW = y3.shape[1] * y3.shape[2]
             dz3 = torch.empty_like(y3)
             dtemp = torch.zeros(1, device=xs.device, dtype=torch.float32) if ctx.needs_input_grad[9] else None
-            _lib.tag(f"spatial_softmax_bwd_bf16[F={F_},HW={HW}]", 0.0)
+            _lib.tag(f"spatial_softmax_bwd_bf16[F={F_},HW={HW}]", 0.0, 4.0 * y3.numel() + 4.0 * dout.numel())  # y3 in, dz3 out
             call("hulc2_spatial_softmax_bwd_bf16", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
                  dout.data_ptr(), dz3.data_ptr(), _p(dtemp), F_, HW, 64, 1)
             g = _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3)
@@ -805,6 +826,8 @@ class AttentionFunction(torch.autograd.Function):
         E = qkv.shape[-1] // 3
         out = torch.empty(B * S, E, device=qkv.device, dtype=torch.float32)
         probs = torch.empty(B, H, S, S, device=qkv.device, dtype=torch.float32)
+        _lib.tag(f"attention_fwd[B={B},S={S},H={H},dh={E // H}]", 4.0 * B * H * S * S * (E // H),
+                 4.0 * B * S * 4 * E + B * H * S * S * (4.0 + (1.0 if keep is not None else 0.0)))
         call("hulc2_attention_fwd", qkv.data_ptr(), _p(keep), keep_scale, out.data_ptr(), probs.data_ptr(), B, S, H, E // H)
         ctx.save_for_backward(qkv, probs)
         ctx.dims, ctx.keep, ctx.keep_scale = (B, S, H, E // H), keep, keep_scale
@@ -816,6 +839,8 @@ class AttentionFunction(torch.autograd.Function):
         B, S, H, Dh = ctx.dims
         dout = dout.contiguous()
         dqkv = torch.empty_like(qkv)
+        _lib.tag(f"attention_bwd[B={B},S={S},H={H},dh={Dh}]", 8.0 * B * H * S * S * Dh,
+                 4.0 * B * S * 7 * H * Dh + B * H * S * S * (4.0 + (1.0 if ctx.keep is not None else 0.0)))
         call("hulc2_attention_bwd", qkv.data_ptr(), probs.data_ptr(), _p(ctx.keep), ctx.keep_scale, dout.data_ptr(),
              dqkv.data_ptr(), B, S, H, Dh)
         return dqkv, None, None, None, None, None
@@ -855,6 +880,7 @@ class KLFunction(torch.autograd.Function):
         row = pp.shape[1] * 4
         b0 = 0
         for i, n in enumerate(segs):
+            _lib.tag(f"kl_fwd[B={n},{cats}x{classes}]", 0.0, 8.0 * n * cats * classes)          # 8 KB / window forward
             call("hulc2_kl_fwd", pp.data_ptr() + b0 * row, pr.data_ptr() + b0 * row, loss.data_ptr() + 4 * i, n, cats, classes, alpha, beta)
             b0 += n
         ctx.save_for_backward(pp, pr)
@@ -870,6 +896,7 @@ class KLFunction(torch.autograd.Function):
         row = pp.shape[1] * 4
         b0 = 0
         for i, n in enumerate(segs):
+            _lib.tag(f"kl_bwd[B={n},{cats}x{classes}]", 0.0, 16.0 * n * cats * classes)
             call("hulc2_kl_bwd", pp.data_ptr() + b0 * row, pr.data_ptr() + b0 * row, g.data_ptr() + 4 * i, dpp.data_ptr() + b0 * row,
                  dpr.data_ptr() + b0 * row, n, cats, classes, alpha, beta)
             b0 += n
@@ -1056,7 +1083,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         H0 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         h00 = h0[0].contiguous() if h0 is not None else None
         h01 = h0[1].contiguous() if h0 is not None else None
-        _lib.tag(f"rnn_relu_fwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
+        _lib.tag(f"rnn_relu_fwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H, S * (2.0 * H * H + 12.0 * B * H))
         call("hulc2_rnn_relu_fwd", pre.data_ptr(), wh0.data_ptr(), _p(h00), H0.data_ptr(), S, B, H, _lib_precision(), ws.data_ptr(), ws.numel())
         H0h = None
         if b16:
@@ -1065,7 +1092,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         else:
             gemm(S * B, H, H, H0, H, 1, wi1, H, 1, pre, H, bias=bsum1)
         H1 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
-        _lib.tag(f"rnn_relu_fwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
+        _lib.tag(f"rnn_relu_fwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H, S * (2.0 * H * H + 12.0 * B * H))
         call("hulc2_rnn_relu_fwd", pre.data_ptr(), wh1.data_ptr(), _p(h01), H1.data_ptr(), S, B, H, _lib_precision(), ws.data_ptr(), ws.numel())
         hn = torch.empty(2, B, H, device=dev, dtype=torch.float32)
         call("hulc2_copy2d", H0.data_ptr() + 4 * (S - 1) * B * H, B * H, hn.data_ptr(), B * H, 1, B * H, 0)
@@ -1092,7 +1119,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         dH1 = dH1.contiguous()
         dz1 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         call("hulc2_copy2d", dH1.data_ptr(), step, dz1.data_ptr(), step, S, step, 0)
-        _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
+        _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H, S * (2.0 * H * H + 16.0 * B * H))
         call("hulc2_rnn_relu_bwd", dz1.data_ptr(), wh1.data_ptr(), H1.data_ptr(), None, S, B, H, prec, ws.data_ptr(), ws.numel())
         dwh1 = grad_buffer(wh1)
         if S > 1:
@@ -1107,7 +1134,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         colsum(dz1, H, S * B, H, db1)
         dz0 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         gemm(S * B, H, H, dz1, H, 1, wi1, 1, H, dz0, H)                      # dH0 = dz1 W_ih1
-        _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
+        _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H, S * (2.0 * H * H + 16.0 * B * H))
         call("hulc2_rnn_relu_bwd", dz0.data_ptr(), wh0.data_ptr(), H0.data_ptr(), None, S, B, H, prec, ws.data_ptr(), ws.numel())
         dwh0 = grad_buffer(wh0)
         if S > 1:
@@ -1151,7 +1178,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         dH1 = dH1.contiguous()
         dz1 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         call("hulc2_copy2d", dH1.data_ptr(), step, dz1.data_ptr(), step, S, step, 0)
-        _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
+        _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H, S * (2.0 * H * H + 16.0 * B * H))
         call("hulc2_rnn_relu_bwd", dz1.data_ptr(), wh1.data_ptr(), H1.data_ptr(), None, S, B, H, 1, ws.data_ptr(), ws.numel())
         dz1h, H1h = to_bf16(dz1), to_bf16(H1)
         dwh1 = grad_buffer(wh1)
@@ -1167,7 +1194,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         colsum(dz1, H, S * B, H, db1)
         dz0 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         gemm16(S * B, H, H, dz1h, H, 1, wi1h, 1, H, dz0, H)                      # dH0 = dz1 W_ih1
-        _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H)
+        _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H, S * (2.0 * H * H + 16.0 * B * H))
         call("hulc2_rnn_relu_bwd", dz0.data_ptr(), wh0.data_ptr(), H0.data_ptr(), None, S, B, H, 1, ws.data_ptr(), ws.numel())
         dz0h = to_bf16(dz0)
         dwh0 = grad_buffer(wh0)
@@ -1248,7 +1275,7 @@ class GatedRNNDecoderFunction(torch.autograd.Function):
                     call("hulc2_copy2d", bh.data_ptr(), 0, gh.data_ptr(), GH, B, GH, 0)
                 else:
                     gemm(B, GH, H, hp, H, 1, wh, H, 1, gh, GH, bias=bh)
-                _lib.tag(f"{kind}_cell_fwd[B={B},H={H}]")
+                _lib.tag(f"{kind}_cell_fwd[B={B},H={H}]", 0.0, (48.0 if kind == "gru" else 60.0) * B * H)
                 if kind == "gru":
                     call("hulc2_gru_cell_fwd", gi[t].data_ptr(), GH, gh.data_ptr(), _p(hp), Hl[t].data_ptr(), sv[t].data_ptr(), B, H)
                 else:
@@ -1289,7 +1316,7 @@ class GatedRNNDecoderFunction(torch.autograd.Function):
             for t in range(S - 1, -1, -1):
                 hp = Hl[t - 1] if t > 0 else h0l
                 dhb = rec[(t + 1) & 1] if t < S - 1 else None
-                _lib.tag(f"{kind}_cell_bwd[B={B},H={H}]")
+                _lib.tag(f"{kind}_cell_bwd[B={B},H={H}]", 0.0, (52.0 if kind == "gru" else 56.0) * B * H)
                 if kind == "gru":
                     call("hulc2_gru_cell_bwd", dHs[t].data_ptr(), _p(dhb), sv[t].data_ptr(), _p(hp), dgi[t].data_ptr(), GH,
                          dgh[t].data_ptr(), rec[t & 1].data_ptr(), B, H)
@@ -1403,6 +1430,7 @@ class DecoderLossFunction(torch.autograd.Function):
         out = torch.empty(len(segs), 3, device=Hs.device, dtype=torch.float32)
         b0 = 0
         for i, a in enumerate(segs):
+            _lib.tag(f"logistic_loss_fwd[B={a.shape[0]},S={S}]", 0.0, 124.0 * a.shape[0] * S * A)  # 124 B per (b,s,dim) row
             call("hulc2_logistic_loss_seg_fwd", heads.data_ptr() + 4 * b0 * HEAD_LD, HEAD_LD, a.data_ptr(), amin.data_ptr(),
                  amax.data_ptr(), out.data_ptr() + 12 * i, a.shape[0], S, A, M, num_classes, ls_min, alpha, 1, B, ws.data_ptr(), ws.numel())
             b0 += a.shape[0]
@@ -1422,6 +1450,7 @@ class DecoderLossFunction(torch.autograd.Function):
         dheads = torch.empty_like(heads)
         b0 = 0
         for i, a in enumerate(segs):
+            _lib.tag(f"logistic_loss_bwd[B={a.shape[0]},S={S}]", 0.0, 244.0 * a.shape[0] * S * A)
             call("hulc2_logistic_loss_seg_bwd", heads.data_ptr() + 4 * b0 * HEAD_LD, HEAD_LD, a.data_ptr(), amin.data_ptr(),
                  amax.data_ptr(), g.data_ptr() + 4 * i, dheads.data_ptr() + 4 * b0 * HEAD_LD, a.shape[0], S, A, M, num_classes,
                  ls_min, alpha, 1, B)
@@ -1516,6 +1545,16 @@ def logistic_sample(heads, u1, u2, gripper_bounds, B, S, A, M, ls_min, time_majo
     return act
 
 
+def val_metrics(pred: torch.Tensor, actions: torch.Tensor) -> torch.Tensor:
+    """hulc2.py:292-302 + the reductions logged in validation_step (:559-575) in one launch:
+    -> float32[4] = (total MAE, position MAE, orientation MAE, discrete-gripper success rate) for pred / actions [B,S,A+1]."""
+    p, a = _f32(pred).contiguous(), _f32(actions).contiguous()
+    B, S, A1 = a.shape
+    out = torch.empty(4, device=p.device, dtype=torch.float32)
+    call("hulc2_val_metrics", p.data_ptr(), a.data_ptr(), out.data_ptr(), B, S, A1 - 1)
+    return out
+
+
 def world_to_tcp(actions: torch.Tensor, robot_obs: torch.Tensor) -> torch.Tensor:
     a, r = _f32(actions).contiguous(), _f32(robot_obs).contiguous()
     out = torch.empty_like(a)
@@ -1540,6 +1579,7 @@ class InfoNCEFunction(torch.autograd.Function):
         B, D = img.shape
         loss = torch.empty(1, device=img.device, dtype=torch.float32)
         ws = workspace(img.device)
+        _lib.tag(f"infonce_fwd[B={B},D={D}]", 4.0 * B * B * D, 8.0 * B * D)
         call("hulc2_infonce_fwd", img.data_ptr(), txt.data_ptr(), _p(use), logit_scale.data_ptr(), loss.data_ptr(), B, D,
              ws.data_ptr(), ws.numel())
         ctx.save_for_backward(img, txt, logit_scale)
@@ -1553,6 +1593,7 @@ class InfoNCEFunction(torch.autograd.Function):
         dimg, dtxt = torch.empty_like(img), torch.empty_like(txt)
         dls = torch.zeros((), device=img.device, dtype=torch.float32)
         ws = workspace(img.device)
+        _lib.tag(f"infonce_bwd[B={B},D={D}]", 8.0 * B * B * D, 16.0 * B * D)
         call("hulc2_infonce_bwd", img.data_ptr(), txt.data_ptr(), _p(ctx.use), logit_scale.data_ptr(), g.contiguous().data_ptr(),
              dimg.data_ptr(), dtxt.data_ptr(), dls.data_ptr(), B, D, ws.data_ptr(), ws.numel())
         return dimg, dtxt, dls, None

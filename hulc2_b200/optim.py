@@ -12,6 +12,7 @@ from typing import Dict, Iterable, List
 import torch
 
 from ._lib import call
+from ._lib import tag as _lib_tag
 
 _ALIGN = 8  # elements: every parameter starts 32-byte aligned, so its bf16 mirror (ops.weight16) is a legal TMA base
 
@@ -139,10 +140,12 @@ class FusedAdam(torch.optim.Optimizer):
             if self.capturable:
                 # step = (device counter of completed steps) + 1; the trainer bumps the counter after every step.  The
                 # learning rate is read from device memory, so schedulers keep working when this launch is replayed.
+                _lib_tag(f"adam_step[n={a['n']}]", 0.0, 28.0 * a["n"])      # 16 B/param read + 12 B/param written
                 call("hulc2_adam_step_graph", a["p"].data_ptr(), a["g"].data_ptr(), a["m"].data_ptr(), a["v"].data_ptr(), a["n"],
                      self._lr_dev.data_ptr() + 4 * gi, float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
                      ctr.data_ptr(), 1, float(self.grad_scale))
             else:
+                _lib_tag(f"adam_step[n={a['n']}]", 0.0, 28.0 * a["n"])
                 call("hulc2_adam_step", a["p"].data_ptr(), a["g"].data_ptr(), a["m"].data_ptr(), a["v"].data_ptr(), a["n"],
                      float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(a["step"]),
                      float(self.grad_scale))

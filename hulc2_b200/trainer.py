@@ -172,7 +172,13 @@ class PolicyTrainer:
         return loss
 
     def _capture(self, batch, batch_idx):
-        self.static_batch = batch               # the tensors the graph reads; later batches are copied into them
+        # The graph reads its inputs from the trainer's OWN static buffers; every later batch is copied into them (a caller
+        # that wants zero-copy steps fills / passes ``trainer.static_batch`` itself).  The caller's tensors are never written.
+        if self.static_batch is None or not _same_shapes(self.static_batch, batch):
+            self.static_batch = tree_map(torch.clone, batch)
+        else:
+            _zip_copy(self.static_batch, batch)
+        batch = self.static_batch
         from ._lib import load_library
 
         self._captured_scalars = self._host_scalars()
@@ -262,3 +268,69 @@ def _same_shapes(a, b) -> bool:
     if isinstance(a, torch.Tensor):
         return isinstance(b, torch.Tensor) and a.shape == b.shape and a.dtype == b.dtype
     return True
+
+
+class PolicyValidator:
+    """``Hulc2.validation_step`` (hulc2/models/hulc2.py:510-598) driven as Lightning's validation loop does (no_grad, eval
+    mode), with the whole step -- encoders, both plan networks, the two decoder passes with action sampling, KL, the MAE /
+    gripper-success reductions -- captured in ONE CUDA graph over a static batch and replayed.  Sampling noise comes from
+    the Philox kernels keyed by the device epoch counter, bumped once per replay.  ``validate`` returns the step's output
+    dict and the logged scalars as device tensors (static buffers, overwritten by the next call)."""
+
+    def __init__(self, model, use_graph: bool = True):
+        self.model = model
+        self.device = next(model.parameters()).device
+        self.use_graph = use_graph
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self.static_batch = None
+        self._out = None
+        self._logged = None
+        self.launches_per_replay = 0
+        self.replays = 0
+        self._keepalive: list = []
+
+    def _body(self, batch, batch_idx):
+        noise.begin_step()
+        out = self.model.validation_step(batch, batch_idx)
+        call("hulc2_counter_add", noise.epoch_tensor(self.device).data_ptr(), 1)
+        logged = {k: v for k, v in getattr(self.model, "logged", {}).items() if k.startswith("val") and isinstance(v, torch.Tensor)}
+        return out, logged
+
+    def validate(self, batch: Dict[str, dict], batch_idx: int = 0):
+        was_training = self.model.training
+        self.model.eval()
+        caller = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(caller)
+        try:
+            with torch.cuda.stream(self.stream), torch.no_grad():
+                if not self.use_graph:
+                    res = self._body(batch, batch_idx)
+                elif self._graph is None:
+                    res = self._body(batch, batch_idx)         # the first call runs eagerly (fills the bf16 weight mirrors) ...
+                    torch.cuda.synchronize()
+                    self.static_batch = tree_map(torch.clone, batch)   # ... then the same body is recorded over own static inputs
+                    from ._lib import load_library
+
+                    g = torch.cuda.CUDAGraph()
+                    n0 = load_library().hulc2_launch_count()
+                    with torch.cuda.graph(g, stream=self.stream):
+                        self._out, self._logged = self._body(self.static_batch, batch_idx)
+                    self.launches_per_replay = int(load_library().hulc2_launch_count() - n0)
+                    self._graph = g
+                    self._keepalive.append((dict(ops._w16), [a[1] for a in ops._arenas]))
+                else:
+                    _zip_copy(self.static_batch, batch)
+                    self._graph.replay()
+                    self.replays += 1
+                    res = (self._out, self._logged)
+        finally:
+            self.model.train(was_training)
+        caller.wait_stream(self.stream)
+        return res
+
+    def refresh(self) -> None:
+        """Parameters changed since the capture (training continued): the captured bf16 weight mirrors are stale."""
+        ops.invalidate_weight_mirrors()
+        self._graph = None
+        self._keepalive.clear()

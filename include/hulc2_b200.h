@@ -245,6 +245,10 @@ int hulc2_logistic_sample(const float* heads, long long ld, const float* u1, con
                           const float* gripper_bounds, float* act, int B, int S, int A, int M, float log_scale_min,
                           int time_major, hulc2_stream_t stream);
 /* splits the fused heads buffer into the reference's forward() outputs (logistic_decoder_rnn.py:275-284) */
+/* Validation metrics of lmp_val / validation_step (hulc2.py:292-302, 559-575) for one modality's windows: pred = sampled
+ * actions [B,S,A+1], actions = ground truth; out[4] = {mean |err| over the A continuous dims, over dims 0-2 (position), over
+ * dims 3-5 (orientation), success rate of the discretised gripper action (pred > 0 ? 1 : -1) == gt}. */
+int hulc2_val_metrics(const float* pred, const float* actions, float* out, int B, int S, int A, hulc2_stream_t stream);
 int hulc2_heads_unpack(const float* heads, long long ld, float* logit_probs, float* log_scales, float* means,
                        float* gripper, int B, int S, int A, int M, float log_scale_min, int time_major,
                        hulc2_stream_t stream);

@@ -276,15 +276,47 @@ def world_to_tcp_frame(action: Tensor, robot_obs: Tensor) -> Tensor:
     return torch.cat([pos.view(b, s, -1), o.view(b, s, -1), action[..., -1:]], -1)
 
 
+def matrix_to_quaternion(m: Tensor) -> Tensor:
+    """pytorch3d.transforms.matrix_to_quaternion (unpinned third-party dependency, requirements.txt:20; restated from its
+    published algorithm, rotation_conversions.py): the four candidate quaternions (r,i,j,k) built from the matrix, the one
+    with the largest |component| selected, divided by 2 * max(that component, 0.1)."""
+    m00, m01, m02, m10, m11, m12, m20, m21, m22 = torch.unbind(m.reshape(m.shape[:-2] + (9,)), -1)
+    arg = torch.stack([1.0 + m00 + m11 + m22, 1.0 + m00 - m11 - m22, 1.0 - m00 + m11 - m22, 1.0 - m00 - m11 + m22], -1)
+    q_abs = torch.where(arg > 0, torch.sqrt(torch.clamp(arg, min=0)), torch.zeros_like(arg))      # _sqrt_positive_part
+    cand = torch.stack([
+        torch.stack([q_abs[..., 0] ** 2, m21 - m12, m02 - m20, m10 - m01], -1),
+        torch.stack([m21 - m12, q_abs[..., 1] ** 2, m10 + m01, m02 + m20], -1),
+        torch.stack([m02 - m20, m10 + m01, q_abs[..., 2] ** 2, m12 + m21], -1),
+        torch.stack([m10 - m01, m20 + m02, m21 + m12, q_abs[..., 3] ** 2], -1),
+    ], -2)
+    cand = cand / (2.0 * q_abs[..., None].clamp(min=0.1))
+    pick = torch.nn.functional.one_hot(q_abs.argmax(-1), 4) > 0.5
+    return cand[pick, :].reshape(m.shape[:-2] + (4,))
+
+
+def quaternion_to_matrix(q: Tensor) -> Tensor:
+    """pytorch3d.transforms.quaternion_to_matrix (real part first), restated from its published algorithm."""
+    r, i, j, k = torch.unbind(q, -1)
+    two_s = 2.0 / (q * q).sum(-1)
+    o = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+    return o.reshape(q.shape[:-1] + (3, 3))
+
+
 def tcp_to_world_frame(action: Tensor, robot_obs: Tensor) -> Tensor:
-    """gripper_control.py:39-63 (NaN/quaternion fallback not restated: asin domain is never left
-    for the synthetic inputs; tests assert no NaN)."""
+    """gripper_control.py:39-63, including the NaN fallback (:51-55): when asin leaves its domain by fp32 rounding near the
+    gimbal pole (|M02| = 1 + ulp), the angles of the WHOLE batch are re-derived from the matrix re-normalised through a
+    quaternion round trip."""
     b, s, _ = action.shape
     w_T = euler_xyz_to_matrix(robot_obs[..., 3:6]).float().view(-1, 3, 3)
     pos = w_T @ action[..., :3].reshape(-1, 3, 1)
     rel = euler_xyz_to_matrix(action[..., 3:6] * 0.01).float().view(-1, 3, 3)
     w_T_new = w_T @ torch.inverse(rel)
-    o = matrix_to_euler_xyz(w_T_new).float() - robot_obs[..., 3:6].reshape(-1, 3)
+    e = matrix_to_euler_xyz(w_T_new).float()
+    if bool(torch.any(e.isnan())):
+        e = matrix_to_euler_xyz(quaternion_to_matrix(matrix_to_quaternion(w_T_new))).float()
+    o = e - robot_obs[..., 3:6].reshape(-1, 3)
     o = _wrap_pi(o) * 100
     return torch.cat([pos.view(b, s, -1), o.view(b, s, -1), action[..., -1:]], -1)
 

@@ -138,8 +138,13 @@ def matrix_to_euler_angles(matrix, convention):
     return torch.stack((a, b, c), -1)
 
 
-def _nyi(*a, **k):  # NaN-fallback path only (gripper_control.py:51-55)
-    raise NotImplementedError("quaternion fallback not restated")
+def _quat(name):  # NaN-fallback path only (gripper_control.py:51-55): pytorch3d's algorithm as restated in the oracle
+    def fn(x):
+        from oracle import hulc2_oracle as O
+
+        return getattr(O, name)(x)
+
+    return fn
 
 
 _installed = False
@@ -183,8 +188,8 @@ def install_shims():
             "pytorch3d.transforms",
             euler_angles_to_matrix=euler_angles_to_matrix,
             matrix_to_euler_angles=matrix_to_euler_angles,
-            matrix_to_quaternion=_nyi,
-            quaternion_to_matrix=_nyi,
+            matrix_to_quaternion=_quat("matrix_to_quaternion"),
+            quaternion_to_matrix=_quat("quaternion_to_matrix"),
         )
         _mod("pytorch3d", transforms=p3t)
 

@@ -60,6 +60,35 @@ def assert_close(a, b, tol, what=""):
     assert e <= tol, f"{what}: rel err {e:.3e} > {tol:.1e}"
 
 
+def gimbal_pole_cases(n: int = 400000, seed: int = 1, keep: int = 64):
+    """(action [1,K,7], robot_obs [1,K,15]) near the XYZ-Euler gimbal pole (pitch within 0.01 rad of +-pi/2), K = `keep` rows of
+    which the first ones are chosen so that the reference's fp32 asin argument exceeds 1 by one ulp -- the inputs for which
+    tcp_to_world_frame takes its quaternion NaN fallback (gripper_control.py:51-55) -- followed by ordinary near-pole rows."""
+    import math
+
+    from oracle import hulc2_oracle as O
+
+    g = torch.Generator().manual_seed(seed)
+    rob = torch.zeros(1, n, 15)
+    rob[..., 3] = torch.rand(n, generator=g) * 2 - 1
+    sgn = torch.where(torch.rand(n, generator=g) < 0.5, -1.0, 1.0)
+    rob[..., 4] = sgn * (math.pi / 2 - torch.rand(n, generator=g) * 0.01)
+    rob[..., 5] = torch.rand(n, generator=g) * 2 - 1
+    act = torch.rand(1, n, 7, generator=g) * 2 - 1
+    w_T = O.euler_xyz_to_matrix(rob[..., 3:6]).float().view(-1, 3, 3)
+    rel = O.euler_xyz_to_matrix(act[..., 3:6] * 0.01).float().view(-1, 3, 3)
+    W = w_T @ torch.inverse(rel)
+    bad = O.matrix_to_euler_xyz(W).isnan().any(-1)
+    # the quaternion round trip rescues most of them; for a few the re-normalised matrix STILL has |m02| = 1 + ulp and the
+    # reference dies on its `assert not isnan` (gripper_control.py:62) -- those are returned separately (`fatal`)
+    again = O.matrix_to_euler_xyz(O.quaternion_to_matrix(O.matrix_to_quaternion(W))).isnan().any(-1)
+    nan_rows = (bad & ~again).nonzero().flatten()[: keep // 2]
+    rest = (~bad).nonzero().flatten()[: keep - len(nan_rows)]
+    sel = torch.cat([nan_rows, rest])
+    fatal = (bad & again).nonzero().flatten()[:8]
+    return act[:, sel].clone(), rob[:, sel].clone(), int(len(nan_rows)), (act[:, fatal].clone(), rob[:, fatal].clone())
+
+
 GRAD_SAMPLE = 4096
 
 

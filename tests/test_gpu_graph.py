@@ -56,6 +56,7 @@ def _drive(use_graph, batches, steps, precision, dropout_p, hidden=256, hooks=No
     ops.set_precision(precision)
     noise.manual_seed(1234)
     noise.epoch_tensor(torch.device(DEV)).zero_()
+    before = [float(b["vis"]["actions"].sum()) for b in batches]
     m = build_model("calvin", dropout_p=dropout_p, hidden_size=hidden).to(DEV).train()
     tr = PolicyTrainer(m, use_graph=use_graph, device_counters=True)
     out = []
@@ -65,6 +66,8 @@ def _drive(use_graph, batches, steps, precision, dropout_p, hidden=256, hooks=No
         loss = tr.train_step(batches[i % len(batches)], i)
         torch.cuda.synchronize()
         out.append((float(loss), _params(m)))
+    # the captured graph reads the trainer's own static inputs: the caller's batches are never written
+    assert before == [float(b["vis"]["actions"].sum()) for b in batches]
     return out, tr
 
 
@@ -78,7 +81,7 @@ def test_graph_replay_equals_eager_steps(precision, loss_tol):
     assert trg._graph is not None and trg.replays == 4 and tre._graph is None
     assert trg.launches_per_replay > 100
     for k, ((lg, pg), (le, pe)) in enumerate(zip(g, e), 1):
-        assert abs(lg - le) <= loss_tol * abs(le), f"step {k}: loss {lg} (graph) vs {le} (eager)"
+        assert abs(lg - le) <= loss_tol * abs(le), f"step {k}: loss {lg} (graph) vs {le} (eager); all: {[x[0] for x in g]} vs {[x[0] for x in e]}"
         _compare_params(pg, pe, k, f"{precision} graph vs eager")
     # the device counters advanced once per step in both runs
     assert int(trg.optimizer.step_counter(torch.device(DEV))) == 6 and int(tre.optimizer.step_counter(torch.device(DEV))) == 6
@@ -131,7 +134,10 @@ def test_graph_replay_vs_oracle_and_torch_adam():
         assert abs(float(loss) - ref[i][0]) <= tol * abs(ref[i][0]), f"step {i + 1}: {float(loss)} vs {ref[i][0]}"
         print(f"[graph vs oracle] step {i + 1}: loss rel err {abs(float(loss) - ref[i][0]) / abs(ref[i][0]):.2e}")
         mine = {n: p.detach().cpu() for n, p in m.named_parameters() if n in ref[i][1]}
-        _compare_params(mine, ref[i][1], i + 1, "graph vs oracle+torch.optim.Adam", frac_tol=5e-3)
+        # (elements whose gradient is at fp32 rounding level take Adam's +-lr step in a different direction: 6e-4 of them after
+        # step 1, growing with every step; bounded per element by _compare_params)
+        frac = _compare_params(mine, ref[i][1], i + 1, "graph vs oracle+torch.optim.Adam", frac_tol=1e-2 * (i + 1))
+        print(f"[graph vs oracle] step {i + 1}: {frac:.2e} of the elements moved differently")
     assert tr.replays == steps - 2
 
 
@@ -210,3 +216,39 @@ def test_scheduler_is_stepped_by_the_trainer():
     torch.cuda.synchronize()
     assert lrs == [LR * 0.5 ** (i + 1) for i in range(4)]
     assert abs(float(tr.optimizer._lr_dev[0]) - LR * 0.5 ** 3) < 1e-12   # the value the last replay read
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_validation_graph_replay_equals_eager(precision):
+    """PolicyValidator: validation_step (hulc2.py:510-598) captured as one graph; replays draw fresh Philox noise per call
+    (device epoch) and must equal the eager validator call for call -- sampled plans bit-exact, every logged metric equal."""
+    from hulc2_b200.trainer import PolicyValidator
+
+    batches = [to_device(synthetic_batch(2, seed=80 + i, aux="half"), DEV) for i in range(3)]
+
+    def drive(use_graph):
+        ops.set_precision(precision)
+        noise.manual_seed(77)
+        noise.epoch_tensor(torch.device(DEV)).zero_()
+        m = build_model("calvin", hidden_size=256).to(DEV).train()       # validate() switches to eval and back
+        val = PolicyValidator(m, use_graph=use_graph)
+        res = []
+        for i in range(4):
+            out, logged = val.validate(batches[i % 3], i)
+            torch.cuda.synchronize()
+            res.append(({k: v.clone() for k, v in out.items()}, {k: float(v) for k, v in logged.items()}))
+        assert m.training
+        return res, val
+
+    g, vg = drive(True)
+    e, _ = drive(False)
+    assert vg.replays == 3 and vg.launches_per_replay > 50
+    for i, ((og, lg), (oe, le)) in enumerate(zip(g, e)):
+        assert set(og) == set(oe) == {"sampled_plan_pp_vis", "sampled_plan_pr_vis", "idx_vis", "sampled_plan_pp_lang", "sampled_plan_pr_lang", "idx_lang"}
+        for k in og:
+            assert torch.equal(og[k], oe[k]), f"call {i}: {k}"
+        assert set(lg) == set(le) and len(lg) >= 24
+        for k in lg:
+            assert abs(lg[k] - le[k]) <= 1e-6 * max(abs(le[k]), 1e-3), f"call {i}: {k}: {lg[k]} vs {le[k]}"
+    # different calls really saw different noise and different batches
+    assert not torch.equal(g[0][0]["sampled_plan_pp_vis"], g[1][0]["sampled_plan_pp_vis"])

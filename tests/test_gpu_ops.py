@@ -336,6 +336,37 @@ def test_frames_golden():
     assert_close(tcp_to_world_frame(act, robot), gt("op/frames/tcp_to_world"), 2e-5)
 
 
+def test_tcp_to_world_near_the_gimbal_pole():
+    """gripper_control.py:39-63 next to pitch = +-pi/2, including inputs for which the reference's fp32 asin leaves its domain
+    and the quaternion fallback (:51-55) runs.  Individual Euler angles are ill-conditioned there (only their combination is
+    determined), so the comparison is on what they encode: the new world orientation R(theta + out/100) against the fp64
+    product world_T_tcp * inverse(tcp_new_T_tcp_old); positions and gripper pass through to fp32 rounding.  The kernel works
+    in double with asin's argument clamped, so it also stays finite on the few inputs where the reference dies on its NaN assert."""
+    from helpers import gimbal_pole_cases
+    from hulc2_b200.models.decoders.utils.gripper_control import tcp_to_world_frame
+    from oracle import hulc2_oracle as O
+
+    act, rob, n_nan, (fatal_act, fatal_rob) = gimbal_pole_cases()
+    assert n_nan >= 4
+    for a, r in ((act, rob), (fatal_act, fatal_rob)):
+        if a.shape[1] == 0:
+            continue
+        out = tcp_to_world_frame(a.to(DEV), r.to(DEV)).cpu()
+        assert bool(torch.isfinite(out).all())
+        assert torch.equal(out[..., 6], a[..., 6])
+        R = O.euler_xyz_to_matrix(r[..., 3:6].double())
+        T = O.euler_xyz_to_matrix(a[..., 3:6].float().mul(0.01).double())
+        want = R @ torch.inverse(T)
+        got = O.euler_xyz_to_matrix(r[..., 3:6].double() + out[..., 3:6].double() / 100.0)
+        assert float((got - want).abs().max()) <= 2e-5, float((got - want).abs().max())
+        assert float((out[..., :3].double() - (R @ a[..., :3].double().unsqueeze(-1)).squeeze(-1)).abs().max()) <= 1e-5
+    # where the reference (= the oracle, pinned bit-exact in test_oracle_vs_reference) is defined, same values to the
+    # conditioning of the angles next to the pole
+    ref = O.tcp_to_world_frame(act, rob)
+    out = tcp_to_world_frame(act.to(DEV), rob.to(DEV)).cpu()
+    assert float((out - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+
+
 def test_infonce_golden_masked():
     m = build_model("calvin").to(DEV)
     sf, gl = gt("op/clip/seq_feat").to(DEV).requires_grad_(), gt("op/clip/goal").to(DEV).requires_grad_()
