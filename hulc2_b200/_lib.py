@@ -138,7 +138,7 @@ _SIGS = {
 }
 _NO_STREAM = {"hulc2_last_error": (C.c_char_p, []), "hulc2_version": (I, []), "hulc2_device_supports_tcgen05": (I, []),
               "hulc2_launch_count": (C.c_ulonglong, []), "hulc2_tma_gemm_count": (C.c_ulonglong, []), "hulc2_convb_supported": (I, [I, I, I, I, I]),
-              "hulc2_rnn_select_kernel": (I, [I]), "hulc2_rnn_cluster_capacity": (I, [I]), "hulc2_rnn_device_error": (I, [I])}
+              "hulc2_rnn_select_kernel": (I, [I]), "hulc2_rnn_cluster_capacity": (I, [I]), "hulc2_rnn_device_error": (I, [I]), "hulc2_rnn_last_path": (I, [])}
 
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + list(_NO_STREAM))
 

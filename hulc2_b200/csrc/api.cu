@@ -1,5 +1,6 @@
 // extern "C" entry points that dispatch between the fp32 CUDA-core path and the bf16 tcgen05 path,
 // plus the host-side step loops of the decoder recurrence.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -18,6 +19,10 @@ int hulc2_rnn_persistent_launch(const float* add, const float* w, const float* i
                                 cudaStream_t st);
 
 int hulc2_rnn_cluster_device_error(int clear);
+int hulc2_rnn_cluster2_device_error(int clear);
+int hulc2_rnn_cluster2_launch(const float* add, const float* w, const float* init, const float* mask, float* out, float* final_out,
+                              int S, int B, int H, int relu, int reverse, int transpose_w, void* workspace, long long workspace_bytes,
+                              cudaStream_t st);
 int hulc2_rnn_persistent_device_error(int clear);
 int hulc2_rnn_cluster_launch(const float* add, const float* w, const float* init, const float* mask, float* out, float* final_out,
                              int S, int B, int H, int relu, int reverse, int transpose_w, void* workspace, long long workspace_bytes,
@@ -84,7 +89,15 @@ int hulc2_conv2d_dgrad(const hulc2_conv_args* a, cudaStream_t st) {
   return HULC2_EINVAL;
 }
 
+static int g_rnn_path = 0;      // which kernel served the last hulc2_rnn_relu_{fwd,bwd}: 1 = (a'), 2 = (a), 3 = (b), 4 = per-step GEMMs
+int g_rnn_v2_reject = 0;        // why (a') last declined: see rnn_cluster2_sm100.cu
+int hulc2_rnn_last_path(void) { return g_rnn_path | (g_rnn_v2_reject << 8); }
 static int g_rnn_kernel = 0;
+static bool rnn_v2() {   // HULC2_RNN_V1=1: skip the TMA-fed cluster kernel (rnn_cluster2_sm100.cu) -- A/B switch, read once
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HULC2_RNN_V1"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
 int hulc2_rnn_select_kernel(int which) {
   int prev = g_rnn_kernel;
   g_rnn_kernel = which;
@@ -93,8 +106,9 @@ int hulc2_rnn_select_kernel(int which) {
 
 int hulc2_rnn_device_error(int clear) {
   const int a = hulc2_rnn_cluster_device_error(clear), b = hulc2_rnn_persistent_device_error(clear);
-  if (a < 0 || b < 0) return -1;
-  return a | (b << 1);
+  const int c = hulc2_rnn_cluster2_device_error(clear);
+  if (a < 0 || b < 0 || c < 0) return -1;
+  return a | (b << 1) | (c << 2);
 }
 
 // h[t] = relu(pre[t] + h[t-1] W_hh^T)      (nn.RNN, nonlinearity=relu; decoders/utils/rnn.py:5-14)
@@ -103,11 +117,14 @@ int hulc2_rnn_relu_fwd(const float* pre, const float* w_hh, const float* h0, flo
   if (S <= 0 || B <= 0) return HULC2_OK;
   if (precision == 1 && hulc2_device_supports_tcgen05()) {
     int e = HULC2_ENOTIMPL;
+    if (g_rnn_kernel == 0 && rnn_v2()) e = hulc2_rnn_cluster2_launch(pre, w_hh, h0, nullptr, h, nullptr, S, B, H, 1, 0, 0, workspace, workspace_bytes, st);
+    if (e != HULC2_ENOTIMPL) { g_rnn_path = 1; return e; }
     if (g_rnn_kernel < 1) e = hulc2_rnn_cluster_launch(pre, w_hh, h0, nullptr, h, nullptr, S, B, H, 1, 0, 0, workspace, workspace_bytes, st);
-    if (e != HULC2_ENOTIMPL) return e;
+    if (e != HULC2_ENOTIMPL) { g_rnn_path = 2; return e; }
     if (g_rnn_kernel < 2) e = hulc2_rnn_persistent_launch(pre, w_hh, h0, nullptr, h, nullptr, S, B, H, 1, 0, 0, workspace, workspace_bytes, st);
-    if (e != HULC2_ENOTIMPL) return e;
+    if (e != HULC2_ENOTIMPL) { g_rnn_path = 3; return e; }
   }
+  g_rnn_path = 4;
   const long long step = (long long)B * H;
   for (int t = 0; t < S; ++t) {
     hulc2_gemm_args g;
@@ -131,11 +148,14 @@ int hulc2_rnn_relu_bwd(float* dh, const float* w_hh, const float* h, float* dh0,
   if (S <= 0 || B <= 0) return HULC2_OK;
   if (precision == 1 && hulc2_device_supports_tcgen05()) {
     int e = HULC2_ENOTIMPL;
+    if (g_rnn_kernel == 0 && rnn_v2()) e = hulc2_rnn_cluster2_launch(dh, w_hh, nullptr, h, dh, dh0, S, B, H, 0, 1, 1, workspace, workspace_bytes, st);
+    if (e != HULC2_ENOTIMPL) { g_rnn_path = 1; return e; }
     if (g_rnn_kernel < 1) e = hulc2_rnn_cluster_launch(dh, w_hh, nullptr, h, dh, dh0, S, B, H, 0, 1, 1, workspace, workspace_bytes, st);
-    if (e != HULC2_ENOTIMPL) return e;
+    if (e != HULC2_ENOTIMPL) { g_rnn_path = 2; return e; }
     if (g_rnn_kernel < 2) e = hulc2_rnn_persistent_launch(dh, w_hh, nullptr, h, dh, dh0, S, B, H, 0, 1, 1, workspace, workspace_bytes, st);
-    if (e != HULC2_ENOTIMPL) return e;
+    if (e != HULC2_ENOTIMPL) { g_rnn_path = 3; return e; }
   }
+  g_rnn_path = 4;
   const long long step = (long long)B * H;
   if (int e = hulc2_relu_mask(dh + (S - 1) * step, h + (S - 1) * step, dh + (S - 1) * step, step, st)) return e;
   for (int t = S - 2; t >= -1; --t) {

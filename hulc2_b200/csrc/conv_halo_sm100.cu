@@ -456,6 +456,182 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_wgrad_kernel(const __gri
   if (warp == 0) tmem_dealloc(tmem_d, tcols);
 }
 
+
+// ---- the same tile scheme with cp.async producers instead of two TMA boxes per tile.  A TMA box over 128-byte rows is one
+// request per row (850 per conv1 tile, one every ~7-10 cycles: 0.92 ms for conv1's weight gradient), and it moves 128 bytes per
+// pixel although a packed conv1 pixel has 96 and its dZ pixel 64.  Here the 8 warps that dump the accumulators at the end
+// copy exactly the live 16-byte chunks of every pixel (6 + 4 per position for conv1 instead of the gather kernel's 28 per output
+// pixel, which re-reads every source pixel once per tap) into the same 128-byte-swizzled raster tile; out-of-range positions
+// are zero-filled (src-size 0), so the MMAs and the shifted MN-major descriptors are exactly those of the TMA version.
+struct HaloWgradCpParams {
+  HaloWgradParams g;
+  const uint8_t* x;        // bf16 NHWC source [F, H, W, xpe]
+  const uint8_t* dz;       // bf16 [F, OH, OW, zpe]
+  int H, W, OH, OW;
+  int lag;                 // copy groups a producer thread keeps in flight before it publishes the oldest
+};
+
+__device__ __forceinline__ void cp_wait_dyn(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    default: cp_async_wait<3>(); break;
+  }
+}
+
+constexpr int WGCP_MAX_ISS = 6;
+constexpr int NT_WGCP = 256 + 32 * WGCP_MAX_ISS;     // 8 producer / dump warps + 6 MMA issuer warps
+
+template <int CX, int CZ>      // 16-byte chunks per source / dZ pixel (6, 4: conv1 over packed frames; 8, 8: conv3)
+__global__ void __launch_bounds__(NT_WGCP, 1) conv_halo_wgrad_cp_kernel(const __grid_constant__ HaloWgradCpParams q) {
+  const HaloWgradParams& p = q.g;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_ST], empty_bar[MAX_ST], done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ST = (uint32_t)p.stages;
+  const uint32_t stage_bytes = (uint32_t)(p.a_bytes + p.b_bytes);
+  const uint32_t ones_smem = base + ST * stage_bytes;           // 32 rows x 128 B of bf16 1.0
+  const int nmt = p.nmt;
+  // issuers: one per M-tile, times two halves of a tile's k-steps when TMEM holds a second accumulator set (added in the dump)
+  const int ksplit = (2 * nmt * 64 <= 512 && 2 * nmt <= WGCP_MAX_ISS) ? 2 : 1;
+  const int ni_m = nmt < WGCP_MAX_ISS / ksplit ? nmt : WGCP_MAX_ISS / ksplit;
+  const int niss = ni_m * ksplit;
+  const uint32_t need_cols = (uint32_t)(ksplit * nmt * 64);
+  const uint32_t tcols = need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u));
+  constexpr int NPROD = 256;
+
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), tcols);
+  if (tid == 32) {
+    for (uint32_t s = 0; s < ST; ++s) { mbar_init(smem_u32(&full_bar[s]), NPROD); mbar_init(smem_u32(&empty_bar[s]), (uint32_t)niss); }
+    mbar_init(smem_u32(&done_bar), (uint32_t)niss);
+    mbar_fence_init();
+  }
+  // zero all stages once (chunks beyond a pixel's live channels and the rows behind a tile are read by the MMAs: they must be
+  // finite; nobody writes them afterwards), then the ones tile
+  for (uint32_t o = tid * 16; o < ST * stage_bytes; o += NT_WGCP * 16)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(0u) : "memory");
+  for (uint32_t o = tid * 16; o < 32 * 128; o += NT_WGCP * 16)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ones_smem + o), "r"(0x3F803F80u) : "memory");
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+  const int KL = p.BH * p.PW;                                    // contraction positions per tile (multiple of 16)
+
+  if (warp < 8) {
+    // ---------------------------------------------------------------- producers (then dump, below)
+    uint32_t s = 0, ph = 1, ps = 0;
+    int inflight = 0;
+    const int xrows = p.BH + p.KH - 1;
+    const long long xrow_b = (long long)q.W * CX * 16, xfr_b = (long long)q.H * xrow_b;
+    const long long zrow_b = (long long)q.OW * CZ * 16, zfr_b = (long long)q.OH * zrow_b;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int f = tile / p.tiles_per_frame, ti = tile - f * p.tiles_per_frame;
+      const int y0 = ti * p.BH;
+      mbar_wait(smem_u32(&empty_bar[s]), ph);
+      const uint32_t a_tile = base + s * stage_bytes, b_tile = a_tile + (uint32_t)p.a_bytes;
+      const uint8_t* xf = q.x + f * xfr_b;
+      for (int i = 0; i < xrows; ++i) {
+        const int y = y0 + i;
+        const uint8_t* xr = xf + (long long)y * xrow_b;
+        const bool yok = y < q.H;
+        for (int idx = tid; idx < p.PW * CX; idx += NPROD) {
+          const int j = idx / CX, c = idx - j * CX;
+          const bool ok = yok && j < q.W;
+          cp_async16(a_tile + swz128(i * p.PW + j, c), ok ? xr + idx * 16 : q.x, ok ? 16u : 0u);
+        }
+      }
+      const uint8_t* zf = q.dz + f * zfr_b;
+      for (int i = 0; i < p.BH; ++i) {
+        const int y = y0 + i;
+        const uint8_t* zr = zf + (long long)y * zrow_b;
+        const bool yok = y < q.OH;
+        for (int idx = tid; idx < p.PW * CZ; idx += NPROD) {
+          const int j = idx / CZ, c = idx - j * CZ;
+          const bool ok = yok && j < q.OW;
+          cp_async16(b_tile + swz128(i * p.PW + j, c), ok ? zr + idx * 16 : q.dz, ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      if (++s == ST) { s = 0; ph ^= 1; }
+      if (inflight == q.lag) {
+        cp_wait_dyn(q.lag);
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&full_bar[ps]));
+        if (++ps == ST) ps = 0;
+      } else {
+        ++inflight;
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (; inflight > 0; --inflight) {
+      mbar_arrive(smem_u32(&full_bar[ps]));
+      if (++ps == ST) ps = 0;
+    }
+    // ---------------------------------------------------------------- dump: warp w <-> TMEM lanes 32*(w%4).., columns (w/4)*32..+32
+    const int lq = warp & 3, half = warp >> 2;
+    mbar_wait_relaxed(smem_u32(&done_bar), 0);
+    tc_fence_after();
+    float* out = p.partial + (size_t)blockIdx.x * nmt * 128 * 64;
+    for (int mt = 0; mt < nmt; ++mt) {
+      uint32_t acc[32];
+#pragma unroll
+      for (int c = 0; c < 32; c += 16)
+        tmem_ld16_nowait(tmem_d + ((uint32_t)(lq * 32) << 16) + mt * 64 + half * 32 + c, *reinterpret_cast<uint32_t(*)[16]>(&acc[c]));
+      tmem_ld_wait();
+      if (ksplit == 2) {
+        uint32_t acc2[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 16)
+          tmem_ld16_nowait(tmem_d + ((uint32_t)(lq * 32) << 16) + (nmt + mt) * 64 + half * 32 + c, *reinterpret_cast<uint32_t(*)[16]>(&acc2[c]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = __float_as_uint(__uint_as_float(acc[c]) + __uint_as_float(acc2[c]));
+      }
+      float4* o4 = reinterpret_cast<float4*>(out + (size_t)(mt * 128 + lq * 32 + lane) * 64 + half * 32);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o4[c] = make_float4(__uint_as_float(acc[4 * c]), __uint_as_float(acc[4 * c + 1]), __uint_as_float(acc[4 * c + 2]), __uint_as_float(acc[4 * c + 3]));
+    }
+  } else if (warp >= 8 && warp < 8 + niss) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = make_idesc(128, CZ * 8, true, true);   // N = the live dZ channels (32 for conv1: half the MMA work)
+      const int me = warp - 8;
+      const int im = me % ni_m, ik = me / ni_m;
+      const uint32_t acc0 = tmem_d + (uint32_t)(ik * nmt * 64);
+      uint32_t s = 0, ph = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        const uint32_t a_tile = base + s * stage_bytes, b_tile = a_tile + (uint32_t)p.a_bytes;
+        for (int ks = ik; ks < KL / 16; ks += ksplit) {
+          const uint64_t bd = make_desc(b_tile + ks * 2048, 0);
+          for (int mt = im; mt < nmt; mt += ni_m) {
+            const int t0 = 2 * mt, t1 = 2 * mt + 1;
+            const uint32_t a0 = t0 < p.ntaps ? a_tile + (uint32_t)p.delta[t0] * 128u + ks * 2048 : ones_smem;
+            const uint32_t a1 = t1 < p.ntaps ? a_tile + (uint32_t)p.delta[t1] * 128u + ks * 2048 : ones_smem;
+            const uint32_t lbo = a1 > a0 ? a1 - a0 : 128u;
+            umma_bf16(acc0 + mt * 64, make_desc(a0, lbo), bd, IDESC, (first && ks == ik) ? 0u : 1u);
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[s]));
+        first = false;
+        if (++s == ST) { s = 0; ph ^= 1; }
+      }
+      umma_commit(smem_u32(&done_bar));
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, tcols);
+}
+
 }  // namespace
 
 // Returns HULC2_ENOTIMPL when the shape does not fit.  On success *grid_out CTAs wrote partial[g][nblk*64][64] with
@@ -500,6 +676,30 @@ int hulc2_conv_halo_wgrad(const void* x, int xpe, const void* dz, int zpe, int F
   if (!partial || partial_bytes < need) return HULC2_ENOTIMPL;
   p.partial = partial;
 
+  static const int variant = getenv("HULC2_WGRAD_HALO") ? atoi(getenv("HULC2_WGRAD_HALO")) : 2;   // 1 = TMA boxes, 2 = cp.async producers
+  if (variant != 1 && ((xpe == 48 && zpe == 32) || (xpe == 64 && zpe == 64))) {
+    HaloWgradCpParams q{};
+    q.g = p; q.x = (const uint8_t*)x; q.dz = (const uint8_t*)dz; q.H = H; q.W = W; q.OH = OH; q.OW = OW;
+    // a producer publishes tile n after issuing tile n + lag; lag = stages - 2 leaves one free slot, so publishing tile n + 1 never
+    // waits behind the MMAs of tile n (with lag = stages - 1 the copy issue and the MMAs of consecutive tiles serialise)
+    q.lag = stages >= 2 ? (stages - 2 < 3 ? stages - 2 : 3) : 0;
+    const int smem = stages * (p.a_bytes + p.b_bytes) + 32 * 128 + 1024;
+    static int configured_cp = 0;
+    if (configured_cp < smem) {
+      if (cudaFuncSetAttribute(conv_halo_wgrad_cp_kernel<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_halo_wgrad_cp_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return HULC2_ENOTIMPL;
+      }
+      configured_cp = smem;
+    }
+    if (xpe == 48) conv_halo_wgrad_cp_kernel<6, 4><<<grid, NT_WGCP, smem, st>>>(q);
+    else conv_halo_wgrad_cp_kernel<8, 8><<<grid, NT_WGCP, smem, st>>>(q);
+    HULC2_CHECK_LAUNCH();
+    *grid_out = grid;
+    *nblk_out = 2 * p.nmt;
+    return HULC2_OK;
+  }
   CUtensorMap tmx, tmz;
   cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   {

@@ -49,7 +49,8 @@ constexpr int N_EPI = EPI_WARPS * 32, N_PROD = PROD_WARPS * 32;
 constexpr int MMA_WARP = EPI_WARPS;
 constexpr int NT = N_EPI + 32 + N_PROD;      // 544 threads
 constexpr int WG_MMA_WARP2 = EPI_WARPS + 1 + PROD_WARPS;  // weight-gradient kernel: second MMA issuer (warp 17)
-constexpr int NT_WG = NT + 32;                // 576 threads
+constexpr int WG_MAX_ISS = 5;                 // weight-gradient kernel: MMA issuer warps = MMA_WARP and WG_MMA_WARP2 .. + 3
+constexpr int NT_WG = NT + 32 * (WG_MAX_ISS - 1);   // 672 threads
 constexpr int MAX_CLS = 4;
 constexpr int MAX_TAB = 160;
 
@@ -368,13 +369,21 @@ __global__ void __launch_bounds__(NT_WG, 1) conv_wgrad_kernel(const __grid_const
   const uint32_t WG_STAGES = (uint32_t)p.stages, WG_LAG = (uint32_t)p.lag;
   const int nbd = p.K / 64;                                               // data blocks
   const int nmt = p.nblk / 2;
-  const uint32_t tcols = nmt * 64 <= 64 ? 64u : (nmt * 64 <= 128 ? 128u : (nmt * 64 <= 256 ? 256u : 512u));
+  // MMA issuers: ONE thread gets a 128 x 64 x 16 MMA with two MN-major operands through only every ~375 cycles (ncu r02: the
+  // producers wait for free ring slots, tensor pipe 19-27 %), so the issue is spread over up to WG_MAX_ISS threads: one per
+  // M-tile of dW^T, and -- when TMEM has room for a second accumulator set (conv1: 2 M-tiles) -- times two halves of a stage's
+  // k-steps, each half accumulating into its own set (added in the dump).
+  const int ksplit = (2 * nmt * 64 <= 512 && 2 * nmt <= WG_MAX_ISS) ? 2 : 1;
+  const int ni_m = nmt < WG_MAX_ISS / ksplit ? nmt : WG_MAX_ISS / ksplit;
+  const int niss = ni_m * ksplit;
+  const uint32_t need_cols = (uint32_t)(ksplit * nmt * 64);
+  const uint32_t tcols = need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u));
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), tcols);
   if (tid == 32) {
-    // two MMA issuers (below) each commit once per stage / at the end
-    for (uint32_t s = 0; s < WG_STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), N_PROD); mbar_init(smem_u32(&empty_bar[s]), 2); }
-    mbar_init(smem_u32(&done_bar), 2);
+    // every MMA issuer (below) commits once per stage / at the end
+    for (uint32_t s = 0; s < WG_STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), N_PROD); mbar_init(smem_u32(&empty_bar[s]), (uint32_t)niss); }
+    mbar_init(smem_u32(&done_bar), (uint32_t)niss);
     mbar_fence_init();
   }
   // zero every stage, then fill the ones block (bf16 1.0 = 0x3F80) -- neither is touched by the producers
@@ -443,24 +452,23 @@ __global__ void __launch_bounds__(NT_WG, 1) conv_wgrad_kernel(const __grid_const
       mbar_arrive(smem_u32(&full_bar[ps]));
       if (++ps == WG_STAGES) ps = 0;
     }
-  } else if (warp == MMA_WARP || warp == WG_MMA_WARP2) {
-    // Two MMA issuer threads split the M-tiles of dW^T (disjoint TMEM columns): one thread issues a tcgen05.mma only every
-    // ~110 cycles, and a 32-pixel stage of conv2 / conv3 needs 10 of them (K = 512 / 576) -- the issue time was the stage time.
-    if (lane == 0) {
+  } else if (warp == MMA_WARP || warp >= WG_MMA_WARP2) {
+    // issuer index: MMA_WARP -> 0, WG_MMA_WARP2 + j -> 1 + j;  issuer = (im, ik): M-tiles mt = im, im + ni_m, ..; k-steps ks = ik, ik + ksplit, ..
+    const int me = warp == MMA_WARP ? 0 : 1 + (warp - WG_MMA_WARP2);
+    if (lane == 0 && me < niss) {
       constexpr uint32_t IDESC = make_idesc(128, 64, true, true);
-      const int half = (nmt + 1) / 2;
-      const int mt0 = warp == MMA_WARP ? 0 : half, mt1 = warp == MMA_WARP ? half : nmt;
+      const int im = me % ni_m, ik = me / ni_m;
+      const uint32_t acc0 = tmem_d + (uint32_t)(ik * nmt * 64);
       uint32_t s = 0, ph = 0;
       for (int st = sbeg; st < send; ++st) {
         mbar_wait(smem_u32(&full_bar[s]), ph);
         tc_fence_after();
         const uint32_t sb = base + s * stage_bytes;
-#pragma unroll
-        for (int ks = 0; ks < WG_KP / 16; ++ks) {
+        for (int ks = ik; ks < WG_KP / 16; ks += ksplit) {
           const uint64_t bd = make_desc(sb + p.nblk * WG_BLK + ks * 2048, WG_BLK);
-          for (int mt = mt0; mt < mt1; ++mt) {
+          for (int mt = im; mt < nmt; mt += ni_m) {
             const uint64_t ad = make_desc(sb + mt * 2 * WG_BLK + ks * 2048, WG_BLK);
-            umma_bf16(tmem_d + mt * 64, ad, bd, IDESC, (st > sbeg || ks > 0) ? 1u : 0u);
+            umma_bf16(acc0 + mt * 64, ad, bd, IDESC, (st > sbeg || ks > ik) ? 1u : 0u);
           }
         }
         umma_commit(smem_u32(&empty_bar[s]));
@@ -481,6 +489,15 @@ __global__ void __launch_bounds__(NT_WG, 1) conv_wgrad_kernel(const __grid_const
       for (int c = 0; c < 32; c += 16)
         tmem_ld16_nowait(tmem_d + ((uint32_t)(lq * 32) << 16) + mt * 64 + half * 32 + c, *reinterpret_cast<uint32_t(*)[16]>(&acc[c]));
       tmem_ld_wait();
+      if (ksplit == 2) {                       // second accumulator set (the other half of every stage's k-steps)
+        uint32_t acc2[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 16)
+          tmem_ld16_nowait(tmem_d + ((uint32_t)(lq * 32) << 16) + (nmt + mt) * 64 + half * 32 + c, *reinterpret_cast<uint32_t(*)[16]>(&acc2[c]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = __float_as_uint(__uint_as_float(acc[c]) + __uint_as_float(acc2[c]));
+      }
       float4* o4 = reinterpret_cast<float4*>(out + (size_t)(mt * 128 + lq * 32 + lane) * 64 + half * 32);
 #pragma unroll
       for (int c = 0; c < 8; ++c) o4[c] = make_float4(__uint_as_float(acc[4 * c]), __uint_as_float(acc[4 * c + 1]), __uint_as_float(acc[4 * c + 2]), __uint_as_float(acc[4 * c + 3]));
@@ -542,6 +559,9 @@ __global__ void pack_frames_kernel(const float* __restrict__ x, uint8_t* __restr
     const float4 hi = *reinterpret_cast<const float4*>(&rows[(ci * 4 + a + 1) * wu + 4 * J]);
     out[q] = make_uint4(pack_bf16x2(lo.x, lo.y), pack_bf16x2(lo.z, lo.w), pack_bf16x2(hi.x, hi.y), pack_bf16x2(hi.z, hi.w));
   }
+  // zero the 128 bytes of slack behind the last pixel (read through conv1's 64-element rows; 0-weight x NaN would be NaN)
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 8)
+    reinterpret_cast<uint4*>(xs + (size_t)gridDim.x * W4 * c16 * 2)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // mode 0: wp[co][(kh,kw,ci)] = w[co][ci][kh][kw];  mode 1: packed-frames order for a [Cout, Cin, 4KH, 4KW] weight:

@@ -97,6 +97,10 @@ __global__ void __launch_bounds__(256) frames_u8_pack_kernel(const uint8_t* __re
     }
     out[q] = make_uint4(bf16x2(v[0], v[1]), bf16x2(v[2], v[3]), bf16x2(v[4], v[5]), bf16x2(v[6], v[7]));
   }
+  // The 128 bytes of slack behind the last pixel: conv1's halo path reads every 48-channel pixel as a 64-element row, so the
+  // last pixel's row ends in the slack.  Those positions meet zero weights, but 0 x NaN = NaN: they must hold finite values.
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 8)
+    reinterpret_cast<uint4*>(xs + (size_t)gridDim.x / nseg * H4 * W4 * c16 * 2)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // uint8 [*,H,W,C] -> fp32 NCHW [F,C,H,W] (the reference batch contract; fp32 parity path).  One block per (frame, row).

@@ -141,6 +141,8 @@ int hulc2_nchw_to_nhwc_bf16(const float* src, void* dst, int F, int HW, int C, c
  * shift  : int32 [F,2] = (dx,dy) per output frame, each in [-pad,pad] (the reference's randint draw minus pad), null = none:
  *          out[y,x] = in[clamp(y+dy,0,H-1), clamp(x+dx,0,W-1)];  value = ((u8/255) - 0.5)/0.5 in fp32, reference op order.
  * pack_bf16 writes the packed-frames layout of hulc2_pack_frames_bf16 directly; to_f32 writes fp32 NCHW [F,C,H,W].
+ * Both pack functions need 128 bytes of slack behind the last packed pixel of `xs` and ZERO them (conv1's halo path reads
+ * 48-channel pixels as 64-element rows: the last row ends in the slack, where only finite values are harmless).
  * window_gather_f32: out[b,t,:] = store[win_start[b]+t, :] (fp32 [N,D]) for t < win_len[b]; padded steps by mode:
  *          0 repeat the last valid row, 1 zeros, 2 zeros except the last component which repeats (relative actions). */
 int hulc2_frames_u8_pack_bf16(const void* store, const long long* win_start, const int* win_len, const int* shift, void* xs,
@@ -277,21 +279,29 @@ int hulc2_rnn_relu_fwd(const float* pre, const float* w_hh, const float* h0, flo
 int hulc2_rnn_relu_bwd(float* dh_inout, const float* w_hh, const float* h, float* dh0, int S, int B, int H,
                        int precision, void* workspace, long long workspace_bytes, hulc2_stream_t stream);
 /* precision 1 runs all S steps in ONE persistent tcgen05 kernel when the shape fits, tried in this order:
+ *  (a') TMA-fed cluster split-K kernel (rnn_cluster2_sm100.cu): as (a) with workspace >= 2*(S+1)*B*H + 1024 bytes; the state
+ *       slice of a step arrives as TMA boxes, CTAs publish per warp (HULC2_RNN_V1=1 in the environment skips it);
  *  (a) cluster split-K kernel (rnn_cluster_sm100.cu): B <= 128, H % 512 == 0, H <= 2048, workspace >= 2*S*B*H + 1024
  *      bytes, H/16 CTAs in clusters of 8 or 4 all co-resident -- W_hh block resident in shared memory, partial sums reduced
  *      through distributed shared memory, per-K-slice release/acquire flags between steps;
  *  (b) 1-D persistent kernel (rnn_persistent_sm100.cu): B <= 128, H % 64 == 0, H/16 <= #SMs, workspace >= 2*S*B*H + 256;
  *  otherwise one GEMM per step. */
-/* test / benchmark hook: 0 = automatic (default), 1 = skip (a), 2 = skip (a) and (b). Returns the previous value. */
+/* test / benchmark hook: 0 = automatic (default), -1 = skip (a'), 1 = skip (a') and (a), 2 = skip (a'), (a) and (b).
+ * Returns the previous value. */
 int hulc2_rnn_select_kernel(int which);
 /* number of cluster_size-CTA (8 or 4) clusters of kernel (a) that can be co-resident on the current device; (a) runs with
  * clusters of 8 when H/128 of them fit, else with clusters of 4 when H/64 fit (a 148-SM B200 reports 15 clusters of 8) */
 int hulc2_rnn_cluster_capacity(int cluster_size);
 /* The persistent kernels (a)/(b) are launched cooperatively (every CTA / cluster co-resident or the launch is refused and the
  * next kernel in the list runs).  Should a step-flag wait still give up, the kernel flags the error on the device and finishes
- * (no trap, the context survives).  This reads the flags -- SYNCHRONISES the device: bit 0 = kernel (a), bit 1 = kernel (b);
+ * (no trap, the context survives).  This reads the flags -- SYNCHRONISES the device: bit 0 = kernel (a), bit 1 = kernel (b),
+ * bit 2 = kernel (a');
  * clear != 0 resets them; -1 on a CUDA error. */
 int hulc2_rnn_device_error(int clear);
+/* Which kernel served the last hulc2_rnn_relu_{fwd,bwd} call with precision 1 (bits 0-7: 1 = (a'), 2 = (a), 3 = (b), 4 = one GEMM per
+ * step) and, in bits 8-15, why (a') last declined (0 = it ran; 1 shape, 2 workspace, 3 alignment, 4 no driver entry point,
+ * 5 clusters not co-resident, 6 tensor map, 7 launch refused).  Tests use it to make sure no silent fallback is being measured. */
+int hulc2_rnn_last_path(void);
 
 /* ------------------------------------------------------------------ gated recurrence cells (decoders/utils/rnn.py:17-36)
  * One step of nn.GRU (gate order r,z,n) / nn.LSTM (i,f,g,o); the contractions are hulc2_gemm calls, these are the

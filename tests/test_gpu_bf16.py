@@ -277,7 +277,7 @@ def rnn_kernel_reset():
     _lib.load_library().hulc2_rnn_select_kernel(0)
 
 
-@pytest.mark.parametrize("kernel", [0, 1], ids=["cluster", "persistent1d"])
+@pytest.mark.parametrize("kernel", [0, -1, 1], ids=["cluster_tma", "cluster", "persistent1d"])
 @pytest.mark.parametrize("B,S,H,with_h0", [(64, 32, 2048, False), (128, 32, 2048, False), (5, 3, 2048, True), (128, 4, 1024, True),
                                            (33, 5, 512, True), (16, 5, 256, True)])
 def test_persistent_rnn_matches_step_loop(B, S, H, with_h0, kernel, rnn_kernel_reset):
@@ -299,6 +299,12 @@ def test_persistent_rnn_matches_step_loop(B, S, H, with_h0, kernel, rnn_kernel_r
         call("hulc2_rnn_relu_fwd", pre.data_ptr(), w.data_ptr(), None if h0 is None else h0.data_ptr(), h.data_ptr(), S, B, H, prec, ws.data_ptr(), ws.numel())
         outs.append(h)
     torch.cuda.synchronize()
+    # no silent fallback: the kernel generation under test really served the call when the shape fits it
+    path = _lib.load_library().hulc2_rnn_last_path()
+    if H % 512 == 0 and kernel in (0, -1):
+        assert path & 255 == (1 if kernel == 0 else 2), f"expected the cluster kernel, got path {path & 255} (reject {path >> 8})"
+    elif kernel == 1 or H % 512:
+        assert path & 255 == 3, path
     assert_close(outs[1], outs[0], 2e-2, "forward states")
     # ... and against plain PyTorch fp32 (nn.RNN relu recurrence, decoders/utils/rnn.py:5-14), not only this library's own kernel
     hp = h0 if h0 is not None else torch.zeros(B, H, device=dev)

@@ -81,7 +81,11 @@ def test_conv1_over_packed_frames(Fr, H, W):
     torch.cuda.synchronize()
     ref = F.relu(F.conv2d(_bf(x), _bf(w), b, stride=4))
     assert y.shape == (Fr, ref.shape[2], ref.shape[3], 32)
-    assert_close(_nchw(y.float().cpu()), ref, 1e-2, "conv1 fwd")
+    got = _nchw(y.float().cpu())
+    err = (got - ref).abs()
+    bad = (err > 1e-2 * ref.abs().max()).nonzero()
+    where = f"{len(bad)} elements off, first at (f, c, y, x) = {bad[:4].tolist()}, got {[float(got[tuple(i)]) for i in bad[:4]]} want {[float(ref[tuple(i)]) for i in bad[:4]]}"
+    assert_close(got, ref, 1e-2, "conv1 fwd: " + where)
 
 
 @pytest.mark.parametrize("Fr,C,H,W,Cout,k,s", [(7, 32, 49, 49, 64, 4, 2), (7, 64, 23, 23, 64, 3, 1), (3, 32, 20, 20, 64, 4, 2),

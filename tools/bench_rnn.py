@@ -20,7 +20,8 @@ h = torch.empty(S, B, H, device=dev)
 flops = 2.0 * S * B * H * H
 stream_bytes = S * (H * H * 2 + 3 * B * H * 4)
 ref = None
-for which, name in ((1, "1-D persistent (rnn_persistent_sm100.cu)"), (0, "cluster split-K (rnn_cluster_sm100.cu)")):
+for which, name in ((1, "1-D persistent (rnn_persistent_sm100.cu)"), (-1, "cluster split-K (rnn_cluster_sm100.cu)"),
+                    (0, "cluster split-K, TMA-fed (rnn_cluster2_sm100.cu)")):
     lib.hulc2_rnn_select_kernel(which)
     res = {}
     for label in ("fwd", "bwd"):
@@ -49,6 +50,8 @@ for which, name in ((1, "1-D persistent (rnn_persistent_sm100.cu)"), (0, "cluste
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / reps * 1e3 - (c0.elapsed_time(c1) / reps * 1e3 if label == "bwd" else 0.0)
         res[label] = us
+    path = lib.hulc2_rnn_last_path()
+    name += f" [path {path & 255}, v2 reject {path >> 8}]"
     out = h.clone()
     if ref is None:
         ref = out
