@@ -114,6 +114,21 @@ class DeviceEpisodeStore:
             prop = (prop - dv(robot_mean, torch.float32)) / std
         self.proprio = torch.cat([prop[:, a:b] for a, b in proprio_keep], dim=1).contiguous()
 
+    def write_frames(self, start: int, rgb: Dict[str, torch.Tensor], rel_actions=None, robot_obs=None, scene_obs=None) -> None:
+        """Streaming ingestion: overwrite store rows ``[start, start + n)`` with new steps (uint8 HWC frames per camera and,
+        optionally, their per-step vectors) from (pinned) host memory, asynchronously on the CURRENT stream.  With a ring of
+        frames resident in HBM a training step only has to move the frames that are new since the previous step across PCIe
+        -- consecutive windows of play data share 31 of their 32 frames -- while batches stay index descriptors."""
+        n = None
+        for k, v in rgb.items():
+            n = v.shape[0] if n is None else n
+            if start < 0 or start + v.shape[0] > self.N or v.shape[1:] != self.rgb[k].shape[1:] or v.dtype != torch.uint8:
+                raise ValueError(f"write_frames: camera '{k}' rows [{start}, {start + v.shape[0]}) do not fit the store")
+            self.rgb[k][start : start + v.shape[0]].copy_(v, non_blocking=True)
+        for name, v in (("rel_actions", rel_actions), ("robot_obs", robot_obs), ("scene_obs", scene_obs)):
+            if v is not None:
+                getattr(self, name)[start : start + v.shape[0]].copy_(v, non_blocking=True)
+
     def gather(self, table: torch.Tensor, win_start: torch.Tensor, win_len: Optional[torch.Tensor], S: int, mode: int) -> torch.Tensor:
         B, D = win_start.numel(), table.shape[1]
         out = torch.empty(B, S, D, device=self.device, dtype=torch.float32)
@@ -139,6 +154,23 @@ class DeviceEpisodeStore:
         if self.scene_obs is not None:
             d["state_info"]["scene_obs"] = self.gather(self.scene_obs, win_start, win_len, S, PAD_REPEAT)
         return d
+
+
+    def batch_from_descriptors(self, desc: Dict[str, dict], S: int) -> Dict[str, dict]:
+        """Device-side collate: ``desc[mod] = {"win_start" [B] int64, optional "win_len" [B] int32, optional
+        "shift_<camera>" [B,S,2] int32, and for language modalities "lang" [B,384] + "use_for_aux_lang_loss" [B] bool}`` (all
+        device tensors) -> the SURVEY 8b batch dict: cameras as ``ops.U8Frames`` windows of the resident store, per-step
+        vectors gathered and padded by ``hulc2_window_gather_f32``.  Only library kernels run, so a trainer can capture it
+        together with the step (``PolicyTrainer(collate=...)``) and replay it on refreshed descriptors."""
+        out = {}
+        for mod, d in desc.items():
+            shifts = {k[len("shift_"):]: v for k, v in d.items() if k.startswith("shift_")}
+            b = self.window_batch(d["win_start"], d.get("win_len"), S, shifts)
+            for k in ("lang", "use_for_aux_lang_loss"):
+                if k in d:
+                    b[k] = d[k]
+            out[mod] = b
+        return out
 
 
 # ----------------------------------------------------------------------------- loaders

@@ -58,8 +58,12 @@ def _zip_copy(dst, src, non_blocking=True):
 
 class PolicyTrainer:
     def __init__(self, model, bucket_mb: float = 25.0, use_graph: bool = False, graph_warmup: int = 2,
-                 device_counters: Optional[bool] = None):
+                 device_counters: Optional[bool] = None, collate=None):
         self.model = model
+        # collate: optional device-side batch builder run INSIDE the step (and therefore inside the captured graph): maps
+        # the tensors handed to train_step (e.g. window descriptors: starts, lengths, augmentation draws) to the model's batch
+        # dict (datamodule.DeviceEpisodeStore.batch_from_descriptors gathers windows out of a frame store resident in HBM)
+        self.collate = collate
         opt_cfg = model.configure_optimizers()
         self.optimizer = opt_cfg["optimizer"]
         sched = opt_cfg.get("lr_scheduler")
@@ -95,6 +99,8 @@ class PolicyTrainer:
     def _step_body(self, batch: Dict[str, dict], batch_idx: int) -> torch.Tensor:
         noise.begin_step() if self.device_counters else None
         self.optimizer.zero_grad()
+        if self.collate is not None:
+            batch = self.collate(batch)
         loss = self.model.training_step(batch, batch_idx)
         if self.reducer is not None:
             self.reducer.prepare()
@@ -206,13 +212,17 @@ class PolicyTrainer:
         return float(loss)  # device->host read of the step's result
 
     # ------------------------------------------------------------------ pipelined host loop (what Trainer.fit does)
-    def fit_host(self, host_batches: Iterable[Dict[str, dict]]) -> List[float]:
+    def fit_host(self, host_batches: Iterable[Dict[str, dict]], pre_copy=None) -> List[float]:
         """Trains on an iterable of PINNED host batches and returns every step's loss (read back to the host).
 
         Software pipeline over three streams: the H2D copy of batch i+1 (copy stream, into one of two device staging
         buffers) runs while the trainer stream computes step i; the loss of step i is copied to a pinned slot right
         behind the step and read by the host one step later, so neither PCIe nor the host read stalls the kernels.
-        Every step still moves its own inputs host->device and its own result device->host."""
+        Every step still moves its own inputs host->device and its own result device->host.
+
+        ``pre_copy(i)``: optional callable run on the copy stream right before batch i's copy -- the hook through which a
+        device-resident episode store (``datamodule.DeviceEpisodeStore.write_frames``) ingests the frames that are new in step
+        i, so that batches only carry window descriptors (``ops.U8Frames``) instead of 32 frames per window."""
         if self.stream is None:
             return [self.train_step_from_host(b, i) for i, b in enumerate(host_batches)]
         dev = self.device
@@ -234,6 +244,8 @@ class PolicyTrainer:
             with torch.cuda.stream(copy):
                 if i >= 2:
                     copy.wait_event(free[i % 2])          # the step that consumed this staging buffer has read it
+                if pre_copy is not None:
+                    pre_copy(i)
                 _zip_copy(self._staging[i % 2], hb)
                 ready[i % 2].record(copy)
 

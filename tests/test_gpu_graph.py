@@ -256,3 +256,63 @@ def test_validation_graph_replay_equals_eager(precision):
             assert abs(lg[k] - le[k]) <= 1e-6 * max(abs(le[k]), 1e-3), f"call {i}: {k}: {lg[k]} vs {le[k]}"
     # different calls really saw different noise and different batches
     assert not torch.equal(g[0][0]["sampled_plan_pp_vis"], g[1][0]["sampled_plan_pp_vis"])
+
+
+def test_captured_collate_from_resident_store_equals_eager_batches():
+    """PolicyTrainer(collate=DeviceEpisodeStore.batch_from_descriptors): the window gather out of the HBM-resident frame store
+    is captured together with the step; fit_host copies only descriptors (+ frames ingested through pre_copy).  Must equal
+    eager steps on the batches the same descriptors describe, including after new frames were written into the ring."""
+    from hulc2_b200.datamodule import synthetic_store
+    from hulc2_b200.synthetic import tree_map
+
+    B, S, N = 2, 32, 512
+    g = torch.Generator().manual_seed(5)
+
+    def make_store():
+        return synthetic_store(N, device=DEV, seed=9)
+
+    fresh = {"rgb_static": torch.randint(0, 256, (8, 200, 200, 3), generator=g, dtype=torch.uint8).pin_memory(),
+             "rgb_gripper": torch.randint(0, 256, (8, 84, 84, 3), generator=g, dtype=torch.uint8).pin_memory()}
+
+    def desc(i):
+        d = {}
+        for mod in ("vis", "lang"):
+            dd = {"win_start": torch.randint(N // 2, N - S, (B,), generator=g), "win_len": torch.randint(20, S + 1, (B,), generator=g, dtype=torch.int32),
+                  "shift_rgb_static": torch.randint(-10, 11, (B, S, 2), generator=g, dtype=torch.int32),
+                  "shift_rgb_gripper": torch.randint(-4, 5, (B, S, 2), generator=g, dtype=torch.int32)}
+            if mod == "lang":
+                dd["lang"] = torch.randn(B, 384, generator=g)
+                dd["use_for_aux_lang_loss"] = torch.tensor([True, False])
+            d[mod] = dd
+        # one window covers the rows the ingest hook (re)writes for THIS step; the writes of consecutive steps are 64 rows apart and
+        # every other window lies in the upper half of the ring, so an ingest never touches rows the step still in flight reads
+        d["vis"]["win_start"][0] = 64 * (i % 4)
+        return tree_map(lambda t: t.pin_memory(), d)
+
+    descs = [desc(i) for i in range(5)]
+
+    def run(graph):
+        ops.set_precision("bf16")
+        noise.manual_seed(99)
+        noise.epoch_tensor(torch.device(DEV)).zero_()
+        store = make_store()
+        m = build_model("calvin", dropout_p=0.1, hidden_size=256).to(DEV).train()
+        if graph:
+            tr = PolicyTrainer(m, use_graph=True, collate=lambda d: store.batch_from_descriptors(d, S))
+            losses = tr.fit_host(descs, pre_copy=lambda i: store.write_frames(64 * (i % 4), fresh))
+            assert tr.replays == 3
+        else:
+            tr = PolicyTrainer(m, use_graph=False, device_counters=True)
+            losses = []
+            for i, d in enumerate(descs):
+                store.write_frames(64 * (i % 4), fresh)
+                batch = store.batch_from_descriptors(to_device(d, DEV), S)
+                losses.append(float(tr.train_step(batch, i)))
+        torch.cuda.synchronize()
+        return losses, _params(m)
+
+    lg, pg = run(True)
+    le, pe = run(False)
+    for k, (a, b) in enumerate(zip(lg, le), 1):
+        assert abs(a - b) <= 1e-4 * abs(b), f"step {k}: {a} (captured collate) vs {b} (eager batches); {lg} vs {le}"
+    _compare_params(pg, pe, 5, "captured collate vs eager batches", frac_tol=0.15)
