@@ -36,7 +36,6 @@ struct TmaParams {
   int ktiles, kt_per_split, splits, stages;
   Epilogue E;
   float* partial;               // [splits, M, N] when splits > 1
-  int counter_base;             // first split-K tile counter of this launch (g_splitk_counters)
   __nv_bfloat16* C16;           // optional bf16 mirror of the output (same row addressing with ld16)
   long long ld16;
   int vec;                      // 16-byte epilogue accesses are legal for every pointer involved
@@ -61,13 +60,6 @@ __device__ __forceinline__ void store_scalar(const TmaParams& p, float acc, int 
   if (p.C16) p.C16[(long long)m * p.ld16 + n] = __float2bfloat16_rn(v);
 }
 
-// Split-K without a second kernel: every CTA of an output tile writes its partial tile, then takes a ticket on the tile's
-// counter; the CTA that draws the last ticket sums all partials (fixed order z = 0 .. splits-1: deterministic) and runs the
-// epilogue.  The counter is reset by that CTA, so the array stays zero between launches; launches rotate through 16 disjoint
-// counter ranges so that two GEMMs in flight on different streams do not share tickets.
-constexpr int SPLITK_TILES = 128, SPLITK_RANGES = 16;
-__device__ unsigned int g_splitk_counters[SPLITK_TILES * SPLITK_RANGES];
-
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, const TmaParams p) {
@@ -76,7 +68,6 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ uint32_t splitk_last;
   constexpr uint32_t B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -239,48 +230,6 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
         }
       }
     }
-    if (p.splits > 1) {
-      // ticket: the 128 epilogue threads have written this CTA's partial tile
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp == 2 && lane == 0) {
-        unsigned int* ctr = g_splitk_counters + p.counter_base + blockIdx.y * gridDim.x + blockIdx.x;
-        const unsigned int old = atomicAdd(ctr, 1u);
-        const bool last = old == (unsigned int)(p.splits - 1);
-        if (last) *ctr = 0u;                     // nobody else touches this counter before the next launch
-        splitk_last = last ? 1u : 0u;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (splitk_last && mvalid) {
-        __threadfence();
-        const long long total = (long long)p.M * p.N;
-        const float* prow = p.partial + (long long)m * p.N;
-        for (int c = 0; c < BN; c += 4) {
-          const int n = n0 + c;
-          if (n >= p.N) break;
-          if (p.vec && n + 4 <= p.N) {
-            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int z = 0; z < p.splits; ++z) {
-              const float4 t = __ldcg(reinterpret_cast<const float4*>(prow + (long long)z * total + n));
-              sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
-            }
-            float v[4] = {E.alpha * sum.x, E.alpha * sum.y, E.alpha * sum.z, E.alpha * sum.w};
-            if (E.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(E.bias + n)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
-            if (E.accumulate) { const float4 t = *reinterpret_cast<const float4*>(E.C + crow + n); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
-            *reinterpret_cast<float4*>(E.C + crow + n) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-            for (int e = 0; e < 4 && n + e < p.N; ++e) {
-              float sum = 0.f;
-              for (int z = 0; z < p.splits; ++z) sum += __ldcg(prow + (long long)z * total + n + e);
-              float v = E.alpha * sum;
-              if (E.bias) v += E.bias[n + e];
-              if (E.accumulate) v += E.C[crow + n + e];
-              E.C[crow + n + e] = v;
-            }
-          }
-        }
-      }
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -331,7 +280,12 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TmaParams& p, int
   kern<<<grid, NT, smem, st>>>(ta, tb, p);
   HULC2_CHECK_LAUNCH();
   ++g_tma_gemms;
-  if (p.splits > 1 && p.C16) { hulc2_set_error("gemm_tma: internal: bf16 mirror with split-K"); return HULC2_EINVAL; }
+  if (p.splits > 1) {
+    long long total = (long long)p.M * p.N;
+    splitk_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(p.partial, p.splits, p.M, p.N, p.E);
+    HULC2_CHECK_LAUNCH();
+    if (p.C16) { hulc2_set_error("gemm_tma: internal: bf16 mirror with split-K"); return HULC2_EINVAL; }
+  }
   return HULC2_OK;
 }
 
@@ -383,12 +337,10 @@ int hulc2_gemm_tma_impl(const hulc2_gemm_args* a, cudaStream_t st) {
     int s = want < maxs ? want : maxs;
     const long long per = (long long)a->M * a->N * (long long)sizeof(float);
     while (s > 1 && (long long)s * per > a->workspace_bytes) --s;
-    if (s > 1 && tiles <= SPLITK_TILES) {
+    if (s > 1) {
       p.kt_per_split = hulc2_cdiv(p.ktiles, s);
       p.splits = hulc2_cdiv(p.ktiles, p.kt_per_split);
       p.partial = (float*)a->workspace;
-      static unsigned int seq = 0;                 // rotate through the counter ranges (see g_splitk_counters)
-      p.counter_base = (int)((seq++ % SPLITK_RANGES) * SPLITK_TILES);
     }
   }
   const int stage_bytes = (int)A_BYTES + BN * 128;
