@@ -480,8 +480,8 @@ __device__ __forceinline__ void cp_wait_dyn(int n) {
   }
 }
 
-constexpr int WGCP_MAX_ISS = 6;
-constexpr int NT_WGCP = 256 + 32 * WGCP_MAX_ISS;     // 8 producer / dump warps + 6 MMA issuer warps
+constexpr int WGCP_MAX_ISS = 12;
+constexpr int NT_WGCP = 256 + 32 * WGCP_MAX_ISS;     // 8 producer / dump warps + up to 12 MMA issuer warps
 
 template <int CX, int CZ>      // 16-byte chunks per source / dZ pixel (6, 4: conv1 over packed frames; 8, 8: conv3)
 __global__ void __launch_bounds__(NT_WGCP, 1) conv_halo_wgrad_cp_kernel(const __grid_constant__ HaloWgradCpParams q) {
@@ -496,10 +496,13 @@ __global__ void __launch_bounds__(NT_WGCP, 1) conv_halo_wgrad_cp_kernel(const __
   const uint32_t ones_smem = base + ST * stage_bytes;           // 32 rows x 128 B of bf16 1.0
   const int nmt = p.nmt;
   // issuers: one per M-tile, times two halves of a tile's k-steps when TMEM holds a second accumulator set (added in the dump)
-  const int ksplit = (2 * nmt * 64 <= 512 && 2 * nmt <= WGCP_MAX_ISS) ? 2 : 1;
+  // (an accumulator is NACC = the live dZ channels wide: 32 columns for conv1, so four sets of its 3 M-tiles fit in 384 columns)
+  constexpr int NACC = CZ * 8;
+  int ksplit = 1;
+  while (2 * ksplit * nmt * NACC <= 512 && 2 * ksplit * nmt <= WGCP_MAX_ISS && 2 * ksplit <= 4 && 2 * ksplit <= (p.BH * p.PW) / 16) ksplit *= 2;
   const int ni_m = nmt < WGCP_MAX_ISS / ksplit ? nmt : WGCP_MAX_ISS / ksplit;
   const int niss = ni_m * ksplit;
-  const uint32_t need_cols = (uint32_t)(ksplit * nmt * 64);
+  const uint32_t need_cols = (uint32_t)(ksplit * nmt * NACC);
   const uint32_t tcols = need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u));
   constexpr int NPROD = 256;
 
@@ -524,36 +527,51 @@ __global__ void __launch_bounds__(NT_WGCP, 1) conv_halo_wgrad_cp_kernel(const __
 
   if (warp < 8) {
     // ---------------------------------------------------------------- producers (then dump, below)
-    uint32_t s = 0, ph = 1, ps = 0;
-    int inflight = 0;
+    // The (row, chunk) positions a thread copies are the same for every tile: their shared-memory offsets and their global
+    // offsets relative to the tile's first source row are computed ONCE (ncu r02: with the index arithmetic inside the tile loop the
+    // producers were issue-bound -- 51 % of the issue slots, MMA issuers starving); per tile a copy is one 64-bit add + cp.async.
+    // Positions right of the frame (j >= W) are never copied: they stay zero from the initial fill.
+    constexpr int MAXS = CX == 6 ? 8 : 16;       // copies per thread and tile and operand (conv1 tiles: 7 + 4)
+    uint32_t xg[MAXS], xs_[MAXS], zg[MAXS], zs_[MAXS];      // global byte offset | smem offset (low 17 bits) + tile row (high bits)
     const int xrows = p.BH + p.KH - 1;
     const long long xrow_b = (long long)q.W * CX * 16, xfr_b = (long long)q.H * xrow_b;
     const long long zrow_b = (long long)q.OW * CZ * 16, zfr_b = (long long)q.OH * zrow_b;
+    const int nxc = xrows * p.PW * CX, nzc = p.BH * p.PW * CZ;
+#pragma unroll
+    for (int k = 0; k < MAXS; ++k) {
+      const int c = tid + NPROD * k;
+      xg[k] = 0xffffffffu; zg[k] = 0xffffffffu; xs_[k] = 0; zs_[k] = 0;
+      if (c < nxc) {
+        const int i = c / (p.PW * CX), idx = c - i * (p.PW * CX), j = idx / CX, ch = idx - j * CX;
+        if (j < q.W) { xg[k] = (uint32_t)(i * xrow_b + idx * 16); xs_[k] = swz128(i * p.PW + j, ch) | ((uint32_t)i << 17); }
+      }
+      if (c < nzc) {
+        const int i = c / (p.PW * CZ), idx = c - i * (p.PW * CZ), j = idx / CZ, ch = idx - j * CZ;
+        if (j < q.OW) { zg[k] = (uint32_t)(i * zrow_b + idx * 16); zs_[k] = swz128(i * p.PW + j, ch) | ((uint32_t)i << 17); }
+      }
+    }
+    uint32_t s = 0, ph = 1, ps = 0;
+    int inflight = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int f = tile / p.tiles_per_frame, ti = tile - f * p.tiles_per_frame;
       const int y0 = ti * p.BH;
       mbar_wait(smem_u32(&empty_bar[s]), ph);
       const uint32_t a_tile = base + s * stage_bytes, b_tile = a_tile + (uint32_t)p.a_bytes;
-      const uint8_t* xf = q.x + f * xfr_b;
-      for (int i = 0; i < xrows; ++i) {
-        const int y = y0 + i;
-        const uint8_t* xr = xf + (long long)y * xrow_b;
-        const bool yok = y < q.H;
-        for (int idx = tid; idx < p.PW * CX; idx += NPROD) {
-          const int j = idx / CX, c = idx - j * CX;
-          const bool ok = yok && j < q.W;
-          cp_async16(a_tile + swz128(i * p.PW + j, c), ok ? xr + idx * 16 : q.x, ok ? 16u : 0u);
+      const uint8_t* xb = q.x + f * xfr_b + (long long)y0 * xrow_b;
+      const uint8_t* zb = q.dz + f * zfr_b + (long long)y0 * zrow_b;
+      const int xlim = q.H - y0, zlim = q.OH - y0;          // tile rows i >= lim lie below the frame: zero-filled
+#pragma unroll
+      for (int k = 0; k < MAXS; ++k) {
+        if (xg[k] != 0xffffffffu) {
+          const bool ok = (int)(xs_[k] >> 17) < xlim;
+          cp_async16(a_tile + (xs_[k] & 0x1ffffu), ok ? xb + xg[k] : q.x, ok ? 16u : 0u);
         }
       }
-      const uint8_t* zf = q.dz + f * zfr_b;
-      for (int i = 0; i < p.BH; ++i) {
-        const int y = y0 + i;
-        const uint8_t* zr = zf + (long long)y * zrow_b;
-        const bool yok = y < q.OH;
-        for (int idx = tid; idx < p.PW * CZ; idx += NPROD) {
-          const int j = idx / CZ, c = idx - j * CZ;
-          const bool ok = yok && j < q.OW;
-          cp_async16(b_tile + swz128(i * p.PW + j, c), ok ? zr + idx * 16 : q.dz, ok ? 16u : 0u);
+#pragma unroll
+      for (int k = 0; k < MAXS; ++k) {
+        if (zg[k] != 0xffffffffu) {
+          const bool ok = (int)(zs_[k] >> 17) < zlim;
+          cp_async16(b_tile + (zs_[k] & 0x1ffffu), ok ? zb + zg[k] : q.dz, ok ? 16u : 0u);
         }
       }
       cp_async_commit();
@@ -578,31 +596,30 @@ __global__ void __launch_bounds__(NT_WGCP, 1) conv_halo_wgrad_cp_kernel(const __
     mbar_wait_relaxed(smem_u32(&done_bar), 0);
     tc_fence_after();
     float* out = p.partial + (size_t)blockIdx.x * nmt * 128 * 64;
+    constexpr int HC = NACC / 2;                       // columns per warp half: 16 or 32
     for (int mt = 0; mt < nmt; ++mt) {
-      uint32_t acc[32];
+      float acc[HC];
 #pragma unroll
-      for (int c = 0; c < 32; c += 16)
-        tmem_ld16_nowait(tmem_d + ((uint32_t)(lq * 32) << 16) + mt * 64 + half * 32 + c, *reinterpret_cast<uint32_t(*)[16]>(&acc[c]));
-      tmem_ld_wait();
-      if (ksplit == 2) {
-        uint32_t acc2[32];
+      for (int c = 0; c < HC; ++c) acc[c] = 0.f;
+      for (int a = 0; a < ksplit; ++a) {               // add the accumulator sets of the k-step groups
+        uint32_t r[HC];
 #pragma unroll
-        for (int c = 0; c < 32; c += 16)
-          tmem_ld16_nowait(tmem_d + ((uint32_t)(lq * 32) << 16) + (nmt + mt) * 64 + half * 32 + c, *reinterpret_cast<uint32_t(*)[16]>(&acc2[c]));
+        for (int c = 0; c < HC; c += 16)
+          tmem_ld16_nowait(tmem_d + ((uint32_t)(lq * 32) << 16) + (a * nmt + mt) * NACC + half * HC + c, *reinterpret_cast<uint32_t(*)[16]>(&r[c]));
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = __float_as_uint(__uint_as_float(acc[c]) + __uint_as_float(acc2[c]));
+        for (int c = 0; c < HC; ++c) acc[c] += __uint_as_float(r[c]);
       }
-      float4* o4 = reinterpret_cast<float4*>(out + (size_t)(mt * 128 + lq * 32 + lane) * 64 + half * 32);
+      float4* o4 = reinterpret_cast<float4*>(out + (size_t)(mt * 128 + lq * 32 + lane) * 64 + half * HC);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) o4[c] = make_float4(__uint_as_float(acc[4 * c]), __uint_as_float(acc[4 * c + 1]), __uint_as_float(acc[4 * c + 2]), __uint_as_float(acc[4 * c + 3]));
+      for (int c = 0; c < HC / 4; ++c) o4[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
     }
   } else if (warp >= 8 && warp < 8 + niss) {
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc(128, CZ * 8, true, true);   // N = the live dZ channels (32 for conv1: half the MMA work)
       const int me = warp - 8;
       const int im = me % ni_m, ik = me / ni_m;
-      const uint32_t acc0 = tmem_d + (uint32_t)(ik * nmt * 64);
+      const uint32_t acc0 = tmem_d + (uint32_t)(ik * nmt * NACC);
       uint32_t s = 0, ph = 0;
       bool first = true;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -616,7 +633,7 @@ __global__ void __launch_bounds__(NT_WGCP, 1) conv_halo_wgrad_cp_kernel(const __
             const uint32_t a0 = t0 < p.ntaps ? a_tile + (uint32_t)p.delta[t0] * 128u + ks * 2048 : ones_smem;
             const uint32_t a1 = t1 < p.ntaps ? a_tile + (uint32_t)p.delta[t1] * 128u + ks * 2048 : ones_smem;
             const uint32_t lbo = a1 > a0 ? a1 - a0 : 128u;
-            umma_bf16(acc0 + mt * 64, make_desc(a0, lbo), bd, IDESC, (first && ks == ik) ? 0u : 1u);
+            umma_bf16(acc0 + mt * NACC, make_desc(a0, lbo), bd, IDESC, (first && ks == ik) ? 0u : 1u);
           }
         }
         umma_commit(smem_u32(&empty_bar[s]));
@@ -676,8 +693,11 @@ int hulc2_conv_halo_wgrad(const void* x, int xpe, const void* dz, int zpe, int F
   if (!partial || partial_bytes < need) return HULC2_ENOTIMPL;
   p.partial = partial;
 
-  static const int variant = getenv("HULC2_WGRAD_HALO") ? atoi(getenv("HULC2_WGRAD_HALO")) : 2;   // 1 = TMA boxes, 2 = cp.async producers
+  static const int variant = getenv("HULC2_WGRAD_HALO") ? atoi(getenv("HULC2_WGRAD_HALO")) : 2;   // 1 = TMA boxes, else cp.async producers
   if (variant != 1 && ((xpe == 48 && zpe == 32) || (xpe == 64 && zpe == 64))) {
+    const int cxh = xpe / 8, czh = zpe / 8;
+    if ((p.BH + KH - 1) * p.PW * cxh > 16 * 256 || p.BH * p.PW * czh > 16 * 256 || (long long)(p.BH + KH) * W * xpe * 2 > 0x7fffffffLL)
+      return HULC2_ENOTIMPL;                      // more than 16 copies per producer thread and tile: the gather kernel takes it
     HaloWgradCpParams q{};
     q.g = p; q.x = (const uint8_t*)x; q.dz = (const uint8_t*)dz; q.H = H; q.W = W; q.OH = OH; q.OW = OW;
     // a producer publishes tile n after issuing tile n + lag; lag = stages - 2 leaves one free slot, so publishing tile n + 1 never

@@ -840,12 +840,16 @@ int hulc2_convb_wgrad(const hulc2_convb_args* a, cudaStream_t st) {
   if (int e = check_convb(a)) return e;
   if (!hulc2_convb_supported(a->C, a->Cout, a->KH, a->KW, a->stride)) { hulc2_set_error("convb_wgrad: unsupported shape"); return HULC2_ENOTIMPL; }
   const int OH = (a->H - a->KH) / a->stride + 1, OW = (a->W - a->KW) / a->stride + 1;
+  // Halo-tile weight gradient (conv_halo_sm100.cu): the source tile is staged ONCE per tile and the taps are read through shifted
+  // MN-major descriptors, instead of gathering every source pixel once per tap.  HULC2_WGRAD_HALO: unset = the cp.async-producer
+  // variant for conv1 over packed frames (48-channel pixels, 32 outputs: 0.80 -> 0.46 ms at F = 4096, the gather kernel moves
+  // 448 bytes per output pixel through LDGSTS, this one 160) and the gather kernel for everything else (64-channel sources:
+  // measured 0.24 ms gather vs 0.42-0.68 ms halo); 0 = gather everywhere; 1 = TMA-box variant, 2 = cp.async variant wherever
+  // the shape fits (both slower on conv3: their 5 M-tiles of shifted-descriptor MMAs pace them).
+  static const int wg_halo = getenv("HULC2_WGRAD_HALO") ? atoi(getenv("HULC2_WGRAD_HALO")) : -1;
+  const bool conv1_like = a->C == 48 && a->Cout == 32;
   if (a->stride == 1 && a->C >= 32 && a->C <= 64 && (a->Cout == 32 || a->Cout == 64) && a->F * OH * OW > 0 && hulc2_conv_halo_enabled() &&
-      getenv("HULC2_WGRAD_HALO") && atoi(getenv("HULC2_WGRAD_HALO"))) {
-    // halo-tile weight gradient: both operands by TMA, taps through shifted MN-major descriptors (conv_halo_sm100.cu).
-    // Correct (same tests) but OPT-IN: measured slower than the gather kernel (conv1 0.92 vs 0.80 ms, conv3 0.33 vs 0.27 ms) --
-    // a tile needs 850 TMA rows of 128 bytes and the TMA unit delivers one row per ~7-10 cycles, so the loads, not the MMAs,
-    // pace it.
+      (wg_halo > 0 || (wg_halo < 0 && conv1_like))) {
     int grid = 0, nblk = 0;
     const int rc = hulc2_conv_halo_wgrad(a->x, a->C, a->dy, a->Cout, a->F, a->H, a->W, a->KH, a->KW, (float*)a->workspace, a->workspace_bytes,
                                          &grid, &nblk, st);
