@@ -79,6 +79,8 @@ _SIGS = {
     "hulc2_convb_wgrad": [C.POINTER(ConvbArgs)],
     "hulc2_spatial_softmax_fwd_bf16": [P, P, P, P, P, I, I, I],
     "hulc2_spatial_softmax_bwd_bf16": [P, P, P, P, P, P, P, I, I, I, I],
+    "hulc2_spatial_softmax_fwd_bf16_stats": [P, P, P, P, P, P, I, I, I],
+    "hulc2_spatial_softmax_bwd_bf16_stats": [P, P, P, P, P, P, P, P, P, I, I, I, I],
     "hulc2_nhwc_bf16_to_nchw": [P, P, I, I, I],
     "hulc2_nchw_to_nhwc_bf16": [P, P, I, I, I, P],
     "hulc2_copy2d": [P, LL, P, LL, LL, I, I],
@@ -138,7 +140,7 @@ _SIGS = {
 }
 _NO_STREAM = {"hulc2_last_error": (C.c_char_p, []), "hulc2_version": (I, []), "hulc2_device_supports_tcgen05": (I, []),
               "hulc2_launch_count": (C.c_ulonglong, []), "hulc2_tma_gemm_count": (C.c_ulonglong, []), "hulc2_convb_supported": (I, [I, I, I, I, I]),
-              "hulc2_rnn_select_kernel": (I, [I]), "hulc2_rnn_cluster_capacity": (I, [I]), "hulc2_rnn_device_error": (I, [I]), "hulc2_rnn_last_path": (I, [])}
+              "hulc2_rnn_select_kernel": (I, [I]), "hulc2_spatial_softmax_stats_supported": (I, [I, I]), "hulc2_rnn_cluster_capacity": (I, [I]), "hulc2_rnn_device_error": (I, [I]), "hulc2_rnn_last_path": (I, [])}
 
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + list(_NO_STREAM))
 

@@ -2,6 +2,8 @@
 // bf16 tcgen05 backends).  Operands are addressed as off(r,k) = R(r) + Kf(k) (separable): row-major,
 // transposed, two-level row strides, both im2col layouts; the dgrad gather adds a validity predicate.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "../../include/hulc2_b200.h"
 
@@ -146,8 +148,11 @@ __device__ __forceinline__ long long c_row_off(const Epilogue& E, int m) {
   return E.c_inner > 0 ? (long long)(m / E.c_inner) * E.cs_outer + (long long)(m % E.c_inner) * E.cs_inner : (long long)m * E.ldc;
 }
 
-// split-K second stage: C = (accumulate ? C : 0) + alpha * sum_z partial[z] (+ bias)
-static __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N, Epilogue E) {
+// split-K second stage: C = epilogue(sum_z partial[z]) -- the FULL epilogue (alpha, bias, add, accumulate, ReLU, mask, dropout keep) and
+// the optional bf16 mirror of the result, so that skinny problems with a fused epilogue (the M = 64..128 layers of the plan
+// networks and goal encoders: one M-tile x 16 N-tiles = 16 CTAs streaming 8 MB of weights) can be split along K as well.
+static __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N, Epilogue E,
+                                            __nv_bfloat16* __restrict__ C16, long long ld16) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)M * N;
   if (idx >= total) return;
@@ -155,10 +160,9 @@ static __global__ void splitk_reduce_kernel(const float* __restrict__ part, int 
   float s = 0.f;
   for (int z = 0; z < splits; ++z) s += part[(long long)z * total + idx];
   long long crow = c_row_off(E, m);
-  float v = E.alpha * s;
-  if (E.bias) v += E.bias[n];
-  if (E.accumulate) v += E.C[crow + n];
+  const float v = apply_epilogue(E, s, m, n, crow);
   E.C[crow + n] = v;
+  if (C16) C16[(long long)m * ld16 + n] = __float2bfloat16_rn(v);
 }
 
 // ------------------------------------------------------------------ host-side parameter builders

@@ -206,7 +206,7 @@ int launch_cfg(const GemmParams& p, cudaStream_t st) {
   HULC2_CHECK_LAUNCH();
   if (p.splits > 1) {
     long long total = (long long)p.M * p.N;
-    splitk_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(p.partial, p.splits, p.M, p.N, p.E);
+    splitk_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(p.partial, p.splits, p.M, p.N, p.E, nullptr, 0);
     HULC2_CHECK_LAUNCH();
   }
   return HULC2_OK;
@@ -247,7 +247,9 @@ int hulc2_gemm_f32_impl(const hulc2_gemm_args* a, cudaStream_t st) {
   if (a->M == 0 || a->N == 0) return HULC2_OK;
   long long out_ctas = (long long)hulc2_cdiv(a->M, 64) * hulc2_cdiv(a->N, 64);
   // split-K for reductions over many rows into a small output (weight gradients)
-  if (simple_epilogue(a) && out_ctas < 64) plan_splitk(p, out_ctas, 296, 256, BK, a->workspace, a->workspace_bytes);
+  // (the reduce kernel applies the full epilogue, so layers with bias / ReLU / mask split as well: e.g. the fp32 contrastive
+  // projection 64 x 128 x 4096 would otherwise run on 8 CTAs)
+  if (out_ctas < 64) plan_splitk(p, out_ctas, 296, 256, BK, a->workspace, a->workspace_bytes);
   else plan_splitk(p, 1, 1, 1 << 30, BK, nullptr, 0);
   return dispatch(p, OP_DENSE, OP_DENSE, st);
 }

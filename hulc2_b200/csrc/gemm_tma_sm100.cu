@@ -282,9 +282,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TmaParams& p, int
   ++g_tma_gemms;
   if (p.splits > 1) {
     long long total = (long long)p.M * p.N;
-    splitk_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(p.partial, p.splits, p.M, p.N, p.E);
+    splitk_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(p.partial, p.splits, p.M, p.N, p.E, p.C16, p.ld16);
     HULC2_CHECK_LAUNCH();
-    if (p.C16) { hulc2_set_error("gemm_tma: internal: bf16 mirror with split-K"); return HULC2_EINVAL; }
   }
   return HULC2_OK;
 }
@@ -330,7 +329,8 @@ int hulc2_gemm_tma_impl(const hulc2_gemm_args* a, cudaStream_t st) {
 
   // split-K: skinny outputs with a long contraction get ~2 waves of CTAs, >= 4 k-tiles each
   p.splits = 1; p.kt_per_split = p.ktiles; p.partial = nullptr;
-  const bool simple = simple_epilogue(a) && !a->C16 && a->c_inner == 0;
+  // (the reduce kernel applies the full epilogue and writes the bf16 mirror, so fused-epilogue layers split too)
+  const bool simple = a->c_inner == 0;
   if (simple && tiles < 100 && p.ktiles >= 8 && a->workspace) {
     int want = (int)((296 + tiles - 1) / tiles);
     int maxs = p.ktiles / 4;

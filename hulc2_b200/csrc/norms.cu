@@ -188,7 +188,9 @@ __global__ void __launch_bounds__(SSM_NT) ssm_bf16_kernel(const __nv_bfloat16* _
                                                        const float* __restrict__ y_map, const float* __restrict__ temperature,
                                                        float* __restrict__ out, const float* __restrict__ dout,
                                                        __nv_bfloat16* __restrict__ dx, float* __restrict__ dtemp, int HW, int C,
-                                                       int relu_mask) {
+                                                       int relu_mask, float* __restrict__ stats) {
+  // stats [F][C/2][4] = (max0, 1/sum0, max1, 1/sum1) per channel pair: written by the forward pass when given; a backward pass
+  // that gets them (and the forward output in `out`) skips its two statistics passes over the frame and only runs the gradient pass
   extern __shared__ __align__(16) unsigned char ssm_raw[];
   __nv_bfloat162* tile = reinterpret_cast<__nv_bfloat162*>(ssm_raw);               // [HW][C/2]
   const int C2 = C >> 1, G = blockDim.x / C2;
@@ -203,6 +205,13 @@ __global__ void __launch_bounds__(SSM_NT) ssm_bf16_kernel(const __nv_bfloat16* _
   const int cp = threadIdx.x % C2, g = threadIdx.x / C2;
   const bool active = g < G;
   float m0 = -INFINITY, m1 = -INFINITY;
+  float inv0, inv1, ex0, ey0, ex1, ey1;
+  const bool have_stats = BWD && stats != nullptr;
+  if (have_stats) {
+    const float4 st = *reinterpret_cast<const float4*>(stats + (size_t)blockIdx.x * 2 * C + 4 * cp);
+    const float4 eo = *reinterpret_cast<const float4*>(out + (size_t)blockIdx.x * 2 * C + 4 * cp);
+    m0 = st.x; inv0 = st.y; m1 = st.z; inv1 = st.w; ex0 = eo.x; ey0 = eo.y; ex1 = eo.z; ey1 = eo.w;
+  } else {
   if (active)
     for (int i = g; i < HW; i += G) {
       const float2 v = __bfloat1622float2(tile[i * C2 + cp]);
@@ -234,11 +243,14 @@ __global__ void __launch_bounds__(SSM_NT) ssm_bf16_kernel(const __nv_bfloat16* _
       se0 += r[0]; sx0 += r[G * C2]; sy0 += r[2 * G * C2]; se1 += r[3 * G * C2]; sx1 += r[4 * G * C2]; sy1 += r[5 * G * C2];
     }
   }
-  const float inv0 = active ? 1.f / se0 : 0.f, inv1 = active ? 1.f / se1 : 0.f;
-  const float ex0 = sx0 * inv0, ey0 = sy0 * inv0, ex1 = sx1 * inv1, ey1 = sy1 * inv1;
+  inv0 = active ? 1.f / se0 : 0.f; inv1 = active ? 1.f / se1 : 0.f;
+  ex0 = sx0 * inv0; ey0 = sy0 * inv0; ex1 = sx1 * inv1; ey1 = sy1 * inv1;
+  }   // !have_stats
   if (!BWD) {
-    if (active && g == 0)
+    if (active && g == 0) {
       *reinterpret_cast<float4*>(out + (size_t)blockIdx.x * 2 * C + 4 * cp) = make_float4(ex0, ey0, ex1, ey1);
+      if (stats) *reinterpret_cast<float4*>(stats + (size_t)blockIdx.x * 2 * C + 4 * cp) = make_float4(m0, inv0, m1, inv1);
+    }
     return;
   }
   float dt = 0.f;
@@ -338,7 +350,7 @@ int hulc2_spatial_softmax_fwd_bf16(const void* x, const float* x_map, const floa
     const size_t smem = ssm_bf16_smem(HW, C);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(ssm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
-    ssm_bf16_kernel<false><<<F, SSM_NT, smem, st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, out, nullptr, nullptr, nullptr, HW, C, 0);
+    ssm_bf16_kernel<false><<<F, SSM_NT, smem, st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, out, nullptr, nullptr, nullptr, HW, C, 0, nullptr);
     HULC2_CHECK_LAUNCH();
     return HULC2_OK;
   }
@@ -359,13 +371,42 @@ int hulc2_spatial_softmax_bwd_bf16(const void* x, const float* x_map, const floa
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(ssm_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
     ssm_bf16_kernel<true><<<F, SSM_NT, smem, st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, nullptr, dout, (__nv_bfloat16*)dx, dtemperature,
-                                                HW, C, relu_mask);
+                                                HW, C, relu_mask, nullptr);
     HULC2_CHECK_LAUNCH();
     return HULC2_OK;
   }
   int G = 256 / C;
   spatial_softmax_kernel<true, __nv_bfloat16><<<F, 256, 3 * G * C * sizeof(float), st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, nullptr,
                                                                                          dout, (__nv_bfloat16*)dx, dtemperature, HW, C, relu_mask);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+
+// Forward that also saves the per-(frame, channel) softmax statistics, and the backward that consumes them together with the
+// forward output: one pass over the frame instead of three (max, sums, gradient).  Only the bf16 shared-memory kernel serves
+// these (hulc2_spatial_softmax_stats_supported); stats is fp32 [F, 2 C].
+int hulc2_spatial_softmax_stats_supported(int HW, int C) { return ssm_bf16_ok(HW, C) ? 1 : 0; }
+int hulc2_spatial_softmax_fwd_bf16_stats(const void* x, const float* x_map, const float* y_map, const float* temperature, float* out,
+                                         float* stats, int F, int HW, int C, cudaStream_t st) {
+  if (F <= 0) return HULC2_OK;
+  if (!ssm_bf16_ok(HW, C) || !stats) { hulc2_set_error("spatial_softmax_fwd_bf16_stats: unsupported shape"); return HULC2_ENOTIMPL; }
+  const size_t smem = ssm_bf16_smem(HW, C);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(ssm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
+  ssm_bf16_kernel<false><<<F, SSM_NT, smem, st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, out, nullptr, nullptr, nullptr, HW, C, 0, stats);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_spatial_softmax_bwd_bf16_stats(const void* x, const float* x_map, const float* y_map, const float* temperature, const float* out,
+                                         const float* stats, const float* dout, void* dx, float* dtemperature, int F, int HW, int C,
+                                         int relu_mask, cudaStream_t st) {
+  if (F <= 0) return HULC2_OK;
+  if (!ssm_bf16_ok(HW, C) || !stats || !out) { hulc2_set_error("spatial_softmax_bwd_bf16_stats: unsupported shape"); return HULC2_ENOTIMPL; }
+  const size_t smem = ssm_bf16_smem(HW, C);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(ssm_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
+  ssm_bf16_kernel<true><<<F, SSM_NT, smem, st>>>((const __nv_bfloat16*)x, x_map, y_map, temperature, const_cast<float*>(out), dout, (__nv_bfloat16*)dx,
+                                              dtemperature, HW, C, relu_mask, const_cast<float*>(stats));
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

@@ -181,19 +181,35 @@ class WindowLoader:
     def __init__(self, store: DeviceEpisodeStore, episode_lookup: np.ndarray, batch_size: int, min_window_size: int = 16,
                  max_window_size: int = 32, train: bool = True, shift_pad: Optional[Dict[str, int]] = None, seed: int = 0,
                  lang_lookup: Optional[np.ndarray] = None, lang_emb: Optional[torch.Tensor] = None, aux_lang_loss_window: int = 1,
-                 shuffle: Optional[bool] = None, drop_last: bool = False):
+                 shuffle: Optional[bool] = None, drop_last: Optional[bool] = None, rank: Optional[int] = None, world: Optional[int] = None):
         self.store, self.lookup, self.B = store, np.asarray(episode_lookup, dtype=np.int64), int(batch_size)
         self.min_ws, self.max_ws, self.train = int(min_window_size), int(max_window_size), bool(train)
         self.shift_pad = dict(shift_pad or {}) if train else {}
-        self.rng = np.random.default_rng(seed)
+        # Data parallel (the reference relies on Lightning injecting a DistributedSampler): every rank walks the SAME permutation
+        # (order_rng, seeded identically) and takes entries rank, rank + world, ... of it, padded to an equal count; the window-size
+        # and RandomShiftsAug draws come from a per-rank stream.
+        if rank is None or world is None:
+            import torch.distributed as dist
+
+            on = dist.is_available() and dist.is_initialized()
+            rank, world = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+        self.rank, self.world = int(rank), int(world)
+        self.order_rng = np.random.default_rng(seed)
+        self.rng = np.random.default_rng([seed, self.rank])
         self.lang_lookup = None if lang_lookup is None else np.asarray(lang_lookup, dtype=np.int64)
         self.lang_emb = None if lang_emb is None else torch.as_tensor(lang_emb).to(store.device, torch.float32)
         self.aux_window = aux_lang_loss_window
         self.shuffle = bool(train) if shuffle is None else bool(shuffle)
-        self.drop_last = drop_last
+        # training batches feed a captured step with static shapes: the ragged last batch is dropped by default
+        self.drop_last = bool(train) if drop_last is None else bool(drop_last)
+        if len(self.lookup) and int(self.lookup.max()) + self.max_ws > store.N + self.max_ws - self.min_ws:
+            raise ValueError("episode_lookup points past the store: a window of min_window_size would read out of bounds")
+
+    def _shard_len(self) -> int:
+        return (len(self.lookup) + self.world - 1) // self.world
 
     def __len__(self) -> int:
-        n = len(self.lookup)
+        n = self._shard_len()
         return n // self.B if self.drop_last else (n + self.B - 1) // self.B
 
     def window_size(self, idx: int) -> int:
@@ -219,7 +235,10 @@ class WindowLoader:
         return starts, lens, shifts
 
     def __iter__(self) -> Iterator[dict]:
-        order = self.rng.permutation(len(self.lookup)) if self.shuffle else np.arange(len(self.lookup))
+        order = self.order_rng.permutation(len(self.lookup)) if self.shuffle else np.arange(len(self.lookup))
+        if self.world > 1:
+            n = self._shard_len() * self.world                   # pad by wrapping so that every rank gets the same count
+            order = np.resize(order, n)[self.rank :: self.world]
         for b in range(len(self)):
             ids = order[b * self.B : (b + 1) * self.B]
             starts, lens, shifts = self.describe(ids)

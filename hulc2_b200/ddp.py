@@ -19,7 +19,7 @@ import torch.distributed as dist
 
 
 class GradBucketReducer:
-    def __init__(self, optimizer, bucket_mb: float = 25.0, process_group=None):
+    def __init__(self, optimizer, bucket_mb: float = 25.0, process_group=None, head_mb: float = 4.0):
         self.opt = optimizer
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -31,6 +31,7 @@ class GradBucketReducer:
         self._fired = set()
         self.used = None  # learned on the first step: ids of parameters that actually receive gradients
         cap = int(bucket_mb * (1 << 20) / 4)
+        head_cap = int(head_mb * (1 << 20) / 4)
         for arena in optimizer._arenas:
             if not arena["n"]:
                 continue
@@ -45,7 +46,20 @@ class GradBucketReducer:
                     self._add_bucket(arena, start, end, cur_params)
                     cur_params, end = [], start
             if cur_params:
-                self._add_bucket(arena, start, end, cur_params)
+                # The head-of-arena bucket holds the parameters whose gradients arrive LAST (the perceptual encoders: conv1's weight
+                # gradient is the final kernel of backward), so its all-reduce is the one transfer nothing can overlap.  Keep it
+                # small: everything but the first ~head_mb of the arena goes into a bucket of its own that completes earlier.
+                ordered = list(reversed(cur_params))            # arena order
+                off_of = {id(p): o for p, o in zip(params, offs)}
+                cut = 0                                           # parameters that fit in the first head_cap elements
+                while cut + 1 < len(ordered) and off_of[id(ordered[cut + 1])] - start <= head_cap:
+                    cut += 1
+                if head_cap > 0 and end - start > head_cap and 0 < cut < len(ordered):
+                    split = off_of[id(ordered[cut])]
+                    self._add_bucket(arena, split, end, list(reversed(ordered[cut:])))
+                    self._add_bucket(arena, start, split, list(reversed(ordered[:cut])))
+                else:
+                    self._add_bucket(arena, start, end, cur_params)
 
     def _add_bucket(self, arena, start, end, params):
         b = {"view": arena["g"][start:end], "params": list(params), "pending": 0, "index": len(self.buckets)}

@@ -677,9 +677,17 @@ class StaticConvSSM(torch.autograd.Function):
             xs, y1, y2, y3 = _convb_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
             HW = y3.shape[1] * y3.shape[2]
             _lib.tag(f"spatial_softmax_fwd_bf16[F={F_},HW={HW}]", 0.0, 2.0 * y3.numel() + 4.0 * out.numel())
-            call("hulc2_spatial_softmax_fwd_bf16", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
-                 out.data_ptr(), F_, HW, 64)
-            ctx.save_for_backward(xs, y1, y2, y3, w1, w2, w3, x_map, y_map, temperature)
+            # the softmax statistics are kept for the backward when a gradient will be asked for (one pass there instead of three)
+            stats = None
+            if any(ctx.needs_input_grad) and _lib.load_library().hulc2_spatial_softmax_stats_supported(HW, 64):
+                stats = torch.empty(F_, 128, device=w1.device, dtype=torch.float32)
+                call("hulc2_spatial_softmax_fwd_bf16_stats", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
+                     out.data_ptr(), stats.data_ptr(), F_, HW, 64)
+            else:
+                call("hulc2_spatial_softmax_fwd_bf16", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
+                     out.data_ptr(), F_, HW, 64)
+            ctx.has_stats = stats is not None
+            ctx.save_for_backward(xs, y1, y2, y3, w1, w2, w3, x_map, y_map, temperature, *((out, stats) if stats is not None else ()))
             return out
         y1, y2, y3 = _conv_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
         HW = y3.shape[1] * y3.shape[2]
@@ -692,14 +700,19 @@ class StaticConvSSM(torch.autograd.Function):
     def backward(ctx, dout):
         dout = dout.contiguous()
         if ctx.bf16:
-            xs, y1, y2, y3, w1, w2, w3, x_map, y_map, temperature = ctx.saved_tensors
+            xs, y1, y2, y3, w1, w2, w3, x_map, y_map, temperature, *extra = ctx.saved_tensors
             F_ = xs.shape[0]
             HW = y3.shape[1] * y3.shape[2]
             dz3 = torch.empty_like(y3)
             dtemp = torch.zeros(1, device=xs.device, dtype=torch.float32) if ctx.needs_input_grad[9] else None
             _lib.tag(f"spatial_softmax_bwd_bf16[F={F_},HW={HW}]", 0.0, 4.0 * y3.numel() + 4.0 * dout.numel())  # y3 in, dz3 out
-            call("hulc2_spatial_softmax_bwd_bf16", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
-                 dout.data_ptr(), dz3.data_ptr(), _p(dtemp), F_, HW, 64, 1)
+            if ctx.has_stats:
+                fwd_out, stats = extra
+                call("hulc2_spatial_softmax_bwd_bf16_stats", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
+                     fwd_out.data_ptr(), stats.data_ptr(), dout.data_ptr(), dz3.data_ptr(), _p(dtemp), F_, HW, 64, 1)
+            else:
+                call("hulc2_spatial_softmax_bwd_bf16", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
+                     dout.data_ptr(), dz3.data_ptr(), _p(dtemp), F_, HW, 64, 1)
             g = _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3)
             return (None, g["w1"], g["b1"], g["w2"], g["b2"], g["w3"], g["b3"], None, None, dtemp)
         x, y1, y2, y3, w2, w3, x_map, y_map, temperature, out = ctx.saved_tensors

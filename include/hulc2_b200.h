@@ -126,6 +126,15 @@ int hulc2_spatial_softmax_fwd_bf16(const void* x, const float* x_map, const floa
 int hulc2_spatial_softmax_bwd_bf16(const void* x, const float* x_map, const float* y_map, const float* temperature,
                                    const float* dout, void* dx, float* dtemperature, int F, int HW, int C, int relu_mask,
                                    hulc2_stream_t stream);
+/* Same, with the per-(frame, channel) softmax statistics (max, 1/sum; fp32 [F, 2C]) saved by the forward and consumed -- together
+ * with the forward output `out` -- by the backward, which then makes ONE pass over the frame instead of three.  Served by the
+ * shared-memory bf16 kernel only: check hulc2_spatial_softmax_stats_supported(HW, C) first (else HULC2_ENOTIMPL). */
+int hulc2_spatial_softmax_stats_supported(int HW, int C);
+int hulc2_spatial_softmax_fwd_bf16_stats(const void* x, const float* x_map, const float* y_map, const float* temperature,
+                                         float* out, float* stats, int F, int HW, int C, hulc2_stream_t stream);
+int hulc2_spatial_softmax_bwd_bf16_stats(const void* x, const float* x_map, const float* y_map, const float* temperature,
+                                         const float* out, const float* stats, const float* dout, void* dx,
+                                         float* dtemperature, int F, int HW, int C, int relu_mask, hulc2_stream_t stream);
 int hulc2_nhwc_bf16_to_nchw(const void* src, float* dst, int F, int HW, int C, hulc2_stream_t stream);
 int hulc2_nchw_to_nhwc_bf16(const float* src, void* dst, int F, int HW, int C, const void* mask, hulc2_stream_t stream);
 

@@ -208,3 +208,27 @@ def test_datamodule_batches_train_step():
     # validation loader: no augmentation, deterministic order
     vb = next(iter(dm.val_dataloader()))
     assert vb["vis"]["rgb_obs"]["rgb_static"].shift is None
+
+
+def test_loaders_shard_windows_across_ranks():
+    """Data parallel: rank r of `world` takes entries r, r + world, ... of the SAME epoch permutation (what Lightning's injected
+    DistributedSampler does for the reference), padded to equal length; augmentation draws differ per rank."""
+    from hulc2_b200.datamodule import WindowLoader, build_episode_lookup, synthetic_store
+
+    store = synthetic_store(200, device=DEV, seed=3)
+    look = build_episode_lookup([(0, 99), (100, 199)], 16, 32)
+    loaders = [WindowLoader(store, look, 4, 16, 32, True, {"rgb_static": 10}, seed=7, rank=r, world=2) for r in range(2)]
+    assert len(loaders[0]) == len(loaders[1]) == ((len(look) + 1) // 2) // 4
+    seen, shifts = [], []
+    for ld in loaders:
+        ids = []
+        for b in ld:
+            assert b["actions"].shape == (4, 32, 7)               # drop_last: static shapes for the captured step
+            ids += b["idx"].tolist()
+            shifts.append(b["rgb_obs"]["rgb_static"].shift[:8].clone())
+        seen.append(ids)
+    assert not set(seen[0]) & set(seen[1])
+    assert len(set(seen[0]) | set(seen[1])) >= len(look) - 8        # all but the dropped ragged tail of each shard
+    assert not torch.equal(shifts[0], shifts[len(shifts) // 2])
+    with pytest.raises(ValueError):
+        WindowLoader(store, np.asarray([0, 195]), 2, 16, 32)        # a 16-step window from frame 195 would leave the 200-frame store

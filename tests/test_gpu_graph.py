@@ -71,7 +71,7 @@ def _drive(use_graph, batches, steps, precision, dropout_p, hidden=256, hooks=No
     return out, tr
 
 
-@pytest.mark.parametrize("precision,loss_tol,frac_tol", [("fp32", 1e-5, 2e-3), ("bf16", 1e-4, 2e-3)])
+@pytest.mark.parametrize("precision,loss_tol,frac_tol", [("fp32", 1e-5, 2e-3), ("bf16", 1e-4, 2e-2)])
 def test_graph_replay_equals_eager_steps(precision, loss_tol, frac_tol):
     """6 steps (2 eager, capture + 4 replays) vs 6 eager steps with identical device-side noise epochs: dropout masks and the
     plan draw come from the Philox kernels in both, so every loss and every parameter must agree step by step."""
