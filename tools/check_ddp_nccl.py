@@ -65,6 +65,7 @@ def main():
     # (2) the captured step with the NCCL all-reduce inside the graph, lr = 0
     m = build_model("calvin", hidden_size=args.hidden).to(dev).train()
     tr = PolicyTrainer(m, use_graph=True)
+    tr.scheduler = None                    # a scheduler step would write its base lr back into the group after step 1
     for grp in tr.optimizer.param_groups:
         grp["lr"] = 0.0
     worst = []
@@ -73,16 +74,25 @@ def main():
     for step in range(4):
         ctx = noise.supplied(categories=draws) if tr._graph is None else contextlib.nullcontext()
         with ctx:
-            tr.train_step(batch, step)
+            loss_t = tr.train_step(batch, step)
         torch.cuda.synchronize()
+        if rank == 0 and os.environ.get("HULC2_DDP_CHECK_VERBOSE"):
+            ar = tr.optimizer._arenas[0]
+            print(f"[step {step + 1}] loss {float(loss_t):.6f} (single-GPU eager loss of this rank {float(loss0):.6f}) param checksum "
+                  f"{float(ar['p'].double().abs().sum()):.9f} m checksum {float(ar['m'].double().abs().sum()):.6e} lr_dev {tr.optimizer._lr_dev.tolist()} "
+                  f"step_dev {int(tr.optimizer._step_dev)} draws checksum {[int(d.sum()) for d in draws]}", flush=True)
         got = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for _, p in m.named_parameters()]).double()
         got = got * tr.optimizer.grad_scale
         errs, o = [], 0
         for n, sz in zip(names, sizes):
             e, r = got[o:o + sz], expected[o:o + sz]
-            errs.append((float((e - r).abs().max() / (r.abs().max() + 1e-30)), n))
+            errs.append((float((e - r).abs().max() / (r.abs().max() + 1e-30)), n, e[:3].tolist(), r[:3].tolist()))
             o += sz
         worst.append(max(errs))
+        if rank == 0 and os.environ.get("HULC2_DDP_CHECK_VERBOSE"):
+            bad = sorted(errs, reverse=True)[:6]
+            print(f"[step {step + 1}] " + "; ".join(f"{n}: err {x:.2e} got {g_} want {w_}" for x, n, g_, w_ in bad), flush=True)
+            print(f"[step {step + 1}] params with err > 1e-3: {sum(1 for x in errs if x[0] > 1e-3)} of {len(errs)}", flush=True)
     assert tr._graph is not None and tr.replays == 2
 
     # (3) real updates: parameters must stay bit-identical across ranks
