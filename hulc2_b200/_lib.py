@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("precision", I),
         ("workspace", P), ("workspace_bytes", LL),
         ("A16", P), ("B16", P), ("C16", P), ("ld16", LL),
+        ("rowsum", P),
     ]
 
 
@@ -87,6 +88,8 @@ _SIGS = {
     "hulc2_transpose01": [P, LL, LL, P, LL, I, I, I, I],
     "hulc2_fill": [P, LL, F],
     "hulc2_axpy": [P, P, LL, F],
+    "hulc2_weighted_sum": [P, P, I, P],
+    "hulc2_weighted_fanout": [P, P, I, P],
     "hulc2_colsum": [P, LL, LL, I, P, I, P, LL],
     "hulc2_relu_mask": [P, P, P, LL],
     "hulc2_nhwc_to_nchw": [P, P, I, I, I],
@@ -186,6 +189,7 @@ def stream() -> int:
 _prof = None   # list of (key, flops, start_event, end_event) while profiling
 _tag = None    # (key, flops) annotation for the next call
 _flush = None  # (ptr, n floats) of a buffer larger than L2: written before every profiled call
+_prof_external = False   # events become event-record NODES of the CUDA graph being captured (timeline of a replay)
 
 
 def tag(key: str, flops: float = 0.0, nbytes: float = 0.0) -> None:
@@ -200,14 +204,49 @@ def profile_begin(flush: Optional[torch.Tensor] = None) -> None:
     re-written (``hulc2_fill``) before EVERY profiled call.  That does two things: each kernel starts with a cold L2 (as under
     ncu), and the ~40 us the GPU spends on the fill keep it behind the host, so the event pair brackets the kernel alone
     instead of the host's launch latency (an eager step is host-bound: without the fill every small call reads 15-20 us)."""
-    global _prof, _flush
+    global _prof, _flush, _prof_external
     _prof = []
     _flush = None if flush is None else (flush.data_ptr(), flush.numel())
+    _prof_external = False
+
+
+def profile_begin_graph() -> None:
+    """Per-call timing INSIDE a CUDA graph: call while the step is being captured.  Every C-ABI call is bracketed by two
+    external timing events (cudaEventRecordExternal -> event-record nodes of the graph); after a replay ``profile_read_graph``
+    returns what each call took in the replayed step -- no host latency, warm caches, the order and overlap of the real step."""
+    global _prof, _flush, _prof_external
+    _prof, _flush, _prof_external = [], None, True
+
+
+def profile_read_graph(other_key: str = "(between calls: torch kernels, memsets, launch gaps)") -> dict:
+    """After a replay of the graph captured under ``profile_begin_graph``: {key: {key, ms, calls, flops, bytes}}; the time
+    between the end of one C-ABI call and the start of the next is booked under ``other_key``."""
+    torch.cuda.synchronize()
+    out = {}
+    prev = None
+    for key, flops, nbytes, e0, e1 in _prof:
+        r = out.setdefault(key, {"key": key, "ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0})
+        r["ms"] += e0.elapsed_time(e1)
+        r["calls"] += 1
+        r["flops"] += flops
+        r["bytes"] += nbytes
+        if prev is not None:
+            g = out.setdefault(other_key, {"key": other_key, "ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0})
+            g["ms"] += max(prev.elapsed_time(e0), 0.0)
+            g["calls"] += 1
+        prev = e1
+    return out
+
+
+def profile_end_graph() -> None:
+    global _prof, _tag, _flush, _prof_external
+    _prof, _tag, _flush, _prof_external = None, None, None, False
 
 
 def profile_end() -> dict:
     """Returns {key: {key, ms, calls, flops}} aggregated over the profiled region (CUDA events on the launch stream)."""
-    global _prof, _tag, _flush
+    global _prof, _tag, _flush, _prof_external
+    _prof_external = False
     torch.cuda.synchronize()
     out = {}
     for key, flops, nbytes, e0, e1 in _prof:
@@ -253,7 +292,7 @@ def call(name: str, *args) -> None:
     if _prof is not None:
         key, flops, nbytes = _tag if _tag is not None else (_auto_key(name, args), 0.0, _auto_bytes(name, args))
         _tag = None
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True, external=_prof_external), torch.cuda.Event(enable_timing=True, external=_prof_external)
         if _flush is not None:
             lib.hulc2_fill(_flush[0], _flush[1], 0.0, stream())
         e0.record()

@@ -54,6 +54,7 @@ int hulc2_device_supports_tcgen05(void) {
 
 int hulc2_gemm(const hulc2_gemm_args* a, cudaStream_t st) {
   if (!a) { hulc2_set_error("gemm: null args"); return HULC2_EINVAL; }
+  if (a->precision == 0 && a->rowsum) { hulc2_set_error("gemm: rowsum is served by the bf16 TMA path only (precision 1)"); return HULC2_EINVAL; }
   if (a->precision == 0) return hulc2_gemm_f32_impl(a, st);
   if (a->precision == 1) return hulc2_gemm_bf16_impl(a, st);
   hulc2_set_error("gemm: unknown precision");

@@ -35,6 +35,17 @@ __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += a * x[i];
 }
 
+// scalar combine: out = sum_i w_i * x_i[0] (forward), out[i] = w_i * g[0] (backward); n <= 8 terms, one thread
+struct WeightedTerms { const float* x[8]; float w[8]; int n; };
+__global__ void weighted_sum_kernel(const WeightedTerms t, float* __restrict__ out) {
+  float s = 0.f;
+  for (int i = 0; i < t.n; ++i) s = fmaf(t.w[i], *t.x[i], s);
+  *out = s;
+}
+__global__ void weighted_fanout_kernel(const float* __restrict__ g, const WeightedTerms t, float* __restrict__ out) {
+  if ((int)threadIdx.x < t.n) out[threadIdx.x] = t.w[threadIdx.x] * *g;
+}
+
 __global__ void relu_mask_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dz[i] = y[i] > 0.f ? dy[i] : 0.f;
@@ -390,6 +401,24 @@ int hulc2_fill(float* dst, long long n, float value, cudaStream_t st) {
 int hulc2_axpy(const float* x, float* y, long long n, float a, cudaStream_t st) {
   if (n <= 0) return HULC2_OK;
   axpy_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, y, n, a);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_weighted_sum(const float* const* xs, const float* w, int n, float* out, cudaStream_t st) {
+  if (n <= 0 || n > 8 || !xs || !w || !out) { hulc2_set_error("weighted_sum: 1..8 terms"); return HULC2_EINVAL; }
+  WeightedTerms t{};
+  t.n = n;
+  for (int i = 0; i < n; ++i) { t.x[i] = xs[i]; t.w[i] = w[i]; }
+  weighted_sum_kernel<<<1, 1, 0, st>>>(t, out);
+  HULC2_CHECK_LAUNCH();
+  return HULC2_OK;
+}
+int hulc2_weighted_fanout(const float* g, const float* w, int n, float* out, cudaStream_t st) {
+  if (n <= 0 || n > 8 || !g || !w || !out) { hulc2_set_error("weighted_fanout: 1..8 terms"); return HULC2_EINVAL; }
+  WeightedTerms t{};
+  t.n = n;
+  for (int i = 0; i < n; ++i) t.w[i] = w[i];
+  weighted_fanout_kernel<<<1, 32, 0, st>>>(g, t, out);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

@@ -417,6 +417,7 @@ int hulc2_gemm_bf16_impl(const hulc2_gemm_args* a, cudaStream_t st) {
   }
   if (a && (!a->A || !a->B)) { hulc2_set_error("gemm: bf16-only operands (A/B NULL) need a TMA-compatible layout: 16-byte aligned base, row stride % 8 == 0, K > 0"); return HULC2_EINVAL; }
   if (a && a->C16) { hulc2_set_error("gemm: a bf16 output mirror (C16) needs the TMA path (aligned bf16 operand mirrors)"); return HULC2_EINVAL; }
+  if (a && a->rowsum) { hulc2_set_error("gemm: rowsum needs the TMA path (aligned bf16 operand mirrors)"); return HULC2_EINVAL; }
   GemmParams p;
   if (!dense_params(a, p)) return HULC2_EINVAL;
   if (a->M == 0 || a->N == 0) return HULC2_OK;

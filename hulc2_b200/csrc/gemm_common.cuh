@@ -152,10 +152,16 @@ __device__ __forceinline__ long long c_row_off(const Epilogue& E, int m) {
 // the optional bf16 mirror of the result, so that skinny problems with a fused epilogue (the M = 64..128 layers of the plan
 // networks and goal encoders: one M-tile x 16 N-tiles = 16 CTAs streaming 8 MB of weights) can be split along K as well.
 static __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N, Epilogue E,
-                                            __nv_bfloat16* __restrict__ C16, long long ld16) {
+                                            __nv_bfloat16* __restrict__ C16, long long ld16,
+                                            const float* __restrict__ rowsum_part = nullptr, float* __restrict__ rowsum = nullptr) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)M * N;
   if (idx >= total) return;
+  if (rowsum && idx < M) {               // row sums of A (gemm_tma_sm100.cu), one partial per split
+    float rs = 0.f;
+    for (int z = 0; z < splits; ++z) rs += rowsum_part[(long long)z * M + idx];
+    rowsum[idx] = rs;
+  }
   int m = (int)(idx / N), n = (int)(idx - (long long)m * N);
   float s = 0.f;
   for (int z = 0; z < splits; ++z) s += part[(long long)z * total + idx];

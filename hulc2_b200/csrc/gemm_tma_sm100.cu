@@ -40,6 +40,8 @@ struct TmaParams {
   long long ld16;
   int vec;                      // 16-byte epilogue accesses are legal for every pointer involved
   int vec8;                     // ... and so are 32-byte ones (8 fp32 columns per 256-bit access)
+  float* rowsum;                // optional [M]: rowsum[m] = sum_k A(m,k) (an nn.Linear's bias gradient out of its weight-gradient GEMM)
+  float* rowsum_partial;        // [splits, M] when splits > 1
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
@@ -83,7 +85,19 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), BN);
+  // Row sums of A ride along as one more accumulator: the CTAs of the first N-tile column multiply every A k-slice with a
+  // constant all-ones B operand as well (N = 16, the narrowest UMMA at M = 128; all elements are equal, so its swizzled layout
+  // is immaterial) into TMEM columns [BN, BN + 16): the "ones column" of the weight-gradient contraction, without touching
+  // the operand layouts in HBM.
+  const bool row_sums = p.rowsum != nullptr && blockIdx.y == 0;
+  const uint32_t tmem_cols = p.rowsum ? 2u * BN : (uint32_t)BN;      // power of two >= 32
+  const uint32_t ones_tile = tiles + (uint32_t)ST * STAGE_BYTES;     // 2 KB behind the ring (1024-byte aligned)
+  if (row_sums) {
+    for (int i = tid; i < 2048 / 16; i += NT)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ones_tile + 16u * i), "r"(0x3F803F80u) : "memory");
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -124,6 +138,12 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
         const uint64_t ad = make_desc(a_tile, A_MN ? 8192u : 0u), bd = make_desc(b_tile, B_MN ? 8192u : 0u);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, ad + A_STEP * k, bd + B_STEP * k, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+        if (row_sums) {
+          constexpr uint32_t IDESC_RS = make_idesc(BM, 16, A_MN, false);
+          const uint64_t od = make_desc(ones_tile, 0u);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d + BN, ad + A_STEP * k, od, IDESC_RS, (i > 0 || k > 0) ? 1u : 0u);
+        }
         umma_commit(smem_u32(&empty_bar[s]));     // stage free once these MMAs have read it
       }
       umma_commit(smem_u32(&acc_bar));            // accumulator complete
@@ -138,6 +158,15 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
     mbar_wait_relaxed(smem_u32(&acc_bar), 0);
     tc_fence_after();
     const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
+    if (row_sums) {                               // block-uniform
+      uint32_t rs[16];
+      tmem_ld16_nowait(trow + (uint32_t)BN, rs);
+      tmem_ld_wait();
+      if (mvalid) {
+        if (p.splits > 1) p.rowsum_partial[(long long)blockIdx.z * p.M + m] = __uint_as_float(rs[0]);
+        else p.rowsum[m] = __uint_as_float(rs[0]);
+      }
+    }
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       if (n0 + c >= p.N) break;                   // warp-uniform
@@ -233,7 +262,7 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_d, BN);
+  if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -282,7 +311,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TmaParams& p, int
   ++g_tma_gemms;
   if (p.splits > 1) {
     long long total = (long long)p.M * p.N;
-    splitk_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(p.partial, p.splits, p.M, p.N, p.E, p.C16, p.ld16);
+    splitk_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(p.partial, p.splits, p.M, p.N, p.E, p.C16, p.ld16, p.rowsum_partial, p.rowsum);
     HULC2_CHECK_LAUNCH();
   }
   return HULC2_OK;
@@ -324,6 +353,7 @@ int hulc2_gemm_tma_impl(const hulc2_gemm_args* a, cudaStream_t st) {
   const int mt = hulc2_cdiv(a->M, BM);
   int BN = a->N <= 64 ? 64 : (a->N <= 128 ? 128 : 256);
   if (BN == 256 && (long long)mt * hulc2_cdiv(a->N, 256) < 148) BN = 128;   // more, smaller tiles when the grid is short
+  if (BN == 256 && a->rowsum) BN = 128;                                      // the row-sum accumulator doubles the TMEM allocation
   if (BN == 128 && a->N > 64 && (long long)mt * hulc2_cdiv(a->N, 128) < 74 && p.ktiles <= 8) BN = 64;
   const long long tiles = (long long)mt * hulc2_cdiv(a->N, BN);
 
@@ -335,12 +365,13 @@ int hulc2_gemm_tma_impl(const hulc2_gemm_args* a, cudaStream_t st) {
     int want = (int)((296 + tiles - 1) / tiles);
     int maxs = p.ktiles / 4;
     int s = want < maxs ? want : maxs;
-    const long long per = (long long)a->M * a->N * (long long)sizeof(float);
+    const long long per = ((long long)a->M * a->N + (a->rowsum ? a->M : 0)) * (long long)sizeof(float);
     while (s > 1 && (long long)s * per > a->workspace_bytes) --s;
     if (s > 1) {
       p.kt_per_split = hulc2_cdiv(p.ktiles, s);
       p.splits = hulc2_cdiv(p.ktiles, p.kt_per_split);
       p.partial = (float*)a->workspace;
+      p.rowsum_partial = a->rowsum ? p.partial + (long long)p.splits * a->M * a->N : nullptr;
     }
   }
   const int stage_bytes = (int)A_BYTES + BN * 128;
@@ -351,7 +382,8 @@ int hulc2_gemm_tma_impl(const hulc2_gemm_args* a, cudaStream_t st) {
   if (stages > p.kt_per_split) stages = p.kt_per_split;
   if (stages < 1) stages = 1;
   p.stages = stages;
-  const int smem = stages * stage_bytes + 1024;
+  const int smem = stages * stage_bytes + 1024 + (a->rowsum ? 2048 : 0);
+  p.rowsum = a->rowsum;
 
   // 16-byte epilogue accesses
   bool vec = al(a->C, 16) && a->ldc % 4 == 0;

@@ -1,6 +1,7 @@
 // LayerNorm (+residual +dropout) and SpatialSoftmax, forward and backward.  Memory-bound: one pass
 // over HBM per tensor, warp-shuffle reductions, coalesced along the feature/channel axis.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/hulc2_b200.h"
@@ -276,6 +277,142 @@ __global__ void __launch_bounds__(SSM_NT) ssm_bf16_kernel(const __nv_bfloat16* _
   }
 }
 
+// Streaming SpatialSoftmax for the 64-channel trunk (third generation).  ncu r02 showed the shared-memory kernel above
+// issue-bound (71 % of issue slots, 28-30 % of HBM): a frame was staged with LDG.128 + STS.128, then walked two or three times
+// with LDS per channel pair.  Here thread (lane = channel pair, warp = position group g of 8) loads ITS OWN bf16 pairs straight
+// from HBM -- a warp reads one 128-byte position row per load, fully coalesced -- and every element is touched once;
+// exponentials are one FFMA + one ex2.approx (1/T and log2 e folded into the scale).  No frame staging, no barrier before the
+// arithmetic, ~3x fewer instructions per element.  The maps are read through L1 (every lane of a warp reads the same
+// address).  stats keep the format of ssm_bf16_kernel: (max of x/T, 1/sum) per channel.
+constexpr float SSM_LOG2E = 1.4426950408889634f, SSM_LN2 = 0.6931471805599453f;
+__device__ __forceinline__ float ssm_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// forward: ONE streaming pass with an online maximum.  Positions are taken in batches of 8 per thread (8 independent 128-byte
+// row loads in flight per warp); per batch the running maximum moves at most once, so rescaling the three running sums costs one
+// ex2 + three multiplies per 8 positions.  ~45 registers: 5 blocks per SM.
+__global__ void __launch_bounds__(256) ssm_reg_fwd_kernel(const uint32_t* __restrict__ x, const float* __restrict__ x_map,
+                                                          const float* __restrict__ y_map, const float* __restrict__ temperature,
+                                                          float* __restrict__ out, float* __restrict__ stats, int HW) {
+  __shared__ float red[8][8][32];        // [m0, se0, sx0, sy0, m1, se1, sx1, sy1][warp][lane]
+  const int cp = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const uint32_t* xf = x + (size_t)blockIdx.x * HW * 32 + cp;
+  const float a = SSM_LOG2E / temperature[0];
+  float m0 = -INFINITY, m1 = -INFINITY;
+  float se0 = 0.f, sx0 = 0.f, sy0 = 0.f, se1 = 0.f, sx1 = 0.f, sy1 = 0.f;
+  for (int i0 = g; i0 < HW; i0 += 64) {
+    uint32_t u[8];
+    float xm[8], ym[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + 8 * k;
+      const bool ok = i < HW;
+      u[k] = ok ? __ldg(xf + (size_t)i * 32) : 0u;
+      xm[k] = ok ? __ldg(x_map + i) : 0.f;
+      ym[k] = ok ? __ldg(y_map + i) : 0.f;
+    }
+    float b0 = m0, b1 = m1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (i0 + 8 * k < HW) { b0 = fmaxf(b0, bf16lo(u[k]) * a); b1 = fmaxf(b1, bf16hi(u[k]) * a); }
+    // (first batch: m = -inf, sums = 0: ex2(-inf) = 0 keeps them 0)
+    const float r0 = ssm_ex2(m0 - b0), r1 = ssm_ex2(m1 - b1);
+    se0 *= r0; sx0 *= r0; sy0 *= r0; se1 *= r1; sx1 *= r1; sy1 *= r1;
+    m0 = b0; m1 = b1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (i0 + 8 * k < HW) {
+        const float e0 = ssm_ex2(fmaf(bf16lo(u[k]), a, -m0)), e1 = ssm_ex2(fmaf(bf16hi(u[k]), a, -m1));
+        se0 += e0; sx0 = fmaf(e0, xm[k], sx0); sy0 = fmaf(e0, ym[k], sy0);
+        se1 += e1; sx1 = fmaf(e1, xm[k], sx1); sy1 = fmaf(e1, ym[k], sy1);
+      }
+  }
+  red[0][g][cp] = m0; red[1][g][cp] = se0; red[2][g][cp] = sx0; red[3][g][cp] = sy0;
+  red[4][g][cp] = m1; red[5][g][cp] = se1; red[6][g][cp] = sx1; red[7][g][cp] = sy1;
+  __syncthreads();
+  if (g == 0) {
+    float M0 = -INFINITY, M1 = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { M0 = fmaxf(M0, red[0][k][cp]); M1 = fmaxf(M1, red[4][k][cp]); }
+    se0 = sx0 = sy0 = se1 = sx1 = sy1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {        // a warp that saw no position has m = -inf, sums 0: weight ex2(-inf) = 0
+      const float w0 = ssm_ex2(red[0][k][cp] - M0), w1 = ssm_ex2(red[4][k][cp] - M1);
+      se0 = fmaf(w0, red[1][k][cp], se0); sx0 = fmaf(w0, red[2][k][cp], sx0); sy0 = fmaf(w0, red[3][k][cp], sy0);
+      se1 = fmaf(w1, red[5][k][cp], se1); sx1 = fmaf(w1, red[6][k][cp], sx1); sy1 = fmaf(w1, red[7][k][cp], sy1);
+    }
+    const float inv0 = 1.f / se0, inv1 = 1.f / se1;
+    *reinterpret_cast<float4*>(out + (size_t)blockIdx.x * 128 + 4 * cp) = make_float4(sx0 * inv0, sy0 * inv0, sx1 * inv1, sy1 * inv1);
+    if (stats) *reinterpret_cast<float4*>(stats + (size_t)blockIdx.x * 128 + 4 * cp) = make_float4(M0 * SSM_LN2, inv0, M1 * SSM_LN2, inv1);
+  }
+}
+
+// backward from the saved statistics: ONE streaming pass, x in -> dz out (ReLU mask of the producing conv fused), nothing staged;
+// loads are issued 8 positions ahead of the arithmetic / stores (the compiler does not move loads across the stores by itself)
+__global__ void __launch_bounds__(256) ssm_reg_bwd_kernel(const uint32_t* __restrict__ x, const float* __restrict__ x_map,
+                                                          const float* __restrict__ y_map, const float* __restrict__ temperature,
+                                                          const float* __restrict__ out, const float* __restrict__ stats,
+                                                          const float* __restrict__ dout, uint32_t* __restrict__ dx,
+                                                          float* __restrict__ dtemp, int HW, int relu_mask) {
+  __shared__ float red[32];
+  const int cp = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const size_t fo = (size_t)blockIdx.x * 128 + 4 * cp;
+  const float4 st = *reinterpret_cast<const float4*>(stats + fo);      // (max0, 1/sum0, max1, 1/sum1), natural-log units
+  const float4 eo = *reinterpret_cast<const float4*>(out + fo);        // (ex0, ey0, ex1, ey1)
+  const float4 gq = *reinterpret_cast<const float4*>(dout + fo);       // (gx0, gy0, gx1, gy1)
+  const float invT = 1.f / temperature[0], a = SSM_LOG2E * invT;
+  const float mb0 = st.x * SSM_LOG2E, mb1 = st.z * SSM_LOG2E;
+  // dl = p (gx (xm - ex) + gy (ym - ey)) = p (gx xm + gy ym - c) with c = gx ex + gy ey
+  const float c0 = gq.x * eo.x + gq.y * eo.y, c1 = gq.z * eo.z + gq.w * eo.w;
+  const uint32_t* xf = x + (size_t)blockIdx.x * HW * 32 + cp;
+  uint32_t* df = dx + (size_t)blockIdx.x * HW * 32 + cp;
+  float dt = 0.f;
+  for (int i0 = g; i0 < HW; i0 += 64) {
+    uint32_t u[8];
+    float xm[8], ym[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + 8 * k;
+      const bool ok = i < HW;
+      u[k] = ok ? __ldg(xf + (size_t)i * 32) : 0u;
+      xm[k] = ok ? __ldg(x_map + i) : 0.f;
+      ym[k] = ok ? __ldg(y_map + i) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + 8 * k;
+      if (i < HW) {
+        const float v0 = bf16lo(u[k]), v1 = bf16hi(u[k]);
+        const float p0 = ssm_ex2(fmaf(v0, a, -mb0)) * st.y, p1 = ssm_ex2(fmaf(v1, a, -mb1)) * st.w;
+        const float dl0 = p0 * (fmaf(gq.x, xm[k], gq.y * ym[k]) - c0), dl1 = p1 * (fmaf(gq.z, xm[k], gq.w * ym[k]) - c1);
+        dt = fmaf(dl0, v0, fmaf(dl1, v1, dt));
+        float o0 = dl0 * invT, o1 = dl1 * invT;
+        if (relu_mask) { if (!(v0 > 0.f)) o0 = 0.f; if (!(v1 > 0.f)) o1 = 0.f; }
+        const __nv_bfloat162 o = __floats2bfloat162_rn(o0, o1);
+        df[(size_t)i * 32] = *reinterpret_cast<const uint32_t*>(&o);
+      }
+    }
+  }
+  if (dtemp) {
+    dt = block_sum(dt, red);
+    if (threadIdx.x == 0) atomicAdd(dtemp, -dt * invT * invT);
+  }
+}
+
+static int ssm_reg_np(int HW, int C) {           // 0: shape not served by the streaming kernels (one warp = one 64-channel position row)
+  return (C == 64 && HW > 0) ? 1 : 0;
+}
+static bool ssm_reg_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HULC2_SSM_REG"); v = (e && e[0] == '0') ? 0 : 1; }   // A/B switch, read once
+  return v == 1;
+}
+
 static size_t ssm_bf16_smem(int HW, int C) {
   const int C2 = C / 2, G = SSM_NT / C2;
   return (((size_t)HW * C * 2 + 15) & ~(size_t)15) + (size_t)(6 * G * C2 + 2 * HW) * sizeof(float);
@@ -346,6 +483,13 @@ int hulc2_spatial_softmax_fwd_bf16(const void* x, const float* x_map, const floa
                                    int F, int HW, int C, cudaStream_t st) {
   if (F <= 0) return HULC2_OK;
   if (!ssm_threads(C)) { hulc2_set_error("spatial_softmax: C must be <= 256"); return HULC2_EINVAL; }
+  if (const int np = ssm_reg_enabled() ? ssm_reg_np(HW, C) : 0) {
+    const uint32_t* xu = (const uint32_t*)x;
+    (void)np;
+    ssm_reg_fwd_kernel<<<F, 256, 0, st>>>(xu, x_map, y_map, temperature, out, nullptr, HW);
+    HULC2_CHECK_LAUNCH();
+    return HULC2_OK;
+  }
   if (ssm_bf16_ok(HW, C)) {
     const size_t smem = ssm_bf16_smem(HW, C);
     static bool attr = false;
@@ -390,6 +534,13 @@ int hulc2_spatial_softmax_fwd_bf16_stats(const void* x, const float* x_map, cons
                                          float* stats, int F, int HW, int C, cudaStream_t st) {
   if (F <= 0) return HULC2_OK;
   if (!ssm_bf16_ok(HW, C) || !stats) { hulc2_set_error("spatial_softmax_fwd_bf16_stats: unsupported shape"); return HULC2_ENOTIMPL; }
+  if (const int np = ssm_reg_enabled() ? ssm_reg_np(HW, C) : 0) {
+    const uint32_t* xu = (const uint32_t*)x;
+    (void)np;
+    ssm_reg_fwd_kernel<<<F, 256, 0, st>>>(xu, x_map, y_map, temperature, out, stats, HW);
+    HULC2_CHECK_LAUNCH();
+    return HULC2_OK;
+  }
   const size_t smem = ssm_bf16_smem(HW, C);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(ssm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
@@ -402,6 +553,11 @@ int hulc2_spatial_softmax_bwd_bf16_stats(const void* x, const float* x_map, cons
                                          int relu_mask, cudaStream_t st) {
   if (F <= 0) return HULC2_OK;
   if (!ssm_bf16_ok(HW, C) || !stats || !out) { hulc2_set_error("spatial_softmax_bwd_bf16_stats: unsupported shape"); return HULC2_ENOTIMPL; }
+  if (ssm_reg_enabled() && ssm_reg_np(HW, C)) {
+    ssm_reg_bwd_kernel<<<F, 256, 0, st>>>((const uint32_t*)x, x_map, y_map, temperature, out, stats, dout, (uint32_t*)dx, dtemperature, HW, relu_mask);
+    HULC2_CHECK_LAUNCH();
+    return HULC2_OK;
+  }
   const size_t smem = ssm_bf16_smem(HW, C);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(ssm_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }

@@ -30,14 +30,11 @@ __device__ __forceinline__ float kl_term(float p, float lp, float q, float lq, b
 // global scratch: every CTA writes its block sum into CTA 0's shared memory (distributed shared memory), CTA 0 adds the
 // 8 partials in rank order.
 constexpr int KL_CLUSTER = 8;
-__global__ void __cluster_dims__(KL_CLUSTER, 1, 1) __launch_bounds__(512)
-    kl_fwd_kernel(const float* __restrict__ pp, const float* __restrict__ pr, float* __restrict__ loss, int rows, int classes, int B,
-                  float alpha, float beta) {
-  __shared__ float red[32];
-  __shared__ float part[KL_CLUSTER];
+// sum over the rows of a grid-stride range of KL(softmax(pr_row) || softmax(pp_row)), one THREAD per row
+__device__ __forceinline__ float kl_rows_sum(const float* __restrict__ pp, const float* __restrict__ pr, long long rows, int classes) {
   float acc = 0.f;
   const bool vec = (classes & 3) == 0;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
     float zp[32], zq[32];
     const float* a = pr + (long long)r * classes;
     const float* b = pp + (long long)r * classes;
@@ -72,6 +69,27 @@ __global__ void __cluster_dims__(KL_CLUSTER, 1, 1) __launch_bounds__(512)
       }
     acc += t;
   }
+  return acc;
+}
+
+// Large problems (rows beyond what the 8-CTA cluster covers in a few iterations; the size sweep of profiles/): a plain grid
+// over all SMs; every block adds its share of the (linear) loss with one atomic into the zeroed output.
+__global__ void __launch_bounds__(256) kl_fwd_grid_kernel(const float* __restrict__ pp, const float* __restrict__ pr, float* __restrict__ loss,
+                                                         long long rows, int classes, int B, float alpha, float beta) {
+  __shared__ float red[32];
+  const float tot = block_sum(kl_rows_sum(pp, pr, rows, classes), red);
+  if (threadIdx.x == 0) {
+    const float kl = tot / (float)B;
+    atomicAdd(loss, (alpha * kl + (1.f - alpha) * kl) * beta);
+  }
+}
+
+__global__ void __cluster_dims__(KL_CLUSTER, 1, 1) __launch_bounds__(512)
+    kl_fwd_kernel(const float* __restrict__ pp, const float* __restrict__ pr, float* __restrict__ loss, int rows, int classes, int B,
+                  float alpha, float beta) {
+  __shared__ float red[32];
+  __shared__ float part[KL_CLUSTER];
+  const float acc = kl_rows_sum(pp, pr, rows, classes);
   const float tot = block_sum(acc, red);
   if (threadIdx.x == 0) {
     // part[rank] of CTA 0, written through the cluster shared-memory window
@@ -165,7 +183,15 @@ extern "C" {
 int hulc2_kl_fwd(const float* pp, const float* pr, float* loss, int B, int cats, int classes, float alpha, float beta,
                  cudaStream_t st) {
   if (classes > 32 || classes <= 0) { hulc2_set_error("kl: class_size must be in [1,32]"); return HULC2_EINVAL; }
-  kl_fwd_kernel<<<KL_CLUSTER, 512, 0, st>>>(pp, pr, loss, B * cats, classes, B, alpha, beta);
+  const long long rows = (long long)B * cats;
+  if (rows > 4LL * KL_CLUSTER * 512) {          // beyond 16 k rows the 8-SM cluster is the bottleneck: all SMs + one atomic per block
+    if (cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) { hulc2_set_error("kl_fwd: memset failed"); return HULC2_ELAUNCH; }
+    long long blocks = (rows + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    kl_fwd_grid_kernel<<<(int)blocks, 256, 0, st>>>(pp, pr, loss, rows, classes, B, alpha, beta);
+  } else {
+    kl_fwd_kernel<<<KL_CLUSTER, 512, 0, st>>>(pp, pr, loss, (int)rows, classes, B, alpha, beta);
+  }
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }

@@ -73,7 +73,7 @@ def _ld(t: torch.Tensor) -> int:
 def gemm(M, N, K, A, a_rs, a_ks, B, b_rs, b_ks, Cout, ldc, *, a_off=0, b_off=0, c_off=0, bias=None, add=None, ld_add=0,
          mask=None, ld_mask=0, keep=None, ld_keep=0, keep_scale=1.0, relu=False, accumulate=False, alpha=1.0,
          a_inner=0, a_rs_outer=0, a_rs_inner=0, c_inner=0, c_rs_outer=0, c_rs_inner=0, precision=None,
-         A16=None, B16=None, C16=None, ld16=0, c16_off=0):
+         A16=None, B16=None, C16=None, ld16=0, c16_off=0, rowsum=None):
     """C[m,n] = epi(alpha * sum_k A(m,k) B(n,k)); offsets are in elements.
     A16/B16: bf16 mirrors of the tensors A/B (same flat layout, see :func:`to_bf16`) -> TMA-fed tcgen05 kernel;
     C16: bf16 tensor that additionally receives the result (row stride ld16)."""
@@ -98,6 +98,7 @@ def gemm(M, N, K, A, a_rs, a_ks, B, b_rs, b_ks, Cout, ldc, *, a_off=0, b_off=0, 
         g.B16 = None if B16 is None else B16.data_ptr() + 2 * b_off
         g.C16 = None if C16 is None else C16.data_ptr() + 2 * c16_off
         g.ld16 = ld16
+    g.rowsum = _p(rowsum)
     _lib.tag(f"gemm[M={int(M)},N={int(N)},K={int(K)}]", 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N))
     call("hulc2_gemm", C.byref(g))
 
@@ -207,9 +208,10 @@ def weight16(W: torch.Tensor) -> torch.Tensor:
 
 def gemm16(M, N, K, A16, a_rs, a_ks, B16, b_rs, b_ks, Cout, ldc, *, a_off=0, b_off=0, c_off=0, bias=None, add=None, ld_add=0,
            mask=None, ld_mask=0, keep=None, ld_keep=0, keep_scale=1.0, relu=False, accumulate=False, alpha=1.0,
-           C16=None, ld16=0):
+           C16=None, ld16=0, rowsum=None):
     """C[m,n] = epi(alpha * sum_k A(m,k) B(n,k)) with bf16-only operands (TMA-fed tcgen05 kernel): A(m,k) =
-    A16[a_off + m*a_rs + k*a_ks], one of (a_rs, a_ks) being 1; same for B.  C fp32 (+ optional bf16 copy C16)."""
+    A16[a_off + m*a_rs + k*a_ks], one of (a_rs, a_ks) being 1; same for B.  C fp32 (+ optional bf16 copy C16).
+    rowsum: optional fp32 [M] that receives sum_k A(m,k) -- the bias gradient when this is a weight-gradient contraction."""
     ws = workspace(Cout.device)
     g = GemmArgs()
     g.M, g.N, g.K = int(M), int(N), int(K)
@@ -225,6 +227,7 @@ def gemm16(M, N, K, A16, a_rs, a_ks, B16, b_rs, b_ks, Cout, ldc, *, a_off=0, b_o
     g.precision = 1
     g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
     g.C16, g.ld16 = _p(C16), ld16
+    g.rowsum = _p(rowsum)
     _lib.tag(f"gemm16[M={int(M)},N={int(N)},K={int(K)}]", 2.0 * M * N * K,
              2.0 * (M * K + N * K) + M * N * (4.0 + (2.0 if C16 is not None else 0.0) + (4.0 if accumulate or add is not None else 0.0)))
     call("hulc2_gemm", C.byref(g))
@@ -315,14 +318,15 @@ class MLPFunction(torch.autograd.Function):
                 N, K = W.shape
                 in16 = mirrors[i]
                 ld_in = in16.shape[1]
+                db = grad_buffer(wb[2 * i + 1]) if ctx.needs_input_grad[5 + 2 * i] else None
                 if ctx.needs_input_grad[4 + 2 * i]:
                     dW = grad_buffer(W)
-                    gemm16(N, K, M, g16, 1, ldg, in16, 1, ld_in, dW, K)          # dW = g^T inp (both MN-major)
+                    # dW = g^T inp (both MN-major); the bias gradient = row sums of g^T rides along (one more narrow MMA)
+                    gemm16(N, K, M, g16, 1, ldg, in16, 1, ld_in, dW, K, rowsum=db)
                     grads[2 * i] = dW
-                if ctx.needs_input_grad[5 + 2 * i]:
-                    db = grad_buffer(wb[2 * i + 1])
+                elif db is not None:
                     colsum(g, N, M, N, db)
-                    grads[2 * i + 1] = db
+                grads[2 * i + 1] = db
                 if i > 0 or ctx.needs_input_grad[0]:
                     gi = torch.empty(M, K, device=W.device, dtype=torch.float32)
                     gi16 = torch.empty(M, _pad8(K), device=W.device, dtype=torch.bfloat16) if i > 0 else None
@@ -538,12 +542,12 @@ def convb_dgrad(dy, w_oihw, xmask, F, C, H, W, Cout, k, stride, name="conv") -> 
     return dx
 
 
-def convb_wgrad(x, dy, F, C, H, W, Cout, k, stride, dw_shape, dw_layout=0, name="conv", param=None):
+def convb_wgrad(x, dy, F, C, H, W, Cout, k, stride, dw_shape, dw_layout=0, name="conv", param=None, bias_param=None):
     """(dw fp32 in dw_shape (OIHW), db fp32 [Cout]) from the bf16 NHWC input x and output gradient dy.  ``param``: the weight
     tensor the gradient belongs to (lets the result land directly in the optimizer's gradient arena, see grad_buffer)."""
     ws = workspace(x.device)
     dw = grad_buffer(param) if param is not None and tuple(param.shape) == tuple(dw_shape) else torch.empty(dw_shape, device=x.device, dtype=torch.float32)
-    db = torch.empty(Cout, device=x.device, dtype=torch.float32)
+    db = grad_buffer(bias_param) if bias_param is not None and bias_param.numel() == Cout else torch.empty(Cout, device=x.device, dtype=torch.float32)
     a = _cb(F, C, H, W, Cout, k, stride)
     a.x, a.dy, a.dw, a.db, a.dw_layout = x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), dw_layout
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
@@ -651,15 +655,15 @@ def _convb_trunk_fwd(x, w1, b1, w2, b2, w3, b3):
     return xs, y1, y2, y3
 
 
-def _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3):
+def _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3, biases=(None, None, None)):
     """dz3 = bf16 gradient wrt conv3's pre-activation (already ReLU-masked).  Returns the six parameter gradients."""
     F_, H4, W4, C16 = xs.shape
     H1, W1, H2, W2 = y1.shape[1], y1.shape[2], y2.shape[1], y2.shape[2]
-    dw3, db3 = convb_wgrad(y2, dz3, F_, 64, H2, W2, 64, 3, 1, tuple(w3.shape), name="c3", param=w3)
+    dw3, db3 = convb_wgrad(y2, dz3, F_, 64, H2, W2, 64, 3, 1, tuple(w3.shape), name="c3", param=w3, bias_param=biases[2])
     dz2 = convb_dgrad(dz3, w3, y2, F_, 64, H2, W2, 64, 3, 1, name="c3")
-    dw2, db2 = convb_wgrad(y1, dz2, F_, 32, H1, W1, 64, 4, 2, tuple(w2.shape), name="c2", param=w2)
+    dw2, db2 = convb_wgrad(y1, dz2, F_, 32, H1, W1, 64, 4, 2, tuple(w2.shape), name="c2", param=w2, bias_param=biases[1])
     dz1 = convb_dgrad(dz2, w2, y1, F_, 32, H1, W1, 64, 4, 2, name="c2")
-    dw1, db1 = convb_wgrad(xs, dz1, F_, C16, H4, W4, 32, 2, 1, tuple(w1.shape), dw_layout=1, name="c1", param=w1)
+    dw1, db1 = convb_wgrad(xs, dz1, F_, C16, H4, W4, 32, 2, 1, tuple(w1.shape), dw_layout=1, name="c1", param=w1, bias_param=biases[0])
     return {"w1": dw1, "b1": db1, "w2": dw2, "b2": db2, "w3": dw3, "b3": db3}
 
 
@@ -671,6 +675,7 @@ class StaticConvSSM(torch.autograd.Function):
         _, (F_, _c, _h, _w) = _frame_groups(x)
         out = torch.empty(F_, 128, device=w1.device, dtype=torch.float32)
         ctx.bf16 = convb_trunk_supported(x)
+        ctx.biases = (b1, b2, b3)              # only their identity is used: the bias gradients land in their arena slices
         if not ctx.bf16:
             x = _frames_tensor(x)
         if ctx.bf16:
@@ -713,7 +718,7 @@ class StaticConvSSM(torch.autograd.Function):
             else:
                 call("hulc2_spatial_softmax_bwd_bf16", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
                      dout.data_ptr(), dz3.data_ptr(), _p(dtemp), F_, HW, 64, 1)
-            g = _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3)
+            g = _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3, ctx.biases)
             return (None, g["w1"], g["b1"], g["w2"], g["b2"], g["w3"], g["b3"], None, None, dtemp)
         x, y1, y2, y3, w2, w3, x_map, y_map, temperature, out = ctx.saved_tensors
         F_ = x.shape[0]
@@ -735,6 +740,7 @@ class GripperConvFlatten(torch.autograd.Function):
     def forward(ctx, x, w1, b1, w2, b2, w3, b3):
         _, (F_, _c, _h, _w) = _frame_groups(x)
         ctx.bf16 = convb_trunk_supported(x)
+        ctx.biases = (b1, b2, b3)              # only their identity is used: the bias gradients land in their arena slices
         if not ctx.bf16:
             x = _frames_tensor(x)
         if ctx.bf16:
@@ -760,7 +766,7 @@ class GripperConvFlatten(torch.autograd.Function):
             HW = y3.shape[1] * y3.shape[2]
             dz3 = torch.empty_like(y3)
             call("hulc2_nchw_to_nhwc_bf16", dflat.data_ptr(), dz3.data_ptr(), F_, HW, 64, y3.data_ptr())
-            g = _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3)
+            g = _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3, ctx.biases)
             return (None, g["w1"], g["b1"], g["w2"], g["b2"], g["w3"], g["b3"])
         x, y1, y2, y3, w2, w3 = ctx.saved_tensors
         F_ = x.shape[0]
@@ -788,18 +794,20 @@ class LayerNormFunction(torch.autograd.Function):
         call("hulc2_layernorm_fwd", x2.data_ptr(), _ld(x2), _p(r2), _ld(r2) if r2 is not None else 0, _p(keep), keep_scale,
              gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), D, _p(t), mean.data_ptr(), rstd.data_ptr(), rows, D, eps)
         ctx.save_for_backward(t if t is not None else x2, gamma, mean, rstd)
+        ctx.beta = beta                        # identity only (grad_buffer)
         ctx.keep, ctx.keep_scale, ctx.has_res, ctx.shape = keep, keep_scale, res is not None, x.shape
         return y.view(x.shape)
 
     @staticmethod
     def backward(ctx, dy):
         t, gamma, mean, rstd = ctx.saved_tensors
+        beta = ctx.beta
         rows, D = t.shape[0], gamma.shape[0]
         dy2 = _rows2d(dy.contiguous())
         dx = torch.empty(rows, D, device=dy.device, dtype=torch.float32)
         dres = torch.empty(rows, D, device=dy.device, dtype=torch.float32) if ctx.has_res else None
         dgamma = grad_buffer(gamma, zero=True)
-        dbeta = torch.zeros(D, device=dy.device, dtype=torch.float32)
+        dbeta = grad_buffer(beta, zero=True)
         call("hulc2_layernorm_bwd", dy2.data_ptr(), D, t.data_ptr(), _ld(t), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
              dx.data_ptr(), D, _p(dres), _p(ctx.keep), ctx.keep_scale, dgamma.data_ptr(), dbeta.data_ptr(), rows, D)
         return (dx.view(ctx.shape), dres.view(ctx.shape) if dres is not None else None, None, None, dgamma, dbeta, None)
@@ -1111,6 +1119,7 @@ class RNNDecoderFunction(torch.autograd.Function):
         call("hulc2_copy2d", H0.data_ptr() + 4 * (S - 1) * B * H, B * H, hn.data_ptr(), B * H, 1, B * H, 0)
         call("hulc2_copy2d", H1.data_ptr() + 4 * (S - 1) * B * H, B * H, hn.data_ptr() + 4 * B * H, B * H, 1, B * H, 0)
         ctx.b16 = b16
+        ctx.bias_params = (bi0, bh0, bi1, bh1)     # identity only: their gradients land in the arena slices (grad_buffer)
         extra = (plan16, goal16, embT16, H0h) if b16 else ()
         ctx.save_for_backward(plan, embT, goal, H0, H1, wi0, wh0, wi1, wh1, h00 if h00 is not None else plan.new_empty(0),
                               h01 if h01 is not None else plan.new_empty(0), *extra)
@@ -1202,9 +1211,11 @@ class RNNDecoderFunction(torch.autograd.Function):
         if ctx.has_h0:
             gemm(H, H, B, dz1, 1, H, h01, 1, H, dwh1, H, accumulate=True)
         dwi1 = grad_buffer(wi1)
-        gemm16(H, H, S * B, dz1h, 1, H, H0h, 1, H, dwi1, H)
-        db1 = torch.empty(H, device=dev, dtype=torch.float32)
-        colsum(dz1, H, S * B, H, db1)
+        bi0, bh0, bi1, bh1 = ctx.bias_params
+        db1 = grad_buffer(bi1)
+        gemm16(H, H, S * B, dz1h, 1, H, H0h, 1, H, dwi1, H, rowsum=db1)         # + bias gradient = row sums of dz1^T
+        db1h = grad_buffer(bh1)                                                  # b_hh receives the same gradient as b_ih
+        call("hulc2_copy2d", db1.data_ptr(), H, db1h.data_ptr(), H, 1, H, 0)
         dz0 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         gemm16(S * B, H, H, dz1h, H, 1, wi1h, 1, H, dz0, H)                      # dH0 = dz1 W_ih1
         _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H, S * (2.0 * H * H + 16.0 * B * H))
@@ -1217,14 +1228,13 @@ class RNNDecoderFunction(torch.autograd.Function):
             call("hulc2_fill", dwh0.data_ptr(), dwh0.numel(), 0.0)
         if ctx.has_h0:
             gemm(H, H, B, dz0, 1, H, h00, 1, H, dwh0, H, accumulate=True)
-        db0 = torch.empty(H, device=dev, dtype=torch.float32)
-        colsum(dz0, H, S * B, H, db0)
+        db0 = grad_buffer(bi0)
         dzsum = torch.empty(B, H, device=dev, dtype=torch.float32)
         colsum(dz0, B * H, S, B * H, dzsum)                                      # sum over time
         dzsumh = to_bf16(dzsum)
         dwi0 = grad_buffer(wi0)
         gemm16(H, P, B, dzsumh, 1, H, plan16, 1, P, dwi0, In)
-        gemm16(H, Es, S * B, dz0h, 1, H, embT16, 1, Es, dwi0, In, c_off=P)
+        gemm16(H, Es, S * B, dz0h, 1, H, embT16, 1, Es, dwi0, In, c_off=P, rowsum=db0)   # + bias gradient = row sums of dz0^T
         gemm16(H, G, B, dzsumh, 1, H, goal16, 1, ldg, dwi0, In, c_off=P + Es)
         dplan = dgoal = demb = None
         if ctx.needs_input_grad[0]:
@@ -1238,7 +1248,9 @@ class RNNDecoderFunction(torch.autograd.Function):
             gemm16(S * B, Es, H, dz0h, H, 1, wi0h, 1, In, dembT, Es, b_off=P)
             demb = torch.empty(B, S, Es, device=dev, dtype=torch.float32)
             call("hulc2_transpose01", dembT.data_ptr(), B * Es, Es, demb.data_ptr(), Es, S, B, Es, 0)
-        return (dplan, demb, dgoal, None, dwi0, dwh0, db0, db0.clone(), dwi1, dwh1, db1, db1.clone())
+        db0h = grad_buffer(bh0)
+        call("hulc2_copy2d", db0.data_ptr(), H, db0h.data_ptr(), H, 1, H, 0)
+        return (dplan, demb, dgoal, None, dwi0, dwh0, db0, db0h, dwi1, dwh1, db1, db1h)
 
 
 class GatedRNNDecoderFunction(torch.autograd.Function):
@@ -1469,8 +1481,9 @@ class DecoderLossFunction(torch.autograd.Function):
                  ls_min, alpha, 1, B)
             b0 += a.shape[0]
         dbias = torch.empty(3 * AM + 2, device=dev, dtype=torch.float32)
-        colsum(dheads, HEAD_LD, rows, 3 * AM + 2, dbias)
         dH = torch.empty(S, B, H, device=dev, dtype=torch.float32)
+        if not ctx.b16:
+            colsum(dheads, HEAD_LD, rows, 3 * AM + 2, dbias)
         if ctx.b16:
             NH = 3 * AM + 2
             Hs16 = Hs                                                     # the bf16 mirror was saved instead of the fp32 states
@@ -1478,7 +1491,7 @@ class DecoderLossFunction(torch.autograd.Function):
             Wcat = torch.cat([weight16(wp), weight16(wm), weight16(wsc), weight16(wg)], 0)
             gemm16(rows, H, NH, dh16, ldh, 1, Wcat, 1, H, dH, H)          # dH = dheads Wcat
             dW = torch.empty(NH, H, device=dev, dtype=torch.float32)
-            gemm16(NH, H, rows, dh16, 1, ldh, Hs16, 1, H, dW, H)          # dWcat = dheads^T Hs
+            gemm16(NH, H, rows, dh16, 1, ldh, Hs16, 1, H, dW, H, rowsum=dbias)   # dWcat = dheads^T Hs, dbias = its row sums
             return (dH, None, None, None, None, dW[0:AM], dbias[0:AM], dW[AM : 2 * AM], dbias[AM : 2 * AM], dW[2 * AM : 3 * AM],
                     dbias[2 * AM : 3 * AM], dW[3 * AM :], dbias[3 * AM :])
         wgrads = []
@@ -1618,20 +1631,20 @@ class WeightedSumFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, weights, *xs):
-        out = torch.zeros((), device=xs[0].device, dtype=torch.float32)
-        for w, x in zip(weights, xs):
-            call("hulc2_axpy", x.contiguous().data_ptr(), out.data_ptr(), 1, float(w))
+        n = len(xs)
+        assert 1 <= n <= 8 and len(weights) == n
+        xs = [_f32(x).contiguous() for x in xs]
+        out = torch.empty((), device=xs[0].device, dtype=torch.float32)
+        call("hulc2_weighted_sum", (C.c_void_p * n)(*[x.data_ptr() for x in xs]), (C.c_float * n)(*weights), n, out.data_ptr())
         ctx.weights = weights
         return out
 
     @staticmethod
     def backward(ctx, g):
-        outs = []
-        for w in ctx.weights:
-            t = torch.zeros((), device=g.device, dtype=torch.float32)
-            call("hulc2_axpy", g.contiguous().data_ptr(), t.data_ptr(), 1, float(w))
-            outs.append(t)
-        return (None, *outs)
+        n = len(ctx.weights)
+        outs = torch.empty(n, device=g.device, dtype=torch.float32)
+        call("hulc2_weighted_fanout", g.contiguous().data_ptr(), (C.c_float * n)(*ctx.weights), n, outs.data_ptr())
+        return (None, *outs.unbind(0))
 
 
 def weighted_sum(weights, xs):

@@ -177,6 +177,33 @@ class PolicyTrainer:
         caller.wait_stream(self.stream)
         return loss
 
+    def profile_replay(self, batch, passes: int = 3) -> List[dict]:
+        """Per-call timeline of a REPLAYED step: captures the step body once more with an external timing event on either
+        side of every C-ABI call (event-record nodes of the graph, ``_lib.profile_begin_graph``), replays that graph
+        ``passes`` times and returns one {key: record} dict per replay.  What bench.py's roofline table is built from: the
+        durations are those of the kernels inside the real replay (no host launch latency, no cold-cache artefact)."""
+        from . import _lib
+
+        assert self.use_graph and self.static_batch is not None, "profile_replay needs a trainer that has captured its step"
+        _zip_copy(self.static_batch, batch)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        _lib.profile_begin_graph()
+        try:
+            with torch.cuda.graph(g, stream=self.stream):
+                self._step_body(self.static_batch, 0)
+            for a in self.optimizer._arenas:       # the capture executed nothing (see _capture)
+                if a["n"]:
+                    a["step"] -= 1
+            out = []
+            for _ in range(passes):
+                g.replay()
+                self.optimizer.note_replayed_step()
+                out.append(_lib.profile_read_graph())
+        finally:
+            _lib.profile_end_graph()
+        return out
+
     def _capture(self, batch, batch_idx):
         # The graph reads its inputs from the trainer's OWN static buffers; every later batch is copied into them (a caller
         # that wants zero-copy steps fills / passes ``trainer.static_batch`` itself).  The caller's tensors are never written.

@@ -42,7 +42,11 @@ int hulc2_device_supports_tcgen05(void);
  * kernel (csrc/gemm_tma_sm100.cu); otherwise the gather kernel converts the fp32 operands on the fly.  A and/or B may be
  * NULL when the mirror is the only copy (then the strides describe the mirror and a layout the TMA path cannot take is
  * an error, not a fallback).  C16 (row stride ld16) additionally receives the epilogue result as bf16: the next layer's
- * operand. */
+ * operand.
+ * rowsum (precision 1, TMA path only, optional): float[M] that receives sum_k A(m,k) of the bf16 operand -- in a weight
+ * gradient dW = g^T x this is the bias gradient sum_rows g (the reference's autograd of nn.Linear's bias), computed by one
+ * more narrow MMA against a constant ones operand instead of a separate column-sum pass.  Requesting it on a problem the
+ * TMA path cannot take is an error. */
 typedef struct {
   int M, N, K;
   const float* A; long long a_rs, a_ks; int a_inner; long long a_rs_outer, a_rs_inner;
@@ -58,6 +62,7 @@ typedef struct {
   void* workspace; long long workspace_bytes;
   const void* A16; const void* B16;
   void* C16; long long ld16;
+  float* rowsum;
 } hulc2_gemm_args;
 int hulc2_gemm(const hulc2_gemm_args* a, hulc2_stream_t stream);
 /* number of contractions served by the TMA-fed kernel so far (tests assert the fast path was taken) */
@@ -171,6 +176,11 @@ int hulc2_transpose01(const float* src, long long src_s0, long long src_s1, floa
                       int D2, int accumulate, hulc2_stream_t stream);
 int hulc2_fill(float* dst, long long n, float value, hulc2_stream_t stream);
 int hulc2_axpy(const float* x, float* y, long long n, float a, hulc2_stream_t stream); /* y += a*x */
+/* Scalar loss combine (hulc2/models/hulc2.py:243,426-430: total = action + kl_beta*kl + clip_beta*clip and the logged
+ * means): out[0] = sum_i w[i] * xs[i][0] for n <= 8 device scalars (xs, w: HOST arrays read at call time), and its
+ * gradient fan-out out[i] = w[i] * g[0]. */
+int hulc2_weighted_sum(const float* const* xs, const float* w, int n, float* out, hulc2_stream_t stream);
+int hulc2_weighted_fanout(const float* g, const float* w, int n, float* out, hulc2_stream_t stream);
 int hulc2_colsum(const float* x, long long ld, long long rows, int cols, float* out, int accumulate, void* workspace,
                  long long workspace_bytes, hulc2_stream_t stream);
 int hulc2_relu_mask(const float* dy, const float* y, float* dz, long long n, hulc2_stream_t stream);

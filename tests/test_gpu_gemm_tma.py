@@ -126,3 +126,42 @@ def test_tma_falls_back_when_unaligned():
     ops.gemm(M, N, K, A, K, 1, B, K, 1, out, N, A16=ops.to_bf16(A), B16=ops.to_bf16(B))
     assert_close(out, _bf(A.cpu()) @ _bf(B.cpu()).t(), 1e-4)
     assert _launches() == n0
+
+
+@pytest.mark.parametrize("Mw,Kw,R", [(2048, 2048, 4096), (128, 2048, 4096), (2048, 128, 4096), (184, 2048, 4096), (2048, 160, 128),
+                                     (64, 512, 4096), (384, 128, 4096), (32, 128, 200), (1024, 4096, 128), (72, 40, 1000)])
+def test_tma_rowsum_bias_gradient(Mw, Kw, R):
+    """Weight-gradient contraction dW[Mw,Kw] = g^T x over R rows (both operands MN-major) with the bias gradient
+    sum_rows g riding along as an extra ones-operand MMA (hulc2_gemm_args.rowsum): every tiling / split-K choice."""
+    from hulc2_b200 import ops
+
+    g, x = _rand(R, Mw, seed=21), _rand(R, Kw, seed=22)
+    g16, x16 = ops.to_bf16(g.to(DEV)), ops.to_bf16(x.to(DEV))
+    dW = torch.empty(Mw, Kw, device=DEV)
+    db = torch.full((Mw,), 7.0, device=DEV)           # overwritten, not accumulated
+    n0 = _launches()
+    ops.gemm16(Mw, Kw, R, g16, 1, Mw, x16, 1, Kw, dW, Kw, rowsum=db)
+    torch.cuda.synchronize()
+    assert _launches() - n0 == 1
+    assert_close(dW, _bf(g).t() @ _bf(x), 1e-4)
+    assert_close(db, _bf(g).double().sum(0).float(), 1e-5)
+    # K-major A as well: rowsum[m] = sum_k A[m, k]
+    A = _rand(Mw, R, seed=23)
+    out = torch.empty(Mw, Kw, device=DEV)
+    rs = torch.empty(Mw, device=DEV)
+    ops.gemm16(Mw, Kw, R, ops.to_bf16(A.to(DEV)), R, 1, x16, 1, Kw, out, Kw, rowsum=rs)
+    torch.cuda.synchronize()
+    assert_close(out, _bf(A) @ _bf(x), 1e-4)
+    assert_close(rs, _bf(A).double().sum(1).float(), 1e-5)
+
+
+def test_rowsum_needs_the_tma_path():
+    """No silent fallback: the fp32 CUDA-core path and the bf16 gather path do not serve rowsum -> error."""
+    from hulc2_b200 import ops
+
+    A, B = _rand(64, 64, seed=1).to(DEV), _rand(64, 64, seed=2).to(DEV)
+    out, rs = torch.empty(64, 64, device=DEV), torch.empty(64, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.gemm(64, 64, 64, A, 64, 1, B, 64, 1, out, 64, precision=0, rowsum=rs)
+    with pytest.raises(RuntimeError):
+        ops.gemm(64, 64, 64, A, 64, 1, B, 64, 1, out, 64, precision=1, rowsum=rs)       # no bf16 mirrors -> gather kernel
