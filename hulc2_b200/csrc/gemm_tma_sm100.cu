@@ -15,6 +15,7 @@
 // operands of a weight gradient); the only difference is the TMA box orientation and the UMMA descriptor.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "gemm_common.cuh"
 #include "sm100.cuh"
@@ -155,6 +156,23 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
     const bool mvalid = m < p.M;
     const Epilogue& E = p.E;
     const long long crow = mvalid ? c_row_off(E, m) : 0;
+    // The ReLU-mask / dropout-keep operands of the epilogue are the only long-latency loads between the accumulator and the
+    // stores (ncu r02: the big-output, small-K contractions sat on long_scoreboard with 9 % of the issue slots busy: one load
+    // group in flight per thread, because loads are not moved across the stores of the previous group).  They are fetched one
+    // 32-column chunk AHEAD into registers: the first chunk while the main loop still runs, chunk c + 1 before chunk c is stored.
+    uint32_t mk_next[4][8];
+    uint2 kp_next[4];
+    const bool pf = p.vec8 && mvalid && p.splits == 1 && (E.mask || E.keep);
+    auto prefetch = [&](int c) {
+      if (!pf || n0 + c + 32 > p.N || c >= BN) return;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + c + 8 * j;
+        if (E.mask) ldg256_nc(E.mask + (long long)m * E.ld_mask + n, mk_next[j]);
+        if (E.keep) kp_next[j] = *reinterpret_cast<const uint2*>(E.keep + (long long)m * E.ld_keep + n);
+      }
+    };
+    prefetch(0);
     mbar_wait_relaxed(smem_u32(&acc_bar), 0);
     tc_fence_after();
     const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
@@ -192,6 +210,15 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
       if (p.vec8 && n0 + c + 32 <= p.N) {
         // 8 columns per access: rows are >= 128 bytes apart across lanes, so every access is its own L1 wavefront -- 256-bit
         // LDG/STG halve them (the big-output, small-K contractions are bound by exactly this: 4096x2048x128 took 80 us)
+        uint32_t mk[4][8];
+        uint2 kp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          kp[j] = kp_next[j];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) mk[j][e] = mk_next[j][e];
+        }
+        prefetch(c + 32);
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           const int n = n0 + c + j;
@@ -213,11 +240,11 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
           }
-          if (E.mask) { ldg256_nc(E.mask + (long long)m * E.ld_mask + n, t);
+          if (E.mask) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(t[e]) > 0.f ? v[e] : 0.f; }
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(mk[j >> 3][e]) > 0.f ? v[e] : 0.f; }
           if (E.keep) {
-            const uint2 k2 = *reinterpret_cast<const uint2*>(E.keep + (long long)m * E.ld_keep + n);
+            const uint2 k2 = kp[j >> 3];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = (((e < 4 ? k2.x : k2.y) >> (8 * (e & 3))) & 0xffu) ? v[e] * E.keep_scale : 0.f;
           }
@@ -326,6 +353,11 @@ int launch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap&
 }
 
 bool al(const void* p, uintptr_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
+bool gemm_small_k_bn128() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HULC2_GEMM_SMALLK_BN128"); v = (e && e[0] == '1') ? 1 : 0; }   // A/B switch (default off), read once
+  return v == 1;
+}
 
 }  // namespace
 
@@ -353,7 +385,9 @@ int hulc2_gemm_tma_impl(const hulc2_gemm_args* a, cudaStream_t st) {
   const int mt = hulc2_cdiv(a->M, BM);
   int BN = a->N <= 64 ? 64 : (a->N <= 128 ? 128 : 256);
   if (BN == 256 && (long long)mt * hulc2_cdiv(a->N, 256) < 148) BN = 128;   // more, smaller tiles when the grid is short
-  if (BN == 256 && a->rowsum) BN = 128;                                      // the row-sum accumulator doubles the TMEM allocation
+  if (BN == 256 && a->rowsum) BN = 128;
+  // small K with a big output: the epilogue is the kernel; 128-column tiles put four CTAs (16 epilogue warps) on an SM instead of two
+  if (BN == 256 && p.ktiles <= 4 && gemm_small_k_bn128()) BN = 128;                                      // the row-sum accumulator doubles the TMEM allocation
   if (BN == 128 && a->N > 64 && (long long)mt * hulc2_cdiv(a->N, 128) < 74 && p.ktiles <= 8) BN = 64;
   const long long tiles = (long long)mt * hulc2_cdiv(a->N, BN);
 
