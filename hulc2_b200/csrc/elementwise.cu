@@ -27,6 +27,21 @@ __global__ void copy2d_kernel(const float* __restrict__ src, long long lds, floa
   }
 }
 
+// 16-byte variant (aligned rows, cols % 4 == 0): the decoder's broadcast of the per-window term over 32 steps and the in-place
+// recurrence's input copy move 33 MB each
+__global__ void __launch_bounds__(256) copy2d_vec4_kernel(const float4* __restrict__ src, long long lds4, float4* __restrict__ dst, long long ldd4,
+                                                          long long rows, int cols4, int accumulate) {
+  const long long total = rows * cols4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = (int)(i - r * cols4);
+    float4 v = __ldg(src + r * lds4 + c);
+    float4* d = dst + r * ldd4 + c;
+    if (accumulate) { const float4 o = *d; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+    *d = v;
+  }
+}
+
 __global__ void fill_kernel(float* __restrict__ dst, long long n, float value) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = value;
 }
@@ -107,6 +122,30 @@ __global__ void __launch_bounds__(256) colsum_partial4_kernel(const float* __res
     for (int j = 0; j < 8; ++j) acc += red[j][t >> 2][t & 3];
     partial[(long long)blockIdx.y * cols + blockIdx.x * 128 + t] = acc;
   }
+}
+// Short-and-wide sums (the decoder's sum over time: 32 rows x B*H columns): thread = 4 adjacent columns, all rows, 8 independent
+// 16-byte loads in flight; one pass, no partials.
+__global__ void __launch_bounds__(256) colsum_wide_kernel(const float* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ out,
+                                                          int accumulate) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (c >= cols) return;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int r = 0;
+  for (; r + 8 <= rows; r += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(x + (long long)(r + k) * ld + c));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s0 += (double)v[k].x; s1 += (double)v[k].y; s2 += (double)v[k].z; s3 += (double)v[k].w; }
+  }
+  for (; r < rows; ++r) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + (long long)r * ld + c));
+    s0 += (double)a.x; s1 += (double)a.y; s2 += (double)a.z; s3 += (double)a.w;
+  }
+  float4* o = reinterpret_cast<float4*>(out + c);
+  float4 res = make_float4((float)s0, (float)s1, (float)s2, (float)s3);
+  if (accumulate) { const float4 p = *o; res.x += p.x; res.y += p.y; res.z += p.z; res.w += p.w; }
+  *o = res;
 }
 // One-launch column sum for the bias gradients (rows <= a few thousand): a thread-block cluster of 8 CTAs splits the rows of a
 // 128-column block, every CTA writes its 128 double partials into rank 0's shared memory (DSMEM), rank 0 adds them in rank order.
@@ -194,6 +233,34 @@ __global__ void transpose_frames_kernel(const TI* __restrict__ src, TO* __restri
       st_el(dst + o, v);
     }
   }
+}
+
+// Small frames (the gripper trunk's 7 x 7 x 64 maps: the 32 x 32 tiles above are half empty and every access is a scalar): one
+// block per frame, the whole frame through shared memory, both the read and the write linear in memory.
+template <typename TI, typename TO, typename TM>
+__global__ void __launch_bounds__(256) transpose_small_frames_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int rows, int cols,
+                                                                     const TM* __restrict__ mask) {
+  extern __shared__ float tsf_tile[];                 // [rows][pitch], pitch odd: conflict-free column reads
+  const int pitch = cols | 1, n = rows * cols;
+  const long long fbase = (long long)blockIdx.x * n;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int r = i / cols, c = i - r * cols;
+    tsf_tile[r * pitch + c] = ld_el(src + fbase + i);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < n; o += 256) {
+    const int c = o / rows, r = o - c * rows;
+    float v = tsf_tile[r * pitch + c];
+    if (mask) v = ld_el(mask + fbase + o) > 0.f ? v : 0.f;
+    st_el(dst + fbase + o, v);
+  }
+}
+template <typename TI, typename TO, typename TM>
+static bool transpose_small(const TI* src, TO* dst, int F, int rows, int cols, const TM* mask, cudaStream_t st) {
+  const size_t smem = (size_t)rows * (cols | 1) * sizeof(float);
+  if (smem > 48 * 1024) return false;
+  transpose_small_frames_kernel<TI, TO, TM><<<F, 256, smem, st>>>(src, dst, rows, cols, mask);
+  return true;
 }
 
 // dst[d1, d0, :D2] (+)= src[d0*src_s0 + d1*src_s1 + :D2]   (batch-major <-> time-major row shuffles)
@@ -368,6 +435,14 @@ extern "C" {
 int hulc2_copy2d(const float* src, long long lds, float* dst, long long ldd, long long rows, int cols, int accumulate,
                  cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return HULC2_OK;
+  if (cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0 && rows * cols >= 4096) {
+    long long blocks = (rows * (cols / 4) + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    copy2d_vec4_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(src), lds / 4, reinterpret_cast<float4*>(dst), ldd / 4, rows,
+                                                    cols / 4, accumulate);
+    HULC2_CHECK_LAUNCH();
+    return HULC2_OK;
+  }
   copy2d_kernel<<<grid_for(rows * cols, 256), 256, 0, st>>>(src, lds, dst, ldd, rows, cols, accumulate);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
@@ -433,6 +508,11 @@ int hulc2_colsum(const float* x, long long ld, long long rows, int cols, float* 
   if (cols <= 0) return HULC2_OK;
   const bool vec4 = (cols % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   int colblocks = hulc2_cdiv(cols, vec4 ? 128 : 32);
+  if (vec4 && rows > 0 && rows <= 64 && cols >= 32768 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+    colsum_wide_kernel<<<hulc2_cdiv(cols / 4, 256), 256, 0, st>>>(x, ld, (int)rows, cols, out, accumulate);
+    HULC2_CHECK_LAUNCH();
+    return HULC2_OK;
+  }
   if (vec4 && rows <= 32768 && rows > 0) {
     colsum_cluster_kernel<<<dim3(colblocks, CS_CLUSTER), dim3(32, 8), 0, st>>>(x, ld, rows, cols, out, accumulate);
     HULC2_CHECK_LAUNCH();
@@ -472,6 +552,7 @@ int hulc2_nchw_to_nhwc(const float* src, float* dst, int F, int HW, int C, const
 // bf16 conv trunk <-> fp32 heads: y3 (bf16 NHWC) -> nn.Flatten order (fp32 [F, C*HW]) and its gradient back (ReLU-masked by y3)
 int hulc2_nhwc_bf16_to_nchw(const void* src, float* dst, int F, int HW, int C, cudaStream_t st) {
   if (F <= 0) return HULC2_OK;
+  if (transpose_small<__nv_bfloat16, float, float>((const __nv_bfloat16*)src, dst, F, HW, C, nullptr, st)) { HULC2_CHECK_LAUNCH(); return HULC2_OK; }
   dim3 grid(hulc2_cdiv(C, 32), hulc2_cdiv(HW, 32), F);
   transpose_frames_kernel<__nv_bfloat16, float, float><<<grid, dim3(32, 8), 0, st>>>((const __nv_bfloat16*)src, dst, HW, C, nullptr);
   HULC2_CHECK_LAUNCH();
@@ -479,6 +560,7 @@ int hulc2_nhwc_bf16_to_nchw(const void* src, float* dst, int F, int HW, int C, c
 }
 int hulc2_nchw_to_nhwc_bf16(const float* src, void* dst, int F, int HW, int C, const void* mask, cudaStream_t st) {
   if (F <= 0) return HULC2_OK;
+  if (transpose_small<float, __nv_bfloat16, __nv_bfloat16>(src, (__nv_bfloat16*)dst, F, C, HW, (const __nv_bfloat16*)mask, st)) { HULC2_CHECK_LAUNCH(); return HULC2_OK; }
   dim3 grid(hulc2_cdiv(HW, 32), hulc2_cdiv(C, 32), F);
   transpose_frames_kernel<float, __nv_bfloat16, __nv_bfloat16><<<grid, dim3(32, 8), 0, st>>>(src, (__nv_bfloat16*)dst, C, HW, (const __nv_bfloat16*)mask);
   HULC2_CHECK_LAUNCH();
