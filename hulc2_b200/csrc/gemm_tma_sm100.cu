@@ -80,8 +80,10 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
   const int ST = p.stages;
 
   if (tid == 0) {
-    for (int s = 0; s < ST; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    mbar_init(smem_u32(&acc_bar), 1);
+    // (row sums: a second issuer thread commits on the same barriers, see below)
+    const uint32_t issuers = (p.rowsum != nullptr && blockIdx.y == 0) ? 2u : 1u;
+    for (int s = 0; s < ST; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), issuers); }
+    mbar_init(smem_u32(&acc_bar), issuers);
     mbar_fence_init();
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
@@ -139,18 +141,34 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
         const uint64_t ad = make_desc(a_tile, A_MN ? 8192u : 0u), bd = make_desc(b_tile, B_MN ? 8192u : 0u);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, ad + A_STEP * k, bd + B_STEP * k, IDESC, (i > 0 || k > 0) ? 1u : 0u);
-        if (row_sums) {
-          constexpr uint32_t IDESC_RS = make_idesc(BM, 16, A_MN, false);
-          const uint64_t od = make_desc(ones_tile, 0u);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d + BN, ad + A_STEP * k, od, IDESC_RS, (i > 0 || k > 0) ? 1u : 0u);
-        }
         umma_commit(smem_u32(&empty_bar[s]));     // stage free once these MMAs have read it
       }
       umma_commit(smem_u32(&acc_bar));            // accumulator complete
     }
   } else {
     // ---------------------------------------------------------------- epilogue warps
+    if (warp == 2 && row_sums) {
+      // The ones-operand MMAs come from a SECOND issuer thread (one thread issues a tcgen05.mma only every ~110 cycles: issued
+      // behind the main MMAs they doubled the main loop of the 16 row-sum CTAs, and the whole grid waited for those -- ncu r02:
+      // 2048 x 2048 x 4096 weight gradient 39 -> 48 us).  Lane 0 of the first epilogue warp, idle until the accumulator is
+      // complete, follows the same full barriers; both issuers commit on the stage's empty barrier and on the accumulator barrier.
+      if (lane == 0) {
+        constexpr uint32_t IDESC_RS = make_idesc(BM, 16, A_MN, false);
+        constexpr uint64_t A_STEP = (A_MN ? 2048u : 32u) >> 4;
+        const uint64_t od = make_desc(ones_tile, 0u);
+        for (int i = 0; i < nkt; ++i) {
+          const int s = i % ST;
+          mbar_wait(smem_u32(&full_bar[s]), (uint32_t)((i / ST) & 1));
+          tc_fence_after();
+          const uint64_t ad = make_desc(tiles + s * STAGE_BYTES, A_MN ? 8192u : 0u);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d + BN, ad + A_STEP * k, od, IDESC_RS, (i > 0 || k > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&empty_bar[s]));
+        }
+        umma_commit(smem_u32(&acc_bar));
+      }
+      __syncwarp();
+    }
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
     const bool mvalid = m < p.M;

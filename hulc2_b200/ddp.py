@@ -79,6 +79,9 @@ class GradBucketReducer:
 
     def _launch(self, bucket):
         if self.world > 1:
+            from . import ops
+
+            ops.join_side()            # weight gradients written on the side stream (ops.wgrad_section) must be complete
             self._handles.append(dist.all_reduce(bucket["view"], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
         bucket["launched"] = True
 

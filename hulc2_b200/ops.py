@@ -38,10 +38,87 @@ def get_precision() -> str:
 
 
 def workspace(device) -> torch.Tensor:
-    key = (device.type, device.index)
+    key = (device.type, device.index, _on_side)      # launches on the weight-gradient side stream get a scratch buffer of their own
     if key not in _ws:
         _ws[key] = torch.empty(_WS_BYTES, dtype=torch.uint8, device=device)
     return _ws[key]
+
+
+# ----------------------------------------------------------------------------- weight gradients off the critical path
+# The gradient of a layer's weights is read by nobody before the optimizer (or its bucket's all-reduce), while the gradient of
+# its input is the next link of backward's dependency chain.  Most of those launches are latency-bound (M = 64..128 rows, or
+# 4096 x 128 outputs), so running the weight-gradient contractions on a SIDE stream lets them fill the SMs the chain leaves
+# idle; in the captured step the fork / join become graph edges.  Rules that keep this race-free:
+#   * a section starts after everything enqueued so far on the caller's stream (side.wait_stream(main));
+#   * its launches use their own workspace; the tensors they read / write are kept alive until the join, so the allocator cannot
+#     hand their memory to a later launch of the main stream;
+#   * the join (main waits for side) happens at the end of the backward pass (autograd final callback), before a bucket of the
+#     gradient arena is all-reduced (ddp.GradBucketReducer), and before a parameter receives a SECOND gradient in the same step
+#     (grad_buffer), because autograd adds that one on the main stream.
+# MEASURED (r02, B200, bench step): 6.556 ms with the side stream, 6.575 ms without -- the weight-gradient contractions are
+# wide enough (>= 128 CTAs after split-K) that they do not fit beside the chain's kernels, so the fork / join buys 0.3 %.  The
+# mechanism therefore stays OFF by default (one stream, nothing to reason about); HULC2_SIDE_WGRAD=1 switches it on (A/B).
+import os as _os0
+
+side_wgrads = _os0.environ.get("HULC2_SIDE_WGRAD", "0") == "1"
+_on_side = False
+_side_streams: dict = {}
+_side_active = False
+_side_keepalive: list = []
+
+
+def _in_grad_arena(t: torch.Tensor) -> bool:
+    ptr = t.data_ptr()
+    seen = set()
+    for g, _o, _n in _grad_views.values():
+        if id(g) in seen:
+            continue
+        seen.add(id(g))
+        base = g.data_ptr()
+        if base <= ptr < base + 4 * g.numel() and g.device == t.device:
+            return True
+    return False
+
+
+def wgrad_section(fn, reads=(), outs=()) -> None:
+    """Runs ``fn()`` -- weight-gradient launches only -- on the side stream of the current device (see above).  ``reads``: the
+    operand tensors (kept alive until the join); ``outs``: the gradients written.  Only gradients that live in the optimizer's
+    gradient arena qualify: autograd adopts such a slice as ``param.grad`` without launching anything, whereas any other tensor
+    may be cloned or accumulated on the main stream right after the backward function returns -- then ``fn`` runs inline."""
+    global _on_side, _side_active
+    if not side_wgrads or _on_side or not outs or not all(o is None or _in_grad_arena(o) for o in outs):
+        fn()
+        return
+    main = torch.cuda.current_stream()
+    key = main.device.index
+    side = _side_streams.get(key)
+    if side is None:
+        side = _side_streams[key] = torch.cuda.Stream(device=main.device)
+    side.wait_stream(main)
+    _on_side = True
+    try:
+        with torch.cuda.stream(side):
+            fn()
+    finally:
+        _on_side = False
+    _side_keepalive.extend(t for t in reads if t is not None)
+    if not _side_active:
+        _side_active = True
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(join_side)
+        except RuntimeError:          # not inside a backward pass: nothing will join later
+            join_side()
+
+
+def join_side() -> None:
+    """The caller's stream waits for the weight-gradient side stream (no-op when nothing is outstanding)."""
+    global _side_active
+    if not _side_active:
+        return
+    for idx, side in _side_streams.items():
+        torch.cuda.current_stream(side.device).wait_stream(side)
+    _side_active = False
+    _side_keepalive.clear()
 
 
 def _p(t) -> Optional[int]:
@@ -186,6 +263,8 @@ def grad_buffer(W: torch.Tensor, zero: bool = False) -> torch.Tensor:
             _grad_claimed.add(key)
             g, o, n = ent
             return g[o : o + n].view(W.shape)
+        if ent is not None and key in _grad_claimed:
+            join_side()       # autograd will ADD this second gradient to the first one on the main stream: that one must be complete
     return torch.zeros_like(W, dtype=torch.float32) if zero else torch.empty_like(W, dtype=torch.float32)
 
 
@@ -321,8 +400,10 @@ class MLPFunction(torch.autograd.Function):
                 db = grad_buffer(wb[2 * i + 1]) if ctx.needs_input_grad[5 + 2 * i] else None
                 if ctx.needs_input_grad[4 + 2 * i]:
                     dW = grad_buffer(W)
-                    # dW = g^T inp (both MN-major); the bias gradient = row sums of g^T rides along (one more narrow MMA)
-                    gemm16(N, K, M, g16, 1, ldg, in16, 1, ld_in, dW, K, rowsum=db)
+                    # dW = g^T inp (both MN-major); the bias gradient = row sums of g^T rides along (one more narrow MMA).  Off the
+                    # critical path: the input gradient below is what the rest of backward waits for
+                    wgrad_section(lambda g16=g16, ldg=ldg, in16=in16, ld_in=ld_in, dW=dW, db=db, N=N, K=K:
+                                  gemm16(N, K, M, g16, 1, ldg, in16, 1, ld_in, dW, K, rowsum=db), (g16, in16), (dW, db))
                     grads[2 * i] = dW
                 elif db is not None:
                     colsum(g, N, M, N, db)
@@ -1202,40 +1283,50 @@ class RNNDecoderFunction(torch.autograd.Function):
         call("hulc2_copy2d", dH1.data_ptr(), step, dz1.data_ptr(), step, S, step, 0)
         _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H, S * (2.0 * H * H + 16.0 * B * H))
         call("hulc2_rnn_relu_bwd", dz1.data_ptr(), wh1.data_ptr(), H1.data_ptr(), None, S, B, H, 1, ws.data_ptr(), ws.numel())
-        dz1h, H1h = to_bf16(dz1), to_bf16(H1)
-        dwh1 = grad_buffer(wh1)
-        if S > 1:
-            gemm16(H, H, (S - 1) * B, dz1h, 1, H, H1h, 1, H, dwh1, H, a_off=step)
-        else:
-            call("hulc2_fill", dwh1.data_ptr(), dwh1.numel(), 0.0)
-        if ctx.has_h0:
-            gemm(H, H, B, dz1, 1, H, h01, 1, H, dwh1, H, accumulate=True)
-        dwi1 = grad_buffer(wi1)
+        dz1h = to_bf16(dz1)
+        H1h = torch.empty(H1.shape, device=dev, dtype=torch.bfloat16)
+        dwh1, dwi1 = grad_buffer(wh1), grad_buffer(wi1)
         bi0, bh0, bi1, bh1 = ctx.bias_params
-        db1 = grad_buffer(bi1)
-        gemm16(H, H, S * B, dz1h, 1, H, H0h, 1, H, dwi1, H, rowsum=db1)         # + bias gradient = row sums of dz1^T
-        db1h = grad_buffer(bh1)                                                  # b_hh receives the same gradient as b_ih
-        call("hulc2_copy2d", db1.data_ptr(), H, db1h.data_ptr(), H, 1, H, 0)
+        db1, db1h = grad_buffer(bi1), grad_buffer(bh1)                           # b_hh receives the same gradient as b_ih
+
+        def layer1_wgrads():
+            call("hulc2_f32_to_bf16", H1.data_ptr(), H1h.data_ptr(), H1.numel())
+            if S > 1:
+                gemm16(H, H, (S - 1) * B, dz1h, 1, H, H1h, 1, H, dwh1, H, a_off=step)
+            else:
+                call("hulc2_fill", dwh1.data_ptr(), dwh1.numel(), 0.0)
+            if ctx.has_h0:
+                gemm(H, H, B, dz1, 1, H, h01, 1, H, dwh1, H, accumulate=True)
+            gemm16(H, H, S * B, dz1h, 1, H, H0h, 1, H, dwi1, H, rowsum=db1)     # + bias gradient = row sums of dz1^T
+            call("hulc2_copy2d", db1.data_ptr(), H, db1h.data_ptr(), H, 1, H, 0)
+
+        # the four weight-gradient contractions of a layer (2 x 34 GFLOP) run beside the next layer's recurrence, which leaves
+        # the tensor pipes 94 % idle
+        wgrad_section(layer1_wgrads, (dz1, dz1h, H1, H1h, H0h, h01), (dwh1, dwi1, db1, db1h))
         dz0 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         gemm16(S * B, H, H, dz1h, H, 1, wi1h, 1, H, dz0, H)                      # dH0 = dz1 W_ih1
         _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H, S * (2.0 * H * H + 16.0 * B * H))
         call("hulc2_rnn_relu_bwd", dz0.data_ptr(), wh0.data_ptr(), H0.data_ptr(), None, S, B, H, 1, ws.data_ptr(), ws.numel())
         dz0h = to_bf16(dz0)
-        dwh0 = grad_buffer(wh0)
-        if S > 1:
-            gemm16(H, H, (S - 1) * B, dz0h, 1, H, H0h, 1, H, dwh0, H, a_off=step)
-        else:
-            call("hulc2_fill", dwh0.data_ptr(), dwh0.numel(), 0.0)
-        if ctx.has_h0:
-            gemm(H, H, B, dz0, 1, H, h00, 1, H, dwh0, H, accumulate=True)
-        db0 = grad_buffer(bi0)
         dzsum = torch.empty(B, H, device=dev, dtype=torch.float32)
         colsum(dz0, B * H, S, B * H, dzsum)                                      # sum over time
         dzsumh = to_bf16(dzsum)
-        dwi0 = grad_buffer(wi0)
-        gemm16(H, P, B, dzsumh, 1, H, plan16, 1, P, dwi0, In)
-        gemm16(H, Es, S * B, dz0h, 1, H, embT16, 1, Es, dwi0, In, c_off=P, rowsum=db0)   # + bias gradient = row sums of dz0^T
-        gemm16(H, G, B, dzsumh, 1, H, goal16, 1, ldg, dwi0, In, c_off=P + Es)
+        dwh0, dwi0 = grad_buffer(wh0), grad_buffer(wi0)
+        db0, db0h = grad_buffer(bi0), grad_buffer(bh0)
+
+        def layer0_wgrads():
+            if S > 1:
+                gemm16(H, H, (S - 1) * B, dz0h, 1, H, H0h, 1, H, dwh0, H, a_off=step)
+            else:
+                call("hulc2_fill", dwh0.data_ptr(), dwh0.numel(), 0.0)
+            if ctx.has_h0:
+                gemm(H, H, B, dz0, 1, H, h00, 1, H, dwh0, H, accumulate=True)
+            gemm16(H, P, B, dzsumh, 1, H, plan16, 1, P, dwi0, In)
+            gemm16(H, Es, S * B, dz0h, 1, H, embT16, 1, Es, dwi0, In, c_off=P, rowsum=db0)   # + bias gradient = row sums of dz0^T
+            gemm16(H, G, B, dzsumh, 1, H, goal16, 1, ldg, dwi0, In, c_off=P + Es)
+            call("hulc2_copy2d", db0.data_ptr(), H, db0h.data_ptr(), H, 1, H, 0)
+
+        wgrad_section(layer0_wgrads, (dz0, dz0h, dzsumh, H0h, h00, plan16, embT16, goal16), (dwh0, dwi0, db0, db0h))
         dplan = dgoal = demb = None
         if ctx.needs_input_grad[0]:
             dplan = torch.empty(B, P, device=dev, dtype=torch.float32)
@@ -1248,8 +1339,6 @@ class RNNDecoderFunction(torch.autograd.Function):
             gemm16(S * B, Es, H, dz0h, H, 1, wi0h, 1, In, dembT, Es, b_off=P)
             demb = torch.empty(B, S, Es, device=dev, dtype=torch.float32)
             call("hulc2_transpose01", dembT.data_ptr(), B * Es, Es, demb.data_ptr(), Es, S, B, Es, 0)
-        db0h = grad_buffer(bh0)
-        call("hulc2_copy2d", db0.data_ptr(), H, db0h.data_ptr(), H, 1, H, 0)
         return (dplan, demb, dgoal, None, dwi0, dwh0, db0, db0h, dwi1, dwh1, db1, db1h)
 
 

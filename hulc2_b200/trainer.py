@@ -105,6 +105,7 @@ class PolicyTrainer:
         if self.reducer is not None:
             self.reducer.prepare()
         loss.backward()
+        ops.join_side()                     # (the autograd final callback has joined already; no-op then)
         if self.reducer is not None:
             self.reducer.finish()
         self.optimizer.step()

@@ -18,7 +18,8 @@ import torch  # noqa: E402
 from hulc2_b200 import _lib, ops  # noqa: E402
 from hulc2_b200._lib import call  # noqa: E402
 
-REPS = 15
+REPS = int(os.environ.get("HULC2_SWEEP_REPS", "15"))      # 1 under ncu (HULC2_SWEEP_ONLY=large restricts the run to the >= 256 MB rows)
+ONLY = os.environ.get("HULC2_SWEEP_ONLY", "")
 dev = torch.device("cuda")
 peak = 6539.9
 p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -86,10 +87,13 @@ def ssm(F, tag):
     xm, ym = lin.repeat_interleave(21).contiguous(), lin.repeat(21).contiguous()
     temp = torch.ones(1, device=dev)
     out, dout, dz = torch.empty(F, 128, device=dev), R(F, 128), torch.empty_like(y3)
-    timed("SpatialSoftmax fwd (bf16 NHWC in)", tag, 2.0 * y3.numel() + 4.0 * out.numel(), lambda: call(
-        "hulc2_spatial_softmax_fwd_bf16", y3.data_ptr(), xm.data_ptr(), ym.data_ptr(), temp.data_ptr(), out.data_ptr(), F, HW, C))
-    timed("SpatialSoftmax bwd (+ conv3 ReLU mask)", tag, 4.0 * y3.numel() + 4.0 * dout.numel(), lambda: call(
-        "hulc2_spatial_softmax_bwd_bf16", y3.data_ptr(), xm.data_ptr(), ym.data_ptr(), temp.data_ptr(), dout.data_ptr(), dz.data_ptr(), None, F, HW, C, 1))
+    stats = torch.empty(F, 128, device=dev)
+    # the calls the train step makes: forward saving the softmax statistics, backward consuming them (one pass each)
+    timed("SpatialSoftmax fwd (bf16 NHWC in, saves statistics)", tag, 2.0 * y3.numel() + 8.0 * out.numel(), lambda: call(
+        "hulc2_spatial_softmax_fwd_bf16_stats", y3.data_ptr(), xm.data_ptr(), ym.data_ptr(), temp.data_ptr(), out.data_ptr(), stats.data_ptr(), F, HW, C))
+    timed("SpatialSoftmax bwd (from statistics, + conv3 ReLU mask)", tag, 4.0 * y3.numel() + 12.0 * dout.numel(), lambda: call(
+        "hulc2_spatial_softmax_bwd_bf16_stats", y3.data_ptr(), xm.data_ptr(), ym.data_ptr(), temp.data_ptr(), out.data_ptr(), stats.data_ptr(), dout.data_ptr(),
+        dz.data_ptr(), None, F, HW, C, 1))
 
 
 def adam(n, tag):
@@ -138,20 +142,28 @@ def tcp(rows_, tag):
 
 def main():
     cfg, big = "config (B=128 windows)", ">= 256 MB"
-    logistic(128, 32, cfg)
+    small = ONLY != "large"
+    if small:
+        logistic(128, 32, cfg)
     logistic(128 * 96, 32, big)            # 12288 windows: 293 MB fwd
-    kl(128, cfg)
+    if small:
+        kl(128, cfg)
     kl(32768, big)                         # 268 MB fwd
     ssm(4096, cfg + ": 4096 frames")       # already 231 MB
-    ssm(8192, "2x config")
+    if small:
+        ssm(8192, "2x config")
     adam(47053840, cfg + ": 47.05 M parameters")
-    layernorm(4096, 128, cfg)
+    if small:
+        layernorm(4096, 128, cfg)
     layernorm(4096 * 128, 128, big)
-    cells(128, 2048, cfg)
+    if small:
+        cells(128, 2048, cfg)
     cells(128 * 24, 2048, big)
-    frames(2048, cfg + ": 2048 frames")
+    if small:
+        frames(2048, cfg + ": 2048 frames")
     frames(4096, "2x config")
-    tcp(4096, cfg)
+    if small:
+        tcp(4096, cfg)
     tcp(4096 * 1024, big)
     print("# r02 size sweep of the memory-bound kernels (C-ABI calls, L2 flushed before every call, median of %d, CUDA events)\n" % REPS)
     print(f"HBM peak = {peak:.0f} GB/s (MEASURED_PEAKS.json). `alg MB` = algorithmic bytes (SURVEY.md 8d).\n")
