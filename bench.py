@@ -285,7 +285,17 @@ def measure_e2e_store(args, dev, world, rank, hw, barrier, steps):
 
 
 def family_of(key: str) -> str:
-    """Kernel family of a per-call profile key: the entry point, with the two directions of the recurrence merged."""
+    """Kernel of a per-call profile key: one entry point AT ONE PROBLEM SHAPE (`gemm16[M=4096,N=2048,K=128]` and
+    `gemm16[M=128,N=2048,K=2048]` are different tilings / split-K plans of the contraction kernel and sit at different points of
+    the roofline: adding their bytes and times up describes no kernel), with the two directions of the recurrence merged (the
+    same kernel, run forward and reversed)."""
+    base, _, shape = key.partition("[")
+    if base in ("rnn_relu_fwd", "rnn_relu_bwd"):
+        return "rnn_relu[" + shape
+    return key
+
+
+def entry_point_of(key: str) -> str:
     base = key.split("[")[0]
     return {"rnn_relu_fwd": "rnn_relu", "rnn_relu_bwd": "rnn_relu"}.get(base, base)
 
@@ -300,10 +310,10 @@ def median_profile(passes):
 
 
 COLD_TIMING = ("CUDA events per C-ABI call on the launch stream, eager step behind the timed region, L2 flushed (256 MB write) before every call, "
-               "median of {n} passes; family = all calls of one kernel entry point; achieved = sum of algorithmic bytes (or FLOPs) / sum of durations")
+               "median of {n} passes; kernel = one entry point at one problem shape (recurrence: both directions); achieved = sum of algorithmic bytes (or FLOPs) / sum of durations")
 GRAPH_TIMING = ("CUDA event-record nodes (cudaEventRecordExternal) on either side of every C-ABI call INSIDE a replayed CUDA graph of the whole step "
                 "(the path the timed region runs: no host launch latency, caches as in the real step; activations and frames exceed L2), median of {n} "
-                "replays; family = all calls of one kernel entry point; achieved = sum of algorithmic bytes (or FLOPs) / sum of durations")
+                "replays; kernel = one entry point at one problem shape (recurrence: both directions); achieved = sum of algorithmic bytes (or FLOPs) / sum of durations")
 
 
 def roofline_from_profile(recs, peaks, step_tflops, n_passes, timing=COLD_TIMING):
@@ -346,6 +356,15 @@ def roofline_from_profile(recs, peaks, step_tflops, n_passes, timing=COLD_TIMING
             "timing": timing.format(n=n_passes)}
     roof["top_kernels"] = [{"family": f["family"], "ms": round(f["ms"], 4), "calls": f["calls"], "share_of_step": round(f["share_of_step"], 4), "bound": f["bound"],
                             "achieved": round(f["achieved"], 1), "unit": f["unit"], "frac": round(f["frac"], 4)} for f in ranked[:8]]
+    # the same records added up per ENTRY POINT (all shapes of a kernel together): where the step's time goes
+    eps = {}
+    for r in recs.values():
+        e = eps.setdefault(entry_point_of(r["key"]), {"entry_point": entry_point_of(r["key"]), "ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0})
+        e["ms"] += r["ms"]; e["calls"] += r["calls"]; e["flops"] += r["flops"]; e["bytes"] += r.get("bytes", 0.0)
+    roof["by_entry_point"] = [{"entry_point": e["entry_point"], "ms": round(e["ms"], 4), "calls": e["calls"], "share_of_step": round(e["ms"] / total_ms, 4),
+                               "gbs": round(e["bytes"] / (e["ms"] * 1e-3) / 1e9, 1) if e["ms"] > 0 else None,
+                               "tflops": round(e["flops"] / (e["ms"] * 1e-3) / 1e12, 1) if e["ms"] > 0 else None}
+                              for e in sorted(eps.values(), key=lambda e: -e["ms"])[:10]]
     roof["profiled_step_ms"] = total_ms
     return roof
 
@@ -525,6 +544,11 @@ def run_b200(args):
         if graph_passes:
             recs_g = median_profile(graph_passes)
             roof = roofline_from_profile(recs_g, load_peaks(), step_tflops, len(graph_passes), timing=GRAPH_TIMING)
+            if roof is not None:
+                # where the replayed step WAITS: the largest intervals between two consecutive library calls (at N > 1 the exposed
+                # part of the gradient all-reduce shows up here, in front of the optimizer step)
+                roof["largest_gaps_between_calls"] = [{"ms": round(g["ms"], 4), "after": g["after"], "before": g["before"]}
+                                                      for g in getattr(trainer, "last_profile_gaps", [])[:8]]
             if roof is not None and cold is not None:
                 roof["cold_cache_eager_profile"] = {"top_kernels": cold["top_kernels"], "profiled_step_ms": cold["profiled_step_ms"],
                                                     "timing": cold["timing"]}

@@ -218,6 +218,18 @@ def profile_begin_graph() -> None:
     _prof, _flush, _prof_external = [], None, True
 
 
+def profile_read_gaps(top: int = 12) -> list:
+    """After a replay of the graph captured under ``profile_begin_graph``: the ``top`` largest intervals BETWEEN two consecutive
+    C-ABI calls, each with the calls on either side -- where the replayed step waits (the gradient all-reduce before the optimizer
+    step, torch kernels, stream joins): [{"ms", "after", "before", "index"}]."""
+    torch.cuda.synchronize()
+    out = []
+    for i in range(1, len(_prof)):
+        out.append({"ms": max(_prof[i - 1][4].elapsed_time(_prof[i][3]), 0.0), "after": _prof[i - 1][0], "before": _prof[i][0], "index": i})
+    out.sort(key=lambda g: -g["ms"])
+    return out[:top]
+
+
 def profile_read_graph(other_key: str = "(between calls: torch kernels, memsets, launch gaps)") -> dict:
     """After a replay of the graph captured under ``profile_begin_graph``: {key: {key, ms, calls, flops, bytes}}; the time
     between the end of one C-ABI call and the start of the next is booked under ``other_key``."""

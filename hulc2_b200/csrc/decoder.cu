@@ -319,7 +319,9 @@ __global__ void val_metrics_kernel(const float* __restrict__ pred, const float* 
 
 inline int grid_for(long long n, int block) {
   long long want = (n + block - 1) / block;
-  long long cap = 148LL * 4;
+  // up to 16 blocks of 128 threads per SM: these kernels are transcendental-heavy (ncu r02 at >= 256 MB: 45 % of the issue slots
+  // busy with 4 blocks per SM, warps waiting on fixed-latency dependencies), so occupancy, not memory, is what they need
+  long long cap = 148LL * 16;
   return (int)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 

@@ -57,8 +57,17 @@ def _zip_copy(dst, src, non_blocking=True):
 
 
 class PolicyTrainer:
-    def __init__(self, model, bucket_mb: float = 25.0, use_graph: bool = False, graph_warmup: int = 2,
+    def __init__(self, model, bucket_mb: Optional[float] = None, use_graph: bool = False, graph_warmup: int = 2,
                  device_counters: Optional[bool] = None, collate=None):
+        import os
+
+        if bucket_mb is None:
+            # Default: ONE bucket behind the small head-of-arena bucket.  Measured at 4 x B200 (tools/scale_ab_buckets.sh): 12 / 25 /
+            # 50 / 100 / 200 MB buckets -> 7.20 / 7.09 / 7.14 / 7.04 / 6.89 ms per step (6.7 at N = 1).  The bucket that holds everything
+            # but the first 4 MB completes when the encoders' MLP gradients arrive, ~2 ms before the end of backward, so its 184 MB
+            # all-reduce still hides behind the conv trunk's backward, while every additional captured NCCL launch costs fork / join
+            # edges in the step graph and SMs taken from the kernels running beside it.  HULC2_BUCKET_MB overrides (A/B switch).
+            bucket_mb = float(os.environ.get("HULC2_BUCKET_MB", "256"))
         self.model = model
         # collate: optional device-side batch builder run INSIDE the step (and therefore inside the captured graph): maps
         # the tensors handed to train_step (e.g. window descriptors: starts, lengths, augmentation draws) to the model's batch
@@ -201,6 +210,7 @@ class PolicyTrainer:
                 g.replay()
                 self.optimizer.note_replayed_step()
                 out.append(_lib.profile_read_graph())
+            self.last_profile_gaps = _lib.profile_read_gaps()      # of the last replay
         finally:
             _lib.profile_end_graph()
         return out

@@ -64,7 +64,7 @@ def main():
 
     # (2) the captured step with the NCCL all-reduce inside the graph, lr = 0
     m = build_model("calvin", hidden_size=args.hidden).to(dev).train()
-    tr = PolicyTrainer(m, use_graph=True)
+    tr = PolicyTrainer(m, use_graph=True, bucket_mb=25.0)      # several buckets launched from inside backward (the default is one + head)
     tr.scheduler = None                    # a scheduler step would write its base lr back into the group after step 1
     for grp in tr.optimizer.param_groups:
         grp["lr"] = 0.0

@@ -1,0 +1,15 @@
+cd $GRAFT_REPO_ROOT
+run() {
+  env $2 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port $3 bench.py --gpus 4 --steps 100 --warmup 5 --no-cpu-baseline --no-fp32-frames --no-store-e2e --e2e-steps 2 --profile-passes 1 --no-graph-profile > gpurun_out/r02y_n4_$1.json 2> gpurun_out/r02y_n4_$1.err
+  python - <<PY
+import json
+for line in open('gpurun_out/r02y_n4_$1.json'):
+    if line.startswith('{'):
+        d=json.loads(line); print('$1', d['value'], d['ms_per_step'])
+PY
+}
+run mb25 "HULC2_BUCKET_MB=25" 29541
+run mb50 "HULC2_BUCKET_MB=50" 29542
+run mb100 "HULC2_BUCKET_MB=100" 29543
+run mb200 "HULC2_BUCKET_MB=200" 29544
+run mb12 "HULC2_BUCKET_MB=12" 29545
