@@ -336,7 +336,7 @@ int launch_bn(const Bf16Params& bp, cudaStream_t st) {
   HULC2_CHECK_LAUNCH();
   if (p.splits > 1) {
     long long total = (long long)p.M * p.N;
-    splitk_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(p.partial, p.splits, p.M, p.N, p.E, nullptr, 0);
+    launch_splitk_reduce(p.partial, p.splits, p.M, p.N, p.E, nullptr, 0, nullptr, nullptr, st);
     HULC2_CHECK_LAUNCH();
   }
   return HULC2_OK;

@@ -356,7 +356,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TmaParams& p, int
   ++g_tma_gemms;
   if (p.splits > 1) {
     long long total = (long long)p.M * p.N;
-    splitk_reduce_kernel<<<hulc2_cdiv(total, 256), 256, 0, st>>>(p.partial, p.splits, p.M, p.N, p.E, p.C16, p.ld16, p.rowsum_partial, p.rowsum);
+    launch_splitk_reduce(p.partial, p.splits, p.M, p.N, p.E, p.C16, p.ld16, p.rowsum_partial, p.rowsum, st);
     HULC2_CHECK_LAUNCH();
   }
   return HULC2_OK;

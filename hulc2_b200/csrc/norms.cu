@@ -11,6 +11,9 @@ namespace {
 constexpr int LN_VALS = 8;  // per-lane register slots: D <= 256
 
 // --------------------------------------------------------------------------- LayerNorm
+constexpr int LN_MAX_BLOCKS = 148 * 2;
+__device__ float g_ln_part[2][LN_MAX_BLOCKS][LN_VALS * 32];     // per-block partial sums of dgamma / dbeta (backward)
+__device__ unsigned int g_ln_count = 0;
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ res, long long ldr,
                                      const unsigned char* __restrict__ keep, float keep_scale,
                                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
@@ -105,13 +108,32 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, long long ldy
 #pragma unroll
   for (int j = 0; j < LN_VALS; ++j) { sg[w][lane + 32 * j] = ag[j]; sb[w][lane + 32 * j] = ab[j]; }
   __syncthreads();
+  // Deterministic cross-block reduction: every block parks its partial sums, the block that arrives LAST adds them up in block
+  // order.  (fp32 atomics here used to be the one source of run-to-run noise of a train step: the order of up to 296 adds per
+  // element differed between two runs, and after a few Adam steps in bf16 the rounding differences grow chaotically -- the
+  // graph-vs-eager parity tests had to tolerate that.)  The scratch is per device; LayerNorm backward kernels of one process run
+  // on one stream, so they never overlap.
+  __shared__ bool last_block;
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float a = 0.f, b = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) { a += sg[k][c]; b += sb[k][c]; }
-    if (dgamma) atomicAdd(dgamma + c, a);
-    if (dbeta) atomicAdd(dbeta + c, b);
+    g_ln_part[0][blockIdx.x][c] = a;
+    g_ln_part[1][blockIdx.x][c] = b;
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last_block = atomicAdd(&g_ln_count, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last_block) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (unsigned int k = 0; k < gridDim.x; ++k) { a += __ldcg(&g_ln_part[0][k][c]); b += __ldcg(&g_ln_part[1][k][c]); }
+    if (dgamma) dgamma[c] += a;
+    if (dbeta) dbeta[c] += b;
+  }
+  if (threadIdx.x == 0) g_ln_count = 0;
 }
 
 // --------------------------------------------------------------------------- SpatialSoftmax (NHWC)
@@ -444,7 +466,7 @@ int hulc2_layernorm_bwd(const float* dy, long long ldy, const float* t, long lon
   if (rows <= 0) return HULC2_OK;
   if (D > 32 * LN_VALS || D <= 0) { hulc2_set_error("layernorm: D must be in (0,256]"); return HULC2_EINVAL; }
   long long blocks = (rows + 7) / 8;
-  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (blocks > LN_MAX_BLOCKS) blocks = LN_MAX_BLOCKS;
   layernorm_bwd_kernel<<<(int)blocks, 256, 0, st>>>(dy, ldy, t, ldt, gamma, mean, rstd, dx, lddx, dres, keep, keep_scale, dgamma, dbeta, rows, D);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
