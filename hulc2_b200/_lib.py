@@ -98,7 +98,12 @@ _SIGS = {
     "hulc2_spatial_softmax_bwd": [P, P, P, P, P, P, P, P, I, I, I, I],
     "hulc2_layernorm_fwd": [P, LL, P, LL, P, F, P, P, P, LL, P, P, P, LL, I, F],
     "hulc2_layernorm_bwd": [P, LL, P, LL, P, P, P, P, LL, P, P, F, P, P, LL, I],
+    "hulc2_layernorm_fwd_m": [P, LL, P, LL, P, F, P, P, P, LL, P, P, P, LL, I, F, P, LL],
+    "hulc2_layernorm_bwd_m": [P, LL, P, LL, P, P, P, P, LL, P, P, F, P, P, LL, I, P, P, LL],
     "hulc2_add_pos_fwd": [P, P, P, F, P, I, I, I],
+    "hulc2_add_pos_fwd_m": [P, P, P, F, P, P, I, I, I],
+    "hulc2_attention_fwd_m": [P, P, F, P, P, P, LL, I, I, I, I],
+    "hulc2_attention_bwd_m": [P, P, P, F, P, P, P, LL, I, I, I, I],
     "hulc2_add_pos_bwd": [P, P, F, P, P, I, I, I],
     "hulc2_attention_fwd": [P, P, F, P, P, I, I, I, I],
     "hulc2_attention_bwd": [P, P, P, F, P, P, I, I, I, I],
@@ -122,6 +127,8 @@ _SIGS = {
     "hulc2_infonce_bwd": [P, P, P, P, P, P, P, P, I, I, P, LL],
     "hulc2_rnn_relu_fwd": [P, P, P, P, I, I, I, I, P, LL],
     "hulc2_rnn_relu_bwd": [P, P, P, P, I, I, I, I, P, LL],
+    "hulc2_rnn_relu_fwd_m": [P, P, P, P, P, I, I, I, I, P, LL],
+    "hulc2_rnn_relu_bwd_m": [P, P, P, P, P, I, I, I, I, P, LL],
     "hulc2_gru_cell_fwd": [P, LL, P, P, P, P, I, I],
     "hulc2_gru_cell_bwd": [P, P, P, P, P, LL, P, P, I, I],
     "hulc2_lstm_cell_fwd": [P, LL, P, P, P, P, P, I, I],
@@ -272,13 +279,15 @@ def profile_end() -> dict:
 
 
 _AUTO_KEY = {"hulc2_f32_to_bf16": (2,), "hulc2_f32_to_bf16_2d": (4, 5), "hulc2_axpy": (2,), "hulc2_copy2d": (4, 5), "hulc2_colsum": (2, 3),
-             "hulc2_fill": (1,), "hulc2_layernorm_fwd": (14, 15), "hulc2_layernorm_bwd": (14, 15), "hulc2_dropout_mask_ep": (1,)}
+             "hulc2_fill": (1,), "hulc2_layernorm_fwd": (14, 15), "hulc2_layernorm_bwd": (14, 15), "hulc2_dropout_mask_ep": (1,),
+             "hulc2_layernorm_fwd_m": (14, 15), "hulc2_layernorm_bwd_m": (14, 15)}
 
 
 # algorithmic HBM bytes of the untagged memory-bound helpers (same argument positions as above): product of the size
 # arguments times bytes moved per element
 _AUTO_BYTES = {"hulc2_f32_to_bf16": 6, "hulc2_f32_to_bf16_2d": 6, "hulc2_axpy": 12, "hulc2_copy2d": 8, "hulc2_colsum": 4, "hulc2_fill": 4,
-               "hulc2_layernorm_fwd": 16, "hulc2_layernorm_bwd": 16, "hulc2_dropout_mask_ep": 1}
+               "hulc2_layernorm_fwd": 16, "hulc2_layernorm_bwd": 16, "hulc2_dropout_mask_ep": 1,
+               "hulc2_layernorm_fwd_m": 18, "hulc2_layernorm_bwd_m": 18}
 
 
 def _auto_bytes(name: str, args) -> float:
@@ -294,7 +303,8 @@ def _auto_bytes(name: str, args) -> float:
 def _auto_key(name: str, args) -> str:
     """Profile key of an untagged call: the entry point plus its size arguments (profiling only)."""
     idx = _AUTO_KEY.get(name)
-    return name if idx is None else f"{name}[{','.join(str(args[i]) for i in idx)}]"
+    base = name[:-2] if name.endswith("_m") else name       # "_m" = same operation + bf16 mirror output: one family
+    return base if idx is None else f"{base}[{','.join(str(args[i]) for i in idx)}]"
 
 
 def call(name: str, *args) -> None:

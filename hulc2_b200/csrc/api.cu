@@ -22,7 +22,7 @@ int hulc2_rnn_cluster_device_error(int clear);
 int hulc2_rnn_cluster2_device_error(int clear);
 int hulc2_rnn_cluster2_launch(const float* add, const float* w, const float* init, const float* mask, float* out, float* final_out,
                               int S, int B, int H, int relu, int reverse, int transpose_w, void* workspace, long long workspace_bytes,
-                              cudaStream_t st);
+                              void* states16, cudaStream_t st);
 int hulc2_rnn_persistent_device_error(int clear);
 int hulc2_rnn_cluster_launch(const float* add, const float* w, const float* init, const float* mask, float* out, float* final_out,
                              int S, int B, int H, int relu, int reverse, int transpose_w, void* workspace, long long workspace_bytes,
@@ -112,18 +112,25 @@ int hulc2_rnn_device_error(int clear) {
   return a | (b << 1) | (c << 2);
 }
 
+// bf16 mirror of the states for the kernels that do not write it themselves: slot t + 1 of states16 = bf16(state t)
+static int mirror_states(const float* states, void* states16, int S, int B, int H, int e, cudaStream_t st) {
+  if (e != HULC2_OK || !states16) return e;
+  const long long step = (long long)B * H;
+  return hulc2_f32_to_bf16(states, reinterpret_cast<unsigned short*>(states16) + step, (long long)S * step, st);
+}
+
 // h[t] = relu(pre[t] + h[t-1] W_hh^T)      (nn.RNN, nonlinearity=relu; decoders/utils/rnn.py:5-14)
-int hulc2_rnn_relu_fwd(const float* pre, const float* w_hh, const float* h0, float* h, int S, int B, int H, int precision,
-                       void* workspace, long long workspace_bytes, cudaStream_t st) {
+int hulc2_rnn_relu_fwd_m(const float* pre, const float* w_hh, const float* h0, float* h, void* h16, int S, int B, int H, int precision,
+                         void* workspace, long long workspace_bytes, cudaStream_t st) {
   if (S <= 0 || B <= 0) return HULC2_OK;
   if (precision == 1 && hulc2_device_supports_tcgen05()) {
     int e = HULC2_ENOTIMPL;
-    if (g_rnn_kernel == 0 && rnn_v2()) e = hulc2_rnn_cluster2_launch(pre, w_hh, h0, nullptr, h, nullptr, S, B, H, 1, 0, 0, workspace, workspace_bytes, st);
+    if (g_rnn_kernel == 0 && rnn_v2()) e = hulc2_rnn_cluster2_launch(pre, w_hh, h0, nullptr, h, nullptr, S, B, H, 1, 0, 0, workspace, workspace_bytes, h16, st);
     if (e != HULC2_ENOTIMPL) { g_rnn_path = 1; return e; }
     if (g_rnn_kernel < 1) e = hulc2_rnn_cluster_launch(pre, w_hh, h0, nullptr, h, nullptr, S, B, H, 1, 0, 0, workspace, workspace_bytes, st);
-    if (e != HULC2_ENOTIMPL) { g_rnn_path = 2; return e; }
+    if (e != HULC2_ENOTIMPL) { g_rnn_path = 2; return mirror_states(h, h16, S, B, H, e, st); }
     if (g_rnn_kernel < 2) e = hulc2_rnn_persistent_launch(pre, w_hh, h0, nullptr, h, nullptr, S, B, H, 1, 0, 0, workspace, workspace_bytes, st);
-    if (e != HULC2_ENOTIMPL) { g_rnn_path = 3; return e; }
+    if (e != HULC2_ENOTIMPL) { g_rnn_path = 3; return mirror_states(h, h16, S, B, H, e, st); }
   }
   g_rnn_path = 4;
   const long long step = (long long)B * H;
@@ -140,21 +147,25 @@ int hulc2_rnn_relu_fwd(const float* pre, const float* w_hh, const float* h0, flo
     g.precision = precision;
     if (int e = hulc2_gemm(&g, st)) return e;
   }
-  return HULC2_OK;
+  return mirror_states(h, h16, S, B, H, HULC2_OK, st);
+}
+int hulc2_rnn_relu_fwd(const float* pre, const float* w_hh, const float* h0, float* h, int S, int B, int H, int precision,
+                       void* workspace, long long workspace_bytes, cudaStream_t st) {
+  return hulc2_rnn_relu_fwd_m(pre, w_hh, h0, h, nullptr, S, B, H, precision, workspace, workspace_bytes, st);
 }
 
 // in place: dh[t] <- dz[t] = (dh[t] + dz[t+1] W_hh) * (h[t] > 0); optional dh0 = dz[0] W_hh
-int hulc2_rnn_relu_bwd(float* dh, const float* w_hh, const float* h, float* dh0, int S, int B, int H, int precision,
-                       void* workspace, long long workspace_bytes, cudaStream_t st) {
+int hulc2_rnn_relu_bwd_m(float* dh, const float* w_hh, const float* h, float* dh0, void* dz16, int S, int B, int H, int precision,
+                         void* workspace, long long workspace_bytes, cudaStream_t st) {
   if (S <= 0 || B <= 0) return HULC2_OK;
   if (precision == 1 && hulc2_device_supports_tcgen05()) {
     int e = HULC2_ENOTIMPL;
-    if (g_rnn_kernel == 0 && rnn_v2()) e = hulc2_rnn_cluster2_launch(dh, w_hh, nullptr, h, dh, dh0, S, B, H, 0, 1, 1, workspace, workspace_bytes, st);
+    if (g_rnn_kernel == 0 && rnn_v2()) e = hulc2_rnn_cluster2_launch(dh, w_hh, nullptr, h, dh, dh0, S, B, H, 0, 1, 1, workspace, workspace_bytes, dz16, st);
     if (e != HULC2_ENOTIMPL) { g_rnn_path = 1; return e; }
     if (g_rnn_kernel < 1) e = hulc2_rnn_cluster_launch(dh, w_hh, nullptr, h, dh, dh0, S, B, H, 0, 1, 1, workspace, workspace_bytes, st);
-    if (e != HULC2_ENOTIMPL) { g_rnn_path = 2; return e; }
+    if (e != HULC2_ENOTIMPL) { g_rnn_path = 2; return mirror_states(dh, dz16, S, B, H, e, st); }
     if (g_rnn_kernel < 2) e = hulc2_rnn_persistent_launch(dh, w_hh, nullptr, h, dh, dh0, S, B, H, 0, 1, 1, workspace, workspace_bytes, st);
-    if (e != HULC2_ENOTIMPL) { g_rnn_path = 3; return e; }
+    if (e != HULC2_ENOTIMPL) { g_rnn_path = 3; return mirror_states(dh, dz16, S, B, H, e, st); }
   }
   g_rnn_path = 4;
   const long long step = (long long)B * H;
@@ -176,7 +187,11 @@ int hulc2_rnn_relu_bwd(float* dh, const float* w_hh, const float* h, float* dh0,
     }
     if (int e = hulc2_gemm(&g, st)) return e;
   }
-  return HULC2_OK;
+  return mirror_states(dh, dz16, S, B, H, HULC2_OK, st);
+}
+int hulc2_rnn_relu_bwd(float* dh, const float* w_hh, const float* h, float* dh0, int S, int B, int H, int precision,
+                       void* workspace, long long workspace_bytes, cudaStream_t st) {
+  return hulc2_rnn_relu_bwd_m(dh, w_hh, h, dh0, nullptr, S, B, H, precision, workspace, workspace_bytes, st);
 }
 
 }  // extern "C"

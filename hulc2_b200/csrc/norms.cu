@@ -18,7 +18,8 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, long long ldx,
                                      const unsigned char* __restrict__ keep, float keep_scale,
                                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
                                      long long ldy, float* __restrict__ tsum, float* __restrict__ mean_out,
-                                     float* __restrict__ rstd_out, long long rows, int D, float eps) {
+                                     float* __restrict__ rstd_out, long long rows, int D, float eps,
+                                     __nv_bfloat16* __restrict__ y16, long long ld16) {
   int lane = threadIdx.x & 31;
   long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -53,7 +54,11 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, long long ldx,
 #pragma unroll
     for (int j = 0; j < LN_VALS; ++j) {
       int c = lane + 32 * j;
-      if (c < D) y[r * ldy + c] = (v[j] - mu) * rs * gamma[c] + beta[c];
+      if (c < D) {
+        const float o = (v[j] - mu) * rs * gamma[c] + beta[c];
+        y[r * ldy + c] = o;
+        if (y16) y16[r * ld16 + c] = __float2bfloat16_rn(o);      // operand mirror for the contraction that consumes y
+      }
     }
     if (lane == 0) {
       if (mean_out) mean_out[r] = mu;
@@ -66,7 +71,8 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, long long ldy
                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                      const float* __restrict__ rstd, float* __restrict__ dx, long long lddx,
                                      float* __restrict__ dres, const unsigned char* __restrict__ keep, float keep_scale,
-                                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int D) {
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int D,
+                                     __nv_bfloat16* __restrict__ dx16, __nv_bfloat16* __restrict__ dres16, long long ld16) {
   __shared__ float sg[8][LN_VALS * 32];
   __shared__ float sb[8][LN_VALS * 32];
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -101,7 +107,12 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, long long ldy
       if (c < D) {
         float v = rs * (g[j] - c1 - xh[j] * c2);
         dx[r * lddx + c] = v;
-        if (dres) dres[r * D + c] = keep ? (keep[r * D + c] ? v * keep_scale : 0.f) : v;
+        if (dx16) dx16[r * ld16 + c] = __float2bfloat16_rn(v);
+        if (dres) {
+          const float dr = keep ? (keep[r * D + c] ? v * keep_scale : 0.f) : v;
+          dres[r * D + c] = dr;
+          if (dres16) dres16[r * ld16 + c] = __float2bfloat16_rn(dr);
+        }
       }
     }
   }
@@ -448,28 +459,42 @@ static bool ssm_bf16_ok(int HW, int C) {
 
 extern "C" {
 
-int hulc2_layernorm_fwd(const float* x, long long ldx, const float* res, long long ldr, const unsigned char* keep,
-                        float keep_scale, const float* gamma, const float* beta, float* y, long long ldy, float* tsum,
-                        float* mean, float* rstd, long long rows, int D, float eps, cudaStream_t st) {
+int hulc2_layernorm_fwd_m(const float* x, long long ldx, const float* res, long long ldr, const unsigned char* keep,
+                          float keep_scale, const float* gamma, const float* beta, float* y, long long ldy, float* tsum,
+                          float* mean, float* rstd, long long rows, int D, float eps, void* y16, long long ld16, cudaStream_t st) {
   if (rows <= 0) return HULC2_OK;
   if (D > 32 * LN_VALS || D <= 0) { hulc2_set_error("layernorm: D must be in (0,256]"); return HULC2_EINVAL; }
   long long blocks = (rows + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  layernorm_fwd_kernel<<<(int)blocks, 256, 0, st>>>(x, ldx, res, ldr, keep, keep_scale, gamma, beta, y, ldy, tsum, mean, rstd, rows, D, eps);
+  layernorm_fwd_kernel<<<(int)blocks, 256, 0, st>>>(x, ldx, res, ldr, keep, keep_scale, gamma, beta, y, ldy, tsum, mean, rstd, rows, D, eps,
+                                                    (__nv_bfloat16*)y16, ld16);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
 }
+int hulc2_layernorm_fwd(const float* x, long long ldx, const float* res, long long ldr, const unsigned char* keep,
+                        float keep_scale, const float* gamma, const float* beta, float* y, long long ldy, float* tsum,
+                        float* mean, float* rstd, long long rows, int D, float eps, cudaStream_t st) {
+  return hulc2_layernorm_fwd_m(x, ldx, res, ldr, keep, keep_scale, gamma, beta, y, ldy, tsum, mean, rstd, rows, D, eps, nullptr, 0, st);
+}
 
-int hulc2_layernorm_bwd(const float* dy, long long ldy, const float* t, long long ldt, const float* gamma, const float* mean,
-                        const float* rstd, float* dx, long long lddx, float* dres, const unsigned char* keep, float keep_scale,
-                        float* dgamma, float* dbeta, long long rows, int D, cudaStream_t st) {
+int hulc2_layernorm_bwd_m(const float* dy, long long ldy, const float* t, long long ldt, const float* gamma, const float* mean,
+                          const float* rstd, float* dx, long long lddx, float* dres, const unsigned char* keep, float keep_scale,
+                          float* dgamma, float* dbeta, long long rows, int D, void* dx16, void* dres16, long long ld16,
+                          cudaStream_t st) {
   if (rows <= 0) return HULC2_OK;
   if (D > 32 * LN_VALS || D <= 0) { hulc2_set_error("layernorm: D must be in (0,256]"); return HULC2_EINVAL; }
   long long blocks = (rows + 7) / 8;
   if (blocks > LN_MAX_BLOCKS) blocks = LN_MAX_BLOCKS;
-  layernorm_bwd_kernel<<<(int)blocks, 256, 0, st>>>(dy, ldy, t, ldt, gamma, mean, rstd, dx, lddx, dres, keep, keep_scale, dgamma, dbeta, rows, D);
+  layernorm_bwd_kernel<<<(int)blocks, 256, 0, st>>>(dy, ldy, t, ldt, gamma, mean, rstd, dx, lddx, dres, keep, keep_scale, dgamma, dbeta, rows, D,
+                                                    (__nv_bfloat16*)dx16, (__nv_bfloat16*)dres16, ld16);
   HULC2_CHECK_LAUNCH();
   return HULC2_OK;
+}
+int hulc2_layernorm_bwd(const float* dy, long long ldy, const float* t, long long ldt, const float* gamma, const float* mean,
+                        const float* rstd, float* dx, long long lddx, float* dres, const unsigned char* keep, float keep_scale,
+                        float* dgamma, float* dbeta, long long rows, int D, cudaStream_t st) {
+  return hulc2_layernorm_bwd_m(dy, ldy, t, ldt, gamma, mean, rstd, dx, lddx, dres, keep, keep_scale, dgamma, dbeta, rows, D, nullptr,
+                               nullptr, 0, st);
 }
 
 static int ssm_threads(int C) {

@@ -439,13 +439,15 @@ int hulc2_rnn_cluster2_device_error(int clear) {
 extern int g_rnn_v2_reject;   // 1 shape, 2 workspace, 3 alignment, 4 no driver entry point, 5 clusters not co-resident, 6 tensor map, 7 launch
 int hulc2_rnn_cluster2_launch(const float* add, const float* w, const float* init, const float* mask, float* out, float* final_out,
                               int S, int B, int H, int relu, int reverse, int transpose_w, void* workspace, long long workspace_bytes,
-                              cudaStream_t st) {
+                              void* states16, cudaStream_t st) {
+  // states16 (optional): caller-owned bf16 [S+1, B, H] that takes the place of the workspace's state buffer -- slot t + 1 = state t
+  // is exactly the operand mirror the caller's contractions over the states need, so no separate conversion pass
   g_rnn_v2_reject = 0;
   if (B > BM || B <= 0 || S <= 0 || H > MAX_H || H % 512 != 0) { g_rnn_v2_reject = 1; return HULC2_ENOTIMPL; }
-  const long long need = (long long)(S + 1) * B * H * 2 + 1024;
+  const long long need = states16 ? 1024 : (long long)(S + 1) * B * H * 2 + 1024;
   if (!workspace || workspace_bytes < need) { g_rnn_v2_reject = 2; return HULC2_ENOTIMPL; }
   if (((uintptr_t)add | (uintptr_t)out | (uintptr_t)w | (uintptr_t)workspace | (uintptr_t)(mask ? mask : out) | (uintptr_t)(init ? init : out) |
-       (uintptr_t)(final_out ? final_out : out)) & 15) {
+       (uintptr_t)(final_out ? final_out : out) | (uintptr_t)states16) & 15) {
     g_rnn_v2_reject = 3;
     return HULC2_ENOTIMPL;
   }
@@ -459,7 +461,7 @@ int hulc2_rnn_cluster2_launch(const float* add, const float* w, const float* ini
   ClusterRnnParams p;
   p.add = add; p.w = w; p.has_init = init ? 1 : 0; p.mask = mask; p.out = out; p.final_out = final_out;
   p.counters = reinterpret_cast<unsigned int*>(workspace);
-  p.outb = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + 1024);
+  p.outb = states16 ? reinterpret_cast<__nv_bfloat16*>(states16) : reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + 1024);
   p.S = S; p.B = B; p.H = H; p.relu = relu; p.reverse = reverse; p.transpose_w = transpose_w;
   // bf16 states [S+1, B, H]: one box = 64 k x 128 rows of one slot, 128-byte swizzled = one A k-tile; rows >= B read as zeros
   CUtensorMap tm;

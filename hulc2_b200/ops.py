@@ -189,13 +189,57 @@ def to_bf16(t: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def mirror_like(t: torch.Tensor) -> torch.Tensor:
+    """bf16 mirror with the shape of the dense fp32 tensor ``t``: the one its producer wrote, else a conversion."""
+    t = _f32(t)
+    if t.is_contiguous() and t.dim() >= 2:
+        hit = _find_mirror(t.view(-1, t.shape[-1]))
+        if hit is not None and hit[1] == t.shape[-1]:
+            return hit[0].view(t.shape)
+    return to_bf16(t)
+
+
 def _pad8(n: int) -> int:
     return (int(n) + 7) & ~7
+
+
+# Activation mirrors written by their PRODUCER (the "_m" entry points: LayerNorm, attention, positional add, the recurrence):
+# data_ptr of the fp32 tensor -> (fp32 tensor, its version, bf16 mirror, mirror row stride, rows, cols).  The entry holds the
+# fp32 tensor, so its memory cannot be recycled under a live key, and the version guards against in-place torch updates
+# (autograd accumulating into a gradient buffer).  Cleared at every step boundary (zero_grad, optimizer.step, start of a
+# training / validation / rollout step).  A consumer that finds no entry converts as before.
+_act16: dict = {}
+producer_mirrors = __import__("os").environ.get("HULC2_PRODUCER_MIRRORS", "1") != "0"     # A/B switch
+
+
+def emit_mirrors() -> bool:
+    return producer_mirrors and _precision == 1
+
+
+def register_mirror(src: torch.Tensor, m16: torch.Tensor, ld: int, rows: int, cols: int) -> None:
+    _act16[src.data_ptr()] = (src, src._version, m16, int(ld), int(rows), int(cols))
+
+
+def clear_mirrors() -> None:
+    _act16.clear()
+
+
+def _find_mirror(x2: torch.Tensor):
+    ent = _act16.get(x2.data_ptr())
+    if ent is None:
+        return None
+    src, ver, m16, ld, rows, cols = ent
+    if x2.dim() != 2 or x2.shape[0] != rows or x2.shape[1] != cols or not x2.is_contiguous() or x2._version != ver or src._version != ver:
+        return None
+    return m16, ld
 
 
 def mirror2d(x2: torch.Tensor) -> Tuple[torch.Tensor, int]:
     """Compact bf16 mirror [rows, pad8(cols)] of a 2-D fp32 tensor with unit inner stride (rows may be strided)."""
     x2 = _f32(x2)
+    hit = _find_mirror(x2)
+    if hit is not None:
+        return hit
     rows, cols = x2.shape
     ld = _pad8(cols)
     out = torch.empty(rows, ld, device=x2.device, dtype=torch.bfloat16)
@@ -221,6 +265,7 @@ def register_param_arena(arena: torch.Tensor) -> None:
 
 def invalidate_weight_mirrors() -> None:
     _w16.clear()
+    _act16.clear()
     for a in _arenas:
         a[1] = None
 
@@ -251,6 +296,7 @@ def unregister_grad_views(keys) -> None:
 def begin_grad_step() -> None:
     """Start of a step (the gradient arena has just been zero-filled): every parameter's slice can be claimed again."""
     _grad_claimed.clear()
+    _act16.clear()
 
 
 def grad_buffer(W: torch.Tensor, zero: bool = False) -> torch.Tensor:
@@ -872,8 +918,12 @@ class LayerNormFunction(torch.autograd.Function):
         rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
         r2 = _rows2d(res) if res is not None else None
         t = torch.empty(rows, D, device=x.device, dtype=torch.float32) if res is not None else None
-        call("hulc2_layernorm_fwd", x2.data_ptr(), _ld(x2), _p(r2), _ld(r2) if r2 is not None else 0, _p(keep), keep_scale,
-             gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), D, _p(t), mean.data_ptr(), rstd.data_ptr(), rows, D, eps)
+        y16 = torch.empty(rows, _pad8(D), device=x.device, dtype=torch.bfloat16) if emit_mirrors() and rows > 0 else None
+        call("hulc2_layernorm_fwd_m", x2.data_ptr(), _ld(x2), _p(r2), _ld(r2) if r2 is not None else 0, _p(keep), keep_scale,
+             gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), D, _p(t), mean.data_ptr(), rstd.data_ptr(), rows, D, eps,
+             _p(y16), _pad8(D))
+        if y16 is not None:
+            register_mirror(y, y16, _pad8(D), rows, D)
         ctx.save_for_backward(t if t is not None else x2, gamma, mean, rstd)
         ctx.beta = beta                        # identity only (grad_buffer)
         ctx.keep, ctx.keep_scale, ctx.has_res, ctx.shape = keep, keep_scale, res is not None, x.shape
@@ -889,8 +939,13 @@ class LayerNormFunction(torch.autograd.Function):
         dres = torch.empty(rows, D, device=dy.device, dtype=torch.float32) if ctx.has_res else None
         dgamma = grad_buffer(gamma, zero=True)
         dbeta = grad_buffer(beta, zero=True)
-        call("hulc2_layernorm_bwd", dy2.data_ptr(), D, t.data_ptr(), _ld(t), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-             dx.data_ptr(), D, _p(dres), _p(ctx.keep), ctx.keep_scale, dgamma.data_ptr(), dbeta.data_ptr(), rows, D)
+        # the gradient that goes straight into a contraction's backward: the residual branch's when there is one, else dx
+        g16 = torch.empty(rows, _pad8(D), device=dy.device, dtype=torch.bfloat16) if emit_mirrors() and rows > 0 else None
+        call("hulc2_layernorm_bwd_m", dy2.data_ptr(), D, t.data_ptr(), _ld(t), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+             dx.data_ptr(), D, _p(dres), _p(ctx.keep), ctx.keep_scale, dgamma.data_ptr(), dbeta.data_ptr(), rows, D,
+             _p(g16) if dres is None else None, _p(g16) if dres is not None else None, _pad8(D))
+        if g16 is not None:
+            register_mirror(dres if dres is not None else dx, g16, _pad8(D), rows, D)
         return (dx.view(ctx.shape), dres.view(ctx.shape) if dres is not None else None, None, None, dgamma, dbeta, None)
 
 
@@ -905,7 +960,10 @@ class AddPosFunction(torch.autograd.Function):
         emb = _f32(emb).contiguous()
         B, S, E = emb.shape
         out = torch.empty_like(emb)
-        call("hulc2_add_pos_fwd", emb.data_ptr(), pos.data_ptr(), _p(keep), keep_scale, out.data_ptr(), B, S, E)
+        out16 = torch.empty(B * S, E, device=emb.device, dtype=torch.bfloat16) if emit_mirrors() and E % 8 == 0 and B * S > 0 else None
+        call("hulc2_add_pos_fwd_m", emb.data_ptr(), pos.data_ptr(), _p(keep), keep_scale, out.data_ptr(), _p(out16), B, S, E)
+        if out16 is not None:
+            register_mirror(out, out16, E, B * S, E)
         ctx.keep, ctx.keep_scale, ctx.pos_shape = keep, keep_scale, pos.shape
         return out
 
@@ -930,7 +988,11 @@ class AttentionFunction(torch.autograd.Function):
         probs = torch.empty(B, H, S, S, device=qkv.device, dtype=torch.float32)
         _lib.tag(f"attention_fwd[B={B},S={S},H={H},dh={E // H}]", 4.0 * B * H * S * S * (E // H),
                  4.0 * B * S * 4 * E + B * H * S * S * (4.0 + (1.0 if keep is not None else 0.0)))
-        call("hulc2_attention_fwd", qkv.data_ptr(), _p(keep), keep_scale, out.data_ptr(), probs.data_ptr(), B, S, H, E // H)
+        out16 = torch.empty(B * S, _pad8(E), device=qkv.device, dtype=torch.bfloat16) if emit_mirrors() and B * S > 0 else None
+        call("hulc2_attention_fwd_m", qkv.data_ptr(), _p(keep), keep_scale, out.data_ptr(), probs.data_ptr(), _p(out16), _pad8(E),
+             B, S, H, E // H)
+        if out16 is not None:
+            register_mirror(out, out16, _pad8(E), B * S, E)
         ctx.save_for_backward(qkv, probs)
         ctx.dims, ctx.keep, ctx.keep_scale = (B, S, H, E // H), keep, keep_scale
         return out
@@ -943,8 +1005,12 @@ class AttentionFunction(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         _lib.tag(f"attention_bwd[B={B},S={S},H={H},dh={Dh}]", 8.0 * B * H * S * S * Dh,
                  4.0 * B * S * 7 * H * Dh + B * H * S * S * (4.0 + (1.0 if ctx.keep is not None else 0.0)))
-        call("hulc2_attention_bwd", qkv.data_ptr(), probs.data_ptr(), _p(ctx.keep), ctx.keep_scale, dout.data_ptr(),
-             dqkv.data_ptr(), B, S, H, Dh)
+        E3 = 3 * H * Dh
+        d16 = torch.empty(B * S, _pad8(E3), device=qkv.device, dtype=torch.bfloat16) if emit_mirrors() and B * S > 0 else None
+        call("hulc2_attention_bwd_m", qkv.data_ptr(), probs.data_ptr(), _p(ctx.keep), ctx.keep_scale, dout.data_ptr(),
+             dqkv.data_ptr(), _p(d16), _pad8(E3), B, S, H, Dh)
+        if d16 is not None:
+            register_mirror(dqkv, d16, _pad8(E3), B * S, E3)
         return dqkv, None, None, None, None, None
 
 
@@ -1186,22 +1252,32 @@ class RNNDecoderFunction(torch.autograd.Function):
         h00 = h0[0].contiguous() if h0 is not None else None
         h01 = h0[1].contiguous() if h0 is not None else None
         _lib.tag(f"rnn_relu_fwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H, S * (2.0 * H * H + 12.0 * B * H))
-        call("hulc2_rnn_relu_fwd", pre.data_ptr(), wh0.data_ptr(), _p(h00), H0.data_ptr(), S, B, H, _lib_precision(), ws.data_ptr(), ws.numel())
+        # bf16 mirrors of the states come out of the recurrence kernel itself ([S+1,B,H]: slot t + 1 = state t is the kernel's own
+        # step-to-step operand store): no fp32 -> bf16 pass over 32 MB per layer and direction
+        S16 = (lambda: torch.empty(S + 1, B, H, device=dev, dtype=torch.bfloat16)) if b16 and emit_mirrors() else (lambda: None)
+        H0s = S16()
+        call("hulc2_rnn_relu_fwd_m", pre.data_ptr(), wh0.data_ptr(), _p(h00), H0.data_ptr(), _p(H0s), S, B, H, _lib_precision(),
+             ws.data_ptr(), ws.numel())
         H0h = None
         if b16:
-            H0h = to_bf16(H0)
+            H0h = H0s[1:] if H0s is not None else to_bf16(H0)
             gemm16(S * B, H, H, H0h, H, 1, wi1h, H, 1, pre, H, bias=bsum1)
         else:
             gemm(S * B, H, H, H0, H, 1, wi1, H, 1, pre, H, bias=bsum1)
         H1 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
+        H1s = S16()
         _lib.tag(f"rnn_relu_fwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H, S * (2.0 * H * H + 12.0 * B * H))
-        call("hulc2_rnn_relu_fwd", pre.data_ptr(), wh1.data_ptr(), _p(h01), H1.data_ptr(), S, B, H, _lib_precision(), ws.data_ptr(), ws.numel())
+        call("hulc2_rnn_relu_fwd_m", pre.data_ptr(), wh1.data_ptr(), _p(h01), H1.data_ptr(), _p(H1s), S, B, H, _lib_precision(),
+             ws.data_ptr(), ws.numel())
+        H1h = H1s[1:] if H1s is not None else None
+        if H1h is not None:
+            register_mirror(H1, H1h, H, S * B, H)          # the decoder heads' operand (heads_forward / DecoderLossFunction)
         hn = torch.empty(2, B, H, device=dev, dtype=torch.float32)
         call("hulc2_copy2d", H0.data_ptr() + 4 * (S - 1) * B * H, B * H, hn.data_ptr(), B * H, 1, B * H, 0)
         call("hulc2_copy2d", H1.data_ptr() + 4 * (S - 1) * B * H, B * H, hn.data_ptr() + 4 * B * H, B * H, 1, B * H, 0)
         ctx.b16 = b16
         ctx.bias_params = (bi0, bh0, bi1, bh1)     # identity only: their gradients land in the arena slices (grad_buffer)
-        extra = (plan16, goal16, embT16, H0h) if b16 else ()
+        extra = (plan16, goal16, embT16, H0h) + ((H1h,) if H1h is not None else ()) if b16 else ()
         ctx.save_for_backward(plan, embT, goal, H0, H1, wi0, wh0, wi1, wh1, h00 if h00 is not None else plan.new_empty(0),
                               h01 if h01 is not None else plan.new_empty(0), *extra)
         ctx.dims = (B, S, Es, P, G, H, In)
@@ -1271,7 +1347,8 @@ class RNNDecoderFunction(torch.autograd.Function):
     @staticmethod
     def _backward16(ctx, dH1):
         """Same gradient algebra as ``backward`` on bf16 operand mirrors (TMA-fed contractions)."""
-        plan, embT, goal, H0, H1, wi0, wh0, wi1, wh1, h00, h01, plan16, goal16, embT16, H0h = ctx.saved_tensors
+        plan, embT, goal, H0, H1, wi0, wh0, wi1, wh1, h00, h01, plan16, goal16, embT16, H0h, *rest = ctx.saved_tensors
+        H1h_saved = rest[0] if rest else None
         B, S, Es, P, G, H, In = ctx.dims
         dev = plan.device
         ws = workspace(dev)
@@ -1282,15 +1359,18 @@ class RNNDecoderFunction(torch.autograd.Function):
         dz1 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         call("hulc2_copy2d", dH1.data_ptr(), step, dz1.data_ptr(), step, S, step, 0)
         _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H, S * (2.0 * H * H + 16.0 * B * H))
-        call("hulc2_rnn_relu_bwd", dz1.data_ptr(), wh1.data_ptr(), H1.data_ptr(), None, S, B, H, 1, ws.data_ptr(), ws.numel())
-        dz1h = to_bf16(dz1)
-        H1h = torch.empty(H1.shape, device=dev, dtype=torch.bfloat16)
+        S16 = (lambda: torch.empty(S + 1, B, H, device=dev, dtype=torch.bfloat16)) if emit_mirrors() else (lambda: None)
+        dz1s = S16()
+        call("hulc2_rnn_relu_bwd_m", dz1.data_ptr(), wh1.data_ptr(), H1.data_ptr(), None, _p(dz1s), S, B, H, 1, ws.data_ptr(), ws.numel())
+        dz1h = dz1s[1:] if dz1s is not None else to_bf16(dz1)
+        H1h = H1h_saved if H1h_saved is not None else torch.empty(H1.shape, device=dev, dtype=torch.bfloat16)
         dwh1, dwi1 = grad_buffer(wh1), grad_buffer(wi1)
         bi0, bh0, bi1, bh1 = ctx.bias_params
         db1, db1h = grad_buffer(bi1), grad_buffer(bh1)                           # b_hh receives the same gradient as b_ih
 
         def layer1_wgrads():
-            call("hulc2_f32_to_bf16", H1.data_ptr(), H1h.data_ptr(), H1.numel())
+            if H1h_saved is None:
+                call("hulc2_f32_to_bf16", H1.data_ptr(), H1h.data_ptr(), H1.numel())
             if S > 1:
                 gemm16(H, H, (S - 1) * B, dz1h, 1, H, H1h, 1, H, dwh1, H, a_off=step)
             else:
@@ -1306,8 +1386,9 @@ class RNNDecoderFunction(torch.autograd.Function):
         dz0 = torch.empty(S, B, H, device=dev, dtype=torch.float32)
         gemm16(S * B, H, H, dz1h, H, 1, wi1h, 1, H, dz0, H)                      # dH0 = dz1 W_ih1
         _lib.tag(f"rnn_relu_bwd[S={S},B={B},H={H}]", 2.0 * S * B * H * H, S * (2.0 * H * H + 16.0 * B * H))
-        call("hulc2_rnn_relu_bwd", dz0.data_ptr(), wh0.data_ptr(), H0.data_ptr(), None, S, B, H, 1, ws.data_ptr(), ws.numel())
-        dz0h = to_bf16(dz0)
+        dz0s = S16()
+        call("hulc2_rnn_relu_bwd_m", dz0.data_ptr(), wh0.data_ptr(), H0.data_ptr(), None, _p(dz0s), S, B, H, 1, ws.data_ptr(), ws.numel())
+        dz0h = dz0s[1:] if dz0s is not None else to_bf16(dz0)
         dzsum = torch.empty(B, H, device=dev, dtype=torch.float32)
         colsum(dz0, B * H, S, B * H, dzsum)                                      # sum over time
         dzsumh = to_bf16(dzsum)
@@ -1513,7 +1594,7 @@ def heads_forward(Hs, wp, bp, wm, bm, wsc, bsc, wg, bg, Hs16=None) -> torch.Tens
         # one contraction over the stacked head weights [3*A*M + 2, H] (bf16 mirrors)
         Wcat = torch.cat([weight16(wp), weight16(wm), weight16(wsc), weight16(wg)], 0)
         bcat = torch.cat([bp, bm, bsc, bg], 0)
-        Hs16 = Hs16 if Hs16 is not None else to_bf16(Hs.contiguous())
+        Hs16 = Hs16 if Hs16 is not None else mirror_like(Hs.contiguous())
         gemm16(rows, 3 * AM + 2, H, Hs16, H, 1, Wcat, H, 1, heads, HEAD_LD, bias=bcat)
         return heads
     for W, b, off in ((wp, bp, 0), (wm, bm, AM), (wsc, bsc, 2 * AM)):
@@ -1535,7 +1616,7 @@ class DecoderLossFunction(torch.autograd.Function):
         S, B, H = Hs.shape
         A, M, num_classes, ls_min, alpha = cfg
         ctx.b16 = _heads16_ok(Hs, wp, wg)
-        Hs16 = to_bf16(Hs) if ctx.b16 else None
+        Hs16 = mirror_like(Hs) if ctx.b16 else None
         heads = heads_forward(Hs, wp, bp, wm, bm, wsc, bsc, wg, bg, Hs16=Hs16)
         ws = workspace(Hs.device)
         segmented = isinstance(actions, (tuple, list))

@@ -206,6 +206,17 @@ int hulc2_layernorm_bwd(const float* dy, long long ldy, const float* t, long lon
                         const float* mean, const float* rstd, float* dx, long long lddx, float* dres,
                         const unsigned char* keep, float keep_scale, float* dgamma, float* dbeta, long long rows, int D,
                         hulc2_stream_t stream);
+/* "_m" variants (here and below): the same operation that ALSO writes the bf16 operand mirror of its result (row stride ld16
+ * elements, null = none) for the tcgen05 contraction that consumes it -- the mirror comes out of the producer's registers
+ * instead of a separate fp32 -> bf16 pass over HBM (round-to-nearest-even, bit-identical to hulc2_f32_to_bf16). */
+int hulc2_layernorm_fwd_m(const float* x, long long ldx, const float* res, long long ldr, const unsigned char* keep,
+                          float keep_scale, const float* gamma, const float* beta, float* y, long long ldy, float* tsum,
+                          float* mean, float* rstd, long long rows, int D, float eps, void* y16, long long ld16,
+                          hulc2_stream_t stream);
+int hulc2_layernorm_bwd_m(const float* dy, long long ldy, const float* t, long long ldt, const float* gamma,
+                          const float* mean, const float* rstd, float* dx, long long lddx, float* dres,
+                          const unsigned char* keep, float keep_scale, float* dgamma, float* dbeta, long long rows, int D,
+                          void* dx16, void* dres16, long long ld16, hulc2_stream_t stream);
 
 /* ------------------------------------------------------------------ plan-recognition transformer pieces
  * plan_recognition_net.py:125-148 + torch nn.TransformerEncoderLayer (post-LN, ReLU, 8 heads x 16, S <= 32).
@@ -219,6 +230,13 @@ int hulc2_attention_fwd(const float* qkv, const unsigned char* keep, float keep_
                         int S, int H, int Dh, hulc2_stream_t stream);
 int hulc2_attention_bwd(const float* qkv, const float* probs, const unsigned char* keep, float keep_scale,
                         const float* dout, float* dqkv, int B, int S, int H, int Dh, hulc2_stream_t stream);
+int hulc2_add_pos_fwd_m(const float* emb, const float* pos, const unsigned char* keep, float keep_scale, float* out,
+                        void* out16, int B, int S, int E, hulc2_stream_t stream);
+int hulc2_attention_fwd_m(const float* qkv, const unsigned char* keep, float keep_scale, float* out, float* probs,
+                          void* out16, long long ld16, int B, int S, int H, int Dh, hulc2_stream_t stream);
+int hulc2_attention_bwd_m(const float* qkv, const float* probs, const unsigned char* keep, float keep_scale,
+                          const float* dout, float* dqkv, void* dqkv16, long long ld16, int B, int S, int H, int Dh,
+                          hulc2_stream_t stream);
 int hulc2_mean_seq_fwd(const float* x, float* out, int B, int S, int E, hulc2_stream_t stream);
 int hulc2_mean_seq_bwd(const float* dout, float* dx, int B, int S, int E, hulc2_stream_t stream);
 
@@ -297,6 +315,13 @@ int hulc2_rnn_relu_fwd(const float* pre, const float* w_hh, const float* h0, flo
                        int precision, void* workspace, long long workspace_bytes, hulc2_stream_t stream);
 int hulc2_rnn_relu_bwd(float* dh_inout, const float* w_hh, const float* h, float* dh0, int S, int B, int H,
                        int precision, void* workspace, long long workspace_bytes, hulc2_stream_t stream);
+/* + bf16 mirror of the states: h16 / dz16 = bf16 [S+1, B, H], 16-byte aligned; on return slot t + 1 holds bf16(h[t]) /
+ * bf16(dz[t]) (slot 0 is scratch: the initial state).  Kernel (a') uses the buffer as its own step-to-step operand store (its
+ * workspace need drops to 1024 bytes), so the mirror the caller's input / weight-gradient contractions read costs nothing. */
+int hulc2_rnn_relu_fwd_m(const float* pre, const float* w_hh, const float* h0, float* h, void* h16, int S, int B, int H,
+                         int precision, void* workspace, long long workspace_bytes, hulc2_stream_t stream);
+int hulc2_rnn_relu_bwd_m(float* dh_inout, const float* w_hh, const float* h, float* dh0, void* dz16, int S, int B, int H,
+                         int precision, void* workspace, long long workspace_bytes, hulc2_stream_t stream);
 /* precision 1 runs all S steps in ONE persistent tcgen05 kernel when the shape fits, tried in this order:
  *  (a') TMA-fed cluster split-K kernel (rnn_cluster2_sm100.cu): as (a) with workspace >= 2*(S+1)*B*H + 1024 bytes; the state
  *       slice of a step arrives as TMA boxes, CTAs publish per warp (HULC2_RNN_V1=1 in the environment skips it);
