@@ -1,7 +1,9 @@
 // bf16 dense contractions for sm_100a, second generation: operands are bf16 in HBM (row-major mirrors of the fp32
 // master tensors, written once by their producer), moved by TMA (cp.async.bulk.tensor, SWIZZLE_128B boxes) into a
 // multi-stage shared-memory ring, multiplied by tcgen05.mma (UMMA 128 x BN x 16, fp32 accumulators in TMEM) and
-// drained by four epilogue warps with 16-byte loads/stores.
+// drained by four epilogue warps: straight from the TMEM row registers with 256-bit stores when the epilogue reads no
+// per-element operand, else turned around through the (by then idle) ring so that the mask / keep / add / accumulate operands,
+// the result and the split-K partials all move as coalesced 16-byte accesses.
 //
 // Warp roles (192 threads):  warp 0 = TMA producer (one elected lane),  warp 1 = TMEM owner + MMA issuer (one lane),
 // warps 2-5 = epilogue (TMEM lane quarter = warp & 3).  full/empty mbarriers per stage; the MMA warp recycles a stage
@@ -64,7 +66,7 @@ __device__ __forceinline__ void store_scalar(const TmaParams& p, float acc, int 
 }
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(NT, 2) gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, const TmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -174,20 +176,31 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
     const bool mvalid = m < p.M;
     const Epilogue& E = p.E;
     const long long crow = mvalid ? c_row_off(E, m) : 0;
-    // The ReLU-mask / dropout-keep operands of the epilogue are the only long-latency loads between the accumulator and the
-    // stores (ncu r02: the big-output, small-K contractions sat on long_scoreboard with 9 % of the issue slots busy: one load
-    // group in flight per thread, because loads are not moved across the stores of the previous group).  They are fetched one
-    // 32-column chunk AHEAD into registers: the first chunk while the main loop still runs, chunk c + 1 before chunk c is stored.
-    uint32_t mk_next[4][8];
-    uint2 kp_next[4];
-    const bool pf = p.vec8 && mvalid && p.splits == 1 && (E.mask || E.keep);
+    // Transposed epilogue (r02).  tcgen05.ld hands every thread ONE ROW of the tile (32 columns per chunk), so stores straight
+    // from those registers put the 32 lanes of an instruction on 32 different rows: 32 L1 wavefronts per instruction, a quarter
+    // line each -- the big-output, small-K contractions (FFN 4096 x 2048 x 128: 50 MB out, 41 MB of mask / keep in) were bound by
+    // exactly that (38 -> 33 us; the split-K contractions with M = 4096 rows 22 -> 18 us).  Each epilogue warp turns its 32 x 32 chunk around through shared memory (the
+    // pipeline ring is idle once the accumulator barrier has fired; row pitch 36 floats: conflict-free both ways): lane ->
+    // (row quad lane >> 3, column quad lane & 7), one instruction = 4 rows x 128 contiguous bytes = 4 full lines, every epilogue
+    // operand and result moves with coalesced 16-byte accesses.  The ReLU-mask / dropout-keep operands are fetched one chunk
+    // AHEAD (first chunk while the main loop still runs), as before.
+    const int rq = lane >> 3, cq = lane & 7;
+    const uint32_t stg = tiles + (uint32_t)(warp - 2) * (32u * 144u);
+    const bool tp = p.vec && p.splits == 1;                                  // CTA-uniform
+    const bool direct = p.vec8 && !(E.mask || E.keep || E.add || E.accumulate);
+    const int mrow0 = m0 + q * 32 + rq;                                      // this lane's row in iteration it: mrow0 + 4 * it
+    uint4 mk_next[8];
+    uint32_t kp_next[8];
     auto prefetch = [&](int c) {
-      if (!pf || n0 + c + 32 > p.N || c >= BN) return;
+      if (!tp || !(E.mask || E.keep) || n0 + c + 32 > p.N || c >= BN) return;
+      const int n = n0 + c + 4 * cq;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = n0 + c + 8 * j;
-        if (E.mask) ldg256_nc(E.mask + (long long)m * E.ld_mask + n, mk_next[j]);
-        if (E.keep) kp_next[j] = *reinterpret_cast<const uint2*>(E.keep + (long long)m * E.ld_keep + n);
+      for (int it = 0; it < 8; ++it) {
+        const int mr = mrow0 + 4 * it;
+        if (mr < p.M) {
+          if (E.mask) mk_next[it] = __ldg(reinterpret_cast<const uint4*>(E.mask + (long long)mr * E.ld_mask + n));
+          if (E.keep) kp_next[it] = __ldg(reinterpret_cast<const unsigned int*>(E.keep + (long long)mr * E.ld_keep + n));
+        }
       }
     };
     prefetch(0);
@@ -210,6 +223,108 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
       tmem_ld16_nowait(trow + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
       tmem_ld16_nowait(trow + (uint32_t)(c + 16), *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
       tmem_ld_wait();
+      if (direct && n0 + c + 32 <= p.N) {
+        // no per-element operand to read (bias / ReLU / bf16 mirror only: plain outputs, weight gradients): the thread's row goes
+        // out straight from its registers with 256-bit stores -- every 32-byte sector is written whole, and measured against the
+        // turn-around below this is 2-10 us faster per launch (in-graph timeline: 4096 x 2048 x 182 22 vs 33 us, x 2048 56 vs 65)
+        if (!mvalid) continue;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const int n = n0 + c + j;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = E.alpha * __uint_as_float(r[j + e]);
+          uint32_t t[8];
+          if (E.bias) { ldg256_nc(E.bias + n, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += __uint_as_float(t[e]); }
+          if (E.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t[e] = __float_as_uint(v[e]);
+          stg256(E.C + crow + n, t);
+          if (p.C16)
+            *reinterpret_cast<uint4*>(p.C16 + (long long)m * p.ld16 + n) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+        continue;
+      }
+      if (tp && n0 + c + 32 <= p.N) {             // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)lane * 144u + 16u * j), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                       "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+        uint4 mk[8];
+        uint32_t kp[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) { mk[it] = mk_next[it]; kp[it] = kp_next[it]; }
+        prefetch(c + 32);
+        __syncwarp();
+        const int n = n0 + c + 4 * cq;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (E.bias) bias4 = __ldg(reinterpret_cast<const float4*>(E.bias + n));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 ad[4], ca[4];
+          long long cro[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {            // the loads of four row quads are issued before the first store
+            const int mr = mrow0 + 4 * (4 * h + u);
+            cro[u] = mr < p.M ? c_row_off(E, mr) : 0;
+            if (mr < p.M) {
+              if (E.add) ad[u] = *reinterpret_cast<const float4*>(E.add + (long long)mr * E.ld_add + n);
+              if (E.accumulate) ca[u] = *reinterpret_cast<const float4*>(E.C + cro[u] + n);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int it = 4 * h + u;
+            const int mr = mrow0 + 4 * it;
+            float4 a;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                         : "r"(stg + (uint32_t)(4 * it + rq) * 144u + 16u * cq) : "memory");
+            if (mr >= p.M) continue;
+            float v[4] = {E.alpha * a.x, E.alpha * a.y, E.alpha * a.z, E.alpha * a.w};
+            if (E.bias) { v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w; }
+            if (E.add) { v[0] += ad[u].x; v[1] += ad[u].y; v[2] += ad[u].z; v[3] += ad[u].w; }
+            if (E.accumulate) { v[0] += ca[u].x; v[1] += ca[u].y; v[2] += ca[u].z; v[3] += ca[u].w; }
+            if (E.relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+            if (E.mask) {
+              v[0] = __uint_as_float(mk[it].x) > 0.f ? v[0] : 0.f; v[1] = __uint_as_float(mk[it].y) > 0.f ? v[1] : 0.f;
+              v[2] = __uint_as_float(mk[it].z) > 0.f ? v[2] : 0.f; v[3] = __uint_as_float(mk[it].w) > 0.f ? v[3] : 0.f;
+            }
+            if (E.keep) {
+              const uint32_t k4 = kp[it];
+              v[0] = (k4 & 0xffu) ? v[0] * E.keep_scale : 0.f; v[1] = (k4 & 0xff00u) ? v[1] * E.keep_scale : 0.f;
+              v[2] = (k4 & 0xff0000u) ? v[2] * E.keep_scale : 0.f; v[3] = (k4 & 0xff000000u) ? v[3] * E.keep_scale : 0.f;
+            }
+            *reinterpret_cast<float4*>(E.C + cro[u] + n) = make_float4(v[0], v[1], v[2], v[3]);
+            if (p.C16) *reinterpret_cast<uint2*>(p.C16 + (long long)mr * p.ld16 + n) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+          }
+        }
+        __syncwarp();                              // the staging rows are rewritten by the next chunk
+        continue;
+      }
+      if (p.splits > 1 && p.vec && n0 + c + 32 <= p.N) {      // warp-uniform: split-K partials, same turn-around, no operands
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)lane * 144u + 16u * j), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                       "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+        __syncwarp();
+        const int n = n0 + c + 4 * cq;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int mr = mrow0 + 4 * it;
+          float4 a;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                       : "r"(stg + (uint32_t)(4 * it + rq) * 144u + 16u * cq) : "memory");
+          if (mr < p.M) *reinterpret_cast<float4*>(p.partial + ((long long)blockIdx.z * p.M + mr) * p.N + n) = a;
+        }
+        __syncwarp();
+        continue;
+      }
       if (!mvalid) continue;
       if (p.splits > 1) {
         float* prow = p.partial + ((long long)blockIdx.z * p.M + m) * p.N;
@@ -222,56 +337,6 @@ __global__ void __launch_bounds__(NT) gemm_tma_kernel(const __grid_constant__ CU
           } else {
             for (int e = 0; e < 4; ++e) if (n + e < p.N) prow[n + e] = __uint_as_float(r[j + e]);
           }
-        }
-        continue;
-      }
-      if (p.vec8 && n0 + c + 32 <= p.N) {
-        // 8 columns per access: rows are >= 128 bytes apart across lanes, so every access is its own L1 wavefront -- 256-bit
-        // LDG/STG halve them (the big-output, small-K contractions are bound by exactly this: 4096x2048x128 took 80 us)
-        uint32_t mk[4][8];
-        uint2 kp[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          kp[j] = kp_next[j];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) mk[j][e] = mk_next[j][e];
-        }
-        prefetch(c + 32);
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const int n = n0 + c + j;
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = E.alpha * __uint_as_float(r[j + e]);
-          uint32_t t[8];
-          if (E.bias) { ldg256_nc(E.bias + n, t);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += __uint_as_float(t[e]); }
-          if (E.add) { ldg256_nc(E.add + (long long)m * E.ld_add + n, t);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += __uint_as_float(t[e]); }
-          if (E.accumulate) {
-            const float4 t0 = *reinterpret_cast<const float4*>(E.C + crow + n), t1 = *reinterpret_cast<const float4*>(E.C + crow + n + 4);
-            v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w; v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
-          }
-          if (E.relu) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-          }
-          if (E.mask) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(mk[j >> 3][e]) > 0.f ? v[e] : 0.f; }
-          if (E.keep) {
-            const uint2 k2 = kp[j >> 3];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = (((e < 4 ? k2.x : k2.y) >> (8 * (e & 3))) & 0xffu) ? v[e] * E.keep_scale : 0.f;
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) t[e] = __float_as_uint(v[e]);
-          stg256(E.C + crow + n, t);
-          if (p.C16)
-            *reinterpret_cast<uint4*>(p.C16 + (long long)m * p.ld16 + n) =
-                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
         continue;
       }
@@ -355,7 +420,6 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TmaParams& p, int
   HULC2_CHECK_LAUNCH();
   ++g_tma_gemms;
   if (p.splits > 1) {
-    long long total = (long long)p.M * p.N;
     launch_splitk_reduce(p.partial, p.splits, p.M, p.N, p.E, p.C16, p.ld16, p.rowsum_partial, p.rowsum, st);
     HULC2_CHECK_LAUNCH();
   }
@@ -448,9 +512,6 @@ int hulc2_gemm_tma_impl(const hulc2_gemm_args* a, cudaStream_t st) {
   p.vec = vec ? 1 : 0;
   bool vec8 = vec && p.splits == 1 && al(a->C, 32) && a->ldc % 8 == 0 && a->c_inner == 0;
   if (a->bias) vec8 = vec8 && al(a->bias, 32);
-  if (a->add) vec8 = vec8 && al(a->add, 32) && a->ld_add % 8 == 0;
-  if (a->mask) vec8 = vec8 && al(a->mask, 32) && a->ld_mask % 8 == 0;
-  if (a->keep) vec8 = vec8 && al(a->keep, 8) && a->ld_keep % 8 == 0;
   if (a->C16) vec8 = vec8 && al(a->C16, 16) && a->ld16 % 8 == 0;
   p.vec8 = vec8 ? 1 : 0;
 
