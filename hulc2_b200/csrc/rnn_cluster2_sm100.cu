@@ -49,6 +49,7 @@ constexpr int NT = 256;
 constexpr int MAX_H = 2048;
 constexpr uint32_t A_TILE = BM * 128;               // 16 KB: 128 rows x 64 bf16
 constexpr uint32_t CTR_STRIDE = 32;                 // counters 128 bytes apart (in u32)
+constexpr long long CTR_BYTES = (MAX_H / KT) * CTR_STRIDE * 4;   // 4 KB at the head of the workspace: one counter per k-tile
 template <int CS>
 struct Geo {
   static constexpr int NC = NR * CS;                     // output columns per cluster (UMMA N)
@@ -66,9 +67,10 @@ struct ClusterRnnParams {
   float* out;                // [S,B,H] fp32 states
   __nv_bfloat16* outb;       // [S+1,B,H] bf16 states (workspace): slot 0 = initial state, slot t+1 = state t
   float* final_out;          // bwd only: dh0 [B,H] = dz[0] W_hh (or null)
-  unsigned int* counters;    // CS counters, CTR_STRIDE apart (zeroed before launch); one arrival per WARP per step
+  unsigned int* counters;    // CS (kt_flags: H / 64) counters, CTR_STRIDE apart (zeroed before launch); one arrival per WARP per step
   int S, B, H;
   int relu, reverse, transpose_w;
+  int kt_flags;              // 1: one flag per 64-column k-tile (4 producer CTAs) instead of one per K slice (KS / 16 producer CTAs)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -223,7 +225,29 @@ __global__ void __launch_bounds__(NT, 1) rnn_cluster2_kernel(const __grid_consta
     if (has_prev) {
       const uint32_t par = mma_uses & 1;
       if (warp == 0) {
-        if (lane == 0) {
+        if (p.kt_flags) {
+          // One flag per k-tile: lane kt waits for the 4 CTAs that produce columns [k0 + 64 kt, + 64) of the previous state and
+          // issues that box itself, so the boxes of early producers are in flight while the slowest CTA of the slice still publishes.
+          if (lane < nkt) {
+            if (it > 0 || final_pass) {
+              const unsigned int target = generation * (unsigned int)(KT / NR) * WARPS;
+              const unsigned int* c = p.counters + ((int)rank * nkt + lane) * CTR_STRIDE;
+              unsigned int v, spins = 0;
+              do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+                if ((++spins & 1023u) == 0) {
+                  if (spins > (1u << 23)) atomicExch(&g_cluster2_rnn_error, 1u);
+                  if (*reinterpret_cast<volatile unsigned int*>(&g_cluster2_rnn_error)) break;
+                }
+              } while (v < target);
+              asm volatile("fence.proxy.async.global;" ::: "memory");
+            }
+            const uint32_t bar = smem_u32(&full_bar[lane]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(A_TILE) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         ::"r"(a_smem + lane * A_TILE), "l"((uint64_t)&tm_state), "r"(bar), "r"(k0 + lane * KT), "r"(0), "r"(slot_prev) : "memory");
+          }
+        } else if (lane == 0) {
           if (it > 0 || final_pass) {
             // K slice `rank` of the previous state is complete: every warp of its `producers` CTAs has arrived `generation` times
             const unsigned int target = generation * (unsigned int)producers * WARPS;
@@ -327,7 +351,7 @@ __global__ void __launch_bounds__(NT, 1) rnn_cluster2_kernel(const __grid_consta
       generation += 1;
       __syncwarp();
       if (lane == 0)   // release: this warp's share of the CTA's 16 columns of K slice nf / KS is visible before the count moves
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters + (nf / KS) * CTR_STRIDE) : "memory");
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters + (p.kt_flags ? nf / KT : nf / KS) * CTR_STRIDE) : "memory");
       if (eactive) {
         float4* o4 = reinterpret_cast<float4*>(p.out + (long long)t * step + (long long)erow * H + ecol);
         o4[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -344,6 +368,12 @@ __global__ void __launch_bounds__(NT, 1) rnn_cluster2_kernel(const __grid_consta
 static bool rnn_cooperative() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("HULC2_RNN_COOP"); v = (e && e[0] == '0') ? 0 : 1; }   // A/B switch, read once
+  return v == 1;
+}
+
+static bool rnn_kt_flags() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HULC2_RNN_KT_FLAGS"); v = (e && e[0] == '0') ? 0 : 1; }   // A/B switch, read once
   return v == 1;
 }
 
@@ -444,7 +474,7 @@ int hulc2_rnn_cluster2_launch(const float* add, const float* w, const float* ini
   // is exactly the operand mirror the caller's contractions over the states need, so no separate conversion pass
   g_rnn_v2_reject = 0;
   if (B > BM || B <= 0 || S <= 0 || H > MAX_H || H % 512 != 0) { g_rnn_v2_reject = 1; return HULC2_ENOTIMPL; }
-  const long long need = states16 ? 1024 : (long long)(S + 1) * B * H * 2 + 1024;
+  const long long need = states16 ? CTR_BYTES : (long long)(S + 1) * B * H * 2 + CTR_BYTES;
   if (!workspace || workspace_bytes < need) { g_rnn_v2_reject = 2; return HULC2_ENOTIMPL; }
   if (((uintptr_t)add | (uintptr_t)out | (uintptr_t)w | (uintptr_t)workspace | (uintptr_t)(mask ? mask : out) | (uintptr_t)(init ? init : out) |
        (uintptr_t)(final_out ? final_out : out) | (uintptr_t)states16) & 15) {
@@ -461,8 +491,9 @@ int hulc2_rnn_cluster2_launch(const float* add, const float* w, const float* ini
   ClusterRnnParams p;
   p.add = add; p.w = w; p.has_init = init ? 1 : 0; p.mask = mask; p.out = out; p.final_out = final_out;
   p.counters = reinterpret_cast<unsigned int*>(workspace);
-  p.outb = states16 ? reinterpret_cast<__nv_bfloat16*>(states16) : reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + 1024);
+  p.outb = states16 ? reinterpret_cast<__nv_bfloat16*>(states16) : reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + CTR_BYTES);
   p.S = S; p.B = B; p.H = H; p.relu = relu; p.reverse = reverse; p.transpose_w = transpose_w;
+  p.kt_flags = rnn_kt_flags() ? 1 : 0;
   // bf16 states [S+1, B, H]: one box = 64 k x 128 rows of one slot, 128-byte swizzled = one A k-tile; rows >= B read as zeros
   CUtensorMap tm;
   cuuint64_t dims[3] = {(cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)(S + 1)};
@@ -474,7 +505,7 @@ int hulc2_rnn_cluster2_launch(const float* add, const float* w, const float* ini
     g_rnn_v2_reject = 6;
     return HULC2_ENOTIMPL;
   }
-  if (cudaMemsetAsync(p.counters, 0, 1024, st) != cudaSuccess) return HULC2_ELAUNCH;
+  if (cudaMemsetAsync(p.counters, 0, CTR_BYTES, st) != cudaSuccess) return HULC2_ELAUNCH;
   if (init) {
     const long long n = (long long)B * H;
     init_state_bf16_kernel<<<hulc2_cdiv(n / 4, 256), 256, 0, st>>>(init, p.outb, n);

@@ -323,7 +323,7 @@ int hulc2_rnn_relu_fwd_m(const float* pre, const float* w_hh, const float* h0, f
 int hulc2_rnn_relu_bwd_m(float* dh_inout, const float* w_hh, const float* h, float* dh0, void* dz16, int S, int B, int H,
                          int precision, void* workspace, long long workspace_bytes, hulc2_stream_t stream);
 /* precision 1 runs all S steps in ONE persistent tcgen05 kernel when the shape fits, tried in this order:
- *  (a') TMA-fed cluster split-K kernel (rnn_cluster2_sm100.cu): as (a) with workspace >= 2*(S+1)*B*H + 1024 bytes; the state
+ *  (a') TMA-fed cluster split-K kernel (rnn_cluster2_sm100.cu): as (a) with workspace >= 2*(S+1)*B*H + 4096 bytes; the state
  *       slice of a step arrives as TMA boxes, CTAs publish per warp (HULC2_RNN_V1=1 in the environment skips it);
  *  (a) cluster split-K kernel (rnn_cluster_sm100.cu): B <= 128, H % 512 == 0, H <= 2048, workspace >= 2*S*B*H + 1024
  *      bytes, H/16 CTAs in clusters of 8 or 4 all co-resident -- W_hh block resident in shared memory, partial sums reduced
