@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "gemm_common.cuh"
 #include "sm100.cuh"
@@ -45,7 +46,24 @@ struct TmaParams {
   int vec8;                     // ... and so are 32-byte ones (8 fp32 columns per 256-bit access)
   float* rowsum;                // optional [M]: rowsum[m] = sum_k A(m,k) (an nn.Linear's bias gradient out of its weight-gradient GEMM)
   float* rowsum_partial;        // [splits, M] when splits > 1
+  int cluster_splitk;           // splits > 1: the CTAs of one output tile form a thread-block cluster (1, 1, splits) and reduce their
+                                // accumulators through distributed shared memory -- no partial buffer, no reduce kernel
 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -131,6 +149,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_tma_kernel(const __grid_constant__
         }
       }
     }
+    __syncwarp();                                  // (the cluster barriers of the split-K reduction are warp-aligned)
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc(BM, BN, A_MN, B_MN);
@@ -147,6 +166,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_tma_kernel(const __grid_constant__
       }
       umma_commit(smem_u32(&acc_bar));            // accumulator complete
     }
+    __syncwarp();
   } else {
     // ---------------------------------------------------------------- epilogue warps
     if (warp == 2 && row_sums) {
@@ -171,6 +191,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_tma_kernel(const __grid_constant__
       }
       __syncwarp();
     }
+    if (!p.cluster_splitk) {
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
     const bool mvalid = m < p.M;
@@ -369,6 +390,105 @@ __global__ void __launch_bounds__(NT, 2) gemm_tma_kernel(const __grid_constant__
         }
       }
     }
+    }   // !cluster_splitk
+  }
+  if (p.cluster_splitk) {
+    // ------------------------------------------------------------ split-K reduced through distributed shared memory
+    // The `splits` CTAs of an output tile are one cluster.  CTA z finalises rows [z rp, (z + 1) rp) of the tile (rp = ceil(128 /
+    // splits)): every CTA pushes each accumulator row into the shared memory of the row's owner (RED[source z][local row][BN + 4],
+    // in the pipeline ring, idle by then), one cluster barrier, the owner adds the `splits` strips in source order (deterministic)
+    // and runs the full epilogue with coalesced 16-byte rows.  Replaces [splits, M, N] fp32 partials through HBM / L2 plus a
+    // second launch (49 split-K contractions per train step) -- implemented, parity-green (195 GPU tests) and OFF by default: slower
+    // than what it replaces, see gemm_cluster_splitk().
+    const Epilogue& E = p.E;
+    const int splits = p.splits;
+    const int rp = (BM + splits - 1) / splits;
+    constexpr int PITCH = BN + 4;                              // floats; column BN carries the row sum of A
+    const uint32_t z = cluster_ctarank();
+    if (warp >= 2) {
+      mbar_wait_relaxed(smem_u32(&acc_bar), 0);                // this CTA's MMAs have read the ring for the last time
+      tc_fence_after();
+    }
+    cluster_sync_all();                                        // ... and so have those of every CTA of the cluster
+    if (warp >= 2) {
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const uint32_t remote = mapa(tiles + (uint32_t)(((int)z * rp + row % rp) * PITCH) * 4u, (uint32_t)(row / rp));
+      const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= p.N) break;
+        uint32_t r[32];
+        tmem_ld16_nowait(trow + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        tmem_ld16_nowait(trow + (uint32_t)(c + 16), *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)(c + 4 * j) * 4u), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                       "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+      }
+      if (row_sums) {
+        uint32_t rs[16];
+        tmem_ld16_nowait(trow + (uint32_t)BN, rs);
+        tmem_ld_wait();
+        asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(remote + (uint32_t)BN * 4u), "r"(rs[0]) : "memory");
+      }
+      tc_fence_before();
+    }
+    cluster_sync_all();                                        // every strip has landed
+    if (warp >= 2) {
+      const int te = tid - 64;                                 // 0 .. 127
+      const int row_lo = (int)z * rp;
+      const int nrows = min(rp, BM - row_lo);                  // (<= 0 for the CTAs behind a ragged split: nothing to finalise)
+      constexpr int G = BN / 4;
+      for (int item = te; item < nrows * G; item += 128) {
+        const int lr = item / G, c4 = item - lr * G;
+        const int mr = m0 + row_lo + lr, n = n0 + 4 * c4;
+        if (mr >= p.M || n >= p.N) continue;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int sidx = 0; sidx < splits; ++sidx) {
+          float4 a;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                       : "r"(tiles + (uint32_t)((sidx * rp + lr) * PITCH + 4 * c4) * 4u) : "memory");
+          v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+        }
+        const long long cro = c_row_off(E, mr);
+        if (p.vec && n + 4 <= p.N) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] *= E.alpha;
+          if (E.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(E.bias + n)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+          if (E.add) { const float4 t = *reinterpret_cast<const float4*>(E.add + (long long)mr * E.ld_add + n); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+          if (E.accumulate) { const float4 t = *reinterpret_cast<const float4*>(E.C + cro + n); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+          if (E.relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+          if (E.mask) {
+            const float4 t = *reinterpret_cast<const float4*>(E.mask + (long long)mr * E.ld_mask + n);
+            v[0] = t.x > 0.f ? v[0] : 0.f; v[1] = t.y > 0.f ? v[1] : 0.f; v[2] = t.z > 0.f ? v[2] : 0.f; v[3] = t.w > 0.f ? v[3] : 0.f;
+          }
+          if (E.keep) {
+            const uchar4 t = *reinterpret_cast<const uchar4*>(E.keep + (long long)mr * E.ld_keep + n);
+            v[0] = t.x ? v[0] * E.keep_scale : 0.f; v[1] = t.y ? v[1] * E.keep_scale : 0.f;
+            v[2] = t.z ? v[2] * E.keep_scale : 0.f; v[3] = t.w ? v[3] * E.keep_scale : 0.f;
+          }
+          *reinterpret_cast<float4*>(E.C + cro + n) = make_float4(v[0], v[1], v[2], v[3]);
+          if (p.C16) *reinterpret_cast<uint2*>(p.C16 + (long long)mr * p.ld16 + n) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+        } else {
+          for (int e = 0; e < 4; ++e) if (n + e < p.N) store_scalar(p, v[e], mr, n + e, cro);
+        }
+      }
+      if (row_sums) {
+        for (int lr = te; lr < nrows; lr += 128) {
+          const int mr = m0 + row_lo + lr;
+          if (mr >= p.M) continue;
+          float rs = 0.f;
+          for (int sidx = 0; sidx < splits; ++sidx) {
+            float a;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(tiles + (uint32_t)((sidx * rp + lr) * PITCH + BN) * 4u) : "memory");
+            rs += a;
+          }
+          p.rowsum[mr] = rs;
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -416,6 +536,19 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TmaParams& p, int
     configured = smem;
   }
   dim3 grid(hulc2_cdiv(p.M, BM), hulc2_cdiv(p.N, BN), p.splits);
+  if (p.cluster_splitk) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)p.splits;
+    cfg.gridDim = grid; cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    if (e != cudaSuccess) { cudaGetLastError(); hulc2_set_error(cudaGetErrorString(e)); return HULC2_ELAUNCH; }
+    ++g_tma_gemms;
+    return HULC2_OK;
+  }
   kern<<<grid, NT, smem, st>>>(ta, tb, p);
   HULC2_CHECK_LAUNCH();
   ++g_tma_gemms;
@@ -435,6 +568,14 @@ int launch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap&
 }
 
 bool al(const void* p, uintptr_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
+bool gemm_cluster_splitk() {
+  static int v = -1;
+  // A/B switch, read once.  Default OFF -- measured (r02, 1 x B200, interleaved runs): 221 instead of 315 launches per step but
+  // 6.66 vs 6.41 ms: a cluster of 8 CTAs pushing 64 KB each through DSMEM behind two cluster barriers costs 8-11 us per launch
+  // (128 x 2048 x 2048: 17 -> 28 us), more than the partial round trip through L2 plus the reduce launch it replaces.
+  if (v < 0) { const char* e = getenv("HULC2_GEMM_CLUSTER_SPLITK"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 bool gemm_small_k_bn128() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("HULC2_GEMM_SMALLK_BN128"); v = (e && e[0] == '1') ? 1 : 0; }   // A/B switch (default off), read once
@@ -477,17 +618,26 @@ int hulc2_gemm_tma_impl(const hulc2_gemm_args* a, cudaStream_t st) {
   p.splits = 1; p.kt_per_split = p.ktiles; p.partial = nullptr;
   // (the reduce kernel applies the full epilogue and writes the bf16 mirror, so fused-epilogue layers split too)
   const bool simple = a->c_inner == 0;
-  if (simple && tiles < 100 && p.ktiles >= 8 && a->workspace) {
+  const bool cluster_ok = gemm_cluster_splitk() && BN <= 128;       // (split problems never take 256-column tiles: tiles < 100)
+  if (simple && tiles < 100 && p.ktiles >= 8 && (a->workspace || cluster_ok)) {
     int want = (int)((296 + tiles - 1) / tiles);
     int maxs = p.ktiles / 4;
     int s = want < maxs ? want : maxs;
-    const long long per = ((long long)a->M * a->N + (a->rowsum ? a->M : 0)) * (long long)sizeof(float);
-    while (s > 1 && (long long)s * per > a->workspace_bytes) --s;
+    if (cluster_ok) {
+      if (s > 8) s = 8;                              // portable cluster size
+    } else {
+      const long long per = ((long long)a->M * a->N + (a->rowsum ? a->M : 0)) * (long long)sizeof(float);
+      while (s > 1 && (long long)s * per > a->workspace_bytes) --s;
+    }
     if (s > 1) {
       p.kt_per_split = hulc2_cdiv(p.ktiles, s);
       p.splits = hulc2_cdiv(p.ktiles, p.kt_per_split);
-      p.partial = (float*)a->workspace;
-      p.rowsum_partial = a->rowsum ? p.partial + (long long)p.splits * a->M * a->N : nullptr;
+      if (cluster_ok) {
+        p.cluster_splitk = 1;
+      } else {
+        p.partial = (float*)a->workspace;
+        p.rowsum_partial = a->rowsum ? p.partial + (long long)p.splits * a->M * a->N : nullptr;
+      }
     }
   }
   const int stage_bytes = (int)A_BYTES + BN * 128;
@@ -497,6 +647,12 @@ int hulc2_gemm_tma_impl(const hulc2_gemm_args* a, cudaStream_t st) {
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages > p.kt_per_split) stages = p.kt_per_split;
   if (stages < 1) stages = 1;
+  if (p.cluster_splitk) {
+    // RED[splits][ceil(128 / splits)][BN + 4] fp32 lives in the ring: give the ring the stages it needs for that
+    const int rp = (BM + p.splits - 1) / p.splits;
+    const long long red = (long long)p.splits * rp * (BN + 4) * 4;
+    while ((long long)stages * stage_bytes < red) ++stages;
+  }
   p.stages = stages;
   const int smem = stages * stage_bytes + 1024 + (a->rowsum ? 2048 : 0);
   p.rowsum = a->rowsum;
@@ -508,7 +664,7 @@ int hulc2_gemm_tma_impl(const hulc2_gemm_args* a, cudaStream_t st) {
   if (a->mask) vec = vec && al(a->mask, 16) && a->ld_mask % 4 == 0;
   if (a->keep) vec = vec && al(a->keep, 4) && a->ld_keep % 4 == 0;
   if (a->C16) vec = vec && al(a->C16, 8) && a->ld16 % 4 == 0;
-  if (p.splits > 1) vec = al(p.partial, 16) && a->N % 4 == 0;
+  if (p.splits > 1 && !p.cluster_splitk) vec = al(p.partial, 16) && a->N % 4 == 0;
   p.vec = vec ? 1 : 0;
   bool vec8 = vec && p.splits == 1 && al(a->C, 32) && a->ldc % 8 == 0 && a->c_inner == 0;
   if (a->bias) vec8 = vec8 && al(a->bias, 32);
