@@ -58,6 +58,7 @@ class ConvbArgs(C.Structure):
         ("dy", P), ("dx", P), ("xmask", P),
         ("dw", P), ("db", P), ("dw_layout", I),
         ("workspace", P), ("workspace_bytes", LL),
+        ("mask_bits", P), ("mask_bits_written", I),
     ]
 
 

@@ -8,6 +8,8 @@ struct HaloParams {
   const uint8_t* w;        // packed bf16 weights [NT][ntaps * 64], tap-major contraction index
   const float* bias;       // [NT] or null (forward only)
   const uint8_t* mask;     // bf16, output-shaped: keep where > 0 (input gradient) or null
+  const uint8_t* mask_bits;  // the same mask as 1 bit per output element (input gradient; takes precedence over `mask`) or null
+  uint8_t* mask_out;       // forward: (y > 0) as 1 bit per output element, or null
   uint8_t* y;              // bf16 output [F, oH, oW, BNc]
   int NT;                  // accumulator columns = ncls * BNc (64 or 128)
   int BNc;                 // channels per output pixel

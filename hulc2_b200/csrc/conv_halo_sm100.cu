@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
       long long off[NCH];
       bool ok[NCH];
       uint32_t mk[NCH][8];
+      uint32_t mb[NCH];           // ... or its 16 sign bits (r02: 2 bytes instead of 32 per chunk -- the input gradient of conv2 read
+                                  // 629 MB of bf16 activations per step only to test their sign)
 #pragma unroll
       for (int q = 0; q < NCH; ++q) {
         const int col = half * HC + q * 16;             // first of 16 accumulator columns: one class, 16 channels
@@ -161,7 +163,9 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
         ok[q] = il < p.BH && i < p.clsH[cls] && jl < p.clsW[cls];
         const long long opix = ((long long)f * p.oH + i * p.oS + p.clsPh[cls]) * p.oW + jl * p.oS + p.clsPw[cls];
         off[q] = (opix * BNc + ch) * 2;
-        if (DGRAD && p.mask && ok[q]) ldg256_nc(p.mask + off[q], mk[q]);      // 32 bytes = this chunk's 16 channels
+        if (DGRAD && p.mask_bits) {
+          mb[q] = ok[q] ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p.mask_bits + (off[q] >> 4))) : 0u;
+        } else if (DGRAD && p.mask && ok[q]) ldg256_nc(p.mask + off[q], mk[q]);      // 32 bytes = this chunk's 16 channels
       }
       mbar_wait_relaxed(smem_u32(&tfull_bar[buf]), par);
       tc_fence_after();
@@ -173,6 +177,7 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+      uint32_t mybits = 0;
 #pragma unroll
       for (int q = 0; q < NCH; ++q) {
         if (!ok[q]) continue;
@@ -187,7 +192,22 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
           }
           o[e] = pack_bf16x2(lo, hi);
         }
-        if (DGRAD && p.mask) {
+        if (!DGRAD && p.mask_out) {
+          // sign bits of this chunk's 16 outputs, the same predicate the input gradient applies to the bf16 values
+          uint32_t bits = 0;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t mm = o[e];
+            bits |= (((mm & 0x7fffu) != 0 && !(mm & 0x8000u)) ? 1u : 0u) << (2 * e);
+            bits |= (((mm & 0x7fff0000u) != 0 && !(mm & 0x80000000u)) ? 1u : 0u) << (2 * e + 1);
+          }
+          mybits |= bits << (16 * (q & 1));
+        }
+        if (DGRAD && p.mask_bits) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            o[e] &= (((mb[q] >> (2 * e)) & 1u) ? 0x0000ffffu : 0u) | (((mb[q] >> (2 * e + 1)) & 1u) ? 0xffff0000u : 0u);
+        } else if (DGRAD && p.mask) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             // bf16 activations are >= 0 after ReLU: keep a half-word where the mask half-word is a positive number
@@ -198,6 +218,15 @@ __global__ void __launch_bounds__(NT_HALO, 1) conv_halo_kernel(const __grid_cons
           }
         }
         stg256(p.y + off[q], o);
+      }
+      if (!DGRAD && NCH <= 2 && p.mask_out && ok[0]) {
+        // the thread's 16 / 32 sign bits as one aligned 2- / 4-byte store.  Measured: worth it for the 64-channel layers only (conv2
+        // forward +15 us, conv3 input gradient -50 us per 4096 frames); on conv1 forward, whose epilogue paces the kernel (16 columns
+        // per thread, 860 cycles of HBM time per tile), the extra ~50 ALU instructions cost 0.10 ms -- more than conv2's input
+        // gradient gains (0.06 ms) -- and pairing the two column halves of a pixel through shared memory for full-word stores
+        // is worse still (0.38 -> 0.54 ms): ops requests the bits for conv2's output only.
+        if (NCH == 2) *reinterpret_cast<uint32_t*>(p.mask_out + (off[0] >> 4)) = mybits;
+        else *reinterpret_cast<unsigned short*>(p.mask_out + (off[0] >> 4)) = (unsigned short)mybits;
       }
       ++ti;
     }

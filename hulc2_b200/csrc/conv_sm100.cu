@@ -711,7 +711,9 @@ int hulc2_convb_fwd(const hulc2_convb_args* a, cudaStream_t st) {
     h.tiles_per_frame = hulc2_cdiv(OH, h.BH);
     h.oH = OH; h.oW = OW; h.oS = 1;
     h.clsH[0] = (short)OH; h.clsW[0] = (short)OW; h.clsPh[0] = h.clsPw[0] = 0;
+    h.mask_out = a->relu ? (uint8_t*)a->mask_bits : nullptr;
     const int rc = hulc2_conv_halo_launch(a->x, a->F, a->H, a->W, h, false, st);
+    if (rc == HULC2_OK && h.mask_out) const_cast<hulc2_convb_args*>(a)->mask_bits_written = 1;
     if (rc != HULC2_ENOTIMPL) return rc;
   }
   if (a->C % 8 == 0 && a->C < 64 && a->C >= 32 && a->Cout == 32 && a->stride == 1 && a->KH * a->KW <= 4 && a->W <= 128 &&
@@ -731,7 +733,9 @@ int hulc2_convb_fwd(const hulc2_convb_args* a, cudaStream_t st) {
     h.tiles_per_frame = hulc2_cdiv(OH, h.BH);
     h.oH = OH; h.oW = OW; h.oS = 1;
     h.clsH[0] = (short)OH; h.clsW[0] = (short)OW; h.clsPh[0] = h.clsPw[0] = 0;
+    h.mask_out = a->relu ? (uint8_t*)a->mask_bits : nullptr;
     const int rc = hulc2_conv_halo_launch_packed(a->x, a->F, a->H, a->W, a->C, h, st);
+    if (rc == HULC2_OK && h.mask_out) const_cast<hulc2_convb_args*>(a)->mask_bits_written = 1;
     if (rc != HULC2_ENOTIMPL) return rc;
   }
   if (a->C == 32 && a->Cout == 64 && a->stride == 2 && a->KH == 4 && a->KW == 4 && OW + 1 <= 128 && hulc2_conv_halo_enabled()) {
@@ -750,7 +754,9 @@ int hulc2_convb_fwd(const hulc2_convb_args* a, cudaStream_t st) {
     h.tiles_per_frame = hulc2_cdiv(OH, h.BH);
     h.oH = OH; h.oW = OW; h.oS = 1;
     h.clsH[0] = (short)OH; h.clsW[0] = (short)OW; h.clsPh[0] = h.clsPw[0] = 0;
+    h.mask_out = a->relu ? (uint8_t*)a->mask_bits : nullptr;
     const int rc = hulc2_conv_halo_launch_s2(a->x, a->F, a->H, a->W, h, st);
+    if (rc == HULC2_OK && h.mask_out) const_cast<hulc2_convb_args*>(a)->mask_bits_written = 1;
     if (rc != HULC2_ENOTIMPL) return rc;
   }
   ConvParams p{};
@@ -785,6 +791,7 @@ int hulc2_convb_dgrad(const hulc2_convb_args* a, cudaStream_t st) {
     // classes (2 x 2 taps each) share one halo tile, their packed weights are stacked along N.
     HaloParams h{};
     h.w = (const uint8_t*)a->w; h.bias = nullptr; h.mask = (const uint8_t*)a->xmask; h.y = (uint8_t*)a->dx; h.relu = 0;
+    h.mask_bits = (const uint8_t*)a->mask_bits;
     h.BNc = a->C; h.ncls = s * s; h.NT = h.ncls * h.BNc;
     const int KA = a->KH / s, KB = a->KW / s;                    // taps per class along each axis
     const int mH = (a->H + s - 1) / s, mW = (a->W + s - 1) / s;  // largest class

@@ -70,6 +70,7 @@ struct ClusterRnnParams {
   unsigned int* counters;    // CS (kt_flags: H / 64) counters, CTR_STRIDE apart (zeroed before launch); one arrival per WARP per step
   int S, B, H;
   int relu, reverse, transpose_w;
+  int pair_rows;             // 1: the two column halves of a row are adjacent lanes (full-sector state stores)
   int kt_flags;              // 1: one flag per 64-column k-tile (4 producer CTAs) instead of one per K slice (KS / 16 producer CTAs)
 };
 
@@ -180,8 +181,10 @@ __global__ void __launch_bounds__(NT, 1) rnn_cluster2_kernel(const __grid_consta
   unsigned int generation = 0;
   bool readers_pending = false;      // a cluster barrier phase "strips consumed" has been arrived on but not waited for
   const long long step = (long long)B * H;
-  // epilogue ownership: thread -> row (tid & 127), 8 of the CTA's 16 columns (half = tid >> 7)
-  const int erow = tid & 127, ehalf = tid >> 7;
+  // epilogue ownership: thread -> row tid >> 1, 8 of the CTA's 16 columns (half = tid & 1): the two halves of a row are adjacent
+  // lanes, so the 16-byte bf16 pieces they publish form ONE full 32-byte sector per instruction (with half = tid >> 7 every state
+  // store was a partial-sector write from two different warps)
+  const int erow = p.pair_rows ? tid >> 1 : tid & 127, ehalf = p.pair_rows ? tid & 1 : tid >> 7;
   const bool eactive = erow < B;
   const int ecol = nf + 8 * ehalf;
   // push ownership: TMEM lane = (warp & 3) * 32 + lane, columns (NC/2) * (warp >> 2) .. + NC/2 - 1  -> destination ranks
@@ -494,6 +497,7 @@ int hulc2_rnn_cluster2_launch(const float* add, const float* w, const float* ini
   p.outb = states16 ? reinterpret_cast<__nv_bfloat16*>(states16) : reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + CTR_BYTES);
   p.S = S; p.B = B; p.H = H; p.relu = relu; p.reverse = reverse; p.transpose_w = transpose_w;
   p.kt_flags = rnn_kt_flags() ? 1 : 0;
+  { static int v = -1; if (v < 0) { const char* e = getenv("HULC2_RNN_PAIR_ROWS"); v = (e && e[0] == '0') ? 0 : 1; } p.pair_rows = v; }   // A/B switch
   // bf16 states [S+1, B, H]: one box = 64 k x 128 rows of one slot, 128-byte swizzled = one A k-tile; rows >= B read as zeros
   CUtensorMap tm;
   cuuint64_t dims[3] = {(cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)(S + 1)};

@@ -643,28 +643,42 @@ def pack_conv_weight(w: torch.Tensor, mode: int, stride: int = 1) -> torch.Tenso
     return wp
 
 
-def convb_fwd(x, wp, bias, F, C, H, W, Cout, k, stride, relu=True, name="conv") -> torch.Tensor:
-    """x bf16 NHWC [F,H,W,C] -> bf16 NHWC [F,OH,OW,Cout]."""
+relu_sign_bits = __import__("os").environ.get("HULC2_RELU_BITS", "1") != "0"      # A/B switch
+
+
+def convb_fwd(x, wp, bias, F, C, H, W, Cout, k, stride, relu=True, name="conv", sign_bits=False):
+    """x bf16 NHWC [F,H,W,C] -> bf16 NHWC [F,OH,OW,Cout].  sign_bits: also return (y > 0) packed 1 bit per element (uint8 tensor,
+    NHWC element order) when the kernel that ran can write it, else None -- what the next layer's input gradient masks with."""
     OH, OW = _osz(H, k, stride), _osz(W, k, stride)
     y = _bf16(F, OH, OW, Cout, device=x.device)
     a = _cb(F, C, H, W, Cout, k, stride)
     a.x, a.w, a.bias, a.y, a.relu = x.data_ptr(), wp.data_ptr(), _p(bias), y.data_ptr(), int(relu)
     ws = workspace(x.device)
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()        # scratch for re-tiled weights (conv1 halo path)
+    bits = None
+    if sign_bits and relu and relu_sign_bits:
+        bits = torch.empty(2 * ((y.numel() + 15) // 16), device=x.device, dtype=torch.uint8)
+        a.mask_bits = bits.data_ptr()
     _lib.tag(f"convb_fwd[{name},F={F},{C}x{H}x{W}->{Cout},k{k}s{stride}]", 2.0 * y.numel() * C * k * k,
-             2.0 * (x.numel() + y.numel()))
+             2.0 * (x.numel() + y.numel()) + (bits.numel() if bits is not None else 0))
     call("hulc2_convb_fwd", C_byref(a))
-    return y
+    if not sign_bits:
+        return y
+    return y, (bits if bits is not None and a.mask_bits_written else None)
 
 
-def convb_dgrad(dy, w_oihw, xmask, F, C, H, W, Cout, k, stride, name="conv") -> torch.Tensor:
-    """dy bf16 [F,OH,OW,Cout] -> dx bf16 [F,H,W,C], zeroed where xmask <= 0."""
+def convb_dgrad(dy, w_oihw, xmask, F, C, H, W, Cout, k, stride, name="conv", sign_bits=None) -> torch.Tensor:
+    """dy bf16 [F,OH,OW,Cout] -> dx bf16 [F,H,W,C], zeroed where xmask <= 0 (sign_bits: the same mask, 1 bit per element, from
+    ``convb_fwd(..., sign_bits=True)`` -- read instead of the bf16 activations by the halo kernels)."""
     wp = pack_conv_weight(w_oihw, 2, stride)
     dx = _bf16(F, H, W, C, device=dy.device)
     a = _cb(F, C, H, W, Cout, k, stride)
     a.dy, a.w, a.dx, a.xmask = dy.data_ptr(), wp.data_ptr(), dx.data_ptr(), _p(xmask)
+    a.mask_bits = _p(sign_bits)
+    # algorithmic bytes: with sign bits the mask costs 1/16 of the activation bytes
+    mask_bytes = 0.0 if xmask is None else (dx.numel() / 8.0 if sign_bits is not None else 2.0 * dx.numel())
     _lib.tag(f"convb_dgrad[{name},F={F},{C}x{H}x{W}<-{Cout},k{k}s{stride}]", 2.0 * dy.numel() * C * k * k,
-             2.0 * (dy.numel() + dx.numel() * (2 if xmask is not None else 1)))
+             2.0 * (dy.numel() + dx.numel()) + mask_bytes)
     call("hulc2_convb_dgrad", C_byref(a))
     return dx
 
@@ -776,20 +790,28 @@ def _convb_trunk_fwd(x, w1, b1, w2, b2, w3, b3):
     H4, W4 = H // 4, W // 4
     H1, W1 = H4 - 1, W4 - 1
     H2, W2 = _osz(H1, 4, 2), _osz(W1, 4, 2)
-    y1 = convb_fwd(xs, pack_conv_weight(w1, 1), b1, F_, 16 * Cin, H4, W4, 32, 2, 1, name="c1")
-    y2 = convb_fwd(y1, pack_conv_weight(w2, 0), b2, F_, 32, H1, W1, 64, 4, 2, name="c2")
+    # sign bits for conv2's output only: on conv1 the forward pays more for writing them than conv2's input gradient gains
+    y1, m1 = convb_fwd(xs, pack_conv_weight(w1, 1), b1, F_, 16 * Cin, H4, W4, 32, 2, 1, name="c1"), None
+    y2, m2 = convb_fwd(y1, pack_conv_weight(w2, 0), b2, F_, 32, H1, W1, 64, 4, 2, name="c2", sign_bits=True)
     y3 = convb_fwd(y2, pack_conv_weight(w3, 0), b3, F_, 64, H2, W2, 64, 3, 1, name="c3")
-    return xs, y1, y2, y3
+    return xs, y1, y2, y3, (m1, m2)
 
 
-def _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3, biases=(None, None, None)):
-    """dz3 = bf16 gradient wrt conv3's pre-activation (already ReLU-masked).  Returns the six parameter gradients."""
+def _bits_saved(bits):
+    """(m1, m2) -> tensors for save_for_backward (an empty tensor stands for "no sign bits")."""
+    return tuple(m if m is not None else torch.empty(0, dtype=torch.uint8) for m in bits)
+
+
+def _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3, biases=(None, None, None), bits=(None, None)):
+    """dz3 = bf16 gradient wrt conv3's pre-activation (already ReLU-masked).  Returns the six parameter gradients.
+    bits: ReLU sign bits of (y1, y2) from the forward (convb_fwd(sign_bits=True)); empty / None = mask with the activations."""
+    m1, m2 = (m if m is not None and m.numel() > 0 else None for m in bits)
     F_, H4, W4, C16 = xs.shape
     H1, W1, H2, W2 = y1.shape[1], y1.shape[2], y2.shape[1], y2.shape[2]
     dw3, db3 = convb_wgrad(y2, dz3, F_, 64, H2, W2, 64, 3, 1, tuple(w3.shape), name="c3", param=w3, bias_param=biases[2])
-    dz2 = convb_dgrad(dz3, w3, y2, F_, 64, H2, W2, 64, 3, 1, name="c3")
+    dz2 = convb_dgrad(dz3, w3, y2, F_, 64, H2, W2, 64, 3, 1, name="c3", sign_bits=m2)
     dw2, db2 = convb_wgrad(y1, dz2, F_, 32, H1, W1, 64, 4, 2, tuple(w2.shape), name="c2", param=w2, bias_param=biases[1])
-    dz1 = convb_dgrad(dz2, w2, y1, F_, 32, H1, W1, 64, 4, 2, name="c2")
+    dz1 = convb_dgrad(dz2, w2, y1, F_, 32, H1, W1, 64, 4, 2, name="c2", sign_bits=m1)
     dw1, db1 = convb_wgrad(xs, dz1, F_, C16, H4, W4, 32, 2, 1, tuple(w1.shape), dw_layout=1, name="c1", param=w1, bias_param=biases[0])
     return {"w1": dw1, "b1": db1, "w2": dw2, "b2": db2, "w3": dw3, "b3": db3}
 
@@ -806,7 +828,7 @@ class StaticConvSSM(torch.autograd.Function):
         if not ctx.bf16:
             x = _frames_tensor(x)
         if ctx.bf16:
-            xs, y1, y2, y3 = _convb_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
+            xs, y1, y2, y3, bits = _convb_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
             HW = y3.shape[1] * y3.shape[2]
             _lib.tag(f"spatial_softmax_fwd_bf16[F={F_},HW={HW}]", 0.0, 2.0 * y3.numel() + 4.0 * out.numel())
             # the softmax statistics are kept for the backward when a gradient will be asked for (one pass there instead of three)
@@ -819,7 +841,8 @@ class StaticConvSSM(torch.autograd.Function):
                 call("hulc2_spatial_softmax_fwd_bf16", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
                      out.data_ptr(), F_, HW, 64)
             ctx.has_stats = stats is not None
-            ctx.save_for_backward(xs, y1, y2, y3, w1, w2, w3, x_map, y_map, temperature, *((out, stats) if stats is not None else ()))
+            ctx.save_for_backward(xs, y1, y2, y3, w1, w2, w3, x_map, y_map, temperature, *_bits_saved(bits),
+                                  *((out, stats) if stats is not None else ()))
             return out
         y1, y2, y3 = _conv_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
         HW = y3.shape[1] * y3.shape[2]
@@ -832,7 +855,7 @@ class StaticConvSSM(torch.autograd.Function):
     def backward(ctx, dout):
         dout = dout.contiguous()
         if ctx.bf16:
-            xs, y1, y2, y3, w1, w2, w3, x_map, y_map, temperature, *extra = ctx.saved_tensors
+            xs, y1, y2, y3, w1, w2, w3, x_map, y_map, temperature, m1, m2, *extra = ctx.saved_tensors
             F_ = xs.shape[0]
             HW = y3.shape[1] * y3.shape[2]
             dz3 = torch.empty_like(y3)
@@ -845,7 +868,7 @@ class StaticConvSSM(torch.autograd.Function):
             else:
                 call("hulc2_spatial_softmax_bwd_bf16", y3.data_ptr(), x_map.data_ptr(), y_map.data_ptr(), temperature.data_ptr(),
                      dout.data_ptr(), dz3.data_ptr(), _p(dtemp), F_, HW, 64, 1)
-            g = _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3, ctx.biases)
+            g = _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3, ctx.biases, bits=(m1, m2))
             return (None, g["w1"], g["b1"], g["w2"], g["b2"], g["w3"], g["b3"], None, None, dtemp)
         x, y1, y2, y3, w2, w3, x_map, y_map, temperature, out = ctx.saved_tensors
         F_ = x.shape[0]
@@ -871,11 +894,11 @@ class GripperConvFlatten(torch.autograd.Function):
         if not ctx.bf16:
             x = _frames_tensor(x)
         if ctx.bf16:
-            xs, y1, y2, y3 = _convb_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
+            xs, y1, y2, y3, bits = _convb_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
             HW = y3.shape[1] * y3.shape[2]
             flat = torch.empty(F_, 64 * HW, device=w1.device, dtype=torch.float32)
             call("hulc2_nhwc_bf16_to_nchw", y3.data_ptr(), flat.data_ptr(), F_, HW, 64)
-            ctx.save_for_backward(xs, y1, y2, y3, w1, w2, w3)
+            ctx.save_for_backward(xs, y1, y2, y3, w1, w2, w3, *_bits_saved(bits))
             return flat
         y1, y2, y3 = _conv_trunk_fwd(x, w1, b1, w2, b2, w3, b3)
         HW = y3.shape[1] * y3.shape[2]
@@ -888,12 +911,12 @@ class GripperConvFlatten(torch.autograd.Function):
     def backward(ctx, dflat):
         dflat = dflat.contiguous()
         if ctx.bf16:
-            xs, y1, y2, y3, w1, w2, w3 = ctx.saved_tensors
+            xs, y1, y2, y3, w1, w2, w3, m1, m2 = ctx.saved_tensors
             F_ = xs.shape[0]
             HW = y3.shape[1] * y3.shape[2]
             dz3 = torch.empty_like(y3)
             call("hulc2_nchw_to_nhwc_bf16", dflat.data_ptr(), dz3.data_ptr(), F_, HW, 64, y3.data_ptr())
-            g = _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3, ctx.biases)
+            g = _convb_trunk_bwd(xs, y1, y2, dz3, w1, w2, w3, ctx.biases, bits=(m1, m2))
             return (None, g["w1"], g["b1"], g["w2"], g["b2"], g["w3"], g["b3"])
         x, y1, y2, y3, w2, w3 = ctx.saved_tensors
         F_ = x.shape[0]

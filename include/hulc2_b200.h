@@ -117,6 +117,11 @@ typedef struct {
   const void* dy; void* dx; const void* xmask;
   float* dw; float* db; int dw_layout;
   void* workspace; long long workspace_bytes;
+  /* ReLU sign bits of an activation tensor, 1 bit per element in NHWC element order (bit i of the tensor = bit i % 8 of byte
+   * i / 8; 2-byte aligned, >= ceil(elements / 16) * 2 bytes).  fwd (relu != 0): optional OUTPUT -- the halo kernels also write
+   * (y > 0) here and set mask_bits_written = 1 (the gather kernel leaves it 0).  dgrad: optional INPUT, used INSTEAD of reading the
+   * bf16 activations `xmask` (16x fewer mask bytes; the halo kernels only -- keep passing xmask for the gather kernel). */
+  void* mask_bits; int mask_bits_written;
 } hulc2_convb_args;
 int hulc2_convb_supported(int C, int Cout, int KH, int KW, int stride);
 int hulc2_pack_frames_bf16(const float* x, void* xs, int F, int C, int H, int W, hulc2_stream_t stream);

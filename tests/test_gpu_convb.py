@@ -143,8 +143,15 @@ def test_static_trunk_many_tiles(Fr, H, W):
     ws = [_rand(32, 3, 8, 8, seed=2, scale=0.08), _rand(64, 32, 4, 4, seed=3, scale=0.05), _rand(64, 64, 3, 3, seed=4, scale=0.05)]
     bs = [_rand(32, seed=5, scale=0.1), _rand(64, seed=6, scale=0.1), _rand(64, seed=7, scale=0.1)]
     d = [t.to(DEV) for t in (x, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2])]
-    xs, y1, y2, y3 = ops._convb_trunk_fwd(*d)
+    xs, y1, y2, y3, bits = ops._convb_trunk_fwd(*d)
     torch.cuda.synchronize()
+    # ReLU sign bits written by the forward kernels: bit i of the packed tensor == (element i of the activation > 0)
+    assert bits[0] is None                      # (requested for conv2's output only, see ops._convb_trunk_fwd)
+    for y, m in ((y2, bits[1]),):
+        assert m is not None, "the halo forward kernels write the sign bits"
+        ref_bits = (y.reshape(-1) > 0).cpu()
+        got = ((m.cpu().view(-1, 1) >> torch.arange(8, dtype=torch.uint8)) & 1).bool().reshape(-1)[: ref_bits.numel()]
+        assert torch.equal(got, ref_bits)
     r1 = F.relu(F.conv2d(_bf(x), _bf(ws[0]), bs[0], stride=4))
     assert_close(_nchw(y1.float().cpu()), r1, 1e-2, "y1")
     r2 = F.relu(F.conv2d(_nchw(y1.float().cpu()), _bf(ws[1]), bs[1], stride=2))
@@ -205,3 +212,32 @@ def test_gripper_trunk_bf16_vs_torch():
     assert_close(flat.cpu(), a, 1e-2, "flatten")
     for d, r, nm in zip(dev, ref_p, ("w1", "b1", "w2", "b2", "w3", "b3")):
         assert_close(d.grad.cpu(), r.grad, 2e-2, nm)
+
+
+@pytest.mark.parametrize("Fr,H,W", [(40, 200, 200), (24, 150, 200), (64, 84, 84)])
+def test_trunk_backward_sign_bits_equal_activation_mask(Fr, H, W):
+    """Input gradients masked with the forward's ReLU sign bits (2 bytes per 16 channels) are BIT-IDENTICAL to those masked
+    with the bf16 activations themselves (32 bytes per 16 channels), for both stride classes of the trunk."""
+    from hulc2_b200 import ops
+
+    x = _rand(Fr, 3, H, W, seed=1)
+    ws = [_rand(32, 3, 8, 8, seed=2, scale=0.08), _rand(64, 32, 4, 4, seed=3, scale=0.05), _rand(64, 64, 3, 3, seed=4, scale=0.05)]
+    bs = [_rand(32, seed=5, scale=0.1), _rand(64, seed=6, scale=0.1), _rand(64, seed=7, scale=0.1)]
+    d = [t.to(DEV) for t in (x, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2])]
+    xs, y1, y2, y3, bits = ops._convb_trunk_fwd(*d)
+    assert bits[1] is not None
+    # conv1's bits are not produced by the trunk (not worth it there): ask the kernel for them directly
+    H4, W4 = H // 4, W // 4
+    y1b, m1 = ops.convb_fwd(xs, ops.pack_conv_weight(d[1], 1), d[2], Fr, 48, H4, W4, 32, 2, 1, name="c1", sign_bits=True)
+    assert m1 is not None and torch.equal(y1b.view(torch.int16), y1.view(torch.int16))
+    bits = (m1, bits[1])
+    dz3 = (_rand(*y3.shape, seed=8).to(DEV) * (y3 > 0)).bfloat16()
+    H1, W1, H2, W2 = y1.shape[1], y1.shape[2], y2.shape[1], y2.shape[2]
+    dz2_a = ops.convb_dgrad(dz3, d[5], y2, Fr, 64, H2, W2, 64, 3, 1, name="c3")
+    dz2_b = ops.convb_dgrad(dz3, d[5], y2, Fr, 64, H2, W2, 64, 3, 1, name="c3", sign_bits=bits[1])
+    dz1_a = ops.convb_dgrad(dz2_a, d[3], y1, Fr, 32, H1, W1, 64, 4, 2, name="c2")
+    dz1_b = ops.convb_dgrad(dz2_a, d[3], y1, Fr, 32, H1, W1, 64, 4, 2, name="c2", sign_bits=bits[0])
+    torch.cuda.synchronize()
+    assert torch.equal(dz2_a.view(torch.int16), dz2_b.view(torch.int16))
+    assert torch.equal(dz1_a.view(torch.int16), dz1_b.view(torch.int16))
+    assert float(dz1_a.float().abs().sum()) > 0

@@ -26,9 +26,9 @@ bs = [torch.zeros(32, device=dev), torch.zeros(64, device=dev), torch.zeros(64, 
 for rep in range(a.reps):
     if rep == a.reps - 1:
         _lib.profile_begin()
-    xs, y1, y2, y3 = ops._convb_trunk_fwd(x, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2])
+    xs, y1, y2, y3, bits = ops._convb_trunk_fwd(x, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2])
     dz3 = (torch.randn_like(y3, dtype=torch.float32) * (y3 > 0)).bfloat16()
-    gr = ops._convb_trunk_bwd(xs, y1, y2, dz3, *ws)
+    gr = ops._convb_trunk_bwd(xs, y1, y2, dz3, *ws, bits=bits)
 torch.cuda.synchronize()
 recs = _lib.profile_end()
 tot = 0.0
