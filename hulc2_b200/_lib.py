@@ -151,7 +151,8 @@ _SIGS = {
 }
 _NO_STREAM = {"hulc2_last_error": (C.c_char_p, []), "hulc2_version": (I, []), "hulc2_device_supports_tcgen05": (I, []),
               "hulc2_launch_count": (C.c_ulonglong, []), "hulc2_tma_gemm_count": (C.c_ulonglong, []), "hulc2_convb_supported": (I, [I, I, I, I, I]),
-              "hulc2_rnn_select_kernel": (I, [I]), "hulc2_spatial_softmax_stats_supported": (I, [I, I]), "hulc2_rnn_cluster_capacity": (I, [I]), "hulc2_rnn_device_error": (I, [I]), "hulc2_rnn_last_path": (I, [])}
+              "hulc2_rnn_select_kernel": (I, [I]), "hulc2_spatial_softmax_stats_supported": (I, [I, I]), "hulc2_rnn_cluster_capacity": (I, [I]), "hulc2_rnn_device_error": (I, [I]), "hulc2_rnn_last_path": (I, []),
+              "hulc2_rnn_set_trace": (I, [P])}
 
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + list(_NO_STREAM))
 

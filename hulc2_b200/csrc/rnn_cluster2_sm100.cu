@@ -70,6 +70,7 @@ struct ClusterRnnParams {
   unsigned int* counters;    // CS (kt_flags: H / 64) counters, CTR_STRIDE apart (zeroed before launch); one arrival per WARP per step
   int S, B, H;
   int relu, reverse, transpose_w;
+  unsigned long long* trace; // diagnostic (hulc2_rnn_set_trace): clock64 stamps of CTA 0, 16 slots per step, or null
   int pair_rows;             // 1: the two column halves of a row are adjacent lanes (full-sector state stores)
   int kt_flags;              // 1: one flag per 64-column k-tile (4 producer CTAs) instead of one per K slice (KS / 16 producer CTAs)
 };
@@ -110,6 +111,9 @@ __device__ __forceinline__ void wait_pending(int n) {   // cp.async.wait_group n
 // step protocol is still matched, so the kernel terminates with wrong numbers instead of trapping the context; the host
 // reads the flag through hulc2_rnn_device_error().
 __device__ unsigned int g_cluster2_rnn_error = 0;
+
+static unsigned long long* g_trace = nullptr;
+#define RNN_STAMP(slot) do { if (p.trace && blockIdx.x == 0) p.trace[it * 16 + (slot)] = clock64(); } while (0)
 
 template <int CS>
 __global__ void __launch_bounds__(NT, 1) rnn_cluster2_kernel(const __grid_constant__ CUtensorMap tm_state, const ClusterRnnParams p) {
@@ -206,6 +210,7 @@ __global__ void __launch_bounds__(NT, 1) rnn_cluster2_kernel(const __grid_consta
     // slot of the operand state: slot 0 = initial state, slot t + 1 = state t; the final pass reads dz[0] = slot 1
     const int slot_prev = final_pass ? 1 : (it > 0 ? tprev + 1 : 0);
 
+    if (tid == 0) RNN_STAMP(0);
     // prefetch the epilogue addend / mask for this thread's 8 outputs (overlaps the flag wait and the k loop)
     float addv[8], mk[8];
 #pragma unroll
@@ -245,6 +250,8 @@ __global__ void __launch_bounds__(NT, 1) rnn_cluster2_kernel(const __grid_consta
               } while (v < target);
               asm volatile("fence.proxy.async.global;" ::: "memory");
             }
+            if (lane == 0) RNN_STAMP(1);
+            if (lane == nkt - 1) RNN_STAMP(2);
             const uint32_t bar = smem_u32(&full_bar[lane]);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(A_TILE) : "memory");
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -281,42 +288,73 @@ __global__ void __launch_bounds__(NT, 1) rnn_cluster2_kernel(const __grid_consta
           const uint32_t acc_t = tmem_d + (uint32_t)((warp - 1) * NC);
           for (int kt = kt_lo; kt < kt_hi; ++kt) {
             mbar_wait(smem_u32(&full_bar[kt]), par);
+            if (kt == 0) RNN_STAMP(3);
+            if (kt == nkt - 1) RNN_STAMP(4);
             tc_fence_after();
             const uint64_t ad = make_desc(a_smem + kt * A_TILE, 0), bd = make_desc(w_smem + kt * W_TILE, 0);
 #pragma unroll
             for (int k = 0; k < KT / 16; ++k) umma_bf16(acc_t, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), IDESC, (kt > kt_lo || k > 0) ? 1u : 0u);
           }
           umma_commit(smem_u32(&mma_done));
+          if (warp == issuers) RNN_STAMP(5);
         }
         __syncwarp();
       }
       mbar_wait(smem_u32(&mma_done), par);
+      if (tid == 0) RNN_STAMP(6);
       mma_uses += 1;
       tc_fence_after();
 
-      // push: this CTA's partial strip for destination rank d -> d's RED[rank][q][row][4]
-      uint32_t r[DPT][16];
+      // push: this CTA's partial strip for destination rank d -> d's RED[rank][q][row][4].  The accumulators of all issuers are
+      // read behind ONE tcgen05.wait::ld (they used to be read and added issuer by issuer: three more TMEM round trips per step)
+      constexpr bool ONE_WAIT = MAXI * DPT * 16 <= 128;        // registers: clusters of 4 (the B200 configuration) yes, of 8 no
+      constexpr int NA = ONE_WAIT ? MAXI : 1;
+      uint32_t ra[NA][DPT][16];
+      uint32_t (&r)[DPT][16] = ra[0];
+      if (ONE_WAIT) {
 #pragma unroll
-      for (int j = 0; j < DPT; ++j) tmem_ld16_nowait(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((phalf * DPT + j) * NR), r[j]);
-      tmem_ld_wait();
-      for (int a = 1; a < issuers; ++a) {            // add the other issuers' partial accumulators
-        uint32_t r2[DPT][16];
+        for (int a = 0; a < NA; ++a)
+          if (a < issuers) {
 #pragma unroll
-        for (int j = 0; j < DPT; ++j) tmem_ld16_nowait(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * NC + (phalf * DPT + j) * NR), r2[j]);
+            for (int j = 0; j < DPT; ++j) tmem_ld16_nowait(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * NC + (phalf * DPT + j) * NR), ra[a][j]);
+          }
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < DPT; ++j)
+        for (int a = 1; a < NA; ++a)
+          if (a < issuers) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) r[j][e] = __float_as_uint(__uint_as_float(r[j][e]) + __uint_as_float(r2[j][e]));
+            for (int j = 0; j < DPT; ++j)
+#pragma unroll
+              for (int e = 0; e < 16; ++e) r[j][e] = __float_as_uint(__uint_as_float(r[j][e]) + __uint_as_float(ra[a][j][e]));
+          }
+      } else {
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) tmem_ld16_nowait(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((phalf * DPT + j) * NR), r[j]);
+        tmem_ld_wait();
+        for (int a = 1; a < issuers; ++a) {            // add the other issuers' partial accumulators
+          uint32_t r2[DPT][16];
+#pragma unroll
+          for (int j = 0; j < DPT; ++j) tmem_ld16_nowait(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * NC + (phalf * DPT + j) * NR), r2[j]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < DPT; ++j)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[j][e] = __float_as_uint(__uint_as_float(r[j][e]) + __uint_as_float(r2[j][e]));
+        }
       }
       tc_fence_before();
+      if (tid == 0) RNN_STAMP(7);
       if (readers_pending) cluster_wait();      // every CTA of the cluster has consumed the strips of the previous step
+      if (tid == 0) RNN_STAMP(11);
 #pragma unroll
       for (int j = 0; j < DPT; ++j)
 #pragma unroll
         for (int q = 0; q < 4; ++q) st_cluster_v4(remote[j] + q * (BM * 16), r[j][4 * q], r[j][4 * q + 1], r[j][4 * q + 2], r[j][4 * q + 3]);
+      if (tid == 0) RNN_STAMP(12);
       cluster_arrive();
+      if (tid == 0) RNN_STAMP(13);
       cluster_wait();
+      if (tid == 0) RNN_STAMP(8);
       // local reduce of the CS strips
 #pragma unroll
       for (int src = 0; src < CS; ++src) {
@@ -326,7 +364,9 @@ __global__ void __launch_bounds__(NT, 1) rnn_cluster2_kernel(const __grid_consta
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w) : "r"(a + BM * 16) : "memory");
         acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w; acc[4] += y.x; acc[5] += y.y; acc[6] += y.z; acc[7] += y.w;
       }
+      if (tid == 0) RNN_STAMP(14);
       cluster_arrive();                          // strips consumed (waited for before the next push)
+      if (tid == 0) RNN_STAMP(15);
       readers_pending = true;
     }
 
@@ -352,9 +392,11 @@ __global__ void __launch_bounds__(NT, 1) rnn_cluster2_kernel(const __grid_consta
         b4[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
       }
       generation += 1;
+      if (tid == 0) RNN_STAMP(9);
       __syncwarp();
       if (lane == 0)   // release: this warp's share of the CTA's 16 columns of K slice nf / KS is visible before the count moves
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters + (p.kt_flags ? nf / KT : nf / KS) * CTR_STRIDE) : "memory");
+      if (tid == 0) RNN_STAMP(10);
       if (eactive) {
         float4* o4 = reinterpret_cast<float4*>(p.out + (long long)t * step + (long long)erow * H + ecol);
         o4[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -460,6 +502,9 @@ static EncodeTiledFn encode_fn() {
 
 }  // namespace
 
+// diagnostic hook (tools/trace_rnn.py): device buffer of (S + 1) * 16 u64 that receives clock64 stamps of CTA 0, or null
+extern "C" int hulc2_rnn_set_trace(void* buf) { g_trace = reinterpret_cast<unsigned long long*>(buf); return HULC2_OK; }
+
 int hulc2_rnn_cluster2_device_error(int clear) {
   unsigned int v = 0;
   if (cudaMemcpyFromSymbol(&v, g_cluster2_rnn_error, sizeof(v)) != cudaSuccess) { cudaGetLastError(); return -1; }
@@ -497,6 +542,7 @@ int hulc2_rnn_cluster2_launch(const float* add, const float* w, const float* ini
   p.outb = states16 ? reinterpret_cast<__nv_bfloat16*>(states16) : reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + CTR_BYTES);
   p.S = S; p.B = B; p.H = H; p.relu = relu; p.reverse = reverse; p.transpose_w = transpose_w;
   p.kt_flags = rnn_kt_flags() ? 1 : 0;
+  p.trace = g_trace;
   { static int v = -1; if (v < 0) { const char* e = getenv("HULC2_RNN_PAIR_ROWS"); v = (e && e[0] == '0') ? 0 : 1; } p.pair_rows = v; }   // A/B switch
   // bf16 states [S+1, B, H]: one box = 64 k x 128 rows of one slot, 128-byte swizzled = one A k-tile; rows >= B read as zeros
   CUtensorMap tm;

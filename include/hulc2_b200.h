@@ -351,6 +351,10 @@ int hulc2_rnn_device_error(int clear);
  * step) and, in bits 8-15, why (a') last declined (0 = it ran; 1 shape, 2 workspace, 3 alignment, 4 no driver entry point,
  * 5 clusters not co-resident, 6 tensor map, 7 launch refused).  Tests use it to make sure no silent fallback is being measured. */
 int hulc2_rnn_last_path(void);
+/* Diagnostic: device buffer of (S+1)*16 u64 that receives clock64 stamps of CTA 0 of kernel (a') at its phase boundaries
+ * (slot = 16*step + phase: 0 step start, 1 flag seen, 2 last box issued, 3 / 4 first / last box landed, 5 last MMA committed,
+ * 6 accumulator complete, 7 TMEM read, 8 strips exchanged, 9 state stored, 10 flag released); null switches it off. */
+int hulc2_rnn_set_trace(void* device_buffer);
 
 /* ------------------------------------------------------------------ gated recurrence cells (decoders/utils/rnn.py:17-36)
  * One step of nn.GRU (gate order r,z,n) / nn.LSTM (i,f,g,o); the contractions are hulc2_gemm calls, these are the
