@@ -217,6 +217,8 @@ def emit_mirrors() -> bool:
 
 
 def register_mirror(src: torch.Tensor, m16: torch.Tensor, ld: int, rows: int, cols: int) -> None:
+    if len(_act16) >= 512:          # a caller that never reaches a step boundary (a long no-grad loop) must not pin memory
+        _act16.clear()
     _act16[src.data_ptr()] = (src, src._version, m16, int(ld), int(rows), int(cols))
 
 

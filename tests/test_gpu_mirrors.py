@@ -177,3 +177,9 @@ def test_mirror_registry_guards_cpu():
     ops.register_mirror(src, m16, 8, 6, 8)
     ops.invalidate_weight_mirrors()
     assert ops._find_mirror(src) is None
+    # a loop that never reaches a step boundary cannot pin more than 512 tensors
+    keep = [torch.zeros(2, 8) for _ in range(600)]
+    for t in keep:
+        ops.register_mirror(t, m16, 8, 2, 8)
+    assert len(ops._act16) <= 512
+    ops.clear_mirrors()
