@@ -502,7 +502,7 @@ def run_b200(args):
     e2e_val = 2 * B * world / (float(e2e_ms) * 1e-3)
     e2e_store = None
     if args.variant == "calvin" and args.frames == "uint8" and not args.no_store_e2e:
-        e2e_store = measure_e2e_store(args, dev, world, rank, hw, barrier, max(e2e_steps, 20))
+        e2e_store = measure_e2e_store(args, dev, world, rank, hw, barrier, max(e2e_steps, 50))     # (pipeline fill / drain amortised over >= 50 steps)
     # the same without the software pipeline: one blocking call per step (copy, then step, then read)
     t0 = time.perf_counter()
     for i in range(2):

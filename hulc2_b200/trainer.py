@@ -272,10 +272,11 @@ class PolicyTrainer:
         if getattr(self, "_staging", None) is None or not _same_shapes(self._staging[0], first):
             self._staging = [tree_map(lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev), first) for _ in range(2)]
             self._pipe_static = tree_map(lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev), first)
-        ready = [torch.cuda.Event() for _ in range(2)]
-        free = [torch.cuda.Event() for _ in range(2)]
-        loss_slots = torch.empty(2, dtype=torch.float32).pin_memory()
-        loss_done = [torch.cuda.Event() for _ in range(2)]
+        if getattr(self, "_pipe_sync", None) is None:
+            # events and the pinned loss slots are made once per trainer: cudaHostAlloc costs milliseconds, a whole step's worth
+            self._pipe_sync = ([torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)],
+                               torch.empty(2, dtype=torch.float32).pin_memory(), [torch.cuda.Event() for _ in range(2)])
+        ready, free, loss_slots, loss_done = self._pipe_sync
         losses: List[float] = []
 
         def upload(i, hb):
