@@ -13,6 +13,7 @@ Layout notes
 from __future__ import annotations
 
 import ctypes as C
+import os
 from ctypes import byref as C_byref
 from typing import List, Optional, Sequence, Tuple
 
@@ -209,7 +210,7 @@ def _pad8(n: int) -> int:
 # (autograd accumulating into a gradient buffer).  Cleared at every step boundary (zero_grad, optimizer.step, start of a
 # training / validation / rollout step).  A consumer that finds no entry converts as before.
 _act16: dict = {}
-producer_mirrors = __import__("os").environ.get("HULC2_PRODUCER_MIRRORS", "1") != "0"     # A/B switch
+producer_mirrors = os.environ.get("HULC2_PRODUCER_MIRRORS", "1") != "0"     # A/B switch
 
 
 def emit_mirrors() -> bool:
@@ -645,7 +646,7 @@ def pack_conv_weight(w: torch.Tensor, mode: int, stride: int = 1) -> torch.Tenso
     return wp
 
 
-relu_sign_bits = __import__("os").environ.get("HULC2_RELU_BITS", "1") != "0"      # A/B switch
+relu_sign_bits = os.environ.get("HULC2_RELU_BITS", "1") != "0"      # A/B switch
 
 
 def convb_fwd(x, wp, bias, F, C, H, W, Cout, k, stride, relu=True, name="conv", sign_bits=False):
