@@ -183,11 +183,12 @@ def test_mirror_registry_guards_cpu():
         ops.register_mirror(t, m16, 8, 2, 8)
     assert len(ops._act16) <= 512
     ops.clear_mirrors()
-    # mirror_like: the registered mirror comes back with the shape of the fp32 tensor (the decoder heads' [S,B,H] operand)
+    # the consumer-facing lookups refuse CPU tensors like every other op (no CPU fallback), registry hit or not
     h = torch.zeros(3, 2, 8)
-    h16 = torch.ones(3, 2, 8, dtype=torch.bfloat16)
-    ops.register_mirror(h, h16, 8, 6, 8)
-    got = ops.mirror_like(h)
-    assert got.shape == h.shape and got.data_ptr() == h16.data_ptr()
+    ops.register_mirror(h, torch.ones(3, 2, 8, dtype=torch.bfloat16), 8, 6, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.mirror_like(h)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.mirror2d(h.view(6, 8))
     ops.clear_mirrors()
     assert ops._bits_saved((None, h))[0].numel() == 0 and ops._bits_saved((None, h))[1] is h
